@@ -1,0 +1,286 @@
+/* ORACLE — TEST INFRASTRUCTURE ONLY. Never imported, linked or called by the
+ * product path (cassiopee_b200/). Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may use it, as the checker.
+ *
+ * Thin extern "C" driver around the reference's OWN compiled C++:
+ * oracle/Makefile compiles KCore/KCore/Interp/*.cpp, Metric/compVolOfStructCell.cpp,
+ * CompGeom/compGeom.cpp and Def/DefCplusPlusConst.cpp unchanged from
+ * /root/reference into oracle/_ref/libcassref.so together with this file.
+ * Nothing of the algorithm lives here: this file only
+ *   (1) loops over receptors exactly like
+ *       Connector/Connector/setInterpData.cpp:978-1114 (getInterpolationCell,
+ *       then getExtrapolationCell when allowed) and returns the per-receptor
+ *       result instead of per-thread chunk buffers (the chunk concatenation at
+ *       :1183-1252 yields ascending receptor order per donor zone, which the
+ *       Python side re-creates with a stable selection);
+ *   (2) runs the reference transfer loops by #including the reference's own
+ *       fragment headers commonInterpTransfers_{indirect,direct}.h /
+ *       commonInterpTransfers.h / commonCellNTransfersStrict.h with the local
+ *       variable names those fragments expect
+ *       (Connector/Connector/setInterpTransfers.cpp:285-467,
+ *        setInterpTransfersD.cpp:106-303);
+ *   (3) exposes the ADT candidate list for debugging the device ADT replica.
+ * It bypasses the CPython/numpy marshalling of KCore (not buildable here
+ * without scons+gfortran).
+ */
+#include <vector>
+#include <list>
+#include <algorithm>
+#include <cstring>
+#include <omp.h>
+#include "Interp/Interp.h"
+#include "Metric/metric.h"
+#include "CompGeom/compGeom.h"
+#include "parallel.h"
+
+using namespace std;
+using namespace K_FLD;
+
+/* SIZECF: Connector/Connector/connector.h:27-37 (pulled by macro re-statement
+ * because connector.h drags the whole Connector module in). */
+#define SIZECF(type, meshtype, sizecf)                     \
+  {                                                        \
+    if (type == 1) sizecf = 1;                             \
+    else if (type == 2 && meshtype == 1) sizecf = 8;       \
+    else if (type == 3 && meshtype == 1) sizecf = 9;       \
+    else if (type == 44 && meshtype == 1) sizecf = 12;     \
+    else if (type == 4 && meshtype == 1) sizecf = 8;       \
+    else if (type == 4 && meshtype == 2) sizecf = 4;       \
+    else if (type == 5 && meshtype == 1) sizecf = 15;      \
+    else if (type == 22 && meshtype == 1) sizecf = 4;      \
+    else sizecf = -1;                                      \
+  }
+
+struct RefZone
+{
+  E_Int ni, nj, nk;
+  FldArrayF* f;  // (npts, 4): x, y, z, cellN
+  K_INTERP::InterpAdt* adt;
+};
+
+extern "C" {
+
+int ref_num_threads() { return omp_get_max_threads(); }
+void ref_set_num_threads(int n) { omp_set_num_threads(n); }
+
+/* Donor zone = coordinates + cellN + ADT (setInterpData.cpp:772-787). */
+void* ref_zone_create(int ni, int nj, int nk, const double* x, const double* y,
+                      const double* z, const double* cellN, int buildAdt)
+{
+  RefZone* zn = new RefZone;
+  zn->ni = ni; zn->nj = nj; zn->nk = nk;
+  E_Int npts = ni * nj * nk;
+  zn->f = new FldArrayF(npts, 4);
+  memcpy(zn->f->begin(1), x, sizeof(double) * npts);
+  memcpy(zn->f->begin(2), y, sizeof(double) * npts);
+  memcpy(zn->f->begin(3), z, sizeof(double) * npts);
+  if (cellN) memcpy(zn->f->begin(4), cellN, sizeof(double) * npts);
+  else for (E_Int i = 0; i < npts; i++) (*zn->f)(i, 4) = 1.;
+  zn->adt = NULL;
+  if (buildAdt)
+  {
+    E_Int built = 0;
+    zn->adt = new K_INTERP::InterpAdt(npts, zn->f->begin(1), zn->f->begin(2),
+                                      zn->f->begin(3), &zn->ni, &zn->nj,
+                                      &zn->nk, built);
+    if (built != 1) { delete zn->adt; zn->adt = NULL; }
+  }
+  return zn;
+}
+
+int ref_zone_has_adt(void* h) { return ((RefZone*)h)->adt != NULL; }
+
+void ref_zone_free(void* h)
+{
+  RefZone* zn = (RefZone*)h;
+  if (zn->adt) delete zn->adt;
+  delete zn->f;
+  delete zn;
+}
+
+void ref_zone_bbox(void* h, double* bb)
+{
+  K_INTERP::InterpAdt* a = ((RefZone*)h)->adt;
+  bb[0] = a->_xmin; bb[1] = a->_ymin; bb[2] = a->_zmin;
+  bb[3] = a->_xmax; bb[4] = a->_ymax; bb[5] = a->_zmax;
+}
+
+/* InterpAdt::getListOfCandidateCells (InterpAdt.cpp:658-929). */
+int ref_candidates(void* h, double x, double y, double z, double alphaTol,
+                   int* out, int cap)
+{
+  list<E_Int> l;
+  ((RefZone*)h)->adt->getListOfCandidateCells(x, y, z, l, alphaTol);
+  int n = 0;
+  for (list<E_Int>::iterator it = l.begin(); it != l.end(); ++it, ++n)
+    if (n < cap) out[n] = *it;
+  return n;
+}
+
+/* Per-receptor loop of K_CONNECTOR::setInterpData (setInterpData.cpp:978-1114).
+ * Outputs, one entry per receptor:
+ *   noblk[n]   0 = orphan, else 1-based donor zone
+ *   type[n]    InterpolantsType (1,2,3,5,22,44)
+ *   dind[n]    donor index
+ *   isext[n]   1 when produced by getExtrapolationCell
+ *   cf[n*16+k] coefficients (ncfmax<=15 used)
+ *   vol[n]     selection volume
+ */
+int ref_set_interp_data(int nrcv, const double* xr, const double* yr,
+                        const double* zr, int nz, void** zones, int order,
+                        int nature, int penalty, int extrap, int* noblk_o,
+                        int* type_o, int* dind_o, int* isext_o, double* cf_o,
+                        double* vol_o)
+{
+  K_INTERP::InterpData::InterpolationType interpType;
+  E_Int nindi = 1, ncfmax;
+  switch (order)  // setInterpData.cpp:624-652
+  {
+    case 2: interpType = K_INTERP::InterpData::O2CF; ncfmax = 8; break;
+    case 3: interpType = K_INTERP::InterpData::O3ABC; ncfmax = 9; break;
+    case 4: interpType = K_INTERP::InterpData::O4ABC; ncfmax = 12; break;
+    case 5: interpType = K_INTERP::InterpData::O5ABC; ncfmax = 15; break;
+    default: interpType = K_INTERP::InterpData::O2CF; ncfmax = 8; break;
+  }
+  vector<K_INTERP::InterpData*> interpDatas;
+  vector<FldArrayF*> fields;
+  vector<void*> a2, a3, a4, a5;
+  vector<E_Int> posxs, posys, poszs, poscs;
+  for (int i = 0; i < nz; i++)
+  {
+    RefZone* zn = (RefZone*)zones[i];
+    if (!zn->adt) return -1;
+    interpDatas.push_back(zn->adt);
+    fields.push_back(zn->f);
+    a2.push_back(&zn->ni); a3.push_back(&zn->nj); a4.push_back(&zn->nk);
+    a5.push_back(NULL);
+    posxs.push_back(1); posys.push_back(2); poszs.push_back(3); poscs.push_back(4);
+  }
+  E_Int nbI = nrcv;
+#pragma omp parallel
+  {
+    FldArrayI indi(nindi); FldArrayF cf(ncfmax);
+    FldArrayI tmpIndi(nindi); FldArrayF tmpCf(ncfmax);
+    E_Float x, y, z, vol;
+    E_Int noblk = 0;
+    short ok;
+    E_Int type, isExtrapolated;
+#pragma omp for
+    for (E_Int ind = 0; ind < nbI; ind++)
+    {
+      x = xr[ind]; y = yr[ind]; z = zr[ind];
+      type = 0;
+      ok = K_INTERP::getInterpolationCell(
+        x, y, z, interpDatas, fields, a2, a3, a4, a5, posxs, posys, poszs,
+        poscs, vol, indi, cf, tmpIndi, tmpCf, type, noblk, interpType, nature,
+        penalty);
+      isExtrapolated = 0;
+      if (ok != 1 && extrap == 1)
+      {
+        ok = K_INTERP::getExtrapolationCell(
+          x, y, z, interpDatas, fields, a2, a3, a4, a5, posxs, posys, poszs,
+          poscs, vol, indi, cf, type, noblk, interpType, nature, penalty);
+        if (noblk > 0) isExtrapolated = 1;
+      }
+      noblk_o[ind] = noblk;
+      isext_o[ind] = isExtrapolated;
+      vol_o[ind] = vol;
+      for (int k = 0; k < 16; k++) cf_o[(size_t)ind * 16 + k] = 0.;
+      if (noblk > 0)
+      {
+        type_o[ind] = type;
+        dind_o[ind] = indi[0];
+        E_Int ncf = cf.getSize() < ncfmax ? cf.getSize() : ncfmax;
+        for (E_Int k = 0; k < ncf; k++) cf_o[(size_t)ind * 16 + k] = cf[k];
+      }
+      else { type_o[ind] = 0; dind_o[ind] = -1; }
+    }
+  }
+  return 0;
+}
+
+/* _setInterpTransfers general path (setInterpTransfers.cpp:436-449) on raw
+ * pointers: fieldR[v][rcvPts[n]] = sum cf*fieldD[v][stencil]. */
+void ref_transfer(int nvars_, double** dnrFields, double** rcvFields, int imd_,
+                  int jmd_, int nrcv, const int* rcvPts_, const int* donorPts_,
+                  const int* types_, const double* coefs, int ncoefs)
+{
+  E_Int imd = imd_, jmd = jmd_, imdjmd, nvars = nvars_, meshtype = 1;
+  E_Int nbRcvPts = nrcv;
+  E_Int* rcvPts = (E_Int*)rcvPts_;
+  E_Int* donorPts = (E_Int*)donorPts_;
+  E_Int* types = (E_Int*)types_;
+  E_Int* ptrcnd = NULL; E_Int cnNfldD = 0;
+  FldArrayF donorCoefs(ncoefs > 0 ? ncoefs : 1);
+  if (ncoefs > 0) memcpy(donorCoefs.begin(), coefs, sizeof(double) * ncoefs);
+  FldArrayF* donorCoefsF = &donorCoefs;
+  vector<E_Float*> vectOfRcvFields(nvars), vectOfDnrFields(nvars);
+  for (E_Int eq = 0; eq < nvars; eq++)
+  {
+    vectOfRcvFields[eq] = rcvFields[eq];
+    vectOfDnrFields[eq] = dnrFields[eq];
+  }
+  (void)ptrcnd; (void)cnNfldD;
+# include "commonInterpTransfers_indirect.h"
+}
+
+/* _setInterpTransfersD (setInterpTransfersD.cpp:106-303): dense (nvars,nrcv)
+ * output, indR = noind. */
+void ref_transferD(int nvars_, double** dnrFields, double* out, int imd_,
+                   int jmd_, int nrcv, const int* donorPts_, const int* types_,
+                   const double* coefs, int ncoefs)
+{
+  E_Int imd = imd_, jmd = jmd_, imdjmd, nvars = nvars_, meshtype = 1;
+  E_Int nbRcvPts = nrcv;
+  E_Int* donorPts = (E_Int*)donorPts_;
+  E_Int* types = (E_Int*)types_;
+  E_Int* ptrcnd = NULL; E_Int cnNfldD = 0;
+  FldArrayF donorCoefs(ncoefs > 0 ? ncoefs : 1);
+  if (ncoefs > 0) memcpy(donorCoefs.begin(), coefs, sizeof(double) * ncoefs);
+  FldArrayF* donorCoefsF = &donorCoefs;
+  vector<E_Float*> vectOfRcvFields(nvars), vectOfDnrFields(nvars);
+  for (E_Int eq = 0; eq < nvars; eq++)
+  {
+    vectOfRcvFields[eq] = out + (size_t)eq * nrcv;
+    vectOfDnrFields[eq] = dnrFields[eq];
+  }
+  (void)ptrcnd; (void)cnNfldD;
+# include "commonInterpTransfers_direct.h"
+}
+
+/* Strict cellN transfer (setInterpTransfers.cpp:452-467). */
+void ref_transfer_celln(double* cellND, double* cellNR, int imd_, int jmd_,
+                        int nrcv, const int* rcvPts_, const int* donorPts_,
+                        const int* types_, const double* coefs)
+{
+  E_Int imd = imd_, jmd = jmd_, imdjmd = imd * jmd, meshtype = 1;
+  E_Int nbRcvPts = nrcv;
+  E_Int* rcvPts = (E_Int*)rcvPts_;
+  E_Int* donorPts = (E_Int*)donorPts_;
+  E_Int* types = (E_Int*)types_;
+  E_Int* ptrcnd = NULL; E_Int cnNfldD = 0;
+  E_Int indR, type, nocf;
+  E_Int indD0, indD, ncfLoc;
+  E_Int noi = 0;
+  E_Int sizecoefs = 0;
+  E_Float* ptrCoefs = (E_Float*)coefs;
+  (void)ptrcnd; (void)cnNfldD; (void)ncfLoc;
+  for (E_Int noind = 0; noind < nbRcvPts; noind++)
+  {
+    indR = rcvPts[noind];
+# include "commonCellNTransfersStrict.h"
+  }
+}
+
+/* K_METRIC::compVolOfStructCell3D (selection volume, for unit checks). */
+double ref_cell_volume(void* h, int indnode)
+{
+  RefZone* zn = (RefZone*)h;
+  E_Float vol;
+  K_METRIC::compVolOfStructCell3D(zn->ni, zn->nj, zn->nk, -1, indnode,
+                                  zn->f->begin(1), zn->f->begin(2),
+                                  zn->f->begin(3), vol);
+  return vol;
+}
+
+}  // extern "C"
