@@ -1,0 +1,106 @@
+"""Array-level Connector API on the device (mirror of
+/root/reference/Cassiopee/Connector/Connector/Connector.py:425-446, :600-606).
+
+A Converter "array" is ``[varString, ndarray(nfld, npts) float64 C-order, ni, nj, nk]``
+(structured) — the object the reference's C entry points receive
+(SURVEY.md 8(b)/(c)).
+"""
+import numpy
+from .. import _lib
+
+
+def _pos(varString, names):
+    v = varString.split(',')
+    for n in names:
+        if n in v:
+            return v.index(n)
+    return -1
+
+
+def _posxyz(varString):
+    px = _pos(varString, ['x', 'CoordinateX'])
+    py = _pos(varString, ['y', 'CoordinateY'])
+    pz = _pos(varString, ['z', 'CoordinateZ'])
+    return px, py, pz
+
+
+def _poscelln(varString):
+    return _pos(varString, ['cellN', 'cellnf', 'cellNF'])
+
+
+def getInterpolatedPoints__(a):
+    """connector.getInterpolatedPoints (getInterpolatedPoints.cpp:1675-1732):
+    keep points with |cellN-2| <= 1e-15, in source order, append 'indcell' (the
+    original index, stored as a double like the reference does)."""
+    if isinstance(a[0], list):
+        return [getInterpolatedPoints__(i) for i in a]
+    posc = _poscelln(a[0])
+    if posc == -1:
+        raise TypeError("getInterpolatedPoints: array must contain cellN.")
+    f = a[1]
+    t = f[posc, :] - 2.
+    sel = numpy.nonzero((t >= -1.e-15) & (t <= 1.e-15))[0]
+    out = numpy.empty((f.shape[0] + 1, sel.size), dtype=numpy.float64)
+    out[:-1, :] = f[:, sel]
+    out[-1, :] = sel
+    return [a[0] + ',indcell', out, sel.size, 1, 1]
+
+
+def createHooks__(zonesD, ctx=None):
+    """One device ADT per donor array (analogue of [C.createHook(z,'adt') ...])."""
+    ctx = ctx or _lib.default_context()
+    hooks = []
+    for a in zonesD:
+        px, py, pz = _posxyz(a[0])
+        pc = _poscelln(a[0])
+        if px == -1 or py == -1 or pz == -1:
+            raise TypeError("setInterpData: 2nd argument is not valid.")
+        f = a[1]
+        hooks.append(_lib.Zone(ctx, a[2], a[3], a[4], numpy.ascontiguousarray(f[px]), numpy.ascontiguousarray(f[py]),
+                               numpy.ascontiguousarray(f[pz]),
+                               numpy.ascontiguousarray(f[pc]) if pc != -1 else None))
+    return hooks
+
+
+def setInterpData__(interpPts, zonesD, order=2, penalty=1, extrap=1, nature=0, method='lagrangian',
+                    interpDataType=1, hook=None, dim=3, ctx=None):
+    """connector.setInterpData on the device.  Returns the reference's list
+    [rcvInd1D]*nz, [donorInd1D]*nz, [donorType]*nz, [coefs]*nz, [extrap]*nz, orphan, [EXdir]
+    (Connector.py:415-439, setInterpData.cpp:1272) or None without receptors.
+    hook: None (device ADTs are built for this call) or a list of device
+    zones from createHooks__, one per donor, same order."""
+    if method != 'lagrangian':
+        if method == 'leastsquares':
+            raise NotImplementedError("setInterpData: method='leastsquares' has no device path.")
+        raise ValueError("setInterpData__: %s: not a valid interpolation method." % method)
+    if isinstance(interpPts[0], list):
+        raise NotImplementedError("setInterpData: double-wall receptor lists have no device path.")
+    if interpPts[1].shape[1] == 0:
+        return None
+    types = interpDataType if isinstance(interpDataType, list) else [interpDataType] * len(zonesD)
+    for t in types:
+        if t not in (0, 1):
+            raise TypeError("setInterpData: InterpDataType must be 0 for CART or 1 for ADT.")
+        if t == 0:
+            raise NotImplementedError("setInterpData: interpDataType=0 (InterpCart) has no device path.")
+    if len(zonesD) == 0:
+        raise TypeError("setInterpData: no valid donor zone found.")
+    ctx = ctx or _lib.default_context()
+    px, py, pz = _posxyz(interpPts[0])
+    if px == -1 or py == -1 or pz == -1:
+        raise TypeError("setInterpData: 1st arg must contain coordinates.")
+    if hook is None:
+        zones = createHooks__(zonesD, ctx)
+    else:
+        if not isinstance(hook, list):
+            raise TypeError("setInterpData: hook must be a list of hooks.")
+        if len(hook) != len(zonesD):
+            raise TypeError("setInterpData: size of list of hooks must be equal to the number of donor zones.")
+        zones = hook
+    f = interpPts[1]
+    res = _lib.set_interp_data(ctx, numpy.ascontiguousarray(f[px]), numpy.ascontiguousarray(f[py]),
+                               numpy.ascontiguousarray(f[pz]), zones, order=order, nature=nature, penalty=penalty,
+                               extrap=extrap)
+    out = res.fetch()
+    out.append(res.stats())   # extra 8th entry: device statistics (ignored by callers of the 7-list)
+    return out

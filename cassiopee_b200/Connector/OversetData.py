@@ -1,0 +1,511 @@
+"""Connector.PyTree chimera path on the device: setInterpData / setInterpTransfers.
+
+Host-side mirror (same names, arguments, storage layout, error behaviour) of
+/root/reference/Cassiopee/Connector/Connector/OversetData.py:
+  setInterpData :1133, _setInterpData :1147, _setInterpDataChimera :1174,
+  _createInterpRegion__ :1752, setInterpTransfers :1924, _setInterpTransfers :1962,
+  setInterpTransfersD :2167, _setInterpTransfersD :2179, _adaptForRANSLES__ :1702.
+The C entry points the reference calls (connector.setInterpData,
+connector._setInterpTransfers, connector._setInterpTransfersD,
+connector.getInterpolatedPoints) are replaced by the CUDA library through
+cassiopee_b200._lib (include/cassiopee_b200.h).  Everything that is not the
+structured-donor 'lagrangian' chimera path raises NotImplementedError — there
+is no CPU fallback.
+
+Differences that do not change results:
+* device ADTs are built once per call for all donor zones (the reference
+  rebuilds every donor ADT for every receptor zone when hook=None,
+  OversetData.py:1223-1264 x setInterpData.cpp:772-818);
+* the local->zone index remap uses numpy fancy indexing instead of the
+  per-element Python loops at OversetData.py:1287-1313;
+* transfer plans (device-resident interpData) are cached per ID_* subregion.
+"""
+import weakref
+import numpy
+from .. import Internal
+from .. import Converter as C
+from .. import _lib
+from . import Connector
+
+
+# ---------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------
+def _addCellN__(t, loc='nodes'):
+    """Add cellN=1 at loc on zones that lack it (OversetData.py _addCellN__)."""
+    var = 'cellN' if loc == 'nodes' else 'centers:cellN'
+    for z in Internal.getZones(t):
+        if C.isNamePresent(z, var) == -1:
+            C._initVars(z, var, 1.)
+    return None
+
+
+def _zoneArray(z, withCellN=True):
+    """Converter array ['x,y,z,cellN', (4,npts), ni,nj,nk] of a zone at nodes."""
+    _, ni, nj, nk, _ = Internal.getZoneDim(z)
+    x, y, zc = C.getCoords(z)
+    n = ni * nj * nk
+    rows = [x.reshape(n, order='F'), y.reshape(n, order='F'), zc.reshape(n, order='F')]
+    names = 'x,y,z'
+    if withCellN:
+        c = C.getFieldArray(z, 'cellN')
+        if c is not None:
+            rows.append(c.reshape(n, order='F'))
+            names += ',cellN'
+    return [names, numpy.ascontiguousarray(numpy.stack(rows)), ni, nj, nk]
+
+
+def _adaptForRANSLES__(tR, tD, dictOfModels=None):
+    """Flag RANS/LES and NS/LBM donor-receptor pairs (OversetData.py:1702-1750)."""
+    zrdict = {}
+    if dictOfModels is None:
+        dictOfModels = {}
+        for tp in [tR, tD]:
+            bases = Internal.getBases(tp)
+            if bases != []:
+                for b in bases:
+                    model_b = Internal.getNodeFromName2(b, 'GoverningEquations')
+                    model_b = Internal.getValue(model_b) if model_b is not None else 'None'
+                    for z in Internal.getZones(b):
+                        model = Internal.getNodeFromName2(z, 'GoverningEquations')
+                        dictOfModels[z[0]] = model_b if model is None else Internal.getValue(model)
+            else:
+                for z in Internal.getZones(tp):
+                    model = Internal.getNodeFromName2(z, 'GoverningEquations')
+                    dictOfModels[z[0]] = 'None' if model is None else Internal.getValue(model)
+    for zr in Internal.getZones(tR):
+        zrdict[zr[0]] = zr
+    for zd in Internal.getZones(tD):
+        model_zd = dictOfModels.get(zd[0], 'None')
+        for s in Internal.getNodesFromType1(zd, 'ZoneSubRegion_t'):
+            zrcvname = Internal.getValue(s)
+            if zrcvname in zrdict:
+                model_zr = dictOfModels.get(zrcvname, 'None')
+                if model_zr != 'None' and model_zd != 'None':
+                    if (model_zr == 'NSTurbulent' or model_zd == 'NSTurbulent') and model_zr != model_zd:
+                        Internal.createUniqueChild(s, 'RANSLES', 'DataArray_t', numpy.ones(1, dtype=Internal.E_NpyInt))
+                    if (model_zr == 'LBMLaminar' or model_zd == 'LBMLaminar') and model_zr != model_zd:
+                        Internal.createUniqueChild(s, 'NSLBM', 'DataArray_t', numpy.ones(1, dtype=Internal.E_NpyInt))
+    return None
+
+
+def _createInterpRegion__(z, zname, pointlist, pointlistdonor, interpCoef, interpType, interpVol, indicesExtrap,
+                          indicesOrphan, EXDir=[], pointlistdonorExtC=None, tag='Receiver', loc='centers',
+                          itype='chimera', prefix=None, RotationAngle=None, RotationCenter=None):
+    """Store one (donor, receptor) interpData block as a ZoneSubRegion_t, same
+    node names / order / concatenation rule as OversetData.py:1752-1884."""
+    if loc == 'faces':
+        raise NotImplementedError("_createInterpRegion__: loc='faces' is not on the device path.")
+    if prefix is None:
+        nameSubRegion = {'chimera': 'ID_', 'abutting': 'ID_', 'ibc': 'IBCD_', 'ibc2': '2_IBCD_'}[itype] + zname
+    else:
+        nameSubRegion = prefix + zname
+    zsr = Internal.getNodesFromName1(z, nameSubRegion)
+    if zsr == []:
+        info = Internal.createChild(z, nameSubRegion, 'ZoneSubRegion_t', value=zname)
+        Internal._createChild(info, 'ZoneRole', 'DataArray_t', value=tag)
+        if loc == 'centers':
+            Internal._createChild(info, 'GridLocation', 'GridLocation_t', value='CellCenter')
+        info[2].append(['PointList', pointlist, [], 'IndexArray_t'])
+        info[2].append(['PointListDonor', pointlistdonor, [], 'IndexArray_t'])
+        info[2].append(['InterpolantsDonor', interpCoef, [], 'DataArray_t'])
+        if interpVol.size > 0:
+            info[2].append(['InterpolantsVol', interpVol, [], 'DataArray_t'])
+        info[2].append(['InterpolantsType', interpType, [], 'DataArray_t'])
+        if indicesOrphan.size > 0:
+            info[2].append(['OrphanPointList', numpy.unique(indicesOrphan), [], 'DataArray_t'])
+        if indicesExtrap.size > 0:
+            info[2].append(['ExtrapPointList', indicesExtrap, [], 'DataArray_t'])
+        if RotationAngle is not None: info[2].append(RotationAngle)
+        if RotationCenter is not None: info[2].append(RotationCenter)
+    else:
+        s = zsr[0]
+        intd = Internal.getNodesFromName1(s, 'InterpolantsDonor')
+        if intd == []:
+            if loc == 'centers':
+                Internal._createChild(s, 'GridLocation', 'GridLocation_t', value='CellCenter')
+            s[2].append(['PointList', pointlist, [], 'IndexArray_t'])
+            s[2].append(['PointListDonor', pointlistdonor, [], 'IndexArray_t'])
+            s[2].append(['InterpolantsDonor', interpCoef, [], 'DataArray_t'])
+            if interpVol.size > 0: s[2].append(['InterpolantsVol', interpVol, [], 'DataArray_t'])
+            s[2].append(['InterpolantsType', interpType, [], 'DataArray_t'])
+            if indicesOrphan.size > 0:
+                s[2].append(['OrphanPointList', numpy.unique(indicesOrphan), [], 'DataArray_t'])
+            if indicesExtrap.size > 0: s[2].append(['ExtrapPointList', indicesExtrap, [], 'DataArray_t'])
+        else:
+            intd[0][1] = numpy.concatenate((intd[0][1], interpCoef))
+            for name, arr in (('InterpolantsType', interpType), ('PointList', pointlist),
+                              ('PointListDonor', pointlistdonor)):
+                node = Internal.getNodesFromName1(s, name)
+                if node != []: node[0][1] = numpy.concatenate((node[0][1], arr))
+            node = Internal.getNodesFromName1(s, 'OrphanPointList')
+            if node != []: node[0][1] = numpy.unique(indicesOrphan)
+            node = Internal.getNodesFromName1(s, 'ExtrapPointList')
+            if node != []: node[0][1] = numpy.concatenate((node[0][1], indicesExtrap))
+    return None
+
+
+# ---------------------------------------------------------------------------
+# 1. setInterpData
+# ---------------------------------------------------------------------------
+def setInterpData(tR, tD, order=2, penalty=1, nature=0, extrap=1,
+                  method='lagrangian', loc='nodes', storage='direct',
+                  interpDataType=1, hook=None, verbose=2,
+                  topTreeRcv=None, topTreeDnr=None, sameName=1, dim=3, itype='both', dictOfModels=None):
+    """Compute and store overset interpolation data."""
+    aR = Internal.copyRef(tR)
+    aD = Internal.copyRef(tD)
+    _setInterpData(aR, aD, order=order, penalty=penalty, nature=nature, extrap=extrap,
+                   method=method, loc=loc, storage=storage, interpDataType=interpDataType,
+                   hook=hook, verbose=verbose,
+                   topTreeRcv=topTreeRcv, topTreeDnr=topTreeDnr, sameName=sameName, dim=dim, itype=itype,
+                   dictOfModels=dictOfModels)
+    if storage == 'direct': return aR
+    else: return aD
+
+
+def _setInterpData(aR, aD, order=2, penalty=1, nature=0, extrap=1,
+                   method='lagrangian', loc='nodes', storage='direct',
+                   interpDataType=1, hook=None, verbose=2,
+                   topTreeRcv=None, topTreeDnr=None, sameName=1, dim=3, itype='both', dictOfModels=None):
+    # The abutting (ghost-cell) part of itype='both' only acts on zones that
+    # carry match/near-match GridConnectivity nodes
+    # (_setInterpDataForGhostCellsStruct__, OversetData.py:1153-1162); it has
+    # no device path.
+    if itype != 'chimera':
+        for z in Internal.getZones(aR):
+            if Internal.getNodesFromType2(z, 'GridConnectivity1to1_t') or Internal.getNodesFromType2(z, 'GridConnectivity_t'):
+                raise NotImplementedError("setInterpData: abutting (ghost-cell) interpolation data has no device "
+                                          "path; call with itype='chimera'.")
+        if itype == 'abutting':
+            return None
+    if itype != 'abutting':
+        _setInterpDataChimera(aR, aD, order=order, penalty=penalty, nature=nature, extrap=extrap, verbose=verbose,
+                              method=method, loc=loc, storage=storage, interpDataType=interpDataType, hook=hook,
+                              topTreeRcv=topTreeRcv, topTreeDnr=topTreeDnr, sameName=sameName, dim=dim, itype=itype,
+                              dictOfModels=dictOfModels)
+    return None
+
+
+def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
+                          method='lagrangian', loc='nodes', storage='direct',
+                          interpDataType=1, hook=None, verbose=2,
+                          topTreeRcv=None, topTreeDnr=None, sameName=1, dim=3, itype='both', dictOfModels=None,
+                          donorLists=None, ctx=None):
+    """donorLists (extension, optional): dict receptorZoneName -> list of donor
+    zone names to consider, in that order — what Connector/Mpi.py:950-983 does
+    with bbox-intersecting donors; None = all donors like the sequential API."""
+    locR = loc
+    if loc == 'nodes': cellNPresent = C.isNamePresent(aR, 'cellN')
+    elif loc == 'centers': cellNPresent = C.isNamePresent(aR, 'centers:cellN')
+    else: raise ValueError("setInterpData: invalid loc.")
+    if cellNPresent == -1 or itype == 'abutting': return None
+    if method == 'conservative':
+        if loc != 'centers':
+            raise ValueError("setInterpData: conservative type is available only for loc='centers'.")
+        raise NotImplementedError("setInterpData: method='conservative' has no device path.")
+    if method != 'lagrangian':
+        if method == 'leastsquares':
+            raise NotImplementedError("setInterpData: method='leastsquares' has no device path.")
+        raise ValueError("setInterpData__: %s: not a valid interpolation method." % method)
+    if order not in (2, 3, 4, 5):
+        print("Warning: setInterpData: unknown interpolation order. Set to 2nd order.")
+        order = 2
+
+    dictIsCellNPresent = {}
+    for zd in Internal.getZones(aD):
+        dictIsCellNPresent[zd[0]] = C.isNamePresent(zd, 'cellN')
+    _addCellN__(aD, loc='nodes')
+
+    zonesRcv = Internal.getZones(aR)
+    zonesDnrL = Internal.getZones(aD)
+    ctx = ctx or _lib.default_context()
+
+    # device donor zones: the hook list given by the caller, or built once here
+    if hook is not None:
+        if not isinstance(hook, list):
+            raise TypeError("setInterpData: hook must be a list of hooks.")
+        if len(hook) != len(zonesDnrL):
+            raise TypeError("setInterpData: size of list of hooks must be equal to the number of donor zones.")
+        allHooksL = hook[:]
+        for h, zd in zip(allHooksL, zonesDnrL):   # cellN may have changed since the hook was built
+            c = C.getFieldArray(zd, 'cellN')
+            h.set_celln(c.reshape(-1, order='F') if c is not None else None)
+    else:
+        allHooksL = [None] * len(zonesDnrL)
+
+    def hookOf(i):
+        if allHooksL[i] is None:
+            a = _zoneArray(zonesDnrL[i])
+            allHooksL[i] = Connector.createHooks__([a], ctx)[0]
+        return allHooksL[i]
+
+    try:
+        for z in zonesRcv:
+            cellNPresent = C.isNamePresent(z, 'cellN' if loc == 'nodes' else 'centers:cellN')
+            if cellNPresent == -1:
+                continue
+            idx = list(range(len(zonesDnrL)))
+            if sameName == 1:
+                for cL, zo in enumerate(zonesDnrL):
+                    if zo[0] == z[0]:
+                        idx.pop(cL)
+                        break
+            if donorLists is not None and z[0] in donorLists:
+                names = donorLists[z[0]]
+                byname = {zonesDnrL[i][0]: i for i in idx}
+                idx = [byname[n] for n in names if n in byname]
+            zonesDnr = [zonesDnrL[i] for i in idx]
+            nzonesDnr = len(zonesDnr)
+
+            # Etape 1: points to interpolate (cellN == 2)
+            _, ni, nj, nk, _ = Internal.getZoneDim(z)
+            x, y, zc = C.getCoords(z)
+            if locR == 'nodes':
+                cellN = C.getFieldArray(z, 'cellN')
+            else:
+                x, y, zc = [C.node2CenterArray(a) for a in (x, y, zc)]
+                cellN = C.getFieldArray(z, 'centers:cellN')
+            npts = cellN.size
+            an = ['x,y,z,cellN', numpy.stack([x.reshape(npts, order='F'), y.reshape(npts, order='F'),
+                                                 zc.reshape(npts, order='F'), cellN.reshape(npts, order='F')]), npts, 1, 1]
+            interpPts = Connector.getInterpolatedPoints__(an)
+            if nzonesDnr == 0:
+                if interpPts[1].shape[1] > 0:
+                    raise TypeError("setInterpData: no valid donor zone found.")
+                continue
+
+            # Etape 2: interpolation data on the device
+            resInterp = Connector.setInterpData__(interpPts, [None] * nzonesDnr, order=order, penalty=penalty,
+                                                  nature=nature, extrap=extrap, method=method,
+                                                  interpDataType=interpDataType, hook=[hookOf(i) for i in idx],
+                                                  dim=dim, ctx=ctx)
+            if resInterp is None:
+                continue
+            nbinterpolated = interpPts[1].shape[1]
+            nbextrapolated = sum(r.shape[0] for r in resInterp[4])
+            nborphan = resInterp[5].size
+            nbinterpolated = nbinterpolated - nbextrapolated - nborphan
+            if verbose != 0:
+                print('Zone %s: interpolated=%d ; extrapolated=%d ; orphan=%d' % (z[0], nbinterpolated, nbextrapolated, nborphan))
+                if nborphan > 0: print('Warning: zone %s has %d orphan points !' % (z[0], nborphan))
+            # local position -> index in the receptor zone (indcell), vectorised
+            indcells = interpPts[1][-1, :].astype(Internal.E_NpyInt)
+            if nborphan > 0:
+                resInterp[5] = indcells[resInterp[5]]
+            for noz in range(nzonesDnr):
+                if resInterp[0][noz].size > 0:
+                    resInterp[0][noz] = indcells[resInterp[0][noz]]
+                if resInterp[4][noz].size > 0:
+                    resInterp[4][noz] = indcells[resInterp[4][noz]]
+
+            # Etape 3: storage in the tree
+            for noz in range(nzonesDnr):
+                if resInterp[0][noz].size > 0:
+                    extrapPts = resInterp[4][noz] if resInterp[4][noz].size > 0 else numpy.array([], dtype=Internal.E_NpyInt)
+                    if storage == 'direct':
+                        _createInterpRegion__(z, zonesDnr[noz][0], resInterp[0][noz], resInterp[1][noz],
+                                              resInterp[3][noz], resInterp[2][noz], numpy.array([], numpy.float64),
+                                              extrapPts, resInterp[5], tag='Receiver', loc=locR)
+                    else:
+                        _createInterpRegion__(zonesDnr[noz], z[0], resInterp[1][noz], resInterp[0][noz],
+                                              resInterp[3][noz], resInterp[2][noz], numpy.array([], numpy.float64),
+                                              extrapPts, resInterp[5], tag='Donor', loc=locR)
+    finally:
+        if storage != 'direct':
+            _adaptForRANSLES__(aR, aD, dictOfModels=dictOfModels)
+        for zd in Internal.getZones(aD):
+            if dictIsCellNPresent[zd[0]] == -1: C._rmVars(zd, ['cellN'])
+    return None
+
+
+# ---------------------------------------------------------------------------
+# 2. setInterpTransfers
+# ---------------------------------------------------------------------------
+_PLAN_CACHE = {}
+
+
+def _getPlan(ctx, zd, nptsR, ListDonor, ListRcv, DonorType, Coefs):
+    """Device-resident interpData of one subregion, cached on the identity of
+    its four numpy arrays (reused across the 100s of calls of a solver loop)."""
+    key = (ctx.device, id(Coefs), id(ListDonor), id(ListRcv), id(DonorType), Coefs.size, ListRcv.size, nptsR)
+    p = _PLAN_CACHE.get(key)
+    if p is None:
+        _, imd, jmd, kmd, _ = Internal.getZoneDim(zd)
+        p = _lib.Plan(ctx, imd, jmd, kmd, nptsR, ListDonor, ListRcv, DonorType, Coefs)
+        _PLAN_CACHE[key] = p
+        for a in (Coefs, ListDonor, ListRcv, DonorType):
+            try:
+                weakref.finalize(a, _PLAN_CACHE.pop, key, None)
+            except TypeError:
+                pass
+    return p
+
+
+def _selectVariables(zr, zd, variables, cellNVariable, loc):
+    """Names to interpolate and whether the strict cellN rule applies
+    (setInterpTransfers.cpp:352-432): listed names present on both sides, or,
+    for an empty list, every name common to the donor's FlowSolution and the
+    receptor's container at loc; cellNVariable present on both is excluded and
+    handled by the strict rule."""
+    locR = 'centers' if loc == 1 else 'nodes'
+    varsD = C.getVarNames(zd, 'nodes')
+    varsR = C.getVarNames(zr, locR)
+    if not varsD:
+        raise TypeError("_setInterpTransfers: no field found in donor zones.")
+    if not varsR:
+        raise TypeError("_setInterpTransfers: no field found in receiver zones.")
+    poscd = cellNVariable in varsD
+    poscr = cellNVariable in varsR
+    cellnD = cellnR = False
+    if isinstance(variables, list) and len(variables) > 0:
+        names = []
+        for v in variables:
+            if not isinstance(v, str):
+                continue
+            if v == cellNVariable and poscd: cellnD = True
+            if v == cellNVariable and poscr: cellnR = True
+            if v in varsD and v in varsR:
+                names.append(v)
+    else:
+        names = [v for v in varsR if v in varsD]
+        cellnD, cellnR = poscd, poscr
+    strict = cellnD and cellnR
+    if strict:
+        names = [v for v in names if v != cellNVariable]
+    return names, strict, locR
+
+
+def setInterpTransfers(aR, topTreeD, variables=[], cellNVariable='cellN',
+                       variablesIBC=['Density', 'VelocityX', 'VelocityY', 'VelocityZ', 'Temperature'],
+                       bcType=0, varType=2, storage=-1, compact=0, compactD=0,
+                       Gamma=1.4, Cv=1.7857142857142865, MuS=1.e-08,
+                       Cs=0.3831337844872463, Ts=1.0):
+    """Transfer variables once interpolation data has been computed."""
+    tR = Internal.copyRef(aR)
+    _setInterpTransfers(tR, topTreeD, variables=variables, variablesIBC=variablesIBC,
+                        bcType=bcType, varType=varType, storage=storage, compact=compact, compactD=compactD,
+                        cellNVariable=cellNVariable, Gamma=Gamma, Cv=Cv, MuS=MuS, Cs=Cs, Ts=Ts)
+    return tR
+
+
+def _transferOne(ctx, zr, zd, s, variables, cellNVariable, ListRcv, ListDonor):
+    location = Internal.getNodeFromName1(s, 'GridLocation')
+    if location is not None: location = Internal.getValue(location)
+    loc = 1 if location == 'CellCenter' else 0
+    if Internal.getNodeFromName1(s, 'RotationAngle') is not None:
+        raise NotImplementedError("_setInterpTransfers: periodicity by rotation has no device path.")
+    Coefs = Internal.getNodeFromName1(s, 'InterpolantsDonor')[1]
+    DonorType = Internal.getNodeFromName1(s, 'InterpolantsType')[1]
+    names, strict, locR = _selectVariables(zr, zd, variables, cellNVariable, loc)
+    nptsR = int(numpy.prod(C.fieldShape(zr, locR)))
+    plan = _getPlan(ctx, zd, nptsR, ListDonor, ListRcv, DonorType, Coefs)
+    if names:
+        fD = [C.getFieldArray(zd, v) for v in names]
+        fR = [C.getFieldArray(zr, (('centers:' + v) if locR == 'centers' else v)) for v in names]
+        plan.transfer(fD, fR)
+    if strict:
+        cD = C.getFieldArray(zd, cellNVariable)
+        cR = C.getFieldArray(zr, ('centers:' + cellNVariable) if locR == 'centers' else cellNVariable)
+        plan.transfer_celln(cD, cR)
+
+
+def _setInterpTransfers(aR, topTreeD, variables=[], cellNVariable='',
+                        variablesIBC=['Density', 'VelocityX', 'VelocityY', 'VelocityZ', 'Temperature'],
+                        bcType=0, varType=2, storage=-1, compact=0, compactD=0,
+                        Gamma=1.4, Cv=1.7857142857142865, MuS=1.e-08, Cs=0.3831337844872463, Ts=1.0, ctx=None):
+    if compact != 0:
+        raise NotImplementedError("_setInterpTransfers: compact=1 (Fast solver layout) has no device path yet.")
+    ctx = ctx or _lib.default_context()
+    # direct storage: data held by the receptor zones (OversetData.py:1968-2033)
+    if storage < 1:
+        znd = {z[0]: z for z in Internal.getZones(topTreeD)}
+        for zr in Internal.getZones(aR):
+            for s in Internal.getNodesFromType1(zr, 'ZoneSubRegion_t'):
+                sname = s[0][0:2]
+                if sname == 'ID' and variables is not None:
+                    idn = Internal.getNodeFromName1(s, 'InterpolantsDonor')
+                    if idn is not None:
+                        zoneRole = Internal.getValue(Internal.getNodeFromName2(s, 'ZoneRole'))
+                        if zoneRole == 'Receiver':
+                            ListRcv = Internal.getNodeFromName1(s, 'PointList')[1]
+                            ListDonor = Internal.getNodeFromName1(s, 'PointListDonor')[1]
+                            zd = znd[Internal.getValue(s)]
+                            _transferOne(ctx, zr, zd, s, variables, cellNVariable, ListRcv, ListDonor)
+    # inverse storage: data held by the donor zones (OversetData.py:2036-2098)
+    if storage != 0:
+        znr = {z[0]: z for z in Internal.getZones(aR)}
+        for zd in Internal.getZones(topTreeD):
+            for s in Internal.getNodesFromType1(zd, 'ZoneSubRegion_t'):
+                sname = s[0][0:2]
+                if sname == 'ID' and variables is not None:
+                    idn = Internal.getNodeFromName1(s, 'InterpolantsDonor')
+                    if idn is not None:
+                        zoneRole = Internal.getValue(Internal.getNodeFromName2(s, 'ZoneRole'))
+                        if zoneRole == 'Donor':
+                            ListDonor = Internal.getNodeFromName1(s, 'PointList')[1]
+                            ListRcv = Internal.getNodeFromName1(s, 'PointListDonor')[1]
+                            zr = znr.get(Internal.getValue(s), None)
+                            if zr is not None:
+                                _transferOne(ctx, zr, zd, s, variables, cellNVariable, ListRcv, ListDonor)
+    return None
+
+
+def setInterpTransfersD(topTreeD, variables=[], cellNVariable='',
+                        variablesIBC=['Density', 'VelocityX', 'VelocityY', 'VelocityZ', 'Temperature'],
+                        bcType=0, varType=2, compact=0, compactD=0,
+                        Gamma=1.4, Cv=1.7857142857142865, MuS=1.e-08,
+                        Cs=0.3831337844872463, Ts=1.0, extract=0, alpha=1.):
+    tD = Internal.copyRef(topTreeD)
+    return _setInterpTransfersD(tD, variables=variables, cellNVariable=cellNVariable, variablesIBC=variablesIBC,
+                                bcType=bcType, varType=varType, compact=compact, compactD=compactD,
+                                Gamma=Gamma, Cv=Cv, MuS=MuS, Cs=Cs, Ts=Ts, extract=extract)
+
+
+def _setInterpTransfersD(topTreeD, variables=[], cellNVariable='',
+                         variablesIBC=['Density', 'VelocityX', 'VelocityY', 'VelocityZ', 'Temperature'],
+                         bcType=0, varType=2, compact=0, compactD=0,
+                         Gamma=1.4, Cv=1.7857142857142865, MuS=1.e-08,
+                         Cs=0.3831337844872463, Ts=1.0, extract=0, alpha=1., ctx=None):
+    """Donor-side transfer: list of [rcvZoneName, array(nvars,nrcv), ListRcv, loc]
+    (OversetData.py:2179-2270; connector._setInterpTransfersD,
+    setInterpTransfersD.cpp:106-303: listed variables present in the donor's
+    FlowSolution, or all of them but cellNVariable for an empty list)."""
+    if compact != 0:
+        raise NotImplementedError("_setInterpTransfersD: compact=1 has no device path yet.")
+    ctx = ctx or _lib.default_context()
+    infos = []
+    for zd in Internal.getZones(topTreeD):
+        for s in Internal.getNodesFromType1(zd, 'ZoneSubRegion_t'):
+            if s[0][0:2] == 'ID' and variables is not None:
+                idn = Internal.getNodeFromName1(s, 'InterpolantsDonor')
+                if idn is None:
+                    continue
+                if Internal.getValue(Internal.getNodeFromName2(s, 'ZoneRole')) != 'Donor':
+                    continue
+                location = Internal.getNodeFromName1(s, 'GridLocation')
+                if location is not None: location = Internal.getValue(location)
+                loc = 'centers' if location == 'CellCenter' else 'nodes'
+                Coefs = idn[1]
+                DonorType = Internal.getNodeFromName1(s, 'InterpolantsType')[1]
+                ListDonor = Internal.getNodeFromName1(s, 'PointList')[1]
+                ListRcv = Internal.getNodeFromName1(s, 'PointListDonor')[1]
+                varsD = C.getVarNames(zd, 'nodes')
+                if isinstance(variables, list) and len(variables) > 0:
+                    names = [v for v in variables if v in varsD and v != cellNVariable]
+                    withCellN = cellNVariable in variables and cellNVariable in varsD
+                else:
+                    names = [v for v in varsD if v != cellNVariable]
+                    withCellN = False
+                nmax = int(ListRcv.max()) + 1 if ListRcv.size else 1
+                plan = _getPlan(ctx, zd, nmax, ListDonor, ListRcv, DonorType, Coefs)
+                arr = plan.transferD([C.getFieldArray(zd, v) for v in names])
+                varString = ','.join(names)
+                if withCellN:
+                    # strict cellN rule evaluated donor side (setInterpTransfersD.cpp:159-180)
+                    cR = numpy.zeros(nmax)
+                    plan.transfer_celln(C.getFieldArray(zd, cellNVariable), cR)
+                    arr = numpy.vstack([arr, cR[ListRcv][None, :]])
+                    varString = (varString + ',' if varString else '') + cellNVariable
+                infos.append([Internal.getValue(s), [varString, arr, ListRcv.size, 1, 1], ListRcv, loc])
+    return infos

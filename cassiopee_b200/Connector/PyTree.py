@@ -1,0 +1,10 @@
+"""Connector.PyTree public names of the chimera path
+(/root/reference/Cassiopee/Connector/Connector/PyTree.py:7-13 re-exports the
+same names from OversetData.py)."""
+from .OversetData import (setInterpData, _setInterpData, _setInterpDataChimera, setInterpTransfers,
+                          _setInterpTransfers, setInterpTransfersD, _setInterpTransfersD,
+                          _createInterpRegion__, _addCellN__)
+from .Connector import setInterpData__, getInterpolatedPoints__, createHooks__
+
+__all__ = ['setInterpData', '_setInterpData', 'setInterpTransfers', '_setInterpTransfers',
+           'setInterpTransfersD', '_setInterpTransfersD']

@@ -1,0 +1,193 @@
+"""Converter.PyTree helpers the chimera path needs on the host side.
+
+Restated minimal subset (plain numpy on CGNS/Python trees):
+
+* node2Center      Converter/Converter/PyTree.py (C.node2Center) +
+                   KCore/KCore/Loc/node2Center.cpp:118-146  (0.125*sum of 8 nodes,
+                   left-associated in the order ind0..ind7)
+* _initVars / _addVars / _rmVars / isNamePresent / getField-style accessors
+* newPyTree, getAllFields helpers
+
+Fields live in ``FlowSolution`` (nodes) and ``FlowSolution#Centers`` (centres),
+one Fortran-ordered (ni,nj,nk) float64 numpy per variable.
+"""
+import numpy
+from . import Internal
+
+
+def newPyTree(args=None):
+    """newPyTree(['Base', z1, z2, 'Base2', z3]) like Converter.PyTree.newPyTree."""
+    t = Internal.newCGNSTree()
+    base = None
+    for a in (args or []):
+        if isinstance(a, str):
+            base = Internal.newCGNSBase(a, 3, 3, parent=t)
+        elif isinstance(a, list):
+            if base is None:
+                base = Internal.newCGNSBase('Base', 3, 3, parent=t)
+            if Internal.isStdNode(a) == -1:
+                base[2].append(a)
+            else:
+                for z in a:
+                    base[2].append(z)
+    return t
+
+
+def _container(z, loc, create=False):
+    name = Internal.__FlowSolutionCenters__ if loc == 'centers' else Internal.__FlowSolutionNodes__
+    c = Internal.getNodeFromName1(z, name)
+    if c is None and create:
+        c = Internal.createChild(z, name, 'FlowSolution_t')
+        if loc == 'centers':
+            Internal.createChild(c, 'GridLocation', 'GridLocation_t', 'CellCenter')
+    return c
+
+
+def _splitName(var):
+    if var.startswith('centers:'):
+        return 'centers', var[8:]
+    if var.startswith('nodes:'):
+        return 'nodes', var[6:]
+    return 'nodes', var
+
+
+def isNamePresent(t, var):
+    """1 if var is in all zones, 0 if in some, -1 if in none (C.isNamePresent)."""
+    loc, name = _splitName(var)
+    zones = Internal.getZones(t)
+    if not zones:
+        return -1
+    n = 0
+    for z in zones:
+        c = _container(z, loc)
+        if c is not None and Internal.getNodeFromName1(c, name) is not None:
+            n += 1
+    if n == len(zones):
+        return 1
+    return 0 if n > 0 else -1
+
+
+def getCoords(z):
+    gc = Internal.getNodeFromName1(z, Internal.__GridCoordinates__)
+    return [Internal.getNodeFromName1(gc, n)[1] for n in ('CoordinateX', 'CoordinateY', 'CoordinateZ')]
+
+
+def getFieldArray(z, var):
+    loc, name = _splitName(var)
+    c = _container(z, loc)
+    if c is None:
+        return None
+    n = Internal.getNodeFromName1(c, name)
+    return None if n is None else n[1]
+
+
+def fieldShape(z, loc):
+    _, ni, nj, nk, _ = Internal.getZoneDim(z)
+    if loc == 'centers':
+        return (max(ni - 1, 1), max(nj - 1, 1), max(nk - 1, 1))
+    return (ni, nj, nk)
+
+
+def _initVars(t, var, value=0.):
+    """Set a field: constant, ndarray, or callable f(x,y,z) of the coordinates at loc."""
+    loc, name = _splitName(var)
+    for z in Internal.getZones(t):
+        shp = fieldShape(z, loc)
+        if callable(value):
+            x, y, zc = getCoords(z)
+            if loc == 'centers':
+                x, y, zc = [node2CenterArray(a) for a in (x, y, zc)]
+            a = numpy.asfortranarray(numpy.asarray(value(x, y, zc), dtype=numpy.float64).reshape(shp, order='F'))
+        elif isinstance(value, numpy.ndarray):
+            a = numpy.asfortranarray(value.astype(numpy.float64).reshape(shp, order='F'))
+        else:
+            a = numpy.full(shp, float(value), dtype=numpy.float64, order='F')
+        c = _container(z, loc, create=True)
+        n = Internal.getNodeFromName1(c, name)
+        if n is None:
+            Internal.createChild(c, name, 'DataArray_t', a)
+        else:
+            n[1] = a
+    return None
+
+
+def initVars(t, var, value=0.):
+    tp = Internal.copyRef(t)
+    _initVars(tp, var, value)
+    return tp
+
+
+def _rmVars(t, variables):
+    if isinstance(variables, str):
+        variables = [variables]
+    for z in Internal.getZones(t):
+        for v in variables:
+            loc, name = _splitName(v)
+            c = _container(z, loc)
+            if c is not None:
+                c[2][:] = [n for n in c[2] if n[0] != name]
+    return None
+
+
+def getVarNames(z, loc='nodes'):
+    c = _container(z, loc)
+    if c is None:
+        return []
+    return [n[0] for n in c[2] if n[3] == 'DataArray_t']
+
+
+def node2CenterArray(a):
+    """(ni,nj,nk) node array -> (ni-1,nj-1,nk-1) centre array; 3-D formula of
+    node2Center.cpp:118-146, summation order ind0..ind7."""
+    a = numpy.asarray(a)
+    ni, nj, nk = a.shape
+    if nk == 1:
+        s = a[:-1, :-1, :] + a[1:, :-1, :]
+        s = s + a[:-1, 1:, :]
+        s = s + a[1:, 1:, :]
+        return numpy.asfortranarray(0.25 * s)
+    s = a[:-1, :-1, :-1] + a[1:, :-1, :-1]
+    s = s + a[:-1, 1:, :-1]
+    s = s + a[1:, 1:, :-1]
+    s = s + a[:-1, :-1, 1:]
+    s = s + a[1:, :-1, 1:]
+    s = s + a[:-1, 1:, 1:]
+    s = s + a[1:, 1:, 1:]
+    return numpy.asfortranarray(0.125 * s)
+
+
+def node2Center(t):
+    """C.node2Center(t): tree of the centre meshes.  Coordinates become the
+    cell centres; centre fields (FlowSolution#Centers) become node fields of
+    the new zones; node fields are averaged to centres.  This is the ``tc``
+    convention of the reference (Apps/Apps/Fast/MB.py:101-103)."""
+    tp = Internal.copyRef(t)
+    for z in Internal.getZones(tp):
+        _, ni, nj, nk, _ = Internal.getZoneDim(z)
+        x, y, zc = getCoords(z)
+        xc, yc, zcc = [node2CenterArray(a) for a in (x, y, zc)]
+        nic, njc, nkc = xc.shape
+        v = numpy.zeros((3, 3), dtype=Internal.E_NpyInt, order='F')
+        v[:, 0] = (nic, njc, nkc)
+        v[:, 1] = (max(nic - 1, 1), max(njc - 1, 1), max(nkc - 1, 1))
+        z[1] = v
+        gc = Internal.getNodeFromName1(z, Internal.__GridCoordinates__)
+        for nm, a in (('CoordinateX', xc), ('CoordinateY', yc), ('CoordinateZ', zcc)):
+            Internal.getNodeFromName1(gc, nm)[1] = a
+        fsn = Internal.getNodeFromName1(z, Internal.__FlowSolutionNodes__)
+        fsc = Internal.getNodeFromName1(z, Internal.__FlowSolutionCenters__)
+        newfields = []
+        if fsn is not None:
+            for n in fsn[2]:
+                if n[3] == 'DataArray_t':
+                    newfields.append([n[0], node2CenterArray(n[1]), [], 'DataArray_t'])
+        if fsc is not None:
+            names = [f[0] for f in newfields]
+            for n in fsc[2]:
+                if n[3] == 'DataArray_t' and n[0] not in names:
+                    newfields.append([n[0], n[1], [], 'DataArray_t'])
+        z[2][:] = [c for c in z[2] if c[0] not in (Internal.__FlowSolutionNodes__, Internal.__FlowSolutionCenters__)]
+        if newfields:
+            c = Internal.createChild(z, Internal.__FlowSolutionNodes__, 'FlowSolution_t')
+            c[2].extend(newfields)
+    return tp

@@ -1,0 +1,394 @@
+"""ctypes binding of csrc/libcassiopee_b200.so (C ABI: include/cassiopee_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device
+can be opened, every compute entry point raises.  numpy host arrays stay owned
+by Python; device mirrors are owned by the handle objects below.
+"""
+import ctypes
+import os
+import weakref
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(_HERE, "csrc", "libcassiopee_b200.so")
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_ll = ctypes.c_longlong
+_d = ctypes.c_double
+_sz = ctypes.c_size_t
+
+_SIGS = {
+    "cx_last_error": (ctypes.c_char_p, []),
+    "cx_version": (_i, []),
+    "cx_device_count": (_i, [_vp]),
+    "cx_ctx_create": (_i, [_i, _vp]),
+    "cx_ctx_destroy": (_i, [_vp]),
+    "cx_ctx_sync": (_i, [_vp]),
+    "cx_ctx_launches": (_ll, [_vp]),
+    "cx_ctx_info": (_i, [_vp, _vp, _vp, _vp]),
+    "cx_event_record": (_i, [_vp, _i]),
+    "cx_event_elapsed_ms": (_i, [_vp, _vp]),
+    "cx_flush_l2": (_i, [_vp]),
+    "cx_dev_alloc": (_i, [_vp, _sz, _vp]),
+    "cx_dev_free": (_i, [_vp, _vp]),
+    "cx_dev_upload": (_i, [_vp, _vp, _vp, _sz]),
+    "cx_dev_download": (_i, [_vp, _vp, _vp, _sz]),
+    "cx_dev_memset": (_i, [_vp, _vp, _i, _sz]),
+    "cx_pinned_alloc": (_i, [_sz, _vp]),
+    "cx_pinned_free": (_i, [_vp]),
+    "cx_zone_create": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "cx_zone_set_celln": (_i, [_vp, _vp]),
+    "cx_zone_info": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "cx_zone_candidates": (_i, [_vp, _d, _d, _d, _d, _vp, _i, _vp]),
+    "cx_zone_export_adt": (_i, [_vp, _vp, _sz]),
+    "cx_zone_destroy": (_i, [_vp]),
+    "cx_set_interp_data": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
+    "cx_set_interp_data_dev": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
+    "cx_result_sizes": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "cx_result_fetch_zone": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "cx_result_fetch_orphans": (_i, [_vp, _vp]),
+    "cx_result_fetch_raw": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "cx_result_stats": (_i, [_vp, _vp]),
+    "cx_result_destroy": (_i, [_vp]),
+    "cx_plan_create": (_i, [_vp, _i, _i, _i, _ll, _i, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "cx_transfer": (_i, [_vp, _i, _vp, _vp]),
+    "cx_transferD": (_i, [_vp, _i, _vp, _vp]),
+    "cx_transfer_celln": (_i, [_vp, _vp, _vp]),
+    "cx_transfer_dev": (_i, [_vp, _i, _vp, _vp]),
+    "cx_transferD_dev": (_i, [_vp, _i, _vp, _vp, _ll]),
+    "cx_transfer_celln_dev": (_i, [_vp, _vp, _vp]),
+    "cx_scatter_dev": (_i, [_vp, _i, _vp, _ll, _i, _vp, _vp]),
+    "cx_plan_info": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "cx_plan_destroy": (_i, [_vp]),
+    "cx_comm_unique_id": (_i, [_vp]),
+    "cx_comm_init": (_i, [_vp, _i, _i, _vp]),
+    "cx_comm_destroy": (_i, [_vp]),
+    "cx_comm_barrier": (_i, [_vp]),
+    "cx_exchange_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+}
+
+EXPORTED_SYMBOLS = sorted(_SIGS.keys())
+
+
+class CxError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library (loudly: no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIBPATH):
+            raise CxError("cassiopee_b200: %s is missing — build it with `python -c 'import __graft_entry__ as g; "
+                          "g.build()'` (nvcc, sm_100a). There is no CPU fallback." % LIBPATH)
+        L = ctypes.CDLL(LIBPATH)
+        for name, (res, args) in _SIGS.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().cx_last_error().decode(errors="replace")
+        if rc == -4:
+            raise NotImplementedError(msg)
+        if rc == -1:
+            raise TypeError(msg)
+        raise CxError("cassiopee_b200 (status %d): %s" % (rc, msg))
+
+
+def f64(a):
+    a = np.asarray(a)
+    if a.dtype != np.float64:
+        raise TypeError("cassiopee_b200: arrays must be float64")
+    if not (a.flags.c_contiguous or a.flags.f_contiguous):
+        raise TypeError("cassiopee_b200: arrays must be C- or F-contiguous (no copy is made)")
+    return a
+
+
+def i32(a):
+    a = np.asarray(a)
+    if a.dtype != np.int32 or not (a.flags.c_contiguous or a.flags.f_contiguous):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+    return a
+
+
+def ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+def ptr_array(ptrs):
+    return (ctypes.c_void_p * len(ptrs))(*ptrs)
+
+
+class Context:
+    """One CUDA device + stream (cx_ctx)."""
+
+    def __init__(self, device=0):
+        h = _vp()
+        check(lib().cx_ctx_create(int(device), ctypes.byref(h)))
+        self.h = h
+        self.device = int(device)
+        self._fin = weakref.finalize(self, lib().cx_ctx_destroy, h)
+
+    def sync(self):
+        check(lib().cx_ctx_sync(self.h))
+
+    def launches(self):
+        return int(lib().cx_ctx_launches(self.h))
+
+    def info(self):
+        sm = _i(); fr = _sz(); tot = _sz()
+        check(lib().cx_ctx_info(self.h, ctypes.byref(sm), ctypes.byref(fr), ctypes.byref(tot)))
+        return dict(sm_count=sm.value, free_bytes=fr.value, total_bytes=tot.value)
+
+    def event_record(self, which):
+        check(lib().cx_event_record(self.h, int(which)))
+
+    def event_elapsed_ms(self):
+        ms = ctypes.c_float()
+        check(lib().cx_event_elapsed_ms(self.h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def flush_l2(self):
+        check(lib().cx_flush_l2(self.h))
+
+    # raw device arrays of doubles / ints
+    def alloc(self, nbytes):
+        p = _vp()
+        check(lib().cx_dev_alloc(self.h, int(nbytes), ctypes.byref(p)))
+        return p.value
+
+    def free(self, dptr):
+        if dptr:
+            lib().cx_dev_free(self.h, _vp(dptr))
+
+    def upload(self, dptr, host):
+        check(lib().cx_dev_upload(self.h, _vp(dptr), ptr(host), host.nbytes))
+
+    def download(self, host, dptr):
+        check(lib().cx_dev_download(self.h, ptr(host), _vp(dptr), host.nbytes))
+
+
+_default_ctx = {}
+
+
+def default_context(device=None):
+    if device is None:
+        device = int(os.environ.get("CX_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        n = _i()
+        check(lib().cx_device_count(ctypes.byref(n)))
+        if n.value > 0:
+            device = device % n.value
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class DeviceArray:
+    """float64/int32 array resident in HBM (cx_dev_alloc)."""
+
+    def __init__(self, ctx, n, dtype=np.float64):
+        self.ctx = ctx
+        self.n = int(n)
+        self.dtype = np.dtype(dtype)
+        self.ptr = ctx.alloc(self.n * self.dtype.itemsize)
+        self._fin = weakref.finalize(self, lib().cx_dev_free, ctx.h, _vp(self.ptr))
+
+    @classmethod
+    def from_host(cls, ctx, a):
+        a = np.asarray(a)
+        d = cls(ctx, a.size, a.dtype)
+        d.upload(a)
+        return d
+
+    def upload(self, a):
+        a = np.asarray(a)
+        assert a.size == self.n and a.dtype == self.dtype
+        if not (a.flags.c_contiguous or a.flags.f_contiguous):
+            a = np.ascontiguousarray(a)
+        self.ctx.upload(self.ptr, a)
+
+    def download(self, out=None):
+        if out is None:
+            out = np.empty(self.n, dtype=self.dtype)
+        self.ctx.download(out, self.ptr)
+        return out
+
+
+class Zone:
+    """Donor zone resident on the device with its ADT replica (cx_zone) — the
+    analogue of the reference's ``C.createHook(z, 'adt')``."""
+
+    def __init__(self, ctx, ni, nj, nk, x, y, z, cellN=None):
+        self.ctx = ctx
+        self.ni, self.nj, self.nk = int(ni), int(nj), int(nk)
+        x, y, z = f64(x), f64(y), f64(z)
+        n = self.ni * self.nj * self.nk
+        if x.size != n or y.size != n or z.size != n:
+            raise TypeError("setInterpData: 2nd argument is not valid.")
+        c = f64(cellN) if cellN is not None else None
+        h = _vp()
+        check(lib().cx_zone_create(ctx.h, self.ni, self.nj, self.nk, ptr(x), ptr(y), ptr(z), ptr(c), ctypes.byref(h)))
+        self.h = h
+        self._fin = weakref.finalize(self, lib().cx_zone_destroy, h)
+
+    def set_celln(self, cellN):
+        c = f64(cellN) if cellN is not None else None
+        check(lib().cx_zone_set_celln(self.h, ptr(c)))
+
+    def info(self):
+        bb = np.zeros(6); nc = _i(); dp = _i(); ms = ctypes.c_float()
+        check(lib().cx_zone_info(self.h, ptr(bb), ctypes.byref(nc), ctypes.byref(dp), ctypes.byref(ms)))
+        return dict(bbox=bb, ncells=nc.value, depth=dp.value, build_ms=float(ms.value))
+
+    def candidates(self, x, y, z, alphaTol=0.0, cap=1 << 16):
+        out = np.zeros(cap, np.int32); n = _i()
+        check(lib().cx_zone_candidates(self.h, float(x), float(y), float(z), float(alphaTol), ptr(out), cap,
+                                       ctypes.byref(n)))
+        return out[:min(n.value, cap)].copy()
+
+    def export_adt(self):
+        nc = self.info()["ncells"]
+        dt = np.dtype([("bb", np.float64, 6), ("mid", np.float64), ("rlo", np.float64), ("left", np.int32),
+                       ("right", np.int32), ("dim", np.int32), ("ind", np.int32)])
+        assert dt.itemsize == 80
+        out = np.zeros(nc, dtype=dt)
+        check(lib().cx_zone_export_adt(self.h, ptr(out), out.nbytes))
+        return out
+
+
+class InterpResult:
+    """Output of one setInterpData call (cx_result)."""
+
+    def __init__(self, h, nz, nrcv):
+        self.h = h
+        self.nz = nz
+        self.nrcv = nrcv
+        self._fin = weakref.finalize(self, lib().cx_result_destroy, h)
+
+    def sizes(self):
+        cnt = np.zeros(self.nz, np.int32); nco = np.zeros(self.nz, np.int32); nex = np.zeros(self.nz, np.int32)
+        no = _i()
+        check(lib().cx_result_sizes(self.h, ptr(cnt), ptr(nco), ptr(nex), ctypes.byref(no)))
+        return cnt, nco, nex, no.value
+
+    def fetch(self):
+        """The reference's 7-list [rcv]*nz,[donor]*nz,[type]*nz,[coefs]*nz,[extrap]*nz,orphan,[]
+        (Connector/Connector/setInterpData.cpp:1272)."""
+        cnt, nco, nex, no = self.sizes()
+        R, D, T, C, E = [], [], [], [], []
+        for z in range(self.nz):
+            r = np.empty(cnt[z], np.int32); d = np.empty(cnt[z], np.int32); t = np.empty(cnt[z], np.int32)
+            c = np.empty(nco[z], np.float64); e = np.empty(nex[z], np.int32)
+            check(lib().cx_result_fetch_zone(self.h, z, ptr(r), ptr(d), ptr(t), ptr(c), ptr(e)))
+            R.append(r); D.append(d); T.append(t); C.append(c); E.append(e)
+        orphan = np.empty(no, np.int32)
+        check(lib().cx_result_fetch_orphans(self.h, ptr(orphan)))
+        return [R, D, T, C, E, orphan, []]
+
+    def raw(self):
+        st = self.stats()
+        ncf = int(st["ncfmax"])
+        n = self.nrcv
+        noblk = np.zeros(n, np.int32); typ = np.zeros(n, np.int32); dind = np.zeros(n, np.int32)
+        isext = np.zeros(n, np.int32); cf = np.zeros((ncf, n))
+        check(lib().cx_result_fetch_raw(self.h, ptr(noblk), ptr(typ), ptr(dind), ptr(isext), ptr(cf)))
+        return dict(noblk=noblk, type=typ, dind=dind, isext=isext, cf=cf.T.copy())
+
+    def stats(self):
+        out = np.zeros(8)
+        check(lib().cx_result_stats(self.h, ptr(out)))
+        return dict(search_ms=out[0], extrap_ms=out[1], nodes_visited=out[2], candidates=out[3], ncfmax=out[4])
+
+
+def set_interp_data(ctx, xr, yr, zr, zones, order=2, nature=0, penalty=1, extrap=1):
+    """connector.setInterpData on host receptor coordinates (numpy)."""
+    xr, yr, zr = f64(xr).reshape(-1), f64(yr).reshape(-1), f64(zr).reshape(-1)
+    n = xr.size
+    hs = (ctypes.c_void_p * len(zones))(*[z.h.value for z in zones])
+    h = _vp()
+    check(lib().cx_set_interp_data(ctx.h, n, ptr(xr), ptr(yr), ptr(zr), len(zones), hs, int(order), int(nature),
+                                   int(penalty), int(extrap), ctypes.byref(h)))
+    return InterpResult(h, len(zones), n)
+
+
+def set_interp_data_dev(ctx, n, dxr, dyr, dzr, zones, order=2, nature=0, penalty=1, extrap=1):
+    hs = (ctypes.c_void_p * len(zones))(*[z.h.value for z in zones])
+    h = _vp()
+    check(lib().cx_set_interp_data_dev(ctx.h, int(n), _vp(dxr), _vp(dyr), _vp(dzr), len(zones), hs, int(order),
+                                       int(nature), int(penalty), int(extrap), ctypes.byref(h)))
+    return InterpResult(h, len(zones), int(n))
+
+
+class Plan:
+    """Device-resident interpData of one ID_* subregion (cx_plan)."""
+
+    def __init__(self, ctx, imd, jmd, kmd, nptsR, donor, rcv, typ, coefs):
+        self.ctx = ctx
+        donor, rcv, typ = i32(donor).reshape(-1), i32(rcv).reshape(-1), i32(typ).reshape(-1)
+        coefs = f64(coefs).reshape(-1)
+        if not (donor.size == rcv.size == typ.size):
+            raise TypeError("_setInterpTransfers: PointList, PointListDonor and InterpolantsType differ in size")
+        self.n = typ.size
+        self.imd, self.jmd, self.kmd, self.nptsR = int(imd), int(jmd), int(kmd), int(nptsR)
+        self.nptsD = self.imd * self.jmd * self.kmd
+        h = _vp()
+        check(lib().cx_plan_create(ctx.h, self.imd, self.jmd, self.kmd, self.nptsR, self.n, ptr(donor), ptr(rcv),
+                                   ptr(typ), ptr(coefs), coefs.size, ctypes.byref(h)))
+        self.h = h
+        self._fin = weakref.finalize(self, lib().cx_plan_destroy, h)
+
+    def _check_fields(self, fields, npts, what):
+        out = []
+        for a in fields:
+            a = f64(a)
+            if a.size != npts:
+                raise TypeError("_setInterpTransfers: %s field has %d values, zone has %d" % (what, a.size, npts))
+            out.append(a)
+        return out
+
+    def transfer(self, fieldsD, fieldsR):
+        """In place on host numpy arrays (connector._setInterpTransfers)."""
+        fD = self._check_fields(fieldsD, self.nptsD, "donor")
+        fR = self._check_fields(fieldsR, self.nptsR, "receptor")
+        assert len(fD) == len(fR)
+        check(lib().cx_transfer(self.h, len(fD), ptr_array([ptr(a) for a in fD]), ptr_array([ptr(a) for a in fR])))
+
+    def transferD(self, fieldsD):
+        """Dense (nvars, n) host array (connector._setInterpTransfersD)."""
+        fD = self._check_fields(fieldsD, self.nptsD, "donor")
+        out = np.empty((len(fD), self.n))
+        check(lib().cx_transferD(self.h, len(fD), ptr_array([ptr(a) for a in fD]), ptr(out)))
+        return out
+
+    def transfer_celln(self, cellND, cellNR):
+        cD = self._check_fields([cellND], self.nptsD, "donor")[0]
+        cR = self._check_fields([cellNR], self.nptsR, "receptor")[0]
+        check(lib().cx_transfer_celln(self.h, ptr(cD), ptr(cR)))
+
+    def transfer_dev(self, dptrsD, dptrsR):
+        check(lib().cx_transfer_dev(self.h, len(dptrsD), ptr_array(dptrsD), ptr_array(dptrsR)))
+
+    def transferD_dev(self, dptrsD, dout, ld):
+        check(lib().cx_transferD_dev(self.h, len(dptrsD), ptr_array(dptrsD), _vp(dout), int(ld)))
+
+    def transfer_celln_dev(self, dD, dR):
+        check(lib().cx_transfer_celln_dev(self.h, _vp(dD), _vp(dR)))
+
+    def info(self):
+        n = _i(); ng = _i(); af = _ll(); di = _ll()
+        check(lib().cx_plan_info(self.h, ctypes.byref(n), ctypes.byref(ng), ctypes.byref(af), ctypes.byref(di)))
+        return dict(n=n.value, ngroups=ng.value, alg_fixed=af.value, distinct=di.value)
+
+    def alg_bytes(self, nvars):
+        """B_alg of SURVEY.md 8(d) for one call with nvars variables."""
+        i = self.info()
+        return i["alg_fixed"] + 8 * nvars * (i["n"] + i["distinct"])

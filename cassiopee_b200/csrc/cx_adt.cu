@@ -1,0 +1,182 @@
+// cx_adt.cu — device build of an exact replica of the reference's ADT.
+//
+// The reference inserts the cells one by one (k,j,i loops, i fastest) into a
+// 6-key alternating digital tree rooted at the zone's boundary-cell bounding
+// box (KCore/KCore/Interp/InterpAdt.cpp:284-433 buildStructAdt, :506-646
+// insert).  The position of a cell in that tree is a pure function of the
+// cells inserted before it: it descends by the key/midpoint rule until it
+// meets an empty slot.  Equivalently, level by level: among the not-yet-placed
+// cells that reach the same empty slot, the one with the smallest insertion
+// rank takes it and the others descend through it.  That gives a
+// level-synchronous, fully parallel build:
+//
+//   claim(L)   every active cell evaluates the reference's midpoint recurrence
+//              for key L%6 on its own region interval and atomicMin's its rank
+//              into the child slot it falls into (warp-aggregated);
+//   resolve(L) the winner is placed (its split thresholds are frozen into the
+//              node), the others make the winner their new parent.
+//
+// Node id == insertion rank == cell id, so no allocation is needed.  The
+// midpoint recurrences (mid=0.5*(hi+lo); right: hi=2*mid-lo, lo=0.5*(hi+lo))
+// are evaluated exactly as the reference does, in fp64 without FMA, because
+// the query prunes with the very same numbers (InterpAdt.cpp:768-925).
+#include "cx_internal.h"
+
+using namespace cx;
+
+namespace {
+
+struct BuildScratch { int* actA; int* actB; int* counter; };
+
+__global__ void k_cell_keys(int ni, int nj, int nk, const double* __restrict__ x, const double* __restrict__ y,
+                            const double* __restrict__ z, double* __restrict__ keys, AdtNode* __restrict__ nodes,
+                            int ncells)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  adt_cell_keys(ni, nj, nk, x, y, z, c, ncells, keys, nodes);
+}
+
+__global__ void k_root(AdtNode* nodes, ZoneBox zb)
+{
+  freeze_node(nodes[0], 0, zb.lo[0], zb.hi[0]);
+}
+
+__global__ void k_init_active(int* act, int* cur, int n)
+{
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  act[a] = a + 1;
+  cur[a + 1] = 0;
+}
+
+__global__ void k_claim(int L, int nact, const int* __restrict__ act, BuildView B)
+{
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  bool on = a < nact;
+  int c = 0, p = 0, right = 0;
+  if (on) { c = act[a]; adt_claim(B, L, c, p, right); }
+  // warp-aggregated atomicMin of the insertion rank on the child slot
+  unsigned live = __ballot_sync(0xffffffffu, on);
+  if (!on) return;
+  int slotKey = p * 2 + right;
+  unsigned grp = __match_any_sync(live, slotKey);
+  int mn = __reduce_min_sync(grp, c);
+  int leader = __ffs(grp) - 1;
+  if ((threadIdx.x & 31) == leader)
+  {
+    int* slot = right ? &B.nodes[p].right : &B.nodes[p].left;
+    atomicMin(slot, mn);
+  }
+}
+
+__global__ void k_resolve(int L, int nact, const int* __restrict__ act, BuildView B, int* __restrict__ next,
+                          int* __restrict__ counter)
+{
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nact) return;
+  int c = act[a];
+  if (!adt_resolve(B, L, c))
+  {
+    int pos = atomicAdd(&counter[0], 1);
+    next[pos] = c;
+  }
+}
+
+}  // namespace
+
+// Zone bounding box over the cells touching the 6 boundary faces
+// (K_COMPGEOM::boundingBoxStruct, KCore/KCore/CompGeom/compGeom.cpp:446-...),
+// i.e. min/max over the nodes with i in {0,1,ni-2,ni-1} or j ... or k ...
+// Host side: the coordinates arrive from the host and the surface is O(n^(2/3)).
+void cx_zone_bbox_host(int ni, int nj, int nk, const double* x, const double* y, const double* z, double* bb)
+{
+  double mn[3] = {1.7976931348623157e308, 1.7976931348623157e308, 1.7976931348623157e308};
+  double mx[3] = {-1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308};
+  const double* arr[3] = {x, y, z};
+  auto visit = [&](int i, int j, int k) {
+    size_t n = (size_t)i + (size_t)ni * j + (size_t)ni * nj * k;
+    for (int d = 0; d < 3; d++)
+    {
+      double v = arr[d][n];
+      if (v < mn[d]) mn[d] = v;
+      if (v > mx[d]) mx[d] = v;
+    }
+  };
+  auto onb = [](int a, int n) { return a <= 1 || a >= n - 2; };
+  for (int k = 0; k < nk; k++)
+    for (int j = 0; j < nj; j++)
+    {
+      bool jk = onb(j, nj) || onb(k, nk);
+      if (jk) { for (int i = 0; i < ni; i++) visit(i, j, k); }
+      else
+      {
+        visit(0, j, k); visit(ni - 1, j, k);
+        if (ni > 2) { visit(1, j, k); visit(ni - 2, j, k); }
+      }
+    }
+  bb[0] = mn[0]; bb[1] = mn[1]; bb[2] = mn[2]; bb[3] = mx[0]; bb[4] = mx[1]; bb[5] = mx[2];
+}
+
+int cx_build_adt(cx_zone* z)
+{
+  cx_ctx* ctx = z->ctx;
+  cudaStream_t s = ctx->stream;
+  const int ncells = z->ncells;
+  const size_t n = ncells;
+  BuildView B; BuildScratch S;
+  CX_CUDA(cudaMalloc(&z->d_nodes, sizeof(AdtNode) * n));
+  B.nodes = z->d_nodes; B.ncells = ncells;
+  CX_CUDA(cudaMalloc(&B.keys, sizeof(double) * 6 * n));
+  CX_CUDA(cudaMalloc(&B.lo, sizeof(double) * 6 * n));
+  CX_CUDA(cudaMalloc(&B.hi, sizeof(double) * 6 * n));
+  CX_CUDA(cudaMalloc(&B.cur, sizeof(int) * n));
+  CX_CUDA(cudaMalloc(&B.br, n));
+  CX_CUDA(cudaMalloc(&S.actA, sizeof(int) * n));
+  CX_CUDA(cudaMalloc(&S.actB, sizeof(int) * n));
+  CX_CUDA(cudaMalloc(&S.counter, sizeof(int) * 2));
+  ZoneBox zb;
+  for (int d = 0; d < 6; d++) { zb.lo[d] = z->bbox[d % 3]; zb.hi[d] = z->bbox[3 + d % 3]; }
+  B.zb = zb;
+
+  CX_CUDA(cudaEventRecord(ctx->ev0, s));
+  const int TB = 256;
+  k_cell_keys<<<cx_grid(n, TB), TB, 0, s>>>(z->ni, z->nj, z->nk, z->d_x, z->d_y, z->d_z, B.keys, z->d_nodes, ncells);
+  k_root<<<1, 1, 0, s>>>(z->d_nodes, zb);
+  ctx->launches += 2;
+  int nact = ncells - 1;
+  if (nact > 0) { k_init_active<<<cx_grid(nact, TB), TB, 0, s>>>(S.actA, B.cur, nact); ctx->launches++; }
+  int* act = S.actA; int* next = S.actB;
+  int L = 0, depth = 0;
+  while (nact > 0)
+  {
+    CX_CUDA(cudaMemsetAsync(S.counter, 0, sizeof(int), s));
+    k_claim<<<cx_grid(nact, TB), TB, 0, s>>>(L, nact, act, B);
+    k_resolve<<<cx_grid(nact, TB), TB, 0, s>>>(L, nact, act, B, next, S.counter);
+    ctx->launches += 2;
+    int nnext = 0;
+    CX_CUDA(cudaMemcpyAsync(&nnext, S.counter, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CX_CUDA(cudaStreamSynchronize(s));
+    if (nnext < nact) depth = L + 1;   // somebody was placed at depth L+1
+    if (nnext >= nact && nact > 0 && L > 100000)
+    { cx_set_error("ADT build does not converge"); return -3; }
+    nact = nnext;
+    int* t = act; act = next; next = t;
+    L++;
+    if (L > 4096) { cx_set_error("ADT deeper than 4096 levels (degenerate/duplicate cells)"); return -3; }
+  }
+  CX_CUDA(cudaEventRecord(ctx->ev1, s));
+  CX_CUDA(cudaStreamSynchronize(s));
+  CX_CUDA(cudaGetLastError());
+  cudaEventElapsedTime(&z->build_ms, ctx->ev0, ctx->ev1);
+  z->depth = depth;
+  z->levels = L;
+  cudaFree(B.keys); cudaFree(B.lo); cudaFree(B.hi); cudaFree(B.cur); cudaFree(B.br);
+  cudaFree(S.actA); cudaFree(S.actB); cudaFree(S.counter);
+  if (depth + 2 > CX_STACK)
+  {
+    cx_set_error("ADT depth %d exceeds the traversal stack (%d)", depth, CX_STACK);
+    return -3;
+  }
+  return 0;
+}

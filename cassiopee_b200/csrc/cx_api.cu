@@ -1,0 +1,579 @@
+// cx_api.cu — C ABI of libcassiopee_b200.so (see include/cassiopee_b200.h).
+#include "cx_internal.h"
+#include "../../include/cassiopee_b200.h"
+#include <stdarg.h>
+#include <string.h>
+#include <algorithm>
+
+using namespace cx;
+
+static thread_local char g_err[1024] = "";
+
+void cx_set_error(const char* fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// from other translation units
+struct cx_result_dev {
+  int* rcv; int* dnr; int* typ; double* coefs; int* ext; int* orphan;
+  std::vector<long long> e_off, c_off, x_off;
+};
+void cx_zone_bbox_host(int ni, int nj, int nk, const double* x, const double* y, const double* z, double* bb);
+int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, const double* d_zr, int nz,
+                  const ZoneView* d_zones, const ZoneView* h_zones, int order, int nature, int penalty, int extrap,
+                  cx_result* R, cx_result_dev* D);
+int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long nptsR, int n, const int* donor,
+                  const int* rcv, const int* type, const double* coefs, long long ncoefs, cx_plan* P);
+int cx_plan_launch(cx_plan* P, int nvars, const double* const* dD, double* const* dR, double* dense, long long ld,
+                   int mode, cudaStream_t s);
+int cx_plan_launch_celln(cx_plan* P, const double* dCellND, double* dCellNR, cudaStream_t s);
+
+struct cx_result_full { cx_result R; cx_result_dev D; };
+
+extern "C" {
+
+const char* cx_last_error(void) { return g_err; }
+int cx_version(void) { return 100; }
+
+int cx_device_count(int* n)
+{
+  CX_CUDA(cudaGetDeviceCount(n));
+  return 0;
+}
+
+int cx_ctx_create(int device, cx_ctx** out)
+{
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+  {
+    cx_set_error("no CUDA device available (%s); libcassiopee_b200 has no CPU fallback",
+                 e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return -2;
+  }
+  if (device < 0 || device >= ndev) { cx_set_error("device %d out of range (0..%d)", device, ndev - 1); return -1; }
+  CX_CUDA(cudaSetDevice(device));
+  cx_ctx* c = new cx_ctx;
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  cudaDeviceProp prop;
+  CX_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  CX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CX_CUDA(cudaEventCreate(&c->ev0));
+  CX_CUDA(cudaEventCreate(&c->ev1));
+  c->pinned = nullptr; c->pinned_bytes = 0; c->launches = 0; c->nccl = nullptr;
+  *out = c;
+  return 0;
+}
+
+int cx_ctx_destroy(cx_ctx* c)
+{
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->nccl) cx_comm_destroy(c);
+  if (c->pinned) cudaFreeHost(c->pinned);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int cx_ctx_sync(cx_ctx* c)
+{
+  CX_CUDA(cudaSetDevice(c->device));
+  CX_CUDA(cudaStreamSynchronize(c->stream));
+  CX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+long long cx_ctx_launches(cx_ctx* c) { return c->launches; }
+
+int cx_ctx_info(cx_ctx* c, int* sm_count, size_t* free_bytes, size_t* total_bytes)
+{
+  CX_CUDA(cudaSetDevice(c->device));
+  if (sm_count) *sm_count = c->sm_count;
+  size_t f, t;
+  CX_CUDA(cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = f;
+  if (total_bytes) *total_bytes = t;
+  return 0;
+}
+
+int cx_event_record(cx_ctx* c, int which)
+{
+  CX_CUDA(cudaEventRecord(which == 0 ? c->ev0 : c->ev1, c->stream));
+  return 0;
+}
+
+int cx_event_elapsed_ms(cx_ctx* c, float* ms)
+{
+  CX_CUDA(cudaEventSynchronize(c->ev1));
+  CX_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return 0;
+}
+
+static void* g_flush = nullptr;
+int cx_flush_l2(cx_ctx* c)
+{
+  const size_t bytes = 256ull << 20;
+  if (!g_flush) CX_CUDA(cudaMalloc(&g_flush, bytes));
+  CX_CUDA(cudaMemsetAsync(g_flush, 1, bytes, c->stream));
+  return 0;
+}
+
+int cx_dev_alloc(cx_ctx* c, size_t bytes, void** dptr)
+{
+  CX_CUDA(cudaSetDevice(c->device));
+  CX_CUDA(cudaMalloc(dptr, bytes ? bytes : 8));
+  return 0;
+}
+int cx_dev_free(cx_ctx* c, void* dptr) { (void)c; CX_CUDA(cudaFree(dptr)); return 0; }
+int cx_dev_upload(cx_ctx* c, void* dptr, const void* host, size_t bytes)
+{
+  CX_CUDA(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, c->stream));
+  CX_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int cx_dev_download(cx_ctx* c, void* host, const void* dptr, size_t bytes)
+{
+  CX_CUDA(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CX_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int cx_dev_memset(cx_ctx* c, void* dptr, int value, size_t bytes)
+{
+  CX_CUDA(cudaMemsetAsync(dptr, value, bytes, c->stream));
+  return 0;
+}
+int cx_pinned_alloc(size_t bytes, void** hptr) { CX_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 8, cudaHostAllocDefault)); return 0; }
+int cx_pinned_free(void* hptr) { CX_CUDA(cudaFreeHost(hptr)); return 0; }
+
+/* ---- zones --------------------------------------------------------------- */
+int cx_zone_create(cx_ctx* c, int ni, int nj, int nk, const double* x, const double* y, const double* z,
+                   const double* cellN, cx_zone** out)
+{
+  if (ni < 2 || nj < 2) { cx_set_error("setInterpData: structured donor zones must be 3D or nk=1."); return -1; }
+  if (nk < 2) { cx_set_error("2-D donor zones (nk=1, type 22) are not supported by the device path"); return -4; }
+  if ((long long)ni * nj * nk > 2000000000ll) { cx_set_error("donor zone too large for int32 indices"); return -1; }
+  CX_CUDA(cudaSetDevice(c->device));
+  cx_zone* zn = new cx_zone;
+  memset(zn, 0, sizeof(*zn));
+  zn->ctx = c; zn->ni = ni; zn->nj = nj; zn->nk = nk;
+  zn->npts = ni * nj * nk;
+  zn->ncells = (ni - 1) * (nj - 1) * (nk - 1);
+  size_t nb = sizeof(double) * (size_t)zn->npts;
+  CX_CUDA(cudaMalloc(&zn->d_x, nb)); CX_CUDA(cudaMalloc(&zn->d_y, nb)); CX_CUDA(cudaMalloc(&zn->d_z, nb));
+  CX_CUDA(cudaMalloc(&zn->d_cellN, nb));
+  CX_CUDA(cudaMemcpyAsync(zn->d_x, x, nb, cudaMemcpyHostToDevice, c->stream));
+  CX_CUDA(cudaMemcpyAsync(zn->d_y, y, nb, cudaMemcpyHostToDevice, c->stream));
+  CX_CUDA(cudaMemcpyAsync(zn->d_z, z, nb, cudaMemcpyHostToDevice, c->stream));
+  cx_zone_bbox_host(ni, nj, nk, x, y, z, zn->bbox);
+  *out = zn;
+  int rc = cx_zone_set_celln(zn, cellN);
+  if (rc == 0) rc = cx_build_adt(zn);
+  if (rc != 0) { cx_zone_destroy(zn); *out = nullptr; return rc; }
+  return 0;
+}
+
+namespace { __global__ void k_fill(double* p, double v, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; } }
+
+int cx_zone_set_celln(cx_zone* zn, const double* cellN)
+{
+  cx_ctx* c = zn->ctx;
+  if (cellN)
+  {
+    CX_CUDA(cudaMemcpyAsync(zn->d_cellN, cellN, sizeof(double) * (size_t)zn->npts, cudaMemcpyHostToDevice, c->stream));
+    CX_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  else { k_fill<<<cx_grid(zn->npts, 256), 256, 0, c->stream>>>(zn->d_cellN, 1.0, zn->npts); c->launches++; }
+  return 0;
+}
+
+int cx_zone_info(cx_zone* zn, double bbox[6], int* ncells, int* depth, float* build_ms)
+{
+  if (bbox) for (int i = 0; i < 6; i++) bbox[i] = zn->bbox[i];
+  if (ncells) *ncells = zn->ncells;
+  if (depth) *depth = zn->depth;
+  if (build_ms) *build_ms = zn->build_ms;
+  return 0;
+}
+
+static ZoneView make_view(const cx_zone* zn)
+{
+  ZoneView V;
+  V.x = zn->d_x; V.y = zn->d_y; V.z = zn->d_z; V.cellN = zn->d_cellN; V.nodes = zn->d_nodes;
+  V.ni = zn->ni; V.nj = zn->nj; V.nk = zn->nk; V.ncells = zn->ncells; V.depth = zn->depth;
+  for (int i = 0; i < 6; i++) V.bbox[i] = zn->bbox[i];
+  return V;
+}
+
+namespace {
+__global__ void k_candidates(ZoneView Z, double x, double y, double z, double alphaTol, int* out, int cap, int* n)
+{
+  int cnt = 0;
+  if (!zone_reject(Z, x, y, z, alphaTol))
+  {
+    AdtQuery q;
+    query_init(q, Z, x, y, z, alphaTol);
+    int c, nid, nv = 0;
+    while ((c = query_next(q, Z.nodes, &nid, &nv)) >= 0) { if (cnt < cap) out[cnt] = c; cnt++; }
+  }
+  *n = cnt;
+}
+}
+
+int cx_zone_candidates(cx_zone* zn, double x, double y, double z, double alphaTol, int* out, int cap, int* n)
+{
+  cx_ctx* c = zn->ctx;
+  int *d_out, *d_n;
+  CX_CUDA(cudaMalloc(&d_out, sizeof(int) * (size_t)std::max(cap, 1)));
+  CX_CUDA(cudaMalloc(&d_n, sizeof(int)));
+  k_candidates<<<1, 1, 0, c->stream>>>(make_view(zn), x, y, z, alphaTol, d_out, cap, d_n);
+  c->launches++;
+  CX_CUDA(cudaMemcpyAsync(n, d_n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CX_CUDA(cudaStreamSynchronize(c->stream));
+  int m = std::min(*n, cap);
+  if (m > 0) CX_CUDA(cudaMemcpy(out, d_out, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost));
+  cudaFree(d_out); cudaFree(d_n);
+  return 0;
+}
+
+int cx_zone_export_adt(cx_zone* zn, void* nodes_out, size_t bytes)
+{
+  size_t need = sizeof(AdtNode) * (size_t)zn->ncells;
+  if (bytes < need) { cx_set_error("export buffer too small: need %zu bytes", need); return -1; }
+  CX_CUDA(cudaMemcpy(nodes_out, zn->d_nodes, need, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int cx_zone_destroy(cx_zone* zn)
+{
+  if (!zn) return 0;
+  cudaFree(zn->d_x); cudaFree(zn->d_y); cudaFree(zn->d_z); cudaFree(zn->d_cellN); cudaFree(zn->d_nodes);
+  delete zn;
+  return 0;
+}
+
+/* ---- setInterpData --------------------------------------------------------- */
+int cx_set_interp_data_dev(cx_ctx* c, int nrcv, const double* d_xr, const double* d_yr, const double* d_zr, int nz,
+                           cx_zone* const* zones, int order, int nature, int penalty, int extrap, cx_result** out)
+{
+  if (order != 2 && order != 3 && order != 5)
+  { cx_set_error("setInterpData: order %d not supported on the device (2, 3 or 5)", order); return -4; }
+  if (nz <= 0) { cx_set_error("setInterpData: no valid donor zone found."); return -1; }
+  CX_CUDA(cudaSetDevice(c->device));
+  std::vector<ZoneView> hv(nz);
+  for (int i = 0; i < nz; i++)
+  {
+    if (!zones[i] || !zones[i]->d_nodes) { cx_set_error("setInterpData: donor zone %d has no ADT", i); return -1; }
+    hv[i] = make_view(zones[i]);
+  }
+  ZoneView* d_zones;
+  CX_CUDA(cudaMalloc(&d_zones, sizeof(ZoneView) * (size_t)nz));
+  CX_CUDA(cudaMemcpyAsync(d_zones, hv.data(), sizeof(ZoneView) * (size_t)nz, cudaMemcpyHostToDevice, c->stream));
+  cx_result_full* F = new cx_result_full;
+  F->R.ctx = c;
+  int rc = cx_search_run(c, nrcv, d_xr, d_yr, d_zr, nz, d_zones, hv.data(), order, nature, penalty, extrap, &F->R, &F->D);
+  cudaFree(d_zones);
+  if (rc != 0) { cx_result_destroy(&F->R); return rc; }
+  *out = &F->R;
+  return 0;
+}
+
+int cx_set_interp_data(cx_ctx* c, int nrcv, const double* xr, const double* yr, const double* zr, int nz,
+                       cx_zone* const* zones, int order, int nature, int penalty, int extrap, cx_result** out)
+{
+  CX_CUDA(cudaSetDevice(c->device));
+  double *dx = nullptr, *dy = nullptr, *dz = nullptr;
+  size_t nb = sizeof(double) * (size_t)std::max(nrcv, 1);
+  CX_CUDA(cudaMalloc(&dx, nb)); CX_CUDA(cudaMalloc(&dy, nb)); CX_CUDA(cudaMalloc(&dz, nb));
+  if (nrcv > 0)
+  {
+    CX_CUDA(cudaMemcpyAsync(dx, xr, sizeof(double) * (size_t)nrcv, cudaMemcpyHostToDevice, c->stream));
+    CX_CUDA(cudaMemcpyAsync(dy, yr, sizeof(double) * (size_t)nrcv, cudaMemcpyHostToDevice, c->stream));
+    CX_CUDA(cudaMemcpyAsync(dz, zr, sizeof(double) * (size_t)nrcv, cudaMemcpyHostToDevice, c->stream));
+  }
+  int rc = cx_set_interp_data_dev(c, nrcv, dx, dy, dz, nz, zones, order, nature, penalty, extrap, out);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(dx); cudaFree(dy); cudaFree(dz);
+  return rc;
+}
+
+int cx_result_sizes(cx_result* R, int* cnt, int* ncoef, int* nextrap, int* norphan)
+{
+  for (int z = 0; z < R->nz; z++)
+  {
+    if (cnt) cnt[z] = R->cnt[z];
+    if (ncoef) ncoef[z] = R->ncoef[z];
+    if (nextrap) nextrap[z] = R->nextrap[z];
+  }
+  if (norphan) *norphan = R->norphan;
+  return 0;
+}
+
+int cx_result_fetch_zone(cx_result* R, int z, int* rcv, int* donor, int* type, double* coefs, int* extrap)
+{
+  cx_result_dev& D = ((cx_result_full*)R)->D;
+  if (z < 0 || z >= R->nz) { cx_set_error("zone %d out of range", z); return -1; }
+  size_t n = (size_t)R->cnt[z];
+  if (n > 0)
+  {
+    if (rcv) CX_CUDA(cudaMemcpy(rcv, D.rcv + D.e_off[z], sizeof(int) * n, cudaMemcpyDeviceToHost));
+    if (donor) CX_CUDA(cudaMemcpy(donor, D.dnr + D.e_off[z], sizeof(int) * n, cudaMemcpyDeviceToHost));
+    if (type) CX_CUDA(cudaMemcpy(type, D.typ + D.e_off[z], sizeof(int) * n, cudaMemcpyDeviceToHost));
+    if (coefs) CX_CUDA(cudaMemcpy(coefs, D.coefs + D.c_off[z], sizeof(double) * (size_t)R->ncoef[z], cudaMemcpyDeviceToHost));
+  }
+  if (extrap && R->nextrap[z] > 0)
+    CX_CUDA(cudaMemcpy(extrap, D.ext + D.x_off[z], sizeof(int) * (size_t)R->nextrap[z], cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int cx_result_fetch_orphans(cx_result* R, int* orphan)
+{
+  cx_result_dev& D = ((cx_result_full*)R)->D;
+  if (R->norphan > 0) CX_CUDA(cudaMemcpy(orphan, D.orphan, sizeof(int) * (size_t)R->norphan, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int cx_result_fetch_raw(cx_result* R, int* noblk, int* type, int* dind, int* isext, double* cf)
+{
+  size_t n = (size_t)R->nrcv;
+  if (n == 0) return 0;
+  if (noblk) CX_CUDA(cudaMemcpy(noblk, R->d_noblk, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  if (type) CX_CUDA(cudaMemcpy(type, R->d_type, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  if (dind) CX_CUDA(cudaMemcpy(dind, R->d_dind, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  if (isext) CX_CUDA(cudaMemcpy(isext, R->d_isext, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  if (cf) CX_CUDA(cudaMemcpy(cf, R->d_cf, sizeof(double) * n * R->ncfmax, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int cx_result_stats(cx_result* R, double* out)
+{
+  out[0] = R->search_ms; out[1] = R->extrap_ms;
+  out[2] = (double)R->stats[0]; out[3] = (double)R->stats[1]; out[4] = (double)R->ncfmax;
+  out[5] = (double)R->stats[2]; out[6] = 0; out[7] = 0;
+  return 0;
+}
+
+int cx_result_destroy(cx_result* R)
+{
+  if (!R) return 0;
+  cx_result_full* F = (cx_result_full*)R;
+  cudaFree(R->d_noblk); cudaFree(R->d_type); cudaFree(R->d_dind); cudaFree(R->d_isext); cudaFree(R->d_cf);
+  cudaFree(F->D.rcv); cudaFree(F->D.dnr); cudaFree(F->D.typ); cudaFree(F->D.coefs); cudaFree(F->D.ext);
+  cudaFree(F->D.orphan);
+  delete F;
+  return 0;
+}
+
+/* ---- transfers ------------------------------------------------------------- */
+struct cx_plan_full {
+  cx_plan P;
+  // scratch for the host-pointer entry points
+  double* d_fields; size_t fields_cap;
+  double* d_dense; size_t dense_cap;
+  double* h_dense; size_t hdense_cap;   // pinned
+  std::vector<int> h_rcv;               // original-order receptor indices (host scatter)
+};
+
+int cx_plan_create(cx_ctx* c, int imd, int jmd, int kmd, long long nptsR, int n, const int* donor, const int* rcv,
+                   const int* type, const double* coefs, long long ncoefs, cx_plan** out)
+{
+  CX_CUDA(cudaSetDevice(c->device));
+  cx_plan_full* F = new cx_plan_full;
+  F->d_fields = nullptr; F->fields_cap = 0; F->d_dense = nullptr; F->dense_cap = 0; F->h_dense = nullptr; F->hdense_cap = 0;
+  int rc = cx_plan_build(c, imd, jmd, (long long)imd * jmd * kmd, nptsR, n, donor, rcv, type, coefs, ncoefs, &F->P);
+  if (rc != 0) { cx_plan_destroy(&F->P); return rc; }
+  F->h_rcv.assign(rcv, rcv + n);
+  *out = &F->P;
+  return 0;
+}
+
+static int ensure(double** p, size_t* cap, size_t need, bool pinned)
+{
+  if (*cap >= need) return 0;
+  if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; }
+  if (pinned) CX_CUDA(cudaHostAlloc((void**)p, need, cudaHostAllocDefault));
+  else CX_CUDA(cudaMalloc((void**)p, need));
+  *cap = need;
+  return 0;
+}
+
+static int upload_fields(cx_plan_full* F, int nvars, const double* const* fieldD, std::vector<const double*>& dptrs)
+{
+  cx_plan* P = &F->P; cx_ctx* c = P->ctx;
+  size_t per = (size_t)P->nptsD;
+  CX_CHECK(ensure(&F->d_fields, &F->fields_cap, sizeof(double) * per * nvars, false));
+  dptrs.resize(nvars);
+  for (int v = 0; v < nvars; v++)
+  {
+    CX_CUDA(cudaMemcpyAsync(F->d_fields + per * v, fieldD[v], sizeof(double) * per, cudaMemcpyHostToDevice, c->stream));
+    dptrs[v] = F->d_fields + per * v;
+  }
+  return 0;
+}
+
+int cx_transferD(cx_plan* P, int nvars, const double* const* fieldD, double* out)
+{
+  cx_plan_full* F = (cx_plan_full*)P; cx_ctx* c = P->ctx;
+  if (P->n == 0 || nvars == 0) return 0;
+  CX_CUDA(cudaSetDevice(c->device));
+  std::vector<const double*> dptrs;
+  CX_CHECK(upload_fields(F, nvars, fieldD, dptrs));
+  size_t nd = (size_t)P->n * nvars;
+  CX_CHECK(ensure(&F->d_dense, &F->dense_cap, sizeof(double) * nd, false));
+  CX_CHECK(cx_plan_launch(P, nvars, dptrs.data(), nullptr, F->d_dense, P->n, 1, c->stream));
+  CX_CUDA(cudaMemcpyAsync(out, F->d_dense, sizeof(double) * nd, cudaMemcpyDeviceToHost, c->stream));
+  CX_CUDA(cudaStreamSynchronize(c->stream));
+  CX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int cx_transfer(cx_plan* P, int nvars, const double* const* fieldD, double* const* fieldR)
+{
+  cx_plan_full* F = (cx_plan_full*)P;
+  if (P->n == 0 || nvars == 0) return 0;
+  size_t nd = (size_t)P->n * nvars;
+  CX_CHECK(ensure(&F->h_dense, &F->hdense_cap, sizeof(double) * nd, true));
+  CX_CHECK(cx_transferD(P, nvars, fieldD, F->h_dense));
+  // host scatter in entry order (duplicates: last wins, like the reference's serial walk)
+  const int n = P->n;
+  const int* rcv = F->h_rcv.data();
+  for (int v = 0; v < nvars; v++)
+  {
+    double* fr = fieldR[v];
+    const double* src = F->h_dense + (size_t)v * n;
+    for (int e = 0; e < n; e++) fr[rcv[e]] = src[e];
+  }
+  return 0;
+}
+
+int cx_transfer_celln(cx_plan* P, const double* cellND, double* cellNR)
+{
+  cx_ctx* c = P->ctx;
+  if (P->n == 0) return 0;
+  CX_CUDA(cudaSetDevice(c->device));
+  double *dD, *dR;
+  CX_CUDA(cudaMalloc(&dD, sizeof(double) * (size_t)P->nptsD));
+  CX_CUDA(cudaMalloc(&dR, sizeof(double) * (size_t)P->nptsR));
+  CX_CUDA(cudaMemcpyAsync(dD, cellND, sizeof(double) * (size_t)P->nptsD, cudaMemcpyHostToDevice, c->stream));
+  CX_CUDA(cudaMemcpyAsync(dR, cellNR, sizeof(double) * (size_t)P->nptsR, cudaMemcpyHostToDevice, c->stream));
+  CX_CHECK(cx_plan_launch_celln(P, dD, dR, c->stream));
+  CX_CUDA(cudaMemcpyAsync(cellNR, dR, sizeof(double) * (size_t)P->nptsR, cudaMemcpyDeviceToHost, c->stream));
+  CX_CUDA(cudaStreamSynchronize(c->stream));
+  CX_CUDA(cudaGetLastError());
+  cudaFree(dD); cudaFree(dR);
+  return 0;
+}
+
+int cx_transfer_dev(cx_plan* P, int nvars, const double* const* d_fieldD, double* const* d_fieldR)
+{
+  if (P->n == 0 || nvars == 0) return 0;
+  return cx_plan_launch(P, nvars, d_fieldD, d_fieldR, nullptr, 0, 0, P->ctx->stream);
+}
+
+int cx_transferD_dev(cx_plan* P, int nvars, const double* const* d_fieldD, double* d_out, long long ld)
+{
+  if (P->n == 0 || nvars == 0) return 0;
+  return cx_plan_launch(P, nvars, d_fieldD, nullptr, d_out, ld, 1, P->ctx->stream);
+}
+
+int cx_transfer_celln_dev(cx_plan* P, const double* d_cellND, double* d_cellNR)
+{
+  if (P->n == 0) return 0;
+  return cx_plan_launch_celln(P, d_cellND, d_cellNR, P->ctx->stream);
+}
+
+namespace {
+struct RPtrs { double* r[16]; };
+__global__ void k_scatter(int n, int nvars, const double* __restrict__ in, long long ld, const int* __restrict__ rcv, RPtrs R)
+{
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  int r = rcv[e];
+  for (int v = 0; v < nvars; v++) R.r[v][r] = in[(size_t)v * ld + e];
+}
+__global__ void k_mark(int m, int sten_o, int imd, int imdjmd, const int* __restrict__ donor, unsigned char* mark)
+{
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m) return;
+  int d0 = donor[e];
+  for (int kk = 0; kk < sten_o; kk++) for (int jj = 0; jj < sten_o; jj++) for (int ii = 0; ii < sten_o; ii++)
+    mark[d0 + ii + jj * imd + kk * imdjmd] = 1;
+}
+__global__ void k_count(long long n, const unsigned char* mark, unsigned long long* cnt)
+{
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned v = (i < n && mark[i]) ? 1u : 0u;
+  unsigned b = __ballot_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(cnt, (unsigned long long)__popc(b));
+}
+}
+
+int cx_scatter_dev(cx_ctx* c, int nvars, const double* d_in, long long ld, int n, const int* d_rcv, double* const* d_fieldR)
+{
+  if (n == 0) return 0;
+  for (int v0 = 0; v0 < nvars; v0 += 16)
+  {
+    int nv = std::min(16, nvars - v0);
+    RPtrs R; for (int v = 0; v < nv; v++) R.r[v] = d_fieldR[v0 + v];
+    k_scatter<<<cx_grid(n, 256), 256, 0, c->stream>>>(n, nv, d_in + (size_t)v0 * ld, ld, d_rcv, R);
+    c->launches++;
+  }
+  return 0;
+}
+
+int cx_plan_info(cx_plan* P, int* n, int* ngroups, long long* alg_fixed, long long* distinct)
+{
+  if (n) *n = P->n;
+  if (ngroups) *ngroups = P->ngroups;
+  if (alg_fixed) *alg_fixed = P->alg_bytes_fixed;
+  if (distinct)
+  {
+    if (P->distinct_nodes < 0 && P->n > 0)
+    {
+      cx_ctx* c = P->ctx;
+      unsigned char* mark; unsigned long long* cnt;
+      CX_CUDA(cudaMalloc(&mark, (size_t)P->nptsD));
+      CX_CUDA(cudaMalloc(&cnt, sizeof(unsigned long long)));
+      CX_CUDA(cudaMemsetAsync(mark, 0, (size_t)P->nptsD, c->stream));
+      CX_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
+      for (auto& G : P->groups)
+      {
+        int o = G.type == 1 ? 1 : G.type == 2 ? 2 : G.type == 3 ? 3 : 5;
+        k_mark<<<cx_grid(G.n, 256), 256, 0, c->stream>>>(G.n, o, P->imd, P->imd * P->jmd, P->d_donor + G.first, mark);
+        c->launches++;
+      }
+      k_count<<<cx_grid(P->nptsD, 256), 256, 0, c->stream>>>(P->nptsD, mark, cnt);
+      c->launches++;
+      unsigned long long h = 0;
+      CX_CUDA(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+      CX_CUDA(cudaStreamSynchronize(c->stream));
+      cudaFree(mark); cudaFree(cnt);
+      P->distinct_nodes = (long long)h;
+    }
+    *distinct = P->n > 0 ? P->distinct_nodes : 0;
+  }
+  return 0;
+}
+
+int cx_plan_destroy(cx_plan* P)
+{
+  if (!P) return 0;
+  cx_plan_full* F = (cx_plan_full*)P;
+  for (auto& G : P->groups) cudaFree(G.d_cf);
+  cudaFree(P->d_donor); cudaFree(P->d_rcv); cudaFree(P->d_pos);
+  if (F->d_fields) cudaFree(F->d_fields);
+  if (F->d_dense) cudaFree(F->d_dense);
+  if (F->h_dense) cudaFreeHost(F->h_dense);
+  delete F;
+  return 0;
+}
+
+}  // extern "C"

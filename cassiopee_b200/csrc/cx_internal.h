@@ -1,0 +1,88 @@
+// cx_internal.h — host-side objects behind the C ABI (include/cassiopee_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "cx_core.cuh"
+
+void cx_set_error(const char* fmt, ...);
+
+#define CX_CUDA(call)                                                                  \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      cx_set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, cudaGetErrorName(e_), \
+                   cudaGetErrorString(e_));                                            \
+      return -2;                                                                       \
+    }                                                                                  \
+  } while (0)
+
+#define CX_CHECK(rc_)                 \
+  do {                                \
+    int r__ = (rc_);                  \
+    if (r__ != 0) return r__;         \
+  } while (0)
+
+struct cx_ctx {
+  int device;
+  int sm_count;
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+  // pinned staging buffer for host<->device copies
+  void* pinned; size_t pinned_bytes;
+  // counters (kernels launched by this library since creation)
+  long long launches;
+  // last timed kernel durations (ms), written by entry points that time themselves
+  float last_kernel_ms;
+  void* nccl;   // cx_comm*
+};
+
+struct cx_zone {
+  cx_ctx* ctx;
+  int ni, nj, nk, npts, ncells;
+  double* d_x; double* d_y; double* d_z; double* d_cellN;   // device coordinates + cellN
+  cx::AdtNode* d_nodes;
+  int depth;
+  int levels;
+  double bbox[6];
+  float build_ms;
+};
+
+struct cx_result {
+  cx_ctx* ctx;
+  int nrcv, nz, ncfmax;
+  // per-receptor table (device)
+  int* d_noblk; int* d_type; int* d_dind; int* d_isext;
+  double* d_cf;       // [ncfmax][nrcv] SoA
+  // per-zone compaction
+  std::vector<int> cnt, ncoef, nextrap;
+  int norphan;
+  // search statistics (sum over receptors): nodes visited, candidates, tetra solves
+  unsigned long long stats[4];
+  float search_ms, extrap_ms, total_ms;
+};
+
+struct cx_plan {
+  cx_ctx* ctx;
+  int imd, jmd, nptsD, nptsR;
+  int n;                // entries
+  int ngroups;          // type groups
+  // entries regrouped by type (stable), SoA coefficients per group
+  struct Group { int type, ncf, sten, n, first; double* d_cf; };
+  std::vector<Group> groups;
+  int* d_donor; int* d_rcv; int* d_pos;   // regrouped order; pos = original entry position
+  long long alg_bytes_fixed;              // sum over entries of (8*ncf + 12)
+  long long distinct_nodes;               // U (computed on demand)
+  float last_ms;
+};
+
+// scan utilities (cx_scan.cu)
+int cx_exclusive_scan_u64(cx_ctx* ctx, const unsigned long long* d_in, unsigned long long* d_out, int n,
+                          unsigned long long* h_total);
+
+// ADT build (cx_adt.cu)
+int cx_build_adt(cx_zone* z);
+
+static inline int cx_grid(long long n, int block) { return (int)((n + block - 1) / block); }

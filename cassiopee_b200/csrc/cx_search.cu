@@ -1,0 +1,254 @@
+// cx_search.cu — setInterpData on the device: one thread per receptor.
+//
+// Replaces the OpenMP receptor loop of K_CONNECTOR::setInterpData
+// (Connector/Connector/setInterpData.cpp:978-1114) and everything below it:
+//   K_INTERP::getInterpolationCell   KCore/KCore/Interp/Interp.cpp:81-165
+//   K_INTERP::getInterpolationData   KCore/KCore/Interp/Interp2.cpp:185-342 (O2CF branch)
+//   cross-zone choice                KCore/KCore/Interp/commonTypesForExtrapAndInterp.h:1-36
+//   coincident collapse (type 1)     KCore/KCore/Interp/commonCheckCoefs.h:1-93
+//   K_INTERP::getExtrapolationCell   KCore/KCore/Interp/Interp.cpp:282-360, Interp2.cpp:84-137
+// and the per-donor-zone packing (setInterpData.cpp:1183-1272), done here by a
+// flag/scan/scatter so every zone's entries come out in ascending receptor
+// order exactly like the reference's static-schedule chunk concatenation.
+#include "cx_internal.h"
+
+using namespace cx;
+
+namespace {
+
+struct RcvTable {
+  int* noblk; int* type; int* dind; int* isext;
+  double* cf;   // [ncfmax][n]
+  int n, ncfmax;
+};
+
+__device__ __forceinline__ void warp_add_stats(unsigned long long* g, const SearchStats& st)
+{
+  unsigned long long a = st.nvisit, b = st.ncand, c = st.ntet;
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    a += __shfl_down_sync(0xffffffffu, a, o);
+    b += __shfl_down_sync(0xffffffffu, b, o);
+    c += __shfl_down_sync(0xffffffffu, c, o);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&g[0], a); atomicAdd(&g[1], b); atomicAdd(&g[2], c); }
+}
+
+// Order-2 interpolation, all donor zones fused in one launch.
+__global__ void __launch_bounds__(128)
+k_interp_o2(int n, const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr,
+            int nz, const ZoneView* __restrict__ zones, int nature, int penalty, RcvTable T,
+            unsigned long long* gstats)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  SearchStats st; st.nvisit = 0; st.ncand = 0; st.ntet = 0;
+  if (r < n)
+  {
+    RcvOut o;
+    interp_o2_receptor(xr[r], yr[r], zr[r], nz, zones, nature, penalty, o, &st);
+    T.noblk[r] = o.noblk; T.type[r] = o.type; T.dind[r] = o.dind; T.isext[r] = 0;
+    for (int i = 0; i < 8; i++) T.cf[(size_t)i * n + r] = o.cf[i];
+  }
+  if (gstats) warp_add_stats(gstats, st);
+}
+
+// Extrapolation pass over the receptors that found no donor.
+__global__ void __launch_bounds__(128)
+k_extrap(int nfail, const int* __restrict__ fail, const double* __restrict__ xr, const double* __restrict__ yr,
+         const double* __restrict__ zr, int nz, const ZoneView* __restrict__ zones, int nature, int penalty,
+         RcvTable T, unsigned long long* gstats)
+{
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  SearchStats st; st.nvisit = 0; st.ncand = 0; st.ntet = 0;
+  if (a < nfail)
+  {
+    int r = fail[a];
+    RcvOut o;
+    extrap_receptor(xr[r], yr[r], zr[r], nz, zones, nature, penalty, o, &st);
+    if (o.noblk > 0)
+    {
+      T.noblk[r] = o.noblk; T.type[r] = o.type; T.dind[r] = o.dind; T.isext[r] = 1;
+      for (int i = 0; i < 8; i++) T.cf[(size_t)i * T.n + r] = o.cf[i];
+    }
+  }
+  if (gstats) warp_add_stats(gstats, st);
+}
+
+__device__ __forceinline__ int ncf_of_type(int t)
+{ // SIZECF, Connector/Connector/connector.h:27-37 (structured donors)
+  return t == 1 ? 1 : t == 2 ? 8 : t == 3 ? 9 : t == 5 ? 15 : t == 44 ? 12 : t == 22 ? 4 : 0;
+}
+
+// flag pass: which = zone (1-based) to select; mode 0: entries (count<<32|ncoef),
+// mode 1: extrapolated entries of that zone, mode 2: orphans (noblk==0)
+__global__ void k_flags(int n, const int* __restrict__ noblk, const int* __restrict__ type,
+                        const int* __restrict__ isext, int which, int mode, unsigned long long* __restrict__ f)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  unsigned long long v = 0;
+  int b = noblk[r];
+  if (mode == 0) { if (b == which) v = (1ull << 32) | (unsigned long long)ncf_of_type(type[r]); }
+  else if (mode == 1) { if (b == which && isext[r] == 1) v = 1; }
+  else { if (b == 0) v = 1; }
+  f[r] = v;
+}
+
+__global__ void k_scatter_entries(int n, RcvTable T, int which, const unsigned long long* __restrict__ f,
+                                  const unsigned long long* __restrict__ pos, int* __restrict__ rcv,
+                                  int* __restrict__ dnr, int* __restrict__ typ, double* __restrict__ coefs)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  if (f[r] == 0) return;
+  unsigned long long p = pos[r];
+  int e = (int)(p >> 32);
+  size_t c = (size_t)(p & 0xffffffffull);
+  int t = T.type[r];
+  rcv[e] = r; dnr[e] = T.dind[r]; typ[e] = t;
+  int ncf = ncf_of_type(t);
+  for (int k = 0; k < ncf; k++) coefs[c + k] = T.cf[(size_t)k * n + r];
+}
+
+__global__ void k_scatter_index(int n, const unsigned long long* __restrict__ f,
+                                const unsigned long long* __restrict__ pos, int* __restrict__ out)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  if (f[r]) out[(int)pos[r]] = r;
+}
+
+}  // namespace
+
+struct cx_result_dev {
+  // packed outputs, zones concatenated
+  int* rcv; int* dnr; int* typ; double* coefs; int* ext; int* orphan;
+  std::vector<long long> e_off, c_off, x_off;
+};
+
+extern int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_xr, const double* d_yr,
+                                const double* d_zr, int nz, const ZoneView* d_zones, const ZoneView* h_zones,
+                                int nature, int penalty, int* noblk, int* type, int* dind, double* cf, int ncfmax,
+                                unsigned long long* d_stats);
+
+int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, const double* d_zr, int nz,
+                  const ZoneView* d_zones, const ZoneView* h_zones, int order, int nature, int penalty, int extrap,
+                  cx_result* R, cx_result_dev* D)
+{
+  cudaStream_t s = ctx->stream;
+  const int ncfmax = (order == 3) ? 9 : (order == 5) ? 15 : 8;
+  R->nrcv = n; R->nz = nz; R->ncfmax = ncfmax;
+  R->cnt.assign(nz, 0); R->ncoef.assign(nz, 0); R->nextrap.assign(nz, 0); R->norphan = 0;
+  for (int i = 0; i < 4; i++) R->stats[i] = 0;
+  D->e_off.assign(nz + 1, 0); D->c_off.assign(nz + 1, 0); D->x_off.assign(nz + 1, 0);
+  D->rcv = D->dnr = D->typ = D->ext = D->orphan = nullptr; D->coefs = nullptr;
+  R->d_noblk = R->d_type = R->d_dind = R->d_isext = nullptr; R->d_cf = nullptr;
+  if (n == 0) return 0;
+  size_t N = n;
+  CX_CUDA(cudaMalloc(&R->d_noblk, sizeof(int) * N));
+  CX_CUDA(cudaMalloc(&R->d_type, sizeof(int) * N));
+  CX_CUDA(cudaMalloc(&R->d_dind, sizeof(int) * N));
+  CX_CUDA(cudaMalloc(&R->d_isext, sizeof(int) * N));
+  CX_CUDA(cudaMalloc(&R->d_cf, sizeof(double) * N * ncfmax));
+  unsigned long long* d_stats;
+  CX_CUDA(cudaMalloc(&d_stats, sizeof(unsigned long long) * 4));
+  CX_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * 4, s));
+  RcvTable T{R->d_noblk, R->d_type, R->d_dind, R->d_isext, R->d_cf, n, ncfmax};
+  const int TB = 128;
+
+  CX_CUDA(cudaEventRecord(ctx->ev0, s));
+  if (order == 2)
+  {
+    k_interp_o2<<<cx_grid(n, TB), TB, 0, s>>>(n, d_xr, d_yr, d_zr, nz, d_zones, nature, penalty, T, d_stats);
+    ctx->launches++;
+  }
+  else
+  {
+    CX_CUDA(cudaMemsetAsync(R->d_isext, 0, sizeof(int) * N, s));
+    CX_CHECK(cx_lagrange_pipeline(ctx, order, n, d_xr, d_yr, d_zr, nz, d_zones, h_zones, nature, penalty,
+                                  R->d_noblk, R->d_type, R->d_dind, R->d_cf, ncfmax, d_stats));
+  }
+  CX_CUDA(cudaEventRecord(ctx->ev1, s));
+
+  unsigned long long *d_f, *d_p;
+  CX_CUDA(cudaMalloc(&d_f, sizeof(unsigned long long) * N));
+  CX_CUDA(cudaMalloc(&d_p, sizeof(unsigned long long) * N));
+  const int TB2 = 256;
+  unsigned long long tot = 0;
+
+  // extrapolation over the orphans of the interpolation pass
+  cudaEvent_t evx0, evx1;
+  cudaEventCreate(&evx0); cudaEventCreate(&evx1);
+  cudaEventRecord(evx0, s);
+  if (extrap == 1)
+  {
+    k_flags<<<cx_grid(n, TB2), TB2, 0, s>>>(n, R->d_noblk, R->d_type, R->d_isext, 0, 2, d_f);
+    ctx->launches++;
+    CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, n, &tot));
+    int nfail = (int)tot;
+    if (nfail > 0)
+    {
+      int* d_fail;
+      CX_CUDA(cudaMalloc(&d_fail, sizeof(int) * (size_t)nfail));
+      k_scatter_index<<<cx_grid(n, TB2), TB2, 0, s>>>(n, d_f, d_p, d_fail);
+      k_extrap<<<cx_grid(nfail, TB), TB, 0, s>>>(nfail, d_fail, d_xr, d_yr, d_zr, nz, d_zones, nature, penalty, T,
+                                                d_stats);
+      ctx->launches += 2;
+      CX_CUDA(cudaStreamSynchronize(s));
+      cudaFree(d_fail);
+    }
+  }
+  cudaEventRecord(evx1, s);
+
+  // per-zone packing
+  CX_CUDA(cudaMalloc(&D->rcv, sizeof(int) * N));
+  CX_CUDA(cudaMalloc(&D->dnr, sizeof(int) * N));
+  CX_CUDA(cudaMalloc(&D->typ, sizeof(int) * N));
+  CX_CUDA(cudaMalloc(&D->ext, sizeof(int) * N));
+  CX_CUDA(cudaMalloc(&D->orphan, sizeof(int) * N));
+  CX_CUDA(cudaMalloc(&D->coefs, sizeof(double) * N * ncfmax));
+  long long eo = 0, co = 0, xo = 0;
+  for (int z = 0; z < nz; z++)
+  {
+    D->e_off[z] = eo; D->c_off[z] = co; D->x_off[z] = xo;
+    k_flags<<<cx_grid(n, TB2), TB2, 0, s>>>(n, R->d_noblk, R->d_type, R->d_isext, z + 1, 0, d_f);
+    ctx->launches++;
+    CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, n, &tot));
+    int cnt = (int)(tot >> 32);
+    long long nco = (long long)(tot & 0xffffffffull);
+    R->cnt[z] = cnt; R->ncoef[z] = (int)nco;
+    if (cnt > 0)
+    {
+      k_scatter_entries<<<cx_grid(n, TB2), TB2, 0, s>>>(n, T, z + 1, d_f, d_p, D->rcv + eo, D->dnr + eo, D->typ + eo,
+                                                       D->coefs + co);
+      ctx->launches++;
+      if (extrap == 1)
+      {
+        k_flags<<<cx_grid(n, TB2), TB2, 0, s>>>(n, R->d_noblk, R->d_type, R->d_isext, z + 1, 1, d_f);
+        ctx->launches++;
+        CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, n, &tot));
+        R->nextrap[z] = (int)tot;
+        if (tot > 0)
+        {
+          k_scatter_index<<<cx_grid(n, TB2), TB2, 0, s>>>(n, d_f, d_p, D->ext + xo);
+          ctx->launches++;
+        }
+      }
+    }
+    eo += cnt; co += nco; xo += R->nextrap[z];
+  }
+  D->e_off[nz] = eo; D->c_off[nz] = co; D->x_off[nz] = xo;
+  k_flags<<<cx_grid(n, TB2), TB2, 0, s>>>(n, R->d_noblk, R->d_type, R->d_isext, 0, 2, d_f);
+  ctx->launches++;
+  CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, n, &tot));
+  R->norphan = (int)tot;
+  if (tot > 0) { k_scatter_index<<<cx_grid(n, TB2), TB2, 0, s>>>(n, d_f, d_p, D->orphan); ctx->launches++; }
+  CX_CUDA(cudaStreamSynchronize(s));
+  CX_CUDA(cudaGetLastError());
+  cudaEventElapsedTime(&R->search_ms, ctx->ev0, ctx->ev1);
+  cudaEventElapsedTime(&R->extrap_ms, evx0, evx1);
+  cudaEventDestroy(evx0); cudaEventDestroy(evx1);
+  CX_CUDA(cudaMemcpy(R->stats, d_stats, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost));
+  cudaFree(d_stats); cudaFree(d_f); cudaFree(d_p);
+  return 0;
+}

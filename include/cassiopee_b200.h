@@ -1,0 +1,141 @@
+/* cassiopee_b200.h — C ABI of libcassiopee_b200.so (sm_100a CUDA).
+ *
+ * Drop-in boundary for the chimera interpolation hot path of ONERA Cassiopee's
+ * Connector module.  Each entry point names the reference interface it
+ * replaces (paths relative to /root/reference/Cassiopee/).  Plain pointers and
+ * sizes only; E_Int = int32, E_Float = double, as in the reference's default
+ * build (KCore/KCore/Def/DefTypes.h:60-86).  Every function returns 0 on
+ * success, a negative status on error (message: cx_last_error()); nothing
+ * throws across the ABI.  There is no CPU fallback: without a CUDA device the
+ * context cannot be created and every other call needs a context.
+ *
+ * Host-pointer entry points copy host<->device inside the call (what a
+ * reference user sees); *_dev entry points work on device-resident arrays
+ * obtained from cx_dev_alloc (what a GPU-resident solver uses every
+ * sub-iteration).
+ */
+#ifndef CASSIOPEE_B200_H
+#define CASSIOPEE_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cx_ctx cx_ctx;        /* one CUDA device + stream */
+typedef struct cx_zone cx_zone;      /* donor zone resident on the device + its ADT replica */
+typedef struct cx_result cx_result;  /* output of one setInterpData call */
+typedef struct cx_plan cx_plan;      /* interpData of one (donor zone, receptor zone) pair, device resident */
+
+const char* cx_last_error(void);
+int cx_version(void);
+int cx_device_count(int* n);
+
+/* ---- context ----------------------------------------------------------- */
+int cx_ctx_create(int device, cx_ctx** out);
+int cx_ctx_destroy(cx_ctx* ctx);
+int cx_ctx_sync(cx_ctx* ctx);
+long long cx_ctx_launches(cx_ctx* ctx);              /* kernels launched by this library so far */
+int cx_ctx_info(cx_ctx* ctx, int* sm_count, size_t* free_bytes, size_t* total_bytes);
+/* CUDA-event timing on the context stream (which = 0 start, 1 stop) */
+int cx_event_record(cx_ctx* ctx, int which);
+int cx_event_elapsed_ms(cx_ctx* ctx, float* ms);     /* synchronises on the stop event */
+int cx_flush_l2(cx_ctx* ctx);                        /* writes a 256 MiB scratch buffer (> 126 MB L2) */
+
+/* ---- raw device / pinned memory (resident SoA fields) -------------------- */
+int cx_dev_alloc(cx_ctx* ctx, size_t bytes, void** dptr);
+int cx_dev_free(cx_ctx* ctx, void* dptr);
+int cx_dev_upload(cx_ctx* ctx, void* dptr, const void* host, size_t bytes);
+int cx_dev_download(cx_ctx* ctx, void* host, const void* dptr, size_t bytes);
+int cx_dev_memset(cx_ctx* ctx, void* dptr, int value, size_t bytes);
+int cx_pinned_alloc(size_t bytes, void** hptr);
+int cx_pinned_free(void* hptr);
+
+/* ---- donor zone = device ADT hook ---------------------------------------
+ * Replaces: new K_INTERP::InterpAdt(...) per donor zone in
+ * Connector/Connector/setInterpData.cpp:772-787 (KCore/KCore/Interp/InterpAdt.cpp:83-108,
+ * :284-433 buildStructAdt, :506-646 insert) and the hook of
+ * Converter/Converter/hook.cpp:578-632 (C.createHook(z,'adt')).
+ * x,y,z,cellN: host arrays of ni*nj*nk doubles, i fastest; cellN may be NULL
+ * (all 1, as OversetData.py:1193 _addCellN__ does).  3-D zones only (nk>1). */
+int cx_zone_create(cx_ctx* ctx, int ni, int nj, int nk, const double* x, const double* y, const double* z,
+                   const double* cellN, cx_zone** out);
+int cx_zone_set_celln(cx_zone* zone, const double* cellN);
+int cx_zone_info(cx_zone* zone, double bbox[6], int* ncells, int* depth, float* build_ms);
+/* test/debug: candidate cells of one point in the reference's list order
+ * (InterpAdt::getListOfCandidateCells, InterpAdt.cpp:658-929), device traversal */
+int cx_zone_candidates(cx_zone* zone, double x, double y, double z, double alphaTol, int* out, int cap, int* n);
+/* test/debug: copy the ADT replica to the host, 80-byte nodes (see cx_core.cuh AdtNode) */
+int cx_zone_export_adt(cx_zone* zone, void* nodes_out, size_t bytes);
+int cx_zone_destroy(cx_zone* zone);
+
+/* ---- setInterpData ------------------------------------------------------
+ * Replaces: connector.setInterpData(interpPts, donorArrays, order, nature,
+ * penalty, extrap, interpDataTypeList, hooks) — Connector/Connector/setInterpData.cpp:585-1322
+ * (and below it KCore/KCore/Interp/Interp.cpp:81-165,:282-360, Interp2.cpp:84-665,
+ * InterpAdt.cpp:658-1400, InterpData.cpp:56-947, Metric/compVolOfStructCell.cpp:91-218).
+ * xr,yr,zr: receptor coordinates (host, nrcv doubles each), zones: ordered
+ * donor list (order matters: commonTypesForExtrapAndInterp.h:16).
+ * order 2|3|5, nature 0|1, penalty 0|1, extrap 0|1 as in the reference. */
+int cx_set_interp_data(cx_ctx* ctx, int nrcv, const double* xr, const double* yr, const double* zr, int nz,
+                       cx_zone* const* zones, int order, int nature, int penalty, int extrap, cx_result** out);
+/* same with receptor coordinates already on the device */
+int cx_set_interp_data_dev(cx_ctx* ctx, int nrcv, const double* d_xr, const double* d_yr, const double* d_zr, int nz,
+                           cx_zone* const* zones, int order, int nature, int penalty, int extrap, cx_result** out);
+/* two-phase fetch (sizes, then copy into caller-allocated numpy): the 7-list
+ * returned by the reference at setInterpData.cpp:1272 —
+ * rcv[n], donor[n], type[n] (int32), coefs (ragged f64), extrap[ne] per donor
+ * zone, ascending receptor position; orphan[no] global. */
+int cx_result_sizes(cx_result* res, int* cnt, int* ncoef, int* nextrap, int* norphan);
+int cx_result_fetch_zone(cx_result* res, int zone, int* rcv, int* donor, int* type, double* coefs, int* extrap);
+int cx_result_fetch_orphans(cx_result* res, int* orphan);
+/* per-receptor table (tests): noblk (0 orphan / 1-based zone), type, donor, isext, cf[ncfmax][nrcv] */
+int cx_result_fetch_raw(cx_result* res, int* noblk, int* type, int* dind, int* isext, double* cf);
+/* out[0..7]: search kernel ms, extrapolation ms, nodes visited, candidates tested, ncfmax, ... */
+int cx_result_stats(cx_result* res, double* out);
+int cx_result_destroy(cx_result* res);
+
+/* ---- setInterpTransfers -------------------------------------------------
+ * A plan is the device-resident interpData of one ID_* ZoneSubRegion:
+ * donor = PointList, rcv = PointListDonor, type = InterpolantsType,
+ * coefs = InterpolantsDonor (ragged, SIZECF connector.h:27-37).
+ * imd,jmd,kmd: donor zone node dims; nptsR: size of the receptor fields. */
+int cx_plan_create(cx_ctx* ctx, int imd, int jmd, int kmd, long long nptsR, int n, const int* donor, const int* rcv,
+                   const int* type, const double* coefs, long long ncoefs, cx_plan** out);
+/* Replaces connector._setInterpTransfers (Connector/Connector/setInterpTransfers.cpp:259-508,
+ * commonInterpTransfers_indirect.h, commonInterpTransfers.h): in place,
+ * fieldR[v][rcv[e]] = sum_k cf_k * fieldD[v][stencil_k].  Host arrays. */
+int cx_transfer(cx_plan* plan, int nvars, const double* const* fieldD, double* const* fieldR);
+/* Replaces connector._setInterpTransfersD (setInterpTransfersD.cpp:106-303):
+ * dense out[v*n + e]. Host arrays. */
+int cx_transferD(cx_plan* plan, int nvars, const double* const* fieldD, double* out);
+/* strict cellN rule (commonCellNTransfersStrict.h; setInterpTransfers.cpp:452-467) */
+int cx_transfer_celln(cx_plan* plan, const double* cellND, double* cellNR);
+/* device-resident variants (pointers from cx_dev_alloc); asynchronous on the
+ * context stream */
+int cx_transfer_dev(cx_plan* plan, int nvars, const double* const* d_fieldD, double* const* d_fieldR);
+int cx_transferD_dev(cx_plan* plan, int nvars, const double* const* d_fieldD, double* d_out, long long ld);
+int cx_transfer_celln_dev(cx_plan* plan, const double* d_cellND, double* d_cellNR);
+/* receptor-side scatter of a dense (nvars, ld) buffer: fieldR[v][rcv[e]] = in[v*ld+e]
+ * (what Connector/Mpi.py:396-440 does with C._setPartialFields on arrival) */
+int cx_scatter_dev(cx_ctx* ctx, int nvars, const double* d_in, long long ld, int n, const int* d_rcv,
+                   double* const* d_fieldR);
+/* alg_fixed: sum over entries of 8*ncf+12 bytes; distinct: number of distinct
+ * donor nodes referenced (U of SURVEY.md 8(d)); B_alg = alg_fixed + 8*N*(n + U) */
+int cx_plan_info(cx_plan* plan, int* n, int* ngroups, long long* alg_fixed, long long* distinct);
+int cx_plan_destroy(cx_plan* plan);
+
+/* ---- multi-GPU (one process per GPU; NCCL over NVLink) -------------------
+ * Replaces the mpi4py pickled isend/recv of Converter/Converter/Mpi4py.py:149-168
+ * used by Connector/Mpi.py:396-440: one packed device buffer per peer rank. */
+int cx_comm_unique_id(char* id128);
+int cx_comm_init(cx_ctx* ctx, int rank, int nranks, const char* id128);
+int cx_comm_destroy(cx_ctx* ctx);
+int cx_comm_barrier(cx_ctx* ctx);
+/* grouped ncclSend/ncclRecv: counts in doubles; device buffers */
+int cx_exchange_dev(cx_ctx* ctx, int npeers, const int* peers, const double* const* d_send,
+                    const long long* sendcounts, double* const* d_recv, const long long* recvcounts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,105 @@
+// tests/hostemu/hostemu.cpp — TEST INFRASTRUCTURE ONLY.
+// Compiles the device header cassiopee_b200/csrc/cx_core.cuh with g++ (CX_D
+// empty) so the per-thread search logic and the level-synchronous ADT build
+// can be checked against the oracle on the GPU-less builder box.  Nothing in
+// the product loads this library; the product has no CPU path.
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include <algorithm>
+#include "../../cassiopee_b200/csrc/cx_core.cuh"
+using namespace cx;
+
+struct EmuZone {
+  int ni, nj, nk, npts, ncells, depth;
+  std::vector<double> x, y, z, c;
+  std::vector<AdtNode> nodes;
+  double bbox[6];
+  ZoneView view() const {
+    ZoneView V; V.x = x.data(); V.y = y.data(); V.z = z.data(); V.cellN = c.data(); V.nodes = nodes.data();
+    V.ni = ni; V.nj = nj; V.nk = nk; V.ncells = ncells; V.depth = depth;
+    for (int i = 0; i < 6; i++) V.bbox[i] = bbox[i];
+    return V;
+  }
+};
+
+extern "C" {
+
+void* emu_zone_create(int ni, int nj, int nk, const double* x, const double* y, const double* z, const double* cellN,
+                      const double* bbox)
+{
+  EmuZone* Z = new EmuZone;
+  Z->ni = ni; Z->nj = nj; Z->nk = nk; Z->npts = ni * nj * nk; Z->ncells = (ni - 1) * (nj - 1) * (nk - 1);
+  Z->x.assign(x, x + Z->npts); Z->y.assign(y, y + Z->npts); Z->z.assign(z, z + Z->npts);
+  if (cellN) Z->c.assign(cellN, cellN + Z->npts); else Z->c.assign(Z->npts, 1.0);
+  for (int i = 0; i < 6; i++) Z->bbox[i] = bbox[i];
+  int n = Z->ncells;
+  Z->nodes.resize(n);
+  std::vector<double> keys(6 * (size_t)n), lo(6 * (size_t)n), hi(6 * (size_t)n);
+  std::vector<int> cur(n, 0); std::vector<unsigned char> br(n, 0);
+  BuildView B; B.keys = keys.data(); B.lo = lo.data(); B.hi = hi.data(); B.cur = cur.data(); B.br = br.data();
+  B.nodes = Z->nodes.data(); B.ncells = n;
+  for (int d = 0; d < 6; d++) { B.zb.lo[d] = bbox[d % 3]; B.zb.hi[d] = bbox[3 + d % 3]; }
+  for (int c = 0; c < n; c++) adt_cell_keys(ni, nj, nk, x, y, z, c, n, B.keys, B.nodes);
+  freeze_node(B.nodes[0], 0, B.zb.lo[0], B.zb.hi[0]);
+  std::vector<int> act, next;
+  for (int c = 1; c < n; c++) act.push_back(c);
+  // shuffle to prove order independence of the level-synchronous build
+  for (size_t i = act.size(); i > 1; i--) { size_t j = (size_t)rand() % i; std::swap(act[i - 1], act[j]); }
+  int L = 0, depth = 0;
+  while (!act.empty())
+  {
+    for (int c : act)
+    {
+      int p, right; adt_claim(B, L, c, p, right);
+      int* slot = right ? &B.nodes[p].right : &B.nodes[p].left;
+      if (c < *slot) *slot = c;   // atomicMin
+    }
+    next.clear();
+    for (int c : act) { if (!adt_resolve(B, L, c)) next.push_back(c); else depth = L + 1; }
+    act.swap(next);
+    L++;
+  }
+  Z->depth = depth;
+  return Z;
+}
+
+void emu_zone_free(void* h) { delete (EmuZone*)h; }
+int emu_zone_depth(void* h) { return ((EmuZone*)h)->depth; }
+
+int emu_candidates(void* h, double x, double y, double z, double alphaTol, int* out, int cap)
+{
+  ZoneView V = ((EmuZone*)h)->view();
+  if (zone_reject(V, x, y, z, alphaTol)) return 0;
+  AdtQuery q; query_init(q, V, x, y, z, alphaTol);
+  int c, nid, nv = 0, n = 0;
+  while ((c = query_next(q, V.nodes, &nid, &nv)) >= 0) { if (n < cap) out[n] = c; n++; }
+  return n;
+}
+
+void emu_set_interp_data(int n, const double* xr, const double* yr, const double* zr, int nz, void** zones,
+                         int nature, int penalty, int extrap, int* noblk, int* type, int* dind, int* isext,
+                         double* cf, long long* stats)
+{
+  std::vector<ZoneView> V(nz);
+  for (int i = 0; i < nz; i++) V[i] = ((EmuZone*)zones[i])->view();
+  SearchStats st; st.nvisit = st.ncand = st.ntet = 0;
+  for (int r = 0; r < n; r++)
+  {
+    RcvOut o;
+    interp_o2_receptor(xr[r], yr[r], zr[r], nz, V.data(), nature, penalty, o, &st);
+    isext[r] = 0;
+    if (o.noblk == 0 && extrap == 1)
+    {
+      extrap_receptor(xr[r], yr[r], zr[r], nz, V.data(), nature, penalty, o, &st);
+      if (o.noblk > 0) isext[r] = 1;
+    }
+    noblk[r] = o.noblk; type[r] = o.noblk > 0 ? o.type : 0; dind[r] = o.noblk > 0 ? o.dind : -1;
+    for (int k = 0; k < 8; k++) cf[(size_t)r * 8 + k] = o.noblk > 0 ? o.cf[k] : 0.;
+  }
+  if (stats) { stats[0] = st.nvisit; stats[1] = st.ncand; }
+}
+
+double emu_cell_volume(void* h, int ind) { ZoneView V = ((EmuZone*)h)->view(); return cell_volume(V, ind); }
+
+}  // extern "C"
