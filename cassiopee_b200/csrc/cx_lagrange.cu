@@ -1,8 +1,614 @@
-// placeholder, replaced below
+// cx_lagrange.cu — order-3 / order-5 Lagrange interpolation data on the device.
+//
+// Reference path (per receptor, per donor zone):
+//   K_INTERP::getInterpolationData, O3ABC / O5ABC branches   KCore/KCore/Interp/Interp2.cpp:344-394, :452-503
+//   CELLN(order) validity macro                              Interp2.cpp:40-67
+//   K_INTERP::compLagrangeCoefs                              Interp2.cpp:517-665
+//   compinterpolatedptinrefelt (27/125-point polynomial map) KCore/KCore/Interp/CompInterpolatedPtInRefElementF.for:25-300
+//   cp_coord_in_stable_frame_3d / coord_in_ref_frame_3d      Cp_coord_in_stable_frame_3dF.for:25-174, Coord_in_ref_frame_3dF.for:23-228
+//   kgaussj (full-pivot Gauss-Jordan, '>=' keeps the LAST max) KCore/KCore/Linear/GaussjF.for:29-100
+//   cross-zone choice / type-1 collapse                      commonTypesForExtrapAndInterp.h, commonCheckCoefs.h
+//
+// Device pipeline per donor zone z (host loop over the ordered zone list):
+//   k_lag_search   one thread per receptor: order-2 cell search (cx_core.cuh)
+//   k_lag_solve    one thread GROUP per found receptor (a warp for 27x27, a
+//                  256-thread CTA for 125x125): gather stencil, stable frame,
+//                  monomial matrix in shared memory, Gauss-Jordan with the
+//                  reference's pivot sequence, evaluate (ksi,eta,zeta)
+//   k_lag_finish   one thread per receptor: Lagrange weights, cellN check,
+//                  order-2 fallback, volume, running best over zones
+// then k_lag_collapse applies the coincident (type 1) rule.
+//
+// Arithmetic: only the columns that are still un-pivoted and the 3 right-hand
+// sides are updated during elimination.  Pivoted columns (the in-place inverse
+// the Fortran routine also builds) are never read again by the pivot search
+// (ipiv(k).EQ.0 filter) nor by the RHS update, so the pivot sequence and every
+// value that reaches (ksi,eta,zeta) are bit-identical while the work halves.
 #include "cx_internal.h"
+
 using namespace cx;
-int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_xr, const double* d_yr,
-                         const double* d_zr, int nz, const ZoneView* d_zones, const ZoneView* h_zones,
-                         int nature, int penalty, int* noblk, int* type, int* dind, double* cf, int ncfmax,
-                         unsigned long long* d_stats)
-{ cx_set_error("order %d not built yet", order); return -4; }
+
+namespace {
+
+struct LagState {
+  int n;
+  int* found;      // [n] 0/1 for the current zone
+  int* ijk;        // [3][n] 1-based cell of the order-2 search
+  double* tcf;     // [15][n] per-receptor tmpCf, persistent across zones (Interp.cpp:113)
+  double* ksi;     // [3][n]
+  int* err;        // [n]
+  double* best;    // [n]
+  int* noblk; int* type; int* dind;
+  double* cf;      // [ncfmax][n]
+  int ncfmax;
+};
+
+__global__ void k_lag_init(LagState S)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= S.n) return;
+  S.best[r] = CX_MAXF; S.noblk[r] = 0; S.type[r] = 0; S.dind[r] = -1;
+  for (int k = 0; k < 15; k++) S.tcf[(size_t)k * S.n + r] = 0.;
+  for (int k = 0; k < S.ncfmax; k++) S.cf[(size_t)k * S.n + r] = 0.;
+}
+
+__global__ void __launch_bounds__(128)
+k_lag_search(LagState S, const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr,
+             const ZoneView* __restrict__ zones, int noz, int order, unsigned long long* __restrict__ flags,
+             unsigned long long* gstats)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= S.n) return;
+  const ZoneView& Z = zones[noz];
+  int ic = 0, jc = 0, kc = 0, found = 0;
+  double cf[8];
+  SearchStats st; st.nvisit = 0; st.ncand = 0; st.ntet = 0;
+  // Interp2.cpp:347-351 / :455-459: zones too thin for the stencil return -1
+  if (!(Z.ni < order || Z.nj < order || Z.nk < order))
+  {
+    found = search_interp_cell(Z, xr[r], yr[r], zr[r], ic, jc, kc, cf, &st);
+    if (found == 1)
+      for (int k = 0; k < 8; k++) S.tcf[(size_t)k * S.n + r] = cf[k];
+  }
+  S.found[r] = found;
+  S.ijk[r] = ic; S.ijk[(size_t)S.n + r] = jc; S.ijk[2 * (size_t)S.n + r] = kc;
+  flags[r] = found ? 1ull : 0ull;
+  if (gstats && st.nvisit) atomicAdd(&gstats[0], (unsigned long long)st.nvisit);
+}
+
+// 1-based start (ics,jcs,kcs) of the Lagrange stencil from the 1-based cell
+// of the order-2 search (Interp2.cpp:359-366 for O3, :469-485 for O5)
+__device__ __forceinline__ void stencil_start(int order, const ZoneView& Z, int ic, int jc, int kc, int& ics, int& jcs,
+                                              int& kcs)
+{
+  if (order == 3)
+  {
+    ic -= 1; jc -= 1; kc -= 1;
+    if (ic < 1) ic = 1;
+    if (jc < 1) jc = 1;
+    if (kc < 1) kc = 1;
+  }
+  else
+  {
+    if (ic >= Z.ni - 1) ic = Z.ni - 4; else ic = ic - 2;
+    if (jc >= Z.nj - 1) jc = Z.nj - 4; else jc = jc - 2;
+    if (kc >= Z.nk - 1) kc = Z.nk - 4; else kc = kc - 2;
+    if (ic < 1) ic = 1;
+    if (jc < 1) jc = 1;
+    if (kc < 1) kc = 1;
+  }
+  ics = ic; jcs = jc; kcs = kc;
+}
+
+__device__ __forceinline__ double det3(const double* m)
+{ // Coord_in_ref_frame_3dF.for:205-211, column-major m(i,j) = m[(i-1)+(j-1)*3]
+#define MM(i, j) m[(i - 1) + (j - 1) * 3]
+  return MM(1, 1) * MM(2, 2) * MM(3, 3) + MM(2, 1) * MM(3, 2) * MM(1, 3) + MM(3, 1) * MM(1, 2) * MM(2, 3) -
+         MM(1, 1) * MM(3, 2) * MM(2, 3) - MM(2, 1) * MM(1, 2) * MM(3, 3) - MM(3, 1) * MM(2, 2) * MM(1, 3);
+#undef MM
+}
+
+// coord_in_ref_frame_3d (Coord_in_ref_frame_3dF.for:23-127); pts(3,4) column-major
+__device__ __forceinline__ void ref_frame(const double* pts, double x1, double y1, double z1, double& x2, double& y2,
+                                          double& z2)
+{
+  double u[3], v[3], w[3], t[3], m[9];
+  for (int i = 0; i < 3; i++) { u[i] = pts[i + 3] - pts[i]; v[i] = pts[i + 6] - pts[i]; w[i] = pts[i + 9] - pts[i]; }
+  t[0] = x1 - pts[0]; t[1] = y1 - pts[1]; t[2] = z1 - pts[2];
+  for (int i = 0; i < 3; i++) { m[i] = u[i]; m[i + 3] = v[i]; m[i + 6] = w[i]; }
+  double invdet = det3(m);
+  invdet = 1.0 / invdet;
+  for (int i = 0; i < 3; i++) { m[i] = t[i]; m[i + 3] = v[i]; m[i + 6] = w[i]; }
+  x2 = det3(m); x2 = x2 * invdet;
+  for (int i = 0; i < 3; i++) { m[i] = u[i]; m[i + 3] = t[i]; m[i + 6] = w[i]; }
+  y2 = det3(m); y2 = y2 * invdet;
+  for (int i = 0; i < 3; i++) { m[i] = u[i]; m[i + 3] = v[i]; m[i + 6] = t[i]; }
+  z2 = det3(m); z2 = z2 * invdet;
+}
+
+template <bool WARP>
+__device__ __forceinline__ void gsync()
+{
+  if (WARP) __syncwarp(); else __syncthreads();
+}
+
+// One thread group (NT threads) solves one receptor's system.
+//   N1 = points per direction (3 or 5), N = N1^3 rows, LD = padded row length
+//   (N columns + 3 RHS, odd number of doubles => conflict-free row-strided
+//   access).  Shared layout per group: A[N][LD], px/py/pz[N], small scratch.
+template <int N1, int NT, bool WARP>
+__device__ void lag_solve_group(const ZoneView& Z, int ics, int jcs, int kcs, double x0, double y0, double z0,
+                                double* sm, int tid, double& ksi, double& eta, double& zeta, int& err)
+{
+  constexpr int N = N1 * N1 * N1;
+  constexpr int LD = (N + 3) | 1;
+  double* A = sm;                 // N*LD
+  double* px = A + N * LD;        // N   stencil coordinates (stable frame)
+  double* py = px + N;
+  double* pz = py + N;
+  double* sc = pz + N;            // 16: pts(3,4) + transformed receptor
+  volatile double* red_v = sc + 16;          // NT/32 partial maxima
+  volatile int* red_i = (volatile int*)(red_v + 8);   // NT/32 indices
+  int* ipiv = (int*)(red_v + 8) + 16;        // N flags
+  int* ctl = ipiv + N + 3;                   // [0]=irow [1]=icol [2]=singular
+
+  const int ni = Z.ni, ninj = Z.ni * Z.nj;
+  const int ind0 = ics - 1 + (jcs - 1) * ni + (kcs - 1) * ninj;
+  // gather the stencil (CompInterpolatedPtInRefElementF.for:77-96)
+  for (int p = tid; p < N; p += NT)
+  {
+    int i = p % N1, j = (p / N1) % N1, k = p / (N1 * N1);
+    int ind = ind0 + i + j * ni + k * ninj;
+    px[p] = Z.x[ind]; py[p] = Z.y[ind]; pz[p] = Z.z[ind];
+    ipiv[p] = 0;
+  }
+  gsync<WARP>();
+  // stable frame (Cp_coord_in_stable_frame_3dF.for:77-150): computed by one thread
+  if (tid == 0)
+  {
+    const int c0 = (N1 + 1) / 2;   // 1-based centre index
+#define IDP(i, j, k) ((i - 1) + (j - 1) * N1 + (k - 1) * N1 * N1)
+    double ui[3] = {0., 0., 0.}, uj[3] = {0., 0., 0.}, uk[3] = {0., 0., 0.};
+    int idc = IDP(c0, c0, c0);
+    double O[3] = {px[idc], py[idc], pz[idc]};
+    for (int dk = 0; dk <= 1; dk++) for (int dj = 0; dj <= 1; dj++)
+    {
+      int a = IDP(c0, c0 + dj, c0 + dk), b = IDP(c0 + 1, c0 + dj, c0 + dk);
+      ui[0] = ui[0] + px[b] - px[a]; ui[1] = ui[1] + py[b] - py[a]; ui[2] = ui[2] + pz[b] - pz[a];
+    }
+    for (int dk = 0; dk <= 1; dk++) for (int di = 0; di <= 1; di++)
+    {
+      int a = IDP(c0 + di, c0, c0 + dk), b = IDP(c0 + di, c0 + 1, c0 + dk);
+      uj[0] = uj[0] + px[b] - px[a]; uj[1] = uj[1] + py[b] - py[a]; uj[2] = uj[2] + pz[b] - pz[a];
+    }
+    for (int dj = 0; dj <= 1; dj++) for (int di = 0; di <= 1; di++)
+    {
+      int a = IDP(c0 + di, c0 + dj, c0), b = IDP(c0 + di, c0 + dj, c0 + 1);
+      uk[0] = uk[0] + px[b] - px[a]; uk[1] = uk[1] + py[b] - py[a]; uk[2] = uk[2] + pz[b] - pz[a];
+    }
+#undef IDP
+    for (int i = 0; i < 3; i++)
+    {
+      ui[i] = ui[i] * 0.25; uj[i] = uj[i] * 0.25; uk[i] = uk[i] * 0.25;
+      sc[i] = O[i]; sc[i + 3] = O[i] + ui[i]; sc[i + 6] = O[i] + uj[i]; sc[i + 9] = O[i] + uk[i];
+    }
+    ctl[2] = 0;
+  }
+  gsync<WARP>();
+  double xp, yp, zp;
+  ref_frame(sc, x0, y0, z0, xp, yp, zp);      // every thread: identical arithmetic
+  for (int p = tid; p < N; p += NT)
+  {
+    double a, b, c;
+    ref_frame(sc, px[p], py[p], pz[p], a, b, c);
+    // monomial row (CompInterpolatedPtInRefElementF.for:121-139) and RHS (:167-180)
+    double* row = A + p * LD;
+    double zp1 = 1;
+    int col = 0;
+    for (int k = 0; k < N1; k++)
+    {
+      double yp1 = 1;
+      for (int j = 0; j < N1; j++)
+      {
+        double xp1 = 1;
+        for (int i = 0; i < N1; i++)
+        {
+          row[col] = xp1 * yp1 * zp1;
+          col++;
+          xp1 = xp1 * a;
+        }
+        yp1 = yp1 * b;
+      }
+      zp1 = zp1 * c;
+    }
+    const double b0 = (N1 == 3) ? -1. : -2.;
+    int i = p % N1, j = (p / N1) % N1, k = p / (N1 * N1);
+    row[N] = b0 + i; row[N + 1] = b0 + j; row[N + 2] = b0 + k;
+  }
+  gsync<WARP>();
+
+  // --- kgaussj (GaussjF.for:29-100) -----------------------------------------
+  // thread -> (row, column segment): SEG segments per row
+  constexpr int SEG = (NT >= 2 * N) ? 2 : 1;
+  constexpr int ROWS = (SEG == 2) ? (NT / 2) : NT;
+  const int row = tid % ROWS;
+  const int seg = tid / ROWS;
+  constexpr int CHUNK = (N + SEG - 1) / SEG;
+  const int c0 = seg * CHUNK;
+  const int c1 = (c0 + CHUNK < N) ? c0 + CHUNK : N;
+  const bool rowOn = row < N && seg < SEG;
+  for (int step = 0; step < N; step++)
+  {
+    // full pivot search; the LAST maximum in (row, column) order wins
+    double big = -1.; int bidx = -1;
+    if (rowOn && ipiv[row] != 1)
+    {
+      const double* ar = A + row * LD;
+      for (int k = c0; k < c1; k++)
+        if (ipiv[k] == 0)
+        {
+          double v = fabs(ar[k]);
+          if (v >= big) { big = v; bidx = row * N + k; }
+        }
+    }
+    // warp argmax: larger value, then larger (row,col) index
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      double ov = __shfl_down_sync(0xffffffffu, big, o);
+      int oi = __shfl_down_sync(0xffffffffu, bidx, o);
+      if (ov > big || (ov == big && oi > bidx)) { big = ov; bidx = oi; }
+    }
+    if (WARP)
+    {
+      bidx = __shfl_sync(0xffffffffu, bidx, 0);
+    }
+    else
+    {
+      if ((tid & 31) == 0) { red_v[tid >> 5] = big; red_i[tid >> 5] = bidx; }
+      __syncthreads();
+      if (tid == 0)
+      {
+        double bv = red_v[0]; int bi = red_i[0];
+        for (int w = 1; w < NT / 32; w++)
+        {
+          double ov = red_v[w]; int oi = red_i[w];
+          if (ov > bv || (ov == bv && oi > bi)) { bv = ov; bi = oi; }
+        }
+        red_i[0] = bi;
+      }
+      __syncthreads();
+      bidx = red_i[0];
+    }
+    // bidx < 0 can only happen with NaNs everywhere; treat like the singular exit
+    if (bidx < 0) { if (tid == 0) ctl[2] = 1; gsync<WARP>(); break; }
+    const int irow = bidx / N, icol = bidx % N;
+    gsync<WARP>();
+    if (tid == 0) ipiv[icol] = ipiv[icol] + 1;
+    // row swap (all live columns + RHS)
+    if (irow != icol)
+    {
+      for (int l = tid; l < N + 3; l += NT)
+      {
+        double* a = A + irow * LD + l; double* b = A + icol * LD + l;
+        double dum = *a; *a = *b; *b = dum;
+      }
+    }
+    gsync<WARP>();
+    double piv = A[icol * LD + icol];
+    if (piv == 0.) { if (tid == 0) ctl[2] = 1; gsync<WARP>(); break; }   // 'singular matrix in gaussj, 2'
+    double pivinv = 1. / piv;
+    gsync<WARP>();
+    // scale the pivot row: a(icol,icol)=1 then row*pivinv (GaussjF.for:70-77)
+    for (int l = tid; l < N + 3; l += NT)
+    {
+      double* a = A + icol * LD + l;
+      if (l == icol) *a = 1. * pivinv;
+      else if (l >= N || ipiv[l] == 0) *a = *a * pivinv;
+    }
+    gsync<WARP>();
+    // eliminate column icol from every other row (GaussjF.for:78-89)
+    if (rowOn && row != icol)
+    {
+      double* ar = A + row * LD;
+      const double* ap = A + icol * LD;
+      double dum = ar[icol];
+      for (int l = c0; l < c1; l++)
+        if (ipiv[l] == 0) ar[l] = ar[l] - ap[l] * dum;
+      if (seg == SEG - 1)
+      {
+        ar[N] = ar[N] - ap[N] * dum; ar[N + 1] = ar[N + 1] - ap[N + 1] * dum; ar[N + 2] = ar[N + 2] - ap[N + 2] * dum;
+      }
+    }
+    gsync<WARP>();
+    // a(ll,icol) = 0 for ll != icol happens implicitly: column icol is never read again
+  }
+  gsync<WARP>();
+  // evaluate the polynomial map at the receptor (CompInterpolatedPtInRefElementF.for:242-263)
+  if (tid < 3)
+  {
+    double acc = 0.;
+    int id = 0;
+    double mk = 1;
+    for (int k = 0; k < N1; k++)
+    {
+      double mj = 1;
+      for (int j = 0; j < N1; j++)
+      {
+        double mi = 1;
+        for (int i = 0; i < N1; i++)
+        {
+          double m = mi * mj * mk;
+          acc = acc + A[id * LD + N + tid] * m;
+          id++;
+          mi = mi * xp;
+        }
+        mj = mj * yp;
+      }
+      mk = mk * zp;
+    }
+    sc[12 + tid] = acc;
+  }
+  gsync<WARP>();
+  ksi = sc[12]; eta = sc[13]; zeta = sc[14];
+  const double thres = (double)(N1 / 2) + 0.001;
+  err = (fabs(ksi) >= thres || fabs(eta) >= thres || fabs(zeta) >= thres) ? 1 : 0;
+  gsync<WARP>();
+}
+
+template <int N1> struct LagCfg {
+  static constexpr int N = N1 * N1 * N1;
+  static constexpr int LD = (N + 3) | 1;
+  // doubles of shared memory per group
+  static constexpr int SMEM_D = N * LD + 3 * N + 16 + 8 + ((16 + N + 3 + 4) * 4 + 7) / 8;
+};
+
+// order 3: one warp per receptor, 4 receptors per CTA
+__global__ void __launch_bounds__(128)
+k_lag_solve3(LagState S, int nlist, const int* __restrict__ list, const double* __restrict__ xr,
+             const double* __restrict__ yr, const double* __restrict__ zr, const ZoneView* __restrict__ zones, int noz)
+{
+  extern __shared__ double smem[];
+  int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int a = blockIdx.x * 4 + w;
+  if (a >= nlist) return;
+  int r = list[a];
+  const ZoneView& Z = zones[noz];
+  int ics, jcs, kcs;
+  stencil_start(3, Z, S.ijk[r], S.ijk[(size_t)S.n + r], S.ijk[2 * (size_t)S.n + r], ics, jcs, kcs);
+  double ksi, eta, zeta; int err;
+  lag_solve_group<3, 32, true>(Z, ics, jcs, kcs, xr[r], yr[r], zr[r], smem + (size_t)w * LagCfg<3>::SMEM_D, lane, ksi,
+                               eta, zeta, err);
+  if (lane == 0)
+  {
+    S.ksi[r] = ksi; S.ksi[(size_t)S.n + r] = eta; S.ksi[2 * (size_t)S.n + r] = zeta; S.err[r] = err;
+  }
+}
+
+// order 5: one 256-thread CTA per receptor, matrix (125 x 129 doubles) in shared memory
+__global__ void __launch_bounds__(256)
+k_lag_solve5(LagState S, int nlist, const int* __restrict__ list, const double* __restrict__ xr,
+             const double* __restrict__ yr, const double* __restrict__ zr, const ZoneView* __restrict__ zones, int noz)
+{
+  extern __shared__ double smem[];
+  for (int a = blockIdx.x; a < nlist; a += gridDim.x)
+  {
+    int r = list[a];
+    const ZoneView& Z = zones[noz];
+    int ics, jcs, kcs;
+    stencil_start(5, Z, S.ijk[r], S.ijk[(size_t)S.n + r], S.ijk[2 * (size_t)S.n + r], ics, jcs, kcs);
+    double ksi, eta, zeta; int err;
+    lag_solve_group<5, 256, false>(Z, ics, jcs, kcs, xr[r], yr[r], zr[r], smem, threadIdx.x, ksi, eta, zeta, err);
+    if (threadIdx.x == 0)
+    {
+      S.ksi[r] = ksi; S.ksi[(size_t)S.n + r] = eta; S.ksi[2 * (size_t)S.n + r] = zeta; S.err[r] = err;
+    }
+    __syncthreads();
+  }
+}
+
+// CELLN(order) (Interp2.cpp:40-67) on the per-receptor tmpCf; (ic,jc,kc) 0-based stencil start
+__device__ __forceinline__ bool celln_valid_lag(const ZoneView& Z, int O, int ic, int jc, int kc, const double* cf,
+                                                int nature)
+{
+  if (Z.cellN == nullptr) return true;
+  const int ni = Z.ni, nij = Z.ni * Z.nj;
+  if (nature == 0)
+  {
+    double val = 1.;
+    for (int kk = 0; kk < O; kk++) for (int jj = 0; jj < O; jj++) for (int ii = 0; ii < O; ii++)
+    {
+      double c0 = Z.cellN[(ic + ii) + (jc + jj) * ni + (kc + kk) * nij];
+      int d = cf[ii] * cf[jj + O] * cf[kk + O * 2] > 1.e-12;
+      val *= c0 - d + 1;
+    }
+    return !eqzero(val, CX_EPS_GEOM);
+  }
+  double val = 0.;
+  for (int kk = 0; kk < O; kk++) for (int jj = 0; jj < O; jj++) for (int ii = 0; ii < O; ii++)
+  {
+    double c0 = Z.cellN[(ic + ii) + (jc + jj) * ni + (kc + kk) * nij];
+    val += fabs(cf[ii] * cf[jj + O] * cf[kk + O * 2]) * fabs(1. - c0);
+  }
+  return eqzero(val, CX_EPS_GEOM);
+}
+
+// Lagrange weights with the reference's literal constants (Interp2.cpp:580-658)
+__device__ __forceinline__ void lagrange_weights(int order, double ksi, double eta, double zeta, double* cf)
+{
+  double ksip = 1. + ksi, ksim = 1. - ksi, etap = 1. + eta, etam = 1. - eta, zetap = 1. + zeta, zetam = 1. - zeta;
+  if (order == 3)
+  {
+    cf[0] = -0.5 * ksi * ksim; cf[1] = ksip * ksim; cf[2] = 0.5 * ksi * ksip;
+    cf[3] = -0.5 * eta * etam; cf[4] = etap * etam; cf[5] = 0.5 * eta * etap;
+    cf[6] = -0.5 * zeta * zetam; cf[7] = zetap * zetam; cf[8] = 0.5 * zeta * zetap;
+  }
+  else
+  {
+    const double inv24 = 0.041666666667, inv6 = 0.166666666667, inv4 = 0.25;
+    double ksip2 = 2. + ksi, ksim2 = 2. - ksi, etap2 = 2. + eta, etam2 = 2. - eta, zetap2 = 2. + zeta, zetam2 = 2. - zeta;
+    cf[0] = inv24 * ksi * ksip * ksim * ksim2;
+    cf[1] = -inv6 * ksi * ksip2 * ksim * ksim2;
+    cf[2] = inv4 * ksim2 * ksim * ksip * ksip2;
+    cf[3] = inv6 * ksi * ksim2 * ksip * ksip2;
+    cf[4] = -inv24 * ksip2 * ksip * ksi * ksim;
+    cf[5] = inv24 * eta * etap * etam * etam2;
+    cf[6] = -inv6 * eta * etap2 * etam * etam2;
+    cf[7] = inv4 * etam2 * etam * etap * etap2;
+    cf[8] = inv6 * eta * etam2 * etap * etap2;
+    cf[9] = -inv24 * etap2 * etap * eta * etam;
+    cf[10] = inv24 * zeta * zetap * zetam * zetam2;
+    cf[11] = -inv6 * zeta * zetap2 * zetam * zetam2;
+    cf[12] = inv4 * zetam2 * zetam * zetap * zetap2;
+    cf[13] = inv6 * zeta * zetam2 * zetap * zetap2;
+    cf[14] = -inv24 * zetap2 * zetap * zeta * zetam;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_lag_finish(LagState S, const ZoneView* __restrict__ zones, int noz, int order, int nature, int penalty)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= S.n) return;
+  if (S.found[r] != 1) return;
+  const ZoneView& Z = zones[noz];
+  const size_t n = S.n;
+  const int O = order, ncf = 3 * order;
+  int ic1 = S.ijk[r], jc1 = S.ijk[n + r], kc1 = S.ijk[2 * n + r];   // 1-based order-2 cell
+  int ics, jcs, kcs;
+  stencil_start(order, Z, ic1, jc1, kc1, ics, jcs, kcs);
+  int ic = ics - 1, jc = jcs - 1, kc = kcs - 1;
+  int isBorder = (ic == 0 || ic == Z.ni - O || jc == 0 || jc == Z.nj - O || kc == 0 || kc == Z.nk - O);
+  int type = order;
+  int tind = ic + jc * Z.ni + kc * Z.ni * Z.nj;
+  double cf[15];
+  for (int k = 0; k < 15; k++) cf[k] = S.tcf[(size_t)k * n + r];
+  const int corr = S.err[r];
+  if (order == 3)
+  {
+    // O3: weights first (when well approximated), then the cellN test (Interp2.cpp:369-372)
+    if (corr == 0) lagrange_weights(3, S.ksi[r], S.ksi[n + r], S.ksi[2 * n + r], cf);
+    if (!celln_valid_lag(Z, 3, ic, jc, kc, cf, nature))
+    {
+      for (int k = 0; k < ncf; k++) S.tcf[(size_t)k * n + r] = cf[k];
+      return;
+    }
+  }
+  else
+  {
+    // O5: cellN test BEFORE the weights, on whatever tmpCf holds (Interp2.cpp:490-492)
+    if (!celln_valid_lag(Z, 5, ic, jc, kc, cf, nature)) return;
+    if (corr == 0) lagrange_weights(5, S.ksi[r], S.ksi[n + r], S.ksi[2 * n + r], cf);
+  }
+  if (corr == 1)
+  {
+    // badly approximated point: order-2 result of the same search (Interp2.cpp:374-382, :493-502)
+    ic = ic1 - 1; jc = jc1 - 1; kc = kc1 - 1;
+    isBorder = (ic == 0 || ic == Z.ni - 2 || jc == 0 || jc == Z.nj - 2 || kc == 0 || kc == Z.nk - 2);
+    type = 2; tind = ic + jc * Z.ni + kc * Z.ni * Z.nj;
+  }
+  for (int k = 0; k < ncf; k++) S.tcf[(size_t)k * n + r] = cf[k];
+  // commonTypesForExtrapAndInterp.h:7-36
+  double vol = cell_volume(Z, tind);
+  if (penalty == 1 && isBorder == 1) vol += 1.e3;
+  if (vol < S.best[r] + CX_EPS_GEOM)
+  {
+    S.best[r] = vol; S.type[r] = type; S.dind[r] = tind; S.noblk[r] = noz + 1;
+    for (int k = 0; k < S.ncfmax; k++) S.cf[(size_t)k * n + r] = cf[k];
+  }
+}
+
+// commonCheckCoefs.h: exactly one stencil weight above 1e-10 -> type 1
+__global__ void k_lag_collapse(LagState S, const ZoneView* __restrict__ zones)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= S.n) return;
+  int nb = S.noblk[r];
+  if (nb <= 0) return;
+  const ZoneView& Z = zones[nb - 1];
+  const size_t n = S.n;
+  int type = S.type[r], dind = S.dind[r];
+  const int ni = Z.ni, ninj = Z.ni * Z.nj;
+  int cnt = 0, indNonZero = -1; double coefNonZero = 0.;
+  if (type == 2)
+  {
+    for (int kk = 0; kk < 2; kk++) for (int jj = 0; jj < 2; jj++) for (int ii = 0; ii < 2; ii++)
+    {
+      double c = S.cf[(size_t)(ii + jj * 2 + kk * 4) * n + r];
+      if (fabs(c) > 1.e-10) { cnt++; indNonZero = dind + ii + jj * ni + kk * ninj; coefNonZero = c; }
+    }
+  }
+  else if (type == 3 || type == 5)
+  {
+    const int O = type;
+    for (int kk = 0; kk < O; kk++) for (int jj = 0; jj < O; jj++) for (int ii = 0; ii < O; ii++)
+    {
+      double c = S.cf[(size_t)ii * n + r] * S.cf[(size_t)(jj + O) * n + r] * S.cf[(size_t)(kk + 2 * O) * n + r];
+      if (fabs(c) > 1.e-10) { cnt++; indNonZero = dind + ii + jj * ni + kk * ninj; coefNonZero = c; }
+    }
+  }
+  if (cnt == 1) { S.type[r] = 1; S.dind[r] = indNonZero; S.cf[r] = coefNonZero; }
+}
+
+__global__ void k_list(int n, const unsigned long long* __restrict__ f, const unsigned long long* __restrict__ pos,
+                       int* __restrict__ out)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  if (f[r]) out[(int)pos[r]] = r;
+}
+
+}  // namespace
+
+int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_xr, const double* d_yr, const double* d_zr,
+                         int nz, const ZoneView* d_zones, const ZoneView* h_zones, int nature, int penalty, int* noblk,
+                         int* type, int* dind, double* cf, int ncfmax, unsigned long long* d_stats)
+{
+  (void)h_zones;
+  cudaStream_t s = ctx->stream;
+  LagState S;
+  size_t N = n;
+  S.n = n; S.noblk = noblk; S.type = type; S.dind = dind; S.cf = cf; S.ncfmax = ncfmax;
+  CX_CUDA(cudaMalloc(&S.found, sizeof(int) * N));
+  CX_CUDA(cudaMalloc(&S.ijk, sizeof(int) * 3 * N));
+  CX_CUDA(cudaMalloc(&S.tcf, sizeof(double) * 15 * N));
+  CX_CUDA(cudaMalloc(&S.ksi, sizeof(double) * 3 * N));
+  CX_CUDA(cudaMalloc(&S.err, sizeof(int) * N));
+  CX_CUDA(cudaMalloc(&S.best, sizeof(double) * N));
+  unsigned long long *d_f, *d_p; int* d_list;
+  CX_CUDA(cudaMalloc(&d_f, sizeof(unsigned long long) * N));
+  CX_CUDA(cudaMalloc(&d_p, sizeof(unsigned long long) * N));
+  CX_CUDA(cudaMalloc(&d_list, sizeof(int) * N));
+  const int TB = 128;
+  k_lag_init<<<cx_grid(n, 256), 256, 0, s>>>(S);
+  ctx->launches++;
+  const size_t smem3 = sizeof(double) * LagCfg<3>::SMEM_D * 4;
+  const size_t smem5 = sizeof(double) * LagCfg<5>::SMEM_D;
+  if (order == 5)
+    CX_CUDA(cudaFuncSetAttribute(k_lag_solve5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+  for (int noz = 0; noz < nz; noz++)
+  {
+    k_lag_search<<<cx_grid(n, TB), TB, 0, s>>>(S, d_xr, d_yr, d_zr, d_zones, noz, order, d_f, d_stats);
+    ctx->launches++;
+    unsigned long long tot = 0;
+    CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, n, &tot));
+    int nlist = (int)tot;
+    if (nlist == 0) continue;
+    k_list<<<cx_grid(n, 256), 256, 0, s>>>(n, d_f, d_p, d_list);
+    if (order == 3)
+      k_lag_solve3<<<cx_grid(nlist, 4), 128, smem3, s>>>(S, nlist, d_list, d_xr, d_yr, d_zr, d_zones, noz);
+    else
+    {
+      int grid = nlist < ctx->sm_count * 4 ? nlist : ctx->sm_count * 4;
+      k_lag_solve5<<<grid, 256, smem5, s>>>(S, nlist, d_list, d_xr, d_yr, d_zr, d_zones, noz);
+    }
+    k_lag_finish<<<cx_grid(n, TB), TB, 0, s>>>(S, d_zones, noz, order, nature, penalty);
+    ctx->launches += 3;
+  }
+  k_lag_collapse<<<cx_grid(n, 256), 256, 0, s>>>(S, d_zones);
+  ctx->launches++;
+  CX_CUDA(cudaStreamSynchronize(s));
+  CX_CUDA(cudaGetLastError());
+  cudaFree(S.found); cudaFree(S.ijk); cudaFree(S.tcf); cudaFree(S.ksi); cudaFree(S.err); cudaFree(S.best);
+  cudaFree(d_f); cudaFree(d_p); cudaFree(d_list);
+  return 0;
+}
