@@ -162,3 +162,60 @@ def test_linear_field_exact(ctx):
 def test_pytree_api_inverse_storage(ctx):
     import __graft_entry__ as g
     g.smoke()
+
+
+@pytest.mark.parametrize("order", [3, 5])
+def test_lagrange_orders_cart_and_cylinder(ctx, order):
+    """Orders 3/5 (directional 9/15 coefficients).  The oracle for these orders
+    is the reference C++ plus the C transliteration of four Fortran routines
+    (oracle/lagrange_restated.c)."""
+    Bg, Oc = cases.c2()
+    rng = np.random.default_rng(11)
+    sel = rng.choice(Oc[3].size, 1500 if order == 5 else 8000, replace=False)
+    sel.sort()
+    got, ref, gz, oz = _compare(ctx, [Bg], (Oc[3][sel], Oc[4][sel], Oc[5][sel]), order=order)
+    assert (got[2][0] == order).any()
+    r = np.sqrt(Bg[3] ** 2 + Bg[4] ** 2)
+    m = np.nonzero((r > 0.5) & (r < 2.5))[0]
+    sel = rng.choice(m, 1000 if order == 5 else 6000, replace=False)
+    sel.sort()
+    _compare(ctx, [Oc], (Bg[3][sel], Bg[4][sel], Bg[5][sel]), order=order)
+
+
+@pytest.mark.parametrize("order", [3, 5])
+@pytest.mark.parametrize("nature", [0, 1])
+def test_lagrange_multizone_holes(ctx, order, nature):
+    Bg, Oc = cases.c2()
+    rng = np.random.default_rng(1)
+    cb = np.ones(Bg[3].size); cb[rng.random(cb.size) < 0.03] = 0.; cb[rng.random(cb.size) < 0.03] = 2.
+    co = np.ones(Oc[3].size); co[rng.random(co.size) < 0.03] = 0.; co[rng.random(co.size) < 0.03] = 2.
+    npt = 1200 if order == 5 else 6000
+    P = rng.uniform(-3.3, 3.3, (3, npt)); P[2] = rng.uniform(-0.2, 2.2, npt)
+    _compare(ctx, [Bg, Oc], P, order=order, nature=nature, cellNs=[cb, co])
+    _compare(ctx, [Oc, Bg], P, order=order, nature=nature, extrap=0, cellNs=[co, cb])
+
+
+@pytest.mark.parametrize("order", [3, 5])
+def test_lagrange_coincident_and_transfer(ctx, order):
+    """C1a: receptors coincide with donor nodes -> type 1 collapse of the
+    directional weights; then order-3/5 transfers vs the reference loops and
+    linear-field exactness (Connector/test/setInterpTransfersPT_t1.py)."""
+    from cassiopee_b200 import _lib
+    from oracle import oracle as O
+    A, B = cases.c1("a", n=17, m=9)
+    _compare(ctx, [A], B[3:], order=order)
+    A, B = cases.c1("c", n=17, m=9)
+    got, ref, gz, oz = _compare(ctx, [A], B[3:], order=order)
+    rcv, dnr, typ, cf = got[0][0], got[1][0], got[2][0], got[3][0]
+    fD = cases.fields(A[3], A[4], A[5], 5) + [A[3] + 2 * A[4] + 3 * A[5]]
+    nR = B[3].size
+    fRg = [np.zeros(nR) for _ in fD]; fRo = [np.zeros(nR) for _ in fD]
+    plan = _lib.Plan(ctx, A[0], A[1], A[2], nR, dnr, rcv, typ, cf)
+    plan.transfer(fD, fRg)
+    O.transfer(fD, fRo, A[0], A[1], rcv, dnr, typ, cf)
+    for a, b in zip(fRg, fRo):
+        assert np.array_equal(a, b)
+    exact = B[3] + 2 * B[4] + 3 * B[5]
+    ext = np.zeros(nR, bool); ext[got[4][0]] = True
+    ok = np.zeros(nR, bool); ok[rcv] = True
+    assert np.abs(fRg[-1] - exact)[ok & ~ext].max() < 1e-10
