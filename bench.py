@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — chimera interpolation hot path on B200 (driver contract).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A "step" is one setInterpTransfers pass over all (donor zone, receptor zone)
+plans of the workload with the interpData already resident in HBM.
+  N=1  workload C2 (BASELINE.json configs[1]): Cartesian background 256^3 +
+       cylinder O-grid (513,129,257), order 2, ~17 M receptors, 5 variables.
+  N>1  workload C4/C5 (configs[3],[4]) weak-scaled at 8 zones of 100^3 per GPU
+       (4x4x4 blocks at N=8), 7 variables, zones placed by Distributor2-style
+       'proc', cross-GPU values over NCCL.
+metric = setInterpTransfers algorithmic GB/s (B_alg of SURVEY.md 8(d) / time);
+setInterpData receptor pts/s is reported in the same line under
+"set_interp_data".  The reference arm times the reference's own C++
+(oracle/_ref/libcassref.so, compiled from /root/reference) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "setInterpTransfers_algorithmic_GBps"
+UNIT = "GB/s"
+NVARS_C2 = 5
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------
+# workload C2 (single GPU)
+# --------------------------------------------------------------------------
+def build_c2(scale):
+    from cassiopee_b200 import workloads as W
+    Bg, Oc = W.c2(scale)
+    return Bg, Oc
+
+
+def alg_bytes(n, ncoef, nvars, distinct):
+    """B_alg of SURVEY.md 8(d): entries*(8*ncf+12) + 8*N*n + 8*N*U."""
+    return 8 * ncoef + 12 * n + 8 * nvars * n + 8 * nvars * distinct
+
+
+def run_c2(args):
+    from cassiopee_b200 import _lib
+    from cassiopee_b200 import workloads as W
+    ctx = _lib.default_context(0)
+    t0 = time.perf_counter()
+    Bg, Oc = build_c2(args.scale)
+    t_gen = time.perf_counter() - t0
+    nrcv = Oc.npts
+    # donor zone on the device (= the ADT hook): upload + level-synchronous ADT build
+    t0 = time.perf_counter()
+    zone = _lib.Zone(ctx, Bg.ni, Bg.nj, Bg.nk, Bg.x, Bg.y, Bg.z)
+    t_zone = time.perf_counter() - t0
+    zinfo = zone.info()
+
+    # ---- setInterpData: device-resident receptor coordinates -----------------
+    dxr = _lib.DeviceArray.from_host(ctx, Oc.x); dyr = _lib.DeviceArray.from_host(ctx, Oc.y)
+    dzr = _lib.DeviceArray.from_host(ctx, Oc.z)
+    sid_ms = []
+    res = None
+    for it in range(args.sid_warmup + args.sid_steps):
+        res = None
+        ctx.sync()
+        l0 = ctx.launches()
+        t0 = time.perf_counter()
+        res = _lib.set_interp_data_dev(ctx, nrcv, dxr.ptr, dyr.ptr, dzr.ptr, [zone], 2, 1, 1, 1)
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        if it >= args.sid_warmup:
+            sid_ms.append(dt * 1e3)
+        sid_launches = ctx.launches() - l0
+    st = res.stats()
+    # end to end through the host-pointer C ABI: H2D receptor coordinates + ADT build + search + D2H of the 7-list
+    t0 = time.perf_counter()
+    if args.quick:
+        out = res.fetch()
+    else:
+        zone_e = _lib.Zone(ctx, Bg.ni, Bg.nj, Bg.nk, Bg.x, Bg.y, Bg.z)
+        res_e = _lib.set_interp_data(ctx, Oc.x, Oc.y, Oc.z, [zone_e], 2, 1, 1, 1)
+        out = res_e.fetch()
+        del zone_e, res_e
+    sid_e2e_s = time.perf_counter() - t0
+    rcv, dnr, typ, coefs = out[0][0], out[1][0], out[2][0], out[3][0]
+    n = rcv.size
+    sid = {"value": nrcv / (np.mean(sid_ms) * 1e-3), "unit": "receptor pts/s", "receptors": int(nrcv),
+           "ms": float(np.mean(sid_ms)), "search_kernel_ms": float(st["search_ms"]),
+           "nodes_visited_per_query": float(st["nodes_visited"]) / max(1, nrcv),
+           "adt_build_ms": float(zinfo["build_ms"]), "adt_depth": int(zinfo["depth"]),
+           "adt_cells": int(zinfo["ncells"]), "zone_create_s": t_zone,
+           "e2e": {"value": nrcv / sid_e2e_s, "unit": "receptor pts/s",
+                   "includes": "H2D donor+receptor coords, ADT build, search, packing, D2H of index/type/coef lists",
+                   "h2d_bytes": int(8 * 3 * (Bg.npts + nrcv)), "d2h_bytes": int(12 * n + 8 * coefs.size)},
+           "interpolated": int(n), "orphans": int(out[5].size), "gpu_launches": int(sid_launches)}
+    res = None
+
+    # ---- transfers: plan + device-resident fields -----------------------------
+    nvars = args.nvars or NVARS_C2
+    plan = _lib.Plan(ctx, Bg.ni, Bg.nj, Bg.nk, nrcv, dnr, rcv, typ, coefs)
+    pinfo = plan.info()
+    B = alg_bytes(n, coefs.size, nvars, pinfo["distinct"])
+    fD = W.conservative_fields(Bg.x, Bg.y, Bg.z, nvars)
+    dD = [_lib.DeviceArray.from_host(ctx, f) for f in fD]
+    dR = [_lib.DeviceArray(ctx, nrcv) for _ in range(nvars)]
+    pD = [d.ptr for d in dD]; pR = [d.ptr for d in dR]
+    for _ in range(max(3, args.warmup)):
+        plan.transfer_dev(pD, pR)
+    ctx.sync()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = ctx.launches()
+    ctx.event_record(0)
+    for _ in range(args.steps):
+        plan.transfer_dev(pD, pR)
+    ctx.event_record(1)
+    ms_total = ctx.event_elapsed_ms()
+    ctx.sync()
+    launches = ctx.launches() - l0
+    ms_step = ms_total / args.steps
+    # keep the GPU busy a little longer so nvidia-smi gets samples under load
+    t_end = time.perf_counter() + 0.6
+    while time.perf_counter() < t_end:
+        for _ in range(20):
+            plan.transfer_dev(pD, pR)
+        ctx.sync()
+    clocks = sampler.stop()
+    value = B / (ms_step * 1e-3) / 1e9
+
+    # ---- end to end through the public API (host buffers, copies inside) ------
+    if args.quick:
+        e2e = None; cpu = None
+    else:
+        hD = [_lib.pinned_copy(f) for f in fD]
+        hR = [_lib.pinned_empty(nrcv) for _ in range(nvars)]
+        for a in hR:
+            a[:] = 0.
+        ne2e = max(2, min(args.steps, 5))
+        plan.transfer(hD, hR)
+        t0 = time.perf_counter()
+        for _ in range(ne2e):
+            plan.transfer(hD, hR)
+        e2e_s = (time.perf_counter() - t0) / ne2e
+        e2e = {"value": B / e2e_s / 1e9, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
+               "h2d_bytes_per_step": int(8 * nvars * Bg.npts), "d2h_bytes_per_step": int(8 * nvars * n),
+               "api": "cx_transfer (connector._setInterpTransfers boundary), pinned host fields"}
+        # ---- CPU baseline: the reference's own transfer loops on the host cores ----
+        cpu = cpu_baseline_transfer(fD, nrcv, Bg, rcv, dnr, typ, coefs, B, nvars)
+
+    peak, how = measured_peaks()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2a: cart 256^3 background -> cylinder O-grid (513,129,257) receptors, order 2, "
+                               "nature=1 penalty=1 extrap=1, %d vars" % nvars if args.scale == 1.0 else
+                               "C2a scaled x%g" % args.scale,
+                   "receptors": int(n), "donor_nodes": int(Bg.npts), "nvars": nvars, "alg_bytes_per_step": int(B),
+                   "distinct_donor_nodes": int(pinfo["distinct"]),
+                   "l2": "inputs larger than L2 (plan+fields %.2f GB per step, L2 126 MB); no flush" %
+                         ((B + 8 * nvars * (Bg.npts - pinfo["distinct"])) / 1e9),
+                   "parallelism": "1 GPU"},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": value, "peak": peak, "unit": "GB/s", "frac": value / peak,
+                     "traffic": None, "peak_source": how, "kernel": "k_transfer<2,0>",
+                     "frac_of_nominal_8TBps": value / 8000.0},
+        "cpu_baseline": cpu,
+        "set_interp_data": sid,
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline_transfer(fD, nrcv, Bg, rcv, dnr, typ, coefs, B, nvars, reps=2):
+    try:
+        from oracle import oracle as O
+        fR = [np.zeros(nrcv) for _ in range(nvars)]
+        O.transfer(fD, fR, Bg.ni, Bg.nj, rcv, dnr, typ, coefs)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            O.transfer(fD, fR, Bg.ni, Bg.nj, rcv, dnr, typ, coefs)
+        dt = (time.perf_counter() - t0) / reps
+        return {"value": B / dt / 1e9, "unit": UNIT, "cores": int(min(nvars, O.num_threads())), "kind": "reference",
+                "host_cores": os.cpu_count(), "ms_per_step": dt * 1e3,
+                "sample": "full workload, %d timed passes of the reference's commonInterpTransfers_indirect.h loop "
+                          "(parallel over variables only: min(nvars, threads) threads)" % reps}
+    except Exception as e:  # oracle missing on this box
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+
+
+# --------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation on the host cores
+# --------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    from cassiopee_b200 import workloads as W
+    nthreads = os.cpu_count() or 1
+    O.set_num_threads(nthreads)
+    if args.gpus == 1:
+        # bounded sample of C2a: donor = background coarsened to 128^3 (ADT build on the CPU is serial:
+        # the full 256^3 tree alone takes minutes), receptors = every 8th O-grid node.
+        Bg, Oc = W.c2(args.scale)
+        s = 2 if args.scale == 1.0 else 1
+        nb = (Bg.ni + s - 1) // s
+        sub = lambda a: np.ascontiguousarray(a.reshape((Bg.ni, Bg.nj, Bg.nk), order='F')[::s, ::s, ::s].reshape(-1, order='F'))
+        x, y, z = sub(Bg.x), sub(Bg.y), sub(Bg.z)
+        stride = 8 if args.scale == 1.0 else 1
+        xr, yr, zr = Oc.x[::stride].copy(), Oc.y[::stride].copy(), Oc.z[::stride].copy()
+        t0 = time.perf_counter()
+        zone = O.RefZone(nb, nb, nb, x, y, z)
+        t_adt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        out = O.set_interp_data(xr, yr, zr, [zone], 2, 1, 1, 1)
+        t_search = time.perf_counter() - t0
+        rcv, dnr, typ, coefs = out[0][0], out[1][0], out[2][0], out[3][0]
+        nvars = args.nvars or NVARS_C2
+        fD = W.conservative_fields(x, y, z, nvars)
+        nrcv = xr.size
+        fR = [np.zeros(nrcv) for _ in range(nvars)]
+        uniq = distinct_nodes(dnr, typ, nb, nb)
+        B = alg_bytes(rcv.size, coefs.size, nvars, uniq)
+        for _ in range(max(1, min(args.warmup, 2))):
+            O.transfer(fD, fR, nb, nb, rcv, dnr, typ, coefs)
+        steps = max(1, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.transfer(fD, fR, nb, nb, rcv, dnr, typ, coefs)
+        dt = (time.perf_counter() - t0) / steps
+        value = B / dt / 1e9
+        cfg = {"workload": "C2a bounded sample: background coarsened to %d^3, every %dth O-grid receptor (%d receptors), "
+                           "order 2, %d vars" % (nb, stride, nrcv, nvars), "receptors": int(rcv.size), "nvars": nvars,
+               "alg_bytes_per_step": int(B)}
+        sid = {"value": nrcv / (t_adt + t_search), "unit": "receptor pts/s", "receptors": int(nrcv),
+               "adt_build_s": t_adt, "search_s": t_search, "cores": nthreads,
+               "note": "hook=None semantics: serial ADT build inside (InterpAdt.cpp:284-433)"}
+    else:
+        value, dt, steps, cfg, sid, nvars = reference_c4(args, O, W, nthreads)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(min(nvars, nthreads)), "kind": "reference",
+                             "host_cores": os.cpu_count(),
+                             "sample": cfg["workload"] + "; transfer threads = min(nvars, host threads)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "set_interp_data": sid, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def distinct_nodes(dnr, typ, imd, jmd):
+    """U of SURVEY.md 8(d) on the host (numpy.unique of the expanded stencils)."""
+    sel = []
+    ij = imd * jmd
+    for t, o in ((1, 1), (2, 2), (3, 3), (5, 5)):
+        m = dnr[typ == t].astype(np.int64)
+        if m.size == 0:
+            continue
+        for kk in range(o):
+            for jj in range(o):
+                for ii in range(o):
+                    sel.append(m + ii + jj * imd + kk * ij)
+    if not sel:
+        return 0
+    return int(np.unique(np.concatenate(sel)).size)
+
+
+def reference_c4(args, O, W, nthreads):
+    from bench_c4 import reference_c4 as impl
+    return impl(args, O, W, nthreads)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the C2 grids (debug only)")
+    ap.add_argument("--nvars", type=int, default=0)
+    ap.add_argument("--sid-steps", type=int, default=3, dest="sid_steps")
+    ap.add_argument("--sid-warmup", type=int, default=1, dest="sid_warmup")
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c4"])
+    ap.add_argument("--quick", action="store_true", help="skip the e2e and CPU-baseline legs (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if (args.gpus > 1 or world > 1 or args.workload == "c4") and args.workload != "c2":
+        from bench_c4 import run_c4
+        return run_c4(args)
+    return run_c2(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -392,3 +392,34 @@ class Plan:
         """B_alg of SURVEY.md 8(d) for one call with nvars variables."""
         i = self.info()
         return i["alg_fixed"] + 8 * nvars * (i["n"] + i["distinct"])
+
+
+class _PinnedBlock:
+    def __init__(self, nbytes):
+        p = _vp()
+        check(lib().cx_pinned_alloc(int(nbytes), ctypes.byref(p)))
+        self.ptr = p.value
+        self.nbytes = int(nbytes)
+        self._fin = weakref.finalize(self, lib().cx_pinned_free, _vp(self.ptr))
+
+
+def pinned_empty(n, dtype=np.float64):
+    """numpy array backed by page-locked host memory (cudaHostAlloc); the
+    memory is released when the array (and its views) are collected."""
+    dtype = np.dtype(dtype)
+    blk = _PinnedBlock(max(1, int(n)) * dtype.itemsize)
+    buf = (ctypes.c_byte * blk.nbytes).from_address(blk.ptr)
+    a = np.frombuffer(buf, dtype=dtype, count=int(n))
+    _PINNED_KEEP[id(buf)] = blk
+    weakref.finalize(buf, _PINNED_KEEP.pop, id(buf), None)
+    return a
+
+
+_PINNED_KEEP = {}
+
+
+def pinned_copy(a):
+    a = np.asarray(a)
+    out = pinned_empty(a.size, a.dtype)
+    out[:] = a.reshape(-1, order='A')
+    return out
