@@ -1,0 +1,67 @@
+"""CPU tests of the DEVICE logic: cassiopee_b200/csrc/cx_core.cuh (the header
+the CUDA kernels are built from) compiled for the host by tests/hostemu and
+compared with the oracle: level-synchronous ADT build (with a shuffled
+insertion-claim order), DFS candidate order, jump walk / fallback, 24-tetra
+coefficients, cellN validity, cross-zone selection, extrapolation.  Bit-exact."""
+import numpy as np
+import pytest
+from tests import cases
+from tests.hostemu import emu as E
+from oracle import oracle as O
+
+
+def _compare(dz, pts, nature=1, penalty=1, extrap=1, cellNs=None):
+    oz, ez = [], []
+    for i, z in enumerate(dz):
+        c = cellNs[i] if cellNs else None
+        oz.append(O.RefZone(*z, cellN=c)); ez.append(E.EmuZone(*z, cellN=c))
+        assert np.array_equal(oz[-1].bbox(), ez[-1].bb)
+    ro = O.set_interp_data_raw(pts[0], pts[1], pts[2], oz, 2, nature, penalty, extrap)
+    re = E.set_interp_data_raw(pts[0], pts[1], pts[2], ez, nature, penalty, extrap)
+    for k in ("noblk", "type", "dind", "isext"):
+        assert np.array_equal(ro[k], re[k]), k
+    cfo = ro["cf"][:, :8].copy(); cfe = re["cf"].copy()
+    t1 = ro["type"] == 1
+    cfo[t1, 1:] = 0; cfe[t1, 1:] = 0
+    assert np.array_equal(cfo, cfe)
+    return ro
+
+
+@pytest.mark.parametrize("variant", ["a", "b", "c"])
+def test_c1_small(variant):
+    A, B = cases.c1(variant, n=17, m=11)
+    r = _compare([A], B[3:])
+    assert (r["noblk"] == 1).all()
+    r = _compare([B], A[3:])
+    assert r["isext"].sum() > 0
+
+
+def test_candidate_lists():
+    A, B = cases.c1("a", n=13, m=7)
+    oz = O.RefZone(*A); ez = E.EmuZone(*A)
+    rng = np.random.default_rng(3)
+    pts = list(zip(B[3][:60], B[4][:60], B[5][:60])) + [tuple(p) for p in rng.uniform(-0.1, 1.1, (60, 3))]
+    for (x, y, z) in pts:
+        for alpha in (0.0, 7.5):
+            assert np.array_equal(ez.candidates(x, y, z, alpha), oz.candidates(x, y, z, alpha))
+
+
+def test_cylinder_and_multizone_holes():
+    Bg, Oc = cases.c2(nb=20, nc=(33, 9, 17))
+    _compare([Bg], Oc[3:])
+    _compare([Oc], Bg[3:])
+    rng = np.random.default_rng(0)
+    cb = np.ones(Bg[3].size); cb[rng.random(cb.size) < 0.05] = 0.; cb[rng.random(cb.size) < 0.05] = 2.
+    co = np.ones(Oc[3].size); co[rng.random(co.size) < 0.05] = 0.; co[rng.random(co.size) < 0.05] = 2.
+    P = rng.uniform(-3.3, 3.3, (3, 4000)); P[2] = rng.uniform(-0.2, 2.2, 4000)
+    for nature in (0, 1):
+        for penalty in (0, 1):
+            _compare([Bg, Oc], P, nature, penalty, 1, [cb, co])
+            _compare([Oc, Bg], P, nature, penalty, 0, [co, cb])
+
+
+def test_volume_matches():
+    Bg, Oc = cases.c2(nb=12, nc=(17, 7, 9))
+    oz = O.RefZone(*Oc); ez = E.EmuZone(*Oc)
+    for ind in (0, 5, 17 * 3 + 4, 17 * 7 * 2 + 17 * 2 + 3):
+        assert oz.volume(ind) == ez.volume(ind)
