@@ -19,6 +19,8 @@
 #include "cx_internal.h"
 #include <algorithm>
 #include <string.h>
+#include <stdlib.h>
+#include <vector>
 
 #define CX_MAXVARS 16
 
@@ -131,6 +133,43 @@ __global__ void k_transfer_celln(int m, const double* __restrict__ cellND, doubl
 static int ncf_host(int t) { return t == 1 ? 1 : t == 2 ? 8 : t == 3 ? 9 : t == 5 ? 15 : -1; }
 static int sten_host(int t) { return t == 1 ? 1 : t == 2 ? 8 : t == 3 ? 27 : t == 5 ? 125 : 0; }
 
+namespace {
+// plan build: counting sort of one type group by donor index (so a warp's
+// stencil gathers come from adjacent donor cells) + slot-major coefficients
+__global__ void k_plan_hist(int n, int T, const int* __restrict__ type, const int* __restrict__ donor,
+                            unsigned long long* __restrict__ cnt)
+{
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n || type[e] != T) return;
+  atomicAdd(&cnt[donor[e]], 1ull);
+}
+__global__ void k_plan_place(int n, int T, int ncf, int m, int sorted, const int* __restrict__ type,
+                             const int* __restrict__ donor, const int* __restrict__ rcv,
+                             const unsigned long long* __restrict__ off, const double* __restrict__ coefs,
+                             unsigned long long* cursor, const unsigned long long* rank,
+                             int* __restrict__ od, int* __restrict__ orc, int* __restrict__ op, double* __restrict__ cfT)
+{
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n || type[e] != T) return;
+  int d0 = donor[e];
+  int slot = sorted ? (int)atomicAdd(&cursor[d0], 1ull) : (int)rank[e];
+  od[slot] = d0; orc[slot] = rcv[e]; op[slot] = e;
+  const double* c = coefs + off[e];
+  for (int k = 0; k < ncf; k++) cfT[(size_t)k * m + slot] = c[k];
+}
+__global__ void k_plan_flag(int n, int T, const int* __restrict__ type, unsigned long long* __restrict__ f)
+{
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) f[e] = (type[e] == T) ? 1ull : 0ull;
+}
+}  // namespace
+
+static int plan_sort_mode()
+{
+  const char* s = getenv("CX_PLAN_SORT");
+  return (s && s[0] == '0') ? 0 : 1;
+}
+
 int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long nptsR, int n, const int* donor,
                   const int* rcv, const int* type, const double* coefs, long long ncoefs, cx_plan* P)
 {
@@ -139,12 +178,12 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
   P->groups.clear();
   if (n == 0) { P->ngroups = 0; return 0; }
   const int types[4] = {1, 2, 3, 5};
-  std::vector<long long> off((size_t)n + 1);
+  std::vector<unsigned long long> off((size_t)n);
   long long run = 0;
   int cnt[4] = {0, 0, 0, 0};
   for (int e = 0; e < n; e++)
   {
-    off[e] = run;
+    off[e] = (unsigned long long)run;
     int nc = ncf_host(type[e]);
     if (nc < 0) { cx_set_error("transfer plan: interpolation type %d is not supported (structured donors: 1,2,3,5)", type[e]); return -1; }
     if (donor[e] < 0 || (long long)donor[e] >= nptsD) { cx_set_error("transfer plan: donor index %d out of range", donor[e]); return -1; }
@@ -152,38 +191,55 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
     run += nc;
     for (int g = 0; g < 4; g++) if (type[e] == types[g]) cnt[g]++;
   }
-  off[n] = run;
   if (run != ncoefs) { cx_set_error("transfer plan: coefficient array has %lld entries, types need %lld", ncoefs, run); return -1; }
   P->alg_bytes_fixed = 8 * run + 12ll * n;
-  std::vector<int> hd(n), hr(n), hp(n);
+  cudaStream_t s = ctx->stream;
+  const size_t N = n;
+  int *r_dn, *r_rc, *r_ty; unsigned long long *r_off, *d_cnt, *d_scan; double* r_cf;
+  CX_CUDA(cudaMalloc(&r_dn, sizeof(int) * N)); CX_CUDA(cudaMalloc(&r_rc, sizeof(int) * N));
+  CX_CUDA(cudaMalloc(&r_ty, sizeof(int) * N)); CX_CUDA(cudaMalloc(&r_off, sizeof(unsigned long long) * N));
+  CX_CUDA(cudaMalloc(&r_cf, sizeof(double) * (size_t)std::max(run, 1ll)));
+  const int sorted = plan_sort_mode();
+  const size_t nscan = sorted ? (size_t)nptsD : N;
+  CX_CUDA(cudaMalloc(&d_cnt, sizeof(unsigned long long) * nscan));
+  CX_CUDA(cudaMalloc(&d_scan, sizeof(unsigned long long) * nscan));
+  CX_CUDA(cudaMemcpyAsync(r_dn, donor, sizeof(int) * N, cudaMemcpyHostToDevice, s));
+  CX_CUDA(cudaMemcpyAsync(r_rc, rcv, sizeof(int) * N, cudaMemcpyHostToDevice, s));
+  CX_CUDA(cudaMemcpyAsync(r_ty, type, sizeof(int) * N, cudaMemcpyHostToDevice, s));
+  CX_CUDA(cudaMemcpyAsync(r_off, off.data(), sizeof(unsigned long long) * N, cudaMemcpyHostToDevice, s));
+  CX_CUDA(cudaMemcpyAsync(r_cf, coefs, sizeof(double) * (size_t)run, cudaMemcpyHostToDevice, s));
+  CX_CUDA(cudaMalloc(&P->d_donor, sizeof(int) * N));
+  CX_CUDA(cudaMalloc(&P->d_rcv, sizeof(int) * N));
+  CX_CUDA(cudaMalloc(&P->d_pos, sizeof(int) * N));
+  const int TB = 256;
   int first = 0;
   for (int g = 0; g < 4; g++)
   {
     if (cnt[g] == 0) continue;
     cx_plan::Group G; G.type = types[g]; G.ncf = ncf_host(types[g]); G.sten = sten_host(types[g]);
     G.n = cnt[g]; G.first = first; G.d_cf = nullptr;
-    std::vector<double> cfT((size_t)G.ncf * G.n);
-    int a = 0;
-    for (int e = 0; e < n; e++)
+    CX_CUDA(cudaMalloc(&G.d_cf, sizeof(double) * (size_t)G.ncf * G.n));
+    if (sorted)
     {
-      if (type[e] != G.type) continue;
-      hd[first + a] = donor[e]; hr[first + a] = rcv[e]; hp[first + a] = e;
-      const double* c = coefs + off[e];
-      for (int k = 0; k < G.ncf; k++) cfT[(size_t)k * G.n + a] = c[k];
-      a++;
+      CX_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * nscan, s));
+      k_plan_hist<<<cx_grid(n, TB), TB, 0, s>>>(n, G.type, r_ty, r_dn, d_cnt);
+      CX_CHECK(cx_exclusive_scan_u64(ctx, d_cnt, d_scan, (int)nscan, nullptr));
     }
-    CX_CUDA(cudaMalloc(&G.d_cf, sizeof(double) * cfT.size()));
-    CX_CUDA(cudaMemcpy(G.d_cf, cfT.data(), sizeof(double) * cfT.size(), cudaMemcpyHostToDevice));
+    else
+    {
+      k_plan_flag<<<cx_grid(n, TB), TB, 0, s>>>(n, G.type, r_ty, d_cnt);
+      CX_CHECK(cx_exclusive_scan_u64(ctx, d_cnt, d_scan, n, nullptr));
+    }
+    k_plan_place<<<cx_grid(n, TB), TB, 0, s>>>(n, G.type, G.ncf, G.n, sorted, r_ty, r_dn, r_rc, r_off, r_cf, d_scan,
+                                              d_scan, P->d_donor + first, P->d_rcv + first, P->d_pos + first, G.d_cf);
+    ctx->launches += 2;
     P->groups.push_back(G);
     first += G.n;
   }
   P->ngroups = (int)P->groups.size();
-  CX_CUDA(cudaMalloc(&P->d_donor, sizeof(int) * (size_t)n));
-  CX_CUDA(cudaMalloc(&P->d_rcv, sizeof(int) * (size_t)n));
-  CX_CUDA(cudaMalloc(&P->d_pos, sizeof(int) * (size_t)n));
-  CX_CUDA(cudaMemcpy(P->d_donor, hd.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
-  CX_CUDA(cudaMemcpy(P->d_rcv, hr.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
-  CX_CUDA(cudaMemcpy(P->d_pos, hp.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+  CX_CUDA(cudaStreamSynchronize(s));
+  CX_CUDA(cudaGetLastError());
+  cudaFree(r_dn); cudaFree(r_rc); cudaFree(r_ty); cudaFree(r_off); cudaFree(r_cf); cudaFree(d_cnt); cudaFree(d_scan);
   return 0;
 }
 
