@@ -257,9 +257,9 @@ class Zone:
 
     def export_adt(self):
         nc = self.info()["ncells"]
-        dt = np.dtype([("bb", np.float64, 6), ("mid", np.float64), ("rlo", np.float64), ("left", np.int32),
-                       ("right", np.int32), ("dim", np.int32), ("ind", np.int32)])
-        assert dt.itemsize == 80
+        dt = np.dtype([("bb", np.float64, 6), ("sub", np.float64, 6), ("mid", np.float64), ("rlo", np.float64),
+                       ("left", np.int32), ("right", np.int32), ("dim", np.int32), ("ind", np.int32)])
+        assert dt.itemsize == 128
         out = np.zeros(nc, dtype=dt)
         check(lib().cx_zone_export_adt(self.h, ptr(out), out.nbytes))
         return out

@@ -70,6 +70,13 @@ __global__ void k_claim(int L, int nact, const int* __restrict__ act, BuildView 
   }
 }
 
+__global__ void k_subtree(int ncells, int L, const int* __restrict__ depth, AdtNode* nodes)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells || depth[c] != L) return;
+  adt_subtree_box(nodes, c);
+}
+
 __global__ void k_resolve(int L, int nact, const int* __restrict__ act, BuildView B, int* __restrict__ next,
                           int* __restrict__ counter)
 {
@@ -132,6 +139,8 @@ int cx_build_adt(cx_zone* z)
   CX_CUDA(cudaMalloc(&B.hi, sizeof(double) * 6 * n));
   CX_CUDA(cudaMalloc(&B.cur, sizeof(int) * n));
   CX_CUDA(cudaMalloc(&B.br, n));
+  CX_CUDA(cudaMalloc(&B.depth, sizeof(int) * n));
+  CX_CUDA(cudaMemsetAsync(B.depth, 0, sizeof(int) * n, s));
   CX_CUDA(cudaMalloc(&S.actA, sizeof(int) * n));
   CX_CUDA(cudaMalloc(&S.actB, sizeof(int) * n));
   CX_CUDA(cudaMalloc(&S.counter, sizeof(int) * 2));
@@ -165,13 +174,19 @@ int cx_build_adt(cx_zone* z)
     L++;
     if (L > 4096) { cx_set_error("ADT deeper than 4096 levels (degenerate/duplicate cells)"); return -3; }
   }
+  // subtree bounding boxes, deepest level first
+  for (int lv = depth - 1; lv >= 0; lv--)
+  {
+    k_subtree<<<cx_grid(n, TB), TB, 0, s>>>(ncells, lv, B.depth, z->d_nodes);
+    ctx->launches++;
+  }
   CX_CUDA(cudaEventRecord(ctx->ev1, s));
   CX_CUDA(cudaStreamSynchronize(s));
   CX_CUDA(cudaGetLastError());
   cudaEventElapsedTime(&z->build_ms, ctx->ev0, ctx->ev1);
   z->depth = depth;
   z->levels = L;
-  cudaFree(B.keys); cudaFree(B.lo); cudaFree(B.hi); cudaFree(B.cur); cudaFree(B.br);
+  cudaFree(B.keys); cudaFree(B.lo); cudaFree(B.hi); cudaFree(B.cur); cudaFree(B.br); cudaFree(B.depth);
   cudaFree(S.actA); cudaFree(S.actB); cudaFree(S.counter);
   if (depth + 2 > CX_STACK)
   {

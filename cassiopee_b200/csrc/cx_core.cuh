@@ -47,8 +47,9 @@ namespace cx {
 #define CX_EPS_GEOM 1.e-8
 #define CX_MAXF 1.7976931348623157e308
 
-struct AdtNode {   // 80 B, 16-B aligned
+struct AdtNode {   // 128 B = one cache line
   double bb[6];    // xmin,ymin,zmin,xmax,ymax,zmax of the cell
+  double sub[6];   // bounding box of all the cells stored in this node's subtree
   double mid;      // descend left  iff a[dim] <= mid
   double rlo;      // descend right iff b[dim] >= rlo
   int left, right; // node ids (CX_NULL = none)
@@ -86,6 +87,7 @@ struct AdtQuery {
   double px, py, pz, alphaTol;
   int stack[CX_STACK];
   int sp;
+  int prune;            // 1: skip subtrees whose bounding box cannot hold a candidate (alphaTol == 0 only)
 };
 
 CX_D bool zone_reject(const ZoneView& Z, double x, double y, double z, double alphaTol)
@@ -110,6 +112,19 @@ CX_D void query_init(AdtQuery& q, const ZoneView& Z, double x, double y, double 
   q.b[3] = Z.bbox[3]; q.b[4] = Z.bbox[4]; q.b[5] = Z.bbox[5];
   q.px = x; q.py = y; q.pz = z; q.alphaTol = alphaTol;
   q.stack[0] = 0; q.sp = 1;
+  q.prune = (alphaTol == 0.0) ? 1 : 0;
+}
+
+// No node of the subtree can pass node_is_candidate (alphaTol = 0) when the
+// point is outside the subtree box inflated by 1e-8: fl(xmax_c + 1e-8) is
+// monotone in xmax_c, so x < xmax_c + 1e-8 implies x < sub_xmax + 1e-8.
+// Skipping such a subtree therefore leaves the reference's candidate list
+// (and its order) unchanged while cutting the visited nodes several-fold.
+CX_D bool subtree_may_hold(const AdtNode& n, double x, double y, double z)
+{
+  return (x < n.sub[3] + CX_EPS_GEOM && x > n.sub[0] - CX_EPS_GEOM &&
+          y < n.sub[4] + CX_EPS_GEOM && y > n.sub[1] - CX_EPS_GEOM &&
+          z < n.sub[5] + CX_EPS_GEOM && z > n.sub[2] - CX_EPS_GEOM);
 }
 
 CX_D bool node_is_candidate(const AdtNode& n, double x, double y, double z, double alphaTol)
@@ -130,11 +145,12 @@ CX_D int query_next(AdtQuery& q, const AdtNode* __restrict__ nodes, int* nodeId,
   {
     int id = q.stack[--q.sp];
     const AdtNode& n = nodes[id];
+    (*nvisit)++;
+    if (q.prune && !subtree_may_hold(n, q.px, q.py, q.pz)) continue;
     int d = n.dim;
     // left pushed first, right second => right popped first (InterpAdt.cpp:768-925)
     if (q.a[d] <= n.mid && n.left != CX_NULL) q.stack[q.sp++] = n.left;
     if (q.b[d] >= n.rlo && n.right != CX_NULL) q.stack[q.sp++] = n.right;
-    (*nvisit)++;
     if (node_is_candidate(n, q.px, q.py, q.pz, q.alphaTol)) { *nodeId = id; return n.ind; }
   }
   return -1;
@@ -684,6 +700,7 @@ struct ZoneBox { double lo[6], hi[6]; };   // region of the root for the 6 keys
 struct BuildView {
   double* keys; double* lo; double* hi;    // [6][ncells]
   int* cur; unsigned char* br; AdtNode* nodes;
+  int* depth;                              // [ncells] depth at which each cell was placed
   int ncells;
   ZoneBox zb;
 };
@@ -729,6 +746,7 @@ CX_D bool adt_resolve(const BuildView& B, int L, int c)
     if (depth < 6) { l = B.zb.lo[d]; h = B.zb.hi[d]; }
     else { size_t o = (size_t)d * B.ncells + c; l = B.lo[o]; h = B.hi[o]; }
     freeze_node(B.nodes[c], depth, l, h);
+    B.depth[c] = depth;
     return true;
   }
   B.cur[c] = w;
@@ -760,8 +778,26 @@ CX_D void adt_cell_keys(int ni, int nj, int nk, const double* x, const double* y
   keys[3 * n + c] = xmax; keys[4 * n + c] = ymax; keys[5 * n + c] = zmax;
   AdtNode nd;
   nd.bb[0] = xmin; nd.bb[1] = ymin; nd.bb[2] = zmin; nd.bb[3] = xmax; nd.bb[4] = ymax; nd.bb[5] = zmax;
+  for (int d = 0; d < 6; d++) nd.sub[d] = nd.bb[d];
   nd.mid = 0.; nd.rlo = 0.; nd.left = CX_NULL; nd.right = CX_NULL; nd.dim = 0; nd.ind = ind;
   nodes[c] = nd;
+}
+
+// bottom-up pass (deepest level first): subtree box = own box U children's boxes
+CX_D void adt_subtree_box(AdtNode* nodes, int c)
+{
+  AdtNode& n = nodes[c];
+  for (int side = 0; side < 2; side++)
+  {
+    int ch = side ? n.right : n.left;
+    if (ch == CX_NULL) continue;
+    const AdtNode& m = nodes[ch];
+    for (int d = 0; d < 3; d++)
+    {
+      if (m.sub[d] < n.sub[d]) n.sub[d] = m.sub[d];
+      if (m.sub[d + 3] > n.sub[d + 3]) n.sub[d + 3] = m.sub[d + 3];
+    }
+  }
 }
 
 }  // namespace cx

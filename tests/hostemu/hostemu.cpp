@@ -36,8 +36,8 @@ void* emu_zone_create(int ni, int nj, int nk, const double* x, const double* y, 
   int n = Z->ncells;
   Z->nodes.resize(n);
   std::vector<double> keys(6 * (size_t)n), lo(6 * (size_t)n), hi(6 * (size_t)n);
-  std::vector<int> cur(n, 0); std::vector<unsigned char> br(n, 0);
-  BuildView B; B.keys = keys.data(); B.lo = lo.data(); B.hi = hi.data(); B.cur = cur.data(); B.br = br.data();
+  std::vector<int> cur(n, 0), dep(n, 0); std::vector<unsigned char> br(n, 0);
+  BuildView B; B.keys = keys.data(); B.lo = lo.data(); B.hi = hi.data(); B.cur = cur.data(); B.br = br.data(); B.depth = dep.data();
   B.nodes = Z->nodes.data(); B.ncells = n;
   for (int d = 0; d < 6; d++) { B.zb.lo[d] = bbox[d % 3]; B.zb.hi[d] = bbox[3 + d % 3]; }
   for (int c = 0; c < n; c++) adt_cell_keys(ni, nj, nk, x, y, z, c, n, B.keys, B.nodes);
@@ -61,6 +61,8 @@ void* emu_zone_create(int ni, int nj, int nk, const double* x, const double* y, 
     L++;
   }
   Z->depth = depth;
+  for (int lv = depth - 1; lv >= 0; lv--)
+    for (int c = 0; c < n; c++) if (dep[c] == lv) adt_subtree_box(B.nodes, c);
   return Z;
 }
 
