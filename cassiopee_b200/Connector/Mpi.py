@@ -1,0 +1,397 @@
+"""Distributed chimera path: zones partitioned across ranks (one process per GPU).
+
+Mirror of the reference's Connector/Connector/Mpi.py for this path:
+  _setInterpData     :858-1022  receptor owner computes; intersecting donor zones
+                                are replicated first (Cmpi._addXZones, :941), the
+                                resulting ID_* subregions are routed to the donor
+                                zone's owner (Cmpi.sendRecv, :1012)
+  _setInterpTransfers :396-440  donor owner runs setInterpTransfersD; local pairs
+                                are scattered in place, remote ones are sent and
+                                scattered on arrival
+Zone placement is the `.Solver#Param/proc` node (Distributor2).  Bulk data
+moves with the library's NCCL communicator (device) or gloo (CPU tests);
+see cassiopee_b200/Mpi.py.  TransferSession is the device-resident steady
+state: all plans of a rank fused in one launch, one packed NCCL message per
+rank pair and iteration, one scatter launch.
+"""
+import numpy
+from .. import Internal
+from .. import Converter as C
+from .. import _lib
+from ..workloads import bbox_intersect
+from . import OversetData as X
+
+
+def _zoneBBox(z):
+    x, y, zz = C.getCoords(z)
+    return [float(x.min()), float(y.min()), float(zz.min()), float(x.max()), float(y.max()), float(zz.max())]
+
+
+def _receptorBBox(z, loc):
+    return _zoneBBox(z)
+
+
+def _makeZone(name, ni, nj, nk, x, y, z, cellN):
+    zn = Internal.newZone(name, ni, nj, nk)
+    gc = Internal.createChild(zn, Internal.__GridCoordinates__, 'GridCoordinates_t')
+    shp = (ni, nj, nk)
+    for nm, a in (('CoordinateX', x), ('CoordinateY', y), ('CoordinateZ', z)):
+        Internal.createChild(gc, nm, 'DataArray_t', numpy.asfortranarray(a.reshape(shp, order='F')))
+    fs = Internal.createChild(zn, Internal.__FlowSolutionNodes__, 'FlowSolution_t')
+    Internal.createChild(fs, 'cellN', 'DataArray_t', numpy.asfortranarray(cellN.reshape(shp, order='F')))
+    return zn
+
+
+def computeDonorGraph(aR, aD, comm, loc='nodes', sameName=1, zoneOrder=None):
+    """Global donor metadata and, per local receptor zone, the ordered list of
+    bbox-intersecting donor zones (what Connector/Mpi.py:950-983 builds with
+    getIntersectingDomains + hooks).  Order = zoneOrder (names) if given, else
+    (rank, position) order, so results do not depend on who computes."""
+    local = []
+    for z in Internal.getZones(aD):
+        _, ni, nj, nk, _ = Internal.getZoneDim(z)
+        local.append(dict(name=z[0], dims=(ni, nj, nk), bbox=_zoneBBox(z), rank=comm.rank))
+    allmeta = comm.allgather_obj(local)
+    meta = [m for part in allmeta for m in part]
+    if zoneOrder is not None:
+        pos = {n: i for i, n in enumerate(zoneOrder)}
+        meta.sort(key=lambda m: pos[m['name']])
+    donorLists = {}
+    for z in Internal.getZones(aR):
+        bb = _receptorBBox(z, loc)
+        donorLists[z[0]] = [m['name'] for m in meta
+                            if not (sameName == 1 and m['name'] == z[0]) and bbox_intersect(bb, m['bbox'])]
+    return meta, donorLists
+
+
+def _addXZones(aD, meta, donorLists, comm):
+    """Replicate the remote donor zones this rank needs (coordinates + cellN):
+    analogue of Cmpi._addXZones(aD, graph, variables=['cellN'])."""
+    byname = {m['name']: m for m in meta}
+    need = sorted({n for lst in donorLists.values() for n in lst if byname[n]['rank'] != comm.rank})
+    allneed = comm.allgather_obj(need)
+    localz = {z[0]: z for z in Internal.getZones(aD)}
+    send = {}
+    for p, lst in enumerate(allneed):
+        if p == comm.rank:
+            continue
+        parts = []
+        for n in lst:
+            if n in localz:
+                z = localz[n]
+                x, y, zz = C.getCoords(z)
+                c = C.getFieldArray(z, 'cellN')
+                npts = x.size
+                parts += [x.reshape(npts, order='F'), y.reshape(npts, order='F'), zz.reshape(npts, order='F'),
+                          c.reshape(npts, order='F') if c is not None else numpy.ones(npts)]
+        if parts:
+            send[p] = numpy.concatenate(parts)
+    recv_sizes = {}
+    for n in need:
+        m = byname[n]
+        recv_sizes[m['rank']] = recv_sizes.get(m['rank'], 0) + 4 * m['dims'][0] * m['dims'][1] * m['dims'][2]
+    got = comm.exchange_host(send, recv_sizes, dtype=numpy.float64)
+    added = []
+    off = {p: 0 for p in recv_sizes}
+    for n in need:     # sorted, same order as the sender's packing
+        m = byname[n]; p = m['rank']
+        ni, nj, nk = m['dims']; npts = ni * nj * nk
+        buf = got[p]; o = off[p]
+        zn = _makeZone(n, ni, nj, nk, buf[o:o + npts], buf[o + npts:o + 2 * npts], buf[o + 2 * npts:o + 3 * npts],
+                       buf[o + 3 * npts:o + 4 * npts])
+        off[p] = o + 4 * npts
+        added.append(zn)
+    return added
+
+
+_FIELDS = (('PointList', numpy.int32), ('PointListDonor', numpy.int32), ('InterpolantsType', numpy.int32),
+           ('InterpolantsDonor', numpy.float64), ('ExtrapPointList', numpy.int32), ('OrphanPointList', numpy.int32))
+
+
+def _setInterpData(aR, aD, order=2, penalty=1, nature=0, extrap=1, method='lagrangian', loc='nodes',
+                   storage='inverse', interpDataType=1, hook=None, verbose=0, sameName=1, dim=3, itype='chimera',
+                   comm=None, zoneOrder=None, backend=None, ctx=None):
+    """Distributed setInterpData, storage='inverse': on return every local donor
+    zone of aD carries the ID_<receptor> subregions of all receptor zones
+    (local or remote) it feeds.  aR / aD hold the zones owned by this rank."""
+    if storage != 'inverse':
+        raise NotImplementedError("Mpi._setInterpData: only storage='inverse' is distributed.")
+    if comm is None or comm.size == 1:
+        return X._setInterpDataChimera(aR, aD, order=order, penalty=penalty, nature=nature, extrap=extrap,
+                                       method=method, loc=loc, storage=storage, interpDataType=interpDataType,
+                                       hook=hook, verbose=verbose, sameName=sameName, dim=dim, itype=itype,
+                                       ctx=ctx, backend=backend,
+                                       donorLists=computeDonorGraph(aR, aD, _Single(), loc, sameName, zoneOrder)[1])
+    hadCellN = {z[0]: C.isNamePresent(z, 'cellN') for z in Internal.getZones(aD)}
+    X._addCellN__(aD, loc='nodes')
+    meta, donorLists = computeDonorGraph(aR, aD, comm, loc, sameName, zoneOrder)
+    byname = {m['name']: m for m in meta}
+    added = _addXZones(aD, meta, donorLists, comm)
+    # working donor list: local zones + replicated ones, in the global order
+    zonesL = {z[0]: z for z in Internal.getZones(aD)}
+    work = []
+    for m in meta:
+        if m['name'] in zonesL: work.append(zonesL[m['name']])
+    addedByName = {z[0]: z for z in added}
+    for m in meta:
+        if m['name'] in addedByName: work.append(addedByName[m['name']])
+    order_pos = {m['name']: i for i, m in enumerate(meta)}
+    work.sort(key=lambda z: order_pos[z[0]])
+    X._setInterpDataChimera(aR, work, order=order, penalty=penalty, nature=nature, extrap=extrap, method=method,
+                            loc=loc, storage='inverse', interpDataType=interpDataType, hook=None, verbose=verbose,
+                            sameName=sameName, dim=dim, itype='chimera', donorLists=donorLists, ctx=ctx,
+                            backend=backend)
+    # route the subregions created under replicated zones to their owners
+    outMeta = {}
+    outData = {}
+    for z in added:
+        p = byname[z[0]]['rank']
+        for s in Internal.getNodesFromType1(z, 'ZoneSubRegion_t'):
+            if not s[0].startswith('ID_'):
+                continue
+            rec = dict(donor=z[0], rcv=Internal.getValue(s),
+                       centers=Internal.getNodeFromName1(s, 'GridLocation') is not None, sizes=[])
+            for name, dt in _FIELDS:
+                node = Internal.getNodeFromName1(s, name)
+                a = numpy.zeros(0, dt) if node is None else numpy.ascontiguousarray(node[1], dtype=dt)
+                rec['sizes'].append(int(a.size))
+                outData.setdefault(p, []).append(a.view(numpy.uint8))
+            outMeta.setdefault(p, []).append(rec)
+    allMeta = comm.allgather_obj(outMeta)
+    send = {p: numpy.concatenate(parts) if parts else numpy.zeros(0, numpy.uint8) for p, parts in outData.items()}
+    recv_sizes = {}
+    for q, om in enumerate(allMeta):
+        if q == comm.rank or comm.rank not in om:
+            continue
+        tot = 0
+        for rec in om[comm.rank]:
+            for (name, dt), n in zip(_FIELDS, rec['sizes']):
+                tot += n * numpy.dtype(dt).itemsize
+        recv_sizes[q] = tot
+    got = comm.exchange_host(send, recv_sizes, dtype=numpy.uint8)
+    for q in sorted(recv_sizes):
+        buf = got[q]; o = 0
+        for rec in allMeta[q][comm.rank]:
+            arrs = []
+            for (name, dt), n in zip(_FIELDS, rec['sizes']):
+                nb = n * numpy.dtype(dt).itemsize
+                arrs.append(buf[o:o + nb].view(dt).copy()); o += nb
+            zd = zonesL[rec['donor']]
+            X._createInterpRegion__(zd, rec['rcv'], arrs[0], arrs[1], arrs[3], arrs[2], numpy.array([], numpy.float64),
+                                    arrs[4], arrs[5], tag='Donor', loc='centers' if rec['centers'] else 'nodes')
+    for z in Internal.getZones(aD):
+        if hadCellN.get(z[0], 1) == -1: C._rmVars(z, ['cellN'])
+    return None
+
+
+class _Single:
+    rank = 0
+    size = 1
+
+    def allgather_obj(self, o):
+        return [o]
+
+
+def _rcvFieldName(v, loc):
+    return ('centers:' + v) if loc == 'centers' else v
+
+
+def _setInterpTransfers(aR, aD, variables=[], cellNVariable='', storage=1, comm=None, backend=None, ctx=None):
+    """Distributed setInterpTransfers on host trees (reference semantics,
+    Connector/Mpi.py:396-440): donor-side dense transfer per ID_* subregion,
+    in-place scatter for local receptor zones, send + scatter for remote ones."""
+    infos = X._setInterpTransfersD(aD, variables=variables, cellNVariable=cellNVariable, ctx=ctx, backend=backend)
+    zr = {z[0]: z for z in Internal.getZones(aR)}
+    owners = {}
+    if comm is not None and comm.size > 1:
+        for p, names in enumerate(comm.allgather_obj(sorted(zr.keys()))):
+            for n in names: owners[n] = p
+    outMeta, outData = {}, {}
+    for rcvName, arr, ListRcv, loc in infos:
+        names = arr[0].split(',') if arr[0] else []
+        if rcvName in zr:
+            _scatter(zr[rcvName], names, arr[1], ListRcv, loc)
+        elif rcvName in owners:
+            p = owners[rcvName]
+            outMeta.setdefault(p, []).append(dict(rcv=rcvName, names=names, n=int(ListRcv.size), loc=loc))
+            outData.setdefault(p, []).append(numpy.ascontiguousarray(ListRcv, dtype=numpy.int32).view(numpy.uint8))
+            outData[p].append(numpy.ascontiguousarray(arr[1], dtype=numpy.float64).reshape(-1).view(numpy.uint8))
+    if comm is None or comm.size == 1:
+        return None
+    allMeta = comm.allgather_obj(outMeta)
+    send = {p: numpy.concatenate(parts) for p, parts in outData.items()}
+    recv_sizes = {}
+    for q, om in enumerate(allMeta):
+        if q != comm.rank and comm.rank in om:
+            recv_sizes[q] = sum(4 * r['n'] + 8 * r['n'] * len(r['names']) for r in om[comm.rank])
+    got = comm.exchange_host(send, recv_sizes, dtype=numpy.uint8)
+    for q in sorted(recv_sizes):
+        buf = got[q]; o = 0
+        for r in allMeta[q][comm.rank]:
+            n = r['n']; nv = len(r['names'])
+            lst = buf[o:o + 4 * n].view(numpy.int32); o += 4 * n
+            vals = buf[o:o + 8 * n * nv].view(numpy.float64).reshape(nv, n); o += 8 * n * nv
+            _scatter(zr[r['rcv']], r['names'], vals, lst, r['loc'])
+    return None
+
+
+def _scatter(z, names, vals, ListRcv, loc):
+    """C._setPartialFields analogue: fieldR[v][ListRcv] = vals[v]."""
+    for v, name in enumerate(names):
+        f = C.getFieldArray(z, _rcvFieldName(name, loc))
+        if f is None:
+            continue
+        f.reshape(-1, order='F')[ListRcv] = vals[v]
+
+
+# ---------------------------------------------------------------------------
+# device-resident steady state
+# ---------------------------------------------------------------------------
+class TransferSession:
+    """All ID_* plans of this rank resident on the GPU: donor fields
+    (FlowSolution of aD zones) and receptor fields (container at the
+    subregion's GridLocation in aR zones) are uploaded once; step() runs one
+    fused transfer launch per interpolation type, one grouped NCCL
+    send/recv (one packed buffer per peer rank) and one scatter launch."""
+
+    def __init__(self, aR, aD, variables, comm=None, ctx=None):
+        self.ctx = ctx or _lib.default_context()
+        self.comm = comm
+        self.variables = list(variables)
+        nv = len(self.variables)
+        ctx = self.ctx
+        rank = comm.rank if comm is not None else 0
+        size = comm.size if comm is not None else 1
+        self.zr = {z[0]: z for z in Internal.getZones(aR)}
+        owners = {}
+        if size > 1:
+            for p, names in enumerate(comm.allgather_obj(sorted(self.zr.keys()))):
+                for n in names: owners[n] = p
+        else:
+            owners = {n: 0 for n in self.zr}
+        # resident fields
+        self.dD, self.dR, self.hR = {}, {}, {}
+        self.h2d_bytes = 0
+        for zd in Internal.getZones(aD):
+            arrs = [C.getFieldArray(zd, v) for v in self.variables]
+            if any(a is None for a in arrs):
+                continue
+            self.dD[zd[0]] = [_lib.DeviceArray.from_host(ctx, a.reshape(-1, order='F')) for a in arrs]
+            self.h2d_bytes += sum(a.nbytes for a in arrs)
+        self._aD = aD
+        self.plans = []
+        items = []
+        remote = {}       # peer -> list of (donorName, rcvName, plan)
+        self.alg_fixed = 0; self.n_entries = 0; self.distinct = 0
+        for zd in Internal.getZones(aD):
+            if zd[0] not in self.dD:
+                continue
+            _, imd, jmd, kmd, _ = Internal.getZoneDim(zd)
+            for s in Internal.getNodesFromType1(zd, 'ZoneSubRegion_t'):
+                if not s[0].startswith('ID_') or Internal.getNodeFromName1(s, 'InterpolantsDonor') is None:
+                    continue
+                rname = Internal.getValue(s)
+                loc = 'centers' if Internal.getNodeFromName1(s, 'GridLocation') is not None else 'nodes'
+                ListDonor = Internal.getNodeFromName1(s, 'PointList')[1]
+                ListRcv = Internal.getNodeFromName1(s, 'PointListDonor')[1]
+                typ = Internal.getNodeFromName1(s, 'InterpolantsType')[1]
+                cf = Internal.getNodeFromName1(s, 'InterpolantsDonor')[1]
+                if rname in self.zr:
+                    zr = self.zr[rname]
+                    nptsR = int(numpy.prod(C.fieldShape(zr, loc)))
+                    self._residentR(zr, loc)
+                    plan = _lib.Plan(ctx, imd, jmd, kmd, nptsR, ListDonor, ListRcv, typ, cf)
+                    items.append((plan, 0, [d.ptr for d in self.dD[zd[0]]], [d.ptr for d in self.dR[rname]], None, 0))
+                elif rname in owners:
+                    nmax = int(ListRcv.max()) + 1 if ListRcv.size else 1
+                    plan = _lib.Plan(ctx, imd, jmd, kmd, nmax, ListDonor, ListRcv, typ, cf)
+                    remote.setdefault(owners[rname], []).append((zd[0], rname, plan, ListRcv, loc))
+                else:
+                    continue
+                self.plans.append(plan)
+                info = plan.info()
+                self.alg_fixed += info['alg_fixed']; self.n_entries += info['n']; self.distinct += info['distinct']
+        # send buffers: one per peer, blocks (nvars, n_pair) in (donor, receptor) name order
+        self.sendbuf, self.sendcnt = {}, {}
+        outMeta, outIdx = {}, {}
+        for p, lst in remote.items():
+            lst.sort(key=lambda t: (t[0], t[1]))
+            tot = sum(t[2].n for t in lst) * nv
+            self.sendbuf[p] = _lib.DeviceArray(ctx, max(tot, 1))
+            self.sendcnt[p] = tot
+            o = 0
+            for dn, rn, plan, ListRcv, loc in lst:
+                items.append((plan, 1, [d.ptr for d in self.dD[dn]], None, self.sendbuf[p].ptr + 8 * o, plan.n))
+                outMeta.setdefault(p, []).append(dict(donor=dn, rcv=rn, n=int(plan.n), loc=loc))
+                outIdx.setdefault(p, []).append(numpy.ascontiguousarray(ListRcv, dtype=numpy.int32).view(numpy.uint8))
+                o += plan.n * nv
+        self.planset = _lib.PlanSet(ctx, nv, items)
+        # receive side: index lists are exchanged once
+        self.recvbuf, self.recvcnt = {}, {}
+        sitems = []
+        self._keep = []
+        if size > 1:
+            allMeta = comm.allgather_obj(outMeta)
+            send = {p: numpy.concatenate(parts) for p, parts in outIdx.items()}
+            recv_sizes = {q: sum(4 * r['n'] for r in om[rank]) for q, om in enumerate(allMeta)
+                          if q != rank and rank in om}
+            got = comm.exchange_host(send, recv_sizes, dtype=numpy.uint8)
+            for q in sorted(recv_sizes):
+                recs = allMeta[q][rank]
+                tot = sum(r['n'] for r in recs) * nv
+                self.recvbuf[q] = _lib.DeviceArray(ctx, max(tot, 1)); self.recvcnt[q] = tot
+                o = 0; ob = 0
+                for r in recs:
+                    n = r['n']
+                    lst = got[q][ob:ob + 4 * n].view(numpy.int32).copy(); ob += 4 * n
+                    zr = self.zr[r['rcv']]
+                    self._residentR(zr, r['loc'])
+                    dl = _lib.DeviceArray.from_host(ctx, lst)
+                    self._keep.append(dl)
+                    sitems.append((n, dl, self.recvbuf[q].ptr + 8 * o, n, [d.ptr for d in self.dR[r['rcv']]]))
+                    o += n * nv
+        self.scatterset = _lib.ScatterSet(ctx, nv, sitems)
+        self.peers = sorted(set(self.sendbuf) | set(self.recvbuf))
+        ctx.sync()
+
+    def _residentR(self, zr, loc):
+        if zr[0] in self.dR:
+            return
+        arrs = [C.getFieldArray(zr, _rcvFieldName(v, loc)) for v in self.variables]
+        self.hR[zr[0]] = arrs
+        self.dR[zr[0]] = [_lib.DeviceArray.from_host(self.ctx, a.reshape(-1, order='F')) for a in arrs]
+
+    def alg_bytes(self):
+        """B_alg of SURVEY.md 8(d) summed over this rank's plans."""
+        nv = len(self.variables)
+        return self.alg_fixed + 8 * nv * (self.n_entries + self.distinct)
+
+    def nccl_bytes(self):
+        return 8 * sum(self.sendcnt.values())
+
+    def upload_donor_fields(self):
+        for zd in Internal.getZones(self._aD):
+            if zd[0] in self.dD:
+                for d, v in zip(self.dD[zd[0]], self.variables):
+                    d.upload(C.getFieldArray(zd, v).reshape(-1, order='F'))
+
+    def step(self):
+        self.planset.run()
+        if self.peers:
+            sp = [self.sendbuf[p].ptr if p in self.sendbuf else 0 for p in self.peers]
+            sc = [self.sendcnt.get(p, 0) for p in self.peers]
+            rp = [self.recvbuf[p].ptr if p in self.recvbuf else 0 for p in self.peers]
+            rc = [self.recvcnt.get(p, 0) for p in self.peers]
+            self.comm.exchange_dev(self.peers, sp, sc, rp, rc)
+            self.scatterset.run()
+
+    def download(self):
+        """Copy the receptor fields back into the host tree (in place)."""
+        self.ctx.sync()
+        nb = 0
+        for name, arrs in self.hR.items():
+            for d, a in zip(self.dR[name], arrs):
+                tmp = d.download()
+                a.reshape(-1, order='F')[:] = tmp
+                nb += tmp.nbytes
+        return nb

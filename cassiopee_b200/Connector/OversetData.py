@@ -191,7 +191,7 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
                           method='lagrangian', loc='nodes', storage='direct',
                           interpDataType=1, hook=None, verbose=2,
                           topTreeRcv=None, topTreeDnr=None, sameName=1, dim=3, itype='both', dictOfModels=None,
-                          donorLists=None, ctx=None):
+                          donorLists=None, ctx=None, backend=None):
     """donorLists (extension, optional): dict receptorZoneName -> list of donor
     zone names to consider, in that order — what Connector/Mpi.py:950-983 does
     with bbox-intersecting donors; None = all donors like the sequential API."""
@@ -219,7 +219,8 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
 
     zonesRcv = Internal.getZones(aR)
     zonesDnrL = Internal.getZones(aD)
-    ctx = ctx or _lib.default_context()
+    if backend is None:
+        backend = _lib.DeviceBackend(ctx or _lib.default_context())
 
     # device donor zones: the hook list given by the caller, or built once here
     if hook is not None:
@@ -230,14 +231,17 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
         allHooksL = hook[:]
         for h, zd in zip(allHooksL, zonesDnrL):   # cellN may have changed since the hook was built
             c = C.getFieldArray(zd, 'cellN')
-            h.set_celln(c.reshape(-1, order='F') if c is not None else None)
+            backend.set_celln(h, c.reshape(-1, order='F') if c is not None else None)
     else:
         allHooksL = [None] * len(zonesDnrL)
 
     def hookOf(i):
         if allHooksL[i] is None:
             a = _zoneArray(zonesDnrL[i])
-            allHooksL[i] = Connector.createHooks__([a], ctx)[0]
+            f = a[1]
+            allHooksL[i] = backend.make_zone(a[2], a[3], a[4], numpy.ascontiguousarray(f[0]),
+                                             numpy.ascontiguousarray(f[1]), numpy.ascontiguousarray(f[2]),
+                                             numpy.ascontiguousarray(f[3]) if f.shape[0] > 3 else None)
         return allHooksL[i]
 
     try:
@@ -276,12 +280,18 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
                 continue
 
             # Etape 2: interpolation data on the device
-            resInterp = Connector.setInterpData__(interpPts, [None] * nzonesDnr, order=order, penalty=penalty,
-                                                  nature=nature, extrap=extrap, method=method,
-                                                  interpDataType=interpDataType, hook=[hookOf(i) for i in idx],
-                                                  dim=dim, ctx=ctx)
-            if resInterp is None:
+            if interpPts[1].shape[1] == 0:
                 continue
+            types = interpDataType if isinstance(interpDataType, list) else [interpDataType] * nzonesDnr
+            for ty in types:
+                if ty not in (0, 1):
+                    raise TypeError("setInterpData: InterpDataType must be 0 for CART or 1 for ADT.")
+                if ty == 0:
+                    raise NotImplementedError("setInterpData: interpDataType=0 (InterpCart) has no device path.")
+            f = interpPts[1]
+            resInterp = backend.set_interp_data(numpy.ascontiguousarray(f[0]), numpy.ascontiguousarray(f[1]),
+                                                numpy.ascontiguousarray(f[2]), [hookOf(i) for i in idx],
+                                                order, nature, penalty, extrap)
             nbinterpolated = interpPts[1].shape[1]
             nbextrapolated = sum(r.shape[0] for r in resInterp[4])
             nborphan = resInterp[5].size
@@ -466,14 +476,15 @@ def _setInterpTransfersD(topTreeD, variables=[], cellNVariable='',
                          variablesIBC=['Density', 'VelocityX', 'VelocityY', 'VelocityZ', 'Temperature'],
                          bcType=0, varType=2, compact=0, compactD=0,
                          Gamma=1.4, Cv=1.7857142857142865, MuS=1.e-08,
-                         Cs=0.3831337844872463, Ts=1.0, extract=0, alpha=1., ctx=None):
+                         Cs=0.3831337844872463, Ts=1.0, extract=0, alpha=1., ctx=None, backend=None):
     """Donor-side transfer: list of [rcvZoneName, array(nvars,nrcv), ListRcv, loc]
     (OversetData.py:2179-2270; connector._setInterpTransfersD,
     setInterpTransfersD.cpp:106-303: listed variables present in the donor's
     FlowSolution, or all of them but cellNVariable for an empty list)."""
     if compact != 0:
         raise NotImplementedError("_setInterpTransfersD: compact=1 has no device path yet.")
-    ctx = ctx or _lib.default_context()
+    if backend is None:
+        ctx = ctx or _lib.default_context()
     infos = []
     for zd in Internal.getZones(topTreeD):
         for s in Internal.getNodesFromType1(zd, 'ZoneSubRegion_t'):
@@ -498,7 +509,11 @@ def _setInterpTransfersD(topTreeD, variables=[], cellNVariable='',
                     names = [v for v in varsD if v != cellNVariable]
                     withCellN = False
                 nmax = int(ListRcv.max()) + 1 if ListRcv.size else 1
-                plan = _getPlan(ctx, zd, nmax, ListDonor, ListRcv, DonorType, Coefs)
+                if backend is None:
+                    plan = _getPlan(ctx, zd, nmax, ListDonor, ListRcv, DonorType, Coefs)
+                else:
+                    _, imd, jmd, kmd, _ = Internal.getZoneDim(zd)
+                    plan = backend.make_plan(imd, jmd, kmd, nmax, ListDonor, ListRcv, DonorType, Coefs)
                 arr = plan.transferD([C.getFieldArray(zd, v) for v in names])
                 varString = ','.join(names)
                 if withCellN:

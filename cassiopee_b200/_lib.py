@@ -61,11 +61,18 @@ _SIGS = {
     "cx_scatter_dev": (_i, [_vp, _i, _vp, _ll, _i, _vp, _vp]),
     "cx_plan_info": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "cx_plan_destroy": (_i, [_vp]),
+    "cx_planset_create": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cx_planset_run": (_i, [_vp]),
+    "cx_planset_destroy": (_i, [_vp]),
+    "cx_scatterset_create": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cx_scatterset_run": (_i, [_vp]),
+    "cx_scatterset_destroy": (_i, [_vp]),
     "cx_comm_unique_id": (_i, [_vp]),
     "cx_comm_init": (_i, [_vp, _i, _i, _vp]),
     "cx_comm_destroy": (_i, [_vp]),
     "cx_comm_barrier": (_i, [_vp]),
     "cx_exchange_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "cx_exchange_bytes_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
 }
 
 EXPORTED_SYMBOLS = sorted(_SIGS.keys())
@@ -423,3 +430,83 @@ def pinned_copy(a):
     out = pinned_empty(a.size, a.dtype)
     out[:] = a.reshape(-1, order='A')
     return out
+
+
+class PlanSet:
+    """Every plan of a rank fused into one launch per interpolation type
+    (cx_planset).  items: list of (plan, mode, donorFieldPtrs, receptorFieldPtrs|None, densePtr|None, ld)."""
+
+    def __init__(self, ctx, nvars, items):
+        self.ctx = ctx
+        self.items = items     # keep plans / arrays alive
+        n = len(items)
+        plans = (ctypes.c_void_p * max(n, 1))(*[it[0].h.value for it in items])
+        modes = (ctypes.c_int * max(n, 1))(*[int(it[1]) for it in items])
+        self._tabs = []
+        fD = (ctypes.c_void_p * max(n, 1))()
+        fR = (ctypes.c_void_p * max(n, 1))()
+        dn = (ctypes.c_void_p * max(n, 1))()
+        ld = (ctypes.c_longlong * max(n, 1))()
+        for i, it in enumerate(items):
+            td = ptr_array(it[2]); self._tabs.append(td)
+            fD[i] = ctypes.cast(td, ctypes.c_void_p).value
+            if it[1] == 0:
+                tr = ptr_array(it[3]); self._tabs.append(tr)
+                fR[i] = ctypes.cast(tr, ctypes.c_void_p).value
+            else:
+                dn[i] = it[4]; ld[i] = int(it[5])
+        h = _vp()
+        check(lib().cx_planset_create(ctx.h, n, plans, int(nvars), modes, fD, fR, dn, ld, ctypes.byref(h)))
+        self.h = h
+        self._fin = weakref.finalize(self, lib().cx_planset_destroy, h)
+
+    def run(self):
+        check(lib().cx_planset_run(self.h))
+
+
+class ScatterSet:
+    """Receptor-side scatter of all received dense blocks in one launch (cx_scatterset).
+    items: list of (n, rcvIndexDeviceArray, inPtr, ld, receptorFieldPtrs)."""
+
+    def __init__(self, ctx, nvars, items):
+        self.ctx = ctx
+        self.items = items
+        n = len(items)
+        cnt = (ctypes.c_int * max(n, 1))(*[int(it[0]) for it in items])
+        rcv = (ctypes.c_void_p * max(n, 1))(*[it[1].ptr for it in items])
+        din = (ctypes.c_void_p * max(n, 1))(*[it[2] for it in items])
+        ld = (ctypes.c_longlong * max(n, 1))(*[int(it[3]) for it in items])
+        self._tabs = []
+        fR = (ctypes.c_void_p * max(n, 1))()
+        for i, it in enumerate(items):
+            tr = ptr_array(it[4]); self._tabs.append(tr)
+            fR[i] = ctypes.cast(tr, ctypes.c_void_p).value
+        h = _vp()
+        check(lib().cx_scatterset_create(ctx.h, n, int(nvars), cnt, rcv, din, ld, fR, ctypes.byref(h)))
+        self.h = h
+        self._fin = weakref.finalize(self, lib().cx_scatterset_destroy, h)
+
+    def run(self):
+        check(lib().cx_scatterset_run(self.h))
+
+
+class DeviceBackend:
+    """Compute backend of the Python layer = the CUDA library.  (The distributed
+    host logic takes a backend object so the CPU tests can inject the oracle;
+    the product only ever constructs this one.)"""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+
+    def make_zone(self, ni, nj, nk, x, y, z, cellN=None):
+        return Zone(self.ctx, ni, nj, nk, x, y, z, cellN)
+
+    def set_celln(self, hook, cellN):
+        hook.set_celln(cellN)
+
+    def set_interp_data(self, xr, yr, zr, hooks, order, nature, penalty, extrap):
+        res = set_interp_data(self.ctx, xr, yr, zr, hooks, order, nature, penalty, extrap)
+        return res.fetch()
+
+    def make_plan(self, imd, jmd, kmd, nptsR, donor, rcv, typ, coefs):
+        return Plan(self.ctx, imd, jmd, kmd, nptsR, donor, rcv, typ, coefs)

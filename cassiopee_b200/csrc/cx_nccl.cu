@@ -117,4 +117,19 @@ int cx_exchange_dev(cx_ctx* ctx, int npeers, const int* peers, const double* con
   return 0;
 }
 
+int cx_exchange_bytes_dev(cx_ctx* ctx, int npeers, const int* peers, const void* const* d_send,
+                          const long long* sendbytes, void* const* d_recv, const long long* recvbytes)
+{
+  cx_comm* c = (cx_comm*)ctx->nccl;
+  if (!c) { cx_set_error("communicator not initialised"); return -5; }
+  CX_NCCL(g_nccl.GroupStart());
+  for (int p = 0; p < npeers; p++)
+  {
+    if (sendbytes[p] > 0) CX_NCCL(g_nccl.Send(d_send[p], (size_t)sendbytes[p], 0 /*ncclInt8*/, peers[p], c->comm, ctx->stream));
+    if (recvbytes[p] > 0) CX_NCCL(g_nccl.Recv(d_recv[p], (size_t)recvbytes[p], 0 /*ncclInt8*/, peers[p], c->comm, ctx->stream));
+  }
+  CX_NCCL(g_nccl.GroupEnd());
+  return 0;
+}
+
 }  // extern "C"

@@ -30,25 +30,23 @@ namespace {
 
 template <int O> struct Sten { };
 
-// MODE 0: scatter to fieldR[v][rcv[e]];  MODE 1: dense out[v*ld + pos[e]]
-template <int TYPE, int MODE>
-__global__ void __launch_bounds__(256)
-k_transfer(int m, int nvars, FieldPtrs P, int imd, int imdjmd, const int* __restrict__ donor,
-           const int* __restrict__ rcv, const int* __restrict__ pos, const double* __restrict__ cfT,
-           double* __restrict__ dense, long long ld)
+// One entry of one plan.  MODE 0: scatter to fieldR[v][rcv[e]];  MODE 1: dense out[v*ld + pos[e]].
+// PD/PR: anything indexable by variable (kernel-parameter struct or device pointer table).
+template <int TYPE, int MODE, class PD, class PR>
+__device__ __forceinline__ void transfer_entry(int e, int m, int nvars, const PD& pd, const PR& pr, int imd, int imdjmd,
+                                               const int* __restrict__ donor, const int* __restrict__ idx,
+                                               const double* __restrict__ cfT, double* __restrict__ dense,
+                                               long long ld)
 {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= m) return;
   const int d0 = donor[e];
-  size_t o;
-  if (MODE == 0) o = (size_t)rcv[e]; else o = (size_t)pos[e];
+  const size_t o = (size_t)idx[e];
   if (TYPE == 1)
   {
     double c0 = cfT[e];
     for (int v = 0; v < nvars; v++)
     {
-      double val = c0 * __ldg(P.d[v] + d0);
-      if (MODE == 0) P.r[v][o] = val; else dense[(size_t)v * ld + o] = val;
+      double val = c0 * __ldg(pd[v] + d0);
+      if (MODE == 0) pr[v][o] = val; else dense[(size_t)v * ld + o] = val;
     }
   }
   else if (TYPE == 2)
@@ -58,7 +56,7 @@ k_transfer(int m, int nvars, FieldPtrs P, int imd, int imdjmd, const int* __rest
     for (int k = 0; k < 8; k++) c[k] = cfT[(size_t)k * m + e];
     for (int v = 0; v < nvars; v++)
     {
-      const double* f = P.d[v] + d0;
+      const double* f = pd[v] + d0;
       double val = 0.;
       val += c[0] * __ldg(f);
       val += c[1] * __ldg(f + 1);
@@ -68,7 +66,7 @@ k_transfer(int m, int nvars, FieldPtrs P, int imd, int imdjmd, const int* __rest
       val += c[5] * __ldg(f + imdjmd + 1);
       val += c[6] * __ldg(f + imdjmd + imd);
       val += c[7] * __ldg(f + imdjmd + imd + 1);
-      if (MODE == 0) P.r[v][o] = val; else dense[(size_t)v * ld + o] = val;
+      if (MODE == 0) pr[v][o] = val; else dense[(size_t)v * ld + o] = val;
     }
   }
   else
@@ -79,9 +77,9 @@ k_transfer(int m, int nvars, FieldPtrs P, int imd, int imdjmd, const int* __rest
     for (int k = 0; k < 3 * O; k++) c[k] = cfT[(size_t)k * m + e];
     for (int v = 0; v < nvars; v++)
     {
-      const double* f = P.d[v] + d0;
+      const double* f = pd[v] + d0;
       double val = 0.;
-#pragma unroll
+#pragma unroll 1
       for (int kk = 0; kk < O; kk++)
 #pragma unroll
         for (int jj = 0; jj < O; jj++)
@@ -91,9 +89,58 @@ k_transfer(int m, int nvars, FieldPtrs P, int imd, int imdjmd, const int* __rest
           for (int ii = 0; ii < O; ii++)
             val += c[ii] * c[jj + O] * c[kk + 2 * O] * __ldg(g + ii);   // left to right, as commonInterpTransfers.h:85,141
         }
-      if (MODE == 0) P.r[v][o] = val; else dense[(size_t)v * ld + o] = val;
+      if (MODE == 0) pr[v][o] = val; else dense[(size_t)v * ld + o] = val;
     }
   }
+}
+
+struct PDk { const double* const* p; __device__ __forceinline__ const double* operator[](int v) const { return p[v]; } };
+struct PRk { double* const* p; __device__ __forceinline__ double* operator[](int v) const { return p[v]; } };
+
+template <int TYPE, int MODE>
+__global__ void __launch_bounds__(256)
+k_transfer(int m, int nvars, FieldPtrs P, int imd, int imdjmd, const int* __restrict__ donor,
+           const int* __restrict__ rcv, const int* __restrict__ pos, const double* __restrict__ cfT,
+           double* __restrict__ dense, long long ld)
+{
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m) return;
+  PDk pd{P.d}; PRk pr{P.r};
+  transfer_entry<TYPE, MODE>(e, m, nvars, pd, pr, imd, imdjmd, donor, MODE == 0 ? rcv : pos, cfT, dense, ld);
+}
+
+// Plan set: every (plan, type group) of a rank in ONE launch.  Block b works on
+// descriptor blk2desc[b]; field pointers come from per-zone device tables.
+struct SetDesc {
+  int m, type, imd, imdjmd, mode, first_block;
+  const int* donor; const int* idx; const double* cfT;
+  const double* const* dptr;   // device table: nvars donor field pointers
+  double* const* rptr;         // device table: nvars receptor field pointers (mode 0)
+  double* dense; long long ld; // mode 1
+};
+
+template <int TYPE>
+__global__ void __launch_bounds__(256)
+k_transfer_set(const SetDesc* __restrict__ descs, const int* __restrict__ blk2desc, int nvars)
+{
+  const SetDesc D = descs[blk2desc[blockIdx.x]];
+  int e = (blockIdx.x - D.first_block) * blockDim.x + threadIdx.x;
+  if (e >= D.m) return;
+  PDk pd{D.dptr}; PRk pr{D.rptr};
+  if (D.mode == 0) transfer_entry<TYPE, 0>(e, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
+  else transfer_entry<TYPE, 1>(e, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
+}
+
+// Receptor-side batched scatter of received dense buffers: fieldR[v][rcv[e]] = in[v*ld + e]
+struct ScatDesc { int n, first_block; const int* rcv; const double* in; long long ld; double* const* rptr; };
+__global__ void __launch_bounds__(256)
+k_scatter_set(const ScatDesc* __restrict__ descs, const int* __restrict__ blk2desc, int nvars)
+{
+  const ScatDesc D = descs[blk2desc[blockIdx.x]];
+  int e = (blockIdx.x - D.first_block) * blockDim.x + threadIdx.x;
+  if (e >= D.n) return;
+  int r = D.rcv[e];
+  for (int v = 0; v < nvars; v++) D.rptr[v][r] = D.in[(size_t)v * D.ld + e];
 }
 
 // strict cellN rule (commonCellNTransfersStrict.h): product of cellN*(2-cellN)
@@ -297,3 +344,155 @@ int cx_plan_launch_celln(cx_plan* P, const double* dCellND, double* dCellNR, cud
   }
   return 0;
 }
+
+
+// ---------------------------------------------------------------------------
+// plan set / scatter set
+// ---------------------------------------------------------------------------
+struct cx_planset {
+  cx_ctx* ctx;
+  int nvars, ndesc;
+  int nblocks[4];                       // per interpolation type 1,2,3,5
+  SetDesc* d_descs[4]; int* d_blk2desc[4];
+  void** d_tables; size_t ntables;      // device pointer tables owned by the set
+};
+
+struct cx_scatterset {
+  cx_ctx* ctx;
+  int nvars, nblocks, ndesc;
+  ScatDesc* d_descs; int* d_blk2desc;
+  std::vector<void*> owned;
+};
+
+static int upload_ptr_table(const double* const* host, int nvars, double*** out)
+{
+  double** d;
+  CX_CUDA(cudaMalloc(&d, sizeof(double*) * (size_t)nvars));
+  CX_CUDA(cudaMemcpy(d, host, sizeof(double*) * (size_t)nvars, cudaMemcpyHostToDevice));
+  *out = d;
+  return 0;
+}
+
+extern "C" {
+
+// modes[p]: 0 in-place into d_fieldR[p] (nvars device pointers), 1 dense into d_dense[p] with leading dim ld[p]
+int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars, const int* modes,
+                      const double* const* const* d_fieldD, double* const* const* d_fieldR, double* const* d_dense,
+                      const long long* ld, cx_planset** out)
+{
+  CX_CUDA(cudaSetDevice(ctx->device));
+  cx_planset* S = new cx_planset;
+  S->ctx = ctx; S->nvars = nvars; S->d_tables = nullptr; S->ntables = 0; S->ndesc = 0;
+  std::vector<SetDesc> descs[4]; std::vector<int> b2d[4]; std::vector<void*> tables;
+  const int TB = 256;
+  int nb[4] = {0, 0, 0, 0};
+  for (int p = 0; p < nplans; p++)
+  {
+    cx_plan* P = plans[p];
+    if (P->n == 0) continue;
+    double** td = nullptr; double** tr = nullptr;
+    CX_CHECK(upload_ptr_table(d_fieldD[p], nvars, &td)); tables.push_back(td);
+    if (modes[p] == 0) { CX_CHECK(upload_ptr_table((const double* const*)d_fieldR[p], nvars, &tr)); tables.push_back(tr); }
+    for (auto& G : P->groups)
+    {
+      int t = G.type == 1 ? 0 : G.type == 2 ? 1 : G.type == 3 ? 2 : 3;
+      SetDesc D;
+      D.m = G.n; D.type = G.type; D.imd = P->imd; D.imdjmd = P->imd * P->jmd; D.mode = modes[p]; D.first_block = nb[t];
+      D.donor = P->d_donor + G.first; D.idx = (modes[p] == 0 ? P->d_rcv : P->d_pos) + G.first; D.cfT = G.d_cf;
+      D.dptr = td; D.rptr = tr; D.dense = modes[p] == 1 ? d_dense[p] : nullptr; D.ld = modes[p] == 1 ? ld[p] : 0;
+      int blocks = cx_grid(G.n, TB);
+      for (int b = 0; b < blocks; b++) b2d[t].push_back((int)descs[t].size());
+      descs[t].push_back(D);
+      nb[t] += blocks;
+      S->ndesc++;
+    }
+  }
+  for (int t = 0; t < 4; t++)
+  {
+    S->nblocks[t] = nb[t]; S->d_descs[t] = nullptr; S->d_blk2desc[t] = nullptr;
+    if (nb[t] == 0) continue;
+    CX_CUDA(cudaMalloc(&S->d_descs[t], sizeof(SetDesc) * descs[t].size()));
+    CX_CUDA(cudaMalloc(&S->d_blk2desc[t], sizeof(int) * b2d[t].size()));
+    CX_CUDA(cudaMemcpy(S->d_descs[t], descs[t].data(), sizeof(SetDesc) * descs[t].size(), cudaMemcpyHostToDevice));
+    CX_CUDA(cudaMemcpy(S->d_blk2desc[t], b2d[t].data(), sizeof(int) * b2d[t].size(), cudaMemcpyHostToDevice));
+  }
+  S->ntables = tables.size();
+  S->d_tables = (void**)malloc(sizeof(void*) * (tables.size() + 1));
+  for (size_t i = 0; i < tables.size(); i++) S->d_tables[i] = tables[i];
+  *out = S;
+  return 0;
+}
+
+int cx_planset_run(cx_planset* S)
+{
+  cudaStream_t s = S->ctx->stream;
+  if (S->nblocks[0]) { k_transfer_set<1><<<S->nblocks[0], 256, 0, s>>>(S->d_descs[0], S->d_blk2desc[0], S->nvars); S->ctx->launches++; }
+  if (S->nblocks[1]) { k_transfer_set<2><<<S->nblocks[1], 256, 0, s>>>(S->d_descs[1], S->d_blk2desc[1], S->nvars); S->ctx->launches++; }
+  if (S->nblocks[2]) { k_transfer_set<3><<<S->nblocks[2], 256, 0, s>>>(S->d_descs[2], S->d_blk2desc[2], S->nvars); S->ctx->launches++; }
+  if (S->nblocks[3]) { k_transfer_set<5><<<S->nblocks[3], 256, 0, s>>>(S->d_descs[3], S->d_blk2desc[3], S->nvars); S->ctx->launches++; }
+  return 0;
+}
+
+int cx_planset_destroy(cx_planset* S)
+{
+  if (!S) return 0;
+  for (int t = 0; t < 4; t++) { cudaFree(S->d_descs[t]); cudaFree(S->d_blk2desc[t]); }
+  for (size_t i = 0; i < S->ntables; i++) cudaFree(S->d_tables[i]);
+  free(S->d_tables);
+  delete S;
+  return 0;
+}
+
+// nsets dense buffers (one per incoming message part): d_in[i] holds (nvars, ld[i]) values for the n[i]
+// receptor indices d_rcv[i] of the zone whose nvars field pointers are d_fieldR[i]
+int cx_scatterset_create(cx_ctx* ctx, int nsets, int nvars, const int* n, const int* const* d_rcv,
+                         const double* const* d_in, const long long* ld, double* const* const* d_fieldR,
+                         cx_scatterset** out)
+{
+  CX_CUDA(cudaSetDevice(ctx->device));
+  cx_scatterset* S = new cx_scatterset;
+  S->ctx = ctx; S->nvars = nvars; S->d_descs = nullptr; S->d_blk2desc = nullptr;
+  std::vector<ScatDesc> descs; std::vector<int> b2d;
+  int nb = 0;
+  for (int i = 0; i < nsets; i++)
+  {
+    if (n[i] == 0) continue;
+    double** tr = nullptr;
+    CX_CHECK(upload_ptr_table((const double* const*)d_fieldR[i], nvars, &tr));
+    S->owned.push_back(tr);
+    ScatDesc D; D.n = n[i]; D.first_block = nb; D.rcv = d_rcv[i]; D.in = d_in[i]; D.ld = ld[i]; D.rptr = tr;
+    int blocks = cx_grid(n[i], 256);
+    for (int b = 0; b < blocks; b++) b2d.push_back((int)descs.size());
+    descs.push_back(D);
+    nb += blocks;
+  }
+  S->nblocks = nb; S->ndesc = (int)descs.size();
+  if (nb > 0)
+  {
+    CX_CUDA(cudaMalloc(&S->d_descs, sizeof(ScatDesc) * descs.size()));
+    CX_CUDA(cudaMalloc(&S->d_blk2desc, sizeof(int) * b2d.size()));
+    CX_CUDA(cudaMemcpy(S->d_descs, descs.data(), sizeof(ScatDesc) * descs.size(), cudaMemcpyHostToDevice));
+    CX_CUDA(cudaMemcpy(S->d_blk2desc, b2d.data(), sizeof(int) * b2d.size(), cudaMemcpyHostToDevice));
+  }
+  *out = S;
+  return 0;
+}
+
+int cx_scatterset_run(cx_scatterset* S)
+{
+  if (S->nblocks == 0) return 0;
+  k_scatter_set<<<S->nblocks, 256, 0, S->ctx->stream>>>(S->d_descs, S->d_blk2desc, S->nvars);
+  S->ctx->launches++;
+  return 0;
+}
+
+int cx_scatterset_destroy(cx_scatterset* S)
+{
+  if (!S) return 0;
+  cudaFree(S->d_descs); cudaFree(S->d_blk2desc);
+  for (void* p : S->owned) cudaFree(p);
+  delete S;
+  return 0;
+}
+
+}  // extern "C"

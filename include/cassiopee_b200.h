@@ -124,6 +124,28 @@ int cx_scatter_dev(cx_ctx* ctx, int nvars, const double* d_in, long long ld, int
 int cx_plan_info(cx_plan* plan, int* n, int* ngroups, long long* alg_fixed, long long* distinct);
 int cx_plan_destroy(cx_plan* plan);
 
+/* ---- batched transfers: every plan of a rank in one launch ------------------
+ * A solver calls setInterpTransfers every sub-iteration over ALL ID_* subregions
+ * (OversetData.py:2036-2098: Python loop over donor zones x subregions, one C
+ * call each).  A plan set fuses that loop into one kernel launch: modes[p]=0
+ * writes plan p in place into its receptor zone's fields, modes[p]=1 writes its
+ * dense (nvars, ld[p]) block into a send buffer (the _setInterpTransfersD shape
+ * the distributed path of Connector/Mpi.py:396-440 needs).  Field pointer
+ * lists are device pointers (cx_dev_alloc), nvars per plan. */
+typedef struct cx_planset cx_planset;
+typedef struct cx_scatterset cx_scatterset;
+int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars, const int* modes,
+                      const double* const* const* d_fieldD, double* const* const* d_fieldR, double* const* d_dense,
+                      const long long* ld, cx_planset** out);
+int cx_planset_run(cx_planset* set);
+int cx_planset_destroy(cx_planset* set);
+/* receptor-side: scatter nsets received dense blocks into the receptor fields in one launch */
+int cx_scatterset_create(cx_ctx* ctx, int nsets, int nvars, const int* n, const int* const* d_rcv,
+                         const double* const* d_in, const long long* ld, double* const* const* d_fieldR,
+                         cx_scatterset** out);
+int cx_scatterset_run(cx_scatterset* set);
+int cx_scatterset_destroy(cx_scatterset* set);
+
 /* ---- multi-GPU (one process per GPU; NCCL over NVLink) -------------------
  * Replaces the mpi4py pickled isend/recv of Converter/Converter/Mpi4py.py:149-168
  * used by Connector/Mpi.py:396-440: one packed device buffer per peer rank. */
@@ -134,6 +156,9 @@ int cx_comm_barrier(cx_ctx* ctx);
 /* grouped ncclSend/ncclRecv: counts in doubles; device buffers */
 int cx_exchange_dev(cx_ctx* ctx, int npeers, const int* peers, const double* const* d_send,
                     const long long* sendcounts, double* const* d_recv, const long long* recvcounts);
+/* same for raw bytes (one-off shipping of donor coordinates and index lists) */
+int cx_exchange_bytes_dev(cx_ctx* ctx, int npeers, const int* peers, const void* const* d_send,
+                          const long long* sendbytes, void* const* d_recv, const long long* recvbytes);
 
 #ifdef __cplusplus
 }

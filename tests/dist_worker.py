@@ -1,0 +1,159 @@
+"""Worker of the world_size>1 tests (launched by tests/test_distributed.py with
+torch.distributed.run).  mode 'gloo-oracle': CPU, gloo host exchange, compute
+backend = the oracle (tests the distributed HOST logic of
+cassiopee_b200/Connector/Mpi.py: donor graph, zone replication, routing of the
+ID_* subregions to the donor owners, packed value messages).  mode 'nccl':
+the CUDA backend + NCCL device exchange (needs one GPU per rank).
+Every rank builds the same global case, keeps the zones placed on it by
+Distributor2, runs the distributed path, and rank 0 compares everything with a
+single-process run of the same backend."""
+import os
+import sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import cassiopee_b200.Internal as Internal        # noqa: E402
+import cassiopee_b200.Converter as C             # noqa: E402
+import cassiopee_b200.Generator as G             # noqa: E402
+import cassiopee_b200.Distributor2 as D2         # noqa: E402
+import cassiopee_b200.Connector.PyTree as X      # noqa: E402
+import cassiopee_b200.Connector.Mpi as Xmpi      # noqa: E402
+from cassiopee_b200 import Mpi as Cmpi           # noqa: E402
+from cassiopee_b200 import workloads as W        # noqa: E402
+
+VARS = ['Density', 'MomentumX', 'EnergyStagnationDensity']
+
+
+class OraclePlan:
+    def __init__(self, imd, jmd, kmd, nptsR, donor, rcv, typ, coefs):
+        self.a = (imd, jmd, donor, typ, coefs)
+        self.n = len(typ)
+
+    def transferD(self, fields):
+        from oracle import oracle as O
+        imd, jmd, donor, typ, coefs = self.a
+        return O.transferD([np.ascontiguousarray(f.reshape(-1, order='F')) for f in fields], imd, jmd, donor, typ, coefs)
+
+
+class OracleBackend:
+    def make_zone(self, ni, nj, nk, x, y, z, cellN=None):
+        from oracle import oracle as O
+        return O.RefZone(ni, nj, nk, x, y, z, cellN)
+
+    def set_celln(self, hook, cellN):
+        pass
+
+    def set_interp_data(self, xr, yr, zr, hooks, order, nature, penalty, extrap):
+        from oracle import oracle as O
+        return O.set_interp_data(xr, yr, zr, hooks, order, nature, penalty, extrap)
+
+    def make_plan(self, *a):
+        return OraclePlan(*a)
+
+
+def build_case(nb=(2, 2, 1), n=13):
+    blocks = W.c4_layout(nb, n=n, overlap=4, seed=1)
+    zones = []
+    for b in blocks:
+        z = G.cart(b['origin'], (b['h'],) * 3, (n, n, n), name=b['name'])
+        C._initVars(z, 'centers:cellN', W.c4_receptor_mask(b, blocks, depth=2))
+        for i, v in enumerate(VARS):
+            C._initVars(z, 'centers:' + v, lambda x, y, zz, i=i: 1. + i + np.sin(3 * x) + 2. * y * y + 3. * zz)
+        zones.append(z)
+    t = C.newPyTree(['Base'] + zones)
+    D2._distribute(t, int(os.environ.get("WORLD_SIZE", "1")), algorithm='rcb')
+    return t
+
+
+def subtree_of(t, rank):
+    zs = [z for z in Internal.getZones(t) if D2.getProc(z) == rank]
+    return C.newPyTree(['Base'] + zs)
+
+
+def collect(tc, t):
+    out = {}
+    for zd in Internal.getZones(tc):
+        for s in Internal.getNodesFromType1(zd, 'ZoneSubRegion_t'):
+            d = {}
+            for c in s[2]:
+                if isinstance(c[1], np.ndarray) and c[1].dtype.char not in ('S', 'c'):
+                    d[c[0]] = np.array(c[1])
+            out[(zd[0], s[0])] = d
+    fields = {}
+    for z in Internal.getZones(t):
+        for v in VARS:
+            fields[(z[0], v)] = np.array(C.getFieldArray(z, 'centers:' + v))
+    return out, fields
+
+
+def main():
+    mode = sys.argv[1] if len(sys.argv) > 1 else 'gloo-oracle'
+    order = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    rank = int(os.environ.get("RANK", "0"))
+    if mode == 'nccl':
+        from cassiopee_b200 import _lib
+        ctx = _lib.default_context()
+        comm = Cmpi.Comm(ctx)
+        backend = None
+    else:
+        ctx = None
+        comm = Cmpi.Comm(None, device=False)
+        backend = OracleBackend()
+    t = build_case()
+    zoneOrder = [z[0] for z in Internal.getZones(t)]
+    tl = subtree_of(t, rank)
+    tcl = C.node2Center(tl)
+    Xmpi._setInterpData(tl, tcl, order=order, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse',
+                        comm=comm, zoneOrder=zoneOrder, backend=backend, ctx=ctx)
+    if mode == 'nccl':
+        sess = Xmpi.TransferSession(tl, tcl, VARS, comm=comm, ctx=ctx)
+        for _ in range(2):
+            sess.step()
+        sess.download()
+    else:
+        Xmpi._setInterpTransfers(tl, tcl, variables=VARS, comm=comm, backend=backend)
+    mine = collect(tcl, tl)
+    allr = comm.allgather_obj(mine)
+    ok = True
+    if rank == 0:
+        # single-process run of the same backend on the whole tree
+        t1 = build_case()
+        tc1 = C.node2Center(t1)
+        Xmpi._setInterpData(t1, tc1, order=order, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse',
+                            comm=None, zoneOrder=zoneOrder, backend=backend, ctx=ctx)
+        if mode == 'nccl':
+            s1 = Xmpi.TransferSession(t1, tc1, VARS, comm=None, ctx=ctx)
+            for _ in range(2):
+                s1.step()
+            s1.download()
+        else:
+            Xmpi._setInterpTransfers(t1, tc1, variables=VARS, comm=None, backend=backend)
+        ref_sub, ref_fld = collect(tc1, t1)
+        got_sub, got_fld = {}, {}
+        for sub, fld in allr:
+            got_sub.update(sub); got_fld.update(fld)
+        if set(got_sub) != set(ref_sub):
+            ok = False; print("subregion sets differ", sorted(set(got_sub) ^ set(ref_sub))[:5])
+        nsub = 0
+        for k in ref_sub:
+            if k not in got_sub: continue
+            for name, a in ref_sub[k].items():
+                b = got_sub[k].get(name)
+                if b is None or not np.array_equal(a, b):
+                    ok = False; print("MISMATCH", k, name)
+            nsub += 1
+        for k, a in ref_fld.items():
+            if not np.array_equal(a, got_fld[k]):
+                ok = False; print("FIELD MISMATCH", k, np.abs(a - got_fld[k]).max())
+        nrcv = sum(v['PointListDonor'].size for v in ref_sub.values())
+        print("dist_worker %s order=%d world=%d: %d subregions, %d receptors, ok=%s" %
+              (mode, order, comm.size, nsub, nrcv, ok))
+        assert nsub > 0 and nrcv > 0
+    oks = comm.allgather_obj(ok)
+    sys.exit(0 if all(oks) else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,39 @@
+"""world_size-2 tests of the distributed path.  CPU: gloo + oracle backend
+(host logic).  GPU: NCCL + CUDA backend, needs >= 2 devices."""
+import os
+import subprocess
+import sys
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(nproc, mode, order=2, port=29611):
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = "2"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py"),
+           mode, str(order)]
+    r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "ok=True" in r.stdout
+    return r.stdout
+
+
+def test_world2_gloo_oracle_backend():
+    _run(2, "gloo-oracle", 2, 29611)
+
+
+def test_world3_gloo_oracle_backend_order3():
+    _run(3, "gloo-oracle", 3, 29612)
+
+
+@pytest.mark.gpu
+def test_world2_nccl_device_backend():
+    import ctypes
+    from cassiopee_b200 import _lib
+    n = ctypes.c_int(0)
+    _lib.lib().cx_device_count(ctypes.byref(n))
+    if n.value < 2:
+        pytest.skip("needs 2 GPUs")
+    _run(2, "nccl", 2, 29613)
