@@ -1,0 +1,254 @@
+"""bench_c4.py — multi-GPU leg of bench.py: workload C4/C5 of BASELINE.json.
+
+64-zone overset cluster (4x4x4 blocks of 100^3 points, 8-cell overlap, per-block
+sub-cell shifts), receptors = outer 2 cell layers lying inside another block,
+zones placed on the GPUs through `.Solver#Param/proc` (Distributor2), weak
+scaling at 8 zones per GPU (N=1: 2x2x2 ... N=8: 4x4x4).  One process per GPU:
+distributed setInterpData (receptor owner computes, donor zones replicated,
+ID_* subregions routed to the donor owners), then the steady-state
+setInterpTransfers loop of 7 variables with the interpData reused: one fused
+transfer launch + one packed NCCL send/recv per rank pair + one scatter launch
+per step.  Timing: barrier + device sync on both sides, CUDA events per rank,
+max over ranks; value = algorithmic bytes of ALL ranks / that time.
+"""
+import json
+import os
+import time
+
+import numpy as np
+
+NBLOCKS = {1: (2, 2, 2), 2: (4, 2, 2), 4: (4, 4, 2), 8: (4, 4, 4)}
+
+
+def layout_for(ngpus, n=100):
+    from cassiopee_b200 import workloads as W
+    nb = NBLOCKS.get(ngpus)
+    if nb is None:
+        nb = (2 * ngpus, 2, 2)
+    return W.c4_layout(nb, n=n, overlap=8, seed=1), nb
+
+
+def build_local(blocks, owners, rank, nvars):
+    import cassiopee_b200.Generator as G
+    import cassiopee_b200.Converter as C
+    from cassiopee_b200 import workloads as W
+    zones = []
+    for b, p in zip(blocks, owners):
+        if p != rank:
+            continue
+        n = b['n']
+        z = G.cart(b['origin'], (b['h'],) * 3, (n, n, n), name=b['name'])
+        C._initVars(z, 'centers:cellN', W.c4_receptor_mask(b, blocks, depth=2))
+        for i, v in enumerate(W.VARS7[:nvars]):
+            C._initVars(z, 'centers:' + v,
+                        lambda x, y, zz, i=i: 1. + 0.1 * (i + 1) * np.sin(2 * np.pi * x) * np.cos(2 * np.pi * y) + 0.05 * (i + 1) * zz)
+        zones.append(z)
+    return C.newPyTree(['Base'] + zones)
+
+
+def run_c4(args):
+    from bench import METRIC, UNIT, ClockSampler, measured_peaks
+    from cassiopee_b200 import _lib, Mpi as Cmpi, Distributor2 as D2, workloads as W
+    import cassiopee_b200.Internal as Internal
+    import cassiopee_b200.Converter as C
+    import cassiopee_b200.Connector.Mpi as Xmpi
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    ngpus = max(args.gpus, world)
+    ctx = _lib.default_context()
+    comm = Cmpi.Comm(ctx) if world > 1 else None
+    nvars = args.nvars or 7
+    nblk = int(os.environ.get("CX_C4_N", "100"))
+    blocks, nb = layout_for(ngpus, nblk)
+    centres = [np.array(b['origin']) + 0.5 * (b['n'] - 1) * b['h'] for b in blocks]
+    owners = D2.distribute_arrays([b['n'] ** 3 for b in blocks], ngpus, centres, 'rcb')['distrib']
+    if world == 1 and ngpus > 1:
+        owners = [0] * len(blocks)        # --workload c4 on one GPU: all zones local
+    tl = build_local(blocks, owners, rank, nvars)
+    tcl = C.node2Center(tl)
+    zoneOrder = [b['name'] for b in blocks]
+    names = W.VARS7[:nvars]
+
+    def barrier():
+        ctx.sync()
+        if comm is not None:
+            comm.barrier()
+
+    # ---- distributed setInterpData ---------------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    Xmpi._setInterpData(tl, tcl, order=2, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse',
+                        comm=comm, zoneOrder=zoneOrder, ctx=ctx, verbose=0)
+    barrier()
+    sid_s = time.perf_counter() - t0
+    nrcv_local = sum(int((C.getFieldArray(z, 'centers:cellN') == 2.).sum()) for z in Internal.getZones(tl))
+
+    # ---- steady-state transfers --------------------------------------------------
+    sess = Xmpi.TransferSession(tl, tcl, names, comm=comm, ctx=ctx)
+    for _ in range(max(3, args.warmup)):
+        sess.step()
+    barrier()
+    sampler = ClockSampler(ctx.device)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches()
+    barrier()
+    ctx.event_record(0)
+    for _ in range(args.steps):
+        sess.step()
+    ctx.event_record(1)
+    ms = ctx.event_elapsed_ms()
+    barrier()
+    launches = ctx.launches() - l0
+    if rank == 0:
+        t_end = time.perf_counter() + 0.5
+    # keep every rank stepping the same number of times (NCCL pairs must match)
+    for _ in range(200):
+        sess.step()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end: host donor fields -> device, step, receptor fields -> host ----
+    ne2e = max(2, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(ne2e):
+        sess.upload_donor_fields()
+        sess.step()
+        d2h = sess.download()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / ne2e
+
+    def gather(v):
+        return comm.allgather_obj(v) if comm is not None else [v]
+
+    B = sum(gather(sess.alg_bytes()))
+    ms_max = max(gather(ms))
+    e2e_max = max(gather(e2e_s))
+    sid_max = max(gather(sid_s))
+    nrcv = sum(gather(nrcv_local))
+    nccl_b = sum(gather(sess.nccl_bytes()))
+    h2d = sum(gather(sess.h2d_bytes)); d2h = sum(gather(d2h))
+    nplans = sum(gather(len(sess.plans)))
+    launches_all = sum(gather(launches))
+    if rank != 0:
+        return
+    ms_step = ms_max / args.steps
+    value = B / (ms_step * 1e-3) / 1e9
+    peak, how = measured_peaks()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ngpus, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C4/C5: %dx%dx%d blocks of %d^3 pts (8-cell overlap, sub-cell shifts), receptors = outer "
+                               "2 cell layers inside another block, order 2, %d vars, interpData reused" %
+                               (nb[0], nb[1], nb[2], nblk, nvars),
+                   "zones": len(blocks), "zones_per_gpu": len(blocks) // max(1, ngpus), "receptors": int(nrcv),
+                   "plans": int(nplans), "nvars": nvars, "alg_bytes_per_step": int(B),
+                   "nccl_bytes_per_step": int(nccl_b),
+                   "l2": "per-GPU working set %.0f MB; L2 not flushed (steady-state loop of a solver)" %
+                         ((B / max(1, ngpus)) / 1e6),
+                   "parallelism": "zones over %d GPU(s) by .Solver#Param/proc (rcb)" % ngpus},
+        "clocks": clocks,
+        "e2e": {"value": B / e2e_max / 1e9, "unit": UNIT, "ms_per_step": e2e_max * 1e3,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "api": "TransferSession.upload_donor_fields/step/download (host trees in, host trees out)"},
+        "gpu_launches": int(launches_all),
+        "roofline": {"bound": "hbm", "achieved": value / ngpus, "peak": peak, "unit": "GB/s per GPU",
+                     "frac": value / ngpus / peak, "traffic": None, "peak_source": how,
+                     "kernel": "k_transfer_set<2> (+ NCCL send/recv + k_scatter_set inside the step)"},
+        "cpu_baseline": None,
+        "set_interp_data": {"value": nrcv / sid_max, "unit": "receptor pts/s", "receptors": int(nrcv),
+                            "s": sid_max, "includes": "donor-zone replication, device ADT builds, search, "
+                            "routing of ID_* subregions to donor owners (host trees in/out)"},
+    }
+    if ngpus == 1 and not args.quick:
+        line["cpu_baseline"] = cpu_baseline_c4(args, blocks, nvars)
+    print(json.dumps(line))
+
+
+def _sample_case(blocks, nvars, nrz=2):
+    """Bounded sample for the CPU arm: the first nrz receptor zones with their
+    bbox-intersecting donor zones."""
+    from cassiopee_b200 import workloads as W
+    grids = {}
+    def grid(b):
+        if b['name'] not in grids:
+            grids[b['name']] = W.c4_block_grid(b).centers()
+        return grids[b['name']]
+    out = []
+    for rb in blocks[:nrz]:
+        g = grid(rb)
+        cellN = W.c4_receptor_mask(rb, blocks, depth=2)
+        sel = np.nonzero(cellN == 2.)[0]
+        bb = g.bbox()
+        donors = [b for b in blocks if b is not rb and W.bbox_intersect(bb, grid(b).bbox())]
+        out.append((rb, g, sel, donors))
+    return out, grid
+
+
+def cpu_baseline_c4(args, blocks, nvars, nrz=2):
+    try:
+        return reference_c4_impl(args, blocks, nvars, nrz)[0]
+    except Exception as e:
+        return {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+
+
+def reference_c4_impl(args, blocks, nvars, nrz=2):
+    from oracle import oracle as O
+    from cassiopee_b200 import workloads as W
+    from bench import alg_bytes, distinct_nodes
+    sample, grid = _sample_case(blocks, nvars, nrz)
+    zones = {}
+    t0 = time.perf_counter()
+    for rb, g, sel, donors in sample:
+        for b in donors:
+            if b['name'] not in zones:
+                d = grid(b)
+                zones[b['name']] = O.RefZone(d.ni, d.nj, d.nk, d.x, d.y, d.z)
+    t_adt = time.perf_counter() - t0
+    plans = []
+    t0 = time.perf_counter()
+    nrcv = 0
+    for rb, g, sel, donors in sample:
+        out = O.set_interp_data(g.x[sel], g.y[sel], g.z[sel], [zones[b['name']] for b in donors], 2, 1, 1, 1)
+        nrcv += sel.size
+        for k, b in enumerate(donors):
+            if out[0][k].size:
+                plans.append((grid(b), sel[out[0][k]].astype(np.int32), out[1][k], out[2][k], out[3][k], g.npts))
+    t_search = time.perf_counter() - t0
+    B = 0
+    fields = {}
+    for d, rcv, dnr, typ, cf, nR in plans:
+        B += alg_bytes(rcv.size, cf.size, nvars, distinct_nodes(dnr, typ, d.ni, d.nj))
+        if d.name not in fields:
+            fields[d.name] = W.conservative_fields(d.x, d.y, d.z, nvars)
+    fR = [np.zeros(plans[0][5]) for _ in range(nvars)] if plans else []
+    steps = max(1, min(args.steps, 20))
+    def one_pass():
+        for d, rcv, dnr, typ, cf, nR in plans:
+            O.transfer(fields[d.name], fR, d.ni, d.nj, rcv, dnr, typ, cf)
+    one_pass()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_pass()
+    dt = (time.perf_counter() - t0) / steps
+    value = B / dt / 1e9
+    nth = os.cpu_count() or 1
+    desc = ("C4 bounded sample: %d receptor zones (%d receptors) with their %d bbox-intersecting donor zones, one ADT "
+            "per donor zone built once (hooks, as Connector/Mpi.py:950-983), %d plans, %d vars" %
+            (nrz, nrcv, len(zones), len(plans), nvars))
+    cpu = {"value": value, "unit": "GB/s", "cores": int(min(nvars, nth)), "kind": "reference", "host_cores": nth,
+           "ms_per_step": dt * 1e3, "sample": desc}
+    sid = {"value": nrcv / (t_adt + t_search), "unit": "receptor pts/s", "receptors": int(nrcv), "adt_build_s": t_adt,
+           "search_s": t_search, "cores": nth}
+    return cpu, sid, dt, steps, desc, B
+
+
+def reference_c4(args, O, W, nthreads):
+    nvars = args.nvars or 7
+    blocks, nb = layout_for(args.gpus, int(os.environ.get("CX_C4_N", "100")))
+    cpu, sid, dt, steps, desc, B = reference_c4_impl(args, blocks, nvars)
+    cfg = {"workload": desc, "nvars": nvars, "alg_bytes_per_step": int(B)}
+    return cpu["value"], dt, steps, cfg, sid, nvars
