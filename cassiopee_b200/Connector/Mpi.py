@@ -281,6 +281,7 @@ class TransferSession:
         self._aD = aD
         self.plans = []
         items = []
+        ritems = []
         remote = {}       # peer -> list of (donorName, rcvName, plan)
         self.alg_fixed = 0; self.n_entries = 0; self.distinct = 0
         for zd in Internal.getZones(aD):
@@ -321,11 +322,12 @@ class TransferSession:
             self.sendcnt[p] = tot
             o = 0
             for dn, rn, plan, ListRcv, loc in lst:
-                items.append((plan, 1, [d.ptr for d in self.dD[dn]], None, self.sendbuf[p].ptr + 8 * o, plan.n))
+                ritems.append((plan, 1, [d.ptr for d in self.dD[dn]], None, self.sendbuf[p].ptr + 8 * o, plan.n))
                 outMeta.setdefault(p, []).append(dict(donor=dn, rcv=rn, n=int(plan.n), loc=loc))
                 outIdx.setdefault(p, []).append(numpy.ascontiguousarray(ListRcv, dtype=numpy.int32).view(numpy.uint8))
                 o += plan.n * nv
-        self.planset = _lib.PlanSet(ctx, nv, items)
+        self.planset = _lib.PlanSet(ctx, nv, items)          # local pairs, in place
+        self.planset_remote = _lib.PlanSet(ctx, nv, ritems) if ritems else None
         # receive side: index lists are exchanged once
         self.recvbuf, self.recvcnt = {}, {}
         sitems = []
@@ -352,6 +354,11 @@ class TransferSession:
                     o += n * nv
         self.scatterset = _lib.ScatterSet(ctx, nv, sitems)
         self.peers = sorted(set(self.sendbuf) | set(self.recvbuf))
+        sp = [self.sendbuf[p].ptr if p in self.sendbuf else 0 for p in self.peers]
+        sc = [self.sendcnt.get(p, 0) for p in self.peers]
+        rp = [self.recvbuf[p].ptr if p in self.recvbuf else 0 for p in self.peers]
+        rc = [self.recvcnt.get(p, 0) for p in self.peers]
+        self._step = _lib.Step(ctx, self.planset_remote, self.planset, self.scatterset, self.peers, sp, sc, rp, rc)
         ctx.sync()
 
     def _residentR(self, zr, loc):
@@ -375,15 +382,10 @@ class TransferSession:
                 for d, v in zip(self.dD[zd[0]], self.variables):
                     d.upload(C.getFieldArray(zd, v).reshape(-1, order='F'))
 
-    def step(self):
-        self.planset.run()
-        if self.peers:
-            sp = [self.sendbuf[p].ptr if p in self.sendbuf else 0 for p in self.peers]
-            sc = [self.sendcnt.get(p, 0) for p in self.peers]
-            rp = [self.recvbuf[p].ptr if p in self.recvbuf else 0 for p in self.peers]
-            rc = [self.recvcnt.get(p, 0) for p in self.peers]
-            self.comm.exchange_dev(self.peers, sp, sc, rp, rc)
-            self.scatterset.run()
+    def step(self, niter=1, overlap=True):
+        """niter iterations (asynchronous): remote plans -> NCCL exchange + scatter on the
+        communication stream, overlapped with the local in-place plans."""
+        self._step.run(niter, overlap)
 
     def download(self):
         """Copy the receptor fields back into the host tree (in place)."""

@@ -36,6 +36,10 @@ class Comm:
                 _lib.check(_lib.lib().cx_comm_unique_id(idbuf))
             ids = self.allgather_obj(bytes(idbuf.raw) if self.rank == 0 else None)
             _lib.check(_lib.lib().cx_comm_init(ctx.h, self.rank, self.size, ids[0]))
+            # establish the NVLink peer connections now (NCCL connects lazily on first use)
+            w = np.zeros(8, np.uint8)
+            self.exchange_host({p: w for p in range(self.size) if p != self.rank},
+                               {p: 8 for p in range(self.size) if p != self.rank})
 
     # -- small objects ------------------------------------------------------
     def allgather_obj(self, obj):

@@ -67,6 +67,9 @@ _SIGS = {
     "cx_scatterset_create": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cx_scatterset_run": (_i, [_vp]),
     "cx_scatterset_destroy": (_i, [_vp]),
+    "cx_step_create": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cx_step_run": (_i, [_vp, _i, _i]),
+    "cx_step_destroy": (_i, [_vp]),
     "cx_comm_unique_id": (_i, [_vp]),
     "cx_comm_init": (_i, [_vp, _i, _i, _vp]),
     "cx_comm_destroy": (_i, [_vp]),
@@ -510,3 +513,24 @@ class DeviceBackend:
 
     def make_plan(self, imd, jmd, kmd, nptsR, donor, rcv, typ, coefs):
         return Plan(self.ctx, imd, jmd, kmd, nptsR, donor, rcv, typ, coefs)
+
+
+class Step:
+    """One iteration of a rank (cx_step): remote plans -> NCCL exchange + scatter (second
+    stream) overlapped with the local plans."""
+
+    def __init__(self, ctx, ps_remote, ps_local, scatterset, peers, send_ptrs, send_counts, recv_ptrs, recv_counts):
+        self.keep = (ps_remote, ps_local, scatterset)
+        n = len(peers)
+        h = _vp()
+        check(lib().cx_step_create(ctx.h, ps_remote.h if ps_remote is not None else None,
+                                   ps_local.h if ps_local is not None else None,
+                                   scatterset.h if scatterset is not None else None, n,
+                                   (ctypes.c_int * max(n, 1))(*peers), ptr_array(send_ptrs or [0]),
+                                   (ctypes.c_longlong * max(n, 1))(*send_counts), ptr_array(recv_ptrs or [0]),
+                                   (ctypes.c_longlong * max(n, 1))(*recv_counts), ctypes.byref(h)))
+        self.h = h
+        self._fin = weakref.finalize(self, lib().cx_step_destroy, h)
+
+    def run(self, niter=1, overlap=True):
+        check(lib().cx_step_run(self.h, int(niter), 1 if overlap else 0))

@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <algorithm>
+#include <thread>
 
 using namespace cx;
 
@@ -64,6 +65,9 @@ int cx_ctx_create(int device, cx_ctx** out)
   CX_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   CX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CX_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  CX_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CX_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   CX_CUDA(cudaEventCreate(&c->ev0));
   CX_CUDA(cudaEventCreate(&c->ev1));
   c->pinned = nullptr; c->pinned_bytes = 0; c->launches = 0; c->nccl = nullptr;
@@ -79,6 +83,8 @@ int cx_ctx_destroy(cx_ctx* c)
   if (c->nccl) cx_comm_destroy(c);
   if (c->pinned) cudaFreeHost(c->pinned);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
+  cudaStreamDestroy(c->comm_stream);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -442,14 +448,27 @@ int cx_transfer(cx_plan* P, int nvars, const double* const* fieldD, double* cons
   size_t nd = (size_t)P->n * nvars;
   CX_CHECK(ensure(&F->h_dense, &F->hdense_cap, sizeof(double) * nd, true));
   CX_CHECK(cx_transferD(P, nvars, fieldD, F->h_dense));
-  // host scatter in entry order (duplicates: last wins, like the reference's serial walk)
+  // host scatter; receptors of one plan are distinct, so entry ranges can go to different threads
   const int n = P->n;
   const int* rcv = F->h_rcv.data();
-  for (int v = 0; v < nvars; v++)
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = (int)std::min<unsigned>(hw ? hw : 1, 16);
+  if ((long long)n * nvars < (1 << 20)) nt = 1;
+  auto work = [&](int t) {
+    int e0 = (int)((long long)n * t / nt), e1 = (int)((long long)n * (t + 1) / nt);
+    for (int v = 0; v < nvars; v++)
+    {
+      double* fr = fieldR[v];
+      const double* src = F->h_dense + (size_t)v * n;
+      for (int e = e0; e < e1; e++) fr[rcv[e]] = src[e];
+    }
+  };
+  if (nt == 1) work(0);
+  else
   {
-    double* fr = fieldR[v];
-    const double* src = F->h_dense + (size_t)v * n;
-    for (int e = 0; e < n; e++) fr[rcv[e]] = src[e];
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
   }
   return 0;
 }

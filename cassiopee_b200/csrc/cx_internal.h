@@ -29,6 +29,8 @@ struct cx_ctx {
   int device;
   int sm_count;
   cudaStream_t stream;
+  cudaStream_t comm_stream;     // NCCL exchange + scatter overlap the local transfers
+  cudaEvent_t ev_fork, ev_join;
   cudaEvent_t ev0, ev1;
   // pinned staging buffer for host<->device copies
   void* pinned; size_t pinned_bytes;

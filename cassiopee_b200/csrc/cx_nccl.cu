@@ -102,19 +102,25 @@ int cx_comm_barrier(cx_ctx* ctx)
   return 0;
 }
 
-int cx_exchange_dev(cx_ctx* ctx, int npeers, const int* peers, const double* const* d_send,
-                    const long long* sendcounts, double* const* d_recv, const long long* recvcounts)
+int cx_exchange_on_stream(cx_ctx* ctx, cudaStream_t st, int npeers, const int* peers, const double* const* d_send,
+                          const long long* sendcounts, double* const* d_recv, const long long* recvcounts)
 {
   cx_comm* c = (cx_comm*)ctx->nccl;
   if (!c) { cx_set_error("communicator not initialised"); return -5; }
   CX_NCCL(g_nccl.GroupStart());
   for (int p = 0; p < npeers; p++)
   {
-    if (sendcounts[p] > 0) CX_NCCL(g_nccl.Send(d_send[p], (size_t)sendcounts[p], ncclFloat64, peers[p], c->comm, ctx->stream));
-    if (recvcounts[p] > 0) CX_NCCL(g_nccl.Recv(d_recv[p], (size_t)recvcounts[p], ncclFloat64, peers[p], c->comm, ctx->stream));
+    if (sendcounts[p] > 0) CX_NCCL(g_nccl.Send(d_send[p], (size_t)sendcounts[p], ncclFloat64, peers[p], c->comm, st));
+    if (recvcounts[p] > 0) CX_NCCL(g_nccl.Recv(d_recv[p], (size_t)recvcounts[p], ncclFloat64, peers[p], c->comm, st));
   }
   CX_NCCL(g_nccl.GroupEnd());
   return 0;
+}
+
+int cx_exchange_dev(cx_ctx* ctx, int npeers, const int* peers, const double* const* d_send,
+                    const long long* sendcounts, double* const* d_recv, const long long* recvcounts)
+{
+  return cx_exchange_on_stream(ctx, ctx->stream, npeers, peers, d_send, sendcounts, d_recv, recvcounts);
 }
 
 int cx_exchange_bytes_dev(cx_ctx* ctx, int npeers, const int* peers, const void* const* d_send,

@@ -17,6 +17,7 @@
 // Roofline: HBM.  Algorithmic bytes per entry: 8*ncf + 4 (donor) + 4 (rcv) + 4 (type)
 // + 8*nvars (receptor write) + 8*nvars*U/n (each distinct donor node read once).
 #include "cx_internal.h"
+#include "../../include/cassiopee_b200.h"
 #include <algorithm>
 #include <string.h>
 #include <stdlib.h>
@@ -423,15 +424,16 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
   return 0;
 }
 
-int cx_planset_run(cx_planset* S)
+static int planset_run_on(cx_planset* S, cudaStream_t s)
 {
-  cudaStream_t s = S->ctx->stream;
   if (S->nblocks[0]) { k_transfer_set<1><<<S->nblocks[0], 256, 0, s>>>(S->d_descs[0], S->d_blk2desc[0], S->nvars); S->ctx->launches++; }
   if (S->nblocks[1]) { k_transfer_set<2><<<S->nblocks[1], 256, 0, s>>>(S->d_descs[1], S->d_blk2desc[1], S->nvars); S->ctx->launches++; }
   if (S->nblocks[2]) { k_transfer_set<3><<<S->nblocks[2], 256, 0, s>>>(S->d_descs[2], S->d_blk2desc[2], S->nvars); S->ctx->launches++; }
   if (S->nblocks[3]) { k_transfer_set<5><<<S->nblocks[3], 256, 0, s>>>(S->d_descs[3], S->d_blk2desc[3], S->nvars); S->ctx->launches++; }
   return 0;
 }
+
+int cx_planset_run(cx_planset* S) { return planset_run_on(S, S->ctx->stream); }
 
 int cx_planset_destroy(cx_planset* S)
 {
@@ -478,11 +480,72 @@ int cx_scatterset_create(cx_ctx* ctx, int nsets, int nvars, const int* n, const 
   return 0;
 }
 
-int cx_scatterset_run(cx_scatterset* S)
+static int scatterset_run_on(cx_scatterset* S, cudaStream_t s)
 {
   if (S->nblocks == 0) return 0;
-  k_scatter_set<<<S->nblocks, 256, 0, S->ctx->stream>>>(S->d_descs, S->d_blk2desc, S->nvars);
+  k_scatter_set<<<S->nblocks, 256, 0, s>>>(S->d_descs, S->d_blk2desc, S->nvars);
   S->ctx->launches++;
+  return 0;
+}
+
+int cx_scatterset_run(cx_scatterset* S) { return scatterset_run_on(S, S->ctx->stream); }
+
+// ---- one solver iteration of a rank -------------------------------------------------
+//   main stream : [wait previous exchange] remote plans (dense blocks -> send buffers) | fork | local plans (in place)
+//   comm stream :                                                       wait fork -> NCCL send/recv -> scatter | join
+// so the NVLink exchange and the scatter of iteration i overlap the local transfers of iteration i.
+extern int cx_exchange_on_stream(cx_ctx* ctx, cudaStream_t st, int npeers, const int* peers, const double* const* d_send,
+                                 const long long* sendcounts, double* const* d_recv, const long long* recvcounts);
+
+struct cx_step {
+  cx_ctx* ctx; cx_planset* ps_remote; cx_planset* ps_local; cx_scatterset* ss;
+  std::vector<int> peers; std::vector<const double*> sp; std::vector<double*> rp;
+  std::vector<long long> sc, rc;
+  int overlap;
+};
+
+int cx_step_create(cx_ctx* ctx, cx_planset* ps_remote, cx_planset* ps_local, cx_scatterset* ss, int npeers,
+                   const int* peers, const double* const* d_send, const long long* sendcounts, double* const* d_recv,
+                   const long long* recvcounts, cx_step** out)
+{
+  cx_step* S = new cx_step;
+  S->ctx = ctx; S->ps_remote = ps_remote; S->ps_local = ps_local; S->ss = ss; S->overlap = 1;
+  for (int p = 0; p < npeers; p++)
+  {
+    S->peers.push_back(peers[p]); S->sp.push_back(d_send[p]); S->rp.push_back(d_recv[p]);
+    S->sc.push_back(sendcounts[p]); S->rc.push_back(recvcounts[p]);
+  }
+  *out = S;
+  return 0;
+}
+
+int cx_step_run(cx_step* S, int niter, int overlap)
+{
+  cx_ctx* c = S->ctx;
+  cudaStream_t s = c->stream, cs = overlap ? c->comm_stream : c->stream;
+  const bool comm = !S->peers.empty();
+  for (int it = 0; it < niter; it++)
+  {
+    if (comm && overlap) CX_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));   // send buffers free again
+    if (S->ps_remote) CX_CHECK(planset_run_on(S->ps_remote, s));
+    if (comm)
+    {
+      if (overlap) { CX_CUDA(cudaEventRecord(c->ev_fork, s)); CX_CUDA(cudaStreamWaitEvent(cs, c->ev_fork, 0)); }
+      CX_CHECK(cx_exchange_on_stream(c, cs, (int)S->peers.size(), S->peers.data(), S->sp.data(), S->sc.data(),
+                                     S->rp.data(), S->rc.data()));
+      if (S->ss) CX_CHECK(scatterset_run_on(S->ss, cs));
+      if (overlap) CX_CUDA(cudaEventRecord(c->ev_join, cs));
+    }
+    if (S->ps_local) CX_CHECK(planset_run_on(S->ps_local, s));
+  }
+  if (comm && overlap) CX_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));     // join: later work on the main stream sees the scatter
+  return 0;
+}
+
+int cx_step_destroy(cx_step* S)
+{
+  if (!S) return 0;
+  delete S;
   return 0;
 }
 

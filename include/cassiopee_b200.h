@@ -146,6 +146,16 @@ int cx_scatterset_create(cx_ctx* ctx, int nsets, int nvars, const int* n, const 
 int cx_scatterset_run(cx_scatterset* set);
 int cx_scatterset_destroy(cx_scatterset* set);
 
+/* one solver iteration of a rank: remote plans (dense blocks into the per-peer send
+ * buffers) -> grouped NCCL send/recv + scatter on a second stream, overlapped with the
+ * local in-place plans; niter iterations are enqueued per call (asynchronous). */
+typedef struct cx_step cx_step;
+int cx_step_create(cx_ctx* ctx, cx_planset* ps_remote, cx_planset* ps_local, cx_scatterset* ss, int npeers,
+                   const int* peers, const double* const* d_send, const long long* sendcounts,
+                   double* const* d_recv, const long long* recvcounts, cx_step** out);
+int cx_step_run(cx_step* step, int niter, int overlap);
+int cx_step_destroy(cx_step* step);
+
 /* ---- multi-GPU (one process per GPU; NCCL over NVLink) -------------------
  * Replaces the mpi4py pickled isend/recv of Converter/Converter/Mpi4py.py:149-168
  * used by Connector/Mpi.py:396-440: one packed device buffer per peer rank. */
