@@ -14,6 +14,8 @@ see cassiopee_b200/Mpi.py.  TransferSession is the device-resident steady
 state: all plans of a rank fused in one launch, one packed NCCL message per
 rank pair and iteration, one scatter launch.
 """
+import os
+import time
 import numpy
 from .. import Internal
 from .. import Converter as C
@@ -122,11 +124,15 @@ def _setInterpData(aR, aD, order=2, penalty=1, nature=0, extrap=1, method='lagra
                                        hook=hook, verbose=verbose, sameName=sameName, dim=dim, itype=itype,
                                        ctx=ctx, backend=backend,
                                        donorLists=computeDonorGraph(aR, aD, _Single(), loc, sameName, zoneOrder)[1])
+    prof = os.environ.get("CX_PROFILE") and comm.rank == 0
+    t0 = time.perf_counter()
     hadCellN = {z[0]: C.isNamePresent(z, 'cellN') for z in Internal.getZones(aD)}
     X._addCellN__(aD, loc='nodes')
     meta, donorLists = computeDonorGraph(aR, aD, comm, loc, sameName, zoneOrder)
     byname = {m['name']: m for m in meta}
+    t1 = time.perf_counter()
     added = _addXZones(aD, meta, donorLists, comm)
+    t2 = time.perf_counter()
     # working donor list: local zones + replicated ones, in the global order
     zonesL = {z[0]: z for z in Internal.getZones(aD)}
     work = []
@@ -141,6 +147,7 @@ def _setInterpData(aR, aD, order=2, penalty=1, nature=0, extrap=1, method='lagra
                             loc=loc, storage='inverse', interpDataType=interpDataType, hook=None, verbose=verbose,
                             sameName=sameName, dim=dim, itype='chimera', donorLists=donorLists, ctx=ctx,
                             backend=backend)
+    t3 = time.perf_counter()
     # route the subregions created under replicated zones to their owners
     outMeta = {}
     outData = {}
@@ -181,6 +188,9 @@ def _setInterpData(aR, aD, order=2, penalty=1, nature=0, extrap=1, method='lagra
                                     arrs[4], arrs[5], tag='Donor', loc='centers' if rec['centers'] else 'nodes')
     for z in Internal.getZones(aD):
         if hadCellN.get(z[0], 1) == -1: C._rmVars(z, ['cellN'])
+    if prof:
+        print("[Mpi._setInterpData rank0] graph %.3fs addXZones %.3fs (%d zones) chimera %.3fs routing %.3fs" %
+              (t1 - t0, t2 - t1, len(added), t3 - t2, time.perf_counter() - t3), flush=True)
     return None
 
 

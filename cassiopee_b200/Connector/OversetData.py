@@ -237,15 +237,20 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
 
     def hookOf(i):
         if allHooksL[i] is None:
-            a = _zoneArray(zonesDnrL[i])
-            f = a[1]
-            allHooksL[i] = backend.make_zone(a[2], a[3], a[4], numpy.ascontiguousarray(f[0]),
-                                             numpy.ascontiguousarray(f[1]), numpy.ascontiguousarray(f[2]),
-                                             numpy.ascontiguousarray(f[3]) if f.shape[0] > 3 else None)
+            zd = zonesDnrL[i]
+            _, ni_, nj_, nk_, _ = Internal.getZoneDim(zd)
+            xd, yd, zzd = [a.reshape(-1, order='F') for a in C.getCoords(zd)]
+            cd = C.getFieldArray(zd, 'cellN')
+            allHooksL[i] = backend.make_zone(ni_, nj_, nk_, xd, yd, zzd,
+                                             cd.reshape(-1, order='F') if cd is not None else None)
         return allHooksL[i]
 
+    import os as _os, time as _time
+    _prof = _os.environ.get("CX_PROFILE")
+    _tt = dict(hooks=0., pts=0., search=0., store=0.)
     try:
         for z in zonesRcv:
+            _t0 = _time.perf_counter()
             cellNPresent = C.isNamePresent(z, 'cellN' if loc == 'nodes' else 'centers:cellN')
             if cellNPresent == -1:
                 continue
@@ -262,25 +267,25 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
             zonesDnr = [zonesDnrL[i] for i in idx]
             nzonesDnr = len(zonesDnr)
 
-            # Etape 1: points to interpolate (cellN == 2)
-            _, ni, nj, nk, _ = Internal.getZoneDim(z)
+            # Etape 1: points to interpolate (cellN == 2): getInterpolatedPoints keeps the points with
+            # |cellN-2| <= 1e-15 in source order and records their index ('indcell'); for loc='centers' the
+            # centre coordinates (node2Center formula) are only evaluated for those cells
             x, y, zc = C.getCoords(z)
+            cellN = C.getFieldArray(z, 'cellN' if locR == 'nodes' else 'centers:cellN')
+            tcn = cellN.reshape(-1, order='F') - 2.
+            sel = numpy.nonzero((tcn >= -1.e-15) & (tcn <= 1.e-15))[0]
             if locR == 'nodes':
-                cellN = C.getFieldArray(z, 'cellN')
+                pts = [numpy.ascontiguousarray(a.reshape(-1, order='F')[sel]) for a in (x, y, zc)]
             else:
-                x, y, zc = [C.node2CenterArray(a) for a in (x, y, zc)]
-                cellN = C.getFieldArray(z, 'centers:cellN')
-            npts = cellN.size
-            an = ['x,y,z,cellN', numpy.stack([x.reshape(npts, order='F'), y.reshape(npts, order='F'),
-                                                 zc.reshape(npts, order='F'), cellN.reshape(npts, order='F')]), npts, 1, 1]
-            interpPts = Connector.getInterpolatedPoints__(an)
+                pts = [C.node2CenterSelected(a, sel) for a in (x, y, zc)]
+            interpPts = ['x,y,z,indcell', pts + [sel], sel.size, 1, 1]
             if nzonesDnr == 0:
-                if interpPts[1].shape[1] > 0:
+                if sel.size > 0:
                     raise TypeError("setInterpData: no valid donor zone found.")
                 continue
 
             # Etape 2: interpolation data on the device
-            if interpPts[1].shape[1] == 0:
+            if sel.size == 0:
                 continue
             types = interpDataType if isinstance(interpDataType, list) else [interpDataType] * nzonesDnr
             for ty in types:
@@ -289,10 +294,15 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
                 if ty == 0:
                     raise NotImplementedError("setInterpData: interpDataType=0 (InterpCart) has no device path.")
             f = interpPts[1]
+            _t1 = _time.perf_counter()
+            hooks_ = [hookOf(i) for i in idx]
+            _t2 = _time.perf_counter()
             resInterp = backend.set_interp_data(numpy.ascontiguousarray(f[0]), numpy.ascontiguousarray(f[1]),
-                                                numpy.ascontiguousarray(f[2]), [hookOf(i) for i in idx],
+                                                numpy.ascontiguousarray(f[2]), hooks_,
                                                 order, nature, penalty, extrap)
-            nbinterpolated = interpPts[1].shape[1]
+            _t3 = _time.perf_counter()
+            _tt['pts'] += _t1 - _t0; _tt['hooks'] += _t2 - _t1; _tt['search'] += _t3 - _t2
+            nbinterpolated = sel.size
             nbextrapolated = sum(r.shape[0] for r in resInterp[4])
             nborphan = resInterp[5].size
             nbinterpolated = nbinterpolated - nbextrapolated - nborphan
@@ -300,7 +310,7 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
                 print('Zone %s: interpolated=%d ; extrapolated=%d ; orphan=%d' % (z[0], nbinterpolated, nbextrapolated, nborphan))
                 if nborphan > 0: print('Warning: zone %s has %d orphan points !' % (z[0], nborphan))
             # local position -> index in the receptor zone (indcell), vectorised
-            indcells = interpPts[1][-1, :].astype(Internal.E_NpyInt)
+            indcells = sel.astype(Internal.E_NpyInt)
             if nborphan > 0:
                 resInterp[5] = indcells[resInterp[5]]
             for noz in range(nzonesDnr):
@@ -321,7 +331,11 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
                         _createInterpRegion__(zonesDnr[noz], z[0], resInterp[1][noz], resInterp[0][noz],
                                               resInterp[3][noz], resInterp[2][noz], numpy.array([], numpy.float64),
                                               extrapPts, resInterp[5], tag='Donor', loc=locR)
+            _tt['store'] += _time.perf_counter() - _t3
     finally:
+        if _prof:
+            print("[_setInterpDataChimera] receptor extraction %.3fs, donor hooks (upload+ADT) %.3fs, search+fetch %.3fs, "
+                  "remap+store %.3fs" % (_tt['pts'], _tt['hooks'], _tt['search'], _tt['store']), flush=True)
         if storage != 'direct':
             _adaptForRANSLES__(aR, aD, dictOfModels=dictOfModels)
         for zd in Internal.getZones(aD):

@@ -132,18 +132,18 @@ int cx_build_adt(cx_zone* z)
   const int ncells = z->ncells;
   const size_t n = ncells;
   BuildView B; BuildScratch S;
-  CX_CUDA(cudaMalloc(&z->d_nodes, sizeof(AdtNode) * n));
+  CX_MALLOC(z->d_nodes, sizeof(AdtNode) * n, s);
   B.nodes = z->d_nodes; B.ncells = ncells;
-  CX_CUDA(cudaMalloc(&B.keys, sizeof(double) * 6 * n));
-  CX_CUDA(cudaMalloc(&B.lo, sizeof(double) * 6 * n));
-  CX_CUDA(cudaMalloc(&B.hi, sizeof(double) * 6 * n));
-  CX_CUDA(cudaMalloc(&B.cur, sizeof(int) * n));
-  CX_CUDA(cudaMalloc(&B.br, n));
-  CX_CUDA(cudaMalloc(&B.depth, sizeof(int) * n));
+  CX_MALLOC(B.keys, sizeof(double) * 6 * n, s);
+  CX_MALLOC(B.lo, sizeof(double) * 6 * n, s);
+  CX_MALLOC(B.hi, sizeof(double) * 6 * n, s);
+  CX_MALLOC(B.cur, sizeof(int) * n, s);
+  CX_MALLOC(B.br, n, s);
+  CX_MALLOC(B.depth, sizeof(int) * n, s);
   CX_CUDA(cudaMemsetAsync(B.depth, 0, sizeof(int) * n, s));
-  CX_CUDA(cudaMalloc(&S.actA, sizeof(int) * n));
-  CX_CUDA(cudaMalloc(&S.actB, sizeof(int) * n));
-  CX_CUDA(cudaMalloc(&S.counter, sizeof(int) * 2));
+  CX_MALLOC(S.actA, sizeof(int) * n, s);
+  CX_MALLOC(S.actB, sizeof(int) * n, s);
+  CX_MALLOC(S.counter, sizeof(int) * 2, s);
   ZoneBox zb;
   for (int d = 0; d < 6; d++) { zb.lo[d] = z->bbox[d % 3]; zb.hi[d] = z->bbox[3 + d % 3]; }
   B.zb = zb;
@@ -186,8 +186,8 @@ int cx_build_adt(cx_zone* z)
   cudaEventElapsedTime(&z->build_ms, ctx->ev0, ctx->ev1);
   z->depth = depth;
   z->levels = L;
-  cudaFree(B.keys); cudaFree(B.lo); cudaFree(B.hi); cudaFree(B.cur); cudaFree(B.br); cudaFree(B.depth);
-  cudaFree(S.actA); cudaFree(S.actB); cudaFree(S.counter);
+  cudaFreeAsync(B.keys, s); cudaFreeAsync(B.lo, s); cudaFreeAsync(B.hi, s); cudaFreeAsync(B.cur, s); cudaFreeAsync(B.br, s); cudaFreeAsync(B.depth, s);
+  cudaFreeAsync(S.actA, s); cudaFreeAsync(S.actB, s); cudaFreeAsync(S.counter, s);
   if (depth + 2 > CX_STACK)
   {
     cx_set_error("ADT depth %d exceeds the traversal stack (%d)", depth, CX_STACK);

@@ -64,6 +64,14 @@ int cx_ctx_create(int device, cx_ctx** out)
   cudaDeviceProp prop;
   CX_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+    {
+      unsigned long long thr = ~0ull;   // keep freed blocks cached in the pool
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
   CX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CX_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
   CX_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -371,9 +379,10 @@ int cx_result_destroy(cx_result* R)
 {
   if (!R) return 0;
   cx_result_full* F = (cx_result_full*)R;
-  cudaFree(R->d_noblk); cudaFree(R->d_type); cudaFree(R->d_dind); cudaFree(R->d_isext); cudaFree(R->d_cf);
-  cudaFree(F->D.rcv); cudaFree(F->D.dnr); cudaFree(F->D.typ); cudaFree(F->D.coefs); cudaFree(F->D.ext);
-  cudaFree(F->D.orphan);
+  cudaStream_t s = R->ctx->stream;
+  void* ptrs[] = {R->d_noblk, R->d_type, R->d_dind, R->d_isext, R->d_cf, F->D.rcv, F->D.dnr, F->D.typ, F->D.coefs,
+                  F->D.ext, F->D.orphan};
+  for (void* p : ptrs) if (p) cudaFreeAsync(p, s);
   delete F;
   return 0;
 }

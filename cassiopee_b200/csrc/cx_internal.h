@@ -87,4 +87,10 @@ int cx_exclusive_scan_u64(cx_ctx* ctx, const unsigned long long* d_in, unsigned 
 // ADT build (cx_adt.cu)
 int cx_build_adt(cx_zone* z);
 
+// stream-ordered allocation (pool keeps freed blocks: release threshold = max, set at ctx creation);
+// pointers obtained here may also be released with plain cudaFree
+static inline cudaError_t cx_malloc_async(void** p, size_t bytes, cudaStream_t s)
+{ return cudaMallocAsync(p, bytes ? bytes : 8, s); }
+#define CX_MALLOC(ptr, bytes, stream) CX_CUDA(cx_malloc_async((void**)&(ptr), (bytes), (stream)))
+
 static inline int cx_grid(long long n, int block) { return (int)((n + block - 1) / block); }

@@ -568,16 +568,16 @@ int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_xr, cons
   LagState S;
   size_t N = n;
   S.n = n; S.noblk = noblk; S.type = type; S.dind = dind; S.cf = cf; S.ncfmax = ncfmax;
-  CX_CUDA(cudaMalloc(&S.found, sizeof(int) * N));
-  CX_CUDA(cudaMalloc(&S.ijk, sizeof(int) * 3 * N));
-  CX_CUDA(cudaMalloc(&S.tcf, sizeof(double) * 15 * N));
-  CX_CUDA(cudaMalloc(&S.ksi, sizeof(double) * 3 * N));
-  CX_CUDA(cudaMalloc(&S.err, sizeof(int) * N));
-  CX_CUDA(cudaMalloc(&S.best, sizeof(double) * N));
+  CX_MALLOC(S.found, sizeof(int) * N, s);
+  CX_MALLOC(S.ijk, sizeof(int) * 3 * N, s);
+  CX_MALLOC(S.tcf, sizeof(double) * 15 * N, s);
+  CX_MALLOC(S.ksi, sizeof(double) * 3 * N, s);
+  CX_MALLOC(S.err, sizeof(int) * N, s);
+  CX_MALLOC(S.best, sizeof(double) * N, s);
   unsigned long long *d_f, *d_p; int* d_list;
-  CX_CUDA(cudaMalloc(&d_f, sizeof(unsigned long long) * N));
-  CX_CUDA(cudaMalloc(&d_p, sizeof(unsigned long long) * N));
-  CX_CUDA(cudaMalloc(&d_list, sizeof(int) * N));
+  CX_MALLOC(d_f, sizeof(unsigned long long) * N, s);
+  CX_MALLOC(d_p, sizeof(unsigned long long) * N, s);
+  CX_MALLOC(d_list, sizeof(int) * N, s);
   const int TB = 128;
   k_lag_init<<<cx_grid(n, 256), 256, 0, s>>>(S);
   ctx->launches++;
@@ -608,7 +608,7 @@ int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_xr, cons
   ctx->launches++;
   CX_CUDA(cudaStreamSynchronize(s));
   CX_CUDA(cudaGetLastError());
-  cudaFree(S.found); cudaFree(S.ijk); cudaFree(S.tcf); cudaFree(S.ksi); cudaFree(S.err); cudaFree(S.best);
-  cudaFree(d_f); cudaFree(d_p); cudaFree(d_list);
+  cudaFreeAsync(S.found, s); cudaFreeAsync(S.ijk, s); cudaFreeAsync(S.tcf, s); cudaFreeAsync(S.ksi, s); cudaFreeAsync(S.err, s); cudaFreeAsync(S.best, s);
+  cudaFreeAsync(d_f, s); cudaFreeAsync(d_p, s); cudaFreeAsync(d_list, s);
   return 0;
 }

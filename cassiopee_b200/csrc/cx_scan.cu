@@ -111,7 +111,7 @@ int cx_exclusive_scan_u64(cx_ctx* ctx, const unsigned long long* d_in, unsigned 
   if (n <= 0) { if (h_total) *h_total = 0; return 0; }
   int nb = (n + TILE - 1) / TILE;
   unsigned long long* d_sums;
-  CX_CUDA(cudaMalloc(&d_sums, sizeof(unsigned long long) * (nb + 1)));
+  CX_MALLOC(d_sums, sizeof(unsigned long long) * (nb + 1), ctx->stream);
   k_tile_sums<<<nb, TB, 0, ctx->stream>>>(d_in, d_sums, n);
   k_scan_sums<<<1, TB, 0, ctx->stream>>>(d_sums, nb);
   k_tile_scan<<<nb, TB, 0, ctx->stream>>>(d_in, d_out, d_sums, n);
@@ -122,6 +122,6 @@ int cx_exclusive_scan_u64(cx_ctx* ctx, const unsigned long long* d_in, unsigned 
     CX_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   CX_CUDA(cudaGetLastError());
-  cudaFree(d_sums);
+  cudaFreeAsync(d_sums, ctx->stream);
   return 0;
 }

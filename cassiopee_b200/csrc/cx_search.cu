@@ -54,15 +54,14 @@ k_interp_o2(int n, const double* __restrict__ xr, const double* __restrict__ yr,
 
 // Extrapolation pass over the receptors that found no donor.
 __global__ void __launch_bounds__(128)
-k_extrap(int nfail, const int* __restrict__ fail, const double* __restrict__ xr, const double* __restrict__ yr,
+k_extrap(int n, const double* __restrict__ xr, const double* __restrict__ yr,
          const double* __restrict__ zr, int nz, const ZoneView* __restrict__ zones, int nature, int penalty,
          RcvTable T, unsigned long long* gstats)
 {
-  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
   SearchStats st; st.nvisit = 0; st.ncand = 0; st.ntet = 0;
-  if (a < nfail)
+  if (r < n && T.noblk[r] == 0)
   {
-    int r = fail[a];
     RcvOut o;
     extrap_receptor(xr[r], yr[r], zr[r], nz, zones, nature, penalty, o, &st);
     if (o.noblk > 0)
@@ -92,6 +91,31 @@ __global__ void k_flags(int n, const int* __restrict__ noblk, const int* __restr
   else if (mode == 1) { if (b == which && isext[r] == 1) v = 1; }
   else { if (b == 0) v = 1; }
   f[r] = v;
+}
+
+// per-zone totals in one pass: cnt[z*3+0] entries, +1 coefficients, +2 extrapolated; cnt[nz*3] orphans
+// (lanes of a warp with the same zone are reduced with match/reduce before the atomics)
+__global__ void k_zone_hist(int n, int nz, const int* __restrict__ noblk, const int* __restrict__ type,
+                            const int* __restrict__ isext, unsigned long long* __restrict__ cnt)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  bool on = r < n;
+  unsigned live = __ballot_sync(0xffffffffu, on);
+  if (!on) return;
+  int b = noblk[r];
+  unsigned ncf = b > 0 ? (unsigned)ncf_of_type(type[r]) : 0u;
+  unsigned ext = (b > 0 && isext[r] == 1) ? 1u : 0u;
+  unsigned grp = __match_any_sync(live, b);
+  unsigned s2 = __reduce_add_sync(grp, ncf);
+  unsigned s3 = __reduce_add_sync(grp, ext);
+  if ((int)(threadIdx.x & 31) != __ffs(grp) - 1) return;
+  if (b > 0)
+  {
+    atomicAdd(&cnt[(b - 1) * 3 + 0], (unsigned long long)__popc(grp));
+    atomicAdd(&cnt[(b - 1) * 3 + 1], (unsigned long long)s2);
+    if (s3) atomicAdd(&cnt[(b - 1) * 3 + 2], (unsigned long long)s3);
+  }
+  else atomicAdd(&cnt[nz * 3], (unsigned long long)__popc(grp));
 }
 
 __global__ void k_scatter_entries(int n, RcvTable T, int which, const unsigned long long* __restrict__ f,
@@ -145,13 +169,13 @@ int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, co
   R->d_noblk = R->d_type = R->d_dind = R->d_isext = nullptr; R->d_cf = nullptr;
   if (n == 0) return 0;
   size_t N = n;
-  CX_CUDA(cudaMalloc(&R->d_noblk, sizeof(int) * N));
-  CX_CUDA(cudaMalloc(&R->d_type, sizeof(int) * N));
-  CX_CUDA(cudaMalloc(&R->d_dind, sizeof(int) * N));
-  CX_CUDA(cudaMalloc(&R->d_isext, sizeof(int) * N));
-  CX_CUDA(cudaMalloc(&R->d_cf, sizeof(double) * N * ncfmax));
+  CX_MALLOC(R->d_noblk, sizeof(int) * N, s);
+  CX_MALLOC(R->d_type, sizeof(int) * N, s);
+  CX_MALLOC(R->d_dind, sizeof(int) * N, s);
+  CX_MALLOC(R->d_isext, sizeof(int) * N, s);
+  CX_MALLOC(R->d_cf, sizeof(double) * N * ncfmax, s);
   unsigned long long* d_stats;
-  CX_CUDA(cudaMalloc(&d_stats, sizeof(unsigned long long) * 4));
+  CX_MALLOC(d_stats, sizeof(unsigned long long) * 4, s);
   CX_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * 4, s));
   RcvTable T{R->d_noblk, R->d_type, R->d_dind, R->d_isext, R->d_cf, n, ncfmax};
   const int TB = 128;
@@ -170,85 +194,74 @@ int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, co
   }
   CX_CUDA(cudaEventRecord(ctx->ev1, s));
 
-  unsigned long long *d_f, *d_p;
-  CX_CUDA(cudaMalloc(&d_f, sizeof(unsigned long long) * N));
-  CX_CUDA(cudaMalloc(&d_p, sizeof(unsigned long long) * N));
+  unsigned long long *d_f, *d_p, *d_cnt;
+  CX_MALLOC(d_f, sizeof(unsigned long long) * N, s);
+  CX_MALLOC(d_p, sizeof(unsigned long long) * N, s);
+  CX_MALLOC(d_cnt, sizeof(unsigned long long) * (size_t)(nz * 3 + 1), s);
   const int TB2 = 256;
-  unsigned long long tot = 0;
 
-  // extrapolation over the orphans of the interpolation pass
+  // extrapolation over the receptors the interpolation pass left without donor
   cudaEvent_t evx0, evx1;
   cudaEventCreate(&evx0); cudaEventCreate(&evx1);
   cudaEventRecord(evx0, s);
   if (extrap == 1)
   {
-    k_flags<<<cx_grid(n, TB2), TB2, 0, s>>>(n, R->d_noblk, R->d_type, R->d_isext, 0, 2, d_f);
+    k_extrap<<<cx_grid(n, TB), TB, 0, s>>>(n, d_xr, d_yr, d_zr, nz, d_zones, nature, penalty, T, d_stats);
     ctx->launches++;
-    CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, n, &tot));
-    int nfail = (int)tot;
-    if (nfail > 0)
-    {
-      int* d_fail;
-      CX_CUDA(cudaMalloc(&d_fail, sizeof(int) * (size_t)nfail));
-      k_scatter_index<<<cx_grid(n, TB2), TB2, 0, s>>>(n, d_f, d_p, d_fail);
-      k_extrap<<<cx_grid(nfail, TB), TB, 0, s>>>(nfail, d_fail, d_xr, d_yr, d_zr, nz, d_zones, nature, penalty, T,
-                                                d_stats);
-      ctx->launches += 2;
-      CX_CUDA(cudaStreamSynchronize(s));
-      cudaFree(d_fail);
-    }
   }
   cudaEventRecord(evx1, s);
 
-  // per-zone packing
-  CX_CUDA(cudaMalloc(&D->rcv, sizeof(int) * N));
-  CX_CUDA(cudaMalloc(&D->dnr, sizeof(int) * N));
-  CX_CUDA(cudaMalloc(&D->typ, sizeof(int) * N));
-  CX_CUDA(cudaMalloc(&D->ext, sizeof(int) * N));
-  CX_CUDA(cudaMalloc(&D->orphan, sizeof(int) * N));
-  CX_CUDA(cudaMalloc(&D->coefs, sizeof(double) * N * ncfmax));
+  // per-zone totals (one pass, one host sync), then flag/scan/scatter per non-empty zone without further syncs
+  CX_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * (size_t)(nz * 3 + 1), s));
+  k_zone_hist<<<cx_grid(n, TB2), TB2, 0, s>>>(n, nz, R->d_noblk, R->d_type, R->d_isext, d_cnt);
+  ctx->launches++;
+  std::vector<unsigned long long> hc((size_t)nz * 3 + 1);
+  CX_CUDA(cudaMemcpyAsync(hc.data(), d_cnt, sizeof(unsigned long long) * hc.size(), cudaMemcpyDeviceToHost, s));
+  CX_CUDA(cudaStreamSynchronize(s));
   long long eo = 0, co = 0, xo = 0;
   for (int z = 0; z < nz; z++)
   {
     D->e_off[z] = eo; D->c_off[z] = co; D->x_off[z] = xo;
-    k_flags<<<cx_grid(n, TB2), TB2, 0, s>>>(n, R->d_noblk, R->d_type, R->d_isext, z + 1, 0, d_f);
-    ctx->launches++;
-    CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, n, &tot));
-    int cnt = (int)(tot >> 32);
-    long long nco = (long long)(tot & 0xffffffffull);
-    R->cnt[z] = cnt; R->ncoef[z] = (int)nco;
-    if (cnt > 0)
-    {
-      k_scatter_entries<<<cx_grid(n, TB2), TB2, 0, s>>>(n, T, z + 1, d_f, d_p, D->rcv + eo, D->dnr + eo, D->typ + eo,
-                                                       D->coefs + co);
-      ctx->launches++;
-      if (extrap == 1)
-      {
-        k_flags<<<cx_grid(n, TB2), TB2, 0, s>>>(n, R->d_noblk, R->d_type, R->d_isext, z + 1, 1, d_f);
-        ctx->launches++;
-        CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, n, &tot));
-        R->nextrap[z] = (int)tot;
-        if (tot > 0)
-        {
-          k_scatter_index<<<cx_grid(n, TB2), TB2, 0, s>>>(n, d_f, d_p, D->ext + xo);
-          ctx->launches++;
-        }
-      }
-    }
-    eo += cnt; co += nco; xo += R->nextrap[z];
+    R->cnt[z] = (int)hc[z * 3]; R->ncoef[z] = (int)hc[z * 3 + 1]; R->nextrap[z] = (int)hc[z * 3 + 2];
+    eo += R->cnt[z]; co += R->ncoef[z]; xo += R->nextrap[z];
   }
   D->e_off[nz] = eo; D->c_off[nz] = co; D->x_off[nz] = xo;
-  k_flags<<<cx_grid(n, TB2), TB2, 0, s>>>(n, R->d_noblk, R->d_type, R->d_isext, 0, 2, d_f);
-  ctx->launches++;
-  CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, n, &tot));
-  R->norphan = (int)tot;
-  if (tot > 0) { k_scatter_index<<<cx_grid(n, TB2), TB2, 0, s>>>(n, d_f, d_p, D->orphan); ctx->launches++; }
+  R->norphan = (int)hc[(size_t)nz * 3];
+  CX_MALLOC(D->rcv, sizeof(int) * (size_t)std::max(eo, 1ll), s);
+  CX_MALLOC(D->dnr, sizeof(int) * (size_t)std::max(eo, 1ll), s);
+  CX_MALLOC(D->typ, sizeof(int) * (size_t)std::max(eo, 1ll), s);
+  CX_MALLOC(D->ext, sizeof(int) * (size_t)std::max(xo, 1ll), s);
+  CX_MALLOC(D->orphan, sizeof(int) * (size_t)std::max(R->norphan, 1), s);
+  CX_MALLOC(D->coefs, sizeof(double) * (size_t)std::max(co, 1ll), s);
+  for (int z = 0; z < nz; z++)
+  {
+    if (R->cnt[z] == 0) continue;
+    k_flags<<<cx_grid(n, TB2), TB2, 0, s>>>(n, R->d_noblk, R->d_type, R->d_isext, z + 1, 0, d_f);
+    CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, n, nullptr));
+    k_scatter_entries<<<cx_grid(n, TB2), TB2, 0, s>>>(n, T, z + 1, d_f, d_p, D->rcv + D->e_off[z], D->dnr + D->e_off[z],
+                                                     D->typ + D->e_off[z], D->coefs + D->c_off[z]);
+    ctx->launches += 2;
+    if (R->nextrap[z] > 0)
+    {
+      k_flags<<<cx_grid(n, TB2), TB2, 0, s>>>(n, R->d_noblk, R->d_type, R->d_isext, z + 1, 1, d_f);
+      CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, n, nullptr));
+      k_scatter_index<<<cx_grid(n, TB2), TB2, 0, s>>>(n, d_f, d_p, D->ext + D->x_off[z]);
+      ctx->launches += 2;
+    }
+  }
+  if (R->norphan > 0)
+  {
+    k_flags<<<cx_grid(n, TB2), TB2, 0, s>>>(n, R->d_noblk, R->d_type, R->d_isext, 0, 2, d_f);
+    CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, n, nullptr));
+    k_scatter_index<<<cx_grid(n, TB2), TB2, 0, s>>>(n, d_f, d_p, D->orphan);
+    ctx->launches += 2;
+  }
   CX_CUDA(cudaStreamSynchronize(s));
   CX_CUDA(cudaGetLastError());
   cudaEventElapsedTime(&R->search_ms, ctx->ev0, ctx->ev1);
   cudaEventElapsedTime(&R->extrap_ms, evx0, evx1);
   cudaEventDestroy(evx0); cudaEventDestroy(evx1);
   CX_CUDA(cudaMemcpy(R->stats, d_stats, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost));
-  cudaFree(d_stats); cudaFree(d_f); cudaFree(d_p);
+  cudaFreeAsync(d_stats, s); cudaFreeAsync(d_f, s); cudaFreeAsync(d_p, s); cudaFreeAsync(d_cnt, s);
   return 0;
 }

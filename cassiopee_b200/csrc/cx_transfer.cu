@@ -244,21 +244,21 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
   cudaStream_t s = ctx->stream;
   const size_t N = n;
   int *r_dn, *r_rc, *r_ty; unsigned long long *r_off, *d_cnt, *d_scan; double* r_cf;
-  CX_CUDA(cudaMalloc(&r_dn, sizeof(int) * N)); CX_CUDA(cudaMalloc(&r_rc, sizeof(int) * N));
-  CX_CUDA(cudaMalloc(&r_ty, sizeof(int) * N)); CX_CUDA(cudaMalloc(&r_off, sizeof(unsigned long long) * N));
-  CX_CUDA(cudaMalloc(&r_cf, sizeof(double) * (size_t)std::max(run, 1ll)));
+  CX_MALLOC(r_dn, sizeof(int) * N, s); CX_MALLOC(r_rc, sizeof(int) * N, s);
+  CX_MALLOC(r_ty, sizeof(int) * N, s); CX_MALLOC(r_off, sizeof(unsigned long long) * N, s);
+  CX_MALLOC(r_cf, sizeof(double) * (size_t)std::max(run, 1ll), s);
   const int sorted = plan_sort_mode();
   const size_t nscan = sorted ? (size_t)nptsD : N;
-  CX_CUDA(cudaMalloc(&d_cnt, sizeof(unsigned long long) * nscan));
-  CX_CUDA(cudaMalloc(&d_scan, sizeof(unsigned long long) * nscan));
+  CX_MALLOC(d_cnt, sizeof(unsigned long long) * nscan, s);
+  CX_MALLOC(d_scan, sizeof(unsigned long long) * nscan, s);
   CX_CUDA(cudaMemcpyAsync(r_dn, donor, sizeof(int) * N, cudaMemcpyHostToDevice, s));
   CX_CUDA(cudaMemcpyAsync(r_rc, rcv, sizeof(int) * N, cudaMemcpyHostToDevice, s));
   CX_CUDA(cudaMemcpyAsync(r_ty, type, sizeof(int) * N, cudaMemcpyHostToDevice, s));
   CX_CUDA(cudaMemcpyAsync(r_off, off.data(), sizeof(unsigned long long) * N, cudaMemcpyHostToDevice, s));
   CX_CUDA(cudaMemcpyAsync(r_cf, coefs, sizeof(double) * (size_t)run, cudaMemcpyHostToDevice, s));
-  CX_CUDA(cudaMalloc(&P->d_donor, sizeof(int) * N));
-  CX_CUDA(cudaMalloc(&P->d_rcv, sizeof(int) * N));
-  CX_CUDA(cudaMalloc(&P->d_pos, sizeof(int) * N));
+  CX_MALLOC(P->d_donor, sizeof(int) * N, s);
+  CX_MALLOC(P->d_rcv, sizeof(int) * N, s);
+  CX_MALLOC(P->d_pos, sizeof(int) * N, s);
   const int TB = 256;
   int first = 0;
   for (int g = 0; g < 4; g++)
@@ -266,7 +266,7 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
     if (cnt[g] == 0) continue;
     cx_plan::Group G; G.type = types[g]; G.ncf = ncf_host(types[g]); G.sten = sten_host(types[g]);
     G.n = cnt[g]; G.first = first; G.d_cf = nullptr;
-    CX_CUDA(cudaMalloc(&G.d_cf, sizeof(double) * (size_t)G.ncf * G.n));
+    CX_MALLOC(G.d_cf, sizeof(double) * (size_t)G.ncf * G.n, s);
     if (sorted)
     {
       CX_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * nscan, s));
@@ -287,7 +287,7 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
   P->ngroups = (int)P->groups.size();
   CX_CUDA(cudaStreamSynchronize(s));
   CX_CUDA(cudaGetLastError());
-  cudaFree(r_dn); cudaFree(r_rc); cudaFree(r_ty); cudaFree(r_off); cudaFree(r_cf); cudaFree(d_cnt); cudaFree(d_scan);
+  cudaFreeAsync(r_dn, s); cudaFreeAsync(r_rc, s); cudaFreeAsync(r_ty, s); cudaFreeAsync(r_off, s); cudaFreeAsync(r_cf, s); cudaFreeAsync(d_cnt, s); cudaFreeAsync(d_scan, s);
   return 0;
 }
 
