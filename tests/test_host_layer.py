@@ -1,0 +1,139 @@
+"""CPU tests of the Python host layer (tree model, storage layout, argument
+semantics, error behaviour) with the oracle injected as compute backend."""
+import numpy as np
+import pytest
+import cassiopee_b200.Internal as Internal
+import cassiopee_b200.Converter as C
+import cassiopee_b200.Generator as G
+import cassiopee_b200.Distributor2 as D2
+import cassiopee_b200.Connector.OversetData as X
+from tests.backends import OracleBackend
+
+
+def _case():
+    h = 1. / 12
+    a = G.cart((0, 0, 0), (h, h, h), (13, 13, 13), name='A')
+    b = G.cart((0.31, 0.28, 0.33), (0.8 * h, 0.8 * h, 0.8 * h), (9, 9, 9), name='B')
+    t = C.newPyTree(['Base', a, b])
+    C._initVars(t, 'centers:Density', lambda x, y, z: 1. + x + 2 * y + 3 * z)
+    C._initVars(t, 'centers:cellN', 1.)
+    C._initVars(Internal.getZones(t)[1], 'centers:cellN', 2.)
+    return t
+
+
+def test_generators_follow_reference_formulas():
+    z = G.cart((1., 2., 3.), (0.5, 0.25, 0.125), (4, 3, 2))
+    x, y, zz = C.getCoords(z)
+    assert x.shape == (4, 3, 2) and x.flags.f_contiguous
+    assert x[3, 0, 0] == 1. + 3 * 0.5 and y[0, 2, 0] == 2. + 2 * 0.25 and zz[0, 0, 1] == 3. + 0.125
+    c = G.cylinder((0, 0, 0), 0.5, 2.5, 360., 0., 2., (9, 5, 3))
+    x, y, zz = C.getCoords(c)
+    assert abs(np.hypot(x[:, 0, 0], y[:, 0, 0]) - 0.5).max() < 1e-15
+    assert abs(np.hypot(x[:, -1, 0], y[:, -1, 0]) - 2.5).max() < 1e-14
+    assert zz[0, 0, -1] == 2.0
+    assert abs(x[0, :, :] - x[-1, :, :]).max() < 1e-14      # seam duplicated
+
+
+def test_tree_model_and_node2center():
+    t = _case()
+    zs = Internal.getZones(t)
+    assert [z[0] for z in zs] == ['A', 'B']
+    assert Internal.getZoneDim(zs[0]) == ['Structured', 13, 13, 13, 3]
+    tc = C.node2Center(t)
+    zc = Internal.getZones(tc)[0]
+    assert Internal.getZoneDim(zc)[1:4] == [12, 12, 12]
+    assert C.getFieldArray(zc, 'Density').shape == (12, 12, 12)      # centre field became a node field of tc
+    assert C.getFieldArray(zs[0], 'centers:Density') is C.getFieldArray(zc, 'Density')   # copyRef shares arrays
+    n = Internal.createNode('s', 'DataArray_t', 'Donor')
+    assert Internal.getValue(n) == 'Donor' and n[1].dtype.char == 'c'
+
+
+def test_set_interp_data_inverse_storage_layout():
+    t = _case()
+    tc = C.node2Center(t)
+    tD = Internal.copyRef(tc); tR = Internal.copyRef(t)
+    X._setInterpDataChimera(tR, tD, order=2, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse',
+                            sameName=1, verbose=0, backend=OracleBackend())
+    zA, zB = Internal.getZones(tD)
+    s = Internal.getNodeFromName1(zA, 'ID_B')
+    assert s is not None and s[3] == 'ZoneSubRegion_t' and Internal.getValue(s) == 'B'
+    names = [c[0] for c in s[2]]
+    assert names[:6] == ['ZoneRole', 'GridLocation', 'PointList', 'PointListDonor', 'InterpolantsDonor',
+                         'InterpolantsType']
+    assert Internal.getValue(s[2][0]) == 'Donor' and Internal.getValue(s[2][1]) == 'CellCenter'
+    pl = Internal.getNodeFromName1(s, 'PointList')[1]; pld = Internal.getNodeFromName1(s, 'PointListDonor')[1]
+    typ = Internal.getNodeFromName1(s, 'InterpolantsType')[1]; cf = Internal.getNodeFromName1(s, 'InterpolantsDonor')[1]
+    assert pl.dtype == np.int32 and pld.dtype == np.int32 and typ.dtype == np.int32 and cf.dtype == np.float64
+    assert pl.size == pld.size == typ.size == 8 ** 3        # every centre of B is a receptor
+    assert np.array_equal(pld, np.arange(8 ** 3))           # ascending receptor index
+    assert cf.size == sum({1: 1, 2: 8}[int(v)] for v in typ)
+    assert Internal.getNodeFromName1(zB, 'ID_A') is None     # A has no cellN==2 points
+    assert C.getFieldArray(zA, 'cellN') is not None          # tc carries the centres' cellN as a node field
+    # sameName=1 drops the donor named like the receptor
+    tD2 = Internal.copyRef(tc); tR2 = Internal.copyRef(t)
+    C._initVars(tR2, 'centers:cellN', 2.)
+    X._setInterpDataChimera(tR2, tD2, order=2, nature=1, loc='centers', storage='inverse', sameName=1, verbose=0,
+                            backend=OracleBackend())
+    for zd in Internal.getZones(tD2):
+        assert Internal.getNodeFromName1(zd, 'ID_' + zd[0]) is None
+
+
+def test_direct_storage_and_orphans():
+    t = _case()
+    tc = C.node2Center(t)
+    tR = Internal.copyRef(t); tD = Internal.copyRef(tc)
+    C._initVars(tR, 'centers:cellN', 2.)       # A's centres mostly lie outside B -> orphans without extrapolation
+    C._initVars(tD, 'cellN', 1.)               # donors all valid
+    X._setInterpDataChimera(tR, tD, order=2, nature=1, extrap=0, loc='centers', storage='direct', verbose=0,
+                            backend=OracleBackend())
+    zA = Internal.getZones(tR)[0]
+    s = Internal.getNodeFromName1(zA, 'ID_B')
+    assert Internal.getValue(Internal.getNodeFromName1(s, 'ZoneRole')) == 'Receiver'
+    orph = Internal.getNodeFromName1(s, 'OrphanPointList')[1]
+    assert orph.size > 0 and np.array_equal(orph, np.unique(orph))
+    rcv = Internal.getNodeFromName1(s, 'PointList')[1]
+    assert np.intersect1d(rcv, orph).size == 0 and rcv.size + orph.size == 12 ** 3
+
+
+def test_argument_errors_match_reference():
+    t = _case(); tc = C.node2Center(t)
+    with pytest.raises(ValueError):
+        X._setInterpDataChimera(t, tc, loc='faces', backend=OracleBackend())
+    with pytest.raises(ValueError):
+        X._setInterpDataChimera(t, tc, loc='centers', method='spline', backend=OracleBackend())
+    with pytest.raises(NotImplementedError):
+        X._setInterpDataChimera(t, tc, loc='centers', method='leastsquares', backend=OracleBackend())
+    with pytest.raises(TypeError):
+        X._setInterpDataChimera(t, tc, loc='centers', hook=[1, 2, 3], backend=OracleBackend())
+    with pytest.raises(NotImplementedError):
+        X._setInterpTransfers(t, tc, variables=['Density'], compact=1)
+    # no cellN on the receptor tree -> nothing to do (OversetData.py:1184)
+    t2 = C.newPyTree(['Base', G.cart((0, 0, 0), (1, 1, 1), (3, 3, 3))])
+    assert X._setInterpDataChimera(t2, t2, loc='nodes', backend=OracleBackend()) is None
+
+
+def test_variable_selection_rules():
+    t = _case(); tc = C.node2Center(t)
+    zr = Internal.getZones(t)[1]; zd = Internal.getZones(tc)[0]
+    C._initVars(zd, 'Extra', 3.)
+    names, strict, loc = X._selectVariables(zr, zd, [], 'cellN', 1)
+    assert 'Density' in names and 'cellN' not in names and 'Extra' not in names and strict and loc == 'centers'
+    names, strict, _ = X._selectVariables(zr, zd, ['Density', 'Missing'], 'cellN', 1)
+    assert names == ['Density'] and not strict
+    names, strict, _ = X._selectVariables(zr, zd, ['Density', 'cellN'], 'cellN', 1)
+    assert names == ['Density'] and strict
+
+
+def test_distributor2_proc_nodes():
+    zones = [G.cart((i, 0, 0), (0.1, 0.1, 0.1), (5, 5, 5), name='z%d' % i) for i in range(6)]
+    t = C.newPyTree(['Base'] + zones)
+    out = D2._distribute(t, 3, algorithm='fast')
+    d = D2.getProcDict(t)
+    assert sorted(d.keys()) == ['z%d' % i for i in range(6)] and set(d.values()) == {0, 1, 2}
+    assert max(out['nptsPerProc']) == min(out['nptsPerProc'])
+    z0 = Internal.getZones(t)[0]
+    node = Internal.getNodeFromName1(Internal.getNodeFromName1(z0, '.Solver#Param'), 'proc')
+    assert node[1].shape == (1, 1) and node[1].dtype == np.int32
+    D2._distribute(t, 2, algorithm='rcb')
+    d = D2.getProcDict(t)
+    assert [d['z%d' % i] for i in range(6)] == [0, 0, 0, 1, 1, 1]
