@@ -31,6 +31,9 @@ sys.path.insert(0, ROOT)
 METRIC = "setInterpTransfers_algorithmic_GBps"
 UNIT = "GB/s"
 NVARS_C2 = 5
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_transfer<2,0> launch on C2a (5 vars), from the
+# `ncu --set full` capture summarised in profiles/r01_b_summary.md (1.621456 GB + 655.629 MB)
+NCU_TRAFFIC_C2A_5VARS = 1621456000 + 655629056
 
 
 def measured_peaks():
@@ -234,7 +237,9 @@ def run_c2(args):
         "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": value, "peak": peak, "unit": "GB/s", "frac": value / peak,
-                     "traffic": None, "peak_source": how, "kernel": "k_transfer<2,0>",
+                     "traffic": NCU_TRAFFIC_C2A_5VARS if (args.scale == 1.0 and nvars == 5) else None,
+                     "traffic_source": "profiles/r01_b_summary.md (ncu --set full, one launch)",
+                     "peak_source": how, "kernel": "k_transfer<2,0>",
                      "frac_of_nominal_8TBps": value / 8000.0},
         "cpu_baseline": cpu,
         "set_interp_data": sid,

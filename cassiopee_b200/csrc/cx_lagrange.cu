@@ -148,8 +148,8 @@ __device__ void lag_solve_group(const ZoneView& Z, int ics, int jcs, int kcs, do
   double* pz = py + N;
   double* sc = pz + N;            // 16: pts(3,4) + transformed receptor
   volatile double* red_v = sc + 16;          // NT/32 partial maxima
-  volatile int* red_i = (volatile int*)(red_v + 8);   // NT/32 indices
-  int* ipiv = (int*)(red_v + 8) + 16;        // N flags
+  volatile int* red_i = (volatile int*)(red_v + 32);  // 2 x NT/32 indices
+  int* ipiv = (int*)(red_v + 32) + 32;       // N flags
   int* ctl = ipiv + N + 3;                   // [0]=irow [1]=icol [2]=singular
 
   const int ni = Z.ni, ninj = Z.ni * Z.nj;
@@ -228,92 +228,95 @@ __device__ void lag_solve_group(const ZoneView& Z, int ics, int jcs, int kcs, do
   gsync<WARP>();
 
   // --- kgaussj (GaussjF.for:29-100) -----------------------------------------
-  // thread -> (row, column segment): SEG segments per row
-  constexpr int SEG = (NT >= 2 * N) ? 2 : 1;
-  constexpr int ROWS = (SEG == 2) ? (NT / 2) : NT;
+  // thread -> (row, column segment): SEG segments per row.  The full-pivot search of step s+1 is fused
+  // into the elimination of step s: while a thread updates its part of a row it tracks that part's
+  // maximum |a| over the still un-pivoted columns (ascending columns, '>=' => last maximum, exactly the
+  // scan order of GaussjF.for:34-44), so each search is only a cross-thread arg-max.
+  constexpr int SEG = (NT >= 4 * N) ? 4 : (NT >= 2 * N) ? 2 : 1;
+  constexpr int ROWS = NT / SEG;
   const int row = tid % ROWS;
   const int seg = tid / ROWS;
   constexpr int CHUNK = (N + SEG - 1) / SEG;
   const int c0 = seg * CHUNK;
   const int c1 = (c0 + CHUNK < N) ? c0 + CHUNK : N;
   const bool rowOn = row < N && seg < SEG;
+  static_assert(CHUNK <= 32, "live-column mask is one 32-bit word per thread");
+  unsigned live = 0u;          // bit i set <=> column c0+i of this thread's segment is still un-pivoted
+  if (rowOn) live = (c1 - c0 >= 32) ? 0xffffffffu : ((1u << (c1 - c0)) - 1u);
+  double tmax = -1.; int tidx = -1;
+  if (rowOn)
+  {
+    const double* ar = A + row * LD;
+    for (int k = c0; k < c1; k++)
+    {
+      double v = fabs(ar[k]);
+      if (v >= tmax) { tmax = v; tidx = row * N + k; }
+    }
+  }
   for (int step = 0; step < N; step++)
   {
-    // full pivot search; the LAST maximum in (row, column) order wins
+    // rows whose index is an already pivoted column are excluded (ipiv(j).NE.1)
     double big = -1.; int bidx = -1;
-    if (rowOn && ipiv[row] != 1)
-    {
-      const double* ar = A + row * LD;
-      for (int k = c0; k < c1; k++)
-        if (ipiv[k] == 0)
-        {
-          double v = fabs(ar[k]);
-          if (v >= big) { big = v; bidx = row * N + k; }
-        }
+    if (rowOn && ipiv[row] != 1) { big = tmax; bidx = tidx; }
+    // arg-max: larger value, then larger (row,col) index == the LAST maximum of the reference's scan
+#define CX_ARGMAX_STEP(o)                                                     \
+    {                                                                         \
+      double ov = __shfl_down_sync(0xffffffffu, big, o);                      \
+      int oi = __shfl_down_sync(0xffffffffu, bidx, o);                        \
+      if (ov > big || (ov == big && oi > bidx)) { big = ov; bidx = oi; }      \
     }
-    // warp argmax: larger value, then larger (row,col) index
-    for (int o = 16; o > 0; o >>= 1)
-    {
-      double ov = __shfl_down_sync(0xffffffffu, big, o);
-      int oi = __shfl_down_sync(0xffffffffu, bidx, o);
-      if (ov > big || (ov == big && oi > bidx)) { big = ov; bidx = oi; }
-    }
+    CX_ARGMAX_STEP(16) CX_ARGMAX_STEP(8) CX_ARGMAX_STEP(4) CX_ARGMAX_STEP(2) CX_ARGMAX_STEP(1)
     if (WARP)
     {
       bidx = __shfl_sync(0xffffffffu, bidx, 0);
     }
     else
     {
-      if ((tid & 31) == 0) { red_v[tid >> 5] = big; red_i[tid >> 5] = bidx; }
+      // one barrier: every warp publishes its winner, then every warp reduces the NT/32 winners itself
+      const int par = step & 1;       // double-buffered so the next step's writes cannot race with late readers
+      if ((tid & 31) == 0) { red_v[par * 16 + (tid >> 5)] = big; red_i[par * 16 + (tid >> 5)] = bidx; }
       __syncthreads();
-      if (tid == 0)
-      {
-        double bv = red_v[0]; int bi = red_i[0];
-        for (int w = 1; w < NT / 32; w++)
-        {
-          double ov = red_v[w]; int oi = red_i[w];
-          if (ov > bv || (ov == bv && oi > bi)) { bv = ov; bi = oi; }
-        }
-        red_i[0] = bi;
-      }
-      __syncthreads();
-      bidx = red_i[0];
+      int ln = tid & 31;
+      big = (ln < NT / 32) ? red_v[par * 16 + ln] : -2.;
+      bidx = (ln < NT / 32) ? red_i[par * 16 + ln] : -1;
+      CX_ARGMAX_STEP(16) CX_ARGMAX_STEP(8) CX_ARGMAX_STEP(4) CX_ARGMAX_STEP(2) CX_ARGMAX_STEP(1)
+      bidx = __shfl_sync(0xffffffffu, bidx, 0);
     }
+#undef CX_ARGMAX_STEP
     // bidx < 0 can only happen with NaNs everywhere; treat like the singular exit
     if (bidx < 0) { if (tid == 0) ctl[2] = 1; gsync<WARP>(); break; }
     const int irow = bidx / N, icol = bidx % N;
-    gsync<WARP>();
-    if (tid == 0) ipiv[icol] = ipiv[icol] + 1;
-    // row swap (all live columns + RHS)
-    if (irow != icol)
-    {
-      for (int l = tid; l < N + 3; l += NT)
-      {
-        double* a = A + irow * LD + l; double* b = A + icol * LD + l;
-        double dum = *a; *a = *b; *b = dum;
-      }
-    }
-    gsync<WARP>();
-    double piv = A[icol * LD + icol];
+    const double piv = A[irow * LD + icol];      // a(icol,icol) after the row interchange
+    if (icol >= c0 && icol < c1) live &= ~(1u << (icol - c0));
+    gsync<WARP>();                               // everybody has read the pivot before rows change
     if (piv == 0.) { if (tid == 0) ctl[2] = 1; gsync<WARP>(); break; }   // 'singular matrix in gaussj, 2'
-    double pivinv = 1. / piv;
-    gsync<WARP>();
-    // scale the pivot row: a(icol,icol)=1 then row*pivinv (GaussjF.for:70-77)
+    const double pivinv = 1. / piv;
+    if (tid == 0) ipiv[icol] = ipiv[icol] + 1;
+    // row interchange irow <-> icol and scaling of the pivot row in one pass (GaussjF.for:51-77)
     for (int l = tid; l < N + 3; l += NT)
     {
-      double* a = A + icol * LD + l;
-      if (l == icol) *a = 1. * pivinv;
-      else if (l >= N || ipiv[l] == 0) *a = *a * pivinv;
+      double* a = A + irow * LD + l; double* b = A + icol * LD + l;
+      double x = *a, y = *b;
+      *b = (l == icol) ? 1. * pivinv : x * pivinv;
+      if (irow != icol) *a = y;
     }
     gsync<WARP>();
-    // eliminate column icol from every other row (GaussjF.for:78-89)
+    // eliminate column icol from every other row (GaussjF.for:78-89); only live columns and the 3 RHS
+    // are updated; the maxima for the next search are tracked on the fly
+    tmax = -1.; tidx = -1;
     if (rowOn && row != icol)
     {
       double* ar = A + row * LD;
       const double* ap = A + icol * LD;
-      double dum = ar[icol];
-      for (int l = c0; l < c1; l++)
-        if (ipiv[l] == 0) ar[l] = ar[l] - ap[l] * dum;
+      const double dum = ar[icol];
+      for (unsigned mk = live; mk; mk &= mk - 1)
+      {
+        int l = c0 + __ffs(mk) - 1;
+        double nv = ar[l] - ap[l] * dum;
+        ar[l] = nv;
+        double v = fabs(nv);
+        if (v >= tmax) { tmax = v; tidx = row * N + l; }
+      }
       if (seg == SEG - 1)
       {
         ar[N] = ar[N] - ap[N] * dum; ar[N + 1] = ar[N + 1] - ap[N + 1] * dum; ar[N + 2] = ar[N + 2] - ap[N + 2] * dum;
@@ -359,7 +362,7 @@ template <int N1> struct LagCfg {
   static constexpr int N = N1 * N1 * N1;
   static constexpr int LD = (N + 3) | 1;
   // doubles of shared memory per group
-  static constexpr int SMEM_D = N * LD + 3 * N + 16 + 8 + ((16 + N + 3 + 4) * 4 + 7) / 8;
+  static constexpr int SMEM_D = N * LD + 3 * N + 16 + 32 + ((32 + N + 3 + 4) * 4 + 7) / 8;
 };
 
 // order 3: one warp per receptor, 4 receptors per CTA
@@ -384,8 +387,8 @@ k_lag_solve3(LagState S, int nlist, const int* __restrict__ list, const double* 
   }
 }
 
-// order 5: one 256-thread CTA per receptor, matrix (125 x 129 doubles) in shared memory
-__global__ void __launch_bounds__(256)
+// order 5: one 512-thread CTA per receptor, matrix (125 x 129 doubles) in shared memory
+__global__ void __launch_bounds__(512)
 k_lag_solve5(LagState S, int nlist, const int* __restrict__ list, const double* __restrict__ xr,
              const double* __restrict__ yr, const double* __restrict__ zr, const ZoneView* __restrict__ zones, int noz)
 {
@@ -397,7 +400,7 @@ k_lag_solve5(LagState S, int nlist, const int* __restrict__ list, const double* 
     int ics, jcs, kcs;
     stencil_start(5, Z, S.ijk[r], S.ijk[(size_t)S.n + r], S.ijk[2 * (size_t)S.n + r], ics, jcs, kcs);
     double ksi, eta, zeta; int err;
-    lag_solve_group<5, 256, false>(Z, ics, jcs, kcs, xr[r], yr[r], zr[r], smem, threadIdx.x, ksi, eta, zeta, err);
+    lag_solve_group<5, 512, false>(Z, ics, jcs, kcs, xr[r], yr[r], zr[r], smem, threadIdx.x, ksi, eta, zeta, err);
     if (threadIdx.x == 0)
     {
       S.ksi[r] = ksi; S.ksi[(size_t)S.n + r] = eta; S.ksi[2 * (size_t)S.n + r] = zeta; S.err[r] = err;
@@ -599,7 +602,7 @@ int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_xr, cons
     else
     {
       int grid = nlist < ctx->sm_count * 4 ? nlist : ctx->sm_count * 4;
-      k_lag_solve5<<<grid, 256, smem5, s>>>(S, nlist, d_list, d_xr, d_yr, d_zr, d_zones, noz);
+      k_lag_solve5<<<grid, 512, smem5, s>>>(S, nlist, d_list, d_xr, d_yr, d_zr, d_zones, noz);
     }
     k_lag_finish<<<cx_grid(n, TB), TB, 0, s>>>(S, d_zones, noz, order, nature, penalty);
     ctx->launches += 3;
