@@ -52,22 +52,121 @@ k_interp_o2(int n, const double* __restrict__ xr, const double* __restrict__ yr,
   if (gstats) warp_add_stats(gstats, st);
 }
 
-// Extrapolation pass over the receptors that found no donor.
+// Extrapolation pass over the receptors that found no donor: ONE WARP per receptor.
+// The reference evaluates all 24 tetrahedra of every candidate cell and folds the candidates
+// sequentially (InterpAdt.cpp:1113-1147).  Here lane 0 walks the ADT and hands out batches of up to 32
+// candidates, the lanes evaluate one candidate each (extrap_coeff_for_cell, the expensive part), and the
+// fold `ret==1 && sum < saved+1e-6 && diff < saved_diff` is then replayed in candidate order with
+// shuffles, so the winner is the reference's.
+__device__ __forceinline__ int search_extrap_cell_warp(const ZoneView& Z, double x, double y, double z, int& ic, int& jc,
+                                                       int& kc, double* cf, int nature, double constraint,
+                                                       int* s_cand, int lane, SearchStats* st)
+{
+  for (int i = 0; i < 8; i++) cf[i] = 0.;
+  double alphaTol = fmax((2 * constraint - 5.) * 0.1, 0.);
+  if (zone_reject(Z, x, y, z, alphaTol)) return 0;
+  AdtQuery q;
+  if (lane == 0) query_init(q, Z, x, y, z, alphaTol);
+  const int ni = Z.ni, nij = Z.ni * Z.nj;
+  double saved_sum = CX_MAXF, saved_diff = CX_MAXF;
+  int found = 0, icsav = 0, jcsav = 0, kcsav = 0, ncand = 0;
+  double cfs[8];
+  for (int i = 0; i < 8; i++) cfs[i] = 0.;
+  bool done = false;
+  while (!done)
+  {
+    int cnt = 0;
+    if (lane == 0)
+    {
+      int c, nid, nvisit = 0;
+      while (cnt < 32 && (c = query_next(q, Z.nodes, &nid, &nvisit)) >= 0) s_cand[cnt++] = c;
+      if (st) st->nvisit += nvisit;
+      if (cnt < 32) cnt |= 0x100;        // traversal exhausted
+    }
+    __syncwarp();
+    cnt = __shfl_sync(0xffffffffu, cnt, 0);
+    done = (cnt & 0x100) != 0;
+    cnt &= 0xff;
+    ncand += cnt;
+    int ret = 0, i = 0, j = 0, k = 0;
+    double sum = 0., diff = CX_MAXF, cft[8];
+    if (lane < cnt)
+    {
+      int c = s_cand[lane];
+      k = c / nij; j = (c - k * nij) / ni; i = c - j * ni - k * nij;
+      k++; j++; i++;
+      ret = extrap_coeff_for_cell(Z, x, y, z, i, j, k, cft, nature, constraint, diff);
+      sum = fabs(cft[0]) + fabs(cft[1]) + fabs(cft[2]) + fabs(cft[3]) + fabs(cft[4]) + fabs(cft[5]) + fabs(cft[6]) +
+            fabs(cft[7]);
+    }
+    __syncwarp();
+    for (int l = 0; l < cnt; l++)
+    {
+      int rl = __shfl_sync(0xffffffffu, ret, l);
+      double sl = __shfl_sync(0xffffffffu, sum, l);
+      double dl = __shfl_sync(0xffffffffu, diff, l);
+      if (rl == 1 && sl < saved_sum + 1.e-6 && dl < saved_diff)      // uniform across the warp
+      {
+        saved_diff = dl; saved_sum = sl; found = 1;
+        icsav = __shfl_sync(0xffffffffu, i, l); jcsav = __shfl_sync(0xffffffffu, j, l);
+        kcsav = __shfl_sync(0xffffffffu, k, l);
+        for (int m = 0; m < 8; m++) cfs[m] = __shfl_sync(0xffffffffu, cft[m], l);
+      }
+    }
+  }
+  if (st && lane == 0) st->ncand += ncand;
+  if (ncand == 0) return 0;
+  ic = icsav; jc = jcsav; kc = kcsav;
+  for (int m = 0; m < 8; m++) cf[m] = cfs[m];
+  return found;
+}
+
 __global__ void __launch_bounds__(128)
-k_extrap(int n, const double* __restrict__ xr, const double* __restrict__ yr,
+k_extrap(int nlist, const int* __restrict__ list, const double* __restrict__ xr, const double* __restrict__ yr,
          const double* __restrict__ zr, int nz, const ZoneView* __restrict__ zones, int nature, int penalty,
          RcvTable T, unsigned long long* gstats)
 {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ int s_cand[4][32];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a = blockIdx.x * 4 + w;
   SearchStats st; st.nvisit = 0; st.ncand = 0; st.ntet = 0;
-  if (r < n && T.noblk[r] == 0)
+  if (a < nlist)                                   // warp-uniform
   {
-    RcvOut o;
-    extrap_receptor(xr[r], yr[r], zr[r], nz, zones, nature, penalty, o, &st);
-    if (o.noblk > 0)
+    const int r = list[a];
+    const double x = xr[r], y = yr[r], z = zr[r];
+    // K_INTERP::getExtrapolationCell (Interp.cpp:282-360): constraint=40, extrapOrder=1, order forced to O2CF
+    double best = CX_MAXF, sumCoefMin = CX_MAXF;
+    int noblk = 0, type = 0, dind = -1;
+    double cf[8], tcf[8];
+    for (int i = 0; i < 8; i++) { cf[i] = 0.; tcf[i] = 0.; }
+    for (int noz = 0; noz < nz; noz++)
     {
-      T.noblk[r] = o.noblk; T.type[r] = o.type; T.dind[r] = o.dind; T.isext[r] = 1;
-      for (int i = 0; i < 8; i++) T.cf[(size_t)i * T.n + r] = o.cf[i];
+      const ZoneView& Z = zones[noz];
+      int ic, jc, kc;
+      int found = search_extrap_cell_warp(Z, x, y, z, ic, jc, kc, tcf, nature, 40., s_cand[w], lane, &st);
+      if (found < 1) continue;
+      ic -= 1; jc -= 1; kc -= 1;
+      int isBorder = (ic == 0 || ic == Z.ni - 2 || jc == 0 || jc == Z.nj - 2 || kc == 0 || kc == Z.nk - 2);
+      int tind = ic + jc * Z.ni + kc * Z.ni * Z.nj;
+      double vol = cell_volume(Z, tind);
+      if (penalty == 1 && isBorder == 1) vol += 1.e3;
+      if (vol < best + CX_EPS_GEOM)
+      {
+        double sumCf = 0.;
+        for (int i = 0; i < 8; i++) sumCf += fabs(tcf[i]);
+        if (sumCf < sumCoefMin)
+        {
+          sumCoefMin = sumCf;
+          best = vol; type = 2; dind = tind; noblk = noz + 1;
+          for (int i = 0; i < 8; i++) cf[i] = tcf[i];
+        }
+      }
+    }
+    if (noblk > 0 && lane == 0)
+    {
+      collapse_type2(zones[noblk - 1], type, dind, cf);
+      T.noblk[r] = noblk; T.type[r] = type; T.dind[r] = dind; T.isext[r] = 1;
+      for (int i = 0; i < 8; i++) T.cf[(size_t)i * T.n + r] = cf[i];
     }
   }
   if (gstats) warp_add_stats(gstats, st);
@@ -200,24 +299,36 @@ int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, co
   CX_MALLOC(d_cnt, sizeof(unsigned long long) * (size_t)(nz * 3 + 1), s);
   const int TB2 = 256;
 
-  // extrapolation over the receptors the interpolation pass left without donor
+  // per-zone totals (one pass); if the interpolation pass left orphans and extrapolation is enabled, run the
+  // warp-per-receptor extrapolation over their compacted list and count again
+  std::vector<unsigned long long> hc((size_t)nz * 3 + 1);
+  auto histogram = [&]() -> int {
+    CX_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * (size_t)(nz * 3 + 1), s));
+    k_zone_hist<<<cx_grid(n, TB2), TB2, 0, s>>>(n, nz, R->d_noblk, R->d_type, R->d_isext, d_cnt);
+    ctx->launches++;
+    CX_CUDA(cudaMemcpyAsync(hc.data(), d_cnt, sizeof(unsigned long long) * hc.size(), cudaMemcpyDeviceToHost, s));
+    CX_CUDA(cudaStreamSynchronize(s));
+    return 0;
+  };
+  CX_CHECK(histogram());
   cudaEvent_t evx0, evx1;
   cudaEventCreate(&evx0); cudaEventCreate(&evx1);
   cudaEventRecord(evx0, s);
-  if (extrap == 1)
+  int nfail = (int)hc[(size_t)nz * 3];
+  if (extrap == 1 && nfail > 0)
   {
-    k_extrap<<<cx_grid(n, TB), TB, 0, s>>>(n, d_xr, d_yr, d_zr, nz, d_zones, nature, penalty, T, d_stats);
-    ctx->launches++;
+    int* d_fail;
+    CX_MALLOC(d_fail, sizeof(int) * (size_t)nfail, s);
+    k_flags<<<cx_grid(n, TB2), TB2, 0, s>>>(n, R->d_noblk, R->d_type, R->d_isext, 0, 2, d_f);
+    CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, n, nullptr));
+    k_scatter_index<<<cx_grid(n, TB2), TB2, 0, s>>>(n, d_f, d_p, d_fail);
+    k_extrap<<<cx_grid(nfail, 4), 128, 0, s>>>(nfail, d_fail, d_xr, d_yr, d_zr, nz, d_zones, nature, penalty, T, d_stats);
+    ctx->launches += 3;
+    cudaFreeAsync(d_fail, s);
+    cudaEventRecord(evx1, s);
+    CX_CHECK(histogram());
   }
-  cudaEventRecord(evx1, s);
-
-  // per-zone totals (one pass, one host sync), then flag/scan/scatter per non-empty zone without further syncs
-  CX_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * (size_t)(nz * 3 + 1), s));
-  k_zone_hist<<<cx_grid(n, TB2), TB2, 0, s>>>(n, nz, R->d_noblk, R->d_type, R->d_isext, d_cnt);
-  ctx->launches++;
-  std::vector<unsigned long long> hc((size_t)nz * 3 + 1);
-  CX_CUDA(cudaMemcpyAsync(hc.data(), d_cnt, sizeof(unsigned long long) * hc.size(), cudaMemcpyDeviceToHost, s));
-  CX_CUDA(cudaStreamSynchronize(s));
+  else cudaEventRecord(evx1, s);
   long long eo = 0, co = 0, xo = 0;
   for (int z = 0; z < nz; z++)
   {
