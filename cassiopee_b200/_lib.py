@@ -290,14 +290,17 @@ class InterpResult:
         check(lib().cx_result_sizes(self.h, ptr(cnt), ptr(nco), ptr(nex), ctypes.byref(no)))
         return cnt, nco, nex, no.value
 
-    def fetch(self):
+    def fetch(self, pinned=False):
         """The reference's 7-list [rcv]*nz,[donor]*nz,[type]*nz,[coefs]*nz,[extrap]*nz,orphan,[]
-        (Connector/Connector/setInterpData.cpp:1272)."""
+        (Connector/Connector/setInterpData.cpp:1272).  pinned=True returns numpy arrays backed by
+        page-locked memory from the reuse pool (fast D2H, no first-touch page faults)."""
         cnt, nco, nex, no = self.sizes()
         R, D, T, C, E = [], [], [], [], []
+        big = 1 << 16
+        mk = (lambda n, dt: pinned_empty(n, dt) if (pinned and n >= big) else np.empty(n, dt))
         for z in range(self.nz):
-            r = np.empty(cnt[z], np.int32); d = np.empty(cnt[z], np.int32); t = np.empty(cnt[z], np.int32)
-            c = np.empty(nco[z], np.float64); e = np.empty(nex[z], np.int32)
+            r = mk(cnt[z], np.int32); d = mk(cnt[z], np.int32); t = mk(cnt[z], np.int32)
+            c = mk(nco[z], np.float64); e = np.empty(nex[z], np.int32)
             check(lib().cx_result_fetch_zone(self.h, z, ptr(r), ptr(d), ptr(t), ptr(c), ptr(e)))
             R.append(r); D.append(d); T.append(t); C.append(c); E.append(e)
         orphan = np.empty(no, np.int32)
@@ -413,19 +416,42 @@ class _PinnedBlock:
         self._fin = weakref.finalize(self, lib().cx_pinned_free, _vp(self.ptr))
 
 
+# Page-locked blocks released by the garbage collector are kept for reuse (cudaHostAlloc of GB-sized
+# blocks costs hundreds of ms); CX_PINNED_POOL_MB bounds what is kept (default 8192).
+_PINNED_FREE = []
+_PINNED_KEEP = {}
+
+
+def _pinned_release(key):
+    blk = _PINNED_KEEP.pop(key, None)
+    if blk is None:
+        return
+    cap = int(os.environ.get("CX_PINNED_POOL_MB", "8192")) << 20
+    if sum(b.nbytes for b in _PINNED_FREE) + blk.nbytes <= cap:
+        _PINNED_FREE.append(blk)
+
+
+def _pinned_take(nbytes):
+    best = None
+    for i, b in enumerate(_PINNED_FREE):
+        if b.nbytes >= nbytes and b.nbytes <= 2 * nbytes + (1 << 20) and (best is None or b.nbytes < _PINNED_FREE[best].nbytes):
+            best = i
+    if best is not None:
+        return _PINNED_FREE.pop(best)
+    return _PinnedBlock(nbytes)
+
+
 def pinned_empty(n, dtype=np.float64):
-    """numpy array backed by page-locked host memory (cudaHostAlloc); the
-    memory is released when the array (and its views) are collected."""
+    """numpy array backed by page-locked host memory (cudaHostAlloc); when the array
+    (and its views) are collected the block goes back to a reuse pool."""
     dtype = np.dtype(dtype)
-    blk = _PinnedBlock(max(1, int(n)) * dtype.itemsize)
-    buf = (ctypes.c_byte * blk.nbytes).from_address(blk.ptr)
+    nbytes = max(1, int(n)) * dtype.itemsize
+    blk = _pinned_take(nbytes)
+    buf = (ctypes.c_byte * nbytes).from_address(blk.ptr)
     a = np.frombuffer(buf, dtype=dtype, count=int(n))
     _PINNED_KEEP[id(buf)] = blk
-    weakref.finalize(buf, _PINNED_KEEP.pop, id(buf), None)
+    weakref.finalize(buf, _pinned_release, id(buf))
     return a
-
-
-_PINNED_KEEP = {}
 
 
 def pinned_copy(a):

@@ -2,6 +2,7 @@
 #include "cx_internal.h"
 #include "../../include/cassiopee_b200.h"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <thread>
@@ -16,6 +17,18 @@ void cx_set_error(const char* fmt, ...)
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+size_t cx_async_max_bytes()
+{
+  static size_t v = 0;
+  if (!v)
+  {
+    const char* e = getenv("CX_ASYNC_MAX_MB");
+    v = (size_t)(e ? atoll(e) : 256) << 20;
+    if (!v) v = 1;
+  }
+  return v;
 }
 
 // from other translation units

@@ -89,8 +89,14 @@ int cx_build_adt(cx_zone* z);
 
 // stream-ordered allocation (pool keeps freed blocks: release threshold = max, set at ctx creation);
 // pointers obtained here may also be released with plain cudaFree
+// Large blocks (> CX_ASYNC_MAX_MB, default 256 MB) go through plain cudaMalloc: first-touch growth of the
+// stream-ordered pool is slow for multi-GB blocks; both kinds may be released with cudaFreeAsync/cudaFree.
+size_t cx_async_max_bytes();
 static inline cudaError_t cx_malloc_async(void** p, size_t bytes, cudaStream_t s)
-{ return cudaMallocAsync(p, bytes ? bytes : 8, s); }
+{
+  if (bytes > cx_async_max_bytes()) return cudaMalloc(p, bytes);
+  return cudaMallocAsync(p, bytes ? bytes : 8, s);
+}
 #define CX_MALLOC(ptr, bytes, stream) CX_CUDA(cx_malloc_async((void**)&(ptr), (bytes), (stream)))
 
 static inline int cx_grid(long long n, int block) { return (int)((n + block - 1) / block); }
