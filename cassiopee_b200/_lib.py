@@ -10,7 +10,7 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(_HERE, "csrc", "libcassiopee_b200.so")
+LIBPATH = os.environ.get("CX_LIBPATH") or os.path.join(_HERE, "csrc", "libcassiopee_b200.so")
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int

@@ -25,7 +25,7 @@ size_t cx_async_max_bytes()
   if (!v)
   {
     const char* e = getenv("CX_ASYNC_MAX_MB");
-    v = (size_t)(e ? atoll(e) : 256) << 20;
+    v = (size_t)(e ? atoll(e) : (1 << 20)) << 20;
     if (!v) v = 1;
   }
   return v;

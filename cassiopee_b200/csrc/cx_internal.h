@@ -89,7 +89,7 @@ int cx_build_adt(cx_zone* z);
 
 // stream-ordered allocation (pool keeps freed blocks: release threshold = max, set at ctx creation);
 // pointers obtained here may also be released with plain cudaFree
-// Large blocks (> CX_ASYNC_MAX_MB, default 256 MB) go through plain cudaMalloc: first-touch growth of the
+// Large blocks (> CX_ASYNC_MAX_MB; default: never) go through plain cudaMalloc: first-touch growth of the
 // stream-ordered pool is slow for multi-GB blocks; both kinds may be released with cudaFreeAsync/cudaFree.
 size_t cx_async_max_bytes();
 static inline cudaError_t cx_malloc_async(void** p, size_t bytes, cudaStream_t s)

@@ -34,8 +34,11 @@ __device__ __forceinline__ void warp_add_stats(unsigned long long* g, const Sear
   if ((threadIdx.x & 31) == 0) { atomicAdd(&g[0], a); atomicAdd(&g[1], b); atomicAdd(&g[2], c); }
 }
 
+#ifndef CX_SEARCH_MINB
+#define CX_SEARCH_MINB 8
+#endif
 // Order-2 interpolation, all donor zones fused in one launch.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, CX_SEARCH_MINB)
 k_interp_o2(int n, const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr,
             int nz, const ZoneView* __restrict__ zones, int nature, int penalty, RcvTable T,
             unsigned long long* gstats)
