@@ -146,6 +146,91 @@ def _createInterpRegion__(z, zname, pointlist, pointlistdonor, interpCoef, inter
 
 
 # ---------------------------------------------------------------------------
+# 0. callers either side of the path, host side
+# ---------------------------------------------------------------------------
+def _applyBCOverlapsStruct__(cellN, minIndex, maxIndex, depth, loc, val=2):
+    """connector.applyBCOverlapStruct (Connector/Connector/applyBCOverlaps.cpp:27-125) on a
+    Fortran-ordered (im,jm,km) cellN array, in place: the `depth` layers next to the window get
+    `val` unless they are blanked (cellN == 0).  Indices 1-based like the reference."""
+    if loc == 'nodes': shift = 1
+    elif loc == 'centers': shift = 0
+    else: raise ValueError("applyBCOverlapsStruct: invalid location.")
+    im, jm, km = cellN.shape
+    (imin, jmin, kmin), (imax, jmax, kmax) = minIndex, maxIndex
+    lim = (im, jm, km) if loc == 'nodes' else (im + 1, jm + 1, km + 1)
+    if imin < 1 or imax > lim[0] or jmin < 1 or jmax > lim[1] or kmin < 1 or kmax > lim[2]:
+        raise TypeError("applyBCOverlaps: indices of structured window are not valid.")
+
+    def rng(a, b, n):
+        if a == b:
+            if a == 1: return 1, min(depth, n)
+            return max(a - depth + shift, 1), b - 1 + shift
+        return a, b - 1 + shift
+    imin, imax = rng(imin, imax, im); jmin, jmax = rng(jmin, jmax, jm); kmin, kmax = rng(kmin, kmax, km)
+    sub = cellN[imin - 1:imax, jmin - 1:jmax, kmin - 1:kmax]
+    sub[sub != 0.] = float(val)
+    return None
+
+
+def _applyBCOverlaps(t, depth=2, loc='centers', val=2, cellNName='cellN'):
+    """Connector.PyTree._applyBCOverlaps for structured zones (Connector/PyTree.py:1548-1600, :1674-1720):
+    cellN (created =1 if absent) is set to `val` in the `depth` layers next to every non doubly-defined
+    BCOverlap window (GridConnectivity_t of type 'Overset' with a PointRange)."""
+    var = cellNName if loc == 'nodes' else 'centers:' + cellNName
+    for z in Internal.getZones(t):
+        if C.isNamePresent(z, var) == -1:
+            C._initVars(z, var, 1.)
+        cellN = C.getFieldArray(z, var)
+        for o in Internal.getNodesFromType2(z, 'GridConnectivity_t'):
+            n = Internal.getNodeFromType1(o, 'GridConnectivityType_t')
+            if n is None or Internal.getValue(n) != 'Overset':
+                continue
+            ud = Internal.getNodeFromName1(o, 'UserDefinedData')
+            if ud is not None and Internal.getNodeFromName1(ud, 'doubly_defined') is not None:
+                continue
+            r = Internal.getNodeFromType1(o, 'IndexRange_t')
+            if r is None:
+                print("Warning: applyBCOverlaps: BCOverlap is ill-defined.")
+                continue
+            w = r[1]
+            _applyBCOverlapsStruct__(cellN, (int(w[0, 0]), int(w[1, 0]), int(w[2, 0])),
+                                     (int(w[0, 1]), int(w[1, 1]), int(w[2, 1])), depth, loc, val=val)
+    return None
+
+
+def applyBCOverlaps(t, depth=2, loc='centers', val=2, cellNName='cellN'):
+    a = Internal.copyRef(t)
+    for z in Internal.getZones(a):      # the cellN array is modified in place: give the copy its own
+        var = cellNName if loc == 'nodes' else 'centers:' + cellNName
+        c = C.getFieldArray(z, var)
+        if c is not None:
+            C._initVars(z, var, numpy.array(c, order='F', copy=True))
+    _applyBCOverlaps(a, depth=depth, loc=loc, val=val, cellNName=cellNName)
+    return a
+
+
+def getIntersectingDomains(t, t2=None, method='AABB', taabb=None, tobb=None, taabb2=None, tobb2=None, tol=1e-10):
+    """Dictionary zoneName -> names of the zones (of t2, or of t) whose axis-aligned bounding box
+    intersects it (OversetData.py:115-215, method 'AABB'; compBoundingBoxIntersection compGeom.cpp:1055-1070)."""
+    if method != 'AABB':
+        raise NotImplementedError("getIntersectingDomains: only method='AABB' is available.")
+    def boxes(tt):
+        out = []
+        for z in Internal.getZones(tt):
+            x, y, zz = C.getCoords(z)
+            out.append((z[0], (x.min(), y.min(), zz.min(), x.max(), y.max(), zz.max())))
+        return out
+    b1 = boxes(t)
+    b2 = boxes(t2) if t2 else b1
+    res = {}
+    for n1, a in b1:
+        res[n1] = [n2 for n2, b in b2 if n2 != n1 and not (
+            a[0] > b[3] + tol or a[3] < b[0] - tol or a[1] > b[4] + tol or a[4] < b[1] - tol or
+            a[2] > b[5] + tol or a[5] < b[2] - tol)]
+    return res
+
+
+# ---------------------------------------------------------------------------
 # 1. setInterpData
 # ---------------------------------------------------------------------------
 def setInterpData(tR, tD, order=2, penalty=1, nature=0, extrap=1,

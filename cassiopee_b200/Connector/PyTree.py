@@ -3,8 +3,10 @@
 same names from OversetData.py)."""
 from .OversetData import (setInterpData, _setInterpData, _setInterpDataChimera, setInterpTransfers,
                           _setInterpTransfers, setInterpTransfersD, _setInterpTransfersD,
-                          _createInterpRegion__, _addCellN__)
+                          _createInterpRegion__, _addCellN__, applyBCOverlaps, _applyBCOverlaps,
+                          getIntersectingDomains)
 from .Connector import setInterpData__, getInterpolatedPoints__, createHooks__
 
 __all__ = ['setInterpData', '_setInterpData', 'setInterpTransfers', '_setInterpTransfers',
-           'setInterpTransfersD', '_setInterpTransfersD']
+           'setInterpTransfersD', '_setInterpTransfersD', 'applyBCOverlaps', '_applyBCOverlaps',
+           'getIntersectingDomains']

@@ -220,3 +220,26 @@ def node2Center(t):
             c = Internal.createChild(z, Internal.__FlowSolutionNodes__, 'FlowSolution_t')
             c[2].extend(newfields)
     return tp
+
+
+def _addBC2Zone(z, bndName, bndType, wrange):
+    """C._addBC2Zone for structured zones, windows given as [imin,imax,jmin,jmax,kmin,kmax] (1-based).
+    'BCOverlap' -> ZoneGridConnectivity/GridConnectivity_t with GridConnectivityType 'Overset' and a
+    PointRange (what Connector.applyBCOverlaps looks for, Connector/PyTree.py:1609-1633);
+    anything else -> ZoneBC/BC_t with a PointRange."""
+    r = numpy.zeros((3, 2), dtype=Internal.E_NpyInt, order='F')
+    r[0, :] = wrange[0:2]; r[1, :] = wrange[2:4]; r[2, :] = wrange[4:6]
+    if bndType == 'BCOverlap':
+        zgc = Internal.getNodeFromName1(z, 'ZoneGridConnectivity')
+        if zgc is None:
+            zgc = Internal.createChild(z, 'ZoneGridConnectivity', 'ZoneGridConnectivity_t')
+        gc = Internal.createChild(zgc, bndName, 'GridConnectivity_t', value=z[0])
+        gc[2].append(['PointRange', r, [], 'IndexRange_t'])
+        Internal.createChild(gc, 'GridConnectivityType', 'GridConnectivityType_t', value='Overset')
+    else:
+        zbc = Internal.getNodeFromName1(z, 'ZoneBC')
+        if zbc is None:
+            zbc = Internal.createChild(z, 'ZoneBC', 'ZoneBC_t')
+        bc = Internal.createChild(zbc, bndName, 'BC_t', value=bndType)
+        bc[2].append(['PointRange', r, [], 'IndexRange_t'])
+    return None

@@ -137,3 +137,33 @@ def test_distributor2_proc_nodes():
     D2._distribute(t, 2, algorithm='rcb')
     d = D2.getProcDict(t)
     assert [d['z%d' % i] for i in range(6)] == [0, 0, 0, 1, 1, 1]
+
+
+def test_apply_bc_overlaps_and_intersecting_domains():
+    """applyBCOverlaps marks the `depth` cell layers next to BCOverlap windows (the receptors of a
+    chimera assembly); getIntersectingDomains gives the bbox-intersecting donor lists."""
+    import cassiopee_b200.Connector.PyTree as XP
+    a = G.cart((0, 0, 0), (0.1, 0.1, 0.1), (11, 11, 11), name='A')
+    b = G.cart((0.75, 0.2, 0.2), (0.1, 0.1, 0.1), (8, 7, 6), name='B')
+    c = G.cart((5, 5, 5), (0.1, 0.1, 0.1), (4, 4, 4), name='C')
+    t = C.newPyTree(['Base', a, b, c])
+    zA, zB, zC = Internal.getZones(t)
+    C._addBC2Zone(zA, 'ov1', 'BCOverlap', [11, 11, 1, 11, 1, 11])     # imax face of A
+    C._addBC2Zone(zB, 'ov1', 'BCOverlap', [1, 1, 1, 7, 1, 6])         # imin face of B
+    C._addBC2Zone(zB, 'wall', 'BCWall', [1, 8, 1, 1, 1, 6])
+    t2 = XP.applyBCOverlaps(t, depth=2, loc='centers')
+    cA = C.getFieldArray(Internal.getZones(t2)[0], 'centers:cellN')
+    cB = C.getFieldArray(Internal.getZones(t2)[1], 'centers:cellN')
+    assert cA.shape == (10, 10, 10) and (cA[8:, :, :] == 2).all() and (cA[:8, :, :] == 1).all()
+    assert (cB[:2, :, :] == 2).all() and (cB[2:, :, :] == 1).all()
+    assert C.getFieldArray(zA, 'centers:cellN') is None               # the input tree is untouched
+    t3 = XP.applyBCOverlaps(t, depth=1, loc='nodes')
+    nA = C.getFieldArray(Internal.getZones(t3)[0], 'cellN')
+    assert (nA[10, :, :] == 2).all() and (nA[:10, :, :] == 1).all()
+    d = XP.getIntersectingDomains(t)
+    assert d == {'A': ['B'], 'B': ['A'], 'C': []}
+    # blanked cells stay blanked
+    C._initVars(zA, 'centers:cellN', 1.)
+    C.getFieldArray(zA, 'centers:cellN')[9, 0, 0] = 0.
+    XP._applyBCOverlaps(zA, depth=2, loc='centers')
+    assert C.getFieldArray(zA, 'centers:cellN')[9, 0, 0] == 0. and C.getFieldArray(zA, 'centers:cellN')[9, 1, 0] == 2.
