@@ -408,6 +408,8 @@ struct cx_plan_full {
   double* d_dense; size_t dense_cap;
   double* h_dense; size_t hdense_cap;   // pinned
   std::vector<int> h_rcv;               // original-order receptor indices (host scatter)
+  bool rcv_contiguous;                  // h_rcv[e] == h_rcv[0] + e
+  std::vector<cudaEvent_t> evk, evd;    // per-variable kernel-done / download-done events (host-pointer pipeline)
 };
 
 int cx_plan_create(cx_ctx* c, int imd, int jmd, int kmd, long long nptsR, int n, const int* donor, const int* rcv,
@@ -419,6 +421,8 @@ int cx_plan_create(cx_ctx* c, int imd, int jmd, int kmd, long long nptsR, int n,
   int rc = cx_plan_build(c, imd, jmd, (long long)imd * jmd * kmd, nptsR, n, donor, rcv, type, coefs, ncoefs, &F->P);
   if (rc != 0) { cx_plan_destroy(&F->P); return rc; }
   F->h_rcv.assign(rcv, rcv + n);
+  F->rcv_contiguous = n > 0;
+  for (int e = 1; e < n && F->rcv_contiguous; e++) if (rcv[e] != rcv[0] + e) F->rcv_contiguous = false;
   *out = &F->P;
   return 0;
 }
@@ -433,16 +437,44 @@ static int ensure(double** p, size_t* cap, size_t need, bool pinned)
   return 0;
 }
 
-static int upload_fields(cx_plan_full* F, int nvars, const double* const* fieldD, std::vector<const double*>& dptrs)
+// Host-pointer transfers are PCIe-bound (8*nvars*(nptsD + n) bytes cross the bus for ~0.5 ms of kernel), so they
+// run as a per-variable pipeline over two streams: variable v's upload + kernel on the main stream, its download
+// on the copy stream as soon as the kernel's event fires.  Uploads and downloads then overlap (the bus is full
+// duplex) and the total tends to max(H2D, D2H) instead of their sum.  The per-variable launches re-read the
+// plan's coefficients nvars times from HBM, which costs ~0.25 ms per variable at C2a size against ~2.5 ms of bus
+// time per variable.
+static int pipeline_events(cx_plan_full* F, int nvars)
+{
+  while ((int)F->evk.size() < nvars)
+  {
+    cudaEvent_t a, b;
+    CX_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    CX_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    F->evk.push_back(a); F->evd.push_back(b);
+  }
+  return 0;
+}
+
+// dst[v]: host destination of variable v's dense (n) block
+static int transfer_pipeline(cx_plan_full* F, int nvars, const double* const* fieldD, double* const* dst)
 {
   cx_plan* P = &F->P; cx_ctx* c = P->ctx;
-  size_t per = (size_t)P->nptsD;
+  CX_CUDA(cudaSetDevice(c->device));
+  const size_t per = (size_t)P->nptsD, n = (size_t)P->n;
   CX_CHECK(ensure(&F->d_fields, &F->fields_cap, sizeof(double) * per * nvars, false));
-  dptrs.resize(nvars);
+  CX_CHECK(ensure(&F->d_dense, &F->dense_cap, sizeof(double) * n * nvars, false));
+  CX_CHECK(pipeline_events(F, nvars));
+  cudaStream_t sa = c->stream, sb = c->comm_stream;
   for (int v = 0; v < nvars; v++)
   {
-    CX_CUDA(cudaMemcpyAsync(F->d_fields + per * v, fieldD[v], sizeof(double) * per, cudaMemcpyHostToDevice, c->stream));
-    dptrs[v] = F->d_fields + per * v;
+    double* dv = F->d_fields + per * v;
+    const double* dvp = dv;
+    CX_CUDA(cudaMemcpyAsync(dv, fieldD[v], sizeof(double) * per, cudaMemcpyHostToDevice, sa));
+    CX_CHECK(cx_plan_launch(P, 1, &dvp, nullptr, F->d_dense + n * v, (long long)n, 1, sa));
+    CX_CUDA(cudaEventRecord(F->evk[v], sa));
+    CX_CUDA(cudaStreamWaitEvent(sb, F->evk[v], 0));
+    CX_CUDA(cudaMemcpyAsync(dst[v], F->d_dense + n * v, sizeof(double) * n, cudaMemcpyDeviceToHost, sb));
+    CX_CUDA(cudaEventRecord(F->evd[v], sb));
   }
   return 0;
 }
@@ -451,13 +483,10 @@ int cx_transferD(cx_plan* P, int nvars, const double* const* fieldD, double* out
 {
   cx_plan_full* F = (cx_plan_full*)P; cx_ctx* c = P->ctx;
   if (P->n == 0 || nvars == 0) return 0;
-  CX_CUDA(cudaSetDevice(c->device));
-  std::vector<const double*> dptrs;
-  CX_CHECK(upload_fields(F, nvars, fieldD, dptrs));
-  size_t nd = (size_t)P->n * nvars;
-  CX_CHECK(ensure(&F->d_dense, &F->dense_cap, sizeof(double) * nd, false));
-  CX_CHECK(cx_plan_launch(P, nvars, dptrs.data(), nullptr, F->d_dense, P->n, 1, c->stream));
-  CX_CUDA(cudaMemcpyAsync(out, F->d_dense, sizeof(double) * nd, cudaMemcpyDeviceToHost, c->stream));
+  std::vector<double*> dst(nvars);
+  for (int v = 0; v < nvars; v++) dst[v] = out + (size_t)P->n * v;
+  CX_CHECK(transfer_pipeline(F, nvars, fieldD, dst.data()));
+  CX_CUDA(cudaStreamSynchronize(c->comm_stream));
   CX_CUDA(cudaStreamSynchronize(c->stream));
   CX_CUDA(cudaGetLastError());
   return 0;
@@ -465,33 +494,50 @@ int cx_transferD(cx_plan* P, int nvars, const double* const* fieldD, double* out
 
 int cx_transfer(cx_plan* P, int nvars, const double* const* fieldD, double* const* fieldR)
 {
-  cx_plan_full* F = (cx_plan_full*)P;
+  cx_plan_full* F = (cx_plan_full*)P; cx_ctx* c = P->ctx;
   if (P->n == 0 || nvars == 0) return 0;
-  size_t nd = (size_t)P->n * nvars;
-  CX_CHECK(ensure(&F->h_dense, &F->hdense_cap, sizeof(double) * nd, true));
-  CX_CHECK(cx_transferD(P, nvars, fieldD, F->h_dense));
-  // host scatter; receptors of one plan are distinct, so entry ranges can go to different threads
   const int n = P->n;
+  std::vector<double*> dst(nvars);
+  if (F->rcv_contiguous)
+  {
+    // receptor indices are one ascending run (every point of the zone, or one slab): the dense block of a
+    // variable IS the receptor field's slice, so it is downloaded in place without a host scatter
+    for (int v = 0; v < nvars; v++) dst[v] = fieldR[v] + F->h_rcv[0];
+    CX_CHECK(transfer_pipeline(F, nvars, fieldD, dst.data()));
+    CX_CUDA(cudaStreamSynchronize(c->comm_stream));
+    CX_CUDA(cudaStreamSynchronize(c->stream));
+    CX_CUDA(cudaGetLastError());
+    return 0;
+  }
+  CX_CHECK(ensure(&F->h_dense, &F->hdense_cap, sizeof(double) * (size_t)n * nvars, true));
+  for (int v = 0; v < nvars; v++) dst[v] = F->h_dense + (size_t)n * v;
+  CX_CHECK(transfer_pipeline(F, nvars, fieldD, dst.data()));
+  // host scatter of variable v while the later variables are still on the bus; receptors of one plan are
+  // distinct, so entry ranges can go to different threads
   const int* rcv = F->h_rcv.data();
   unsigned hw = std::thread::hardware_concurrency();
   int nt = (int)std::min<unsigned>(hw ? hw : 1, 16);
-  if ((long long)n * nvars < (1 << 20)) nt = 1;
-  auto work = [&](int t) {
-    int e0 = (int)((long long)n * t / nt), e1 = (int)((long long)n * (t + 1) / nt);
-    for (int v = 0; v < nvars; v++)
-    {
-      double* fr = fieldR[v];
-      const double* src = F->h_dense + (size_t)v * n;
-      for (int e = e0; e < e1; e++) fr[rcv[e]] = src[e];
-    }
-  };
-  if (nt == 1) work(0);
-  else
+  if (n < (1 << 18)) nt = 1;
+  for (int v = 0; v < nvars; v++)
   {
-    std::vector<std::thread> th;
-    for (int t = 0; t < nt; t++) th.emplace_back(work, t);
-    for (auto& x : th) x.join();
+    CX_CUDA(cudaEventSynchronize(F->evd[v]));
+    double* fr = fieldR[v];
+    const double* src = F->h_dense + (size_t)v * n;
+    auto work = [&](int t) {
+      int e0 = (int)((long long)n * t / nt), e1 = (int)((long long)n * (t + 1) / nt);
+      for (int e = e0; e < e1; e++) fr[rcv[e]] = src[e];
+    };
+    if (nt == 1) work(0);
+    else
+    {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nt; t++) th.emplace_back(work, t);
+      for (auto& x : th) x.join();
+    }
   }
+  CX_CUDA(cudaStreamSynchronize(c->comm_stream));
+  CX_CUDA(cudaStreamSynchronize(c->stream));
+  CX_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -608,11 +654,13 @@ int cx_plan_destroy(cx_plan* P)
 {
   if (!P) return 0;
   cx_plan_full* F = (cx_plan_full*)P;
-  for (auto& G : P->groups) cudaFree(G.d_cf);
+  for (auto& G : P->groups) { cudaFree(G.d_cf); if (G.d_tiles) cudaFree(G.d_tiles); }
   cudaFree(P->d_donor); cudaFree(P->d_rcv); cudaFree(P->d_pos);
   if (F->d_fields) cudaFree(F->d_fields);
   if (F->d_dense) cudaFree(F->d_dense);
   if (F->h_dense) cudaFreeHost(F->h_dense);
+  for (cudaEvent_t e : F->evk) cudaEventDestroy(e);
+  for (cudaEvent_t e : F->evd) cudaEventDestroy(e);
   delete F;
   return 0;
 }

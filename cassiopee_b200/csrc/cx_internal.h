@@ -72,7 +72,8 @@ struct cx_plan {
   int n;                // entries
   int ngroups;          // type groups
   // entries regrouped by type (stable), SoA coefficients per group
-  struct Group { int type, ncf, sten, n, first; double* d_cf; };
+  // layout 0: list order, 1: sorted by donor index, 2: tiled by donor box (type 2 only; d_tiles = ntiles+1 TileRef)
+  struct Group { int type, ncf, sten, n, first; double* d_cf; int layout; void* d_tiles; int ntiles, ntx, nty; };
   std::vector<Group> groups;
   int* d_donor; int* d_rcv; int* d_pos;   // regrouped order; pos = original entry position
   long long alg_bytes_fixed;              // sum over entries of (8*ncf + 12)

@@ -22,6 +22,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <vector>
+#include <cub/device/device_radix_sort.cuh>
 
 #define CX_MAXVARS 16
 
@@ -95,6 +96,212 @@ __device__ __forceinline__ void transfer_entry(int e, int m, int nvars, const PD
   }
 }
 
+// ---- shared-memory staging of a tile's donor rows (type 2) -----------------------------------
+// The plan's entries are sorted by donor index, so the 256 entries of a CTA read four short contiguous
+// row segments of each donor field: rows (j,k), (j+1,k), (j,k+1), (j+1,k+1), nodes [d_lo, d_hi+1].  Instead of
+// 8 dependent 8-byte gathers per entry and variable, one elected thread asks the TMA unit for the four
+// segments (cp.async.bulk global->shared, completion on an mbarrier), two variables in flight per CTA, and
+// the entries then read their 8 stencil values from shared memory.  Every byte of the segment is fetched
+// once per CTA, coalesced, with no register or scoreboard cost while it is in flight.  Tiles whose donors
+// span more than CX_SPAN nodes (row wraps at the edge of the overlap region, sparse fringes) take the
+// direct-gather path.  Arithmetic (operand order, no FMA) is the same on both paths.
+#define CX_SPAN 384
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_fence_init()
+{ asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "CX_WAIT:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra CX_DONE;\n"
+               "bra CX_WAIT;\n"
+               "CX_DONE:\n"
+               "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+struct StageSmem {
+  double buf[2][4][CX_SPAN + 4];
+  unsigned long long bar[2];
+};
+
+// One tile (<= blockDim.x entries starting at t0, all of one plan/type-2 group) of the CTA.
+// Returns false (for the whole CTA) if the tile cannot be staged; the caller then gathers directly.
+template <int MODE, class PD, class PR>
+__device__ __forceinline__ bool transfer_tile2_staged(StageSmem& S, int t0, int m, int nvars, const PD& pd, const PR& pr,
+                                                      int imd, int imdjmd, int nptsD, const int* __restrict__ donor,
+                                                      const int* __restrict__ idx, const double* __restrict__ cfT,
+                                                      double* __restrict__ dense, long long ld)
+{
+  const int tid = threadIdx.x;
+  const int e = t0 + tid;
+  const int last = min(t0 + (int)blockDim.x, m) - 1;
+  const int d_lo = donor[t0], d_hi = donor[last];        // sorted ascending inside a group
+  const int off1 = imd, off2 = imdjmd, off3 = imdjmd + imd;
+  // 16-byte aligned segment starts (element index even) and lengths (even), per row
+  const int s0 = d_lo & 1, s1 = (d_lo + off1) & 1, s2 = (d_lo + off2) & 1, s3 = (d_lo + off3) & 1;
+  const int span = d_hi - d_lo + 2;                      // nodes d_lo .. d_hi+1
+  const int len0 = (span + s0 + 1) & ~1, len1 = (span + s1 + 1) & ~1, len2 = (span + s2 + 1) & ~1, len3 = (span + s3 + 1) & ~1;
+  if (span + 2 > CX_SPAN || d_lo + off3 - s3 + len3 > nptsD || d_lo + off2 - s2 + len2 > nptsD ||
+      d_lo + off1 - s1 + len1 > nptsD || d_lo - s0 + len0 > nptsD)
+    return false;
+  if (tid == 0) { mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1); mbar_fence_init(); }
+  __syncthreads();
+  const unsigned bytes = 8u * (unsigned)(len0 + len1 + len2 + len3);
+  auto issue = [&](int v) {
+    const int st = v & 1;
+    const double* f = pd[v];
+    mbar_expect_tx(&S.bar[st], bytes);
+    bulk_g2s(&S.buf[st][0][0], f + (d_lo - s0), 8u * len0, &S.bar[st]);
+    bulk_g2s(&S.buf[st][1][0], f + (d_lo + off1 - s1), 8u * len1, &S.bar[st]);
+    bulk_g2s(&S.buf[st][2][0], f + (d_lo + off2 - s2), 8u * len2, &S.bar[st]);
+    bulk_g2s(&S.buf[st][3][0], f + (d_lo + off3 - s3), 8u * len3, &S.bar[st]);
+  };
+  if (tid == 0) issue(0);
+  int l = 0; size_t o = 0;
+  double c[8];
+  const bool act = e < m;
+  if (act)
+  {
+    l = donor[e] - d_lo; o = (size_t)idx[e];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = cfT[(size_t)k * m + e];
+  }
+  for (int v = 0; v < nvars; v++)
+  {
+    if (tid == 0 && v + 1 < nvars) issue(v + 1);         // its buffer was released by the barrier ending iteration v-1
+    mbar_wait(&S.bar[v & 1], (unsigned)((v >> 1) & 1));
+    if (act)
+    {
+      const double(*b)[CX_SPAN + 4] = S.buf[v & 1];
+      double val = 0.;
+      val += c[0] * b[0][l + s0];
+      val += c[1] * b[0][l + s0 + 1];
+      val += c[2] * b[1][l + s1];
+      val += c[3] * b[1][l + s1 + 1];
+      val += c[4] * b[2][l + s2];
+      val += c[5] * b[2][l + s2 + 1];
+      val += c[6] * b[3][l + s3];
+      val += c[7] * b[3][l + s3 + 1];
+      if (MODE == 0) pr[v][o] = val; else dense[(size_t)v * ld + o] = val;
+    }
+    __syncthreads();
+  }
+  return true;
+}
+
+// ---- tiled layout (dense overlaps): entries grouped by donor-cell box, receptor order inside ---------
+// When many receptors fall in each donor cell neighbourhood (volume overlaps such as a near-body grid inside
+// a background), the donor-sorted layout above coalesces the stencil reads but scatters every 8-byte
+// receptor store into its own 32-byte sector: ncu shows the L2 tag pipeline (lts__t_tag_requests) as the
+// busiest unit, fed mostly by those partial-sector stores.  The tiled layout keeps BOTH sides local: the
+// plan's type-2 entries are grouped by the CX_TX x CX_TY box of donor cells (one k plane) they fall in and
+// keep their ascending receptor order inside a box.  A CTA owns one box: the box's (CX_TX+1) x (CX_TY+1) x 2
+// donor nodes of every variable arrive in shared memory through cp.async.bulk row segments (one mbarrier),
+// the entries then read their stencils from shared memory, and a warp's 32 consecutive receptors are stored
+// as full sectors.  Arithmetic is unchanged (same operand order, no FMA).
+#define CX_TX 32
+#define CX_TY 8
+#define CX_ROWP 36                                   // row pitch in shared memory (doubles), >= CX_TX + 1 + 2
+#define CX_BOXV (2 * (CX_TY + 1) * CX_ROWP)          // doubles per variable
+struct TileRef { int tile, start; };                 // box id, first entry; entry count = next.start - start
+
+template <int MODE, class PD, class PR>
+__device__ __forceinline__ void transfer_box2(double* __restrict__ sm, unsigned long long* bar, int tile, int start,
+                                              int count, int m, int nvars, const PD& pd, const PR& pr, int imd, int jmd,
+                                              int imdjmd, int nptsD, int ntx, int nty, const int* __restrict__ donor,
+                                              const int* __restrict__ idx, const double* __restrict__ cfT,
+                                              double* __restrict__ dense, long long ld)
+{
+  const int tid = threadIdx.x;
+  const int tx = tile % ntx, ty = (tile / ntx) % nty, k = tile / (ntx * nty);
+  const int i0 = tx * CX_TX, j0 = ty * CX_TY;
+  const int ilen = min(CX_TX + 1, imd - i0), jlen = min(CX_TY + 1, jmd - j0);
+  const int base = i0 + j0 * imd + k * imdjmd;
+  if (base + (jlen - 1) * imd + imdjmd + ilen + 2 > nptsD)
+  {
+    // the 16-byte rounding of the last row segment could run past the end of the field: gather directly
+    for (int c = tid; c < count; c += blockDim.x)
+      transfer_entry<2, MODE>(start + c, m, nvars, pd, pr, imd, imdjmd, donor, idx, cfT, dense, ld);
+    return;
+  }
+  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  __syncthreads();
+  if (tid < 32)
+  {
+    const int nseg = 2 * jlen;
+    int tot = 0;
+    for (int sg = tid; sg < nseg; sg += 32)
+    {
+      const int g = base + (sg % jlen) * imd + (sg / jlen) * imdjmd;
+      tot += (ilen + (g & 1) + 1) & ~1;
+    }
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (tid == 0) mbar_expect_tx(bar, 8u * (unsigned)tot * (unsigned)nvars);
+    __syncwarp();
+    for (int sg = tid; sg < nseg; sg += 32)
+    {
+      const int r = sg % jlen, p = sg / jlen;
+      const int g = base + r * imd + p * imdjmd;
+      const int len = (ilen + (g & 1) + 1) & ~1;
+      for (int v = 0; v < nvars; v++)
+        bulk_g2s(sm + (size_t)v * CX_BOXV + (p * (CX_TY + 1) + r) * CX_ROWP, pd[v] + (g & ~1), 8u * len, bar);
+    }
+  }
+  int c = tid;
+  int d0 = 0; size_t o = 0; double cf[8];
+  if (c < count)
+  {
+    const int e = start + c;
+    d0 = donor[e]; o = (size_t)idx[e];
+#pragma unroll
+    for (int q = 0; q < 8; q++) cf[q] = cfT[(size_t)q * m + e];
+  }
+  mbar_wait(bar, 0u);
+  while (c < count)
+  {
+    const int rel = d0 - base;
+    const int rj = rel / imd, ri = rel - rj * imd;
+    const int g00 = base + rj * imd;
+    const int s00 = g00 & 1, s01 = (g00 + imd) & 1, s10 = (g00 + imdjmd) & 1, s11 = (g00 + imdjmd + imd) & 1;
+    const double* b0 = sm + rj * CX_ROWP + ri;
+    for (int v = 0; v < nvars; v++)
+    {
+      const double* b = b0 + (size_t)v * CX_BOXV;
+      const double* b1 = b + (CX_TY + 1) * CX_ROWP;
+      double val = 0.;
+      val += cf[0] * b[s00];
+      val += cf[1] * b[s00 + 1];
+      val += cf[2] * b[CX_ROWP + s01];
+      val += cf[3] * b[CX_ROWP + s01 + 1];
+      val += cf[4] * b1[s10];
+      val += cf[5] * b1[s10 + 1];
+      val += cf[6] * b1[CX_ROWP + s11];
+      val += cf[7] * b1[CX_ROWP + s11 + 1];
+      if (MODE == 0) pr[v][o] = val; else dense[(size_t)v * ld + o] = val;
+    }
+    c += blockDim.x;
+    if (c < count)
+    {
+      const int e = start + c;
+      d0 = donor[e]; o = (size_t)idx[e];
+#pragma unroll
+      for (int q = 0; q < 8; q++) cf[q] = cfT[(size_t)q * m + e];
+    }
+  }
+}
+
 struct PDk { const double* const* p; __device__ __forceinline__ const double* operator[](int v) const { return p[v]; } };
 struct PRk { double* const* p; __device__ __forceinline__ double* operator[](int v) const { return p[v]; } };
 
@@ -110,24 +317,92 @@ k_transfer(int m, int nvars, FieldPtrs P, int imd, int imdjmd, const int* __rest
   transfer_entry<TYPE, MODE>(e, m, nvars, pd, pr, imd, imdjmd, donor, MODE == 0 ? rcv : pos, cfT, dense, ld);
 }
 
+// type 2 with shared-memory staging (falls back to the direct gather tile by tile)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_transfer2s(int m, int nvars, FieldPtrs P, int imd, int imdjmd, int nptsD, const int* __restrict__ donor,
+             const int* __restrict__ rcv, const int* __restrict__ pos, const double* __restrict__ cfT,
+             double* __restrict__ dense, long long ld)
+{
+  extern __shared__ __align__(16) double dyn_sm[];
+  StageSmem& S = *reinterpret_cast<StageSmem*>(dyn_sm);
+  PDk pd{P.d}; PRk pr{P.r};
+  const int t0 = blockIdx.x * blockDim.x;
+  if (transfer_tile2_staged<MODE>(S, t0, m, nvars, pd, pr, imd, imdjmd, nptsD, donor, MODE == 0 ? rcv : pos, cfT, dense, ld))
+    return;
+  int e = t0 + threadIdx.x;
+  if (e >= m) return;
+  transfer_entry<2, MODE>(e, m, nvars, pd, pr, imd, imdjmd, donor, MODE == 0 ? rcv : pos, cfT, dense, ld);
+}
+
+// type 2, tiled layout: one CTA per non-empty donor box
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_transfer2t(const TileRef* __restrict__ tiles, int m, int nvars, FieldPtrs P, int imd, int jmd, int nptsD, int ntx,
+             int nty, const int* __restrict__ donor, const int* __restrict__ rcv, const int* __restrict__ pos,
+             const double* __restrict__ cfT, double* __restrict__ dense, long long ld)
+{
+  extern __shared__ __align__(16) double dyn_sm[];
+  __shared__ unsigned long long bar;
+  PDk pd{P.d}; PRk pr{P.r};
+  const TileRef t = tiles[blockIdx.x];
+  const int count = tiles[blockIdx.x + 1].start - t.start;
+  transfer_box2<MODE>(dyn_sm, &bar, t.tile, t.start, count, m, nvars, pd, pr, imd, jmd, imd * jmd, nptsD, ntx, nty, donor,
+                      MODE == 0 ? rcv : pos, cfT, dense, ld);
+}
+
 // Plan set: every (plan, type group) of a rank in ONE launch.  Block b works on
 // descriptor blk2desc[b]; field pointers come from per-zone device tables.
 struct SetDesc {
-  int m, type, imd, imdjmd, mode, first_block;
+  int m, type, imd, imdjmd, mode, first_block, nptsD;
+  int layout, jmd, ntx, nty;                 // layout 2: tiled, blocks = boxes
+  const TileRef* tiles;
   const int* donor; const int* idx; const double* cfT;
   const double* const* dptr;   // device table: nvars donor field pointers
   double* const* rptr;         // device table: nvars receptor field pointers (mode 0)
   double* dense; long long ld; // mode 1
 };
 
-template <int TYPE>
+template <int TYPE, bool TILED>
 __global__ void __launch_bounds__(256)
-k_transfer_set(const SetDesc* __restrict__ descs, const int* __restrict__ blk2desc, int nvars)
+k_transfer_set(const SetDesc* __restrict__ descs, const int* __restrict__ blk2desc, int nvars, int staged)
 {
   const SetDesc D = descs[blk2desc[blockIdx.x]];
+  PDk pd{D.dptr}; PRk pr{D.rptr};
+  if (TYPE == 2)
+  {
+    extern __shared__ __align__(16) double dyn_sm[];
+    __shared__ unsigned long long bar;
+    if (TILED && D.layout == 2)
+    {
+      const int b = blockIdx.x - D.first_block;
+      const TileRef t = D.tiles[b];
+      const int count = D.tiles[b + 1].start - t.start;
+      if (staged)
+      {
+        if (D.mode == 0) transfer_box2<0>(dyn_sm, &bar, t.tile, t.start, count, D.m, nvars, pd, pr, D.imd, D.jmd, D.imdjmd, D.nptsD, D.ntx, D.nty, D.donor, D.idx, D.cfT, D.dense, D.ld);
+        else transfer_box2<1>(dyn_sm, &bar, t.tile, t.start, count, D.m, nvars, pd, pr, D.imd, D.jmd, D.imdjmd, D.nptsD, D.ntx, D.nty, D.donor, D.idx, D.cfT, D.dense, D.ld);
+      }
+      else
+        for (int c = threadIdx.x; c < count; c += blockDim.x)
+        {
+          if (D.mode == 0) transfer_entry<2, 0>(t.start + c, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
+          else transfer_entry<2, 1>(t.start + c, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
+        }
+      return;
+    }
+    if (staged && D.layout == 1)
+    {
+      StageSmem& S = *reinterpret_cast<StageSmem*>(dyn_sm);
+      const int t0 = (blockIdx.x - D.first_block) * blockDim.x;
+      bool done = (D.mode == 0)
+        ? transfer_tile2_staged<0>(S, t0, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.nptsD, D.donor, D.idx, D.cfT, D.dense, D.ld)
+        : transfer_tile2_staged<1>(S, t0, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.nptsD, D.donor, D.idx, D.cfT, D.dense, D.ld);
+      if (done) return;
+    }
+  }
   int e = (blockIdx.x - D.first_block) * blockDim.x + threadIdx.x;
   if (e >= D.m) return;
-  PDk pd{D.dptr}; PRk pr{D.rptr};
   if (D.mode == 0) transfer_entry<TYPE, 0>(e, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
   else transfer_entry<TYPE, 1>(e, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
 }
@@ -210,12 +485,105 @@ __global__ void k_plan_flag(int n, int T, const int* __restrict__ type, unsigned
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < n) f[e] = (type[e] == T) ? 1ull : 0ull;
 }
+// tiled layout: sort key = donor box of the entry (entries of other types sort last), value = entry
+__global__ void k_tile_keys(int n, int T, const int* __restrict__ type, const int* __restrict__ donor, int imd, int jmd,
+                            int ntx, int nty, unsigned nboxes, unsigned* __restrict__ key, int* __restrict__ val)
+{
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  unsigned kk = nboxes;
+  if (type[e] == T)
+  {
+    int d = donor[e];
+    int i = d % imd, j = (d / imd) % jmd, k = d / (imd * jmd);
+    kk = (unsigned)((k * nty + j / CX_TY) * ntx + i / CX_TX);
+  }
+  key[e] = kk; val[e] = e;
+}
+__global__ void k_tile_heads(int m, const unsigned* __restrict__ key, unsigned long long* __restrict__ f)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < m) f[s] = (s == 0 || key[s] != key[s - 1]) ? 1ull : 0ull;
+}
+__global__ void k_tile_table(int m, const unsigned* __restrict__ key, const unsigned long long* __restrict__ scan,
+                             TileRef* __restrict__ tiles, int ntiles)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s == 0) { tiles[ntiles].tile = -1; tiles[ntiles].start = m; }
+  if (s >= m) return;
+  if (s == 0 || key[s] != key[s - 1]) { TileRef t; t.tile = (int)key[s]; t.start = s; tiles[scan[s]] = t; }
+}
+__global__ void k_plan_place_perm(int m, int ncf, const int* __restrict__ perm, const int* __restrict__ donor,
+                                  const int* __restrict__ rcv, const unsigned long long* __restrict__ off,
+                                  const double* __restrict__ coefs, int* __restrict__ od, int* __restrict__ orc,
+                                  int* __restrict__ op, double* __restrict__ cfT)
+{
+  int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= m) return;
+  int e = perm[slot];
+  od[slot] = donor[e]; orc[slot] = rcv[e]; op[slot] = e;
+  const double* c = coefs + off[e];
+  for (int k = 0; k < ncf; k++) cfT[(size_t)k * m + slot] = c[k];
+}
 }  // namespace
 
+// CX_TRANSFER_STAGING=0 disables the shared-memory staged type-2 kernel (A/B measurements)
+int cx_transfer_staging()
+{
+  static int v = -1;
+  if (v < 0) { const char* s = getenv("CX_TRANSFER_STAGING"); v = (s && s[0] == '0') ? 0 : 1; }
+  return v;
+}
+
+// CX_PLAN_SORT: 0 = keep the entries in list order, 1 = donor-sorted layout for every group,
+// 2 = tiled layout for the type-2 groups that are dense enough (experimental), unset = 1
 static int plan_sort_mode()
 {
   const char* s = getenv("CX_PLAN_SORT");
-  return (s && s[0] == '0') ? 0 : 1;
+  if (!s || !s[0]) return -1;
+  return s[0] - '0';
+}
+
+// Try the tiled layout for the type-2 group G (m entries).  On success fills G.d_tiles/ntiles and the
+// regrouped arrays and returns 1; returns 0 if the group is too sparse (caller falls back), <0 on error.
+static int build_tiled_group(cx_ctx* ctx, cx_plan* P, cx_plan::Group& G, int n, int kmd, const int* r_ty, const int* r_dn,
+                             const int* r_rc, const unsigned long long* r_off, const double* r_cf, int first, int force)
+{
+  cudaStream_t s = ctx->stream;
+  const int TB = 256;
+  const int ntx = (std::max(P->imd - 1, 1) + CX_TX - 1) / CX_TX, nty = (std::max(P->jmd - 1, 1) + CX_TY - 1) / CX_TY;
+  const long long nboxes_ll = (long long)ntx * nty * std::max(kmd - 1, 1);
+  if (nboxes_ll >= 0x7fffffffll) return 0;
+  const unsigned nboxes = (unsigned)nboxes_ll;
+  unsigned *k_in, *k_out; int *v_in, *v_out; void* tmp = nullptr; size_t tmp_bytes = 0;
+  CX_MALLOC(k_in, sizeof(unsigned) * (size_t)n, s); CX_MALLOC(k_out, sizeof(unsigned) * (size_t)n, s);
+  CX_MALLOC(v_in, sizeof(int) * (size_t)n, s); CX_MALLOC(v_out, sizeof(int) * (size_t)n, s);
+  k_tile_keys<<<cx_grid(n, TB), TB, 0, s>>>(n, G.type, r_ty, r_dn, P->imd, P->jmd, ntx, nty, nboxes, k_in, v_in);
+  int bits = 1; while ((1ull << bits) <= (unsigned long long)nboxes) bits++;
+  // stable LSD radix sort (CUB): entries keep their list order (ascending receptors) inside a box
+  CX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, n, 0, bits, s));
+  CX_MALLOC(tmp, tmp_bytes, s);
+  CX_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, n, 0, bits, s));
+  const int m = G.n;
+  unsigned long long *f, *sc, total = 0;
+  CX_MALLOC(f, sizeof(unsigned long long) * (size_t)m, s); CX_MALLOC(sc, sizeof(unsigned long long) * (size_t)m, s);
+  k_tile_heads<<<cx_grid(m, TB), TB, 0, s>>>(m, k_out, f);
+  CX_CHECK(cx_exclusive_scan_u64(ctx, f, sc, m, &total));
+  ctx->launches += 3;
+  int ok = 0;
+  if (force || (long long)m >= 96ll * (long long)total)
+  {
+    G.ntiles = (int)total; G.ntx = ntx; G.nty = nty; G.layout = 2;
+    CX_CUDA(cudaMalloc(&G.d_tiles, sizeof(TileRef) * ((size_t)total + 1)));
+    k_tile_table<<<cx_grid(m, TB), TB, 0, s>>>(m, k_out, sc, (TileRef*)G.d_tiles, (int)total);
+    k_plan_place_perm<<<cx_grid(m, TB), TB, 0, s>>>(m, G.ncf, v_out, r_dn, r_rc, r_off, r_cf, P->d_donor + first,
+                                                   P->d_rcv + first, P->d_pos + first, G.d_cf);
+    ctx->launches += 2;
+    ok = 1;
+  }
+  cudaFreeAsync(k_in, s); cudaFreeAsync(k_out, s); cudaFreeAsync(v_in, s); cudaFreeAsync(v_out, s);
+  cudaFreeAsync(tmp, s); cudaFreeAsync(f, s); cudaFreeAsync(sc, s);
+  return ok;
 }
 
 int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long nptsR, int n, const int* donor,
@@ -247,7 +615,9 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
   CX_MALLOC(r_dn, sizeof(int) * N, s); CX_MALLOC(r_rc, sizeof(int) * N, s);
   CX_MALLOC(r_ty, sizeof(int) * N, s); CX_MALLOC(r_off, sizeof(unsigned long long) * N, s);
   CX_MALLOC(r_cf, sizeof(double) * (size_t)std::max(run, 1ll), s);
-  const int sorted = plan_sort_mode();
+  const int mode_env = plan_sort_mode();
+  const int sorted = mode_env == 0 ? 0 : 1;
+  const int kmd = (int)(nptsD / ((long long)imd * jmd));
   const size_t nscan = sorted ? (size_t)nptsD : N;
   CX_MALLOC(d_cnt, sizeof(unsigned long long) * nscan, s);
   CX_MALLOC(d_scan, sizeof(unsigned long long) * nscan, s);
@@ -266,7 +636,14 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
     if (cnt[g] == 0) continue;
     cx_plan::Group G; G.type = types[g]; G.ncf = ncf_host(types[g]); G.sten = sten_host(types[g]);
     G.n = cnt[g]; G.first = first; G.d_cf = nullptr;
+    G.layout = sorted ? 1 : 0; G.d_tiles = nullptr; G.ntiles = 0; G.ntx = G.nty = 0;
     CX_MALLOC(G.d_cf, sizeof(double) * (size_t)G.ncf * G.n, s);
+    if (G.type == 2 && mode_env >= 2 && kmd >= 2 && G.n >= 4096)
+    {
+      int rc = build_tiled_group(ctx, P, G, n, kmd, r_ty, r_dn, r_rc, r_off, r_cf, first, mode_env == 3);
+      if (rc < 0) return rc;
+      if (rc == 1) { P->groups.push_back(G); first += G.n; continue; }
+    }
     if (sorted)
     {
       CX_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * nscan, s));
@@ -291,6 +668,21 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
   return 0;
 }
 
+static int tiled_smem_optin()
+{
+  static int done = 0;
+  if (!done)
+  {
+    const int mx = (int)(sizeof(double) * CX_BOXV * CX_MAXVARS);
+    CX_CUDA(cudaFuncSetAttribute(k_transfer2t<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CX_CUDA(cudaFuncSetAttribute(k_transfer2t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CX_CUDA(cudaFuncSetAttribute(k_transfer_set<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    done = 1;
+  }
+  return 0;
+}
+
+
 // mode 0: in-place scatter into receptor fields; mode 1: dense (nvars, ld) output
 int cx_plan_launch(cx_plan* P, int nvars, const double* const* dD, double* const* dR, double* dense, long long ld,
                    int mode, cudaStream_t s)
@@ -312,10 +704,27 @@ int cx_plan_launch(cx_plan* P, int nvars, const double* const* dD, double* const
 #define CX_LAUNCH(T)                                                                                           \
       if (mode == 0) k_transfer<T, 0><<<grid, TB, 0, s>>>(G.n, nv, F, imd, ij, dn_, rc_, ps_, G.d_cf, dn, ld); \
       else k_transfer<T, 1><<<grid, TB, 0, s>>>(G.n, nv, F, imd, ij, dn_, rc_, ps_, G.d_cf, dn, ld);
+      bool staged = G.layout != 0 && cx_transfer_staging();
+      for (int v = 0; v < nv && staged; v++) if (((uintptr_t)F.d[v]) & 15) staged = false;
       switch (G.type)
       {
         case 1: CX_LAUNCH(1) break;
-        case 2: CX_LAUNCH(2) break;
+        case 2:
+          if (staged && G.layout == 2)
+          {
+            const size_t smb = sizeof(double) * CX_BOXV * (size_t)nv;
+            CX_CHECK(tiled_smem_optin());
+            const TileRef* tl = (const TileRef*)G.d_tiles;
+            if (mode == 0) k_transfer2t<0><<<G.ntiles, TB, smb, s>>>(tl, G.n, nv, F, imd, P->jmd, P->nptsD, G.ntx, G.nty, dn_, rc_, ps_, G.d_cf, dn, ld);
+            else k_transfer2t<1><<<G.ntiles, TB, smb, s>>>(tl, G.n, nv, F, imd, P->jmd, P->nptsD, G.ntx, G.nty, dn_, rc_, ps_, G.d_cf, dn, ld);
+          }
+          else if (staged && G.layout == 1)
+          {
+            if (mode == 0) k_transfer2s<0><<<grid, TB, sizeof(StageSmem), s>>>(G.n, nv, F, imd, ij, P->nptsD, dn_, rc_, ps_, G.d_cf, dn, ld);
+            else k_transfer2s<1><<<grid, TB, sizeof(StageSmem), s>>>(G.n, nv, F, imd, ij, P->nptsD, dn_, rc_, ps_, G.d_cf, dn, ld);
+          }
+          else { CX_LAUNCH(2) }
+          break;
         case 3: CX_LAUNCH(3) break;
         case 5: CX_LAUNCH(5) break;
       }
@@ -352,7 +761,8 @@ int cx_plan_launch_celln(cx_plan* P, const double* dCellND, double* dCellNR, cud
 // ---------------------------------------------------------------------------
 struct cx_planset {
   cx_ctx* ctx;
-  int nvars, ndesc;
+  int nvars, ndesc, staged, tiled;
+  size_t smem;                          // dynamic shared memory of the type-2 launch
   int nblocks[4];                       // per interpolation type 1,2,3,5
   SetDesc* d_descs[4]; int* d_blk2desc[4];
   void** d_tables; size_t ntables;      // device pointer tables owned by the set
@@ -384,6 +794,8 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
   CX_CUDA(cudaSetDevice(ctx->device));
   cx_planset* S = new cx_planset;
   S->ctx = ctx; S->nvars = nvars; S->d_tables = nullptr; S->ntables = 0; S->ndesc = 0;
+  S->staged = cx_transfer_staging(); S->smem = 0; S->tiled = 0;
+  if (nvars > CX_MAXVARS) { cx_set_error("plan set: at most %d variables per set", CX_MAXVARS); delete S; return -1; }
   std::vector<SetDesc> descs[4]; std::vector<int> b2d[4]; std::vector<void*> tables;
   const int TB = 256;
   int nb[4] = {0, 0, 0, 0};
@@ -399,9 +811,14 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
       int t = G.type == 1 ? 0 : G.type == 2 ? 1 : G.type == 3 ? 2 : 3;
       SetDesc D;
       D.m = G.n; D.type = G.type; D.imd = P->imd; D.imdjmd = P->imd * P->jmd; D.mode = modes[p]; D.first_block = nb[t];
+      D.nptsD = P->nptsD; D.layout = G.layout; D.jmd = P->jmd; D.ntx = G.ntx; D.nty = G.nty;
+      D.tiles = (const TileRef*)G.d_tiles;
+      if (G.type == 2 && G.layout == 2) { S->smem = std::max(S->smem, sizeof(double) * CX_BOXV * (size_t)nvars); S->tiled = 1; }
+      if (G.type == 2 && G.layout == 1) S->smem = std::max(S->smem, sizeof(StageSmem));
+      for (int v = 0; v < nvars; v++) if (((uintptr_t)d_fieldD[p][v]) & 15) S->staged = 0;
       D.donor = P->d_donor + G.first; D.idx = (modes[p] == 0 ? P->d_rcv : P->d_pos) + G.first; D.cfT = G.d_cf;
       D.dptr = td; D.rptr = tr; D.dense = modes[p] == 1 ? d_dense[p] : nullptr; D.ld = modes[p] == 1 ? ld[p] : 0;
-      int blocks = cx_grid(G.n, TB);
+      int blocks = (G.type == 2 && G.layout == 2) ? G.ntiles : cx_grid(G.n, TB);
       for (int b = 0; b < blocks; b++) b2d[t].push_back((int)descs[t].size());
       descs[t].push_back(D);
       nb[t] += blocks;
@@ -426,10 +843,16 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
 
 static int planset_run_on(cx_planset* S, cudaStream_t s)
 {
-  if (S->nblocks[0]) { k_transfer_set<1><<<S->nblocks[0], 256, 0, s>>>(S->d_descs[0], S->d_blk2desc[0], S->nvars); S->ctx->launches++; }
-  if (S->nblocks[1]) { k_transfer_set<2><<<S->nblocks[1], 256, 0, s>>>(S->d_descs[1], S->d_blk2desc[1], S->nvars); S->ctx->launches++; }
-  if (S->nblocks[2]) { k_transfer_set<3><<<S->nblocks[2], 256, 0, s>>>(S->d_descs[2], S->d_blk2desc[2], S->nvars); S->ctx->launches++; }
-  if (S->nblocks[3]) { k_transfer_set<5><<<S->nblocks[3], 256, 0, s>>>(S->d_descs[3], S->d_blk2desc[3], S->nvars); S->ctx->launches++; }
+  if (S->smem > 48 * 1024) CX_CHECK(tiled_smem_optin());
+  if (S->nblocks[0]) { k_transfer_set<1, false><<<S->nblocks[0], 256, 0, s>>>(S->d_descs[0], S->d_blk2desc[0], S->nvars, S->staged); S->ctx->launches++; }
+  if (S->nblocks[1])
+  {
+    if (S->tiled) k_transfer_set<2, true><<<S->nblocks[1], 256, S->smem, s>>>(S->d_descs[1], S->d_blk2desc[1], S->nvars, S->staged);
+    else k_transfer_set<2, false><<<S->nblocks[1], 256, S->smem, s>>>(S->d_descs[1], S->d_blk2desc[1], S->nvars, S->staged);
+    S->ctx->launches++;
+  }
+  if (S->nblocks[2]) { k_transfer_set<3, false><<<S->nblocks[2], 256, 0, s>>>(S->d_descs[2], S->d_blk2desc[2], S->nvars, S->staged); S->ctx->launches++; }
+  if (S->nblocks[3]) { k_transfer_set<5, false><<<S->nblocks[3], 256, 0, s>>>(S->d_descs[3], S->d_blk2desc[3], S->nvars, S->staged); S->ctx->launches++; }
   return 0;
 }
 
