@@ -7,9 +7,12 @@ A "step" is one setInterpTransfers pass over all (donor zone, receptor zone)
 plans of the workload with the interpData already resident in HBM.
   N=1  workload C2 (BASELINE.json configs[1]): Cartesian background 256^3 +
        cylinder O-grid (513,129,257), order 2, ~17 M receptors, 5 variables.
-  N>1  workload C4/C5 (configs[3],[4]) weak-scaled at 8 zones of 100^3 per GPU
-       (4x4x4 blocks at N=8), 7 variables, zones placed by Distributor2-style
-       'proc', cross-GPU values over NCCL.
+  N>1  the same C2 pair once per GPU ("N bodies in a row", weak scaling), the
+       neighbouring backgrounds overlapping by 8 cells and exchanging their
+       fringes over NCCL (bench_c2n.py); in the same run the C4/C5 workload
+       (configs[3],[4]: 64-zone cluster at N=8, 8 zones of 100^3 per GPU,
+       7 variables, 100-iteration loop) is measured and reported under "c4_c5"
+       (bench_c4.py; alone with --workload c4).
 metric = setInterpTransfers algorithmic GB/s (B_alg of SURVEY.md 8(d) / time);
 setInterpData receptor pts/s is reported in the same line under
 "set_interp_data".  The reference arm times the reference's own C++
@@ -286,7 +289,8 @@ def run_reference(args):
     from cassiopee_b200 import workloads as W
     nthreads = os.cpu_count() or 1
     O.set_num_threads(nthreads)
-    if args.gpus == 1:
+    c4 = None
+    if True:
         Bg, Oc = W.c2(args.scale)
         nvars = args.nvars or NVARS_C2
         # (1) setInterpData on a bounded sample of C2a: donor = background coarsened to 128^3 (the ADT build
@@ -347,8 +351,17 @@ def run_reference(args):
                            "located analytically, see bench.py) ; setInterpData on a bounded sample (see set_interp_data)" %
                            (n, Bg.ni, nvars), "receptors": int(n), "nvars": nvars, "alg_bytes_per_step": int(B),
                "distinct_donor_nodes": uniq}
-    else:
-        value, dt, steps, cfg, sid, nvars = reference_c4(args, O, W, nthreads)
+        if args.gpus > 1:
+            # the N-GPU workload is N such bodies; the host's rate does not depend on how many it is given,
+            # so the bounded sample is one body (the fringe exchange has no CPU counterpart in one process)
+            cfg["workload"] = ("bounded sample = 1 of the %d bodies of the N-GPU workload: " % args.gpus) + cfg["workload"]
+            del fD, fR, coefs, dnr, rcv, typ
+            try:
+                cv, dt4, st4, cfg4, sid4, nv4 = reference_c4(args, O, W, nthreads)
+                c4 = {"value": cv, "unit": UNIT, "ms_per_step": dt4 * 1e3, "config": cfg4, "set_interp_data": sid4,
+                      "cores": int(min(nv4, nthreads))}
+            except Exception as e:
+                c4 = {"unavailable": str(e)}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
@@ -357,6 +370,8 @@ def run_reference(args):
                              "sample": cfg["workload"] + "; transfer threads = min(nvars, host threads)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "set_interp_data": sid, "gpu_launches": 0}
+    if c4 is not None:
+        line["c4_c5"] = c4
     print(json.dumps(line))
 
 
@@ -392,15 +407,18 @@ def main():
     ap.add_argument("--nvars", type=int, default=0)
     ap.add_argument("--sid-steps", type=int, default=3, dest="sid_steps")
     ap.add_argument("--sid-warmup", type=int, default=1, dest="sid_warmup")
-    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c4"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c2n", "c4"])
     ap.add_argument("--quick", action="store_true", help="skip the e2e and CPU-baseline legs (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if (args.gpus > 1 or world > 1 or args.workload == "c4") and args.workload != "c2":
+    if args.workload == "c4":
         from bench_c4 import run_c4
         return run_c4(args)
+    if (args.gpus > 1 or world > 1 or args.workload == "c2n") and args.workload != "c2":
+        from bench_c2n import run_c2n
+        return run_c2n(args)
     return run_c2(args)
 
 

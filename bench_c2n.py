@@ -1,0 +1,171 @@
+"""bench_c2n.py — multi-GPU leg of bench.py: BASELINE.json configs[1] (C2) weak-scaled.
+
+N=1 of bench.py is C2a: one Cartesian background 256^3 + one cylinder O-grid
+(17.0 M receptors).  For N GPUs the same pair is instantiated once per GPU
+("N bodies in a row"), consecutive backgrounds overlap by 8 cells and exchange
+their 2-layer fringes, so the path has its real exchange step: zones are
+placed by `.Solver#Param/proc` (each body's two zones on one GPU, what
+Distributor2 does to minimise communication), the distributed
+Connector.Mpi._setInterpData replicates the neighbouring backgrounds and
+routes the ID_* subregions to the donor owners, and every transfer step runs
+the local plans, the remote plans into per-peer send buffers, one grouped
+NCCL send/recv and one scatter launch.  Per-GPU work is fixed (scaling:
+"weak"); value = algorithmic bytes of ALL ranks / max-over-ranks time.
+
+The C4/C5 configs (64-zone cluster, 7 variables, 100-iteration loop) are
+measured in the same run and reported under "c4_c5" (bench_c4.measure_c4).
+"""
+import json
+import os
+import time
+
+import numpy as np
+
+
+def build_local(bodies, rank, nvars):
+    import cassiopee_b200.Converter as C
+    from cassiopee_b200 import workloads as W
+    zones = []
+    for b in bodies:
+        if b['r'] != rank:
+            continue
+        for z in W.c2n_zones(b):
+            for i, v in enumerate(W.VARS7[:nvars]):
+                C._initVars(z, v, lambda x, y, zz, i=i: 1. + 0.1 * (i + 1) * np.sin(2 * np.pi * x) * np.cos(2 * np.pi * y)
+                            + 0.05 * (i + 1) * zz)
+            zones.append(z)
+    return C.newPyTree(['Base'] + zones)
+
+
+def run_c2n(args):
+    from bench import METRIC, UNIT, ClockSampler, measured_peaks, NVARS_C2
+    from bench_c4 import _warm, measure_c4
+    from cassiopee_b200 import _lib, Mpi as Cmpi, Distributor2 as D2, workloads as W
+    import cassiopee_b200.Internal as Internal
+    import cassiopee_b200.Converter as C
+    import cassiopee_b200.Connector.Mpi as Xmpi
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    ngpus = max(args.gpus, world)
+    ctx = _lib.default_context()
+    comm = Cmpi.Comm(ctx) if world > 1 else None
+    nvars = args.nvars or NVARS_C2
+    bodies = W.c2n_layout(ngpus if world > 1 else 1, args.scale)
+    t0 = time.perf_counter()
+    t = build_local(bodies, rank, nvars)
+    for z in Internal.getZones(t):
+        D2._setProc(z, rank)
+    t_gen = time.perf_counter() - t0
+    zoneOrder = [n for b in bodies for n in (b['bg'], b['og'])]
+    names = W.VARS7[:nvars]
+
+    def barrier():
+        ctx.sync()
+        if comm is not None:
+            comm.barrier()
+
+    def gather(v):
+        return comm.allgather_obj(v) if comm is not None else [v]
+
+    _warm(ctx)
+    # ---- distributed setInterpData (receptor owner computes; neighbour backgrounds replicated) ----
+    barrier()
+    t0 = time.perf_counter()
+    Xmpi._setInterpData(t, t, order=2, nature=1, penalty=1, extrap=1, loc='nodes', storage='inverse',
+                        comm=comm, zoneOrder=zoneOrder, ctx=ctx, verbose=0)
+    barrier()
+    sid_s = time.perf_counter() - t0
+    nrcv_local = sum(int((C.getFieldArray(z, 'cellN') == 2.).sum()) for z in Internal.getZones(t))
+    norphan = 0
+    for z in Internal.getZones(t):
+        for s in Internal.getNodesFromType1(z, 'ZoneSubRegion_t'):
+            o = Internal.getNodeFromName1(s, 'OrphanPointList')
+            if o is not None:
+                norphan = max(norphan, int(o[1].size))
+
+    # ---- steady-state transfers ------------------------------------------------------------------
+    sess = Xmpi.TransferSession(t, t, names, comm=comm, ctx=ctx)
+    sess.step(max(3, args.warmup))
+    barrier()
+    sampler = ClockSampler(ctx.device)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches()
+    barrier()
+    ctx.event_record(0)
+    sess.step(args.steps)
+    ctx.event_record(1)
+    ms = ctx.event_elapsed_ms()
+    barrier()
+    launches = ctx.launches() - l0
+    sess.step(600)          # keep the GPUs busy so nvidia-smi samples clocks under load
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end: host donor fields -> device, step, receptor fields -> host (tree arrays pinned in place) ----
+    sess.pin_host_fields()
+    ne2e = max(2, min(args.steps, 5))
+    sess.upload_donor_fields(); sess.step(); sess.download()
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(ne2e):
+        sess.upload_donor_fields()
+        sess.step()
+        d2h = sess.download()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / ne2e
+    sess.unpin_host_fields()
+
+    B = sum(gather(sess.alg_bytes()))
+    ms_max = max(gather(ms))
+    e2e_max = max(gather(e2e_s))
+    sid_max = max(gather(sid_s))
+    nrcv = sum(gather(nrcv_local))
+    nccl_b = sum(gather(sess.nccl_bytes()))
+    h2d = sum(gather(sess.h2d_bytes)); d2h = sum(gather(d2h))
+    nplans = sum(gather(len(sess.plans)))
+    launches_all = sum(gather(launches))
+    norphan = sum(gather(norphan))
+    # free the C2 session before the C4/C5 leg
+    del sess, t
+    import gc
+    gc.collect()
+    c4 = measure_c4(args, ctx, comm, ngpus, rank, world) if not args.quick else None
+    if rank != 0:
+        return
+    ms_step = ms_max / args.steps
+    value = B / (ms_step * 1e-3) / 1e9
+    peak, how = measured_peaks()
+    b0 = bodies[0]
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ngpus, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2a per GPU (cart %d^3 background -> cylinder O-grid %s receptors, order 2, nature=1 "
+                               "penalty=1 extrap=1, %d vars), %d bodies in a row, neighbouring backgrounds overlap by 8 "
+                               "cells and exchange 2-layer fringes over NCCL; C4/C5 cluster under c4_c5" %
+                               (b0['nb'], str(tuple(b0['nc'])), nvars, len(bodies)),
+                   "zones": 2 * len(bodies), "receptors": int(nrcv), "plans": int(nplans), "nvars": nvars,
+                   "alg_bytes_per_step": int(B), "nccl_bytes_per_step": int(nccl_b), "orphans": int(norphan),
+                   "l2": "inputs larger than L2 (%.2f GB of plan+field traffic per GPU and step, L2 126 MB); no flush" %
+                         (B / max(1, ngpus) / 1e9),
+                   "parallelism": "one body (2 zones) per GPU by .Solver#Param/proc"},
+        "clocks": clocks,
+        "e2e": {"value": B / e2e_max / 1e9, "unit": UNIT, "ms_per_step": e2e_max * 1e3,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "api": "Connector.Mpi.TransferSession upload_donor_fields/step/download (host tree arrays pinned in "
+                       "place, copies inside the timed region)"},
+        "gpu_launches": int(launches_all),
+        "roofline": {"bound": "hbm", "achieved": value / ngpus, "peak": peak, "unit": "GB/s per GPU",
+                     "frac": value / ngpus / peak, "traffic": None, "peak_source": how,
+                     "kernel": "k_transfer2s<0> (local C2a plan) + k_transfer_set<2> (fringe plans) + NCCL send/recv + "
+                               "k_scatter_set"},
+        "cpu_baseline": None,
+        "set_interp_data": {"value": nrcv / sid_max, "unit": "receptor pts/s", "receptors": int(nrcv), "s": sid_max,
+                            "includes": "host trees in/out: donor-zone replication, device ADT builds, search, packing, "
+                                        "D2H of the lists, routing of ID_* subregions to donor owners",
+                            "tree_build_s": t_gen},
+        "c4_c5": c4,
+    }
+    print(json.dumps(line))

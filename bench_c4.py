@@ -46,18 +46,14 @@ def build_local(blocks, owners, rank, nvars):
     return C.newPyTree(['Base'] + zones)
 
 
-def run_c4(args):
-    from bench import METRIC, UNIT, ClockSampler, measured_peaks
-    from cassiopee_b200 import _lib, Mpi as Cmpi, Distributor2 as D2, workloads as W
+def measure_c4(args, ctx, comm, ngpus, rank, world):
+    """C4/C5 on the ranks of this job; returns the result dict on rank 0 (None elsewhere)."""
+    from bench import ClockSampler, measured_peaks
+    from cassiopee_b200 import _lib, Distributor2 as D2, workloads as W
     import cassiopee_b200.Internal as Internal
     import cassiopee_b200.Converter as C
     import cassiopee_b200.Connector.Mpi as Xmpi
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    ngpus = max(args.gpus, world)
-    ctx = _lib.default_context()
-    comm = Cmpi.Comm(ctx) if world > 1 else None
-    nvars = args.nvars or 7
+    nvars = int(os.environ.get("CX_C4_NVARS", "7"))
     nblk = int(os.environ.get("CX_C4_N", "100"))
     blocks, nb = layout_for(ngpus, nblk)
     centres = [np.array(b['origin']) + 0.5 * (b['n'] - 1) * b['h'] for b in blocks]
@@ -101,13 +97,23 @@ def run_c4(args):
     ms = ctx.event_elapsed_ms()
     barrier()
     launches = ctx.launches() - l0
+    # C5: the 100-iteration loop with the interpData reused (first 5 calls skipped)
+    sess.step(5, use_graph)
+    barrier()
+    ctx.event_record(0)
+    sess.step(100, use_graph)
+    ctx.event_record(1)
+    ms100 = ctx.event_elapsed_ms()
+    barrier()
     # keep the GPUs busy so nvidia-smi samples clocks under load (same count on every rank: NCCL pairs must match)
     sess.step(2000, use_graph)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end: host donor fields -> device, step, receptor fields -> host ----
+    sess.pin_host_fields()
     ne2e = max(2, min(args.steps, 5))
+    sess.upload_donor_fields(); sess.step(); sess.download()
     barrier()
     t0 = time.perf_counter()
     d2h = 0
@@ -117,12 +123,14 @@ def run_c4(args):
         d2h = sess.download()
     barrier()
     e2e_s = (time.perf_counter() - t0) / ne2e
+    sess.unpin_host_fields()
 
     def gather(v):
         return comm.allgather_obj(v) if comm is not None else [v]
 
     B = sum(gather(sess.alg_bytes()))
     ms_max = max(gather(ms))
+    ms100_max = max(gather(ms100))
     e2e_max = max(gather(e2e_s))
     sid_max = max(gather(sid_s))
     nrcv = sum(gather(nrcv_local))
@@ -131,14 +139,12 @@ def run_c4(args):
     nplans = sum(gather(len(sess.plans)))
     launches_all = sum(gather(launches))
     if rank != 0:
-        return
+        return None
     ms_step = ms_max / args.steps
     value = B / (ms_step * 1e-3) / 1e9
     peak, how = measured_peaks()
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ngpus, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+    return {
+        "value": value, "unit": "GB/s", "n_gpus": ngpus, "steps": args.steps, "ms_per_step": ms_step,
         "config": {"workload": "C4/C5: %dx%dx%d blocks of %d^3 pts (8-cell overlap, sub-cell shifts), receptors = outer "
                                "2 cell layers inside another block, order 2, %d vars, interpData reused" %
                                (nb[0], nb[1], nb[2], nblk, nvars),
@@ -148,21 +154,43 @@ def run_c4(args):
                    "l2": "per-GPU working set %.0f MB; L2 not flushed (steady-state loop of a solver)" %
                          ((B / max(1, ngpus)) / 1e6),
                    "parallelism": "zones over %d GPU(s) by .Solver#Param/proc (rcb)" % ngpus},
+        "c5_100_iterations": {"ms_total": ms100_max, "ms_per_step": ms100_max / 100.,
+                              "GBps": B / (ms100_max / 100. * 1e-3) / 1e9},
         "clocks": clocks,
-        "e2e": {"value": B / e2e_max / 1e9, "unit": UNIT, "ms_per_step": e2e_max * 1e3,
+        "e2e": {"value": B / e2e_max / 1e9, "unit": "GB/s", "ms_per_step": e2e_max * 1e3,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "api": "TransferSession.upload_donor_fields/step/download (host trees in, host trees out)"},
         "gpu_launches": int(launches_all), "comm_overlap": bool(use_graph),
         "roofline": {"bound": "hbm", "achieved": value / ngpus, "peak": peak, "unit": "GB/s per GPU",
                      "frac": value / ngpus / peak, "traffic": None, "peak_source": how,
                      "kernel": "k_transfer_set<2> (+ NCCL send/recv + k_scatter_set inside the step)"},
-        "cpu_baseline": None,
         "set_interp_data": {"value": nrcv / sid_max, "unit": "receptor pts/s", "receptors": int(nrcv),
                             "s": sid_max, "includes": "donor-zone replication, device ADT builds, search, "
                             "routing of ID_* subregions to donor owners (host trees in/out)"},
     }
-    if ngpus == 1 and not args.quick:
-        line["cpu_baseline"] = cpu_baseline_c4(args, blocks, nvars)
+
+
+def run_c4(args):
+    """`--workload c4`: the C4/C5 leg alone, printed as the bench line."""
+    from bench import METRIC, UNIT
+    from cassiopee_b200 import _lib, Mpi as Cmpi
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    ngpus = max(args.gpus, world)
+    ctx = _lib.default_context()
+    comm = Cmpi.Comm(ctx) if world > 1 else None
+    os.environ.setdefault("CX_C4_NVARS", str(args.nvars or 7))
+    r = measure_c4(args, ctx, comm, ngpus, rank, world)
+    if rank != 0:
+        return
+    line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": ngpus, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+    for k in ("config", "clocks", "e2e", "gpu_launches", "comm_overlap", "roofline", "set_interp_data",
+              "c5_100_iterations"):
+        line[k] = r[k]
+    line["cpu_baseline"] = cpu_baseline_c4(args, layout_for(ngpus, int(os.environ.get("CX_C4_N", "100")))[0],
+                                           int(os.environ.get("CX_C4_NVARS", "7"))) if (ngpus == 1 and not args.quick) else None
     print(json.dumps(line))
 
 

@@ -35,6 +35,10 @@ _SIGS = {
     "cx_dev_upload": (_i, [_vp, _vp, _vp, _sz]),
     "cx_dev_download": (_i, [_vp, _vp, _vp, _sz]),
     "cx_dev_memset": (_i, [_vp, _vp, _i, _sz]),
+    "cx_dev_upload_async": (_i, [_vp, _vp, _vp, _sz]),
+    "cx_dev_download_async": (_i, [_vp, _vp, _vp, _sz]),
+    "cx_host_register": (_i, [_vp, _sz]),
+    "cx_host_unregister": (_i, [_vp]),
     "cx_pinned_alloc": (_i, [_sz, _vp]),
     "cx_pinned_free": (_i, [_vp]),
     "cx_zone_create": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
@@ -185,6 +189,13 @@ class Context:
 
     def download(self, host, dptr):
         check(lib().cx_dev_download(self.h, ptr(host), _vp(dptr), host.nbytes))
+
+    def upload_async(self, dptr, host):
+        """No synchronisation (order with sync()); host should be pinned or registered."""
+        check(lib().cx_dev_upload_async(self.h, _vp(dptr), ptr(host), host.nbytes))
+
+    def download_async(self, host, dptr):
+        check(lib().cx_dev_download_async(self.h, ptr(host), _vp(dptr), host.nbytes))
 
 
 _default_ctx = {}
@@ -405,6 +416,18 @@ class Plan:
         """B_alg of SURVEY.md 8(d) for one call with nvars variables."""
         i = self.info()
         return i["alg_fixed"] + 8 * nvars * (i["n"] + i["distinct"])
+
+
+def host_register(a):
+    """Page-lock a contiguous numpy array in place (cudaHostRegister); returns True if this call pinned it."""
+    rc = lib().cx_host_register(ptr(a), a.nbytes)
+    if rc < 0:
+        check(rc)
+    return rc == 0
+
+
+def host_unregister(a):
+    lib().cx_host_unregister(ptr(a))
 
 
 class _PinnedBlock:

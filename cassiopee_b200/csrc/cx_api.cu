@@ -178,6 +178,31 @@ int cx_dev_memset(cx_ctx* c, void* dptr, int value, size_t bytes)
   CX_CUDA(cudaMemsetAsync(dptr, value, bytes, c->stream));
   return 0;
 }
+// no synchronisation: the caller orders with cx_ctx_sync (host memory should be pinned or registered)
+int cx_dev_upload_async(cx_ctx* c, void* dptr, const void* host, size_t bytes)
+{
+  CX_CUDA(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+int cx_dev_download_async(cx_ctx* c, void* host, const void* dptr, size_t bytes)
+{
+  CX_CUDA(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
+// page-lock a caller-owned host range in place (numpy arrays of a tree that is transferred every iteration)
+int cx_host_register(void* hptr, size_t bytes)
+{
+  cudaError_t e = cudaHostRegister(hptr, bytes, cudaHostRegisterDefault);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 1; }
+  if (e != cudaSuccess) { cudaGetLastError(); cx_set_error("cudaHostRegister: %s", cudaGetErrorString(e)); return -2; }
+  return 0;
+}
+int cx_host_unregister(void* hptr)
+{
+  cudaError_t e = cudaHostUnregister(hptr);
+  if (e != cudaSuccess) cudaGetLastError();
+  return 0;
+}
 int cx_pinned_alloc(size_t bytes, void** hptr) { CX_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 8, cudaHostAllocDefault)); return 0; }
 int cx_pinned_free(void* hptr) { CX_CUDA(cudaFreeHost(hptr)); return 0; }
 

@@ -25,6 +25,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #define CX_MAXVARS 16
+#define CX_BIG_PLAN (1 << 20)   // entries; plan sets launch such plans on their own
 
 struct FieldPtrs { const double* d[CX_MAXVARS]; double* r[CX_MAXVARS]; };
 
@@ -213,7 +214,7 @@ __device__ __forceinline__ bool transfer_tile2_staged(StageSmem& S, int t0, int 
 // as full sectors.  Arithmetic is unchanged (same operand order, no FMA).
 #define CX_TX 32
 #define CX_TY 8
-#define CX_ROWP 36                                   // row pitch in shared memory (doubles), >= CX_TX + 1 + 2
+#define CX_ROWP 34                                   // row pitch in shared memory (doubles): CX_TX + 1 nodes + 1 alignment shift
 #define CX_BOXV (2 * (CX_TY + 1) * CX_ROWP)          // doubles per variable
 struct TileRef { int tile, start; };                 // box id, first entry; entry count = next.start - start
 
@@ -762,6 +763,9 @@ int cx_plan_launch_celln(cx_plan* P, const double* dCellND, double* dCellNR, cud
 struct cx_planset {
   cx_ctx* ctx;
   int nvars, ndesc, staged, tiled;
+  // plans too large to gain anything from fusion run as their own launches (leaner kernel, more CTAs per SM)
+  struct Big { cx_plan* P; int mode; std::vector<const double*> dD; std::vector<double*> dR; double* dense; long long ld; };
+  std::vector<Big> big;
   size_t smem;                          // dynamic shared memory of the type-2 launch
   int nblocks[4];                       // per interpolation type 1,2,3,5
   SetDesc* d_descs[4]; int* d_blk2desc[4];
@@ -803,6 +807,15 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
   {
     cx_plan* P = plans[p];
     if (P->n == 0) continue;
+    if (P->n >= CX_BIG_PLAN)
+    {
+      cx_planset::Big B;
+      B.P = P; B.mode = modes[p]; B.dense = modes[p] == 1 ? d_dense[p] : nullptr; B.ld = modes[p] == 1 ? ld[p] : 0;
+      B.dD.assign(d_fieldD[p], d_fieldD[p] + nvars);
+      if (modes[p] == 0) B.dR.assign(d_fieldR[p], d_fieldR[p] + nvars);
+      S->big.push_back(B);
+      continue;
+    }
     double** td = nullptr; double** tr = nullptr;
     CX_CHECK(upload_ptr_table(d_fieldD[p], nvars, &td)); tables.push_back(td);
     if (modes[p] == 0) { CX_CHECK(upload_ptr_table((const double* const*)d_fieldR[p], nvars, &tr)); tables.push_back(tr); }
@@ -843,6 +856,8 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
 
 static int planset_run_on(cx_planset* S, cudaStream_t s)
 {
+  for (auto& B : S->big)
+    CX_CHECK(cx_plan_launch(B.P, S->nvars, B.dD.data(), B.mode == 0 ? B.dR.data() : nullptr, B.dense, B.ld, B.mode, s));
   if (S->smem > 48 * 1024) CX_CHECK(tiled_smem_optin());
   if (S->nblocks[0]) { k_transfer_set<1, false><<<S->nblocks[0], 256, 0, s>>>(S->d_descs[0], S->d_blk2desc[0], S->nvars, S->staged); S->ctx->launches++; }
   if (S->nblocks[1])
@@ -914,9 +929,9 @@ static int scatterset_run_on(cx_scatterset* S, cudaStream_t s)
 int cx_scatterset_run(cx_scatterset* S) { return scatterset_run_on(S, S->ctx->stream); }
 
 // ---- one solver iteration of a rank -------------------------------------------------
-//   main stream : [wait previous exchange] remote plans (dense blocks -> send buffers) | fork | local plans (in place)
-//   comm stream :                                                       wait fork -> NCCL send/recv -> scatter | join
-// so the NVLink exchange and the scatter of iteration i overlap the local transfers of iteration i.
+//   main stream : fork | local plans (in place)                                                     | join
+//   comm stream :      wait fork -> remote plans (dense blocks -> send buffers) -> NCCL send/recv -> scatter |
+// so the remote plans, the NVLink exchange and the scatter of iteration i overlap its local transfers.
 extern int cx_exchange_on_stream(cx_ctx* ctx, cudaStream_t st, int npeers, const int* peers, const double* const* d_send,
                                  const long long* sendcounts, double* const* d_recv, const long long* recvcounts);
 
@@ -949,19 +964,22 @@ int cx_step_run(cx_step* S, int niter, int overlap)
   const bool comm = !S->peers.empty();
   for (int it = 0; it < niter; it++)
   {
-    if (comm && overlap) CX_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));   // send buffers free again
-    if (S->ps_remote) CX_CHECK(planset_run_on(S->ps_remote, s));
+    // fork at the iteration boundary: everything queued on the main stream so far (the solver's update of the
+    // donor fields) precedes the remote plans; the send buffers are free again because the previous
+    // iteration's exchange ran on the same communication stream
+    if (comm && overlap) { CX_CUDA(cudaEventRecord(c->ev_fork, s)); CX_CUDA(cudaStreamWaitEvent(cs, c->ev_fork, 0)); }
+    if (S->ps_remote) CX_CHECK(planset_run_on(S->ps_remote, comm ? cs : s));
     if (comm)
     {
-      if (overlap) { CX_CUDA(cudaEventRecord(c->ev_fork, s)); CX_CUDA(cudaStreamWaitEvent(cs, c->ev_fork, 0)); }
       CX_CHECK(cx_exchange_on_stream(c, cs, (int)S->peers.size(), S->peers.data(), S->sp.data(), S->sc.data(),
                                      S->rp.data(), S->rc.data()));
       if (S->ss) CX_CHECK(scatterset_run_on(S->ss, cs));
       if (overlap) CX_CUDA(cudaEventRecord(c->ev_join, cs));
     }
     if (S->ps_local) CX_CHECK(planset_run_on(S->ps_local, s));
+    // join: the iteration ends when both the local plans and the scatter of the received values are done
+    if (comm && overlap) CX_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
   }
-  if (comm && overlap) CX_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));     // join: later work on the main stream sees the scatter
   return 0;
 }
 

@@ -137,3 +137,42 @@ def bbox_intersect(b1, b2, tol=1.e-6):
     """K_COMPGEOM::compBoundingBoxIntersection semantics (compGeom.cpp:1055-1070)."""
     return not (b1[0] > b2[3] + tol or b1[3] < b2[0] - tol or b1[1] > b2[4] + tol or b1[4] < b2[1] - tol or
                 b1[2] > b2[5] + tol or b1[5] < b2[2] - tol)
+
+
+# ---------------------------------------------------------------------------
+# C2 weak-scaled over GPUs: one C2a pair per body, backgrounds overlap their neighbours
+# ---------------------------------------------------------------------------
+def c2n_layout(nbodies, scale=1.0, overlap=8, seed=2):
+    """N bodies in a row along x.  Body r = the C2 pair translated by cx_r: background
+    Bg_r = cart((-3+cx_r,-3,0), (6/(nb-1), 6/(nb-1), 2/(nb-1)), nb^3) and near-body O-grid
+    O_r = cylinder((cx_r,0,0), 0.5, 2.5, 360, 0, 2, nc).  Consecutive backgrounds overlap by
+    `overlap` cells (+ a sub-cell shift from default_rng(seed), zero for body 0, so that one
+    body alone is exactly C2a)."""
+    nb = max(8, int(round(256 * scale)))
+    nc = (max(9, int(round(512 * scale)) + 1), max(5, int(round(128 * scale)) + 1), max(5, int(round(256 * scale)) + 1))
+    hx = 6. / (nb - 1)
+    Lx = (nb - 1 - overlap) * hx
+    rng = np.random.default_rng(seed)
+    out = []
+    for r in range(nbodies):
+        sx = 0. if r == 0 else float(rng.uniform(0., hx))
+        out.append(dict(r=r, n=nbodies, cx=r * Lx + sx, nb=nb, nc=nc, bg='Bg_%d' % r, og='O_%d' % r))
+    return out
+
+
+def c2n_zones(body, depth=2):
+    """The two zones (CGNS/Python trees) of one body with node cellN: the O-grid is all receptors
+    (cellN=2, like C2a); the background's `depth` node layers next to a neighbouring background are
+    receptors (what applyBCOverlaps marks next to a BCOverlap window), 1 elsewhere."""
+    nb = body['nb']; cx = body['cx']
+    h = (6. / (nb - 1), 6. / (nb - 1), 2. / (nb - 1))
+    bg = G.cart((-3. + cx, -3., 0.), h, (nb, nb, nb), name=body['bg'])
+    og = G.cylinder((cx, 0., 0.), 0.5, 2.5, 360., 0., 2., body['nc'], name=body['og'])
+    c = np.ones((nb, nb, nb), order='F')
+    if body['r'] > 0:
+        c[:depth, :, :] = 2.
+    if body['r'] < body['n'] - 1:
+        c[nb - depth:, :, :] = 2.
+    C._initVars(bg, 'cellN', c)
+    C._initVars(og, 'cellN', 2.)
+    return bg, og

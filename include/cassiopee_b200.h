@@ -47,6 +47,10 @@ int cx_dev_free(cx_ctx* ctx, void* dptr);
 int cx_dev_upload(cx_ctx* ctx, void* dptr, const void* host, size_t bytes);
 int cx_dev_download(cx_ctx* ctx, void* host, const void* dptr, size_t bytes);
 int cx_dev_memset(cx_ctx* ctx, void* dptr, int value, size_t bytes);
+int cx_dev_upload_async(cx_ctx* ctx, void* dptr, const void* host, size_t bytes);   /* ordered by cx_ctx_sync */
+int cx_dev_download_async(cx_ctx* ctx, void* host, const void* dptr, size_t bytes);
+int cx_host_register(void* hptr, size_t bytes);   /* page-lock a caller-owned range in place; 1 = already registered */
+int cx_host_unregister(void* hptr);
 int cx_pinned_alloc(size_t bytes, void** hptr);
 int cx_pinned_free(void* hptr);
 

@@ -43,6 +43,19 @@ def build_case(nb=(2, 2, 1), n=13):
     return t
 
 
+def build_case_c2n(nbodies):
+    """Tiny version of the multi-body C2 weak-scaling workload of bench_c2n.py (node-located receptors,
+    donor tree == receptor tree, one body = two zones per rank)."""
+    zones = []
+    for b in W.c2n_layout(nbodies, scale=1. / 16, overlap=4):
+        for z in W.c2n_zones(b):
+            for i, v in enumerate(VARS):
+                C._initVars(z, v, lambda x, y, zz, i=i: 1. + i + np.sin(3 * x) + 2. * y * y + 3. * zz)
+            D2._setProc(z, b['r'])
+            zones.append(z)
+    return C.newPyTree(['Base'] + zones)
+
+
 def subtree_of(t, rank):
     zs = [z for z in Internal.getZones(t) if D2.getProc(z) == rank]
     return C.newPyTree(['Base'] + zs)
@@ -60,8 +73,11 @@ def collect(tc, t):
     fields = {}
     for z in Internal.getZones(t):
         for v in VARS:
-            fields[(z[0], v)] = np.array(C.getFieldArray(z, 'centers:' + v))
+            fields[(z[0], v)] = np.array(C.getFieldArray(z, PREFIX[0] + v))
     return out, fields
+
+
+PREFIX = ['centers:']
 
 
 def main():
@@ -77,11 +93,16 @@ def main():
         ctx = None
         comm = Cmpi.Comm(None, device=False)
         backend = OracleBackend()
-    t = build_case()
+    case = sys.argv[3] if len(sys.argv) > 3 else 'c4'
+    loc = 'centers'
+    if case == 'c2n':
+        loc = 'nodes'; PREFIX[0] = ''
+    make = (lambda: build_case_c2n(comm.size)) if case == 'c2n' else build_case
+    t = make()
     zoneOrder = [z[0] for z in Internal.getZones(t)]
     tl = subtree_of(t, rank)
-    tcl = C.node2Center(tl)
-    Xmpi._setInterpData(tl, tcl, order=order, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse',
+    tcl = tl if case == 'c2n' else C.node2Center(tl)
+    Xmpi._setInterpData(tl, tcl, order=order, nature=1, penalty=1, extrap=1, loc=loc, storage='inverse',
                         comm=comm, zoneOrder=zoneOrder, backend=backend, ctx=ctx)
     if mode == 'nccl':
         sess = Xmpi.TransferSession(tl, tcl, VARS, comm=comm, ctx=ctx)
@@ -95,9 +116,9 @@ def main():
     ok = True
     if rank == 0:
         # single-process run of the same backend on the whole tree
-        t1 = build_case()
-        tc1 = C.node2Center(t1)
-        Xmpi._setInterpData(t1, tc1, order=order, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse',
+        t1 = make()
+        tc1 = t1 if case == 'c2n' else C.node2Center(t1)
+        Xmpi._setInterpData(t1, tc1, order=order, nature=1, penalty=1, extrap=1, loc=loc, storage='inverse',
                             comm=None, zoneOrder=zoneOrder, backend=backend, ctx=ctx)
         if mode == 'nccl':
             s1 = Xmpi.TransferSession(t1, tc1, VARS, comm=None, ctx=ctx)

@@ -8,12 +8,12 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(nproc, mode, order=2, port=29611):
+def _run(nproc, mode, order=2, port=29611, case='c4'):
     env = dict(os.environ)
     env["OMP_NUM_THREADS"] = "2"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py"),
-           mode, str(order)]
+           mode, str(order), case]
     r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "ok=True" in r.stdout
@@ -26,6 +26,22 @@ def test_world2_gloo_oracle_backend():
 
 def test_world3_gloo_oracle_backend_order3():
     _run(3, "gloo-oracle", 3, 29612)
+
+
+def test_world2_gloo_oracle_backend_multibody_nodes():
+    """bench_c2n.py's workload shape: node-located receptors, donor tree is the receptor tree."""
+    _run(2, "gloo-oracle", 2, 29614, case='c2n')
+
+
+@pytest.mark.gpu
+def test_world2_nccl_device_backend_multibody_nodes():
+    import ctypes
+    from cassiopee_b200 import _lib
+    n = ctypes.c_int(0)
+    _lib.lib().cx_device_count(ctypes.byref(n))
+    if n.value < 2:
+        pytest.skip("needs 2 GPUs")
+    _run(2, "nccl", 2, 29615, case='c2n')
 
 
 @pytest.mark.gpu
