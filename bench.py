@@ -34,9 +34,9 @@ sys.path.insert(0, ROOT)
 METRIC = "setInterpTransfers_algorithmic_GBps"
 UNIT = "GB/s"
 NVARS_C2 = 5
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_transfer<2,0> launch on C2a (5 vars), from the
-# `ncu --set full` capture summarised in profiles/r01_b_summary.md (1.621456 GB + 655.629 MB)
-NCU_TRAFFIC_C2A_5VARS = 1621456000 + 655629056
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_transfer2s<0> launch on C2a (5 vars), from the
+# `ncu --set full` capture summarised in profiles/r01_c_transfer_staged_summary.md (1.731608 GB + 654.801 MB)
+NCU_TRAFFIC_C2A_5VARS = 1731608000 + 654801152
 
 
 def measured_peaks():
@@ -252,8 +252,8 @@ def run_c2(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": value, "peak": peak, "unit": "GB/s", "frac": value / peak,
                      "traffic": NCU_TRAFFIC_C2A_5VARS if (args.scale == 1.0 and nvars == 5) else None,
-                     "traffic_source": "profiles/r01_b_summary.md (ncu --set full, one launch)",
-                     "peak_source": how, "kernel": "k_transfer<2,0>",
+                     "traffic_source": "profiles/r01_c_transfer_staged_summary.md (ncu --set full, one launch)",
+                     "peak_source": how, "kernel": "k_transfer2s<0>",
                      "frac_of_nominal_8TBps": value / 8000.0},
         "cpu_baseline": cpu,
         "set_interp_data": sid,

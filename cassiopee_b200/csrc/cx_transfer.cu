@@ -35,7 +35,7 @@ template <int O> struct Sten { };
 
 // One entry of one plan.  MODE 0: scatter to fieldR[v][rcv[e]];  MODE 1: dense out[v*ld + pos[e]].
 // PD/PR: anything indexable by variable (kernel-parameter struct or device pointer table).
-template <int TYPE, int MODE, class PD, class PR>
+template <int TYPE, int MODE, class PD, class PR, int VU = 1>
 __device__ __forceinline__ void transfer_entry(int e, int m, int nvars, const PD& pd, const PR& pr, int imd, int imdjmd,
                                                const int* __restrict__ donor, const int* __restrict__ idx,
                                                const double* __restrict__ cfT, double* __restrict__ dense,
@@ -57,7 +57,27 @@ __device__ __forceinline__ void transfer_entry(int e, int m, int nvars, const PD
     double c[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) c[k] = cfT[(size_t)k * m + e];
-    for (int v = 0; v < nvars; v++)
+    int v = 0;
+    if (VU == 2)
+    {
+      // two variables per pass: 16 independent gathers in flight (small, latency-bound plans)
+      for (; v + 1 < nvars; v += 2)
+      {
+        const double* f = pd[v] + d0; const double* g = pd[v + 1] + d0;
+        const double f0 = __ldg(f), f1 = __ldg(f + 1), f2 = __ldg(f + imd), f3 = __ldg(f + imd + 1);
+        const double f4 = __ldg(f + imdjmd), f5 = __ldg(f + imdjmd + 1), f6 = __ldg(f + imdjmd + imd), f7 = __ldg(f + imdjmd + imd + 1);
+        const double g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + imd), g3 = __ldg(g + imd + 1);
+        const double g4 = __ldg(g + imdjmd), g5 = __ldg(g + imdjmd + 1), g6 = __ldg(g + imdjmd + imd), g7 = __ldg(g + imdjmd + imd + 1);
+        double va = 0., vb = 0.;
+        va += c[0] * f0; va += c[1] * f1; va += c[2] * f2; va += c[3] * f3;
+        va += c[4] * f4; va += c[5] * f5; va += c[6] * f6; va += c[7] * f7;
+        vb += c[0] * g0; vb += c[1] * g1; vb += c[2] * g2; vb += c[3] * g3;
+        vb += c[4] * g4; vb += c[5] * g5; vb += c[6] * g6; vb += c[7] * g7;
+        if (MODE == 0) { pr[v][o] = va; pr[v + 1][o] = vb; }
+        else { dense[(size_t)v * ld + o] = va; dense[(size_t)(v + 1) * ld + o] = vb; }
+      }
+    }
+    for (; v < nvars; v++)
     {
       const double* f = pd[v] + d0;
       double val = 0.;
@@ -368,8 +388,17 @@ template <int TYPE, bool TILED>
 __global__ void __launch_bounds__(256)
 k_transfer_set(const SetDesc* __restrict__ descs, const int* __restrict__ blk2desc, int nvars, int staged)
 {
-  const SetDesc D = descs[blk2desc[blockIdx.x]];
-  PDk pd{D.dptr}; PRk pr{D.rptr};
+  // descriptor and field-pointer tables go through shared memory once per CTA: the per-variable pointer
+  // fetches inside the entry loop are then shared-memory reads instead of dependent global loads
+  __shared__ SetDesc sD;
+  __shared__ const double* s_pd[CX_MAXVARS];
+  __shared__ double* s_pr[CX_MAXVARS];
+  if (threadIdx.x == 0) sD = descs[blk2desc[blockIdx.x]];
+  __syncthreads();
+  if (threadIdx.x < nvars) { s_pd[threadIdx.x] = sD.dptr[threadIdx.x]; s_pr[threadIdx.x] = sD.rptr ? sD.rptr[threadIdx.x] : nullptr; }
+  __syncthreads();
+  const SetDesc& D = sD;
+  PDk pd{s_pd}; PRk pr{s_pr};
   if (TYPE == 2)
   {
     extern __shared__ __align__(16) double dyn_sm[];
@@ -404,8 +433,8 @@ k_transfer_set(const SetDesc* __restrict__ descs, const int* __restrict__ blk2de
   }
   int e = (blockIdx.x - D.first_block) * blockDim.x + threadIdx.x;
   if (e >= D.m) return;
-  if (D.mode == 0) transfer_entry<TYPE, 0>(e, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
-  else transfer_entry<TYPE, 1>(e, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
+  if (D.mode == 0) transfer_entry<TYPE, 0, PDk, PRk, 1>(e, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
+  else transfer_entry<TYPE, 1, PDk, PRk, 1>(e, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
 }
 
 // Receptor-side batched scatter of received dense buffers: fieldR[v][rcv[e]] = in[v*ld + e]
