@@ -46,11 +46,13 @@ def getInterpolatedPoints__(a):
     return [a[0] + ',indcell', out, sel.size, 1, 1]
 
 
-def createHooks__(zonesD, ctx=None):
-    """One device ADT per donor array (analogue of [C.createHook(z,'adt') ...])."""
+def createHooks__(zonesD, ctx=None, interpDataType=1):
+    """One device donor per array (analogue of [C.createHook(z,'adt') ...]); interpDataType 0 makes a
+    regular Cartesian donor located in closed form (InterpCart) instead of an ADT."""
     ctx = ctx or _lib.default_context()
     hooks = []
-    for a in zonesD:
+    types = interpDataType if isinstance(interpDataType, list) else [interpDataType] * len(zonesD)
+    for a, ty in zip(zonesD, types):
         px, py, pz = _posxyz(a[0])
         pc = _poscelln(a[0])
         if px == -1 or py == -1 or pz == -1:
@@ -58,7 +60,7 @@ def createHooks__(zonesD, ctx=None):
         f = a[1]
         hooks.append(_lib.Zone(ctx, a[2], a[3], a[4], numpy.ascontiguousarray(f[px]), numpy.ascontiguousarray(f[py]),
                                numpy.ascontiguousarray(f[pz]),
-                               numpy.ascontiguousarray(f[pc]) if pc != -1 else None))
+                               numpy.ascontiguousarray(f[pc]) if pc != -1 else None, interpDataType=ty))
     return hooks
 
 
@@ -81,8 +83,6 @@ def setInterpData__(interpPts, zonesD, order=2, penalty=1, extrap=1, nature=0, m
     for t in types:
         if t not in (0, 1):
             raise TypeError("setInterpData: InterpDataType must be 0 for CART or 1 for ADT.")
-        if t == 0:
-            raise NotImplementedError("setInterpData: interpDataType=0 (InterpCart) has no device path.")
     if len(zonesD) == 0:
         raise TypeError("setInterpData: no valid donor zone found.")
     ctx = ctx or _lib.default_context()
@@ -90,7 +90,7 @@ def setInterpData__(interpPts, zonesD, order=2, penalty=1, extrap=1, nature=0, m
     if px == -1 or py == -1 or pz == -1:
         raise TypeError("setInterpData: 1st arg must contain coordinates.")
     if hook is None:
-        zones = createHooks__(zonesD, ctx)
+        zones = createHooks__(zonesD, ctx, types)
     else:
         if not isinstance(hook, list):
             raise TypeError("setInterpData: hook must be a list of hooks.")

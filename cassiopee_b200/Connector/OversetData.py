@@ -320,14 +320,29 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
     else:
         allHooksL = [None] * len(zonesDnrL)
 
+    # interpDataType: 1 (ADT) or 0 (regular Cartesian donor, InterpCart), one value or one per donor zone of aD
+    # (OversetData.py:1214-1221: a scalar is broadcast).  A hook built by the caller carries its own type.
+    if isinstance(interpDataType, list):
+        if len(interpDataType) != len(zonesDnrL):
+            raise TypeError("setInterpData: size of interpDataType must be equal to the number of donor zones.")
+        typesL = list(interpDataType)
+    else:
+        typesL = [interpDataType] * len(zonesDnrL)
+    for ty in typesL:
+        if ty not in (0, 1):
+            raise TypeError("setInterpData: InterpDataType must be 0 for CART or 1 for ADT.")
+
     def hookOf(i):
         if allHooksL[i] is None:
             zd = zonesDnrL[i]
             _, ni_, nj_, nk_, _ = Internal.getZoneDim(zd)
             xd, yd, zzd = [a.reshape(-1, order='F') for a in C.getCoords(zd)]
             cd = C.getFieldArray(zd, 'cellN')
-            allHooksL[i] = backend.make_zone(ni_, nj_, nk_, xd, yd, zzd,
-                                             cd.reshape(-1, order='F') if cd is not None else None)
+            cdf = cd.reshape(-1, order='F') if cd is not None else None
+            if typesL[i] == 0:
+                allHooksL[i] = backend.make_zone(ni_, nj_, nk_, xd, yd, zzd, cdf, interpDataType=0)
+            else:
+                allHooksL[i] = backend.make_zone(ni_, nj_, nk_, xd, yd, zzd, cdf)
         return allHooksL[i]
 
     import os as _os, time as _time
@@ -372,12 +387,6 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
             # Etape 2: interpolation data on the device
             if sel.size == 0:
                 continue
-            types = interpDataType if isinstance(interpDataType, list) else [interpDataType] * nzonesDnr
-            for ty in types:
-                if ty not in (0, 1):
-                    raise TypeError("setInterpData: InterpDataType must be 0 for CART or 1 for ADT.")
-                if ty == 0:
-                    raise NotImplementedError("setInterpData: interpDataType=0 (InterpCart) has no device path.")
             f = interpPts[1]
             _t1 = _time.perf_counter()
             hooks_ = [hookOf(i) for i in idx]

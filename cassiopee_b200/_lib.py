@@ -42,6 +42,7 @@ _SIGS = {
     "cx_pinned_alloc": (_i, [_sz, _vp]),
     "cx_pinned_free": (_i, [_vp]),
     "cx_zone_create": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "cx_zone_create_cart": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "cx_zone_set_celln": (_i, [_vp, _vp]),
     "cx_zone_info": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "cx_zone_candidates": (_i, [_vp, _d, _d, _d, _d, _vp, _i, _vp]),
@@ -248,16 +249,22 @@ class Zone:
     """Donor zone resident on the device with its ADT replica (cx_zone) — the
     analogue of the reference's ``C.createHook(z, 'adt')``."""
 
-    def __init__(self, ctx, ni, nj, nk, x, y, z, cellN=None):
+    def __init__(self, ctx, ni, nj, nk, x, y, z, cellN=None, interpDataType=1):
+        """interpDataType 1: ADT replica (InterpAdt); 0: regular Cartesian donor located in closed form
+        (InterpCart, setInterpData.cpp:790-804) — no tree is built."""
         self.ctx = ctx
         self.ni, self.nj, self.nk = int(ni), int(nj), int(nk)
+        self.interpDataType = int(interpDataType)
         x, y, z = f64(x), f64(y), f64(z)
         n = self.ni * self.nj * self.nk
         if x.size != n or y.size != n or z.size != n:
             raise TypeError("setInterpData: 2nd argument is not valid.")
+        if self.interpDataType not in (0, 1):
+            raise TypeError("setInterpData: InterpDataType must be 0 for CART or 1 for ADT.")
         c = f64(cellN) if cellN is not None else None
         h = _vp()
-        check(lib().cx_zone_create(ctx.h, self.ni, self.nj, self.nk, ptr(x), ptr(y), ptr(z), ptr(c), ctypes.byref(h)))
+        create = lib().cx_zone_create if self.interpDataType == 1 else lib().cx_zone_create_cart
+        check(create(ctx.h, self.ni, self.nj, self.nk, ptr(x), ptr(y), ptr(z), ptr(c), ctypes.byref(h)))
         self.h = h
         self._fin = weakref.finalize(self, lib().cx_zone_destroy, h)
 
@@ -550,8 +557,8 @@ class DeviceBackend:
     def __init__(self, ctx=None):
         self.ctx = ctx or default_context()
 
-    def make_zone(self, ni, nj, nk, x, y, z, cellN=None):
-        return Zone(self.ctx, ni, nj, nk, x, y, z, cellN)
+    def make_zone(self, ni, nj, nk, x, y, z, cellN=None, interpDataType=1):
+        return Zone(self.ctx, ni, nj, nk, x, y, z, cellN, interpDataType)
 
     def set_celln(self, hook, cellN):
         hook.set_celln(cellN)

@@ -219,6 +219,7 @@ int cx_zone_create(cx_ctx* c, int ni, int nj, int nk, const double* x, const dou
   zn->ctx = c; zn->ni = ni; zn->nj = nj; zn->nk = nk;
   zn->npts = ni * nj * nk;
   zn->ncells = (ni - 1) * (nj - 1) * (nk - 1);
+  zn->topo = 1;
   size_t nb = sizeof(double) * (size_t)zn->npts;
   CX_CUDA(cudaMalloc(&zn->d_x, nb)); CX_CUDA(cudaMalloc(&zn->d_y, nb)); CX_CUDA(cudaMalloc(&zn->d_z, nb));
   CX_CUDA(cudaMalloc(&zn->d_cellN, nb));
@@ -229,6 +230,40 @@ int cx_zone_create(cx_ctx* c, int ni, int nj, int nk, const double* x, const dou
   *out = zn;
   int rc = cx_zone_set_celln(zn, cellN);
   if (rc == 0) rc = cx_build_adt(zn);
+  if (rc != 0) { cx_zone_destroy(zn); *out = nullptr; return rc; }
+  return 0;
+}
+
+// Regular Cartesian donor located in closed form (interpDataType=0): the analogue of
+// new K_INTERP::InterpCart(ni,nj,nk,hi,hj,hk,x0,y0,z0) in Connector/Connector/setInterpData.cpp:790-804
+// (spacings from the first nodes of each direction).  Coordinates and cellN are still resident: the
+// cell volume, the cellN tests and the extrapolation read them like the reference does.
+int cx_zone_create_cart(cx_ctx* c, int ni, int nj, int nk, const double* x, const double* y, const double* z,
+                        const double* cellN, cx_zone** out)
+{
+  if (ni < 2 || nj < 2 || nk < 2) { cx_set_error("Cartesian (InterpCart) donor zones must be 3D on the device path"); return -4; }
+  if ((long long)ni * nj * nk > 2000000000ll) { cx_set_error("donor zone too large for int32 indices"); return -1; }
+  CX_CUDA(cudaSetDevice(c->device));
+  cx_zone* zn = new cx_zone;
+  memset(zn, 0, sizeof(*zn));
+  zn->ctx = c; zn->ni = ni; zn->nj = nj; zn->nk = nk;
+  zn->npts = ni * nj * nk;
+  zn->ncells = (ni - 1) * (nj - 1) * (nk - 1);
+  zn->topo = 0;
+  zn->h[0] = x[1] - x[0]; zn->h[1] = y[ni] - y[0]; zn->h[2] = z[(size_t)ni * nj] - z[0];
+  zn->bbox[0] = x[0]; zn->bbox[1] = y[0]; zn->bbox[2] = z[0];
+  zn->bbox[3] = zn->bbox[0] + (ni - 1) * zn->h[0];
+  zn->bbox[4] = zn->bbox[1] + (nj - 1) * zn->h[1];
+  zn->bbox[5] = zn->bbox[2] + (nk - 1) * zn->h[2];
+  size_t nb = sizeof(double) * (size_t)zn->npts;
+  CX_CUDA(cudaMalloc(&zn->d_x, nb)); CX_CUDA(cudaMalloc(&zn->d_y, nb)); CX_CUDA(cudaMalloc(&zn->d_z, nb));
+  CX_CUDA(cudaMalloc(&zn->d_cellN, nb));
+  CX_CUDA(cudaMemcpyAsync(zn->d_x, x, nb, cudaMemcpyHostToDevice, c->stream));
+  CX_CUDA(cudaMemcpyAsync(zn->d_y, y, nb, cudaMemcpyHostToDevice, c->stream));
+  CX_CUDA(cudaMemcpyAsync(zn->d_z, z, nb, cudaMemcpyHostToDevice, c->stream));
+  *out = zn;
+  int rc = cx_zone_set_celln(zn, cellN);
+  if (rc == 0 && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = -2;
   if (rc != 0) { cx_zone_destroy(zn); *out = nullptr; return rc; }
   return 0;
 }
@@ -262,6 +297,13 @@ static ZoneView make_view(const cx_zone* zn)
   V.x = zn->d_x; V.y = zn->d_y; V.z = zn->d_z; V.cellN = zn->d_cellN; V.nodes = zn->d_nodes;
   V.ni = zn->ni; V.nj = zn->nj; V.nk = zn->nk; V.ncells = zn->ncells; V.depth = zn->depth;
   for (int i = 0; i < 6; i++) V.bbox[i] = zn->bbox[i];
+  V.topo = zn->topo;
+  for (int i = 0; i < 3; i++)
+  {
+    V.h[i] = zn->h[i];
+    V.hinv[i] = zn->topo == 0 ? 1.0 / zn->h[i] : 0.;     // InterpCart.cpp:51-56
+    V.hs2[i] = 0.5 * zn->h[i];
+  }
   return V;
 }
 
@@ -283,6 +325,7 @@ __global__ void k_candidates(ZoneView Z, double x, double y, double z, double al
 int cx_zone_candidates(cx_zone* zn, double x, double y, double z, double alphaTol, int* out, int cap, int* n)
 {
   cx_ctx* c = zn->ctx;
+  if (zn->topo == 0) { cx_set_error("candidate lists are an ADT query; this zone is a Cartesian (InterpCart) donor"); return -1; }
   int *d_out, *d_n;
   CX_CUDA(cudaMalloc(&d_out, sizeof(int) * (size_t)std::max(cap, 1)));
   CX_CUDA(cudaMalloc(&d_n, sizeof(int)));
@@ -298,6 +341,7 @@ int cx_zone_candidates(cx_zone* zn, double x, double y, double z, double alphaTo
 
 int cx_zone_export_adt(cx_zone* zn, void* nodes_out, size_t bytes)
 {
+  if (zn->topo == 0) { cx_set_error("Cartesian (InterpCart) donor zones have no ADT"); return -1; }
   size_t need = sizeof(AdtNode) * (size_t)zn->ncells;
   if (bytes < need) { cx_set_error("export buffer too small: need %zu bytes", need); return -1; }
   CX_CUDA(cudaMemcpy(nodes_out, zn->d_nodes, need, cudaMemcpyDeviceToHost));
@@ -323,7 +367,7 @@ int cx_set_interp_data_dev(cx_ctx* c, int nrcv, const double* d_xr, const double
   std::vector<ZoneView> hv(nz);
   for (int i = 0; i < nz; i++)
   {
-    if (!zones[i] || !zones[i]->d_nodes) { cx_set_error("setInterpData: donor zone %d has no ADT", i); return -1; }
+    if (!zones[i] || (zones[i]->topo != 0 && !zones[i]->d_nodes)) { cx_set_error("setInterpData: donor zone %d has no ADT", i); return -1; }
     hv[i] = make_view(zones[i]);
   }
   ZoneView* d_zones;

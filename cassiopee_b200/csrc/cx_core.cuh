@@ -63,7 +63,11 @@ struct ZoneView {      // device view of one donor zone
   int ni, nj, nk;
   int ncells;
   int depth;           // max node depth (stack bound)
-  double bbox[6];      // xmin,ymin,zmin,xmax,ymax,zmax (boundary-cell bbox)
+  double bbox[6];      // xmin,ymin,zmin,xmax,ymax,zmax (boundary-cell bbox; InterpCart: first point .. first + (n-1)*h)
+  // topo 1: ADT (InterpAdt), topo 0: regular Cartesian donor located in closed form (InterpCart,
+  // KCore/KCore/Interp/InterpCart.cpp:42-66): h = spacing, hinv = 1/h, hs2 = h/2; origin and end = bbox
+  int topo;
+  double h[3], hinv[3], hs2[3];
 };
 
 // double -> int conversion with x86 cvttsd2si semantics (out of range / NaN ->
@@ -444,6 +448,126 @@ CX_DN int search_interp_cell(const ZoneView& Z, double x, double y, double z,
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Regular Cartesian donors (interpDataType=0, K_INTERP::InterpCart): no tree, the cell comes from
+// the point's offset to the first node.  Offsets (_ioff,_joff,_koff) are 1 for zones built by
+// setInterpData (setInterpData.cpp:790-804: InterpCart(ni,nj,nk,hi,hj,hk,x0,y0,z0)).
+// ---------------------------------------------------------------------------
+CX_D bool cart_outside(const ZoneView& Z, double x, double y, double z)
+{ // InterpCart.cpp:76-82
+  const double EPS = CX_EPS_GEOM;
+  return (x < Z.bbox[0] - EPS) || (x > Z.bbox[3] + EPS) || (y < Z.bbox[1] - EPS) || (y > Z.bbox[4] + EPS) ||
+         (z < Z.bbox[2] - EPS) || (z > Z.bbox[5] + EPS);
+}
+
+// InterpCart::searchInterpolationCellCartO2 (InterpCart.cpp:71-125): trilinear weights, (ic,jc,kc) 1-based
+CX_D int cart_search_o2(const ZoneView& Z, double x, double y, double z, int& ic, int& jc, int& kc, double* cf)
+{
+  if (cart_outside(Z, x, y, z)) return 0;
+  const double xmin = Z.bbox[0], ymin = Z.bbox[1], zmin = Z.bbox[2];
+  ic = trunc_int((x - xmin) * Z.hinv[0]) + 1;
+  jc = trunc_int((y - ymin) * Z.hinv[1]) + 1;
+  kc = trunc_int((z - zmin) * Z.hinv[2]) + 1;
+  ic = imin(ic, Z.ni - 1); ic = imax(ic, 1);
+  jc = imin(jc, Z.nj - 1); jc = imax(jc, 1);
+  kc = imin(kc, Z.nk - 1); kc = imax(kc, 1);
+  double x0 = xmin + (ic - 1) * Z.h[0];
+  double y0 = ymin + (jc - 1) * Z.h[1];
+  double z0 = zmin + (kc - 1) * Z.h[2];
+  double x1 = (x - x0) * Z.hinv[0];
+  double x2 = (y - y0) * Z.hinv[1];
+  double x3 = (z - z0) * Z.hinv[2];
+  double t1 = (1. - x1), t2 = (1. - x2), t3 = (1. - x3);
+  double t1t2 = t1 * t2, x2t3 = x2 * t3, x1t2 = x1 * t2, x2x3 = x2 * x3;
+  cf[0] = t1t2 * t3;
+  cf[1] = x1t2 * t3;
+  cf[2] = t1 * x2t3;
+  cf[3] = x1 * x2t3;
+  if (Z.nk <= 2 && fabs(Z.bbox[5] - zmin) < CX_EPS_GEOM) { cf[4] = 0.; cf[5] = 0.; cf[6] = 0.; cf[7] = 0.; }
+  else
+  {
+    cf[4] = t1t2 * x3;
+    cf[5] = x1t2 * x3;
+    cf[6] = t1 * x2x3;
+    cf[7] = x1 * x2x3;
+  }
+  return 1;
+}
+
+// one direction of InterpCart::searchInterpolationCellCartO3 (InterpCart.cpp:151-266, 288-318):
+// 3-node stencil around the cell (shifted left unless the point is in the right half), 1-D Lagrange weights
+CX_D void cart_o3_dir(double x, double xmin, double h, double hs2, int n, int& ic, double* l)
+{
+  double x_i = xmin + (ic - 1) * h, x_ip = x_i + h;
+  double a, b, c;
+  int icHO;
+  if (x - x_i >= hs2)
+  {
+    if (ic >= n - 1) { icHO = ic - 1; a = x_i - h; b = x_i; c = x_ip; }
+    else { icHO = ic; a = x_i; b = x_ip; c = b + h; }
+  }
+  else
+  {
+    if (ic < 3) { icHO = ic; a = x_i; b = x_ip; c = b + h; }
+    else { icHO = ic - 1; a = x_i - h; b = x_i; c = x_ip; }
+  }
+  double hc = b - a, hcp = c - b, hcpp = c - a;
+  double inv_hc = 1. / hc, inv_hcp = 1. / hcp, inv_hcpp = 1. / hcpp;
+  l[0] = (x - b) * (x - c) * inv_hc * inv_hcpp;
+  l[1] = -(x - a) * (x - c) * inv_hc * inv_hcp;
+  l[2] = (x - a) * (x - b) * inv_hcp * inv_hcpp;
+  ic = icHO;
+}
+
+// InterpCart::searchInterpolationCellCartO3: cf[9] by direction, (ic,jc,kc) = 1-based start of the 3x3x3 stencil
+CX_D int cart_search_o3(const ZoneView& Z, double x, double y, double z, int& ic, int& jc, int& kc, double* cf)
+{
+  if (cart_outside(Z, x, y, z)) return 0;
+  const double xmin = Z.bbox[0], ymin = Z.bbox[1], zmin = Z.bbox[2];
+  ic = trunc_int((x - xmin) * Z.hinv[0]) + 1;
+  jc = trunc_int((y - ymin) * Z.hinv[1]) + 1;
+  kc = trunc_int((z - zmin) * Z.hinv[2]) + 1;
+  ic = imax(ic, 1); ic = imin(ic, Z.ni - 1);
+  jc = imax(jc, 1); jc = imin(jc, Z.nj - 1);
+  kc = imax(kc, 1); kc = imin(kc, Z.nk - 1);
+  cart_o3_dir(x, xmin, Z.h[0], Z.hs2[0], Z.ni, ic, cf);
+  cart_o3_dir(y, ymin, Z.h[1], Z.hs2[1], Z.nj, jc, cf + 3);
+  cart_o3_dir(z, zmin, Z.h[2], Z.hs2[2], Z.nk, kc, cf + 6);
+  return 1;
+}
+
+// InterpCart::getListOfCandidateCells (InterpCart.cpp:423-474): the box of cells within 0.1*alphaTol*h of the
+// point, enumerated k-outer / i-inner.  Returns the number of candidates (0: outside) and the 1-based bounds.
+CX_D int cart_candidate_box(const ZoneView& Z, double x, double y, double z, double alphaTol, int* lo, int* hi)
+{
+  const double dx = 0.1 * alphaTol * Z.h[0], dy = 0.1 * alphaTol * Z.h[1], dz = 0.1 * alphaTol * Z.h[2];
+  const double xmin = Z.bbox[0], ymin = Z.bbox[1], zmin = Z.bbox[2];
+  if (x < xmin - dx) return 0;
+  if (y < ymin - dy) return 0;
+  if (Z.nk > 1 && z < zmin - dz) return 0;
+  if (x > Z.bbox[3] + dx) return 0;
+  if (y > Z.bbox[4] + dy) return 0;
+  if (Z.nk > 1 && z > Z.bbox[5] + dz) return 0;
+  double x0 = x - dx, x1 = x + dx, y0 = y - dy, y1 = y + dy, z0 = z - dz, z1 = z + dz;
+  int icmin = trunc_int((x0 - xmin) * Z.hinv[0]) + 1, jcmin = trunc_int((y0 - ymin) * Z.hinv[1]) + 1;
+  int kcmin = trunc_int((z0 - zmin) * Z.hinv[2]) + 1;
+  int icmax = trunc_int((x1 - xmin) * Z.hinv[0]) + 1, jcmax = trunc_int((y1 - ymin) * Z.hinv[1]) + 1;
+  int kcmax = trunc_int((z1 - zmin) * Z.hinv[2]) + 1;
+  if (icmin < 1 && icmax < 1) return 0;
+  if (jcmin < 1 && jcmax < 1) return 0;
+  if (kcmin < 1 && kcmax < 1) return 0;
+  if (icmin > Z.ni && icmax > Z.ni) return 0;
+  if (jcmin > Z.nj && jcmax > Z.nj) return 0;
+  if (kcmin > Z.nk && kcmax > Z.nk) return 0;
+  icmin = imin(Z.ni - 1, icmin); icmin = imax(1, icmin); icmax = imin(Z.ni - 1, icmax); icmax = imax(1, icmax);
+  jcmin = imin(Z.nj - 1, jcmin); jcmin = imax(1, jcmin); jcmax = imin(Z.nj - 1, jcmax); jcmax = imax(1, jcmax);
+  kcmin = imin(Z.nk - 1, kcmin); kcmin = imax(1, kcmin); kcmax = imin(Z.nk - 1, kcmax); kcmax = imax(1, kcmax);
+  lo[0] = icmin; lo[1] = jcmin; lo[2] = kcmin; hi[0] = icmax; hi[1] = jcmax; hi[2] = kcmax;
+  int ni_ = icmax - icmin + 1, nj_ = jcmax - jcmin + 1, nk_ = kcmax - kcmin + 1;
+  if (ni_ <= 0 || nj_ <= 0 || nk_ <= 0) return 0;
+  return ni_ * nj_ * nk_;
+}
+
 // cellN validity of an order-2 stencil (Interp2.cpp:269-298)
 CX_D bool celln_valid_o2(const ZoneView& Z, int ic, int jc, int kc, const double* cf, int nature)
 {
@@ -575,6 +699,33 @@ CX_DN int search_extrap_cell(const ZoneView& Z, double x, double y, double z, in
 {
   for (int i = 0; i < 8; i++) cf[i] = 0.;
   double alphaTol = fmax((2 * constraint - 5.) * 0.1, 0.);
+  if (Z.topo == 0)
+  {
+    // InterpCart::searchExtrapolationCellCart (InterpCart.cpp:478-571), extrapOrder=1: same fold over the box
+    int lo[3], hi[3];
+    if (cart_candidate_box(Z, x, y, z, alphaTol, lo, hi) == 0) return 0;
+    double saved_sum = CX_MAXF, saved_diff = CX_MAXF, diff = CX_MAXF;
+    int found = 0, icsav = 0, jcsav = 0, kcsav = 0, ncand = 0;
+    double cfs[8], cft[8];
+    for (int i = 0; i < 8; i++) { cfs[i] = 0.; cft[i] = 0.; }
+    for (int k = lo[2]; k <= hi[2]; k++) for (int j = lo[1]; j <= hi[1]; j++) for (int i = lo[0]; i <= hi[0]; i++)
+    {
+      ncand++;
+      int ret = extrap_coeff_for_cell(Z, x, y, z, i, j, k, cft, nature, constraint, diff);
+      double s = fabs(cft[0]) + fabs(cft[1]) + fabs(cft[2]) + fabs(cft[3]) +
+                 fabs(cft[4]) + fabs(cft[5]) + fabs(cft[6]) + fabs(cft[7]);
+      if (ret == 1 && s < saved_sum + 1.e-6 && diff < saved_diff)
+      {
+        saved_diff = diff; found = 1; saved_sum = s;
+        icsav = i; jcsav = j; kcsav = k;
+        for (int m = 0; m < 8; m++) cfs[m] = cft[m];
+      }
+    }
+    if (st) st->ncand += ncand;
+    ic = icsav; jc = jcsav; kc = kcsav;
+    for (int m = 0; m < 8; m++) cf[m] = cfs[m];
+    return found;
+  }
   if (zone_reject(Z, x, y, z, alphaTol)) return 0;
   AdtQuery q;
   query_init(q, Z, x, y, z, alphaTol);
@@ -640,7 +791,8 @@ CX_D void interp_o2_receptor(double x, double y, double z, int nz, const ZoneVie
   {
     const ZoneView& Z = zones[noz];
     int ic, jc, kc;
-    int found = search_interp_cell(Z, x, y, z, ic, jc, kc, tcf, st);
+    int found = (Z.topo == 0) ? cart_search_o2(Z, x, y, z, ic, jc, kc, tcf)
+                              : search_interp_cell(Z, x, y, z, ic, jc, kc, tcf, st);
     if (found < 1) continue;
     ic -= 1; jc -= 1; kc -= 1;
     int isBorder = (ic == 0 || ic == Z.ni - 2 || jc == 0 || jc == Z.nj - 2 || kc == 0 || kc == Z.nk - 2);

@@ -50,6 +50,8 @@ struct cx_zone {
   int levels;
   double bbox[6];
   float build_ms;
+  int topo;           // 1: ADT donor, 0: regular Cartesian donor (InterpCart), no tree
+  double h[3];        // topo 0: spacings
 };
 
 struct cx_result {

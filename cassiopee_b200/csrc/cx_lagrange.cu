@@ -66,13 +66,30 @@ k_lag_search(LagState S, const double* __restrict__ xr, const double* __restrict
   // Interp2.cpp:347-351 / :455-459: zones too thin for the stencil return -1
   if (!(Z.ni < order || Z.nj < order || Z.nk < order))
   {
-    found = search_interp_cell(Z, xr[r], yr[r], zr[r], ic, jc, kc, cf, &st);
-    if (found == 1)
-      for (int k = 0; k < 8; k++) S.tcf[(size_t)k * S.n + r] = cf[k];
+    if (Z.topo == 0)
+    {
+      // Cartesian donor (Interp2.cpp:384-393): order 3 has closed-form direction weights (no polynomial solve);
+      // order 5 is not implemented by the reference for Cartesian InterpData (Interp2.cpp:464-467: returns -1)
+      if (order == 3)
+      {
+        double c9[9];
+        if (cart_search_o3(Z, xr[r], yr[r], zr[r], ic, jc, kc, c9) == 1)
+        {
+          found = 2;                  // final coefficients: skip the solve, k_lag_finish only tests and ranks
+          for (int k = 0; k < 9; k++) S.tcf[(size_t)k * S.n + r] = c9[k];
+        }
+      }
+    }
+    else
+    {
+      found = search_interp_cell(Z, xr[r], yr[r], zr[r], ic, jc, kc, cf, &st);
+      if (found == 1)
+        for (int k = 0; k < 8; k++) S.tcf[(size_t)k * S.n + r] = cf[k];
+    }
   }
   S.found[r] = found;
   S.ijk[r] = ic; S.ijk[(size_t)S.n + r] = jc; S.ijk[2 * (size_t)S.n + r] = kc;
-  flags[r] = found ? 1ull : 0ull;
+  flags[r] = (found == 1) ? 1ull : 0ull;
   if (gstats && st.nvisit) atomicAdd(&gstats[0], (unsigned long long)st.nvisit);
 }
 
@@ -472,6 +489,26 @@ k_lag_finish(LagState S, const ZoneView* __restrict__ zones, int noz, int order,
 {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= S.n) return;
+  if (S.found[r] == 2)
+  {
+    // Cartesian donor, order 3 (Interp2.cpp:386-392): stencil start and weights come from the search
+    const ZoneView& Z = zones[noz];
+    const size_t n = S.n;
+    const int ic = S.ijk[r] - 1, jc = S.ijk[n + r] - 1, kc = S.ijk[2 * n + r] - 1;
+    const int tind = ic + jc * Z.ni + kc * Z.ni * Z.nj;
+    const int isBorder = (ic == 0 || ic == Z.ni - 3 || jc == 0 || jc == Z.nj - 3 || kc == 0 || kc == Z.nk - 3);
+    double cf[9];
+    for (int k = 0; k < 9; k++) cf[k] = S.tcf[(size_t)k * n + r];
+    if (!celln_valid_lag(Z, 3, ic, jc, kc, cf, nature)) return;
+    double vol = cell_volume(Z, tind);
+    if (penalty == 1 && isBorder == 1) vol += 1.e3;
+    if (vol < S.best[r] + CX_EPS_GEOM)
+    {
+      S.best[r] = vol; S.type[r] = 3; S.dind[r] = tind; S.noblk[r] = noz + 1;
+      for (int k = 0; k < S.ncfmax; k++) S.cf[(size_t)k * n + r] = k < 9 ? cf[k] : 0.;
+    }
+    return;
+  }
   if (S.found[r] != 1) return;
   const ZoneView& Z = zones[noz];
   const size_t n = S.n;
@@ -566,7 +603,6 @@ int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_xr, cons
                          int nz, const ZoneView* d_zones, const ZoneView* h_zones, int nature, int penalty, int* noblk,
                          int* type, int* dind, double* cf, int ncfmax, unsigned long long* d_stats)
 {
-  (void)h_zones;
   cudaStream_t s = ctx->stream;
   LagState S;
   size_t N = n;
@@ -595,14 +631,17 @@ int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_xr, cons
     unsigned long long tot = 0;
     CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, n, &tot));
     int nlist = (int)tot;
-    if (nlist == 0) continue;
-    k_list<<<cx_grid(n, 256), 256, 0, s>>>(n, d_f, d_p, d_list);
-    if (order == 3)
-      k_lag_solve3<<<cx_grid(nlist, 4), 128, smem3, s>>>(S, nlist, d_list, d_xr, d_yr, d_zr, d_zones, noz);
-    else
+    if (nlist == 0 && h_zones[noz].topo != 0) continue;
+    if (nlist > 0)
     {
-      int grid = nlist < ctx->sm_count * 4 ? nlist : ctx->sm_count * 4;
-      k_lag_solve5<<<grid, 512, smem5, s>>>(S, nlist, d_list, d_xr, d_yr, d_zr, d_zones, noz);
+      k_list<<<cx_grid(n, 256), 256, 0, s>>>(n, d_f, d_p, d_list);
+      if (order == 3)
+        k_lag_solve3<<<cx_grid(nlist, 4), 128, smem3, s>>>(S, nlist, d_list, d_xr, d_yr, d_zr, d_zones, noz);
+      else
+      {
+        int grid = nlist < ctx->sm_count * 4 ? nlist : ctx->sm_count * 4;
+        k_lag_solve5<<<grid, 512, smem5, s>>>(S, nlist, d_list, d_xr, d_yr, d_zr, d_zones, noz);
+      }
     }
     k_lag_finish<<<cx_grid(n, TB), TB, 0, s>>>(S, d_zones, noz, order, nature, penalty);
     ctx->launches += 3;

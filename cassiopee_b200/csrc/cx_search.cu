@@ -67,9 +67,18 @@ __device__ __forceinline__ int search_extrap_cell_warp(const ZoneView& Z, double
 {
   for (int i = 0; i < 8; i++) cf[i] = 0.;
   double alphaTol = fmax((2 * constraint - 5.) * 0.1, 0.);
-  if (zone_reject(Z, x, y, z, alphaTol)) return 0;
+  const bool cart = Z.topo == 0;
+  // Cartesian donor (InterpCart::searchExtrapolationCellCart): the candidates are the cells of a small box
+  // around the point, k-outer / i-inner, handed to the lanes in that order, 32 at a time
+  int clo[3] = {0, 0, 0}, chi[3] = {0, 0, 0}, ctotal = 0, cbase = 0;
+  if (cart)
+  {
+    ctotal = cart_candidate_box(Z, x, y, z, alphaTol, clo, chi);
+    if (ctotal == 0) return 0;
+  }
+  else if (zone_reject(Z, x, y, z, alphaTol)) return 0;
   AdtQuery q;
-  if (lane == 0) query_init(q, Z, x, y, z, alphaTol);
+  if (!cart && lane == 0) query_init(q, Z, x, y, z, alphaTol);
   const int ni = Z.ni, nij = Z.ni * Z.nj;
   double saved_sum = CX_MAXF, saved_diff = CX_MAXF;
   int found = 0, icsav = 0, jcsav = 0, kcsav = 0, ncand = 0;
@@ -79,7 +88,12 @@ __device__ __forceinline__ int search_extrap_cell_warp(const ZoneView& Z, double
   while (!done)
   {
     int cnt = 0;
-    if (lane == 0)
+    if (cart)
+    {
+      cnt = ctotal - cbase < 32 ? ctotal - cbase : 32;
+      if (cbase + cnt >= ctotal) cnt |= 0x100;
+    }
+    else if (lane == 0)
     {
       int c, nid, nvisit = 0;
       while (cnt < 32 && (c = query_next(q, Z.nodes, &nid, &nvisit)) >= 0) s_cand[cnt++] = c;
@@ -95,8 +109,18 @@ __device__ __forceinline__ int search_extrap_cell_warp(const ZoneView& Z, double
     double sum = 0., diff = CX_MAXF, cft[8];
     if (lane < cnt)
     {
-      int c = s_cand[lane];
-      k = c / nij; j = (c - k * nij) / ni; i = c - j * ni - k * nij;
+      if (cart)
+      {
+        const int bi = chi[0] - clo[0] + 1, bj = chi[1] - clo[1] + 1;
+        const int c = cbase + lane;
+        k = c / (bi * bj); j = (c - k * bi * bj) / bi; i = c - j * bi - k * bi * bj;
+        i += clo[0] - 1; j += clo[1] - 1; k += clo[2] - 1;
+      }
+      else
+      {
+        int c = s_cand[lane];
+        k = c / nij; j = (c - k * nij) / ni; i = c - j * ni - k * nij;
+      }
       k++; j++; i++;
       ret = extrap_coeff_for_cell(Z, x, y, z, i, j, k, cft, nature, constraint, diff);
       sum = fabs(cft[0]) + fabs(cft[1]) + fabs(cft[2]) + fabs(cft[3]) + fabs(cft[4]) + fabs(cft[5]) + fabs(cft[6]) +
@@ -116,6 +140,7 @@ __device__ __forceinline__ int search_extrap_cell_warp(const ZoneView& Z, double
         for (int m = 0; m < 8; m++) cfs[m] = __shfl_sync(0xffffffffu, cft[m], l);
       }
     }
+    cbase += cnt;
   }
   if (st && lane == 0) st->ncand += ncand;
   if (ncand == 0) return 0;

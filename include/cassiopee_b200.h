@@ -63,6 +63,12 @@ int cx_pinned_free(void* hptr);
  * (all 1, as OversetData.py:1193 _addCellN__ does).  3-D zones only (nk>1). */
 int cx_zone_create(cx_ctx* ctx, int ni, int nj, int nk, const double* x, const double* y, const double* z,
                    const double* cellN, cx_zone** out);
+/* Regular Cartesian donor, interpDataType=0: replaces new K_INTERP::InterpCart(ni,nj,nk,hi,hj,hk,x0,y0,z0)
+ * (setInterpData.cpp:790-804; KCore/KCore/Interp/InterpCart.cpp:42-66).  No tree: cells are located in closed
+ * form (searchInterpolationCellCartO2/O3, InterpCart.cpp:71-318; searchExtrapolationCellCart :478-571).
+ * Like the reference, order 5 finds nothing in such a donor (Interp2.cpp:464-467). */
+int cx_zone_create_cart(cx_ctx* ctx, int ni, int nj, int nk, const double* x, const double* y, const double* z,
+                        const double* cellN, cx_zone** out);
 int cx_zone_set_celln(cx_zone* zone, const double* cellN);
 int cx_zone_info(cx_zone* zone, double bbox[6], int* ncells, int* depth, float* build_ms);
 /* test/debug: candidate cells of one point in the reference's list order

@@ -96,14 +96,16 @@ class RefZone:
     """Donor zone held by the reference code: coordinates, cellN and its ADT
     (InterpAdt::buildStructAdt, KCore/KCore/Interp/InterpAdt.cpp:284-433)."""
 
-    def __init__(self, ni, nj, nk, x, y, z, cellN=None):
+    def __init__(self, ni, nj, nk, x, y, z, cellN=None, interpDataType=1):
+        """interpDataType 1: InterpAdt; 0: InterpCart built like setInterpData.cpp:790-804."""
         self.ni, self.nj, self.nk = int(ni), int(nj), int(nk)
         self._x, self._y, self._z = _f64(x), _f64(y), _f64(z)
         n = self.ni * self.nj * self.nk
         assert self._x.size == n
         self._c = _f64(cellN) if cellN is not None else None
         self.h = lib().ref_zone_create(self.ni, self.nj, self.nk, self._x.ctypes.data, self._y.ctypes.data,
-                                       self._z.ctypes.data, self._c.ctypes.data if self._c is not None else None, 1)
+                                       self._z.ctypes.data, self._c.ctypes.data if self._c is not None else None,
+                                       1 if interpDataType == 1 else 2)
         if not lib().ref_zone_has_adt(self.h):
             raise RuntimeError("reference ADT build failed")
 

@@ -29,6 +29,7 @@
 #include <cstring>
 #include <omp.h>
 #include "Interp/Interp.h"
+#include "Interp/InterpCart.h"
 #include "Metric/metric.h"
 #include "CompGeom/compGeom.h"
 #include "parallel.h"
@@ -56,6 +57,8 @@ struct RefZone
   E_Int ni, nj, nk;
   FldArrayF* f;  // (npts, 4): x, y, z, cellN
   K_INTERP::InterpAdt* adt;
+  K_INTERP::InterpCart* cart;   // interpDataType 0 (setInterpData.cpp:790-804)
+  K_INTERP::InterpData* data() { return adt ? (K_INTERP::InterpData*)adt : (K_INTERP::InterpData*)cart; }
 };
 
 extern "C" {
@@ -76,8 +79,18 @@ void* ref_zone_create(int ni, int nj, int nk, const double* x, const double* y,
   memcpy(zn->f->begin(3), z, sizeof(double) * npts);
   if (cellN) memcpy(zn->f->begin(4), cellN, sizeof(double) * npts);
   else for (E_Int i = 0; i < npts; i++) (*zn->f)(i, 4) = 1.;
-  zn->adt = NULL;
-  if (buildAdt)
+  zn->adt = NULL; zn->cart = NULL;
+  if (buildAdt == 2)
+  {
+    /* CART branch of setInterpData.cpp:790-804, verbatim arithmetic */
+    E_Float* xt = zn->f->begin(1); E_Float* yt = zn->f->begin(2); E_Float* zt = zn->f->begin(3);
+    E_Float x0 = xt[0]; E_Float y0 = yt[0]; E_Float z0 = zt[0];
+    E_Float hi = xt[1]-xt[0];
+    E_Float hj = yt[ni]-yt[0];
+    E_Float hk = zt[ni*nj]-zt[0];
+    zn->cart = new K_INTERP::InterpCart(ni,nj,nk,hi,hj,hk,x0,y0,z0);
+  }
+  else if (buildAdt)
   {
     E_Int built = 0;
     zn->adt = new K_INTERP::InterpAdt(npts, zn->f->begin(1), zn->f->begin(2),
@@ -88,19 +101,20 @@ void* ref_zone_create(int ni, int nj, int nk, const double* x, const double* y,
   return zn;
 }
 
-int ref_zone_has_adt(void* h) { return ((RefZone*)h)->adt != NULL; }
+int ref_zone_has_adt(void* h) { return ((RefZone*)h)->data() != NULL; }
 
 void ref_zone_free(void* h)
 {
   RefZone* zn = (RefZone*)h;
   if (zn->adt) delete zn->adt;
+  if (zn->cart) delete zn->cart;
   delete zn->f;
   delete zn;
 }
 
 void ref_zone_bbox(void* h, double* bb)
 {
-  K_INTERP::InterpAdt* a = ((RefZone*)h)->adt;
+  K_INTERP::InterpData* a = ((RefZone*)h)->data();
   bb[0] = a->_xmin; bb[1] = a->_ymin; bb[2] = a->_zmin;
   bb[3] = a->_xmax; bb[4] = a->_ymax; bb[5] = a->_zmax;
 }
@@ -149,8 +163,8 @@ int ref_set_interp_data(int nrcv, const double* xr, const double* yr,
   for (int i = 0; i < nz; i++)
   {
     RefZone* zn = (RefZone*)zones[i];
-    if (!zn->adt) return -1;
-    interpDatas.push_back(zn->adt);
+    if (!zn->data()) return -1;
+    interpDatas.push_back(zn->data());
     fields.push_back(zn->f);
     a2.push_back(&zn->ni); a3.push_back(&zn->nj); a4.push_back(&zn->nk);
     a5.push_back(NULL);

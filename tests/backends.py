@@ -16,9 +16,9 @@ class OraclePlan:
 
 
 class OracleBackend:
-    def make_zone(self, ni, nj, nk, x, y, z, cellN=None):
+    def make_zone(self, ni, nj, nk, x, y, z, cellN=None, interpDataType=1):
         from oracle import oracle as O
-        return O.RefZone(ni, nj, nk, x, y, z, cellN)
+        return O.RefZone(ni, nj, nk, x, y, z, cellN, interpDataType=interpDataType)
 
     def set_celln(self, hook, cellN):
         pass

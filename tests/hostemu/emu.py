@@ -19,6 +19,9 @@ def lib():
         L = ctypes.CDLL(_SO)
         L.emu_zone_create.restype = ctypes.c_void_p
         L.emu_zone_create.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 5
+        L.emu_zone_create_cart.restype = ctypes.c_void_p
+        L.emu_zone_create_cart.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 4
+        L.emu_cart_o3.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 6
         L.emu_zone_free.argtypes = [ctypes.c_void_p]
         L.emu_zone_depth.argtypes = [ctypes.c_void_p]
         L.emu_candidates.argtypes = [ctypes.c_void_p] + [ctypes.c_double] * 4 + [ctypes.c_void_p, ctypes.c_int]
@@ -42,10 +45,14 @@ def zone_bbox(ni, nj, nk, x, y, z):
 
 
 class EmuZone:
-    def __init__(self, ni, nj, nk, x, y, z, cellN=None):
+    def __init__(self, ni, nj, nk, x, y, z, cellN=None, interpDataType=1):
         self.x = np.ascontiguousarray(x, np.float64).reshape(-1); self.y = np.ascontiguousarray(y, np.float64).reshape(-1)
         self.z = np.ascontiguousarray(z, np.float64).reshape(-1)
         self.c = np.ascontiguousarray(cellN, np.float64).reshape(-1) if cellN is not None else None
+        if interpDataType == 0:
+            self.h = lib().emu_zone_create_cart(ni, nj, nk, self.x.ctypes.data, self.y.ctypes.data, self.z.ctypes.data,
+                                                self.c.ctypes.data if self.c is not None else None)
+            return
         self.bb = zone_bbox(ni, nj, nk, self.x, self.y, self.z)
         self.h = lib().emu_zone_create(ni, nj, nk, self.x.ctypes.data, self.y.ctypes.data, self.z.ctypes.data,
                                        self.c.ctypes.data if self.c is not None else None, self.bb.ctypes.data)
@@ -64,6 +71,16 @@ class EmuZone:
     def __del__(self):
         try: lib().emu_zone_free(self.h)
         except Exception: pass
+
+
+def cart_o3(zone, xr, yr, zr):
+    xr = np.ascontiguousarray(xr, np.float64).reshape(-1); yr = np.ascontiguousarray(yr, np.float64).reshape(-1)
+    zr = np.ascontiguousarray(zr, np.float64).reshape(-1)
+    n = xr.size
+    found = np.zeros(n, np.int32); dind = np.zeros(n, np.int32); cf = np.zeros((n, 9))
+    lib().emu_cart_o3(zone.h, n, xr.ctypes.data, yr.ctypes.data, zr.ctypes.data, found.ctypes.data, dind.ctypes.data,
+                      cf.ctypes.data)
+    return found, dind, cf
 
 
 def set_interp_data_raw(xr, yr, zr, zones, nature=0, penalty=1, extrap=1):

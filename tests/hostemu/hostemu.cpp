@@ -11,6 +11,7 @@
 using namespace cx;
 
 struct EmuZone {
+  int topo = 1; double h[3] = {0., 0., 0.};
   int ni, nj, nk, npts, ncells, depth;
   std::vector<double> x, y, z, c;
   std::vector<AdtNode> nodes;
@@ -19,6 +20,8 @@ struct EmuZone {
     ZoneView V; V.x = x.data(); V.y = y.data(); V.z = z.data(); V.cellN = c.data(); V.nodes = nodes.data();
     V.ni = ni; V.nj = nj; V.nk = nk; V.ncells = ncells; V.depth = depth;
     for (int i = 0; i < 6; i++) V.bbox[i] = bbox[i];
+    V.topo = topo;
+    for (int i = 0; i < 3; i++) { V.h[i] = h[i]; V.hinv[i] = topo == 0 ? 1.0 / h[i] : 0.; V.hs2[i] = 0.5 * h[i]; }
     return V;
   }
 };
@@ -64,6 +67,34 @@ void* emu_zone_create(int ni, int nj, int nk, const double* x, const double* y, 
   for (int lv = depth - 1; lv >= 0; lv--)
     for (int c = 0; c < n; c++) if (dep[c] == lv) adt_subtree_box(B.nodes, c);
   return Z;
+}
+
+// regular Cartesian donor: same set-up arithmetic as cx_zone_create_cart (cx_api.cu)
+void* emu_zone_create_cart(int ni, int nj, int nk, const double* x, const double* y, const double* z, const double* cellN)
+{
+  EmuZone* Z = new EmuZone;
+  Z->ni = ni; Z->nj = nj; Z->nk = nk; Z->npts = ni * nj * nk; Z->ncells = (ni - 1) * (nj - 1) * (nk - 1); Z->depth = 0;
+  Z->x.assign(x, x + Z->npts); Z->y.assign(y, y + Z->npts); Z->z.assign(z, z + Z->npts);
+  if (cellN) Z->c.assign(cellN, cellN + Z->npts); else Z->c.assign(Z->npts, 1.0);
+  Z->topo = 0;
+  Z->h[0] = x[1] - x[0]; Z->h[1] = y[ni] - y[0]; Z->h[2] = z[(size_t)ni * nj] - z[0];
+  Z->bbox[0] = x[0]; Z->bbox[1] = y[0]; Z->bbox[2] = z[0];
+  Z->bbox[3] = Z->bbox[0] + (ni - 1) * Z->h[0];
+  Z->bbox[4] = Z->bbox[1] + (nj - 1) * Z->h[1];
+  Z->bbox[5] = Z->bbox[2] + (nk - 1) * Z->h[2];
+  return Z;
+}
+
+// InterpCart order 3 of one zone (the device does this in k_lag_search for topo 0)
+void emu_cart_o3(void* h, int n, const double* xr, const double* yr, const double* zr, int* found, int* dind, double* cf)
+{
+  ZoneView V = ((EmuZone*)h)->view();
+  for (int r = 0; r < n; r++)
+  {
+    int ic = 0, jc = 0, kc = 0;
+    found[r] = cart_search_o3(V, xr[r], yr[r], zr[r], ic, jc, kc, cf + (size_t)r * 9);
+    dind[r] = (ic - 1) + (jc - 1) * V.ni + (kc - 1) * V.ni * V.nj;
+  }
 }
 
 void emu_zone_free(void* h) { delete (EmuZone*)h; }

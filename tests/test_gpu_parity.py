@@ -12,21 +12,22 @@ from tests import cases
 pytestmark = pytest.mark.gpu
 
 
-def _zones(ctx, dz, cellNs=None):
+def _zones(ctx, dz, cellNs=None, types=None):
     from cassiopee_b200 import _lib
     from oracle import oracle as O
     gz, oz = [], []
     for i, (ni, nj, nk, x, y, z) in enumerate(dz):
         c = cellNs[i] if cellNs else None
-        gz.append(_lib.Zone(ctx, ni, nj, nk, x, y, z, c))
-        oz.append(O.RefZone(ni, nj, nk, x, y, z, c))
+        t = types[i] if types else 1
+        gz.append(_lib.Zone(ctx, ni, nj, nk, x, y, z, c, interpDataType=t))
+        oz.append(O.RefZone(ni, nj, nk, x, y, z, c, interpDataType=t))
     return gz, oz
 
 
-def _compare(ctx, dz, pts, order=2, nature=1, penalty=1, extrap=1, cellNs=None, rtol=0.0):
+def _compare(ctx, dz, pts, order=2, nature=1, penalty=1, extrap=1, cellNs=None, rtol=0.0, types=None):
     from cassiopee_b200 import _lib
     from oracle import oracle as O
-    gz, oz = _zones(ctx, dz, cellNs)
+    gz, oz = _zones(ctx, dz, cellNs, types)
     for g, o in zip(gz, oz):
         assert np.array_equal(g.info()["bbox"], o.bbox())
     res = _lib.set_interp_data(ctx, pts[0], pts[1], pts[2], gz, order, nature, penalty, extrap)
@@ -271,3 +272,59 @@ def test_transfer_synthetic_plans_staged_and_gather(ctx, dims, density):
             for d, b in zip(dR2, fRo):
                 assert np.array_equal(d.download(), b)
             assert np.array_equal(dense.download().reshape(nvars, n), O.transferD(fD, ni, nj, dnr, typ, cf))
+
+
+@pytest.mark.parametrize("order", [2, 3])
+def test_interpcart_donors(ctx, order):
+    """interpDataType=0 (regular Cartesian donors located in closed form, K_INTERP::InterpCart): single donor,
+    Cartesian + ADT donors mixed in both list orders, holes, nature/penalty, extrapolation and orphans."""
+    for variant in ("a", "b", "c"):
+        A, B = cases.c1(variant)
+        got, ref, _, _ = _compare(ctx, [A], B[3:], order=order, types=[0])
+        assert got[0][0].size == B[3].size
+        got, ref, _, _ = _compare(ctx, [B], A[3:], order=order, types=[0])
+        assert got[5].size > 0
+    Bg, Oc = cases.c2()
+    rng = np.random.default_rng(11)
+    cb = np.ones(Bg[3].size); cb[rng.random(cb.size) < 0.05] = 0.; cb[rng.random(cb.size) < 0.05] = 2.
+    co = np.ones(Oc[3].size); co[rng.random(co.size) < 0.05] = 0.; co[rng.random(co.size) < 0.05] = 2.
+    P = rng.uniform(-3.3, 3.3, (3, 20000)); P[2] = rng.uniform(-0.2, 2.2, 20000)
+    next_ = 0
+    for nature in (0, 1):
+        for penalty in (0, 1):
+            got, _, _, _ = _compare(ctx, [Bg], P, order, nature, penalty, 1, [cb], types=[0])
+            next_ += got[4][0].size
+            _compare(ctx, [Bg, Oc], P, order, nature, penalty, 1, [cb, co], types=[0, 1])
+            _compare(ctx, [Oc, Bg], P, order, nature, penalty, 0, [co, cb], types=[1, 0])
+    assert next_ > 0
+
+
+def test_interpcart_order5_falls_to_extrapolation(ctx):
+    """The reference has no order-5 search in a Cartesian InterpData (Interp2.cpp:464-467 returns -1): every
+    receptor goes through the order-2 extrapolation pass.  Small case (the reference prints one line per query)."""
+    A, B = cases.c1("c", n=13, m=7)
+    got, ref, _, _ = _compare(ctx, [A], B[3:], order=5, types=[0])
+    assert got[4][0].size == got[0][0].size and (got[2][0] == 2).all()
+
+
+def test_interpcart_pytree_api(ctx):
+    """X.setInterpData(..., interpDataType=0) through the tree layer, transfers of a linear field exact."""
+    import cassiopee_b200.Converter as C
+    import cassiopee_b200.Generator as G
+    import cassiopee_b200.Internal as Internal
+    import cassiopee_b200.Connector.PyTree as X
+    a = G.cart((0, 0, 0), (0.1, 0.1, 0.1), (11, 11, 11), name='A')
+    b = G.cart((0.23, 0.31, 0.17), (0.05, 0.05, 0.05), (9, 9, 9), name='B')
+    C._initVars(a, 'F', lambda x, y, z: x + 2 * y + 3 * z)
+    C._initVars(b, 'F', 0.)
+    C._initVars(b, 'cellN', 2.)
+    for order in (2, 3):
+        C._initVars(b, 'F', 0.)
+        tD = X.setInterpData(C.newPyTree(['R', b]), C.newPyTree(['D', a]), order=order, nature=1, loc='nodes',
+                             storage='inverse', interpDataType=0, itype='chimera', verbose=0)
+        s = Internal.getNodeFromName(tD, 'ID_B')
+        assert s is not None and (Internal.getNodeFromName1(s, 'InterpolantsType')[1] == order).all()
+        tR = X.setInterpTransfers(C.newPyTree(['R', b]), tD, variables=['F'], storage=1)
+        zb = Internal.getZones(tR)[0]
+        x, y, z = C.getCoords(zb)
+        assert np.abs(C.getFieldArray(zb, 'F') - (x + 2 * y + 3 * z)).max() < 1e-12

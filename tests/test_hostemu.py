@@ -65,3 +65,59 @@ def test_volume_matches():
     oz = O.RefZone(*Oc); ez = E.EmuZone(*Oc)
     for ind in (0, 5, 17 * 3 + 4, 17 * 7 * 2 + 17 * 2 + 3):
         assert oz.volume(ind) == ez.volume(ind)
+
+
+def _compare_types(dz, pts, types, nature=1, penalty=1, extrap=1, cellNs=None):
+    """Same as _compare with a per-zone interpDataType (0: InterpCart, 1: InterpAdt)."""
+    oz, ez = [], []
+    for i, z in enumerate(dz):
+        c = cellNs[i] if cellNs else None
+        oz.append(O.RefZone(*z, cellN=c, interpDataType=types[i])); ez.append(E.EmuZone(*z, cellN=c, interpDataType=types[i]))
+    ro = O.set_interp_data_raw(pts[0], pts[1], pts[2], oz, 2, nature, penalty, extrap)
+    re = E.set_interp_data_raw(pts[0], pts[1], pts[2], ez, nature, penalty, extrap)
+    for k in ("noblk", "type", "dind", "isext"):
+        assert np.array_equal(ro[k], re[k]), k
+    cfo = ro["cf"][:, :8].copy(); cfe = re["cf"].copy()
+    t1 = ro["type"] == 1
+    cfo[t1, 1:] = 0; cfe[t1, 1:] = 0
+    assert np.array_equal(cfo, cfe)
+    return ro
+
+
+def test_cartesian_donors_interpcart_order2_and_extrapolation():
+    """interpDataType=0: closed-form Cartesian donor search (InterpCart) — trilinear weights, cellN tests,
+    cross-zone choice against an ADT donor, extrapolation over the candidate box."""
+    for variant in ("a", "b", "c"):
+        A, B = cases.c1(variant, n=17, m=11)
+        r = _compare_types([A], B[3:], [0])
+        assert (r["noblk"] == 1).all()
+        r = _compare_types([B], A[3:], [0])
+        assert (r["noblk"] == 0).sum() > 0
+    Bg, Oc = cases.c2(nb=20, nc=(33, 9, 17))
+    rng = np.random.default_rng(1)
+    cb = np.ones(Bg[3].size); cb[rng.random(cb.size) < 0.05] = 0.; cb[rng.random(cb.size) < 0.05] = 2.
+    co = np.ones(Oc[3].size); co[rng.random(co.size) < 0.05] = 0.; co[rng.random(co.size) < 0.05] = 2.
+    P = rng.uniform(-3.3, 3.3, (3, 4000)); P[2] = rng.uniform(-0.2, 2.2, 4000)
+    next_ = 0
+    for nature in (0, 1):
+        for penalty in (0, 1):
+            r = _compare_types([Bg], P, [0], nature, penalty, 1, [cb])
+            next_ += int(r["isext"].sum())
+            _compare_types([Bg, Oc], P, [0, 1], nature, penalty, 1, [cb, co])
+            _compare_types([Oc, Bg], P, [1, 0], nature, penalty, 0, [co, cb])
+    assert next_ > 0
+
+
+def test_cartesian_donors_interpcart_order3_weights():
+    A, B = cases.c1("c", n=17, m=11)
+    rng = np.random.default_rng(2)
+    P = np.concatenate([np.array(B[3:]), rng.uniform(-0.05, 1.05, (3, 3000))], axis=1)
+    oz = O.RefZone(*A, interpDataType=0); ez = E.EmuZone(*A, interpDataType=0)
+    ro = O.set_interp_data_raw(P[0], P[1], P[2], [oz], 3, 1, 1, 0)
+    found, dind, cf = E.cart_o3(ez, P[0], P[1], P[2])
+    hit = ro["noblk"] == 1
+    assert np.array_equal(hit, found == 1) and hit.sum() > 1000 and (~hit).sum() > 100
+    t3 = hit & (ro["type"] == 3)
+    assert t3.sum() > 1000
+    assert np.array_equal(ro["dind"][t3], dind[t3])
+    assert np.array_equal(ro["cf"][t3][:, :9], cf[t3])
