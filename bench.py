@@ -234,6 +234,7 @@ def run_c2(args):
         # ---- CPU baseline: the reference's own transfer loops on the host cores ----
         cpu = cpu_baseline_transfer(fD, nrcv, Bg, rcv, dnr, typ, coefs, B, nvars)
 
+    extra = None if args.quick else extra_legs(ctx, Bg, Oc, zone, dxr, dyr, dzr, pD, nvars)
     peak, how = measured_peaks()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -257,8 +258,76 @@ def run_c2(args):
                      "frac_of_nominal_8TBps": value / 8000.0},
         "cpu_baseline": cpu,
         "set_interp_data": sid,
+        "other_configs": extra,
     }
     print(json.dumps(line))
+
+
+# GJ flop count of SURVEY.md 8(d) (full in-place inverse + 3 RHS, as the reference's kgaussj does)
+def gj_flops(n):
+    return n * (2 * (n + 3) * (n - 1) + (n + 3))
+
+
+def extra_legs(ctx, Bg, Oc, zone, dxr, dyr, dzr, pD, nvars):
+    """Device-resident timings of the other BASELINE configs on the C2a geometry (informational; parity for them
+    is in tests/): C3 = Lagrange order 3 (all receptors) and order 5 (every 16th receptor) + their transfers;
+    interpDataType=0 = the reference's closed-form path for Cartesian donors (InterpCart)."""
+    from cassiopee_b200 import _lib
+    out = {}
+    nrcv = Oc.npts
+    # --- InterpCart, order 2 and 3
+    t0 = time.perf_counter()
+    zc = _lib.Zone(ctx, Bg.ni, Bg.nj, Bg.nk, Bg.x, Bg.y, Bg.z, interpDataType=0)
+    ctx.sync()
+    t_zc = time.perf_counter() - t0
+    for order in (2, 3):
+        ms = []
+        for it in range(4):
+            ctx.sync(); t0 = time.perf_counter()
+            r = _lib.set_interp_data_dev(ctx, nrcv, dxr.ptr, dyr.ptr, dzr.ptr, [zc], order, 1, 1, 1)
+            ctx.sync()
+            if it > 0:
+                ms.append((time.perf_counter() - t0) * 1e3)
+            r = None
+        out["interpcart_order%d" % order] = {"value": nrcv / (np.mean(ms) * 1e-3), "unit": "receptor pts/s",
+                                              "ms": float(np.mean(ms)), "receptors": int(nrcv), "zone_create_s": t_zc}
+    del zc
+    # --- C3: Lagrange orders 3 and 5 through the ADT donor
+    for order, stride in ((3, 1), (5, 16)):
+        if stride == 1:
+            dx, dy, dz, n = dxr, dyr, dzr, nrcv
+        else:
+            dx = _lib.DeviceArray.from_host(ctx, np.ascontiguousarray(Oc.x[::stride]))
+            dy = _lib.DeviceArray.from_host(ctx, np.ascontiguousarray(Oc.y[::stride]))
+            dz = _lib.DeviceArray.from_host(ctx, np.ascontiguousarray(Oc.z[::stride]))
+            n = dx.n
+        ctx.sync(); t0 = time.perf_counter()
+        r = _lib.set_interp_data_dev(ctx, n, dx.ptr, dy.ptr, dz.ptr, [zone], order, 1, 1, 1)
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        o = r.fetch()
+        rcv, dnr, typ, cf = o[0][0], o[1][0], o[2][0], o[3][0]
+        r = None
+        plan = _lib.Plan(ctx, Bg.ni, Bg.nj, Bg.nk, n, dnr, rcv, typ, cf)
+        dR = [_lib.DeviceArray(ctx, n) for _ in range(nvars)]
+        pR = [d.ptr for d in dR]
+        for _ in range(3):
+            plan.transfer_dev(pD, pR)
+        ctx.sync(); ctx.event_record(0)
+        for _ in range(10):
+            plan.transfer_dev(pD, pR)
+        ctx.event_record(1)
+        tms = ctx.event_elapsed_ms() / 10
+        B = plan.alg_bytes(nvars)
+        out["lagrange_order%d" % order] = {
+            "set_interp_data": {"value": n / dt, "unit": "receptor pts/s", "ms": dt * 1e3, "receptors": int(n),
+                                "sample": "all O-grid nodes" if stride == 1 else "every %dth O-grid node" % stride,
+                                "gj_gflops_reference_count": gj_flops(order ** 3) * n / dt / 1e9,
+                                "types": {int(k): int(v) for k, v in zip(*np.unique(typ, return_counts=True))}},
+            "transfer": {"value": B / (tms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": tms, "alg_bytes_per_step": int(B),
+                         "nvars": nvars}}
+        del plan, dR
+    return out
 
 
 def cpu_baseline_transfer(fD, nrcv, Bg, rcv, dnr, typ, coefs, B, nvars, reps=2):
@@ -311,6 +380,26 @@ def run_reference(args):
                "adt_build_s": t_adt, "search_s": t_search, "cores": nthreads,
                "sample": "background coarsened to %d^3, every %dth O-grid receptor" % (nb, stride),
                "note": "hook=None semantics: serial ADT build inside (InterpAdt.cpp:284-433)"}
+        other = {}
+        try:
+            for order, st_ in ((3, 8), (5, 64)):
+                t0 = time.perf_counter()
+                O.set_interp_data(xr[::st_].copy(), yr[::st_].copy(), zr[::st_].copy(), [zone], order, 1, 1, 1)
+                dtl = time.perf_counter() - t0
+                nl = xr[::st_].size
+                other["lagrange_order%d" % order] = {"value": nl / dtl, "unit": "receptor pts/s", "receptors": int(nl),
+                                                     "s": dtl, "cores": nthreads,
+                                                     "sample": "every %dth O-grid node, background coarsened to %d^3, "
+                                                               "ADT build not included" % (stride * st_, nb)}
+            t0 = time.perf_counter()
+            zc = O.RefZone(Bg.ni, Bg.nj, Bg.nk, Bg.x, Bg.y, Bg.z, interpDataType=0)
+            O.set_interp_data(Oc.x, Oc.y, Oc.z, [zc], 2, 1, 1, 1)
+            dtc = time.perf_counter() - t0
+            other["interpcart_order2"] = {"value": Oc.npts / dtc, "unit": "receptor pts/s", "receptors": int(Oc.npts),
+                                          "s": dtc, "cores": nthreads, "sample": "full C2a, InterpCart donor (no tree)"}
+            del zc
+        except Exception as e:
+            other["unavailable"] = str(e)
         del zone, out
         # (2) the transfer loop on the FULL workload.  Its interpData is laid out like the real one (one type-2
         # entry per O-grid node, ascending receptor order, 8 coefficients) but the donor cell is located
@@ -372,6 +461,7 @@ def run_reference(args):
             "set_interp_data": sid, "gpu_launches": 0}
     if c4 is not None:
         line["c4_c5"] = c4
+    line["other_configs"] = other
     print(json.dumps(line))
 
 

@@ -209,6 +209,76 @@ def applyBCOverlaps(t, depth=2, loc='centers', val=2, cellNName='cellN'):
     return a
 
 
+def _holeFringeStruct__(cellN, depth, dir):
+    """connector._getOversetHolesInterpNodes on one structured cellN array (i fastest, shape (im,jm,km)):
+    searchMaskInterpolatedCellsStructOpt (Connector/Connector/getInterpolatedPoints.cpp:370-660).  A point with
+    cellN == 1 becomes 2 when a point of its stencil has cellN == 0.  dir=0: cross (+-1..depth along each axis,
+    indices clamped to the zone, :455-484); dir=1: star (the 26 directions, a component that leaves the zone
+    falls back to the point's own index, :582-640).  In place; evaluated on the input values (Jacobi)."""
+    if dir not in (0, 1):
+        raise NotImplementedError("setHoleInterpolatedPoints: dir=%d (diamond / octahedron stencils) is not available." % dir)
+    im, jm, km = cellN.shape
+    blank = (cellN >= -1.e-15) & (cellN <= 1.e-15)                 # K_FUNC::fEqualZero
+    one = numpy.abs(cellN - 1.) <= 1.e-15                           # K_FUNC::fEqual(cellN, 1.)
+    if not blank.any():
+        return None
+    I, J, K = numpy.arange(im), numpy.arange(jm), numpy.arange(km)
+    hit = numpy.zeros(cellN.shape, dtype=bool)
+
+    def idx(base, off, n, clamp):
+        v = base + off
+        if clamp: return numpy.clip(v, 0, n - 1)
+        return numpy.where((v < 0) | (v > n - 1), base, v)
+    if dir == 0:
+        for d in range(1, depth + 1):
+            for sgn in (-1, 1):
+                hit |= blank[idx(I, sgn * d, im, True), :, :]
+                hit |= blank[:, idx(J, sgn * d, jm, True), :]
+                hit |= blank[:, :, idx(K, sgn * d, km, True)]
+    else:
+        for d in range(1, depth + 1):
+            for kd in (-1, 0, 1):
+                for jd in (-1, 0, 1):
+                    for id_ in (-1, 0, 1):
+                        if id_ == 0 and jd == 0 and kd == 0:
+                            continue
+                        hit |= blank[numpy.ix_(idx(I, id_ * d, im, False), idx(J, jd * d, jm, False),
+                                               idx(K, kd * d, km, False))]
+    cellN[one & hit] = 2.
+    return None
+
+
+def _setHoleInterpolatedPoints(a, depth=2, dir=0, loc='centers', cellNName='cellN', addGC=True):
+    """Connector.PyTree._setHoleInterpolatedPoints for structured zones (Connector/PyTree.py:1766-1783,
+    Connector.py:168-192): cellN=2 on the `depth` layers around the blanked (cellN=0) points; depth<0 grows the
+    fringe inwards (0 and 1 exchanged before and after, Connector.py:179-182).  The reference's second pass on
+    ghost cells (addGC) only propagates through abutting (match) connectivity, which this path does not carry."""
+    if depth == 0: return None
+    var = cellNName if loc == 'nodes' else 'centers:' + cellNName
+    for z in Internal.getZones(a):
+        c = C.getFieldArray(z, var)
+        if c is None: continue
+        if depth < 0:
+            c[...] = 1. - c + (c > 1.5) * 3.
+            _holeFringeStruct__(c, -depth, dir)
+            c[...] = 1. - c + (c > 1.5) * 3.
+        else:
+            _holeFringeStruct__(c, depth, dir)
+    return None
+
+
+def setHoleInterpolatedPoints(a, depth=2, dir=0, loc='centers', cellNName='cellN'):
+    """Set cellN=2 around cellN=0 points."""
+    b = Internal.copyRef(a)
+    var = cellNName if loc == 'nodes' else 'centers:' + cellNName
+    for z in Internal.getZones(b):
+        c = C.getFieldArray(z, var)
+        if c is not None:
+            C._initVars(z, var, numpy.array(c, order='F', copy=True))
+    _setHoleInterpolatedPoints(b, depth=depth, dir=dir, loc=loc, cellNName=cellNName)
+    return b
+
+
 def getIntersectingDomains(t, t2=None, method='AABB', taabb=None, tobb=None, taabb2=None, tobb2=None, tol=1e-10):
     """Dictionary zoneName -> names of the zones (of t2, or of t) whose axis-aligned bounding box
     intersects it (OversetData.py:115-215, method 'AABB'; compBoundingBoxIntersection compGeom.cpp:1055-1070)."""

@@ -4,9 +4,9 @@ same names from OversetData.py)."""
 from .OversetData import (setInterpData, _setInterpData, _setInterpDataChimera, setInterpTransfers,
                           _setInterpTransfers, setInterpTransfersD, _setInterpTransfersD,
                           _createInterpRegion__, _addCellN__, applyBCOverlaps, _applyBCOverlaps,
-                          getIntersectingDomains)
+                          getIntersectingDomains, setHoleInterpolatedPoints, _setHoleInterpolatedPoints)
 from .Connector import setInterpData__, getInterpolatedPoints__, createHooks__
 
 __all__ = ['setInterpData', '_setInterpData', 'setInterpTransfers', '_setInterpTransfers',
            'setInterpTransfersD', '_setInterpTransfersD', 'applyBCOverlaps', '_applyBCOverlaps',
-           'getIntersectingDomains']
+           'getIntersectingDomains', 'setHoleInterpolatedPoints', '_setHoleInterpolatedPoints']

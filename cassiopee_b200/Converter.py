@@ -243,3 +243,35 @@ def _addBC2Zone(z, bndName, bndType, wrange):
         bc = Internal.createChild(zbc, bndName, 'BC_t', value=bndType)
         bc[2].append(['PointRange', r, [], 'IndexRange_t'])
     return None
+
+
+def createHook(a, function='None', ctx=None, backend=None):
+    """C.createHook(z, 'adt') (Converter/Converter/PyTree.py:7198-7209, hook.cpp:578-632): the ADT of one
+    structured zone, built once and passed to setInterpData(hook=[...]) so that it is not rebuilt per call.
+    Here the hook is the zone resident on the device with its ADT replica (cassiopee_b200._lib.Zone);
+    function 'cart' (extension) gives the closed-form Cartesian donor of interpDataType=0 instead.
+    cellN is not part of a hook: setInterpData refreshes it from the donor tree at every call."""
+    from . import _lib
+    if function not in ('adt', 'cart'):
+        raise NotImplementedError("createHook: only function='adt' (and 'cart') has a device hook.")
+    zones = Internal.getZones(a)
+    if len(zones) != 1:
+        raise TypeError("createHook: 'adt' hooks are built per zone: one zone expected, got %d." % len(zones))
+    z = zones[0]
+    _, ni, nj, nk, _ = Internal.getZoneDim(z)
+    x, y, zz = [c.reshape(-1, order='F') for c in getCoords(z)]
+    if backend is None:
+        backend = _lib.DeviceBackend(ctx or _lib.default_context())
+    if function == 'cart':
+        return backend.make_zone(ni, nj, nk, x, y, zz, None, interpDataType=0)
+    return backend.make_zone(ni, nj, nk, x, y, zz, None)
+
+
+def freeHook(hook):
+    """C.freeHook: release the device memory of a hook now (it is also released when the object dies)."""
+    fin = getattr(hook, '_fin', None)
+    if fin is not None:
+        fin()
+    elif hasattr(hook, 'free'):
+        hook.free()
+    return None

@@ -104,14 +104,19 @@ __device__ __forceinline__ void transfer_entry(int e, int m, int nvars, const PD
       double val = 0.;
 #pragma unroll 1
       for (int kk = 0; kk < O; kk++)
+      {
+        double ck = c[2 * O];                              // c[kk + 2*O] without indexing registers dynamically
+#pragma unroll
+        for (int q = 1; q < O; q++) ck = (kk == q) ? c[2 * O + q] : ck;
 #pragma unroll
         for (int jj = 0; jj < O; jj++)
         {
           const double* g = f + jj * imd + kk * imdjmd;
 #pragma unroll
           for (int ii = 0; ii < O; ii++)
-            val += c[ii] * c[jj + O] * c[kk + 2 * O] * __ldg(g + ii);   // left to right, as commonInterpTransfers.h:85,141
+            val += c[ii] * c[jj + O] * ck * __ldg(g + ii);   // left to right, as commonInterpTransfers.h:85,141
         }
+      }
       if (MODE == 0) pr[v][o] = val; else dense[(size_t)v * ld + o] = val;
     }
   }
@@ -218,6 +223,89 @@ __device__ __forceinline__ bool transfer_tile2_staged(StageSmem& S, int t0, int 
       if (MODE == 0) pr[v][o] = val; else dense[(size_t)v * ld + o] = val;
     }
     __syncthreads();
+  }
+  return true;
+}
+
+// Types 3 and 5 (O x O x O stencils, direction weights cf[ii]*cf[jj+O]*cf[kk+2O]): the same row staging with
+// O*O row segments per variable.  Order 3: two variables in flight, spans up to 256 nodes; order 5: one
+// variable at a time (25 rows), spans up to 160 nodes.  Accumulation order is commonInterpTransfers.h:85,141.
+template <int O> struct StageCfg { };
+template <> struct StageCfg<3> { static constexpr int NSTAGE = 2, SPAN = 256; };
+template <> struct StageCfg<5> { static constexpr int NSTAGE = 1, SPAN = 160; };
+template <int O> struct StageSmemO {
+  double buf[StageCfg<O>::NSTAGE][O * O][StageCfg<O>::SPAN + 4];
+  unsigned long long bar[2];
+};
+
+template <int O, int MODE, class PD, class PR>
+__device__ __forceinline__ bool transfer_tileO_staged(StageSmemO<O>& S, int t0, int m, int nvars, const PD& pd,
+                                                      const PR& pr, int imd, int imdjmd, int nptsD,
+                                                      const int* __restrict__ donor, const int* __restrict__ idx,
+                                                      const double* __restrict__ cfT, double* __restrict__ dense,
+                                                      long long ld)
+{
+  constexpr int NSTAGE = StageCfg<O>::NSTAGE, SPAN = StageCfg<O>::SPAN, NROW = O * O;
+  const int tid = threadIdx.x;
+  const int e = t0 + tid;
+  const int last = min(t0 + (int)blockDim.x, m) - 1;
+  const int d_lo = donor[t0], d_hi = donor[last];
+  const int span = d_hi - d_lo + O;                      // nodes d_lo .. d_hi+O-1 of every row
+  const int offmax = (O - 1) * imd + (O - 1) * imdjmd;
+  if (span + 2 > SPAN || d_lo + offmax + span + 2 > nptsD) return false;
+  if (tid == 0) { mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1); mbar_fence_init(); }
+  __syncthreads();
+  auto issue = [&](int v) {      // executed by warp 0
+    const int st = v % NSTAGE;
+    const double* f = pd[v];
+    unsigned bytes = 0;
+    for (int r = 0; r < NROW; r++) bytes += 8u * (unsigned)((span + ((d_lo + (r % O) * imd + (r / O) * imdjmd) & 1) + 1) & ~1);
+    if (tid == 0) mbar_expect_tx(&S.bar[st], bytes);
+    __syncwarp();
+    for (int r = tid; r < NROW; r += 32)
+    {
+      const int g = d_lo + (r % O) * imd + (r / O) * imdjmd;
+      const int len = (span + (g & 1) + 1) & ~1;
+      bulk_g2s(&S.buf[st][r][0], f + (g & ~1), 8u * len, &S.bar[st]);
+    }
+  };
+  if (tid < 32) issue(0);
+  int l = 0; size_t o = 0;
+  double c[3 * O];
+  const bool act = e < m;
+  if (act)
+  {
+    l = donor[e] - d_lo; o = (size_t)idx[e];
+#pragma unroll
+    for (int k = 0; k < 3 * O; k++) c[k] = cfT[(size_t)k * m + e];
+  }
+  for (int v = 0; v < nvars; v++)
+  {
+    if (NSTAGE == 2 && tid < 32 && v + 1 < nvars) issue(v + 1);
+    mbar_wait(&S.bar[v % NSTAGE], (unsigned)((v / NSTAGE) & 1));
+    if (act)
+    {
+      const double(*b)[SPAN + 4] = S.buf[v % NSTAGE];
+      double val = 0.;
+#pragma unroll 1
+      for (int kk = 0; kk < O; kk++)
+      {
+        double ck = c[2 * O];                              // c[kk + 2*O] without indexing registers dynamically
+#pragma unroll
+        for (int q = 1; q < O; q++) ck = (kk == q) ? c[2 * O + q] : ck;
+#pragma unroll
+        for (int jj = 0; jj < O; jj++)
+        {
+          const double* g = &b[jj + O * kk][l + ((d_lo + jj * imd + kk * imdjmd) & 1)];
+#pragma unroll
+          for (int ii = 0; ii < O; ii++)
+            val += c[ii] * c[jj + O] * ck * g[ii];
+        }
+      }
+      if (MODE == 0) pr[v][o] = val; else dense[(size_t)v * ld + o] = val;
+    }
+    __syncthreads();
+    if (NSTAGE == 1 && tid < 32 && v + 1 < nvars) issue(v + 1);
   }
   return true;
 }
@@ -356,6 +444,24 @@ k_transfer2s(int m, int nvars, FieldPtrs P, int imd, int imdjmd, int nptsD, cons
   transfer_entry<2, MODE>(e, m, nvars, pd, pr, imd, imdjmd, donor, MODE == 0 ? rcv : pos, cfT, dense, ld);
 }
 
+// types 3 / 5 with shared-memory staging (falls back to the direct gather tile by tile)
+template <int O, int MODE>
+__global__ void __launch_bounds__(256)
+k_transferOs(int m, int nvars, FieldPtrs P, int imd, int imdjmd, int nptsD, const int* __restrict__ donor,
+             const int* __restrict__ rcv, const int* __restrict__ pos, const double* __restrict__ cfT,
+             double* __restrict__ dense, long long ld)
+{
+  extern __shared__ __align__(16) double dyn_sm[];
+  StageSmemO<O>& S = *reinterpret_cast<StageSmemO<O>*>(dyn_sm);
+  PDk pd{P.d}; PRk pr{P.r};
+  const int t0 = blockIdx.x * blockDim.x;
+  if (transfer_tileO_staged<O, MODE>(S, t0, m, nvars, pd, pr, imd, imdjmd, nptsD, donor, MODE == 0 ? rcv : pos, cfT, dense, ld))
+    return;
+  int e = t0 + threadIdx.x;
+  if (e >= m) return;
+  transfer_entry<O, MODE>(e, m, nvars, pd, pr, imd, imdjmd, donor, MODE == 0 ? rcv : pos, cfT, dense, ld);
+}
+
 // type 2, tiled layout: one CTA per non-empty donor box
 template <int MODE>
 __global__ void __launch_bounds__(256)
@@ -428,6 +534,20 @@ k_transfer_set(const SetDesc* __restrict__ descs, const int* __restrict__ blk2de
       bool done = (D.mode == 0)
         ? transfer_tile2_staged<0>(S, t0, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.nptsD, D.donor, D.idx, D.cfT, D.dense, D.ld)
         : transfer_tile2_staged<1>(S, t0, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.nptsD, D.donor, D.idx, D.cfT, D.dense, D.ld);
+      if (done) return;
+    }
+  }
+  if (TYPE == 3 || TYPE == 5)
+  {
+    constexpr int O = (TYPE == 3) ? 3 : 5;
+    extern __shared__ __align__(16) double dyn_sm[];
+    if (staged && D.layout == 1)
+    {
+      StageSmemO<O>& S = *reinterpret_cast<StageSmemO<O>*>(dyn_sm);
+      const int t0 = (blockIdx.x - D.first_block) * blockDim.x;
+      bool done = (D.mode == 0)
+        ? transfer_tileO_staged<O, 0>(S, t0, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.nptsD, D.donor, D.idx, D.cfT, D.dense, D.ld)
+        : transfer_tileO_staged<O, 1>(S, t0, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.nptsD, D.donor, D.idx, D.cfT, D.dense, D.ld);
       if (done) return;
     }
   }
@@ -755,8 +875,22 @@ int cx_plan_launch(cx_plan* P, int nvars, const double* const* dD, double* const
           }
           else { CX_LAUNCH(2) }
           break;
-        case 3: CX_LAUNCH(3) break;
-        case 5: CX_LAUNCH(5) break;
+        case 3:
+          if (staged && G.layout == 1)
+          {
+            if (mode == 0) k_transferOs<3, 0><<<grid, TB, sizeof(StageSmemO<3>), s>>>(G.n, nv, F, imd, ij, P->nptsD, dn_, rc_, ps_, G.d_cf, dn, ld);
+            else k_transferOs<3, 1><<<grid, TB, sizeof(StageSmemO<3>), s>>>(G.n, nv, F, imd, ij, P->nptsD, dn_, rc_, ps_, G.d_cf, dn, ld);
+          }
+          else { CX_LAUNCH(3) }
+          break;
+        case 5:
+          if (staged && G.layout == 1)
+          {
+            if (mode == 0) k_transferOs<5, 0><<<grid, TB, sizeof(StageSmemO<5>), s>>>(G.n, nv, F, imd, ij, P->nptsD, dn_, rc_, ps_, G.d_cf, dn, ld);
+            else k_transferOs<5, 1><<<grid, TB, sizeof(StageSmemO<5>), s>>>(G.n, nv, F, imd, ij, P->nptsD, dn_, rc_, ps_, G.d_cf, dn, ld);
+          }
+          else { CX_LAUNCH(5) }
+          break;
       }
 #undef CX_LAUNCH
       ctx->launches++;
@@ -795,7 +929,7 @@ struct cx_planset {
   // plans too large to gain anything from fusion run as their own launches (leaner kernel, more CTAs per SM)
   struct Big { cx_plan* P; int mode; std::vector<const double*> dD; std::vector<double*> dR; double* dense; long long ld; };
   std::vector<Big> big;
-  size_t smem;                          // dynamic shared memory of the type-2 launch
+  size_t smem, smem3, smem5;            // dynamic shared memory of the type-2 / 3 / 5 launches
   int nblocks[4];                       // per interpolation type 1,2,3,5
   SetDesc* d_descs[4]; int* d_blk2desc[4];
   void** d_tables; size_t ntables;      // device pointer tables owned by the set
@@ -827,7 +961,7 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
   CX_CUDA(cudaSetDevice(ctx->device));
   cx_planset* S = new cx_planset;
   S->ctx = ctx; S->nvars = nvars; S->d_tables = nullptr; S->ntables = 0; S->ndesc = 0;
-  S->staged = cx_transfer_staging(); S->smem = 0; S->tiled = 0;
+  S->staged = cx_transfer_staging(); S->smem = 0; S->smem3 = 0; S->smem5 = 0; S->tiled = 0;
   if (nvars > CX_MAXVARS) { cx_set_error("plan set: at most %d variables per set", CX_MAXVARS); delete S; return -1; }
   std::vector<SetDesc> descs[4]; std::vector<int> b2d[4]; std::vector<void*> tables;
   const int TB = 256;
@@ -857,6 +991,8 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
       D.tiles = (const TileRef*)G.d_tiles;
       if (G.type == 2 && G.layout == 2) { S->smem = std::max(S->smem, sizeof(double) * CX_BOXV * (size_t)nvars); S->tiled = 1; }
       if (G.type == 2 && G.layout == 1) S->smem = std::max(S->smem, sizeof(StageSmem));
+      if (G.type == 3 && G.layout == 1) S->smem3 = sizeof(StageSmemO<3>);
+      if (G.type == 5 && G.layout == 1) S->smem5 = sizeof(StageSmemO<5>);
       for (int v = 0; v < nvars; v++) if (((uintptr_t)d_fieldD[p][v]) & 15) S->staged = 0;
       D.donor = P->d_donor + G.first; D.idx = (modes[p] == 0 ? P->d_rcv : P->d_pos) + G.first; D.cfT = G.d_cf;
       D.dptr = td; D.rptr = tr; D.dense = modes[p] == 1 ? d_dense[p] : nullptr; D.ld = modes[p] == 1 ? ld[p] : 0;
@@ -895,8 +1031,8 @@ static int planset_run_on(cx_planset* S, cudaStream_t s)
     else k_transfer_set<2, false><<<S->nblocks[1], 256, S->smem, s>>>(S->d_descs[1], S->d_blk2desc[1], S->nvars, S->staged);
     S->ctx->launches++;
   }
-  if (S->nblocks[2]) { k_transfer_set<3, false><<<S->nblocks[2], 256, 0, s>>>(S->d_descs[2], S->d_blk2desc[2], S->nvars, S->staged); S->ctx->launches++; }
-  if (S->nblocks[3]) { k_transfer_set<5, false><<<S->nblocks[3], 256, 0, s>>>(S->d_descs[3], S->d_blk2desc[3], S->nvars, S->staged); S->ctx->launches++; }
+  if (S->nblocks[2]) { k_transfer_set<3, false><<<S->nblocks[2], 256, S->smem3, s>>>(S->d_descs[2], S->d_blk2desc[2], S->nvars, S->staged); S->ctx->launches++; }
+  if (S->nblocks[3]) { k_transfer_set<5, false><<<S->nblocks[3], 256, S->smem5, s>>>(S->d_descs[3], S->d_blk2desc[3], S->nvars, S->staged); S->ctx->launches++; }
   return 0;
 }
 

@@ -237,7 +237,9 @@ def test_transfer_synthetic_plans_staged_and_gather(ctx, dims, density):
     n = max(8, int(density * nD))
     nR = 2 * n + 5
     for contiguous in (False, True):
-        typ = rng.choice(np.array([1, 2, 2, 2, 2, 3], np.int32), n).astype(np.int32)
+        typ = rng.choice(np.array([1, 2, 2, 2, 2, 3, 3, 5], np.int32), n).astype(np.int32)
+        if ni < 5 or nj < 5 or nk < 5:
+            typ[typ == 5] = 3
         if ni < 3 or nj < 3 or nk < 3:
             typ[typ == 3] = 2
         o = np.where(typ == 1, 1, typ)
@@ -246,7 +248,7 @@ def test_transfer_synthetic_plans_staged_and_gather(ctx, dims, density):
         i[:3] = ni - o[:3]; j[:3] = nj - o[:3]; k[:3] = nk - o[:3]          # stencil ends on the last node
         dnr = (i + ni * j + ni * nj * k).astype(np.int32)
         rcv = (np.arange(n) + 3 if contiguous else np.sort(rng.choice(nR, n, replace=False))).astype(np.int32)
-        ncf = np.where(typ == 1, 1, np.where(typ == 2, 8, 9))
+        ncf = np.where(typ == 1, 1, np.where(typ == 2, 8, np.where(typ == 3, 9, 15)))
         cf = rng.standard_normal(int(ncf.sum()))
         for nvars in (1, 2, 5):
             fD = [rng.standard_normal(nD) for _ in range(nvars)]

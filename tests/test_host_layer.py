@@ -167,3 +167,102 @@ def test_apply_bc_overlaps_and_intersecting_domains():
     C.getFieldArray(zA, 'centers:cellN')[9, 0, 0] = 0.
     XP._applyBCOverlaps(zA, depth=2, loc='centers')
     assert C.getFieldArray(zA, 'centers:cellN')[9, 0, 0] == 0. and C.getFieldArray(zA, 'centers:cellN')[9, 1, 0] == 2.
+
+
+def test_hooks_and_interpdatatype_through_the_tree_layer():
+    """hook=[C.createHook(zd,'adt') ...] gives the same tree as hook=None; interpDataType=0 (Cartesian donors,
+    InterpCart) goes through the same layer; bad hook lists / types raise like the reference."""
+    t = _case(); tc = C.node2Center(t)
+    be = OracleBackend()
+    ref = Internal.copyRef(tc)
+    X._setInterpDataChimera(Internal.copyRef(t), ref, order=2, nature=1, loc='centers', storage='inverse', verbose=0,
+                            backend=be)
+    hooks = [C.createHook(z, 'adt', backend=be) for z in Internal.getZones(tc)]
+    got = Internal.copyRef(tc)
+    X._setInterpDataChimera(Internal.copyRef(t), got, order=2, nature=1, loc='centers', storage='inverse', verbose=0,
+                            backend=be, hook=hooks)
+    for za, zb in zip(Internal.getZones(ref), Internal.getZones(got)):
+        sa = Internal.getNodesFromType1(za, 'ZoneSubRegion_t'); sb = Internal.getNodesFromType1(zb, 'ZoneSubRegion_t')
+        assert [s[0] for s in sa] == [s[0] for s in sb]
+        for a, b in zip(sa, sb):
+            for name in ('PointList', 'PointListDonor', 'InterpolantsType', 'InterpolantsDonor'):
+                assert np.array_equal(Internal.getNodeFromName1(a, name)[1], Internal.getNodeFromName1(b, name)[1])
+    for h in hooks:
+        C.freeHook(h)
+    with pytest.raises(TypeError):
+        X._setInterpDataChimera(Internal.copyRef(t), Internal.copyRef(tc), loc='centers', storage='inverse', verbose=0,
+                                backend=be, hook=hooks[:1])
+    with pytest.raises(TypeError):
+        X._setInterpDataChimera(Internal.copyRef(t), Internal.copyRef(tc), loc='centers', storage='inverse', verbose=0,
+                                backend=be, interpDataType=2)
+    with pytest.raises(NotImplementedError):
+        C.createHook(Internal.getZones(tc)[0], 'nodes', backend=be)
+    # Cartesian donors: trilinear weights, type 2 everywhere the ADT path also finds a cell
+    cart = Internal.copyRef(tc)
+    X._setInterpDataChimera(Internal.copyRef(t), cart, order=2, nature=1, loc='centers', storage='inverse', verbose=0,
+                            backend=be, interpDataType=0)
+    sa = Internal.getNodeFromName1(Internal.getZones(ref)[0], 'ID_B'); sc = Internal.getNodeFromName1(Internal.getZones(cart)[0], 'ID_B')
+    assert np.array_equal(Internal.getNodeFromName1(sa, 'PointListDonor')[1], Internal.getNodeFromName1(sc, 'PointListDonor')[1])
+    cf = Internal.getNodeFromName1(sc, 'InterpolantsDonor')[1]; ty = Internal.getNodeFromName1(sc, 'InterpolantsType')[1]
+    assert (ty == 2).all() and np.allclose(cf.reshape(-1, 8).sum(axis=1), 1., atol=1e-13)
+
+
+def _hole_fringe_loops(c, depth, dir):
+    """Restatement with plain loops of searchMaskInterpolatedCellsStructOpt, 3-D
+    (Connector/Connector/getInterpolatedPoints.cpp:444-494 cross, :572-650 star)."""
+    im, jm, km = c.shape
+    out = c.copy()
+    for k in range(km):
+        for j in range(jm):
+            for i in range(im):
+                if abs(c[i, j, k] - 1.) > 1e-15: continue
+                idx = []
+                if dir == 0:
+                    for d in range(-depth, 0): idx.append((i, j, max(0, k + d)))
+                    for d in range(-depth, 0): idx.append((i, max(0, j + d), k))
+                    for d in range(-depth, 0): idx.append((max(0, i + d), j, k))
+                    for d in range(1, depth + 1): idx.append((min(i + d, im - 1), j, k))
+                    for d in range(1, depth + 1): idx.append((i, min(j + d, jm - 1), k))
+                    for d in range(1, depth + 1): idx.append((i, j, min(k + d, km - 1)))
+                else:
+                    def comp(v, off, n):
+                        w = v + off
+                        return v if (w < 0 or w > n - 1) else w
+                    for kd in list(range(-depth, 0)) + list(range(1, depth + 1)):
+                        kk = comp(k, kd, km)
+                        for jd in (-1, 0, 1):
+                            for id_ in (-1, 0, 1):
+                                idx.append((comp(i, id_ * abs(kd), im), comp(j, jd * abs(kd), jm), kk))
+                    for d in range(1, depth + 1):
+                        for jd in (-1, 1):
+                            jj = comp(j, jd * d, jm)
+                            idx += [(comp(i, -d, im), jj, k), (i, jj, k), (comp(i, d, im), jj, k)]
+                        idx += [(comp(i, -d, im), j, k), (comp(i, d, im), j, k)]
+                if any(abs(c[q]) <= 1e-15 for q in idx):
+                    out[i, j, k] = 2.
+    return out
+
+
+def test_set_hole_interpolated_points():
+    import cassiopee_b200.Connector.PyTree as XP
+    rng = np.random.default_rng(4)
+    for shape in ((9, 8, 7), (12, 5, 1)):
+        for dir_ in (0, 1):
+            for depth in (1, 2, 3):
+                c = np.ones(shape, order='F')
+                c[rng.random(shape) < 0.03] = 0.
+                c[rng.random(shape) < 0.03] = 2.
+                z = G.cart((0, 0, 0), (1, 1, 1), (shape[0] + 1, shape[1] + 1, shape[2] + 1), name='Z')
+                C._initVars(z, 'centers:cellN', c)
+                z2 = XP.setHoleInterpolatedPoints(z, depth=depth, dir=dir_, loc='centers')
+                got = C.getFieldArray(Internal.getZones(z2)[0], 'centers:cellN')
+                assert np.array_equal(got, _hole_fringe_loops(c, depth, dir_)), (shape, dir_, depth)
+                assert np.array_equal(C.getFieldArray(z, 'centers:cellN'), c)      # input untouched
+    # depth < 0: the fringe grows into the blanked region
+    c = np.ones((7, 7, 7), order='F'); c[2:5, 2:5, 2:5] = 0.
+    z = G.cart((0, 0, 0), (1, 1, 1), (8, 8, 8), name='Z'); C._initVars(z, 'centers:cellN', c)
+    XP._setHoleInterpolatedPoints(z, depth=-1, dir=0, loc='centers')
+    got = C.getFieldArray(z, 'centers:cellN')
+    assert got[3, 3, 3] == 0. and got[2, 3, 3] == 2. and got[1, 3, 3] == 1. and got[2, 2, 2] == 2.
+    with pytest.raises(NotImplementedError):
+        XP._setHoleInterpolatedPoints(z, depth=2, dir=2, loc='centers')
