@@ -227,9 +227,10 @@ __device__ __forceinline__ bool transfer_tile2_staged(StageSmem& S, int t0, int 
   return true;
 }
 
-// Types 3 and 5 (O x O x O stencils, direction weights cf[ii]*cf[jj+O]*cf[kk+2O]): the same row staging with
-// O*O row segments per variable.  Order 3: two variables in flight, spans up to 256 nodes; order 5: one
-// variable at a time (25 rows), spans up to 160 nodes.  Accumulation order is commonInterpTransfers.h:85,141.
+// Type 3 (3 x 3 x 3 stencils, direction weights cf[ii]*cf[jj+O]*cf[kk+2O]): the same row staging with 9 row
+// segments per variable, two variables in flight, spans up to 256 nodes (0.97 vs 1.07 ms on C2a order 3).  The
+// template also instantiates for O = 5 (25 rows, one variable at a time) but type 5 keeps the direct gather:
+// staging measured slower there (5.5 vs 3.5 ms).  Accumulation order is commonInterpTransfers.h:85,141.
 template <int O> struct StageCfg { };
 template <> struct StageCfg<3> { static constexpr int NSTAGE = 2, SPAN = 256; };
 template <> struct StageCfg<5> { static constexpr int NSTAGE = 1, SPAN = 160; };
@@ -537,9 +538,9 @@ k_transfer_set(const SetDesc* __restrict__ descs, const int* __restrict__ blk2de
       if (done) return;
     }
   }
-  if (TYPE == 3 || TYPE == 5)
+  if (TYPE == 3)
   {
-    constexpr int O = (TYPE == 3) ? 3 : 5;
+    constexpr int O = 3;
     extern __shared__ __align__(16) double dyn_sm[];
     if (staged && D.layout == 1)
     {
@@ -883,14 +884,7 @@ int cx_plan_launch(cx_plan* P, int nvars, const double* const* dD, double* const
           }
           else { CX_LAUNCH(3) }
           break;
-        case 5:
-          if (staged && G.layout == 1)
-          {
-            if (mode == 0) k_transferOs<5, 0><<<grid, TB, sizeof(StageSmemO<5>), s>>>(G.n, nv, F, imd, ij, P->nptsD, dn_, rc_, ps_, G.d_cf, dn, ld);
-            else k_transferOs<5, 1><<<grid, TB, sizeof(StageSmemO<5>), s>>>(G.n, nv, F, imd, ij, P->nptsD, dn_, rc_, ps_, G.d_cf, dn, ld);
-          }
-          else { CX_LAUNCH(5) }
-          break;
+        case 5: CX_LAUNCH(5) break;   // 125-point stencils: staging measured slower (5.5 vs 3.5 ms on C2a), direct gather
       }
 #undef CX_LAUNCH
       ctx->launches++;
@@ -992,7 +986,6 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
       if (G.type == 2 && G.layout == 2) { S->smem = std::max(S->smem, sizeof(double) * CX_BOXV * (size_t)nvars); S->tiled = 1; }
       if (G.type == 2 && G.layout == 1) S->smem = std::max(S->smem, sizeof(StageSmem));
       if (G.type == 3 && G.layout == 1) S->smem3 = sizeof(StageSmemO<3>);
-      if (G.type == 5 && G.layout == 1) S->smem5 = sizeof(StageSmemO<5>);
       for (int v = 0; v < nvars; v++) if (((uintptr_t)d_fieldD[p][v]) & 15) S->staged = 0;
       D.donor = P->d_donor + G.first; D.idx = (modes[p] == 0 ? P->d_rcv : P->d_pos) + G.first; D.cfT = G.d_cf;
       D.dptr = td; D.rptr = tr; D.dense = modes[p] == 1 ? d_dense[p] : nullptr; D.ld = modes[p] == 1 ? ld[p] : 0;
