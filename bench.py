@@ -503,6 +503,8 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly one JSON line: NCCL's version banner / warnings go to a file
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/cx_nccl_%h_%p.log")
     if args.workload == "c4":
         from bench_c4 import run_c4
         return run_c4(args)

@@ -125,6 +125,7 @@ def run_c2n(args):
     nccl_b = sum(gather(sess.nccl_bytes()))
     h2d = sum(gather(sess.h2d_bytes)); d2h = sum(gather(d2h))
     nplans = sum(gather(len(sess.plans)))
+    transport = sess.transport
     launches_all = sum(gather(launches))
     norphan = sum(gather(norphan))
     # free the C2 session before the C4/C5 leg
@@ -147,7 +148,11 @@ def run_c2n(args):
                                "cells and exchange 2-layer fringes over NCCL; C4/C5 cluster under c4_c5" %
                                (b0['nb'], str(tuple(b0['nc'])), nvars, len(bodies)),
                    "zones": 2 * len(bodies), "receptors": int(nrcv), "plans": int(nplans), "nvars": nvars,
-                   "alg_bytes_per_step": int(B), "nccl_bytes_per_step": int(nccl_b), "orphans": int(norphan),
+                   "alg_bytes_per_step": int(B), "nccl_bytes_per_step": int(nccl_b), "exchange_bytes_per_step": int(nccl_b),
+                   "transport": {"p2p": "peer memory: remote plans store into the receptor rank's IPC-mapped buffers over "
+                                        "NVLink, flag per rank pair (no NCCL call in the step)",
+                                 "nccl": "grouped ncclSend/ncclRecv of one packed buffer per rank pair",
+                                 "none": "single rank"}[transport], "orphans": int(norphan),
                    "l2": "inputs larger than L2 (%.2f GB of plan+field traffic per GPU and step, L2 126 MB); no flush" %
                          (B / max(1, ngpus) / 1e9),
                    "parallelism": "one body (2 zones) per GPU by .Solver#Param/proc"},

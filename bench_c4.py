@@ -137,6 +137,7 @@ def measure_c4(args, ctx, comm, ngpus, rank, world):
     nccl_b = sum(gather(sess.nccl_bytes()))
     h2d = sum(gather(sess.h2d_bytes)); d2h = sum(gather(d2h))
     nplans = sum(gather(len(sess.plans)))
+    transport = sess.transport
     launches_all = sum(gather(launches))
     if rank != 0:
         return None
@@ -150,7 +151,11 @@ def measure_c4(args, ctx, comm, ngpus, rank, world):
                                (nb[0], nb[1], nb[2], nblk, nvars),
                    "zones": len(blocks), "zones_per_gpu": len(blocks) // max(1, ngpus), "receptors": int(nrcv),
                    "plans": int(nplans), "nvars": nvars, "alg_bytes_per_step": int(B),
-                   "nccl_bytes_per_step": int(nccl_b),
+                   "nccl_bytes_per_step": int(nccl_b), "exchange_bytes_per_step": int(nccl_b),
+                   "transport": {"p2p": "peer memory: remote plans store into the receptor rank's IPC-mapped buffers over "
+                                        "NVLink, flag per rank pair (no NCCL call in the step)",
+                                 "nccl": "grouped ncclSend/ncclRecv of one packed buffer per rank pair",
+                                 "none": "single rank"}[transport],
                    "l2": "per-GPU working set %.0f MB; L2 not flushed (steady-state loop of a solver)" %
                          ((B / max(1, ngpus)) / 1e6),
                    "parallelism": "zones over %d GPU(s) by .Solver#Param/proc (rcb)" % ngpus},

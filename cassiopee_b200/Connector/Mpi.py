@@ -322,25 +322,25 @@ class TransferSession:
                 self.plans.append(plan)
                 info = plan.info()
                 self.alg_fixed += info['alg_fixed']; self.n_entries += info['n']; self.distinct += info['distinct']
-        # send buffers: one per peer, blocks (nvars, n_pair) in (donor, receptor) name order
-        self.sendbuf, self.sendcnt = {}, {}
+        # one block (nvars, n_pair) per remote plan, in (donor, receptor) name order inside each peer's message.
+        # The blocks are written in the plan's own donor-sorted entry order (mode 2: coalesced stores, also
+        # over NVLink), so the receptor rank gets the index list in that order (once, here).
+        self.sendcnt = {}
         outMeta, outIdx = {}, {}
+        rlayout = {}      # peer -> list of (donorName, plan, offset in doubles)
         for p, lst in remote.items():
             lst.sort(key=lambda t: (t[0], t[1]))
-            tot = sum(t[2].n for t in lst) * nv
-            self.sendbuf[p] = _lib.DeviceArray(ctx, max(tot, 1))
-            self.sendcnt[p] = tot
+            self.sendcnt[p] = sum(t[2].n for t in lst) * nv
             o = 0
             for dn, rn, plan, ListRcv, loc in lst:
-                ritems.append((plan, 1, [d.ptr for d in self.dD[dn]], None, self.sendbuf[p].ptr + 8 * o, plan.n))
+                rlayout.setdefault(p, []).append((dn, plan, o))
                 outMeta.setdefault(p, []).append(dict(donor=dn, rcv=rn, n=int(plan.n), loc=loc))
-                outIdx.setdefault(p, []).append(numpy.ascontiguousarray(ListRcv, dtype=numpy.int32).view(numpy.uint8))
+                outIdx.setdefault(p, []).append(plan.sorted_rcv().view(numpy.uint8))
                 o += plan.n * nv
         self.planset = _lib.PlanSet(ctx, nv, items)          # local pairs, in place
-        self.planset_remote = _lib.PlanSet(ctx, nv, ritems) if ritems else None
         # receive side: index lists are exchanged once
-        self.recvbuf, self.recvcnt = {}, {}
-        sitems = []
+        self.recvcnt = {}
+        rlists = {}       # peer -> list of (n, device index list, offset in doubles, receptor zone name)
         self._keep = []
         if size > 1:
             allMeta = comm.allgather_obj(outMeta)
@@ -350,26 +350,92 @@ class TransferSession:
             got = comm.exchange_host(send, recv_sizes, dtype=numpy.uint8)
             for q in sorted(recv_sizes):
                 recs = allMeta[q][rank]
-                tot = sum(r['n'] for r in recs) * nv
-                self.recvbuf[q] = _lib.DeviceArray(ctx, max(tot, 1)); self.recvcnt[q] = tot
+                self.recvcnt[q] = sum(r['n'] for r in recs) * nv
                 o = 0; ob = 0
                 for r in recs:
                     n = r['n']
                     lst = got[q][ob:ob + 4 * n].view(numpy.int32).copy(); ob += 4 * n
-                    zr = self.zr[r['rcv']]
-                    self._residentR(zr, r['loc'])
+                    self._residentR(self.zr[r['rcv']], r['loc'])
                     dl = _lib.DeviceArray.from_host(ctx, lst)
                     self._keep.append(dl)
-                    sitems.append((n, dl, self.recvbuf[q].ptr + 8 * o, n, [d.ptr for d in self.dR[r['rcv']]]))
+                    rlists.setdefault(q, []).append((n, dl, o, r['rcv']))
                     o += n * nv
+        self.peers = sorted(set(self.sendcnt) | set(self.recvcnt))
+        self.transport = 'none'
+        if size > 1:
+            # collective decision: every rank goes through the same sequence of exchanges, also without peers
+            want = os.environ.get("CX_TRANSPORT", "p2p")
+            ok = self._setup_p2p(rlayout, rlists, nv) if want == 'p2p' else False
+            if ok:
+                self.transport = 'p2p'
+            else:
+                self._setup_nccl(rlayout, rlists, nv)
+                self.transport = 'nccl'
+        else:
+            self.planset_remote = None
+            self.scatterset = _lib.ScatterSet(ctx, nv, [])
+            self._step = _lib.Step(ctx, None, self.planset, self.scatterset, [], [], [], [], [])
+        ctx.sync()
+
+    def _setup_nccl(self, rlayout, rlists, nv):
+        """Remote plans -> per-peer send buffers -> grouped ncclSend/ncclRecv -> scatter."""
+        ctx = self.ctx
+        self.sendbuf = {p: _lib.DeviceArray(ctx, max(c, 1)) for p, c in self.sendcnt.items()}
+        self.recvbuf = {q: _lib.DeviceArray(ctx, max(c, 1)) for q, c in self.recvcnt.items()}
+        ritems = [(plan, 2, [d.ptr for d in self.dD[dn]], None, self.sendbuf[p].ptr + 8 * o, plan.n)
+                  for p, lst in rlayout.items() for dn, plan, o in lst]
+        sitems = [(n, dl, self.recvbuf[q].ptr + 8 * o, n, [d.ptr for d in self.dR[rn]])
+                  for q, lst in rlists.items() for n, dl, o, rn in lst]
+        self.planset_remote = _lib.PlanSet(ctx, nv, ritems) if ritems else None
         self.scatterset = _lib.ScatterSet(ctx, nv, sitems)
-        self.peers = sorted(set(self.sendbuf) | set(self.recvbuf))
         sp = [self.sendbuf[p].ptr if p in self.sendbuf else 0 for p in self.peers]
         sc = [self.sendcnt.get(p, 0) for p in self.peers]
         rp = [self.recvbuf[p].ptr if p in self.recvbuf else 0 for p in self.peers]
         rc = [self.recvcnt.get(p, 0) for p in self.peers]
         self._step = _lib.Step(ctx, self.planset_remote, self.planset, self.scatterset, self.peers, sp, sc, rp, rc)
+
+    def _setup_p2p(self, rlayout, rlists, nv):
+        """Peer-memory transport: this rank's receive buffers (two per peer, by iteration parity) and its flag
+        array are exported with CUDA IPC; the remote plans of the donor ranks store into them directly."""
+        ctx, comm = self.ctx, self.comm
+        rank = comm.rank
+        try:
+            self.recvbuf2 = {q: [_lib.DeviceArray(ctx, max(self.recvcnt.get(q, 0), 1)) for _ in (0, 1)] for q in self.peers}
+            self.flags = _lib.DeviceArray(ctx, max(len(self.peers), 1), numpy.int32)
+            ctx.upload(self.flags.ptr, numpy.zeros(max(len(self.peers), 1), numpy.int32))
+            mine = {q: (_lib.ipc_export(self.recvbuf2[q][0].ptr), _lib.ipc_export(self.recvbuf2[q][1].ptr),
+                        _lib.ipc_export(self.flags.ptr + 4 * k)) for k, q in enumerate(self.peers)}
+            err = None
+        except _lib.CxError as e:
+            mine, err = None, str(e)
+        allx = comm.allgather_obj(mine)
+        if any(x is None for x in allx):
+            if err and os.environ.get("CX_PROFILE"):
+                print("[TransferSession] peer-memory transport unavailable (%s); using NCCL" % err, flush=True)
+            return False
+        try:
+            rbuf = {p: [_lib.ipc_open(ctx, allx[p][rank][par]) for par in (0, 1)] for p in self.peers}
+            pflags = [_lib.ipc_open(ctx, allx[p][rank][2]) for p in self.peers]
+        except _lib.CxError as e:
+            if os.environ.get("CX_PROFILE"):
+                print("[TransferSession] cudaIpcOpenMemHandle failed (%s); using NCCL" % e, flush=True)
+            rbuf = None
+        if not all(comm.allgather_obj(rbuf is not None)):
+            return False
+        ps2, ss2 = [], []
+        for par in (0, 1):
+            ritems = [(plan, 2, [d.ptr for d in self.dD[dn]], None, rbuf[p][par] + 8 * o, plan.n)
+                      for p, lst in rlayout.items() for dn, plan, o in lst]
+            sitems = [(n, dl, self.recvbuf2[q][par].ptr + 8 * o, n, [d.ptr for d in self.dR[rn]])
+                      for q, lst in rlists.items() for n, dl, o, rn in lst]
+            ps2.append(_lib.PlanSet(ctx, nv, ritems) if ritems else None)
+            ss2.append(_lib.ScatterSet(ctx, nv, sitems) if sitems else None)
+        self.planset_remote = ps2[0]
+        self._ps2, self._ss2 = ps2, ss2
+        self._step = _lib.StepP2P(ctx, ps2, self.planset, ss2, pflags, self.flags)
         ctx.sync()
+        comm.barrier()      # every rank's flags are zeroed and mapped before anyone signals
+        return True
 
     def _residentR(self, zr, loc):
         if zr[0] in self.dR:
@@ -384,6 +450,7 @@ class TransferSession:
         return self.alg_fixed + 8 * nv * (self.n_entries + self.distinct)
 
     def nccl_bytes(self):
+        """Bytes this rank ships to other ranks per iteration (NCCL messages or peer-memory stores)."""
         return 8 * sum(self.sendcnt.values())
 
     def pin_host_fields(self):

@@ -439,16 +439,14 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
 
             # Etape 1: points to interpolate (cellN == 2): getInterpolatedPoints keeps the points with
             # |cellN-2| <= 1e-15 in source order and records their index ('indcell'); for loc='centers' the
-            # centre coordinates (node2Center formula) are only evaluated for those cells
+            # centre coordinates (node2Center formula) are only evaluated for those cells.  Done by the backend
+            # (on the device: cx_receptors_create), which keeps the coordinates resident for the search.
             x, y, zc = C.getCoords(z)
             cellN = C.getFieldArray(z, 'cellN' if locR == 'nodes' else 'centers:cellN')
-            tcn = cellN.reshape(-1, order='F') - 2.
-            sel = numpy.nonzero((tcn >= -1.e-15) & (tcn <= 1.e-15))[0]
-            if locR == 'nodes':
-                pts = [numpy.ascontiguousarray(a.reshape(-1, order='F')[sel]) for a in (x, y, zc)]
-            else:
-                pts = [C.node2CenterSelected(a, sel) for a in (x, y, zc)]
-            interpPts = ['x,y,z,indcell', pts + [sel], sel.size, 1, 1]
+            _, ni_r, nj_r, nk_r, _ = Internal.getZoneDim(z)
+            rcvPts = backend.select_receptors(ni_r, nj_r, nk_r, x.reshape(-1, order='F'), y.reshape(-1, order='F'),
+                                              zc.reshape(-1, order='F'), cellN.reshape(-1, order='F'), locR)
+            sel = rcvPts.indcell
             if nzonesDnr == 0:
                 if sel.size > 0:
                     raise TypeError("setInterpData: no valid donor zone found.")
@@ -457,13 +455,10 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
             # Etape 2: interpolation data on the device
             if sel.size == 0:
                 continue
-            f = interpPts[1]
             _t1 = _time.perf_counter()
             hooks_ = [hookOf(i) for i in idx]
             _t2 = _time.perf_counter()
-            resInterp = backend.set_interp_data(numpy.ascontiguousarray(f[0]), numpy.ascontiguousarray(f[1]),
-                                                numpy.ascontiguousarray(f[2]), hooks_,
-                                                order, nature, penalty, extrap)
+            resInterp = backend.set_interp_data_rcv(rcvPts, hooks_, order, nature, penalty, extrap)
             _t3 = _time.perf_counter()
             _tt['pts'] += _t1 - _t0; _tt['hooks'] += _t2 - _t1; _tt['search'] += _t3 - _t2
             nbinterpolated = sel.size

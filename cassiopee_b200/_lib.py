@@ -50,6 +50,11 @@ _SIGS = {
     "cx_zone_destroy": (_i, [_vp]),
     "cx_set_interp_data": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "cx_set_interp_data_dev": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
+    "cx_receptors_create": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    "cx_receptors_count": (_i, [_vp, _vp]),
+    "cx_receptors_fetch": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "cx_receptors_destroy": (_i, [_vp]),
+    "cx_set_interp_data_rcv": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "cx_result_sizes": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "cx_result_fetch_zone": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "cx_result_fetch_orphans": (_i, [_vp, _vp]),
@@ -65,6 +70,10 @@ _SIGS = {
     "cx_transfer_celln_dev": (_i, [_vp, _vp, _vp]),
     "cx_scatter_dev": (_i, [_vp, _i, _vp, _ll, _i, _vp, _vp]),
     "cx_plan_info": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "cx_plan_sorted_rcv": (_i, [_vp, _vp]),
+    "cx_ipc_export": (_i, [_vp, _vp]),
+    "cx_ipc_open": (_i, [_vp, _vp, _vp]),
+    "cx_ipc_close_all": (_i, []),
     "cx_plan_destroy": (_i, [_vp]),
     "cx_planset_create": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cx_planset_run": (_i, [_vp]),
@@ -73,6 +82,7 @@ _SIGS = {
     "cx_scatterset_run": (_i, [_vp]),
     "cx_scatterset_destroy": (_i, [_vp]),
     "cx_step_create": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cx_step_create_p2p": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "cx_step_run": (_i, [_vp, _i, _i]),
     "cx_step_destroy": (_i, [_vp]),
     "cx_comm_unique_id": (_i, [_vp]),
@@ -351,6 +361,50 @@ def set_interp_data(ctx, xr, yr, zr, zones, order=2, nature=0, penalty=1, extrap
     return InterpResult(h, len(zones), n)
 
 
+class Receptors:
+    """Receptor points of one zone extracted on the device (cx_receptors): the points with cellN == 2 at `loc`,
+    their index in the zone ('indcell') and their coordinates (cell centres for loc='centers')."""
+
+    def __init__(self, ctx, ni, nj, nk, x, y, z, cellN, loc):
+        if loc not in ('nodes', 'centers'):
+            raise ValueError("setInterpData: invalid loc.")
+        self.ctx = ctx
+        x, y, z, cellN = f64(x), f64(y), f64(z), f64(cellN)
+        nn = int(ni) * int(nj) * int(nk)
+        npts = nn if loc == 'nodes' else (int(ni) - 1) * (int(nj) - 1) * (int(nk) - 1)
+        if x.size != nn or y.size != nn or z.size != nn or cellN.size != npts:
+            raise TypeError("getInterpolatedPoints: coordinates / cellN do not match the zone dimensions.")
+        h = _vp()
+        check(lib().cx_receptors_create(ctx.h, int(ni), int(nj), int(nk), ptr(x), ptr(y), ptr(z), ptr(cellN),
+                                        0 if loc == 'nodes' else 1, ctypes.byref(h)))
+        self.h = h
+        self._fin = weakref.finalize(self, lib().cx_receptors_destroy, h)
+        n = _i()
+        check(lib().cx_receptors_count(h, ctypes.byref(n)))
+        self.n = n.value
+        self._ind = None
+
+    @property
+    def indcell(self):
+        if self._ind is None:
+            self._ind = np.empty(self.n, np.int32)
+            check(lib().cx_receptors_fetch(self.h, ptr(self._ind), None, None, None))
+        return self._ind
+
+    def coords(self):
+        x = np.empty(self.n); y = np.empty(self.n); z = np.empty(self.n)
+        check(lib().cx_receptors_fetch(self.h, None, ptr(x), ptr(y), ptr(z)))
+        return x, y, z
+
+
+def set_interp_data_rcv(ctx, rcv, zones, order=2, nature=0, penalty=1, extrap=1):
+    hs = (ctypes.c_void_p * len(zones))(*[z.h.value for z in zones])
+    h = _vp()
+    check(lib().cx_set_interp_data_rcv(ctx.h, rcv.h, len(zones), hs, int(order), int(nature), int(penalty),
+                                       int(extrap), ctypes.byref(h)))
+    return InterpResult(h, len(zones), rcv.n)
+
+
 def set_interp_data_dev(ctx, n, dxr, dyr, dzr, zones, order=2, nature=0, penalty=1, extrap=1):
     hs = (ctypes.c_void_p * len(zones))(*[z.h.value for z in zones])
     h = _vp()
@@ -413,6 +467,12 @@ class Plan:
 
     def transfer_celln_dev(self, dD, dR):
         check(lib().cx_transfer_celln_dev(self.h, _vp(dD), _vp(dR)))
+
+    def sorted_rcv(self):
+        """Receptor indices in the plan's own entry order (the order of a mode-2 dense block)."""
+        out = np.empty(self.n, np.int32)
+        check(lib().cx_plan_sorted_rcv(self.h, ptr(out)))
+        return out
 
     def info(self):
         n = _i(); ng = _i(); af = _ll(); di = _ll()
@@ -567,8 +627,48 @@ class DeviceBackend:
         res = set_interp_data(self.ctx, xr, yr, zr, hooks, order, nature, penalty, extrap)
         return res.fetch()
 
+    def select_receptors(self, ni, nj, nk, x, y, z, cellN, loc):
+        """Receptor points (cellN == 2 at loc) of one zone, extracted and kept on the device."""
+        return Receptors(self.ctx, ni, nj, nk, x, y, z, cellN, loc)
+
+    def set_interp_data_rcv(self, rcv, hooks, order, nature, penalty, extrap):
+        return set_interp_data_rcv(self.ctx, rcv, hooks, order, nature, penalty, extrap).fetch()
+
     def make_plan(self, imd, jmd, kmd, nptsR, donor, rcv, typ, coefs):
         return Plan(self.ctx, imd, jmd, kmd, nptsR, donor, rcv, typ, coefs)
+
+
+def ipc_export(dptr):
+    """72-byte CUDA IPC descriptor (handle of the containing allocation + offset) of a device pointer."""
+    buf = ctypes.create_string_buffer(72)
+    check(lib().cx_ipc_export(_vp(dptr), buf))
+    return bytes(buf.raw)
+
+
+def ipc_open(ctx, desc):
+    """Map a peer process's device memory exported with ipc_export; returns the device pointer here."""
+    p = _vp()
+    check(lib().cx_ipc_open(ctx.h, ctypes.c_char_p(desc), ctypes.byref(p)))
+    return p.value
+
+
+class StepP2P:
+    """One solver iteration of a rank with the peer-memory transport (cx_step_create_p2p): remote plans store into
+    the peers' IPC-mapped receive buffers, flags instead of messages, scatter, overlapped with the local plans."""
+
+    def __init__(self, ctx, ps_remote2, ps_local, ss2, peer_flag_ptrs, my_flags):
+        self.ctx = ctx
+        self._keep = (ps_remote2, ps_local, ss2, my_flags)
+        n = len(peer_flag_ptrs)
+        h = _vp()
+        hv = lambda o: o.h if o is not None else None
+        check(lib().cx_step_create_p2p(ctx.h, hv(ps_remote2[0]), hv(ps_remote2[1]), hv(ps_local), hv(ss2[0]), hv(ss2[1]),
+                                       n, ptr_array(peer_flag_ptrs) if n else None, _vp(my_flags.ptr), ctypes.byref(h)))
+        self.h = h
+        self._fin = weakref.finalize(self, lib().cx_step_destroy, h)
+
+    def run(self, niter=1, overlap=True):
+        check(lib().cx_step_run(self.h, int(niter), 1 if overlap else 0))
 
 
 class Step:

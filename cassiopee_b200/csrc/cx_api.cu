@@ -86,7 +86,13 @@ int cx_ctx_create(int device, cx_ctx** out)
     }
   }
   CX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CX_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  {
+    // the communication stream carries short kernels (remote plans, NCCL, scatter) that must not queue behind the
+    // thousands of CTAs of a large local transfer on the main stream: highest priority
+    int lo = 0, hi = 0;
+    CX_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CX_CUDA(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
+  }
   CX_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CX_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   CX_CUDA(cudaEventCreate(&c->ev0));
@@ -685,6 +691,15 @@ int cx_scatter_dev(cx_ctx* c, int nvars, const double* d_in, long long ld, int n
   return 0;
 }
 
+// receptor indices in the plan's own (regrouped, sorted) entry order: what a receptor rank needs to scatter a
+// dense block written with mode 2
+int cx_plan_sorted_rcv(cx_plan* P, int* out)
+{
+  if (P->n == 0) return 0;
+  CX_CUDA(cudaMemcpy(out, P->d_rcv, sizeof(int) * (size_t)P->n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int cx_plan_info(cx_plan* P, int* n, int* ngroups, long long* alg_fixed, long long* distinct)
 {
   if (n) *n = P->n;
@@ -724,7 +739,7 @@ int cx_plan_destroy(cx_plan* P)
   if (!P) return 0;
   cx_plan_full* F = (cx_plan_full*)P;
   for (auto& G : P->groups) { cudaFree(G.d_cf); if (G.d_tiles) cudaFree(G.d_tiles); }
-  cudaFree(P->d_donor); cudaFree(P->d_rcv); cudaFree(P->d_pos);
+  cudaFree(P->d_donor); cudaFree(P->d_rcv); cudaFree(P->d_pos); cudaFree(P->d_seq);
   if (F->d_fields) cudaFree(F->d_fields);
   if (F->d_dense) cudaFree(F->d_dense);
   if (F->h_dense) cudaFreeHost(F->h_dense);

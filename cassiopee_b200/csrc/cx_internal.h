@@ -78,6 +78,7 @@ struct cx_plan {
   struct Group { int type, ncf, sten, n, first; double* d_cf; int layout; void* d_tiles; int ntiles, ntx, nty; };
   std::vector<Group> groups;
   int* d_donor; int* d_rcv; int* d_pos;   // regrouped order; pos = original entry position
+  int* d_seq;                             // 0..n-1 (dense output in the plan's own order)
   long long alg_bytes_fixed;              // sum over entries of (8*ncf + 12)
   long long distinct_nodes;               // U (computed on demand)
   float last_ms;

@@ -1,0 +1,112 @@
+// cx_p2p.cu — peer-memory transport of the cross-GPU donor->receptor values.
+//
+// With NCCL the step of a rank is  remote plans -> send buffers -> ncclSend/ncclRecv -> scatter  and its cost at
+// C4 sizes is the latency of the grouped send/recv (7 peers at 8 GPUs), not the bytes.  Here the donor-side
+// transfer kernel itself is the sender: the receive buffers of every rank are exported with CUDA IPC, mapped
+// by the donor ranks, and the remote plans write their dense (nvars, n_pair) blocks straight into the
+// receptor rank's buffer with coalesced NVLink stores (entries are written in the plan's sorted order; the
+// receptor rank got the matching index list once at set-up).  Completion is a flag per rank pair:
+//     donor rank   : remote plans (stores to peer memory) ; k_p2p_signal: fence.sys, flag[peer][me] = iter
+//     receptor rank: k_p2p_wait spins until flag[me][peer] >= iter for every peer ; scatter
+// Receive buffers are double-buffered by iteration parity.  A rank only writes buffer (i+2)%2 of a peer after it
+// has itself seen that peer's flag i+1, which the peer raises after its scatter of iteration i on the same
+// stream, so no acknowledgement message is needed (flags are exchanged both ways for every pair, also when one
+// direction carries no data).
+#include "cx_internal.h"
+#include "../../include/cassiopee_b200.h"
+#include <dlfcn.h>
+#include <map>
+#include <string>
+#include <string.h>
+
+namespace {
+__global__ void k_p2p_signal(int npeers, int* const* __restrict__ peer_flags, int iter)
+{
+  int p = threadIdx.x;
+  if (p >= npeers) return;
+  __threadfence_system();                       // the remote plans' stores (previous kernel) are performed; order the flag after them
+  *((volatile int*)peer_flags[p]) = iter;
+}
+__global__ void k_p2p_wait(int npeers, const int* my_flags, int iter)
+{
+  int p = threadIdx.x;
+  if (p < npeers)
+  {
+    const volatile int* f = my_flags + p;
+    while (*f < iter) { __nanosleep(100); }
+  }
+  __threadfence_system();
+}
+
+typedef int (*cuMemGetAddressRange_t)(unsigned long long*, size_t*, unsigned long long);
+cuMemGetAddressRange_t g_range = nullptr;
+int load_range()
+{
+  if (g_range) return 0;
+  void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { cx_set_error("cannot dlopen libcuda.so.1: %s", dlerror()); return -5; }
+  g_range = (cuMemGetAddressRange_t)dlsym(h, "cuMemGetAddressRange_v2");
+  if (!g_range) { cx_set_error("cuMemGetAddressRange_v2 missing"); return -5; }
+  return 0;
+}
+std::map<std::string, void*> g_opened;           // IPC handle bytes -> mapped base (a handle can be opened once per process)
+}  // namespace
+
+extern "C" {
+
+// handle72 = 64-byte cudaIpcMemHandle_t of the allocation that contains dptr + 8-byte offset of dptr inside it
+int cx_ipc_export(void* dptr, void* handle72)
+{
+  CX_CHECK(load_range());
+  unsigned long long base = 0; size_t size = 0;
+  if (g_range(&base, &size, (unsigned long long)(uintptr_t)dptr) != 0) { cx_set_error("cuMemGetAddressRange failed"); return -2; }
+  cudaIpcMemHandle_t h;
+  CX_CUDA(cudaIpcGetMemHandle(&h, (void*)(uintptr_t)base));
+  memcpy(handle72, &h, 64);
+  unsigned long long off = (unsigned long long)(uintptr_t)dptr - base;
+  memcpy((char*)handle72 + 64, &off, 8);
+  return 0;
+}
+
+int cx_ipc_open(cx_ctx* ctx, const void* handle72, void** dptr)
+{
+  CX_CUDA(cudaSetDevice(ctx->device));
+  std::string key((const char*)handle72, 64);
+  void* base = nullptr;
+  auto it = g_opened.find(key);
+  if (it != g_opened.end()) base = it->second;
+  else
+  {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle72, 64);
+    CX_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    g_opened[key] = base;
+  }
+  unsigned long long off;
+  memcpy(&off, (const char*)handle72 + 64, 8);
+  *dptr = (char*)base + off;
+  return 0;
+}
+
+int cx_ipc_close_all(void)
+{
+  for (auto& kv : g_opened) cudaIpcCloseMemHandle(kv.second);
+  g_opened.clear();
+  return 0;
+}
+
+}  // extern "C"
+
+// used by cx_step_run (cx_transfer.cu, declared there inside its extern "C" block)
+extern "C" int cx_p2p_signal_on(cudaStream_t s, int npeers, int* const* d_peer_flags, int iter)
+{
+  if (npeers <= 0) return 0;
+  k_p2p_signal<<<1, 32, 0, s>>>(npeers, d_peer_flags, iter);
+  return 0;
+}
+extern "C" int cx_p2p_wait_on(cudaStream_t s, int npeers, const int* d_my_flags, int iter)
+{
+  if (npeers <= 0) return 0;
+  k_p2p_wait<<<1, 32, 0, s>>>(npeers, d_my_flags, iter);
+  return 0;
+}

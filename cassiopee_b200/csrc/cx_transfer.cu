@@ -631,6 +631,11 @@ __global__ void k_plan_place(int n, int T, int ncf, int m, int sorted, const int
   const double* c = coefs + off[e];
   for (int k = 0; k < ncf; k++) cfT[(size_t)k * m + slot] = c[k];
 }
+__global__ void k_iota(int n, int* __restrict__ a)
+{
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) a[e] = e;
+}
 __global__ void k_plan_flag(int n, int T, const int* __restrict__ type, unsigned long long* __restrict__ f)
 {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -741,7 +746,7 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
                   const int* rcv, const int* type, const double* coefs, long long ncoefs, cx_plan* P)
 {
   P->ctx = ctx; P->imd = imd; P->jmd = jmd; P->nptsD = (int)nptsD; P->nptsR = (int)nptsR; P->n = n;
-  P->d_donor = P->d_rcv = P->d_pos = nullptr; P->alg_bytes_fixed = 0; P->distinct_nodes = -1; P->last_ms = 0.f;
+  P->d_donor = P->d_rcv = P->d_pos = P->d_seq = nullptr; P->alg_bytes_fixed = 0; P->distinct_nodes = -1; P->last_ms = 0.f;
   P->groups.clear();
   if (n == 0) { P->ngroups = 0; return 0; }
   const int types[4] = {1, 2, 3, 5};
@@ -780,6 +785,8 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
   CX_MALLOC(P->d_donor, sizeof(int) * N, s);
   CX_MALLOC(P->d_rcv, sizeof(int) * N, s);
   CX_MALLOC(P->d_pos, sizeof(int) * N, s);
+  CX_MALLOC(P->d_seq, sizeof(int) * N, s);
+  k_iota<<<cx_grid(n, 256), 256, 0, s>>>(n, P->d_seq);
   const int TB = 256;
   int first = 0;
   for (int g = 0; g < 4; g++)
@@ -834,10 +841,11 @@ static int tiled_smem_optin()
 }
 
 
-// mode 0: in-place scatter into receptor fields; mode 1: dense (nvars, ld) output
 int cx_plan_launch(cx_plan* P, int nvars, const double* const* dD, double* const* dR, double* dense, long long ld,
-                   int mode, cudaStream_t s)
+                   int mode_in, cudaStream_t s)
 {
+  // mode 0: in place; 1: dense, original entry order (pos); 2: dense, the plan's own sorted order (coalesced stores)
+  const int mode = mode_in == 0 ? 0 : 1;
   cx_ctx* ctx = P->ctx;
   const int TB = 256;
   for (int v0 = 0; v0 < nvars; v0 += CX_MAXVARS)
@@ -850,7 +858,8 @@ int cx_plan_launch(cx_plan* P, int nvars, const double* const* dD, double* const
     for (auto& G : P->groups)
     {
       int grid = cx_grid(G.n, TB);
-      const int* dn_ = P->d_donor + G.first; const int* rc_ = P->d_rcv + G.first; const int* ps_ = P->d_pos + G.first;
+      const int* dn_ = P->d_donor + G.first; const int* rc_ = P->d_rcv + G.first;
+      const int* ps_ = (mode_in == 2 ? P->d_seq : P->d_pos) + G.first;
       int imd = P->imd, ij = P->imd * P->jmd;
 #define CX_LAUNCH(T)                                                                                           \
       if (mode == 0) k_transfer<T, 0><<<grid, TB, 0, s>>>(G.n, nv, F, imd, ij, dn_, rc_, ps_, G.d_cf, dn, ld); \
@@ -967,7 +976,7 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
     if (P->n >= CX_BIG_PLAN)
     {
       cx_planset::Big B;
-      B.P = P; B.mode = modes[p]; B.dense = modes[p] == 1 ? d_dense[p] : nullptr; B.ld = modes[p] == 1 ? ld[p] : 0;
+      B.P = P; B.mode = modes[p]; B.dense = modes[p] != 0 ? d_dense[p] : nullptr; B.ld = modes[p] != 0 ? ld[p] : 0;
       B.dD.assign(d_fieldD[p], d_fieldD[p] + nvars);
       if (modes[p] == 0) B.dR.assign(d_fieldR[p], d_fieldR[p] + nvars);
       S->big.push_back(B);
@@ -980,15 +989,16 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
     {
       int t = G.type == 1 ? 0 : G.type == 2 ? 1 : G.type == 3 ? 2 : 3;
       SetDesc D;
-      D.m = G.n; D.type = G.type; D.imd = P->imd; D.imdjmd = P->imd * P->jmd; D.mode = modes[p]; D.first_block = nb[t];
+      D.m = G.n; D.type = G.type; D.imd = P->imd; D.imdjmd = P->imd * P->jmd; D.mode = modes[p] == 0 ? 0 : 1; D.first_block = nb[t];
       D.nptsD = P->nptsD; D.layout = G.layout; D.jmd = P->jmd; D.ntx = G.ntx; D.nty = G.nty;
       D.tiles = (const TileRef*)G.d_tiles;
       if (G.type == 2 && G.layout == 2) { S->smem = std::max(S->smem, sizeof(double) * CX_BOXV * (size_t)nvars); S->tiled = 1; }
       if (G.type == 2 && G.layout == 1) S->smem = std::max(S->smem, sizeof(StageSmem));
       if (G.type == 3 && G.layout == 1) S->smem3 = sizeof(StageSmemO<3>);
       for (int v = 0; v < nvars; v++) if (((uintptr_t)d_fieldD[p][v]) & 15) S->staged = 0;
-      D.donor = P->d_donor + G.first; D.idx = (modes[p] == 0 ? P->d_rcv : P->d_pos) + G.first; D.cfT = G.d_cf;
-      D.dptr = td; D.rptr = tr; D.dense = modes[p] == 1 ? d_dense[p] : nullptr; D.ld = modes[p] == 1 ? ld[p] : 0;
+      D.donor = P->d_donor + G.first;
+      D.idx = (modes[p] == 0 ? P->d_rcv : modes[p] == 1 ? P->d_pos : P->d_seq) + G.first; D.cfT = G.d_cf;
+      D.dptr = td; D.rptr = tr; D.dense = modes[p] != 0 ? d_dense[p] : nullptr; D.ld = modes[p] != 0 ? ld[p] : 0;
       int blocks = (G.type == 2 && G.layout == 2) ? G.ntiles : cx_grid(G.n, TB);
       for (int b = 0; b < blocks; b++) b2d[t].push_back((int)descs[t].size());
       descs[t].push_back(D);
@@ -1093,8 +1103,13 @@ int cx_scatterset_run(cx_scatterset* S) { return scatterset_run_on(S, S->ctx->st
 extern int cx_exchange_on_stream(cx_ctx* ctx, cudaStream_t st, int npeers, const int* peers, const double* const* d_send,
                                  const long long* sendcounts, double* const* d_recv, const long long* recvcounts);
 
+int cx_p2p_signal_on(cudaStream_t s, int npeers, int* const* d_peer_flags, int iter);
+int cx_p2p_wait_on(cudaStream_t s, int npeers, const int* d_my_flags, int iter);
+
 struct cx_step {
   cx_ctx* ctx; cx_planset* ps_remote; cx_planset* ps_local; cx_scatterset* ss;
+  // peer-memory transport (cx_p2p.cu): plan sets / scatter sets per buffer parity, flags
+  int p2p; cx_planset* ps_remote2[2]; cx_scatterset* ss2[2]; int npeers_p2p; int** d_peer_flags; int* d_my_flags; int iter;
   std::vector<int> peers; std::vector<const double*> sp; std::vector<double*> rp;
   std::vector<long long> sc, rc;
   int overlap;
@@ -1106,6 +1121,7 @@ int cx_step_create(cx_ctx* ctx, cx_planset* ps_remote, cx_planset* ps_local, cx_
 {
   cx_step* S = new cx_step;
   S->ctx = ctx; S->ps_remote = ps_remote; S->ps_local = ps_local; S->ss = ss; S->overlap = 1;
+  S->p2p = 0; S->d_peer_flags = nullptr; S->d_my_flags = nullptr; S->iter = 0; S->npeers_p2p = 0;
   for (int p = 0; p < npeers; p++)
   {
     S->peers.push_back(peers[p]); S->sp.push_back(d_send[p]); S->rp.push_back(d_recv[p]);
@@ -1115,8 +1131,55 @@ int cx_step_create(cx_ctx* ctx, cx_planset* ps_remote, cx_planset* ps_local, cx_
   return 0;
 }
 
+// Peer-memory step.  ps_remote[par] writes into the peers' receive buffers of parity par (IPC-mapped),
+// ss[par] scatters this rank's receive buffers of parity par; peer_flags[p] = address (in peer p's memory) of the
+// flag this rank raises, d_my_flags[p] = the flag peer p raises here.
+int cx_step_create_p2p(cx_ctx* ctx, cx_planset* ps_remote0, cx_planset* ps_remote1, cx_planset* ps_local,
+                       cx_scatterset* ss0, cx_scatterset* ss1, int npeers, int* const* peer_flags, int* d_my_flags,
+                       cx_step** out)
+{
+  CX_CUDA(cudaSetDevice(ctx->device));
+  cx_step* S = new cx_step;
+  S->ctx = ctx; S->ps_remote = nullptr; S->ps_local = ps_local; S->ss = nullptr; S->overlap = 1;
+  S->p2p = 1; S->ps_remote2[0] = ps_remote0; S->ps_remote2[1] = ps_remote1; S->ss2[0] = ss0; S->ss2[1] = ss1;
+  S->npeers_p2p = npeers; S->d_my_flags = d_my_flags; S->iter = 0; S->d_peer_flags = nullptr;
+  if (npeers > 32) { cx_set_error("peer-memory step: at most 32 peers"); delete S; return -1; }
+  if (npeers > 0)
+  {
+    CX_CUDA(cudaMalloc(&S->d_peer_flags, sizeof(int*) * (size_t)npeers));
+    CX_CUDA(cudaMemcpy(S->d_peer_flags, peer_flags, sizeof(int*) * (size_t)npeers, cudaMemcpyHostToDevice));
+  }
+  *out = S;
+  return 0;
+}
+
+static int step_run_p2p(cx_step* S, int niter, int overlap)
+{
+  cx_ctx* c = S->ctx;
+  cudaStream_t s = c->stream, cs = overlap ? c->comm_stream : c->stream;
+  const bool comm = S->npeers_p2p > 0;
+  for (int it = 0; it < niter; it++)
+  {
+    const int iter = ++S->iter, par = iter & 1;
+    if (comm && overlap) { CX_CUDA(cudaEventRecord(c->ev_fork, s)); CX_CUDA(cudaStreamWaitEvent(cs, c->ev_fork, 0)); }
+    if (S->ps_remote2[par]) CX_CHECK(planset_run_on(S->ps_remote2[par], comm ? cs : s));
+    if (comm)
+    {
+      CX_CHECK(cx_p2p_signal_on(cs, S->npeers_p2p, S->d_peer_flags, iter));
+      CX_CHECK(cx_p2p_wait_on(cs, S->npeers_p2p, S->d_my_flags, iter));
+      c->launches += 2;
+      if (S->ss2[par]) CX_CHECK(scatterset_run_on(S->ss2[par], cs));
+      if (overlap) CX_CUDA(cudaEventRecord(c->ev_join, cs));
+    }
+    if (S->ps_local) CX_CHECK(planset_run_on(S->ps_local, s));
+    if (comm && overlap) CX_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
+  }
+  return 0;
+}
+
 int cx_step_run(cx_step* S, int niter, int overlap)
 {
+  if (S->p2p) return step_run_p2p(S, niter, overlap);
   cx_ctx* c = S->ctx;
   cudaStream_t s = c->stream, cs = overlap ? c->comm_stream : c->stream;
   const bool comm = !S->peers.empty();
@@ -1144,6 +1207,7 @@ int cx_step_run(cx_step* S, int niter, int overlap)
 int cx_step_destroy(cx_step* S)
 {
   if (!S) return 0;
+  if (S->d_peer_flags) cudaFree(S->d_peer_flags);
   delete S;
   return 0;
 }

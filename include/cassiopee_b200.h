@@ -25,6 +25,7 @@ typedef struct cx_ctx cx_ctx;        /* one CUDA device + stream */
 typedef struct cx_zone cx_zone;      /* donor zone resident on the device + its ADT replica */
 typedef struct cx_result cx_result;  /* output of one setInterpData call */
 typedef struct cx_plan cx_plan;      /* interpData of one (donor zone, receptor zone) pair, device resident */
+typedef struct cx_receptors cx_receptors;   /* receptor points of one zone (cellN == 2), device resident */
 
 const char* cx_last_error(void);
 int cx_version(void);
@@ -91,6 +92,20 @@ int cx_set_interp_data(cx_ctx* ctx, int nrcv, const double* xr, const double* yr
 /* same with receptor coordinates already on the device */
 int cx_set_interp_data_dev(cx_ctx* ctx, int nrcv, const double* d_xr, const double* d_yr, const double* d_zr, int nz,
                            cx_zone* const* zones, int order, int nature, int penalty, int extrap, cx_result** out);
+/* Receptor extraction on the device.  Replaces connector.getInterpolatedPoints(array)
+ * (Connector/Connector/getInterpolatedPoints.cpp:1675-1732: points with |cellN-2| <= 1e-15, source order,
+ * original index 'indcell') and, for loc=1 (centres), K_LOC::node2centerStruct restricted to the selected cells
+ * (KCore/KCore/Loc/node2Center.cpp:118-146, same summation order).  x,y,z: host node coordinates (ni*nj*nk);
+ * cellN: host, at nodes (loc 0) or at centres (loc 1: (ni-1)*(nj-1)*(nk-1) values). */
+int cx_receptors_create(cx_ctx* ctx, int ni, int nj, int nk, const double* x, const double* y, const double* z,
+                        const double* cellN, int loc, cx_receptors** out);
+int cx_receptors_count(cx_receptors* rcv, int* n);
+/* copies to the host: indcell[n] (index in the zone at loc, ascending) and/or the coordinates; any may be NULL */
+int cx_receptors_fetch(cx_receptors* rcv, int* indcell, double* x, double* y, double* z);
+int cx_receptors_destroy(cx_receptors* rcv);
+/* setInterpData on extracted receptors (receptor positions in the result = positions in indcell) */
+int cx_set_interp_data_rcv(cx_ctx* ctx, cx_receptors* rcv, int nz, cx_zone* const* zones, int order, int nature,
+                           int penalty, int extrap, cx_result** out);
 /* two-phase fetch (sizes, then copy into caller-allocated numpy): the 7-list
  * returned by the reference at setInterpData.cpp:1272 —
  * rcv[n], donor[n], type[n] (int32), coefs (ragged f64), extrap[ne] per donor
@@ -131,6 +146,9 @@ int cx_scatter_dev(cx_ctx* ctx, int nvars, const double* d_in, long long ld, int
                    double* const* d_fieldR);
 /* alg_fixed: sum over entries of 8*ncf+12 bytes; distinct: number of distinct
  * donor nodes referenced (U of SURVEY.md 8(d)); B_alg = alg_fixed + 8*N*(n + U) */
+/* receptor indices in the plan's own (regrouped, donor-sorted) entry order = the order of a dense block written
+ * by a plan set with mode 2 */
+int cx_plan_sorted_rcv(cx_plan* plan, int* out);
 int cx_plan_info(cx_plan* plan, int* n, int* ngroups, long long* alg_fixed, long long* distinct);
 int cx_plan_destroy(cx_plan* plan);
 
@@ -163,12 +181,24 @@ typedef struct cx_step cx_step;
 int cx_step_create(cx_ctx* ctx, cx_planset* ps_remote, cx_planset* ps_local, cx_scatterset* ss, int npeers,
                    const int* peers, const double* const* d_send, const long long* sendcounts,
                    double* const* d_recv, const long long* recvcounts, cx_step** out);
+/* Peer-memory transport of the same step (cx_p2p.cu): the remote plans store their dense blocks straight into the
+ * receptor ranks' receive buffers (exported with CUDA IPC, double-buffered by iteration parity: ps_remote0/1,
+ * ss0/1), and a flag per rank pair replaces the message: peer_flags[p] = address in peer p's memory of the
+ * flag this rank raises, d_my_flags[p] = the flag peer p raises here.  No NCCL call inside the iteration. */
+int cx_step_create_p2p(cx_ctx* ctx, cx_planset* ps_remote0, cx_planset* ps_remote1, cx_planset* ps_local,
+                       cx_scatterset* ss0, cx_scatterset* ss1, int npeers, int* const* peer_flags, int* d_my_flags,
+                       cx_step** out);
 int cx_step_run(cx_step* step, int niter, int overlap);
 int cx_step_destroy(cx_step* step);
 
 /* ---- multi-GPU (one process per GPU; NCCL over NVLink) -------------------
  * Replaces the mpi4py pickled isend/recv of Converter/Converter/Mpi4py.py:149-168
  * used by Connector/Mpi.py:396-440: one packed device buffer per peer rank. */
+/* CUDA IPC: 72-byte descriptor (cudaIpcMemHandle_t of the containing allocation + offset) of a device pointer,
+ * and its mapping in another process of the same node */
+int cx_ipc_export(void* dptr, void* handle72);
+int cx_ipc_open(cx_ctx* ctx, const void* handle72, void** dptr);
+int cx_ipc_close_all(void);
 int cx_comm_unique_id(char* id128);
 int cx_comm_init(cx_ctx* ctx, int rank, int nranks, const char* id128);
 int cx_comm_destroy(cx_ctx* ctx);

@@ -27,5 +27,25 @@ class OracleBackend:
         from oracle import oracle as O
         return O.set_interp_data(xr, yr, zr, hooks, order, nature, penalty, extrap)
 
+    def select_receptors(self, ni, nj, nk, x, y, z, cellN, loc):
+        """numpy restatement of getInterpolatedPoints (+ node2Center of the selected cells)."""
+        import cassiopee_b200.Converter as C
+        tcn = cellN - 2.
+        sel = np.nonzero((tcn >= -1.e-15) & (tcn <= 1.e-15))[0]
+        shp = (ni, nj, nk)
+        if loc == 'nodes':
+            pts = [np.ascontiguousarray(a[sel]) for a in (x, y, z)]
+        else:
+            pts = [C.node2CenterSelected(a.reshape(shp, order='F'), sel) for a in (x, y, z)]
+        return OracleReceptors(sel.astype(np.int32), pts)
+
+    def set_interp_data_rcv(self, rcv, hooks, order, nature, penalty, extrap):
+        return self.set_interp_data(rcv.pts[0], rcv.pts[1], rcv.pts[2], hooks, order, nature, penalty, extrap)
+
     def make_plan(self, *a):
         return OraclePlan(*a)
+
+
+class OracleReceptors:
+    def __init__(self, indcell, pts):
+        self.indcell = indcell; self.pts = pts; self.n = indcell.size

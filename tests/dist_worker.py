@@ -106,9 +106,11 @@ def main():
                         comm=comm, zoneOrder=zoneOrder, backend=backend, ctx=ctx)
     if mode == 'nccl':
         sess = Xmpi.TransferSession(tl, tcl, VARS, comm=comm, ctx=ctx)
-        for _ in range(2):
+        for _ in range(3):          # odd count: both buffer parities of the peer-memory transport are used
             sess.step()
         sess.download()
+        if rank == 0:
+            print("transport=%s" % sess.transport)
     else:
         Xmpi._setInterpTransfers(tl, tcl, variables=VARS, comm=comm, backend=backend)
     mine = collect(tcl, tl)

@@ -8,8 +8,10 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(nproc, mode, order=2, port=29611, case='c4'):
+def _run(nproc, mode, order=2, port=29611, case='c4', transport=None):
     env = dict(os.environ)
+    if transport:
+        env["CX_TRANSPORT"] = transport
     env["OMP_NUM_THREADS"] = "2"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py"),
@@ -41,7 +43,9 @@ def test_world2_nccl_device_backend_multibody_nodes():
     _lib.lib().cx_device_count(ctypes.byref(n))
     if n.value < 2:
         pytest.skip("needs 2 GPUs")
-    _run(2, "nccl", 2, 29615, case='c2n')
+    for k, transport in enumerate(("p2p", "nccl")):
+        out = _run(2, "nccl", 2, 29615 + k, case='c2n', transport=transport)
+        assert ("transport=" + transport) in out
 
 
 @pytest.mark.gpu
@@ -52,4 +56,6 @@ def test_world2_nccl_device_backend():
     _lib.lib().cx_device_count(ctypes.byref(n))
     if n.value < 2:
         pytest.skip("needs 2 GPUs")
-    _run(2, "nccl", 2, 29613)
+    for k, transport in enumerate(("p2p", "nccl")):
+        out = _run(2, "nccl", 2, 29617 + k, transport=transport)
+        assert ("transport=" + transport) in out

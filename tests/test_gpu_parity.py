@@ -330,3 +330,32 @@ def test_interpcart_pytree_api(ctx):
         zb = Internal.getZones(tR)[0]
         x, y, z = C.getCoords(zb)
         assert np.abs(C.getFieldArray(zb, 'F') - (x + 2 * y + 3 * z)).max() < 1e-12
+
+
+@pytest.mark.parametrize("loc", ["nodes", "centers"])
+def test_receptor_extraction_on_device(ctx, loc):
+    """cx_receptors_create (getInterpolatedPoints + node2Center of the selected cells on the device) against the
+    numpy restatement used by the CPU tests; then setInterpData on the resident receptors == host-pointer call."""
+    from cassiopee_b200 import _lib
+    from tests.backends import OracleBackend
+    Bg, Oc = cases.c2()
+    ni, nj, nk, x, y, z = Oc
+    rng = np.random.default_rng(9)
+    npts = ni * nj * nk if loc == "nodes" else (ni - 1) * (nj - 1) * (nk - 1)
+    c = np.ones(npts); c[rng.random(npts) < 0.3] = 2.; c[rng.random(npts) < 0.1] = 0.
+    c[rng.random(npts) < 0.05] = 2. + 1.e-15; c[rng.random(npts) < 0.05] = 2. + 4.e-15
+    dev = _lib.DeviceBackend(ctx).select_receptors(ni, nj, nk, x, y, z, c, loc)
+    ref = OracleBackend().select_receptors(ni, nj, nk, x, y, z, c, loc)
+    assert dev.n == ref.n and dev.n > 0
+    assert np.array_equal(dev.indcell, ref.indcell)
+    for a, b in zip(dev.coords(), ref.pts):
+        assert np.array_equal(a, b)
+    gz, _ = _zones(ctx, [Bg])
+    got = _lib.set_interp_data_rcv(ctx, dev, gz, 2, 1, 1, 1).fetch()
+    exp = _lib.set_interp_data(ctx, ref.pts[0], ref.pts[1], ref.pts[2], gz, 2, 1, 1, 1).fetch()
+    for q in range(5):
+        assert np.array_equal(got[q][0], exp[q][0])
+    assert np.array_equal(got[5], exp[5])
+    # no receptor at all
+    empty = _lib.DeviceBackend(ctx).select_receptors(ni, nj, nk, x, y, z, np.ones(npts), loc)
+    assert empty.n == 0 and empty.indcell.size == 0
