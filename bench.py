@@ -503,8 +503,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    # stdout carries exactly one JSON line: NCCL's version banner / warnings go to a file
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/cx_nccl_%h_%p.log")
+    # stdout carries exactly one JSON line: anything a library prints on fd 1 (e.g. NCCL's version banner) is sent
+    # to stderr, and print() keeps writing to the real stdout
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
     if args.workload == "c4":
         from bench_c4 import run_c4
         return run_c4(args)

@@ -1,0 +1,136 @@
+"""GPU tests at BASELINE.json's full sizes (run with -m gpu on the B200).
+
+The oracle's serial ADT build cannot finish at these sizes, so the full-size checks are
+  * bit-exact parity against the oracle where the reference itself has no tree (interpDataType=0, InterpCart):
+    C2a, all 17.0 M receptors;
+  * size-independent properties of the ADT path (C2a order 2, C4 cluster): every receptor found, ascending
+    receptor lists, coefficients summing to 1, the donor cell of the ADT path = the cell the closed-form
+    Cartesian search finds (points strictly inside a cell), a linear field reproduced to 1e-12 by the transfer,
+    transfers idempotent and linear in the donor field, and dense / in-place / host / device variants agreeing."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c2a(ctx):
+    from cassiopee_b200 import workloads as W
+    Bg, Oc = W.c2(1.0)
+    return Bg, Oc
+
+
+def test_c2a_fullsize_interpcart_bit_exact_vs_reference(ctx, c2a):
+    from cassiopee_b200 import _lib
+    from oracle import oracle as O
+    Bg, Oc = c2a
+    gz = _lib.Zone(ctx, Bg.ni, Bg.nj, Bg.nk, Bg.x, Bg.y, Bg.z, interpDataType=0)
+    oz = O.RefZone(Bg.ni, Bg.nj, Bg.nk, Bg.x, Bg.y, Bg.z, interpDataType=0)
+    for order in (2, 3):
+        got = _lib.set_interp_data(ctx, Oc.x, Oc.y, Oc.z, [gz], order, 1, 1, 1).fetch()
+        ref = O.set_interp_data(Oc.x, Oc.y, Oc.z, [oz], order, 1, 1, 1)
+        assert got[0][0].size == Oc.npts
+        for q in range(5):
+            assert np.array_equal(got[q][0], ref[q][0]), (order, q)
+        assert np.array_equal(got[5], ref[5])
+
+
+def test_c2a_fullsize_adt_path_properties(ctx, c2a):
+    from cassiopee_b200 import _lib
+    Bg, Oc = c2a
+    n = Oc.npts
+    zone = _lib.Zone(ctx, Bg.ni, Bg.nj, Bg.nk, Bg.x, Bg.y, Bg.z)
+    out = _lib.set_interp_data(ctx, Oc.x, Oc.y, Oc.z, [zone], 2, 1, 1, 1).fetch()
+    rcv, dnr, typ, cf = out[0][0], out[1][0], out[2][0], out[3][0]
+    assert rcv.size == n and out[5].size == 0 and out[4][0].size == 0        # all found, none extrapolated
+    assert np.array_equal(rcv, np.arange(n, dtype=np.int32))                  # ascending receptor order
+    assert set(np.unique(typ)) <= {1, 2}
+    t2 = typ == 2
+    ncf = np.where(t2, 8, 1)
+    off = np.concatenate([[0], np.cumsum(ncf)[:-1]])
+    assert cf.size == ncf.sum()
+    c8 = cf[(off[t2][:, None] + np.arange(8)[None, :])]
+    assert np.abs(c8.sum(axis=1) - 1.).max() < 1e-12 and c8.min() > -1e-3    # partition of unity, inside the cell
+    # the donor cell is the one the closed-form Cartesian search finds, for points strictly inside a cell
+    zc = _lib.Zone(ctx, Bg.ni, Bg.nj, Bg.nk, Bg.x, Bg.y, Bg.z, interpDataType=0)
+    oc = _lib.set_interp_data(ctx, Oc.x, Oc.y, Oc.z, [zc], 2, 1, 1, 1).fetch()
+    h = (Bg.x[1] - Bg.x[0], Bg.y[Bg.ni] - Bg.y[0], Bg.z[Bg.ni * Bg.nj] - Bg.z[0])
+    fr = [((a - a0) / hh) % 1. for a, a0, hh in ((Oc.x, Bg.x[0], h[0]), (Oc.y, Bg.y[0], h[1]), (Oc.z, Bg.z[0], h[2]))]
+    interior = t2 & (oc[2][0] == 2)
+    for f in fr:
+        interior &= (f > 1e-6) & (f < 1. - 1e-6)
+    assert interior.sum() > 0.5 * n
+    assert np.array_equal(dnr[interior], oc[1][0][interior])
+    # transfers: linear field exact, idempotent, linear in the donor field, variants agree
+    plan = _lib.Plan(ctx, Bg.ni, Bg.nj, Bg.nk, n, dnr, rcv, typ, cf)
+    F = Bg.x + 2 * Bg.y + 3 * Bg.z
+    rng = np.random.default_rng(0)
+    G = rng.standard_normal(Bg.npts)
+    oF = np.zeros(n); oG = np.zeros(n); oS = np.zeros(n)
+    plan.transfer([F, G], [oF, oG])
+    assert np.abs(oF - (Oc.x + 2 * Oc.y + 3 * Oc.z)).max() < 1e-12
+    oF2 = oF.copy(); oG2 = np.zeros(n)
+    plan.transfer([F, G], [oF2, oG2])
+    assert np.array_equal(oF2, oF) and np.array_equal(oG2, oG)
+    plan.transfer([F + G], [oS])
+    assert np.abs(oS - (oF + oG)).max() < 1e-12 * max(1., np.abs(oS).max())
+    dense = plan.transferD([F, G])
+    assert np.array_equal(dense[0], oF) and np.array_equal(dense[1], oG)      # rcv is the identity here
+    dD = [_lib.DeviceArray.from_host(ctx, a) for a in (F, G)]
+    dR = [_lib.DeviceArray(ctx, n) for _ in range(2)]
+    plan.transfer_dev([d.ptr for d in dD], [d.ptr for d in dR]); ctx.sync()
+    assert np.array_equal(dR[0].download(), oF) and np.array_equal(dR[1].download(), oG)
+    # checksum of checksums: the order of evaluation inside a launch does not matter
+    assert float(np.sum(oG.view(np.uint64) % 1000003)) == float(np.sum(dR[1].download().view(np.uint64) % 1000003))
+
+
+def test_c4_cluster_fullsize_properties(ctx):
+    """8 zones of 100^3 (the per-GPU share of C4): distributed code path with one rank, linear field exact on
+    every interpolated receptor, both plan-set launch and per-plan host-pointer transfers agree."""
+    import cassiopee_b200.Converter as C
+    import cassiopee_b200.Generator as G
+    import cassiopee_b200.Internal as Internal
+    import cassiopee_b200.Connector.Mpi as Xmpi
+    import cassiopee_b200.Connector.PyTree as X
+    from cassiopee_b200 import workloads as W
+    blocks = W.c4_layout((2, 2, 2), n=100, overlap=8, seed=1)
+    zones = []
+    for b in blocks:
+        z = G.cart(b['origin'], (b['h'],) * 3, (b['n'],) * 3, name=b['name'])
+        C._initVars(z, 'centers:cellN', W.c4_receptor_mask(b, blocks, depth=2))
+        C._initVars(z, 'centers:F', lambda x, y, zz: x + 2 * y + 3 * zz)
+        zones.append(z)
+    t = C.newPyTree(['Base'] + zones)
+    tc = C.node2Center(t)
+    Xmpi._setInterpData(t, tc, order=2, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse', comm=None,
+                        zoneOrder=[b['name'] for b in blocks], ctx=ctx, verbose=0)
+    nrcv = 0
+    orphans = {}
+    for zd in Internal.getZones(tc):
+        for s in Internal.getNodesFromType1(zd, 'ZoneSubRegion_t'):
+            pld = Internal.getNodeFromName1(s, 'PointListDonor')[1]
+            assert np.array_equal(pld, np.sort(pld)) and np.unique(pld).size == pld.size
+            o = Internal.getNodeFromName1(s, 'OrphanPointList')
+            if o is not None:
+                orphans[Internal.getValue(s)] = o[1]
+            nrcv += pld.size
+    norph = sum(v.size for v in orphans.values())
+    mask_total = sum(int((C.getFieldArray(z, 'centers:cellN') == 2.).sum()) for z in Internal.getZones(t))
+    assert nrcv + norph == mask_total and nrcv > 400000 and norph < 0.001 * mask_total
+    for z in Internal.getZones(t):          # orphans keep their value: take them out of the receptor mask
+        if z[0] in orphans:
+            C.getFieldArray(z, 'centers:cellN').reshape(-1, order='F')[orphans[z[0]]] = 1.
+    # receptors zeroed, then transferred back: exact for a linear field
+    exact = {}
+    for z in Internal.getZones(t):
+        f = C.getFieldArray(z, 'centers:F'); m = C.getFieldArray(z, 'centers:cellN') == 2.
+        exact[z[0]] = f.copy(); f[m] = 0.
+    t2 = X.setInterpTransfers(t, tc, variables=['F'], storage=1)
+    for z in Internal.getZones(t2):
+        assert np.abs(C.getFieldArray(z, 'centers:F') - exact[z[0]]).max() < 1e-12
+    for z in Internal.getZones(t):
+        f = C.getFieldArray(z, 'centers:F'); f[C.getFieldArray(z, 'centers:cellN') == 2.] = 0.
+    sess = Xmpi.TransferSession(t, tc, ['F'], comm=None, ctx=ctx)
+    sess.step(2); sess.download()
+    for z in Internal.getZones(t):
+        assert np.abs(C.getFieldArray(z, 'centers:F') - exact[z[0]]).max() < 1e-12
