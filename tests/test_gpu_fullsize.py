@@ -102,10 +102,13 @@ def test_c4_cluster_fullsize_properties(ctx):
         zones.append(z)
     t = C.newPyTree(['Base'] + zones)
     tc = C.node2Center(t)
+    for z in Internal.getZones(tc):         # node2Center shares the centre arrays: give the donor tree its own F
+        C._initVars(z, 'F', np.array(C.getFieldArray(z, 'F'), order='F', copy=True))
     Xmpi._setInterpData(t, tc, order=2, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse', comm=None,
                         zoneOrder=[b['name'] for b in blocks], ctx=ctx, verbose=0)
     nrcv = 0
     orphans = {}
+    extrap = {}
     for zd in Internal.getZones(tc):
         for s in Internal.getNodesFromType1(zd, 'ZoneSubRegion_t'):
             pld = Internal.getNodeFromName1(s, 'PointListDonor')[1]
@@ -113,6 +116,9 @@ def test_c4_cluster_fullsize_properties(ctx):
             o = Internal.getNodeFromName1(s, 'OrphanPointList')
             if o is not None:
                 orphans[Internal.getValue(s)] = o[1]
+            x = Internal.getNodeFromName1(s, 'ExtrapPointList')
+            if x is not None and x[1].size:
+                extrap.setdefault(Internal.getValue(s), []).append(x[1])
             nrcv += pld.size
     norph = sum(v.size for v in orphans.values())
     mask_total = sum(int((C.getFieldArray(z, 'centers:cellN') == 2.).sum()) for z in Internal.getZones(t))
@@ -120,17 +126,25 @@ def test_c4_cluster_fullsize_properties(ctx):
     for z in Internal.getZones(t):          # orphans keep their value: take them out of the receptor mask
         if z[0] in orphans:
             C.getFieldArray(z, 'centers:cellN').reshape(-1, order='F')[orphans[z[0]]] = 1.
-    # receptors zeroed, then transferred back: exact for a linear field
-    exact = {}
+    # receptors zeroed, then transferred back: exact for a linear field (extrapolated receptors, next to the outer
+    # boundary of the cluster, are not linear-exact by construction of getExtrapolationCoeffForCell: left out)
+    exact = {}; keep = {}
+    next_ = 0
     for z in Internal.getZones(t):
         f = C.getFieldArray(z, 'centers:F'); m = C.getFieldArray(z, 'centers:cellN') == 2.
         exact[z[0]] = f.copy(); f[m] = 0.
+        k = np.ones(f.size, bool)
+        for lst in extrap.get(z[0], []):
+            k[lst] = False; next_ += lst.size
+        keep[z[0]] = k.reshape(f.shape, order='F')
+    assert next_ < 0.2 * nrcv
     t2 = X.setInterpTransfers(t, tc, variables=['F'], storage=1)
     for z in Internal.getZones(t2):
-        assert np.abs(C.getFieldArray(z, 'centers:F') - exact[z[0]]).max() < 1e-12
+        assert np.abs(C.getFieldArray(z, 'centers:F') - exact[z[0]])[keep[z[0]]].max() < 1e-12
+    got1 = {z[0]: C.getFieldArray(z, 'centers:F').copy() for z in Internal.getZones(t2)}
     for z in Internal.getZones(t):
         f = C.getFieldArray(z, 'centers:F'); f[C.getFieldArray(z, 'centers:cellN') == 2.] = 0.
     sess = Xmpi.TransferSession(t, tc, ['F'], comm=None, ctx=ctx)
     sess.step(2); sess.download()
-    for z in Internal.getZones(t):
-        assert np.abs(C.getFieldArray(z, 'centers:F') - exact[z[0]]).max() < 1e-12
+    for z in Internal.getZones(t):      # fused plan-set launch == per-plan host-pointer calls, bit for bit
+        assert np.array_equal(C.getFieldArray(z, 'centers:F'), got1[z[0]])
