@@ -39,7 +39,7 @@ def build_local(bodies, rank, nvars):
 
 def run_c2n(args):
     from bench import METRIC, UNIT, ClockSampler, measured_peaks, NVARS_C2
-    from bench_c4 import _warm, measure_c4
+    from bench_c4 import _warm, measure_c4, strip_interp_data
     from cassiopee_b200 import _lib, Mpi as Cmpi, Distributor2 as D2, workloads as W
     import cassiopee_b200.Internal as Internal
     import cassiopee_b200.Converter as C
@@ -69,12 +69,17 @@ def run_c2n(args):
 
     _warm(ctx)
     # ---- distributed setInterpData (receptor owner computes; neighbour backgrounds replicated) ----
-    barrier()
-    t0 = time.perf_counter()
-    Xmpi._setInterpData(t, t, order=2, nature=1, penalty=1, extrap=1, loc='nodes', storage='inverse',
-                        comm=comm, zoneOrder=zoneOrder, ctx=ctx, verbose=0)
-    barrier()
-    sid_s = time.perf_counter() - t0
+    # called twice: the first call also pays the growth of the device memory pool (see bench_c4.py)
+    sid_calls = []
+    for call in range(2):
+        strip_interp_data(t)
+        barrier()
+        t0 = time.perf_counter()
+        Xmpi._setInterpData(t, t, order=2, nature=1, penalty=1, extrap=1, loc='nodes', storage='inverse',
+                            comm=comm, zoneOrder=zoneOrder, ctx=ctx, verbose=0)
+        barrier()
+        sid_calls.append(time.perf_counter() - t0)
+    sid_s = sid_calls[-1]
     nrcv_local = sum(int((C.getFieldArray(z, 'cellN') == 2.).sum()) for z in Internal.getZones(t))
     norphan = 0
     for z in Internal.getZones(t):
@@ -121,6 +126,7 @@ def run_c2n(args):
     ms_max = max(gather(ms))
     e2e_max = max(gather(e2e_s))
     sid_max = max(gather(sid_s))
+    sid_first = max(gather(sid_calls[0]))
     nrcv = sum(gather(nrcv_local))
     nccl_b = sum(gather(sess.nccl_bytes()))
     h2d = sum(gather(sess.h2d_bytes)); d2h = sum(gather(d2h))
@@ -168,6 +174,8 @@ def run_c2n(args):
                                "k_scatter_set"},
         "cpu_baseline": None,
         "set_interp_data": {"value": nrcv / sid_max, "unit": "receptor pts/s", "receptors": int(nrcv), "s": sid_max,
+                            "s_first_call": sid_first,
+                            "note": "second call (device memory pool warm); the first call is reported beside it",
                             "includes": "host trees in/out: donor-zone replication, device ADT builds, search, packing, "
                                         "D2H of the lists, routing of ID_* subregions to donor owners",
                             "tree_build_s": t_gen},

@@ -73,12 +73,18 @@ def measure_c4(args, ctx, comm, ngpus, rank, world):
     # CUDA module load / first-launch costs are not part of the metric: run the smoke-sized case once
     _warm(ctx)
     # ---- distributed setInterpData ---------------------------------------------
-    barrier()
-    t0 = time.perf_counter()
-    Xmpi._setInterpData(tl, tcl, order=2, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse',
-                        comm=comm, zoneOrder=zoneOrder, ctx=ctx, verbose=0)
-    barrier()
-    sid_s = time.perf_counter() - t0
+    # called twice: the first call also pays the growth of the device memory pool (physical allocation of
+    # ~150 MB per donor zone); a solver with moving grids calls it every few steps with the pool warm
+    sid_calls = []
+    for call in range(2):
+        strip_interp_data(tcl)
+        barrier()
+        t0 = time.perf_counter()
+        Xmpi._setInterpData(tl, tcl, order=2, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse',
+                            comm=comm, zoneOrder=zoneOrder, ctx=ctx, verbose=0)
+        barrier()
+        sid_calls.append(time.perf_counter() - t0)
+    sid_s = sid_calls[-1]
     nrcv_local = sum(int((C.getFieldArray(z, 'centers:cellN') == 2.).sum()) for z in Internal.getZones(tl))
 
     # ---- steady-state transfers --------------------------------------------------
@@ -133,6 +139,7 @@ def measure_c4(args, ctx, comm, ngpus, rank, world):
     ms100_max = max(gather(ms100))
     e2e_max = max(gather(e2e_s))
     sid_max = max(gather(sid_s))
+    sid_first = max(gather(sid_calls[0]))
     nrcv = sum(gather(nrcv_local))
     nccl_b = sum(gather(sess.nccl_bytes()))
     h2d = sum(gather(sess.h2d_bytes)); d2h = sum(gather(d2h))
@@ -170,7 +177,9 @@ def measure_c4(args, ctx, comm, ngpus, rank, world):
                      "frac": value / ngpus / peak, "traffic": None, "peak_source": how,
                      "kernel": "k_transfer_set<2> (+ NCCL send/recv + k_scatter_set inside the step)"},
         "set_interp_data": {"value": nrcv / sid_max, "unit": "receptor pts/s", "receptors": int(nrcv),
-                            "s": sid_max, "includes": "donor-zone replication, device ADT builds, search, "
+                            "s": sid_max, "s_first_call": sid_first,
+                            "note": "second call (device memory pool warm); the first call is reported beside it",
+                            "includes": "donor-zone replication, device ADT builds, search, "
                             "routing of ID_* subregions to donor owners (host trees in/out)"},
     }
 
@@ -197,6 +206,13 @@ def run_c4(args):
     line["cpu_baseline"] = cpu_baseline_c4(args, layout_for(ngpus, int(os.environ.get("CX_C4_N", "100")))[0],
                                            int(os.environ.get("CX_C4_NVARS", "7"))) if (ngpus == 1 and not args.quick) else None
     print(json.dumps(line))
+
+
+def strip_interp_data(t):
+    """Remove the ID_* subregions of a tree (so that setInterpData can be called again on it)."""
+    import cassiopee_b200.Internal as Internal
+    for z in Internal.getZones(t):
+        z[2][:] = [c for c in z[2] if not (c[3] == 'ZoneSubRegion_t' and c[0].startswith('ID_'))]
 
 
 def _warm(ctx):

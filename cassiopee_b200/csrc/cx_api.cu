@@ -6,6 +6,7 @@
 #include <string.h>
 #include <algorithm>
 #include <thread>
+#include <time.h>
 
 using namespace cx;
 
@@ -213,6 +214,13 @@ int cx_pinned_alloc(size_t bytes, void** hptr) { CX_CUDA(cudaHostAlloc(hptr, byt
 int cx_pinned_free(void* hptr) { CX_CUDA(cudaFreeHost(hptr)); return 0; }
 
 /* ---- zones --------------------------------------------------------------- */
+static double wall_ms()
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 int cx_zone_create(cx_ctx* c, int ni, int nj, int nk, const double* x, const double* y, const double* z,
                    const double* cellN, cx_zone** out)
 {
@@ -220,6 +228,8 @@ int cx_zone_create(cx_ctx* c, int ni, int nj, int nk, const double* x, const dou
   if (nk < 2) { cx_set_error("2-D donor zones (nk=1, type 22) are not supported by the device path"); return -4; }
   if ((long long)ni * nj * nk > 2000000000ll) { cx_set_error("donor zone too large for int32 indices"); return -1; }
   CX_CUDA(cudaSetDevice(c->device));
+  const bool prof = getenv("CX_PROFILE_ZONE") != nullptr;
+  double t0 = wall_ms();
   cx_zone* zn = new cx_zone;
   memset(zn, 0, sizeof(*zn));
   zn->ctx = c; zn->ni = ni; zn->nj = nj; zn->nk = nk;
@@ -227,16 +237,24 @@ int cx_zone_create(cx_ctx* c, int ni, int nj, int nk, const double* x, const dou
   zn->ncells = (ni - 1) * (nj - 1) * (nk - 1);
   zn->topo = 1;
   size_t nb = sizeof(double) * (size_t)zn->npts;
-  CX_CUDA(cudaMalloc(&zn->d_x, nb)); CX_CUDA(cudaMalloc(&zn->d_y, nb)); CX_CUDA(cudaMalloc(&zn->d_z, nb));
-  CX_CUDA(cudaMalloc(&zn->d_cellN, nb));
+  // x, y, z, cellN in one block (one allocation instead of four)
+  CX_CUDA(cudaMalloc(&zn->d_x, 4 * nb));
+  zn->d_y = zn->d_x + zn->npts; zn->d_z = zn->d_y + zn->npts; zn->d_cellN = zn->d_z + zn->npts;
+  double t1 = wall_ms();
   CX_CUDA(cudaMemcpyAsync(zn->d_x, x, nb, cudaMemcpyHostToDevice, c->stream));
   CX_CUDA(cudaMemcpyAsync(zn->d_y, y, nb, cudaMemcpyHostToDevice, c->stream));
   CX_CUDA(cudaMemcpyAsync(zn->d_z, z, nb, cudaMemcpyHostToDevice, c->stream));
+  double t2 = wall_ms();
   cx_zone_bbox_host(ni, nj, nk, x, y, z, zn->bbox);
+  double t3 = wall_ms();
   *out = zn;
   int rc = cx_zone_set_celln(zn, cellN);
+  double t4 = wall_ms();
   if (rc == 0) rc = cx_build_adt(zn);
   if (rc != 0) { cx_zone_destroy(zn); *out = nullptr; return rc; }
+  if (prof)
+    fprintf(stderr, "[cx_zone_create %dx%dx%d] alloc %.2f ms, coord upload %.2f, bbox %.2f, cellN %.2f, ADT %.2f (device %.2f), total %.2f\n",
+            ni, nj, nk, t1 - t0, t2 - t1, t3 - t2, t4 - t3, wall_ms() - t4, zn->build_ms, wall_ms() - t0);
   return 0;
 }
 
@@ -262,8 +280,8 @@ int cx_zone_create_cart(cx_ctx* c, int ni, int nj, int nk, const double* x, cons
   zn->bbox[4] = zn->bbox[1] + (nj - 1) * zn->h[1];
   zn->bbox[5] = zn->bbox[2] + (nk - 1) * zn->h[2];
   size_t nb = sizeof(double) * (size_t)zn->npts;
-  CX_CUDA(cudaMalloc(&zn->d_x, nb)); CX_CUDA(cudaMalloc(&zn->d_y, nb)); CX_CUDA(cudaMalloc(&zn->d_z, nb));
-  CX_CUDA(cudaMalloc(&zn->d_cellN, nb));
+  CX_CUDA(cudaMalloc(&zn->d_x, 4 * nb));
+  zn->d_y = zn->d_x + zn->npts; zn->d_z = zn->d_y + zn->npts; zn->d_cellN = zn->d_z + zn->npts;
   CX_CUDA(cudaMemcpyAsync(zn->d_x, x, nb, cudaMemcpyHostToDevice, c->stream));
   CX_CUDA(cudaMemcpyAsync(zn->d_y, y, nb, cudaMemcpyHostToDevice, c->stream));
   CX_CUDA(cudaMemcpyAsync(zn->d_z, z, nb, cudaMemcpyHostToDevice, c->stream));
@@ -357,7 +375,7 @@ int cx_zone_export_adt(cx_zone* zn, void* nodes_out, size_t bytes)
 int cx_zone_destroy(cx_zone* zn)
 {
   if (!zn) return 0;
-  cudaFree(zn->d_x); cudaFree(zn->d_y); cudaFree(zn->d_z); cudaFree(zn->d_cellN); cudaFree(zn->d_nodes);
+  cudaFree(zn->d_x); cudaFree(zn->d_nodes);   // d_y, d_z, d_cellN live in d_x's block
   delete zn;
   return 0;
 }
