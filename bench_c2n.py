@@ -135,6 +135,7 @@ def run_c2n(args):
     launches_all = sum(gather(launches))
     norphan = sum(gather(norphan))
     # free the C2 session before the C4/C5 leg
+    sess.close()
     del sess, t
     import gc
     gc.collect()

@@ -146,6 +146,7 @@ def measure_c4(args, ctx, comm, ngpus, rank, world):
     nplans = sum(gather(len(sess.plans)))
     transport = sess.transport
     launches_all = sum(gather(launches))
+    sess.close()
     if rank != 0:
         return None
     ms_step = ms_max / args.steps

@@ -413,6 +413,7 @@ class TransferSession:
             if err and os.environ.get("CX_PROFILE"):
                 print("[TransferSession] peer-memory transport unavailable (%s); using NCCL" % err, flush=True)
             return False
+        self._ipc_descs = [d for p in self.peers for d in allx[p][rank]]
         try:
             rbuf = {p: [_lib.ipc_open(ctx, allx[p][rank][par]) for par in (0, 1)] for p in self.peers}
             pflags = [_lib.ipc_open(ctx, allx[p][rank][2]) for p in self.peers]
@@ -436,6 +437,20 @@ class TransferSession:
         ctx.sync()
         comm.barrier()      # every rank's flags are zeroed and mapped before anyone signals
         return True
+
+    def close(self):
+        """Collective: unmap the peers' buffers before anybody frees them (peer-memory transport), then drop the
+        device objects of this session.  Call it before deleting the session when another one will follow."""
+        if getattr(self, 'transport', 'none') == 'p2p':
+            self.ctx.sync()
+            self.comm.barrier()                    # nobody is still storing into a peer
+            self._step = None; self._ps2 = None; self.planset_remote = None
+            for d in getattr(self, '_ipc_descs', []):
+                _lib.ipc_close(d)
+            self._ipc_descs = []
+            self.comm.barrier()                    # every mapping is gone: the exporters may free
+            self.recvbuf2 = None; self.flags = None; self._ss2 = None
+        self.transport = 'closed'
 
     def _residentR(self, zr, loc):
         if zr[0] in self.dR:

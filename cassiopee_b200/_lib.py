@@ -73,6 +73,7 @@ _SIGS = {
     "cx_plan_sorted_rcv": (_i, [_vp, _vp]),
     "cx_ipc_export": (_i, [_vp, _vp]),
     "cx_ipc_open": (_i, [_vp, _vp, _vp]),
+    "cx_ipc_close": (_i, [_vp]),
     "cx_ipc_close_all": (_i, []),
     "cx_plan_destroy": (_i, [_vp]),
     "cx_planset_create": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -650,6 +651,10 @@ def ipc_open(ctx, desc):
     p = _vp()
     check(lib().cx_ipc_open(ctx.h, ctypes.c_char_p(desc), ctypes.byref(p)))
     return p.value
+
+
+def ipc_close(desc):
+    lib().cx_ipc_close(ctypes.c_char_p(desc))
 
 
 class StepP2P:

@@ -88,6 +88,17 @@ int cx_ipc_open(cx_ctx* ctx, const void* handle72, void** dptr)
   return 0;
 }
 
+// unmap one imported allocation (all pointers derived from this descriptor become invalid)
+int cx_ipc_close(const void* handle72)
+{
+  std::string key((const char*)handle72, 64);
+  auto it = g_opened.find(key);
+  if (it == g_opened.end()) return 0;
+  cudaIpcCloseMemHandle(it->second);
+  g_opened.erase(it);
+  return 0;
+}
+
 int cx_ipc_close_all(void)
 {
   for (auto& kv : g_opened) cudaIpcCloseMemHandle(kv.second);

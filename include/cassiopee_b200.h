@@ -198,6 +198,7 @@ int cx_step_destroy(cx_step* step);
  * and its mapping in another process of the same node */
 int cx_ipc_export(void* dptr, void* handle72);
 int cx_ipc_open(cx_ctx* ctx, const void* handle72, void** dptr);
+int cx_ipc_close(const void* handle72);   /* unmap; the exporter may free the memory only after this */
 int cx_ipc_close_all(void);
 int cx_comm_unique_id(char* id128);
 int cx_comm_init(cx_ctx* ctx, int rank, int nranks, const char* id128);

@@ -111,6 +111,7 @@ def main():
         sess.download()
         if rank == 0:
             print("transport=%s" % sess.transport)
+        sess.close()
     else:
         Xmpi._setInterpTransfers(tl, tcl, variables=VARS, comm=comm, backend=backend)
     mine = collect(tcl, tl)
