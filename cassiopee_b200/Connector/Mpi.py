@@ -16,6 +16,7 @@ rank pair and iteration, one scatter launch.
 """
 import os
 import time
+import sys as _sys
 import numpy
 from .. import Internal
 from .. import Converter as C
@@ -190,7 +191,7 @@ def _setInterpData(aR, aD, order=2, penalty=1, nature=0, extrap=1, method='lagra
         if hadCellN.get(z[0], 1) == -1: C._rmVars(z, ['cellN'])
     if prof:
         print("[Mpi._setInterpData rank0] graph %.3fs addXZones %.3fs (%d zones) chimera %.3fs routing %.3fs" %
-              (t1 - t0, t2 - t1, len(added), t3 - t2, time.perf_counter() - t3), flush=True)
+              (t1 - t0, t2 - t1, len(added), t3 - t2, time.perf_counter() - t3), file=_sys.stderr, flush=True)
     return None
 
 
@@ -411,7 +412,7 @@ class TransferSession:
         allx = comm.allgather_obj(mine)
         if any(x is None for x in allx):
             if err and os.environ.get("CX_PROFILE"):
-                print("[TransferSession] peer-memory transport unavailable (%s); using NCCL" % err, flush=True)
+                print("[TransferSession] peer-memory transport unavailable (%s); using NCCL" % err, file=_sys.stderr, flush=True)
             return False
         self._ipc_descs = [d for p in self.peers for d in allx[p][rank]]
         try:
@@ -419,7 +420,7 @@ class TransferSession:
             pflags = [_lib.ipc_open(ctx, allx[p][rank][2]) for p in self.peers]
         except _lib.CxError as e:
             if os.environ.get("CX_PROFILE"):
-                print("[TransferSession] cudaIpcOpenMemHandle failed (%s); using NCCL" % e, flush=True)
+                print("[TransferSession] cudaIpcOpenMemHandle failed (%s); using NCCL" % e, file=_sys.stderr, flush=True)
             rbuf = None
         if not all(comm.allgather_obj(rbuf is not None)):
             return False

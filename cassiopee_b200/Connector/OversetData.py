@@ -21,6 +21,7 @@ Differences that do not change results:
 * transfer plans (device-resident interpData) are cached per ID_* subregion.
 """
 import weakref
+import sys as _sys
 import numpy
 from .. import Internal
 from .. import Converter as C
@@ -494,7 +495,7 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
     finally:
         if _prof:
             print("[_setInterpDataChimera] receptor extraction %.3fs, donor hooks (upload+ADT) %.3fs, search+fetch %.3fs, "
-                  "remap+store %.3fs" % (_tt['pts'], _tt['hooks'], _tt['search'], _tt['store']), flush=True)
+                  "remap+store %.3fs" % (_tt['pts'], _tt['hooks'], _tt['search'], _tt['store']), file=_sys.stderr, flush=True)
         if storage != 'direct':
             _adaptForRANSLES__(aR, aD, dictOfModels=dictOfModels)
         for zd in Internal.getZones(aD):

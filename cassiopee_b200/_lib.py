@@ -626,14 +626,15 @@ class DeviceBackend:
 
     def set_interp_data(self, xr, yr, zr, hooks, order, nature, penalty, extrap):
         res = set_interp_data(self.ctx, xr, yr, zr, hooks, order, nature, penalty, extrap)
-        return res.fetch()
+        return res.fetch(pinned=True)
 
     def select_receptors(self, ni, nj, nk, x, y, z, cellN, loc):
         """Receptor points (cellN == 2 at loc) of one zone, extracted and kept on the device."""
         return Receptors(self.ctx, ni, nj, nk, x, y, z, cellN, loc)
 
     def set_interp_data_rcv(self, rcv, hooks, order, nature, penalty, extrap):
-        return set_interp_data_rcv(self.ctx, rcv, hooks, order, nature, penalty, extrap).fetch()
+        # large lists land in page-locked arrays of the reuse pool (they become the tree's numpy arrays)
+        return set_interp_data_rcv(self.ctx, rcv, hooks, order, nature, penalty, extrap).fetch(pinned=True)
 
     def make_plan(self, imd, jmd, kmd, nptsR, donor, rcv, typ, coefs):
         return Plan(self.ctx, imd, jmd, kmd, nptsR, donor, rcv, typ, coefs)

@@ -34,6 +34,7 @@ struct cx_ctx {
   cudaEvent_t ev0, ev1;
   // pinned staging buffer for host<->device copies
   void* pinned; size_t pinned_bytes;
+  cudaEvent_t ev_stage[2];      // staging buffer reuse (cx_upload)
   // counters (kernels launched by this library since creation)
   long long launches;
   // last timed kernel durations (ms), written by entry points that time themselves
@@ -83,6 +84,9 @@ struct cx_plan {
   long long distinct_nodes;               // U (computed on demand)
   float last_ms;
 };
+
+// pageable host -> device at bus speed (cx_api.cu); ordered on ctx->stream, host buffer reusable on return
+int cx_upload(cx_ctx* ctx, void* dptr, const void* host, size_t bytes);
 
 // scan utilities (cx_scan.cu)
 int cx_exclusive_scan_u64(cx_ctx* ctx, const unsigned long long* d_in, unsigned long long* d_out, int n,

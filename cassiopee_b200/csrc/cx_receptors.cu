@@ -77,10 +77,10 @@ int cx_receptors_create(cx_ctx* c, int ni, int nj, int nk, const double* x, cons
   CX_MALLOC(dx, sizeof(double) * nn, s); CX_MALLOC(dy, sizeof(double) * nn, s); CX_MALLOC(dz, sizeof(double) * nn, s);
   CX_MALLOC(dc, sizeof(double) * np, s);
   CX_MALLOC(f, sizeof(unsigned long long) * np, s); CX_MALLOC(p, sizeof(unsigned long long) * np, s);
-  CX_CUDA(cudaMemcpyAsync(dc, cellN, sizeof(double) * np, cudaMemcpyHostToDevice, s));
-  CX_CUDA(cudaMemcpyAsync(dx, x, sizeof(double) * nn, cudaMemcpyHostToDevice, s));
-  CX_CUDA(cudaMemcpyAsync(dy, y, sizeof(double) * nn, cudaMemcpyHostToDevice, s));
-  CX_CUDA(cudaMemcpyAsync(dz, z, sizeof(double) * nn, cudaMemcpyHostToDevice, s));
+  CX_CHECK(cx_upload(c, dc, cellN, sizeof(double) * np));
+  CX_CHECK(cx_upload(c, dx, x, sizeof(double) * nn));
+  CX_CHECK(cx_upload(c, dy, y, sizeof(double) * nn));
+  CX_CHECK(cx_upload(c, dz, z, sizeof(double) * nn));
   k_rcv_flag<<<cx_grid((long long)np, 256), 256, 0, s>>>((int)np, dc, f);
   c->launches++;
   unsigned long long tot = 0;

@@ -811,11 +811,11 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
   const size_t nscan = sorted ? (size_t)nptsD : N;
   CX_MALLOC(d_cnt, sizeof(unsigned long long) * nscan, s);
   CX_MALLOC(d_scan, sizeof(unsigned long long) * nscan, s);
-  CX_CUDA(cudaMemcpyAsync(r_dn, donor, sizeof(int) * N, cudaMemcpyHostToDevice, s));
-  CX_CUDA(cudaMemcpyAsync(r_rc, rcv, sizeof(int) * N, cudaMemcpyHostToDevice, s));
-  CX_CUDA(cudaMemcpyAsync(r_ty, type, sizeof(int) * N, cudaMemcpyHostToDevice, s));
-  CX_CUDA(cudaMemcpyAsync(r_off, off.data(), sizeof(unsigned long long) * N, cudaMemcpyHostToDevice, s));
-  CX_CUDA(cudaMemcpyAsync(r_cf, coefs, sizeof(double) * (size_t)run, cudaMemcpyHostToDevice, s));
+  CX_CHECK(cx_upload(ctx, r_dn, donor, sizeof(int) * N));
+  CX_CHECK(cx_upload(ctx, r_rc, rcv, sizeof(int) * N));
+  CX_CHECK(cx_upload(ctx, r_ty, type, sizeof(int) * N));
+  CX_CHECK(cx_upload(ctx, r_off, off.data(), sizeof(unsigned long long) * N));
+  CX_CHECK(cx_upload(ctx, r_cf, coefs, sizeof(double) * (size_t)run));
   CX_MALLOC(P->d_donor, sizeof(int) * N, s);
   CX_MALLOC(P->d_rcv, sizeof(int) * N, s);
   CX_MALLOC(P->d_pos, sizeof(int) * N, s);
