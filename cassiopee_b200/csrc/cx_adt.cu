@@ -81,13 +81,18 @@ __global__ void k_resolve(int L, int nact, const int* __restrict__ act, BuildVie
                           int* __restrict__ counter)
 {
   int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= nact) return;
-  int c = act[a];
-  if (!adt_resolve(B, L, c))
-  {
-    int pos = atomicAdd(&counter[0], 1);
-    next[pos] = c;
-  }
+  int c = 0;
+  bool keep = false;
+  if (a < nact) { c = act[a]; keep = !adt_resolve(B, L, c); }
+  // warp-aggregated compaction: one atomicAdd per warp and the lanes keep their relative order, so the active
+  // list stays (piecewise) ascending and the next level's accesses to keys/lo/hi[c] stay coalesced
+  const unsigned m = __ballot_sync(0xffffffffu, keep);
+  if (m == 0) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == __ffs(m) - 1) base = atomicAdd(&counter[0], __popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (keep) next[base + __popc(m & ((1u << lane) - 1u))] = c;
 }
 
 }  // namespace
