@@ -446,8 +446,8 @@ int cx_zone_destroy(cx_zone* zn)
 int cx_set_interp_data_dev(cx_ctx* c, int nrcv, const double* d_xr, const double* d_yr, const double* d_zr, int nz,
                            cx_zone* const* zones, int order, int nature, int penalty, int extrap, cx_result** out)
 {
-  if (order != 2 && order != 3 && order != 5)
-  { cx_set_error("setInterpData: order %d not supported on the device (2, 3 or 5)", order); return -4; }
+  if (order != 2 && order != 3 && order != 4 && order != 5)
+  { cx_set_error("setInterpData: order %d not supported on the device (2, 3, 4 or 5)", order); return -4; }
   if (nz <= 0) { cx_set_error("setInterpData: no valid donor zone found."); return -1; }
   CX_CUDA(cudaSetDevice(c->device));
   std::vector<ZoneView> hv(nz);
@@ -797,7 +797,7 @@ int cx_plan_info(cx_plan* P, int* n, int* ngroups, long long* alg_fixed, long lo
       CX_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
       for (auto& G : P->groups)
       {
-        int o = G.type == 1 ? 1 : G.type == 2 ? 2 : G.type == 3 ? 3 : 5;
+        int o = G.type == 1 ? 1 : G.type == 2 ? 2 : G.type == 3 ? 3 : G.type == 44 ? 4 : 5;
         k_mark<<<cx_grid(G.n, 256), 256, 0, c->stream>>>(G.n, o, P->imd, P->imd * P->jmd, P->d_donor + G.first, mark);
         c->launches++;
       }

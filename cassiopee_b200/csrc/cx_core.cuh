@@ -536,6 +536,40 @@ CX_D int cart_search_o3(const ZoneView& Z, double x, double y, double z, int& ic
   return 1;
 }
 
+// one direction of InterpCart::searchInterpolationCellCartO4 (InterpCart.cpp:347-412): 4-node stencil shifted one
+// node to the left of the cell and pulled back inside at the max boundary, cubic 1-D Lagrange weights
+CX_D void cart_o4_dir(double x, double xmin, double h, int n, int& ic, double* l)
+{
+  if (ic > 1) ic -= 1;
+  if (ic + 3 > n) ic -= ic + 3 - n;
+  double x_i = xmin + (ic - 1) * h, x_ip = x_i + h, x_ipp = x_i + 2 * h, x_ippp = x_i + 3 * h;
+  double norm = -6. * h * h * h;
+  l[0] = (x - x_ip) * (x - x_ipp) * (x - x_ippp) / norm;
+  norm = 2. * h * h * h;
+  l[1] = (x - x_i) * (x - x_ipp) * (x - x_ippp) / norm;
+  norm = -2. * h * h * h;
+  l[2] = (x - x_i) * (x - x_ip) * (x - x_ippp) / norm;
+  norm = 6. * h * h * h;
+  l[3] = (x - x_i) * (x - x_ip) * (x - x_ipp) / norm;
+}
+
+// InterpCart::searchInterpolationCellCartO4: cf[12] by direction, (ic,jc,kc) = 1-based start of the 4x4x4 stencil
+CX_D int cart_search_o4(const ZoneView& Z, double x, double y, double z, int& ic, int& jc, int& kc, double* cf)
+{
+  if (cart_outside(Z, x, y, z)) return 0;
+  const double xmin = Z.bbox[0], ymin = Z.bbox[1], zmin = Z.bbox[2];
+  ic = trunc_int((x - xmin) * Z.hinv[0]) + 1;
+  jc = trunc_int((y - ymin) * Z.hinv[1]) + 1;
+  kc = trunc_int((z - zmin) * Z.hinv[2]) + 1;
+  ic = imax(ic, 1); ic = imin(ic, Z.ni - 1);
+  jc = imax(jc, 1); jc = imin(jc, Z.nj - 1);
+  kc = imax(kc, 1); kc = imin(kc, Z.nk - 1);
+  cart_o4_dir(x, xmin, Z.h[0], Z.ni, ic, cf);
+  cart_o4_dir(y, ymin, Z.h[1], Z.nj, jc, cf + 4);
+  cart_o4_dir(z, zmin, Z.h[2], Z.nk, kc, cf + 8);
+  return 1;
+}
+
 // InterpCart::getListOfCandidateCells (InterpCart.cpp:423-474): the box of cells within 0.1*alphaTol*h of the
 // point, enumerated k-outer / i-inner.  Returns the number of candidates (0: outside) and the 1-based bounds.
 CX_D int cart_candidate_box(const ZoneView& Z, double x, double y, double z, double alphaTol, int* lo, int* hi)

@@ -1,4 +1,4 @@
-// cx_lagrange.cu — order-3 / order-5 Lagrange interpolation data on the device.
+// cx_lagrange.cu — order-3 / order-4 / order-5 Lagrange interpolation data on the device.
 //
 // Reference path (per receptor, per donor zone):
 //   K_INTERP::getInterpolationData, O3ABC / O5ABC branches   KCore/KCore/Interp/Interp2.cpp:344-394, :452-503
@@ -79,6 +79,15 @@ k_lag_search(LagState S, const double* __restrict__ xr, const double* __restrict
           for (int k = 0; k < 9; k++) S.tcf[(size_t)k * S.n + r] = c9[k];
         }
       }
+      else if (order == 4)
+      {
+        double c12[12];
+        if (cart_search_o4(Z, xr[r], yr[r], zr[r], ic, jc, kc, c12) == 1)
+        {
+          found = 2;
+          for (int k = 0; k < 12; k++) S.tcf[(size_t)k * S.n + r] = c12[k];
+        }
+      }
     }
     else
     {
@@ -104,6 +113,16 @@ __device__ __forceinline__ void stencil_start(int order, const ZoneView& Z, int 
     if (ic < 1) ic = 1;
     if (jc < 1) jc = 1;
     if (kc < 1) kc = 1;
+  }
+  else if (order == 4)
+  {
+    // Interp2.cpp:411-416: shift the donor by one, re-centre next to the max boundary
+    if (ic > 1) ic -= 1;
+    if (ic + 3 > Z.ni) ic -= ic + 3 - Z.ni;
+    if (jc > 1) jc -= 1;
+    if (jc + 3 > Z.nj) jc -= jc + 3 - Z.nj;
+    if (kc > 1) kc -= 1;
+    if (kc + 3 > Z.nk) kc -= kc + 3 - Z.nk;
   }
   else
   {
@@ -238,7 +257,7 @@ __device__ void lag_solve_group(const ZoneView& Z, int ics, int jcs, int kcs, do
       }
       zp1 = zp1 * c;
     }
-    const double b0 = (N1 == 3) ? -1. : -2.;
+    const double b0 = (N1 == 5) ? -2. : -1.;     // base(1): -1 for 3 and 4 points, -2 for 5 (CompInterpolatedPtInRefElementF.for:144-163)
     int i = p % N1, j = (p / N1) % N1, k = p / (N1 * N1);
     row[N] = b0 + i; row[N + 1] = b0 + j; row[N + 2] = b0 + k;
   }
@@ -404,6 +423,28 @@ k_lag_solve3(LagState S, int nlist, const int* __restrict__ list, const double* 
   }
 }
 
+// order 4: one 256-thread CTA per receptor, matrix (64 x 67 doubles) in shared memory
+__global__ void __launch_bounds__(256)
+k_lag_solve4(LagState S, int nlist, const int* __restrict__ list, const double* __restrict__ xr,
+             const double* __restrict__ yr, const double* __restrict__ zr, const ZoneView* __restrict__ zones, int noz)
+{
+  extern __shared__ double smem[];
+  for (int a = blockIdx.x; a < nlist; a += gridDim.x)
+  {
+    int r = list[a];
+    const ZoneView& Z = zones[noz];
+    int ics, jcs, kcs;
+    stencil_start(4, Z, S.ijk[r], S.ijk[(size_t)S.n + r], S.ijk[2 * (size_t)S.n + r], ics, jcs, kcs);
+    double ksi, eta, zeta; int err;
+    lag_solve_group<4, 256, false>(Z, ics, jcs, kcs, xr[r], yr[r], zr[r], smem, threadIdx.x, ksi, eta, zeta, err);
+    if (threadIdx.x == 0)
+    {
+      S.ksi[r] = ksi; S.ksi[(size_t)S.n + r] = eta; S.ksi[2 * (size_t)S.n + r] = zeta; S.err[r] = err;
+    }
+    __syncthreads();
+  }
+}
+
 // order 5: one 512-thread CTA per receptor, matrix (125 x 129 doubles) in shared memory
 __global__ void __launch_bounds__(512)
 k_lag_solve5(LagState S, int nlist, const int* __restrict__ list, const double* __restrict__ xr,
@@ -462,6 +503,24 @@ __device__ __forceinline__ void lagrange_weights(int order, double ksi, double e
     cf[3] = -0.5 * eta * etam; cf[4] = etap * etam; cf[5] = 0.5 * eta * etap;
     cf[6] = -0.5 * zeta * zetam; cf[7] = zetap * zetam; cf[8] = 0.5 * zeta * zetap;
   }
+  else if (order == 4)
+  {
+    // Interp2.cpp O4ABC branch (literal inv6, ONE_HALF)
+    const double inv6 = 0.166666666667;
+    double ksim2 = 2. - ksi, etam2 = 2. - eta, zetam2 = 2. - zeta;
+    cf[0] = -inv6 * ksim2 * ksim * ksi;
+    cf[1] = 0.5 * ksim2 * ksim * ksip;
+    cf[2] = 0.5 * ksim2 * ksi * ksip;
+    cf[3] = -inv6 * ksim * ksi * ksip;
+    cf[4] = -inv6 * etam2 * etam * eta;
+    cf[5] = 0.5 * etam2 * etam * etap;
+    cf[6] = 0.5 * etam2 * eta * etap;
+    cf[7] = -inv6 * etam * eta * etap;
+    cf[8] = -inv6 * zetam2 * zetam * zeta;
+    cf[9] = 0.5 * zetam2 * zetam * zetap;
+    cf[10] = 0.5 * zetam2 * zeta * zetap;
+    cf[11] = -inv6 * zetam * zeta * zetap;
+  }
   else
   {
     const double inv24 = 0.041666666667, inv6 = 0.166666666667, inv4 = 0.25;
@@ -491,21 +550,22 @@ k_lag_finish(LagState S, const ZoneView* __restrict__ zones, int noz, int order,
   if (r >= S.n) return;
   if (S.found[r] == 2)
   {
-    // Cartesian donor, order 3 (Interp2.cpp:386-392): stencil start and weights come from the search
+    // Cartesian donor, order 3 or 4 (Interp2.cpp:386-392, :441-447): stencil start and weights come from the search
     const ZoneView& Z = zones[noz];
     const size_t n = S.n;
+    const int O = order, nc = 3 * order;
     const int ic = S.ijk[r] - 1, jc = S.ijk[n + r] - 1, kc = S.ijk[2 * n + r] - 1;
     const int tind = ic + jc * Z.ni + kc * Z.ni * Z.nj;
-    const int isBorder = (ic == 0 || ic == Z.ni - 3 || jc == 0 || jc == Z.nj - 3 || kc == 0 || kc == Z.nk - 3);
-    double cf[9];
-    for (int k = 0; k < 9; k++) cf[k] = S.tcf[(size_t)k * n + r];
-    if (!celln_valid_lag(Z, 3, ic, jc, kc, cf, nature)) return;
+    const int isBorder = (ic == 0 || ic == Z.ni - O || jc == 0 || jc == Z.nj - O || kc == 0 || kc == Z.nk - O);
+    double cf[12];
+    for (int k = 0; k < nc; k++) cf[k] = S.tcf[(size_t)k * n + r];
+    if (!celln_valid_lag(Z, O, ic, jc, kc, cf, nature)) return;
     double vol = cell_volume(Z, tind);
     if (penalty == 1 && isBorder == 1) vol += 1.e3;
     if (vol < S.best[r] + CX_EPS_GEOM)
     {
-      S.best[r] = vol; S.type[r] = 3; S.dind[r] = tind; S.noblk[r] = noz + 1;
-      for (int k = 0; k < S.ncfmax; k++) S.cf[(size_t)k * n + r] = k < 9 ? cf[k] : 0.;
+      S.best[r] = vol; S.type[r] = (O == 4) ? 44 : 3; S.dind[r] = tind; S.noblk[r] = noz + 1;
+      for (int k = 0; k < S.ncfmax; k++) S.cf[(size_t)k * n + r] = k < nc ? cf[k] : 0.;
     }
     return;
   }
@@ -518,16 +578,16 @@ k_lag_finish(LagState S, const ZoneView* __restrict__ zones, int noz, int order,
   stencil_start(order, Z, ic1, jc1, kc1, ics, jcs, kcs);
   int ic = ics - 1, jc = jcs - 1, kc = kcs - 1;
   int isBorder = (ic == 0 || ic == Z.ni - O || jc == 0 || jc == Z.nj - O || kc == 0 || kc == Z.nk - O);
-  int type = order;
+  int type = (order == 4) ? 44 : order;
   int tind = ic + jc * Z.ni + kc * Z.ni * Z.nj;
   double cf[15];
   for (int k = 0; k < 15; k++) cf[k] = S.tcf[(size_t)k * n + r];
   const int corr = S.err[r];
-  if (order == 3)
+  if (order == 3 || order == 4)
   {
-    // O3: weights first (when well approximated), then the cellN test (Interp2.cpp:369-372)
-    if (corr == 0) lagrange_weights(3, S.ksi[r], S.ksi[n + r], S.ksi[2 * n + r], cf);
-    if (!celln_valid_lag(Z, 3, ic, jc, kc, cf, nature))
+    // O3 / O4: weights first (when well approximated), then the cellN test (Interp2.cpp:369-372, :418-425)
+    if (corr == 0) lagrange_weights(order, S.ksi[r], S.ksi[n + r], S.ksi[2 * n + r], cf);
+    if (!celln_valid_lag(Z, order, ic, jc, kc, cf, nature))
     {
       for (int k = 0; k < ncf; k++) S.tcf[(size_t)k * n + r] = cf[k];
       return;
@@ -577,7 +637,7 @@ __global__ void k_lag_collapse(LagState S, const ZoneView* __restrict__ zones)
       if (fabs(c) > 1.e-10) { cnt++; indNonZero = dind + ii + jj * ni + kk * ninj; coefNonZero = c; }
     }
   }
-  else if (type == 3 || type == 5)
+  else if (type == 3 || type == 5)      // no case 44 in commonCheckCoefs.h: order-4 stencils are never collapsed
   {
     const int O = type;
     for (int kk = 0; kk < O; kk++) for (int jj = 0; jj < O; jj++) for (int ii = 0; ii < O; ii++)
@@ -621,6 +681,7 @@ int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_xr, cons
   k_lag_init<<<cx_grid(n, 256), 256, 0, s>>>(S);
   ctx->launches++;
   const size_t smem3 = sizeof(double) * LagCfg<3>::SMEM_D * 4;
+  const size_t smem4 = sizeof(double) * LagCfg<4>::SMEM_D;
   const size_t smem5 = sizeof(double) * LagCfg<5>::SMEM_D;
   if (order == 5)
     CX_CUDA(cudaFuncSetAttribute(k_lag_solve5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
@@ -637,6 +698,11 @@ int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_xr, cons
       k_list<<<cx_grid(n, 256), 256, 0, s>>>(n, d_f, d_p, d_list);
       if (order == 3)
         k_lag_solve3<<<cx_grid(nlist, 4), 128, smem3, s>>>(S, nlist, d_list, d_xr, d_yr, d_zr, d_zones, noz);
+      else if (order == 4)
+      {
+        int grid = nlist < ctx->sm_count * 24 ? nlist : ctx->sm_count * 24;
+        k_lag_solve4<<<grid, 256, smem4, s>>>(S, nlist, d_list, d_xr, d_yr, d_zr, d_zones, noz);
+      }
       else
       {
         int grid = nlist < ctx->sm_count * 4 ? nlist : ctx->sm_count * 4;

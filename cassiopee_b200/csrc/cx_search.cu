@@ -287,7 +287,7 @@ int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, co
                   cx_result* R, cx_result_dev* D)
 {
   cudaStream_t s = ctx->stream;
-  const int ncfmax = (order == 3) ? 9 : (order == 5) ? 15 : 8;
+  const int ncfmax = (order == 3) ? 9 : (order == 4) ? 12 : (order == 5) ? 15 : 8;   // setInterpData.cpp:624-652
   R->nrcv = n; R->nz = nz; R->ncfmax = ncfmax;
   R->cnt.assign(nz, 0); R->ncoef.assign(nz, 0); R->nextrap.assign(nz, 0); R->norphan = 0;
   for (int i = 0; i < 4; i++) R->stats[i] = 0;

@@ -22,6 +22,7 @@ def lib():
         L.emu_zone_create_cart.restype = ctypes.c_void_p
         L.emu_zone_create_cart.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 4
         L.emu_cart_o3.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 6
+        L.emu_cart_o4.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 6
         L.emu_zone_free.argtypes = [ctypes.c_void_p]
         L.emu_zone_depth.argtypes = [ctypes.c_void_p]
         L.emu_candidates.argtypes = [ctypes.c_void_p] + [ctypes.c_double] * 4 + [ctypes.c_void_p, ctypes.c_int]
@@ -73,12 +74,12 @@ class EmuZone:
         except Exception: pass
 
 
-def cart_o3(zone, xr, yr, zr):
+def cart_o3(zone, xr, yr, zr, order=3):
     xr = np.ascontiguousarray(xr, np.float64).reshape(-1); yr = np.ascontiguousarray(yr, np.float64).reshape(-1)
     zr = np.ascontiguousarray(zr, np.float64).reshape(-1)
     n = xr.size
-    found = np.zeros(n, np.int32); dind = np.zeros(n, np.int32); cf = np.zeros((n, 9))
-    lib().emu_cart_o3(zone.h, n, xr.ctypes.data, yr.ctypes.data, zr.ctypes.data, found.ctypes.data, dind.ctypes.data,
+    found = np.zeros(n, np.int32); dind = np.zeros(n, np.int32); cf = np.zeros((n, 3 * order))
+    (lib().emu_cart_o4 if order == 4 else lib().emu_cart_o3)(zone.h, n, xr.ctypes.data, yr.ctypes.data, zr.ctypes.data, found.ctypes.data, dind.ctypes.data,
                       cf.ctypes.data)
     return found, dind, cf
 

@@ -97,6 +97,17 @@ void emu_cart_o3(void* h, int n, const double* xr, const double* yr, const doubl
   }
 }
 
+void emu_cart_o4(void* h, int n, const double* xr, const double* yr, const double* zr, int* found, int* dind, double* cf)
+{
+  ZoneView V = ((EmuZone*)h)->view();
+  for (int r = 0; r < n; r++)
+  {
+    int ic = 0, jc = 0, kc = 0;
+    found[r] = cart_search_o4(V, xr[r], yr[r], zr[r], ic, jc, kc, cf + (size_t)r * 12);
+    dind[r] = (ic - 1) + (jc - 1) * V.ni + (kc - 1) * V.ni * V.nj;
+  }
+}
+
 void emu_zone_free(void* h) { delete (EmuZone*)h; }
 int emu_zone_depth(void* h) { return ((EmuZone*)h)->depth; }
 

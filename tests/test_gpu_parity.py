@@ -165,7 +165,7 @@ def test_pytree_api_inverse_storage(ctx):
     g.smoke()
 
 
-@pytest.mark.parametrize("order", [3, 5])
+@pytest.mark.parametrize("order", [3, 4, 5])
 def test_lagrange_orders_cart_and_cylinder(ctx, order):
     """Orders 3/5 (directional 9/15 coefficients).  The oracle for these orders
     is the reference C++ plus the C transliteration of four Fortran routines
@@ -175,7 +175,7 @@ def test_lagrange_orders_cart_and_cylinder(ctx, order):
     sel = rng.choice(Oc[3].size, 1500 if order == 5 else 8000, replace=False)
     sel.sort()
     got, ref, gz, oz = _compare(ctx, [Bg], (Oc[3][sel], Oc[4][sel], Oc[5][sel]), order=order)
-    assert (got[2][0] == order).any()
+    assert (got[2][0] == (44 if order == 4 else order)).any()
     r = np.sqrt(Bg[3] ** 2 + Bg[4] ** 2)
     m = np.nonzero((r > 0.5) & (r < 2.5))[0]
     sel = rng.choice(m, 1000 if order == 5 else 6000, replace=False)
@@ -183,7 +183,7 @@ def test_lagrange_orders_cart_and_cylinder(ctx, order):
     _compare(ctx, [Oc], (Bg[3][sel], Bg[4][sel], Bg[5][sel]), order=order)
 
 
-@pytest.mark.parametrize("order", [3, 5])
+@pytest.mark.parametrize("order", [3, 4, 5])
 @pytest.mark.parametrize("nature", [0, 1])
 def test_lagrange_multizone_holes(ctx, order, nature):
     Bg, Oc = cases.c2()
@@ -196,7 +196,7 @@ def test_lagrange_multizone_holes(ctx, order, nature):
     _compare(ctx, [Oc, Bg], P, order=order, nature=nature, extrap=0, cellNs=[co, cb])
 
 
-@pytest.mark.parametrize("order", [3, 5])
+@pytest.mark.parametrize("order", [3, 4, 5])
 def test_lagrange_coincident_and_transfer(ctx, order):
     """C1a: receptors coincide with donor nodes -> type 1 collapse of the
     directional weights; then order-3/5 transfers vs the reference loops and
@@ -237,18 +237,20 @@ def test_transfer_synthetic_plans_staged_and_gather(ctx, dims, density):
     n = max(8, int(density * nD))
     nR = 2 * n + 5
     for contiguous in (False, True):
-        typ = rng.choice(np.array([1, 2, 2, 2, 2, 3, 3, 5], np.int32), n).astype(np.int32)
+        typ = rng.choice(np.array([1, 2, 2, 2, 2, 3, 3, 5, 44], np.int32), n).astype(np.int32)
         if ni < 5 or nj < 5 or nk < 5:
             typ[typ == 5] = 3
+        if ni < 4 or nj < 4 or nk < 4:
+            typ[typ == 44] = 3
         if ni < 3 or nj < 3 or nk < 3:
             typ[typ == 3] = 2
-        o = np.where(typ == 1, 1, typ)
+        o = np.where(typ == 1, 1, np.where(typ == 44, 4, typ))
         i = (rng.random(n) * (ni - o + 1)).astype(np.int64); j = (rng.random(n) * (nj - o + 1)).astype(np.int64)
         k = (rng.random(n) * (nk - o + 1)).astype(np.int64)
         i[:3] = ni - o[:3]; j[:3] = nj - o[:3]; k[:3] = nk - o[:3]          # stencil ends on the last node
         dnr = (i + ni * j + ni * nj * k).astype(np.int32)
         rcv = (np.arange(n) + 3 if contiguous else np.sort(rng.choice(nR, n, replace=False))).astype(np.int32)
-        ncf = np.where(typ == 1, 1, np.where(typ == 2, 8, np.where(typ == 3, 9, 15)))
+        ncf = np.where(typ == 1, 1, np.where(typ == 2, 8, np.where(typ == 3, 9, np.where(typ == 44, 12, 15))))
         cf = rng.standard_normal(int(ncf.sum()))
         for nvars in (1, 2, 5):
             fD = [rng.standard_normal(nD) for _ in range(nvars)]
@@ -276,7 +278,7 @@ def test_transfer_synthetic_plans_staged_and_gather(ctx, dims, density):
             assert np.array_equal(dense.download().reshape(nvars, n), O.transferD(fD, ni, nj, dnr, typ, cf))
 
 
-@pytest.mark.parametrize("order", [2, 3])
+@pytest.mark.parametrize("order", [2, 3, 4])
 def test_interpcart_donors(ctx, order):
     """interpDataType=0 (regular Cartesian donors located in closed form, K_INTERP::InterpCart): single donor,
     Cartesian + ADT donors mixed in both list orders, holes, nature/penalty, extrapolation and orphans."""

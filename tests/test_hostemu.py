@@ -108,16 +108,17 @@ def test_cartesian_donors_interpcart_order2_and_extrapolation():
     assert next_ > 0
 
 
-def test_cartesian_donors_interpcart_order3_weights():
+@pytest.mark.parametrize("order", [3, 4])
+def test_cartesian_donors_interpcart_order3_order4_weights(order):
     A, B = cases.c1("c", n=17, m=11)
     rng = np.random.default_rng(2)
     P = np.concatenate([np.array(B[3:]), rng.uniform(-0.05, 1.05, (3, 3000))], axis=1)
     oz = O.RefZone(*A, interpDataType=0); ez = E.EmuZone(*A, interpDataType=0)
-    ro = O.set_interp_data_raw(P[0], P[1], P[2], [oz], 3, 1, 1, 0)
-    found, dind, cf = E.cart_o3(ez, P[0], P[1], P[2])
+    ro = O.set_interp_data_raw(P[0], P[1], P[2], [oz], order, 1, 1, 0)
+    found, dind, cf = E.cart_o3(ez, P[0], P[1], P[2], order)
     hit = ro["noblk"] == 1
     assert np.array_equal(hit, found == 1) and hit.sum() > 1000 and (~hit).sum() > 100
-    t3 = hit & (ro["type"] == 3)
-    assert t3.sum() > 1000
-    assert np.array_equal(ro["dind"][t3], dind[t3])
-    assert np.array_equal(ro["cf"][t3][:, :9], cf[t3])
+    tt = hit & (ro["type"] == (44 if order == 4 else 3))
+    assert tt.sum() > 1000
+    assert np.array_equal(ro["dind"][tt], dind[tt])
+    assert np.array_equal(ro["cf"][tt][:, :3 * order], cf[tt])
