@@ -38,12 +38,28 @@ def golden_cases():
                                      dict(order=order, nature=0, penalty=1, extrap=1))
         g["c2_OfromBg_o%d" % order] = ([Bg], (Oc[3][::7][:n], Oc[4][::7][:n], Oc[5][::7][:n]),
                                        dict(order=order, nature=1, penalty=1, extrap=1))
+    # order 4 (type 44) and regular Cartesian donors (interpDataType=0, InterpCart); `types` = per-zone interpDataType
+    n = 3000
+    g["c2_multi_o4"] = ([Bg, Oc], (P[0][:n], P[1][:n], P[2][:n]), dict(order=4, nature=0, penalty=1, extrap=1))
+    g["c2_OfromBg_o4"] = ([Bg], (Oc[3][::7][:n], Oc[4][::7][:n], Oc[5][::7][:n]),
+                          dict(order=4, nature=1, penalty=1, extrap=1))
+    for order in (2, 3, 4):
+        g["c2_multi_cart_o%d" % order] = ([Bg, Oc], (P[0][:n], P[1][:n], P[2][:n]),
+                                          dict(order=order, nature=1, penalty=1, extrap=1, types=[0, 1]))
     return g
+
+
+def zones_of(dz, kw):
+    kw = dict(kw)
+    types = kw.pop("types", None) or [1] * len(dz)
+    return [O.RefZone(*z, interpDataType=t) for z, t in zip(dz, types)], kw
 
 
 def main():
     for name, (dz, pts, kw) in golden_cases().items():
-        zones = [O.RefZone(*z) for z in dz]
+        if os.path.exists(os.path.join(HERE, name + ".npz")) and "--all" not in sys.argv:
+            continue                       # committed fixtures are not rewritten
+        zones, kw = zones_of(dz, kw)
         out = O.set_interp_data(pts[0], pts[1], pts[2], zones, **kw)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **pack(out))
         print(name, [a.size for a in out[0]], out[5].size)

@@ -361,3 +361,22 @@ def test_receptor_extraction_on_device(ctx, loc):
     # no receptor at all
     empty = _lib.DeviceBackend(ctx).select_receptors(ni, nj, nk, x, y, z, np.ones(npts), loc)
     assert empty.n == 0 and empty.indcell.size == 0
+
+
+def test_committed_golden_fixtures(ctx):
+    """The CUDA path against the committed fixtures of tests/golden (outputs of the reference's compiled code,
+    written by tests/golden/make_golden.py): no oracle library involved."""
+    import os
+    from cassiopee_b200 import _lib
+    from tests.golden.make_golden import golden_cases
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for name, (dz, pts, kw) in golden_cases().items():
+        kw = dict(kw)
+        types = kw.pop("types", None) or [1] * len(dz)
+        zones = [_lib.Zone(ctx, *z, interpDataType=t) for z, t in zip(dz, types)]
+        got = _lib.set_interp_data(ctx, pts[0], pts[1], pts[2], zones, **kw).fetch()
+        ref = np.load(os.path.join(gold, name + ".npz"))
+        for z in range(len(dz)):
+            for q, key in enumerate(("rcv", "dnr", "typ", "cf", "ext")):
+                assert np.array_equal(got[q][z], ref["%s%d" % (key, z)]), (name, key, z)
+        assert np.array_equal(got[5], ref["orphan"]), name
