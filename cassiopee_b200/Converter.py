@@ -275,3 +275,41 @@ def freeHook(hook):
     elif hasattr(hook, 'free'):
         hook.free()
     return None
+
+
+# -- file I/O: the reference's 'bin_pickle' format (Converter/Converter/PyTree.py convertPyTree2File /
+#    convertFile2PyTree with format='bin_pickle': the tree pickled as is).  Enough to carry a donor tree tc with
+#    its ID_* subregions from a preparation run to a solver run; CGNS/HDF5 files are out
+#    of scope (no HDF5 in this image).
+def _formatOf(fileName, format):
+    if format is not None:
+        return format
+    ext = fileName.rsplit('.', 1)[-1].lower() if '.' in fileName else ''
+    return {'pickle': 'bin_pickle', 'pkl': 'bin_pickle', 'ref': 'bin_pickle'}.get(ext, ext)
+
+
+def convertPyTree2File(t, fileName, format=None):
+    """Write a pyTree to a file (format 'bin_pickle' only)."""
+    import pickle
+    fmt = _formatOf(fileName, format)
+    if fmt != 'bin_pickle':
+        raise NotImplementedError("convertPyTree2File: only format='bin_pickle' is available (got %r)." % fmt)
+    with open(fileName, 'wb') as f:
+        pickle.dump(t, f, protocol=pickle.HIGHEST_PROTOCOL)
+    return None
+
+
+def convertFile2PyTree(fileName, format=None):
+    """Read a pyTree from a file (format 'bin_pickle' only)."""
+    import pickle
+    fmt = _formatOf(fileName, format)
+    if fmt != 'bin_pickle':
+        raise NotImplementedError("convertFile2PyTree: only format='bin_pickle' is available (got %r)." % fmt)
+    with open(fileName, 'rb') as f:
+        try:
+            t = pickle.load(f, encoding='latin1')
+        except TypeError:
+            t = pickle.load(f)
+    if not (isinstance(t, list) and len(t) == 4):
+        raise TypeError("convertFile2PyTree: %s does not hold a pyTree." % fileName)
+    return t

@@ -266,3 +266,25 @@ def test_set_hole_interpolated_points():
     assert got[3, 3, 3] == 0. and got[2, 3, 3] == 2. and got[1, 3, 3] == 1. and got[2, 2, 2] == 2.
     with pytest.raises(NotImplementedError):
         XP._setHoleInterpolatedPoints(z, depth=2, dir=2, loc='centers')
+
+
+def test_donor_tree_round_trip_on_disk(tmp_path):
+    """tc with its ID_* subregions written and read back ('bin_pickle', a format of the reference's Converter):
+    the interpData survives bit for bit and drives the same transfers."""
+    t = _case(); tc = C.node2Center(t)
+    be = OracleBackend()
+    X._setInterpDataChimera(t, tc, order=2, nature=1, loc='centers', storage='inverse', verbose=0, backend=be)
+    f = str(tmp_path / "tc.pickle")
+    C.convertPyTree2File(tc, f)
+    tc2 = C.convertFile2PyTree(f)
+    for za, zb in zip(Internal.getZones(tc), Internal.getZones(tc2)):
+        sa = Internal.getNodesFromType1(za, 'ZoneSubRegion_t'); sb = Internal.getNodesFromType1(zb, 'ZoneSubRegion_t')
+        assert [s[0] for s in sa] == [s[0] for s in sb] and len(sa) > 0 or len(sb) == 0
+        for a, b in zip(sa, sb):
+            assert Internal.getValue(a) == Internal.getValue(b)
+            for ca, cb in zip(a[2], b[2]):
+                assert ca[0] == cb[0] and ca[3] == cb[3]
+                if isinstance(ca[1], np.ndarray):
+                    assert ca[1].dtype == cb[1].dtype and np.array_equal(ca[1], cb[1])
+    with pytest.raises(NotImplementedError):
+        C.convertPyTree2File(tc, str(tmp_path / "tc.cgns"))
