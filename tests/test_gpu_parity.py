@@ -374,9 +374,50 @@ def test_committed_golden_fixtures(ctx):
         kw = dict(kw)
         types = kw.pop("types", None) or [1] * len(dz)
         zones = [_lib.Zone(ctx, *z, interpDataType=t) for z, t in zip(dz, types)]
+        pts = [np.ascontiguousarray(p) for p in pts]
         got = _lib.set_interp_data(ctx, pts[0], pts[1], pts[2], zones, **kw).fetch()
         ref = np.load(os.path.join(gold, name + ".npz"))
         for z in range(len(dz)):
             for q, key in enumerate(("rcv", "dnr", "typ", "cf", "ext")):
                 assert np.array_equal(got[q][z], ref["%s%d" % (key, z)]), (name, key, z)
         assert np.array_equal(got[5], ref["orphan"]), name
+
+
+@pytest.mark.parametrize("order", [2, 3])
+def test_post_extract_mesh(ctx, order):
+    """Post.extractMesh = getInterpolationCell(nature 0, penalty 0) -> getExtrapolationCell -> interpolated values of
+    every donor field, zeros where nothing is found; against the same composition of the reference functions."""
+    import cassiopee_b200.Converter as C
+    import cassiopee_b200.Generator as G
+    import cassiopee_b200.Internal as Internal
+    import cassiopee_b200.Post as P
+    from oracle import oracle as O
+    a = G.cart((0, 0, 0), (0.1, 0.1, 0.1), (11, 11, 11), name='A')
+    b = G.cylinder((0.5, 0.5, 0.), 0.1, 0.45, 360., 0., 1., (33, 7, 9), name='B')
+    names = ['F', 'G']
+    for z in (a, b):
+        C._initVars(z, 'F', lambda x, y, zz: x + 2 * y + 3 * zz)
+        C._initVars(z, 'G', lambda x, y, zz: np.sin(3 * x) * np.cos(2 * y) + zz * zz)
+    e = G.cart((-1.83, 0.21, 0.11), (0.17, 0.05, 0.09), (19, 13, 9), name='E')
+    te = P.extractMesh(C.newPyTree(['D', a, b]), C.newPyTree(['E', e]), order=order)
+    ze = Internal.getZones(te)[0]
+    assert C.getFieldArray(e, 'F') is None                                   # the input mesh is untouched
+    xe, ye, zz = [v.reshape(-1, order='F') for v in C.getCoords(e)]
+    oz = []
+    for z in (a, b):
+        d = Internal.getZoneDim(z)
+        oz.append(O.RefZone(d[1], d[2], d[3], *[v.reshape(-1, order='F') for v in C.getCoords(z)]))
+    ref = O.set_interp_data(xe, ye, zz, oz, order, 0, 0, 1)
+    exp = [np.zeros(xe.size) for _ in names]
+    for noz, z in enumerate((a, b)):
+        d = Internal.getZoneDim(z)
+        O.transfer([C.getFieldArray(z, v).reshape(-1, order='F') for v in names], exp, d[1], d[2],
+                   ref[0][noz], ref[1][noz], ref[2][noz], ref[3][noz])
+    found = np.zeros(xe.size, bool)
+    for noz in range(2):
+        found[ref[0][noz]] = True
+    assert found.sum() > 200 and (~found).sum() > 200
+    for v, r in zip(names, exp):
+        got = C.getFieldArray(ze, v).reshape(-1, order='F')
+        assert np.array_equal(got, r), v
+        assert (got[~found] == 0.).all()
