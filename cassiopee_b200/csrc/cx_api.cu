@@ -286,8 +286,7 @@ static double wall_ms()
 int cx_zone_create(cx_ctx* c, int ni, int nj, int nk, const double* x, const double* y, const double* z,
                    const double* cellN, cx_zone** out)
 {
-  if (ni < 2 || nj < 2) { cx_set_error("setInterpData: structured donor zones must be 3D or nk=1."); return -1; }
-  if (nk < 2) { cx_set_error("2-D donor zones (nk=1, type 22) are not supported by the device path"); return -4; }
+  if (ni < 2 || nj < 2 || nk < 1) { cx_set_error("setInterpData: structured donor zones must be 3D or 2D with z=constant."); return -1; }
   if ((long long)ni * nj * nk > 2000000000ll) { cx_set_error("donor zone too large for int32 indices"); return -1; }
   CX_CUDA(cudaSetDevice(c->device));
   const bool prof = getenv("CX_PROFILE_ZONE") != nullptr;
@@ -296,7 +295,7 @@ int cx_zone_create(cx_ctx* c, int ni, int nj, int nk, const double* x, const dou
   memset(zn, 0, sizeof(*zn));
   zn->ctx = c; zn->ni = ni; zn->nj = nj; zn->nk = nk;
   zn->npts = ni * nj * nk;
-  zn->ncells = (ni - 1) * (nj - 1) * (nk - 1);
+  zn->ncells = (ni - 1) * (nj - 1) * std::max(nk - 1, 1);
   zn->topo = 1;
   size_t nb = sizeof(double) * (size_t)zn->npts;
   // x, y, z, cellN in one block (one allocation instead of four)
@@ -308,6 +307,17 @@ int cx_zone_create(cx_ctx* c, int ni, int nj, int nk, const double* x, const dou
   CX_CHECK(cx_upload(c, zn->d_z, z, nb));
   double t2 = wall_ms();
   cx_zone_bbox_host(ni, nj, nk, x, y, z, zn->bbox);
+  if (nk == 1)
+  {
+    // 2-D zone (InterpAdt.cpp:293-301): one z = constant plane, given a fictitious thickness of 1
+    if (fabs(zn->bbox[5] - zn->bbox[2]) < 1.e-8) zn->bbox[5] = zn->bbox[2] + 1.;
+    else
+    {
+      cx_set_error("setInterpData: structured donor zones must be 3D or 2D with z=constant.");
+      cudaFree(zn->d_x); delete zn;
+      return -1;
+    }
+  }
   double t3 = wall_ms();
   *out = zn;
   int rc = cx_zone_set_celln(zn, cellN);
@@ -741,12 +751,12 @@ __global__ void k_scatter(int n, int nvars, const double* __restrict__ in, long 
   int r = rcv[e];
   for (int v = 0; v < nvars; v++) R.r[v][r] = in[(size_t)v * ld + e];
 }
-__global__ void k_mark(int m, int sten_o, int imd, int imdjmd, const int* __restrict__ donor, unsigned char* mark)
+__global__ void k_mark(int m, int sten_o, int sten_k, int imd, int imdjmd, const int* __restrict__ donor, unsigned char* mark)
 {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= m) return;
   int d0 = donor[e];
-  for (int kk = 0; kk < sten_o; kk++) for (int jj = 0; jj < sten_o; jj++) for (int ii = 0; ii < sten_o; ii++)
+  for (int kk = 0; kk < sten_k; kk++) for (int jj = 0; jj < sten_o; jj++) for (int ii = 0; ii < sten_o; ii++)
     mark[d0 + ii + jj * imd + kk * imdjmd] = 1;
 }
 __global__ void k_count(long long n, const unsigned char* mark, unsigned long long* cnt)
@@ -797,8 +807,8 @@ int cx_plan_info(cx_plan* P, int* n, int* ngroups, long long* alg_fixed, long lo
       CX_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
       for (auto& G : P->groups)
       {
-        int o = G.type == 1 ? 1 : G.type == 2 ? 2 : G.type == 3 ? 3 : G.type == 44 ? 4 : 5;
-        k_mark<<<cx_grid(G.n, 256), 256, 0, c->stream>>>(G.n, o, P->imd, P->imd * P->jmd, P->d_donor + G.first, mark);
+        int o = G.type == 1 ? 1 : (G.type == 2 || G.type == 22) ? 2 : G.type == 3 ? 3 : G.type == 44 ? 4 : 5;
+        k_mark<<<cx_grid(G.n, 256), 256, 0, c->stream>>>(G.n, o, G.type == 22 ? 1 : o, P->imd, P->imd * P->jmd, P->d_donor + G.first, mark);
         c->launches++;
       }
       k_count<<<cx_grid(P->nptsD, 256), 256, 0, c->stream>>>(P->nptsD, mark, cnt);

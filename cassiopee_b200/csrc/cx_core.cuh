@@ -192,7 +192,8 @@ CX_D bool query_contains(const AdtQuery& q, const AdtNode* __restrict__ nodes, i
 // ---------------------------------------------------------------------------
 struct Hexa { double x[15], y[15], z[15]; };
 
-// InterpData::coordHexa (InterpData.cpp:56-134); ic,jc,kc 1-based. 3-D zones.
+// InterpData::coordHexa (InterpData.cpp:56-134); ic,jc,kc 1-based.  nk == 1 (2-D zone in a z = constant plane):
+// the top face is the bottom face lifted by 1 in z (:96-102).
 CX_D void coord_hexa(const ZoneView& Z, int ind, int& ic, int& jc, int& kc, Hexa& H)
 {
   const int ni = Z.ni, nij = Z.ni * Z.nj;
@@ -209,9 +210,22 @@ CX_D void coord_hexa(const ZoneView& Z, int ind, int& ic, int& jc, int& kc, Hexa
   int i5 = ic + jcmni + kcnij;
   int i6 = ic - 1 + jcni + kcnij;
   int i7 = ic + jcni + kcnij;
-  const int idx[8] = {i0, i1, i2, i3, i4, i5, i6, i7};
+  if (Z.nk > 1)
+  {
+    const int idx[8] = {i0, i1, i2, i3, i4, i5, i6, i7};
 #pragma unroll
-  for (int v = 0; v < 8; v++) { H.x[v] = Z.x[idx[v]]; H.y[v] = Z.y[idx[v]]; H.z[v] = Z.z[idx[v]]; }
+    for (int v = 0; v < 8; v++) { H.x[v] = Z.x[idx[v]]; H.y[v] = Z.y[idx[v]]; H.z[v] = Z.z[idx[v]]; }
+  }
+  else
+  {
+    const int idx[4] = {i0, i1, i2, i3};
+#pragma unroll
+    for (int v = 0; v < 4; v++)
+    {
+      H.x[v] = Z.x[idx[v]]; H.y[v] = Z.y[idx[v]]; H.z[v] = Z.z[idx[v]];
+      H.x[v + 4] = H.x[v]; H.y[v + 4] = H.y[v]; H.z[v + 4] = H.z[v] + 1.;
+    }
+  }
 #define CX_FC(o, a, b, c, d)                                  \
   H.x[o] = 0.25 * (H.x[a] + H.x[b] + H.x[c] + H.x[d]);        \
   H.y[o] = 0.25 * (H.y[a] + H.y[b] + H.y[c] + H.y[d]);        \
@@ -382,6 +396,24 @@ CX_D double cell_volume(const ZoneView& Z, int indnode)
 #undef CX_FACE
   const double ONE_24TH = 0.125 * 0.33333333333333333333;
   return fabs(v2 - v1 + v4 - v3 + v6 - v5) * ONE_24TH;
+}
+
+// K_METRIC::compVolOfStructCell2D (Metric/compVolOfStructCell.cpp:29-89) with indnode given: signed area of the quad
+CX_D double cell_area_2d(const ZoneView& Z, int indnode)
+{
+  const int ni = Z.ni;
+  const int ind1 = indnode, ind2 = ind1 + ni, ind3 = ind1 + 1, ind4 = ind2 + 1;
+  const double* X = Z.x; const double* Y = Z.y; const double* W = Z.z;
+  double l1x = X[ind1] - X[ind2], l1y = Y[ind1] - Y[ind2], l1z = W[ind1] - W[ind2];
+  double l2x = X[ind1] - X[ind3], l2y = Y[ind1] - Y[ind3], l2z = W[ind1] - W[ind3];
+  double surf1x = (l1y * l2z - l1z * l2y), surf1y = (l1z * l2x - l1x * l2z), surf1z = (l1x * l2y - l1y * l2x);
+  double surface1 = sqrt(surf1x * surf1x + surf1y * surf1y + surf1z * surf1z);
+  double l3x = X[ind4] - X[ind3], l3y = Y[ind4] - Y[ind3], l3z = W[ind4] - W[ind3];
+  double l4x = X[ind4] - X[ind2], l4y = Y[ind4] - Y[ind2], l4z = W[ind4] - W[ind2];
+  double surf2x = (l3y * l4z - l3z * l4y), surf2y = (l3z * l4x - l3x * l4z), surf2z = (l3x * l4y - l3y * l4x);
+  double surface2 = sqrt(surf2x * surf2x + surf2y * surf2y + surf2z * surf2z);
+  double ps = surf1x * surf2x + surf1y * surf2y + surf1z * surf2z;
+  return 0.5 * fsign(ps) * (surface1 + surface2);
 }
 
 struct SearchStats { int nvisit; int ncand; int ntet; };
@@ -627,7 +659,32 @@ CX_D bool celln_valid_o2(const ZoneView& Z, int ic, int jc, int kc, const double
   return eqzero(val, CX_EPS_GEOM);
 }
 
-// InterpData::getExtrapolationCoeffForCell (InterpData.cpp:699-947), 3-D.
+// cellN validity of a 2-D order-2 stencil, coefficients already folded onto 4 nodes (Interp2.cpp:312-338)
+CX_D bool celln_valid_o2_2d(const ZoneView& Z, int ic, int jc, const double* cf, int nature)
+{
+  if (Z.cellN == nullptr) return true;
+  const int ni = Z.ni;
+  if (nature == 0)
+  {
+    double val = 1.;
+    for (int jj = 0; jj < 2; jj++) for (int ii = 0; ii < 2; ii++)
+    {
+      double c0 = Z.cellN[(ic + ii) + (jc + jj) * ni];
+      int d = cf[ii + jj * 2] > 1.e-12;
+      val *= c0 - d + 1;
+    }
+    return !eqzero(val, CX_EPS_GEOM);
+  }
+  double val = 0.;
+  for (int jj = 0; jj < 2; jj++) for (int ii = 0; ii < 2; ii++)
+  {
+    double c0 = Z.cellN[(ic + ii) + (jc + jj) * ni];
+    val += fabs(cf[ii + jj * 2]) * fabs(1. - c0);
+  }
+  return eqzero(val, CX_EPS_GEOM);
+}
+
+// InterpData::getExtrapolationCoeffForCell (InterpData.cpp:699-947), 3-D and 2-D (nk == 1: 4 nodes).
 // (ic,jc,kc) 1-based on entry.  cf holds the last tetra's weights on return 0.
 CX_DN int extrap_coeff_for_cell(const ZoneView& Z, double x, double y, double z, int ic, int jc, int kc,
                                 double* cf, int nature, double constraint, double& diff_coeff)
@@ -643,10 +700,11 @@ CX_DN int extrap_coeff_for_cell(const ZoneView& Z, double x, double y, double z,
   for (int i = 0; i < 8; i++) { cfSav[i] = 0.; cfSav2[i] = 0.; }
   bool valid = false;
   // validity of the 8 vertices does not depend on the tetrahedron
+  const int nkk = (Z.nk == 1) ? 1 : 2;       // dim == 2: the 4 nodes of the plane only (InterpData.cpp:828-850)
   double val = 1.;
   if (Z.cellN != nullptr)
   {
-    for (int kk = 0; kk < 2; kk++) for (int jj = 0; jj < 2; jj++) for (int ii = 0; ii < 2; ii++)
+    for (int kk = 0; kk < nkk; kk++) for (int jj = 0; jj < 2; jj++) for (int ii = 0; ii < 2; ii++)
     {
       double c0 = Z.cellN[(ic + ii) + (jc + jj) * ni + (kc + kk) * nij];
       if (nature == 0) val *= c0; else val *= c0 * (c0 - 2.);
@@ -707,7 +765,7 @@ CX_DN int extrap_coeff_for_cell(const ZoneView& Z, double x, double y, double z,
     {
       sum = 0.;
       int icell = 0;
-      for (int kk = 0; kk < 2; kk++) for (int jj = 0; jj < 2; jj++) for (int ii = 0; ii < 2; ii++)
+      for (int kk = 0; kk < nkk; kk++) for (int jj = 0; jj < 2; jj++) for (int ii = 0; ii < 2; ii++)
       {
         double c0 = Z.cellN[(ic + ii) + (jc + jj) * ni + (kc + kk) * nij];
         if (nature == 1) loc[icell] = 1. - fabs(c0 - 1.);
@@ -718,10 +776,13 @@ CX_DN int extrap_coeff_for_cell(const ZoneView& Z, double x, double y, double z,
     }
     else sum = 8.;
     if (sum < 1.e-15) return 0;
+    const int ncells = (Z.nk == 1) ? 4 : 8;
+    if (Z.nk == 1)                            // 2-D: the 8 coefficients are folded onto the plane first (:927-934)
+      for (int i = 0; i < 4; i++) { cf[i] += cf[i + 4]; cf[i + 4] = 0.; }
     double sum2 = 0.;
-    for (int i = 0; i < 8; i++) sum2 += (1. - loc[i]) * cf[i];
+    for (int i = 0; i < ncells; i++) sum2 += (1. - loc[i]) * cf[i];
     double report = sum2 / sum;
-    for (int i = 0; i < 8; i++) cf[i] = (cf[i] + report) * loc[i];
+    for (int i = 0; i < ncells; i++) cf[i] = (cf[i] + report) * loc[i];
     return 1;
   }
   return 0;
@@ -796,12 +857,22 @@ CX_DN int search_extrap_cell(const ZoneView& Z, double x, double y, double z, in
 // ---------------------------------------------------------------------------
 struct RcvOut { int noblk, type, dind; double cf[8]; };
 
-// commonCheckCoefs.h, type 2 branch: exactly one |coef| > 1e-10 -> type 1
+// commonCheckCoefs.h, type 2 / type 22 branches: exactly one |coef| > 1e-10 -> type 1
 CX_D void collapse_type2(const ZoneView& Z, int& type, int& dind, double* cf)
 {
   const int ni = Z.ni, ninj = Z.ni * Z.nj;
   int nb = 0, indNonZero = -1;
   double coefNonZero = 0.;
+  if (type == 22)
+  {
+    for (int jj = 0; jj < 2; jj++) for (int ii = 0; ii < 2; ii++)
+    {
+      double c = cf[ii + jj * 2];
+      if (fabs(c) > 1.e-10) { nb++; indNonZero = dind + ii + jj * ni; coefNonZero = c; }
+    }
+    if (nb == 1) { type = 1; dind = indNonZero; cf[0] = coefNonZero; }
+    return;
+  }
   for (int kk = 0; kk < 2; kk++) for (int jj = 0; jj < 2; jj++) for (int ii = 0; ii < 2; ii++)
   {
     double c = cf[ii + jj * 2 + kk * 4];
@@ -825,6 +896,26 @@ CX_D void interp_o2_receptor(double x, double y, double z, int nz, const ZoneVie
   {
     const ZoneView& Z = zones[noz];
     int ic, jc, kc;
+    if (Z.nk == 1)
+    {
+      // 2-D donor (Interp2.cpp:204-207, :300-340): z must be the zone's plane; coefficients folded onto the 4 nodes
+      if (fabs(z - Z.bbox[2]) > CX_EPS_GEOM) continue;
+      int found2 = search_interp_cell(Z, x, y, z, ic, jc, kc, tcf, st);
+      if (found2 < 1) continue;
+      ic -= 1; jc -= 1;
+      int isBorder2 = (ic == 0 || ic == Z.ni - 2 || jc == 0 || jc == Z.nj - 2);
+      int tind2 = ic + jc * Z.ni;
+      for (int i = 0; i < 4; i++) { tcf[i] += tcf[i + 4]; tcf[i + 4] = 0.; }
+      if (!celln_valid_o2_2d(Z, ic, jc, tcf, nature)) continue;
+      double vol2 = cell_area_2d(Z, tind2);
+      if (penalty == 1 && isBorder2 == 1) vol2 += 1.e3;
+      if (vol2 < best + CX_EPS_GEOM)
+      {
+        best = vol2; o.type = 22; o.dind = tind2; o.noblk = noz + 1;
+        for (int i = 0; i < 4; i++) { o.cf[i] = tcf[i] + tcf[i + 4]; o.cf[i + 4] = 0.; }
+      }
+      continue;
+    }
     int found = (Z.topo == 0) ? cart_search_o2(Z, x, y, z, ic, jc, kc, tcf)
                               : search_interp_cell(Z, x, y, z, ic, jc, kc, tcf, st);
     if (found < 1) continue;
@@ -860,6 +951,27 @@ CX_D void extrap_receptor(double x, double y, double z, int nz, const ZoneView* 
     int found = search_extrap_cell(Z, x, y, z, ic, jc, kc, tcf, nature, constraint, st);
     if (found < 1) continue;
     ic -= 1; jc -= 1; kc -= 1;
+    if (Z.nk == 1)
+    {
+      // Interp2.cpp:125-136 + commonTypesForExtrapAndInterp.h:72-105
+      int isBorder2 = (ic == 0 || ic == Z.ni - 2 || jc == 0 || jc == Z.nj - 2);
+      int tind2 = ic + jc * Z.ni;
+      for (int i = 0; i < 4; i++) { tcf[i] += tcf[i + 4]; tcf[i + 4] = 0.; }
+      double vol2 = cell_area_2d(Z, tind2);
+      if (penalty == 1 && isBorder2 == 1) vol2 += 1.e3;
+      if (vol2 < best + CX_EPS_GEOM)
+      {
+        double sumCf = 0.;
+        for (int i = 0; i < 4; i++) sumCf += fabs(tcf[i]);
+        if (sumCf < sumCoefMin)
+        {
+          sumCoefMin = sumCf;
+          best = vol2; o.type = 22; o.dind = tind2; o.noblk = noz + 1;
+          for (int i = 0; i < 4; i++) { o.cf[i] = tcf[i] + tcf[i + 4]; o.cf[i + 4] = 0.; }
+        }
+      }
+      continue;
+    }
     int isBorder = (ic == 0 || ic == Z.ni - 2 || jc == 0 || jc == Z.nj - 2 || kc == 0 || kc == Z.nk - 2);
     int tind = ic + jc * Z.ni + kc * Z.ni * Z.nj;
     double vol = cell_volume(Z, tind);
@@ -940,10 +1052,11 @@ CX_D bool adt_resolve(const BuildView& B, int L, int c)
 }
 
 // bbox keys of cell c (InterpAdt.cpp:310-388)
+// nk == 1 (InterpAdt.cpp:391-431): the 4 nodes of the quad give x,y; the z keys are the zone's plane and plane + 1
+// (zmin2d, zmax2d = _zmin, _zmax of the InterpAdt)
 CX_D void adt_cell_keys(int ni, int nj, int nk, const double* x, const double* y, const double* z, int c,
-                        int ncells, double* keys, AdtNode* nodes)
+                        int ncells, double* keys, AdtNode* nodes, double zmin2d = 0., double zmax2d = 0.)
 {
-  (void)nk;
   int nic = ni - 1, njc = nj - 1;
   int k = c / (nic * njc);
   int j = (c - k * nic * njc) / nic;
@@ -951,13 +1064,28 @@ CX_D void adt_cell_keys(int ni, int nj, int nk, const double* x, const double* y
   int nij = ni * nj;
   int ind = i + ni * j + nij * k;
   double xmin = 1.e20, ymin = 1.e20, zmin = 1.e20, xmax = -1.e20, ymax = -1.e20, zmax = -1.e20;
-  const int off[8] = {0, 1, ni, nij, ni + 1, nij + 1, ni + nij, ni + nij + 1};
-  for (int v = 0; v < 8; v++)
+  if (nk > 1)
   {
-    int n = ind + off[v];
-    double xv = x[n], yv = y[n], zv = z[n];
-    xmin = xv < xmin ? xv : xmin; ymin = yv < ymin ? yv : ymin; zmin = zv < zmin ? zv : zmin;
-    xmax = xv > xmax ? xv : xmax; ymax = yv > ymax ? yv : ymax; zmax = zv > zmax ? zv : zmax;
+    const int off[8] = {0, 1, ni, nij, ni + 1, nij + 1, ni + nij, ni + nij + 1};
+    for (int v = 0; v < 8; v++)
+    {
+      int n = ind + off[v];
+      double xv = x[n], yv = y[n], zv = z[n];
+      xmin = xv < xmin ? xv : xmin; ymin = yv < ymin ? yv : ymin; zmin = zv < zmin ? zv : zmin;
+      xmax = xv > xmax ? xv : xmax; ymax = yv > ymax ? yv : ymax; zmax = zv > zmax ? zv : zmax;
+    }
+  }
+  else
+  {
+    const int off[4] = {0, 1, ni, ni + 1};
+    for (int v = 0; v < 4; v++)
+    {
+      int n = ind + off[v];
+      double xv = x[n], yv = y[n];
+      xmin = xv < xmin ? xv : xmin; ymin = yv < ymin ? yv : ymin;
+      xmax = xv > xmax ? xv : xmax; ymax = yv > ymax ? yv : ymax;
+    }
+    zmin = zmin2d; zmax = zmax2d;
   }
   size_t n = ncells;
   keys[c] = xmin; keys[n + c] = ymin; keys[2 * n + c] = zmin;

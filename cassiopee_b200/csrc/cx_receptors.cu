@@ -44,6 +44,19 @@ __global__ void k_rcv_gather(int n, int loc, int ni, int nj, int nk, const unsig
   const int n0 = i + j * ni + k * nij;
   const double* a[3] = {x, y, z};
   double* b[3] = {xo, yo, zo};
+  if (nk == 1)
+  {
+    // 2-D zone (node2Center.cpp:98-117): 0.25*(n0+n1+n2+n3)
+    for (int q = 0; q < 3; q++)
+    {
+      const double* p = a[q] + n0;
+      double s = p[0] + p[1];
+      s = s + p[ni];
+      s = s + p[ni + 1];
+      b[q][o] = 0.25 * s;
+    }
+    return;
+  }
   for (int q = 0; q < 3; q++)
   {
     const double* p = a[q] + n0;
@@ -65,11 +78,11 @@ int cx_receptors_create(cx_ctx* c, int ni, int nj, int nk, const double* x, cons
                         const double* cellN, int loc, cx_receptors** out)
 {
   if (loc != 0 && loc != 1) { cx_set_error("setInterpData: invalid loc."); return -1; }
-  if (ni < 2 || nj < 2 || nk < 2) { cx_set_error("receptor zones must be 3D on the device path"); return -4; }
+  if (ni < 2 || nj < 2 || nk < 1) { cx_set_error("receptor zones must be 3D, or 2D with nk=1"); return -4; }
   CX_CUDA(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   const size_t nn = (size_t)ni * nj * nk;
-  const size_t np = loc == 0 ? nn : (size_t)(ni - 1) * (nj - 1) * (nk - 1);
+  const size_t np = loc == 0 ? nn : (size_t)(ni - 1) * (nj - 1) * (size_t)(nk > 1 ? nk - 1 : 1);
   if (nn > 2000000000ull) { cx_set_error("receptor zone too large for int32 indices"); return -1; }
   cx_receptors* R = new cx_receptors;
   R->ctx = c; R->n = 0; R->npts = (int)np; R->d_ind = nullptr; R->d_x = R->d_y = R->d_z = nullptr;

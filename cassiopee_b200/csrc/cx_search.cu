@@ -174,6 +174,27 @@ k_extrap(int nlist, const int* __restrict__ list, const double* __restrict__ xr,
       int found = search_extrap_cell_warp(Z, x, y, z, ic, jc, kc, tcf, nature, 40., s_cand[w], lane, &st);
       if (found < 1) continue;
       ic -= 1; jc -= 1; kc -= 1;
+      if (Z.nk == 1)
+      {
+        // 2-D donor: type 22, coefficients folded onto the plane (Interp2.cpp:125-136, commonTypesForExtrapAndInterp.h:72-105)
+        int isBorder2 = (ic == 0 || ic == Z.ni - 2 || jc == 0 || jc == Z.nj - 2);
+        int tind2 = ic + jc * Z.ni;
+        for (int i = 0; i < 4; i++) { tcf[i] += tcf[i + 4]; tcf[i + 4] = 0.; }
+        double vol2 = cell_area_2d(Z, tind2);
+        if (penalty == 1 && isBorder2 == 1) vol2 += 1.e3;
+        if (vol2 < best + CX_EPS_GEOM)
+        {
+          double sumCf = 0.;
+          for (int i = 0; i < 4; i++) sumCf += fabs(tcf[i]);
+          if (sumCf < sumCoefMin)
+          {
+            sumCoefMin = sumCf;
+            best = vol2; type = 22; dind = tind2; noblk = noz + 1;
+            for (int i = 0; i < 4; i++) { cf[i] = tcf[i] + tcf[i + 4]; cf[i + 4] = 0.; }
+          }
+        }
+        continue;
+      }
       int isBorder = (ic == 0 || ic == Z.ni - 2 || jc == 0 || jc == Z.nj - 2 || kc == 0 || kc == Z.nk - 2);
       int tind = ic + jc * Z.ni + kc * Z.ni * Z.nj;
       double vol = cell_volume(Z, tind);

@@ -52,6 +52,23 @@ __device__ __forceinline__ void transfer_entry(int e, int m, int nvars, const PD
       if (MODE == 0) pr[v][o] = val; else dense[(size_t)v * ld + o] = val;
     }
   }
+  else if (TYPE == 22)
+  {
+    // 2-D order 2 (commonInterpTransfers.h:56-73): 4 nodes of one plane
+    double c[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) c[k] = cfT[(size_t)k * m + e];
+    for (int v = 0; v < nvars; v++)
+    {
+      const double* f = pd[v] + d0;
+      double val = 0.;
+      val += c[0] * __ldg(f);
+      val += c[1] * __ldg(f + 1);
+      val += c[2] * __ldg(f + imd);
+      val += c[3] * __ldg(f + imd + 1);
+      if (MODE == 0) pr[v][o] = val; else dense[(size_t)v * ld + o] = val;
+    }
+  }
   else if (TYPE == 2)
   {
     double c[8];
@@ -582,6 +599,14 @@ __global__ void k_transfer_celln(int m, const double* __restrict__ cellND, doubl
   const int d0 = donor[e];
   double val = 1.;
   if (TYPE == 1) { double c = cellND[d0]; val = c * (2. - c); }
+  else if (TYPE == 22)
+  {
+    for (int jj = 0; jj < 2; jj++) for (int ii = 0; ii < 2; ii++)
+    {
+      double cf = cfT[(size_t)(ii + 2 * jj) * m + e];
+      if (fabs(cf) > 1.e-11) { double c = cellND[d0 + ii + jj * imd]; val *= c * (2. - c); }
+    }
+  }
   else if (TYPE == 2)
   {
     for (int kk = 0; kk < 2; kk++) for (int jj = 0; jj < 2; jj++) for (int ii = 0; ii < 2; ii++)
@@ -604,8 +629,8 @@ __global__ void k_transfer_celln(int m, const double* __restrict__ cellND, doubl
 
 }  // namespace
 
-static int ncf_host(int t) { return t == 1 ? 1 : t == 2 ? 8 : t == 3 ? 9 : t == 44 ? 12 : t == 5 ? 15 : -1; }
-static int sten_host(int t) { return t == 1 ? 1 : t == 2 ? 8 : t == 3 ? 27 : t == 44 ? 64 : t == 5 ? 125 : 0; }
+static int ncf_host(int t) { return t == 1 ? 1 : t == 2 ? 8 : t == 22 ? 4 : t == 3 ? 9 : t == 44 ? 12 : t == 5 ? 15 : -1; }
+static int sten_host(int t) { return t == 1 ? 1 : t == 2 ? 8 : t == 22 ? 4 : t == 3 ? 27 : t == 44 ? 64 : t == 5 ? 125 : 0; }
 
 namespace {
 // plan build: counting sort of one type group by donor index (so a warp's
@@ -783,19 +808,19 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
   P->d_donor = P->d_rcv = P->d_pos = P->d_seq = nullptr; P->alg_bytes_fixed = 0; P->distinct_nodes = -1; P->last_ms = 0.f;
   P->groups.clear();
   if (n == 0) { P->ngroups = 0; return 0; }
-  const int types[5] = {1, 2, 3, 5, 44};
+  const int types[6] = {1, 2, 3, 5, 44, 22};
   std::vector<unsigned long long> off((size_t)n);
   long long run = 0;
-  int cnt[5] = {0, 0, 0, 0, 0};
+  int cnt[6] = {0, 0, 0, 0, 0, 0};
   for (int e = 0; e < n; e++)
   {
     off[e] = (unsigned long long)run;
     int nc = ncf_host(type[e]);
-    if (nc < 0) { cx_set_error("transfer plan: interpolation type %d is not supported (structured 3-D donors: 1,2,3,44,5)", type[e]); return -1; }
+    if (nc < 0) { cx_set_error("transfer plan: interpolation type %d is not supported (structured donors: 1,2,22,3,44,5)", type[e]); return -1; }
     if (donor[e] < 0 || (long long)donor[e] >= nptsD) { cx_set_error("transfer plan: donor index %d out of range", donor[e]); return -1; }
     if (rcv[e] < 0 || (long long)rcv[e] >= nptsR) { cx_set_error("transfer plan: receptor index %d out of range", rcv[e]); return -1; }
     run += nc;
-    for (int g = 0; g < 5; g++) if (type[e] == types[g]) cnt[g]++;
+    for (int g = 0; g < 6; g++) if (type[e] == types[g]) cnt[g]++;
   }
   if (run != ncoefs) { cx_set_error("transfer plan: coefficient array has %lld entries, types need %lld", ncoefs, run); return -1; }
   P->alg_bytes_fixed = 8 * run + 12ll * n;
@@ -823,7 +848,7 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
   k_iota<<<cx_grid(n, 256), 256, 0, s>>>(n, P->d_seq);
   const int TB = 256;
   int first = 0;
-  for (int g = 0; g < 5; g++)
+  for (int g = 0; g < 6; g++)
   {
     if (cnt[g] == 0) continue;
     cx_plan::Group G; G.type = types[g]; G.ncf = ncf_host(types[g]); G.sten = sten_host(types[g]);
@@ -935,6 +960,7 @@ int cx_plan_launch(cx_plan* P, int nvars, const double* const* dD, double* const
           else { CX_LAUNCH(3) }
           break;
         case 44: CX_LAUNCH(44) break;
+        case 22: CX_LAUNCH(22) break;
         case 5: CX_LAUNCH(5) break;   // 125-point stencils: staging measured slower (5.5 vs 3.5 ms on C2a), direct gather
       }
 #undef CX_LAUNCH
@@ -958,6 +984,7 @@ int cx_plan_launch_celln(cx_plan* P, const double* dCellND, double* dCellNR, cud
       case 2: k_transfer_celln<2><<<grid, TB, 0, s>>>(G.n, dCellND, dCellNR, imd, ij, dn_, rc_, G.d_cf); break;
       case 3: k_transfer_celln<3><<<grid, TB, 0, s>>>(G.n, dCellND, dCellNR, imd, ij, dn_, rc_, G.d_cf); break;
       case 44: k_transfer_celln<44><<<grid, TB, 0, s>>>(G.n, dCellND, dCellNR, imd, ij, dn_, rc_, G.d_cf); break;
+      case 22: k_transfer_celln<22><<<grid, TB, 0, s>>>(G.n, dCellND, dCellNR, imd, ij, dn_, rc_, G.d_cf); break;
       case 5: k_transfer_celln<5><<<grid, TB, 0, s>>>(G.n, dCellND, dCellNR, imd, ij, dn_, rc_, G.d_cf); break;
     }
     P->ctx->launches++;
@@ -976,8 +1003,8 @@ struct cx_planset {
   struct Big { cx_plan* P; int mode; std::vector<const double*> dD; std::vector<double*> dR; double* dense; long long ld; };
   std::vector<Big> big;
   size_t smem, smem3, smem5;            // dynamic shared memory of the type-2 / 3 / 5 launches
-  int nblocks[5];                       // per interpolation type 1,2,3,5,44
-  SetDesc* d_descs[5]; int* d_blk2desc[5];
+  int nblocks[6];                       // per interpolation type 1,2,3,5,44,22
+  SetDesc* d_descs[6]; int* d_blk2desc[6];
   void** d_tables; size_t ntables;      // device pointer tables owned by the set
 };
 
@@ -1009,9 +1036,9 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
   S->ctx = ctx; S->nvars = nvars; S->d_tables = nullptr; S->ntables = 0; S->ndesc = 0;
   S->staged = cx_transfer_staging(); S->smem = 0; S->smem3 = 0; S->smem5 = 0; S->tiled = 0;
   if (nvars > CX_MAXVARS) { cx_set_error("plan set: at most %d variables per set", CX_MAXVARS); delete S; return -1; }
-  std::vector<SetDesc> descs[5]; std::vector<int> b2d[5]; std::vector<void*> tables;
+  std::vector<SetDesc> descs[6]; std::vector<int> b2d[6]; std::vector<void*> tables;
   const int TB = 256;
-  int nb[5] = {0, 0, 0, 0, 0};
+  int nb[6] = {0, 0, 0, 0, 0, 0};
   for (int p = 0; p < nplans; p++)
   {
     cx_plan* P = plans[p];
@@ -1030,7 +1057,7 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
     if (modes[p] == 0) { CX_CHECK(upload_ptr_table((const double* const*)d_fieldR[p], nvars, &tr)); tables.push_back(tr); }
     for (auto& G : P->groups)
     {
-      int t = G.type == 1 ? 0 : G.type == 2 ? 1 : G.type == 3 ? 2 : G.type == 5 ? 3 : 4;
+      int t = G.type == 1 ? 0 : G.type == 2 ? 1 : G.type == 3 ? 2 : G.type == 5 ? 3 : G.type == 44 ? 4 : 5;
       SetDesc D;
       D.m = G.n; D.type = G.type; D.imd = P->imd; D.imdjmd = P->imd * P->jmd; D.mode = modes[p] == 0 ? 0 : 1; D.first_block = nb[t];
       D.nptsD = P->nptsD; D.layout = G.layout; D.jmd = P->jmd; D.ntx = G.ntx; D.nty = G.nty;
@@ -1049,7 +1076,7 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
       S->ndesc++;
     }
   }
-  for (int t = 0; t < 5; t++)
+  for (int t = 0; t < 6; t++)
   {
     S->nblocks[t] = nb[t]; S->d_descs[t] = nullptr; S->d_blk2desc[t] = nullptr;
     if (nb[t] == 0) continue;
@@ -1080,6 +1107,7 @@ static int planset_run_on(cx_planset* S, cudaStream_t s)
   if (S->nblocks[2]) { k_transfer_set<3, false><<<S->nblocks[2], 256, S->smem3, s>>>(S->d_descs[2], S->d_blk2desc[2], S->nvars, S->staged); S->ctx->launches++; }
   if (S->nblocks[3]) { k_transfer_set<5, false><<<S->nblocks[3], 256, S->smem5, s>>>(S->d_descs[3], S->d_blk2desc[3], S->nvars, S->staged); S->ctx->launches++; }
   if (S->nblocks[4]) { k_transfer_set<44, false><<<S->nblocks[4], 256, 0, s>>>(S->d_descs[4], S->d_blk2desc[4], S->nvars, S->staged); S->ctx->launches++; }
+  if (S->nblocks[5]) { k_transfer_set<22, false><<<S->nblocks[5], 256, 0, s>>>(S->d_descs[5], S->d_blk2desc[5], S->nvars, S->staged); S->ctx->launches++; }
   return 0;
 }
 
@@ -1088,7 +1116,7 @@ int cx_planset_run(cx_planset* S) { return planset_run_on(S, S->ctx->stream); }
 int cx_planset_destroy(cx_planset* S)
 {
   if (!S) return 0;
-  for (int t = 0; t < 5; t++) { cudaFree(S->d_descs[t]); cudaFree(S->d_blk2desc[t]); }
+  for (int t = 0; t < 6; t++) { cudaFree(S->d_descs[t]); cudaFree(S->d_blk2desc[t]); }
   for (size_t i = 0; i < S->ntables; i++) cudaFree(S->d_tables[i]);
   free(S->d_tables);
   delete S;

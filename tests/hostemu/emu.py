@@ -42,6 +42,9 @@ def zone_bbox(ni, nj, nk, x, y, z):
         m[sl, :, :] = True; m[:, sl, :] = True; m[:, :, sl] = True
     m = m.reshape(-1)
     lo = [a[m].min() for a in (x, y, z)]; hi = [a[m].max() for a in (x, y, z)]
+    if nk == 1:                      # InterpAdt.cpp:293-301: a z = constant plane gets a thickness of 1
+        assert abs(hi[2] - lo[2]) < 1e-8
+        hi[2] = lo[2] + 1.
     return np.array(lo + hi)
 
 

@@ -32,7 +32,7 @@ void* emu_zone_create(int ni, int nj, int nk, const double* x, const double* y, 
                       const double* bbox)
 {
   EmuZone* Z = new EmuZone;
-  Z->ni = ni; Z->nj = nj; Z->nk = nk; Z->npts = ni * nj * nk; Z->ncells = (ni - 1) * (nj - 1) * (nk - 1);
+  Z->ni = ni; Z->nj = nj; Z->nk = nk; Z->npts = ni * nj * nk; Z->ncells = (ni - 1) * (nj - 1) * (nk > 1 ? nk - 1 : 1);
   Z->x.assign(x, x + Z->npts); Z->y.assign(y, y + Z->npts); Z->z.assign(z, z + Z->npts);
   if (cellN) Z->c.assign(cellN, cellN + Z->npts); else Z->c.assign(Z->npts, 1.0);
   for (int i = 0; i < 6; i++) Z->bbox[i] = bbox[i];
@@ -43,7 +43,7 @@ void* emu_zone_create(int ni, int nj, int nk, const double* x, const double* y, 
   BuildView B; B.keys = keys.data(); B.lo = lo.data(); B.hi = hi.data(); B.cur = cur.data(); B.br = br.data(); B.depth = dep.data();
   B.nodes = Z->nodes.data(); B.ncells = n;
   for (int d = 0; d < 6; d++) { B.zb.lo[d] = bbox[d % 3]; B.zb.hi[d] = bbox[3 + d % 3]; }
-  for (int c = 0; c < n; c++) adt_cell_keys(ni, nj, nk, x, y, z, c, n, B.keys, B.nodes);
+  for (int c = 0; c < n; c++) adt_cell_keys(ni, nj, nk, x, y, z, c, n, B.keys, B.nodes, bbox[2], bbox[5]);
   freeze_node(B.nodes[0], 0, B.zb.lo[0], B.zb.hi[0]);
   std::vector<int> act, next;
   for (int c = 1; c < n; c++) act.push_back(c);

@@ -421,3 +421,72 @@ def test_post_extract_mesh(ctx, order):
         got = C.getFieldArray(ze, v).reshape(-1, order='F')
         assert np.array_equal(got, r), v
         assert (got[~found] == 0.).all()
+
+
+def test_two_dimensional_donors_type22(ctx):
+    """nk = 1 zones (z = constant): setInterpData (type 22 / type 1, extrapolation, holes, mixed with order 3
+    requests that fall back to extrapolation) and type-22 transfers + strict cellN, bit-exact vs the reference."""
+    from cassiopee_b200 import _lib
+    from oracle import oracle as O
+    import cassiopee_b200.Generator as G
+    a = G.cart((0, 0, 0.25), (0.1, 0.1, 1.), (11, 11, 1))
+    b = G.cylinder((0.5, 0.5, 0.25), 0.1, 0.6, 360., 0., 1., (33, 9, 1))
+    A = (11, 11, 1) + tuple(cases.flat(a)); B = (33, 9, 1) + tuple(cases.flat(b))
+    rng = np.random.default_rng(0)
+    P = rng.uniform(-0.3, 1.3, (3, 6000)); P[2] = 0.25
+    P[2][:50] = 0.3
+    P[0][50:250] = np.round(P[0][50:250], 1); P[1][50:250] = np.round(P[1][50:250], 1)
+    ca = np.ones(A[3].size); ca[rng.random(ca.size) < 0.06] = 0.; ca[rng.random(ca.size) < 0.06] = 2.
+    cb = np.ones(B[3].size); cb[rng.random(cb.size) < 0.06] = 0.; cb[rng.random(cb.size) < 0.06] = 2.
+    got, ref, gz, oz = _compare(ctx, [A], P)
+    typ = got[2][0]
+    assert (typ == 22).sum() > 1000 and (typ == 1).sum() > 10 and got[4][0].size > 100
+    for nature in (0, 1):
+        for penalty in (0, 1):
+            _compare(ctx, [A, B], P, 2, nature, penalty, 1, [ca, cb])
+            _compare(ctx, [B, A], P, 2, nature, penalty, 0, [cb, ca])
+    _compare(ctx, [A, B], P, 3, 1, 1, 1, [ca, cb])          # order 3 needs nk >= 3: everything is extrapolated (type 22)
+    # transfers
+    rcv, dnr, cf = got[0][0], got[1][0], got[3][0]
+    nR = P[0].size
+    fD = cases.fields(A[3], A[4], A[5], 5) + [A[3] + 2 * A[4]]
+    fRg = [np.zeros(nR) for _ in fD]; fRo = [np.zeros(nR) for _ in fD]
+    plan = _lib.Plan(ctx, 11, 11, 1, nR, dnr, rcv, typ, cf)
+    plan.transfer(fD, fRg)
+    O.transfer(fD, fRo, 11, 11, rcv, dnr, typ, cf)
+    for x, y in zip(fRg, fRo):
+        assert np.array_equal(x, y)
+    assert np.array_equal(plan.transferD(fD), O.transferD(fD, 11, 11, dnr, typ, cf))
+    ext = np.zeros(nR, bool); ext[got[4][0]] = True
+    ok = np.zeros(nR, bool); ok[rcv] = True
+    assert np.abs(fRg[-1] - (P[0] + 2 * P[1]))[ok & ~ext].max() < 1e-12
+    cRg = np.full(nR, 2.); cRo = np.full(nR, 2.)
+    plan.transfer_celln(ca, cRg)
+    O.transfer_celln(ca, cRo, 11, 11, rcv, dnr, typ, cf)
+    assert np.array_equal(cRg, cRo)
+
+
+def test_two_dimensional_pytree_api(ctx):
+    """X.setInterpData / setInterpTransfers on 2-D zones, receptors at centres (node2Center of quads)."""
+    import cassiopee_b200.Converter as C
+    import cassiopee_b200.Generator as G
+    import cassiopee_b200.Internal as Internal
+    import cassiopee_b200.Connector.PyTree as X
+    a = G.cart((0, 0, 0), (0.1, 0.1, 1.), (21, 21, 1), name='A')
+    b = G.cart((0.53, 0.41, 0), (0.07, 0.06, 1.), (9, 8, 1), name='B')
+    t = C.newPyTree(['Base', a, b])
+    C._initVars(t, 'centers:F', lambda x, y, z: x + 2 * y)
+    C._initVars(t, 'centers:cellN', 1.)
+    zb = Internal.getZones(t)[1]
+    C._initVars(zb, 'centers:cellN', 2.)
+    exact = C.getFieldArray(zb, 'centers:F').copy()
+    C._initVars(zb, 'centers:F', 0.)
+    tc = C.node2Center(t)
+    tc = X.setInterpData(t, tc, order=2, nature=1, loc='centers', storage='inverse', itype='chimera', verbose=0)
+    s = Internal.getNodeFromName1(Internal.getZones(tc)[0], 'ID_B')
+    assert s is not None
+    assert set(np.unique(Internal.getNodeFromName1(s, 'InterpolantsType')[1])) <= {1, 22}
+    assert Internal.getNodeFromName1(s, 'PointListDonor')[1].size == 8 * 7
+    t2 = X.setInterpTransfers(t, tc, variables=['F'], storage=1)
+    got = C.getFieldArray(Internal.getZones(t2)[1], 'centers:F')
+    assert np.abs(got - exact).max() < 1e-12

@@ -122,3 +122,30 @@ def test_cartesian_donors_interpcart_order3_order4_weights(order):
     assert tt.sum() > 1000
     assert np.array_equal(ro["dind"][tt], dind[tt])
     assert np.array_equal(ro["cf"][tt][:, :3 * order], cf[tt])
+
+
+def _zones2d():
+    import cassiopee_b200.Generator as G
+    import cassiopee_b200.Converter as C
+    a = G.cart((0, 0, 0.25), (0.1, 0.1, 1.), (11, 11, 1))
+    b = G.cylinder((0.5, 0.5, 0.25), 0.1, 0.6, 360., 0., 1., (33, 9, 1))
+    A = (11, 11, 1) + tuple(cases.flat(a)); B = (33, 9, 1) + tuple(cases.flat(b))
+    return A, B
+
+
+def test_two_dimensional_donors_type22():
+    """nk = 1 donors in a z = constant plane: extruded hexa search, coefficients folded onto 4 nodes (type 22),
+    quad area for the cross-zone choice, 2-D cellN tests, extrapolation, type-1 collapse."""
+    A, B = _zones2d()
+    rng = np.random.default_rng(0)
+    P = rng.uniform(-0.3, 1.3, (3, 3000)); P[2] = 0.25
+    P[2][:50] = 0.3                                   # off the plane: never interpolated (Interp2.cpp:204-207)
+    P[0][50:150] = np.round(P[0][50:150], 1); P[1][50:150] = np.round(P[1][50:150], 1)   # on donor nodes: type 1
+    ca = np.ones(A[3].size); ca[rng.random(ca.size) < 0.06] = 0.; ca[rng.random(ca.size) < 0.06] = 2.
+    cb = np.ones(B[3].size); cb[rng.random(cb.size) < 0.06] = 0.; cb[rng.random(cb.size) < 0.06] = 2.
+    r = _compare([A], P)
+    assert (r["type"] == 22).sum() > 500 and (r["type"] == 1).sum() > 10 and r["isext"].sum() > 100
+    for nature in (0, 1):
+        for penalty in (0, 1):
+            _compare([A, B], P, nature, penalty, 1, [ca, cb])
+            _compare([B, A], P, nature, penalty, 0, [cb, ca])
