@@ -219,7 +219,7 @@ __device__ __forceinline__ bool transfer_tile2_staged(StageSmem& S, int t0, int 
   {
     l = donor[e] - d_lo; o = (size_t)idx[e];
 #pragma unroll
-    for (int k = 0; k < 8; k++) c[k] = cfT[(size_t)k * m + e];
+    for (int k = 0; k < 8; k++) c[k] = cfT[(size_t)k * m + e];   // (streaming __ldcs loads measured no faster)
   }
   for (int v = 0; v < nvars; v++)
   {
