@@ -27,13 +27,27 @@ __global__ void k_p2p_signal(int npeers, int* const* __restrict__ peer_flags, in
   __threadfence_system();                       // the remote plans' stores (previous kernel) are performed; order the flag after them
   *((volatile int*)peer_flags[p]) = iter;
 }
+__device__ __forceinline__ unsigned long long global_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// A peer that never signals (crashed rank, mismatched iteration counts) must not hang the GPU: after
+// CX_P2P_TIMEOUT_NS the kernel traps and the error surfaces at the next synchronisation.
+#define CX_P2P_TIMEOUT_NS 30000000000ull
 __global__ void k_p2p_wait(int npeers, const int* my_flags, int iter)
 {
   int p = threadIdx.x;
   if (p < npeers)
   {
     const volatile int* f = my_flags + p;
-    while (*f < iter) { __nanosleep(100); }
+    const unsigned long long t0 = global_ns();
+    while (*f < iter)
+    {
+      __nanosleep(100);
+      if (global_ns() - t0 > CX_P2P_TIMEOUT_NS) __trap();
+    }
   }
   __threadfence_system();
 }
