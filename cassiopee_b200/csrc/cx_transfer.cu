@@ -509,7 +509,7 @@ struct SetDesc {
 };
 
 template <int TYPE, bool TILED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, TILED ? 2 : 4)
 k_transfer_set(const SetDesc* __restrict__ descs, const int* __restrict__ blk2desc, int nvars, int staged)
 {
   // descriptor and field-pointer tables go through shared memory once per CTA: the per-variable pointer
@@ -523,6 +523,15 @@ k_transfer_set(const SetDesc* __restrict__ descs, const int* __restrict__ blk2de
   __syncthreads();
   const SetDesc& D = sD;
   PDk pd{s_pd}; PRk pr{s_pr};
+  if (TYPE == 2 && D.type == 1)
+  {
+    // coincident (type 1) entries ride in the type-2 launch: small plans are launch-latency bound, one launch less
+    int e1 = (blockIdx.x - D.first_block) * blockDim.x + threadIdx.x;
+    if (e1 >= D.m) return;
+    if (D.mode == 0) transfer_entry<1, 0, PDk, PRk, 1>(e1, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
+    else transfer_entry<1, 1, PDk, PRk, 1>(e1, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
+    return;
+  }
   if (TYPE == 2)
   {
     extern __shared__ __align__(16) double dyn_sm[];
@@ -1039,6 +1048,10 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
   std::vector<SetDesc> descs[6]; std::vector<int> b2d[6]; std::vector<void*> tables;
   const int TB = 256;
   int nb[6] = {0, 0, 0, 0, 0, 0};
+  bool has2 = false;
+  for (int p = 0; p < nplans; p++)
+    if (plans[p]->n > 0 && plans[p]->n < CX_BIG_PLAN)
+      for (auto& G : plans[p]->groups) if (G.type == 2) has2 = true;
   for (int p = 0; p < nplans; p++)
   {
     cx_plan* P = plans[p];
@@ -1057,7 +1070,7 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
     if (modes[p] == 0) { CX_CHECK(upload_ptr_table((const double* const*)d_fieldR[p], nvars, &tr)); tables.push_back(tr); }
     for (auto& G : P->groups)
     {
-      int t = G.type == 1 ? 0 : G.type == 2 ? 1 : G.type == 3 ? 2 : G.type == 5 ? 3 : G.type == 44 ? 4 : 5;
+      int t = G.type == 1 ? (has2 ? 1 : 0) : G.type == 2 ? 1 : G.type == 3 ? 2 : G.type == 5 ? 3 : G.type == 44 ? 4 : 5;
       SetDesc D;
       D.m = G.n; D.type = G.type; D.imd = P->imd; D.imdjmd = P->imd * P->jmd; D.mode = modes[p] == 0 ? 0 : 1; D.first_block = nb[t];
       D.nptsD = P->nptsD; D.layout = G.layout; D.jmd = P->jmd; D.ntx = G.ntx; D.nty = G.nty;
