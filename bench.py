@@ -158,14 +158,19 @@ def run_c2(args):
         hx = [_lib.pinned_copy(a) for a in (Bg.x, Bg.y, Bg.z)]
         hr = [_lib.pinned_copy(a) for a in (Oc.x, Oc.y, Oc.z)]
         res = None
-        for it in range(2):
+        e2e_calls = []
+        for it in range(3):
             out = None
             ctx.sync()
             t0 = time.perf_counter()
             zone_e = _lib.Zone(ctx, Bg.ni, Bg.nj, Bg.nk, hx[0], hx[1], hx[2])
+            t1 = time.perf_counter()
             res_e = _lib.set_interp_data(ctx, hr[0], hr[1], hr[2], [zone_e], 2, 1, 1, 1)
+            t2 = time.perf_counter()
             out = res_e.fetch(pinned=True)
             sid_e2e_s = time.perf_counter() - t0
+            e2e_calls.append({"total_s": sid_e2e_s, "zone_upload_adt_s": t1 - t0, "search_s": t2 - t1,
+                              "fetch_s": sid_e2e_s - (t2 - t0)})
             del zone_e, res_e
         del hx, hr
     rcv, dnr, typ, coefs = out[0][0], out[1][0], out[2][0], out[3][0]
@@ -177,7 +182,8 @@ def run_c2(args):
            "adt_cells": int(zinfo["ncells"]), "zone_create_s": t_zone,
            "e2e": {"value": nrcv / sid_e2e_s, "unit": "receptor pts/s",
                    "includes": "pinned host buffers: H2D donor+receptor coords, ADT build, search, packing, D2H of "
-                               "index/type/coef lists (2nd call; pinned output pool warm)",
+                               "index/type/coef lists (3rd call; pinned output pool and device memory pool warm)",
+                   "calls": (e2e_calls if not args.quick else None),
                    "h2d_bytes": int(8 * 3 * (Bg.npts + nrcv)), "d2h_bytes": int(12 * n + 8 * coefs.size)},
            "interpolated": int(n), "orphans": int(out[5].size), "gpu_launches": int(sid_launches)}
     res = None
