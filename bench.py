@@ -275,8 +275,9 @@ def gj_flops(n):
 
 
 def extra_legs(ctx, Bg, Oc, zone, dxr, dyr, dzr, pD, nvars):
-    """Device-resident timings of the other BASELINE configs on the C2a geometry (informational; parity for them
-    is in tests/): C3 = Lagrange order 3 (all receptors) and order 5 (every 16th receptor) + their transfers;
+    """Device-resident timings of the other BASELINE configs on the C2 geometry (informational; parity for them
+    is in tests/): C2b = curvilinear donor (receptors = background nodes inside the annulus <- O-grid);
+    C3 = Lagrange order 3 (all receptors) and order 5 (every 16th receptor) + their transfers;
     interpDataType=0 = the reference's closed-form path for Cartesian donors (InterpCart)."""
     from cassiopee_b200 import _lib
     out = {}
@@ -298,6 +299,54 @@ def extra_legs(ctx, Bg, Oc, zone, dxr, dyr, dzr, pD, nvars):
         out["interpcart_order%d" % order] = {"value": nrcv / (np.mean(ms) * 1e-3), "unit": "receptor pts/s",
                                               "ms": float(np.mean(ms)), "receptors": int(nrcv), "zone_create_s": t_zc}
     del zc
+    # --- C2b: curvilinear donor (the O-grid), receptors = background nodes inside the annulus
+    r2 = Bg.x * Bg.x + Bg.y * Bg.y
+    selb = np.nonzero((r2 > 0.25) & (r2 < 6.25))[0]
+    xb, yb, zb = [np.ascontiguousarray(a[selb]) for a in (Bg.x, Bg.y, Bg.z)]
+    t0 = time.perf_counter()
+    zo = _lib.Zone(ctx, Oc.ni, Oc.nj, Oc.nk, Oc.x, Oc.y, Oc.z)
+    ctx.sync()
+    t_zo = time.perf_counter() - t0
+    io = zo.info()
+    dxb = _lib.DeviceArray.from_host(ctx, xb); dyb = _lib.DeviceArray.from_host(ctx, yb); dzb = _lib.DeviceArray.from_host(ctx, zb)
+    ms = []
+    for it in range(3):
+        ctx.sync(); t0 = time.perf_counter()
+        r = _lib.set_interp_data_dev(ctx, selb.size, dxb.ptr, dyb.ptr, dzb.ptr, [zo], 2, 1, 1, 1)
+        ctx.sync()
+        if it > 0:
+            ms.append((time.perf_counter() - t0) * 1e3)
+        if it < 2:
+            r = None
+    st = r.stats()
+    o = r.fetch()
+    r = None
+    planb = _lib.Plan(ctx, Oc.ni, Oc.nj, Oc.nk, selb.size, o[1][0], o[0][0], o[2][0], o[3][0])
+    fO = [np.ascontiguousarray(Oc.x + 2 * Oc.y + 3 * Oc.z)] + [np.ascontiguousarray(np.sin(Oc.x * (v + 1)) + Oc.z) for v in range(nvars - 1)]
+    dO = [_lib.DeviceArray.from_host(ctx, f) for f in fO]
+    dRb = [_lib.DeviceArray(ctx, selb.size) for _ in range(nvars)]
+    pO = [d.ptr for d in dO]; pRb = [d.ptr for d in dRb]
+    for _ in range(3):
+        planb.transfer_dev(pO, pRb)
+    ctx.sync(); ctx.event_record(0)
+    for _ in range(10):
+        planb.transfer_dev(pO, pRb)
+    ctx.event_record(1)
+    tms = ctx.event_elapsed_ms() / 10
+    Bb = planb.alg_bytes(nvars)
+    lin = dRb[0].download()
+    ok = np.zeros(selb.size, bool); ok[o[0][0]] = True
+    ext = np.zeros(selb.size, bool); ext[o[4][0]] = True
+    err = float(np.abs(lin - (xb + 2 * yb + 3 * zb))[ok & ~ext].max()) if (ok & ~ext).any() else None
+    out["c2b_curvilinear_donor"] = {
+        "set_interp_data": {"value": selb.size / (np.mean(ms) * 1e-3), "unit": "receptor pts/s", "ms": float(np.mean(ms)),
+                            "receptors": int(selb.size), "interpolated": int(o[0][0].size), "extrapolated": int(o[4][0].size),
+                            "orphans": int(o[5].size), "search_kernel_ms": float(st["search_ms"]),
+                            "nodes_visited_per_query": float(st["nodes_visited"]) / selb.size,
+                            "adt_build_ms": float(io["build_ms"]), "adt_depth": int(io["depth"]), "zone_create_s": t_zo},
+        "transfer": {"value": Bb / (tms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": tms, "alg_bytes_per_step": int(Bb),
+                     "nvars": nvars, "linear_field_max_abs_error": err}}
+    del planb, dO, dRb, zo, dxb, dyb, dzb
     # --- C3: Lagrange orders 3 and 5 through the ADT donor
     for order, stride in ((3, 1), (5, 16)):
         if stride == 1:
