@@ -148,7 +148,9 @@ __device__ __forceinline__ void transfer_entry(int e, int m, int nvars, const PD
 // once per CTA, coalesced, with no register or scoreboard cost while it is in flight.  Tiles whose donors
 // span more than CX_SPAN nodes (row wraps at the edge of the overlap region, sparse fringes) take the
 // direct-gather path.  Arithmetic (operand order, no FMA) is the same on both paths.
-#define CX_SPAN 384
+// Measured on C2a: tiles of 128 entries 0.576 ms, 256 entries 0.489 ms, 512 entries 0.511 ms; a span buffer of
+// 512 nodes (33 KB per CTA, L1 squeezed to 28 KB) 0.583 ms, 384 or 256 nodes 0.49 ms.
+#define CX_SPAN 256
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
@@ -933,6 +935,8 @@ int cx_plan_launch(cx_plan* P, int nvars, const double* const* dD, double* const
     for (auto& G : P->groups)
     {
       int grid = cx_grid(G.n, TB);
+      static int tb2s = 0;       // CX_T2S_TB: threads per CTA of the staged type-2 kernel (experiment; default 256)
+      if (!tb2s) { const char* e = getenv("CX_T2S_TB"); tb2s = e ? atoi(e) : 256; if (tb2s != 128 && tb2s != 256) tb2s = 256; }
       const int* dn_ = P->d_donor + G.first; const int* rc_ = P->d_rcv + G.first;
       const int* ps_ = (mode_in == 2 ? P->d_seq : P->d_pos) + G.first;
       int imd = P->imd, ij = P->imd * P->jmd;
@@ -955,8 +959,9 @@ int cx_plan_launch(cx_plan* P, int nvars, const double* const* dD, double* const
           }
           else if (staged && G.layout == 1)
           {
-            if (mode == 0) k_transfer2s<0><<<grid, TB, sizeof(StageSmem), s>>>(G.n, nv, F, imd, ij, P->nptsD, dn_, rc_, ps_, G.d_cf, dn, ld);
-            else k_transfer2s<1><<<grid, TB, sizeof(StageSmem), s>>>(G.n, nv, F, imd, ij, P->nptsD, dn_, rc_, ps_, G.d_cf, dn, ld);
+            const int g2 = cx_grid(G.n, tb2s);
+            if (mode == 0) k_transfer2s<0><<<g2, tb2s, sizeof(StageSmem), s>>>(G.n, nv, F, imd, ij, P->nptsD, dn_, rc_, ps_, G.d_cf, dn, ld);
+            else k_transfer2s<1><<<g2, tb2s, sizeof(StageSmem), s>>>(G.n, nv, F, imd, ij, P->nptsD, dn_, rc_, ps_, G.d_cf, dn, ld);
           }
           else { CX_LAUNCH(2) }
           break;

@@ -1,3 +1,2 @@
 cd $GRAFT_REPO_ROOT
-python bench.py --steps 5 --warmup 3 2> gpurun_out/b.err | python -c "import json,sys;d=json.loads(sys.stdin.read());print(json.dumps(d['other_configs']['c2b_curvilinear_donor'],indent=1))"
-tail -3 gpurun_out/b.err
+for tb in 256 512 256 512; do echo TB=$tb; CX_T2S_TB=$tb python tools/exp_store_modes.py 2>&1 | tail -3 | head -1; done
