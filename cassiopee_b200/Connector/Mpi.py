@@ -51,9 +51,11 @@ def computeDonorGraph(aR, aD, comm, loc='nodes', sameName=1, zoneOrder=None):
     getIntersectingDomains + hooks).  Order = zoneOrder (names) if given, else
     (rank, position) order, so results do not depend on who computes."""
     local = []
+    boxes = {}          # zone object -> bbox (a tree that is both receptor and donor is reduced once)
     for z in Internal.getZones(aD):
         _, ni, nj, nk, _ = Internal.getZoneDim(z)
-        local.append(dict(name=z[0], dims=(ni, nj, nk), bbox=_zoneBBox(z), rank=comm.rank))
+        boxes[id(z)] = _zoneBBox(z)
+        local.append(dict(name=z[0], dims=(ni, nj, nk), bbox=boxes[id(z)], rank=comm.rank))
     allmeta = comm.allgather_obj(local)
     meta = [m for part in allmeta for m in part]
     if zoneOrder is not None:
@@ -61,7 +63,7 @@ def computeDonorGraph(aR, aD, comm, loc='nodes', sameName=1, zoneOrder=None):
         meta.sort(key=lambda m: pos[m['name']])
     donorLists = {}
     for z in Internal.getZones(aR):
-        bb = _receptorBBox(z, loc)
+        bb = boxes[id(z)] if id(z) in boxes else _receptorBBox(z, loc)
         donorLists[z[0]] = [m['name'] for m in meta
                             if not (sameName == 1 and m['name'] == z[0]) and bbox_intersect(bb, m['bbox'])]
     return meta, donorLists
