@@ -573,21 +573,108 @@ def setInterpTransfers(aR, topTreeD, variables=[], cellNVariable='cellN',
     return tR
 
 
-def _transferOne(ctx, zr, zd, s, variables, cellNVariable, ListRcv, ListDonor):
+def _rotationOf(s):
+    """(dirR, theta) of an ID_* subregion (OversetData.py:2000-2006, setInterpTransfers.cpp:281-285): the first
+    non-zero component of the RotationAngle child selects the axis; the value goes to cos/sin as it is."""
+    node = Internal.getNodeFromName1(s, 'RotationAngle')
+    if node is None:
+        return 0, 0.
+    ang = numpy.asarray(node[1], dtype=numpy.float64).reshape(-1)
+    for d in range(3):
+        if abs(ang[d]) > 0.:
+            return d + 1, float(ang[d])
+    return 0, 0.
+
+
+def _rotationTriplets(zr, locR, nvars):
+    """Positions rotated by includeTransfers.h: VelocityX/Y/Z and MomentumX/Y/Z are looked up in the receptor
+    container's variable string (setInterpTransfers.cpp:401-410) and used as indices into the list of
+    transferred fields (vectOfRcvFields), exactly like the reference."""
+    varsR = C.getVarNames(zr, locR)
+    trip = []
+    for base in ('Velocity', 'Momentum'):
+        pos = [varsR.index(base + a) if (base + a) in varsR else -1 for a in 'XYZ']
+        if min(pos) > -1:
+            if max(pos) >= nvars:
+                raise ValueError("_setInterpTransfers: %sX/Y/Z sit at positions %s of the receptor fields but only %d "
+                                 "fields are transferred (the reference indexes out of bounds here)." % (base, pos, nvars))
+            trip.append(tuple(pos))
+    return trip
+
+
+def _compactFields(first, nvars, ndimdx, what):
+    """compact=1 (getfromzoneDcompact.h / getfromzoneRcompact.h): only the first variable is looked up, field eq
+    lives at first + eq*ndimdx doubles.  The views are checked against the memory block that owns the first
+    array, so non-compacted trees raise instead of reading out of bounds."""
+    if first is None:
+        raise TypeError("_setInterpTransfers: compact=1: first variable not found in the %s zone." % what)
+    if first.dtype != numpy.float64 or first.size != ndimdx or not (first.flags.f_contiguous or first.flags.c_contiguous):
+        raise TypeError("_setInterpTransfers: compact=1: %s field must be a contiguous float64 array of the zone size." % what)
+    owner = first
+    while isinstance(owner.base, numpy.ndarray):
+        owner = owner.base
+    lo = owner.__array_interface__['data'][0]
+    hi = lo + owner.nbytes
+    a0 = first.__array_interface__['data'][0]
+    if not owner.flags.c_contiguous and not owner.flags.f_contiguous:
+        raise ValueError("_setInterpTransfers: compact=1: the %s fields are not compacted." % what)
+    if a0 < lo or a0 + 8 * ndimdx * nvars > hi:
+        raise ValueError("_setInterpTransfers: compact=1: the %s fields are not compacted (%d fields of %d values "
+                         "expected behind the first variable)." % (what, nvars, ndimdx))
+    flat = owner.reshape(-1, order='A').view(numpy.float64) if owner.dtype == numpy.float64 else None
+    if flat is None:
+        raise TypeError("_setInterpTransfers: compact=1: %s block is not float64." % what)
+    o0 = (a0 - lo) // 8
+    return [flat[o0 + eq * ndimdx: o0 + (eq + 1) * ndimdx] for eq in range(nvars)]
+
+
+def _transferOneCompact(ctx, zr, zd, s, variables, varType, ListRcv, ListDonor):
+    """connector._setInterpTransfers, compact != 0 (setInterpTransfers.cpp:474-497): 5 fields (1 <= varType <= 3)
+    or 6, contiguous behind variables[0] on both sides; no cellN rule, no rotation (the reference warns)."""
     location = Internal.getNodeFromName1(s, 'GridLocation')
     if location is not None: location = Internal.getValue(location)
     loc = 1 if location == 'CellCenter' else 0
-    if Internal.getNodeFromName1(s, 'RotationAngle') is not None:
-        raise NotImplementedError("_setInterpTransfers: periodicity by rotation has no device path.")
+    if not isinstance(variables, list) or len(variables) == 0 or not isinstance(variables[0], str):
+        raise TypeError("_setInterpTransfers: compact=1 needs the name of the first variable.")
+    nvars = 5 if 1 <= varType <= 3 else 6
+    # containers as getfromzoneDcompact.h:2-3 / getfromzoneRcompact.h:5-6 select them
+    solD = Internal.getNodeFromName1(zd, Internal.__FlowSolutionCenters__ if loc == 0 else Internal.__FlowSolutionNodes__)
+    solR = Internal.getNodeFromName1(zr, Internal.__FlowSolutionNodes__ if loc == 0 else Internal.__FlowSolutionCenters__)
+    nD = None if solD is None else Internal.getNodeFromName1(solD, variables[0])
+    nR = None if solR is None else Internal.getNodeFromName1(solR, variables[0])
+    _, imd, jmd, kmd, _ = Internal.getZoneDim(zd)
+    ndimdxD = imd * jmd * kmd
+    ndimdxR = int(numpy.prod(C.fieldShape(zr, 'centers' if loc == 1 else 'nodes')))
+    fD = _compactFields(None if nD is None else nD[1], nvars, ndimdxD, 'donor')
+    fR = _compactFields(None if nR is None else nR[1], nvars, ndimdxR, 'receiver')
+    Coefs = Internal.getNodeFromName1(s, 'InterpolantsDonor')[1]
+    DonorType = Internal.getNodeFromName1(s, 'InterpolantsType')[1]
+    plan = _getPlan(ctx, zd, ndimdxR, ListDonor, ListRcv, DonorType, Coefs)
+    plan.transfer(fD, fR)
+    if _rotationOf(s)[0] != 0:
+        print("Warning: _setInterpTransfers: no correction for periodicity by rotation can be applied in compacted version.")
+
+
+def _transferOne(ctx, zr, zd, s, variables, cellNVariable, ListRcv, ListDonor, varType=2, compact=0):
+    if compact != 0:
+        return _transferOneCompact(ctx, zr, zd, s, variables, varType, ListRcv, ListDonor)
+    location = Internal.getNodeFromName1(s, 'GridLocation')
+    if location is not None: location = Internal.getValue(location)
+    loc = 1 if location == 'CellCenter' else 0
+    dirR, theta = _rotationOf(s)
     Coefs = Internal.getNodeFromName1(s, 'InterpolantsDonor')[1]
     DonorType = Internal.getNodeFromName1(s, 'InterpolantsType')[1]
     names, strict, locR = _selectVariables(zr, zd, variables, cellNVariable, loc)
     nptsR = int(numpy.prod(C.fieldShape(zr, locR)))
     plan = _getPlan(ctx, zd, nptsR, ListDonor, ListRcv, DonorType, Coefs)
+    trip = _rotationTriplets(zr, locR, len(names)) if dirR != 0 else []
     if names:
         fD = [C.getFieldArray(zd, v) for v in names]
         fR = [C.getFieldArray(zr, (('centers:' + v) if locR == 'centers' else v)) for v in names]
-        plan.transfer(fD, fR)
+        if trip:
+            plan.transfer_rot(fD, fR, dirR, theta, trip)
+        else:
+            plan.transfer(fD, fR)
     if strict:
         cD = C.getFieldArray(zd, cellNVariable)
         cR = C.getFieldArray(zr, ('centers:' + cellNVariable) if locR == 'centers' else cellNVariable)
@@ -598,8 +685,6 @@ def _setInterpTransfers(aR, topTreeD, variables=[], cellNVariable='',
                         variablesIBC=['Density', 'VelocityX', 'VelocityY', 'VelocityZ', 'Temperature'],
                         bcType=0, varType=2, storage=-1, compact=0, compactD=0,
                         Gamma=1.4, Cv=1.7857142857142865, MuS=1.e-08, Cs=0.3831337844872463, Ts=1.0, ctx=None):
-    if compact != 0:
-        raise NotImplementedError("_setInterpTransfers: compact=1 (Fast solver layout) has no device path yet.")
     ctx = ctx or _lib.default_context()
     # direct storage: data held by the receptor zones (OversetData.py:1968-2033)
     if storage < 1:
@@ -615,7 +700,7 @@ def _setInterpTransfers(aR, topTreeD, variables=[], cellNVariable='',
                             ListRcv = Internal.getNodeFromName1(s, 'PointList')[1]
                             ListDonor = Internal.getNodeFromName1(s, 'PointListDonor')[1]
                             zd = znd[Internal.getValue(s)]
-                            _transferOne(ctx, zr, zd, s, variables, cellNVariable, ListRcv, ListDonor)
+                            _transferOne(ctx, zr, zd, s, variables, cellNVariable, ListRcv, ListDonor, varType, compact)
     # inverse storage: data held by the donor zones (OversetData.py:2036-2098)
     if storage != 0:
         znr = {z[0]: z for z in Internal.getZones(aR)}
@@ -631,7 +716,7 @@ def _setInterpTransfers(aR, topTreeD, variables=[], cellNVariable='',
                             ListRcv = Internal.getNodeFromName1(s, 'PointListDonor')[1]
                             zr = znr.get(Internal.getValue(s), None)
                             if zr is not None:
-                                _transferOne(ctx, zr, zd, s, variables, cellNVariable, ListRcv, ListDonor)
+                                _transferOne(ctx, zr, zd, s, variables, cellNVariable, ListRcv, ListDonor, varType, compact)
     return None
 
 
@@ -655,8 +740,6 @@ def _setInterpTransfersD(topTreeD, variables=[], cellNVariable='',
     (OversetData.py:2179-2270; connector._setInterpTransfersD,
     setInterpTransfersD.cpp:106-303: listed variables present in the donor's
     FlowSolution, or all of them but cellNVariable for an empty list)."""
-    if compact != 0:
-        raise NotImplementedError("_setInterpTransfersD: compact=1 has no device path yet.")
     if backend is None:
         ctx = ctx or _lib.default_context()
     infos = []
@@ -675,6 +758,23 @@ def _setInterpTransfersD(topTreeD, variables=[], cellNVariable='',
                 DonorType = Internal.getNodeFromName1(s, 'InterpolantsType')[1]
                 ListDonor = Internal.getNodeFromName1(s, 'PointList')[1]
                 ListRcv = Internal.getNodeFromName1(s, 'PointListDonor')[1]
+                if compact != 0:
+                    # setInterpTransfersD.cpp:232-235, :282-296, getfromzonecompactD.h: 5 (1 <= varType <= 3) or 6
+                    # fields behind variables[0] in the donor's FlowSolution; the names given label the array
+                    if backend is not None:
+                        raise NotImplementedError("_setInterpTransfersD: compact=1 needs the device backend.")
+                    if not isinstance(variables, list) or len(variables) == 0 or not isinstance(variables[0], str):
+                        raise TypeError("_setInterpTransfersD: compact=1 needs the name of the first variable.")
+                    nvc = 5 if 1 <= varType <= 3 else 6
+                    _, imd, jmd, kmd, _ = Internal.getZoneDim(zd)
+                    solD = Internal.getNodeFromName1(zd, Internal.__FlowSolutionNodes__)
+                    nD = None if solD is None else Internal.getNodeFromName1(solD, variables[0])
+                    fDc = _compactFields(None if nD is None else nD[1], nvc, imd * jmd * kmd, 'donor')
+                    nmax = int(ListRcv.max()) + 1 if ListRcv.size else 1
+                    plan = _getPlan(ctx, zd, nmax, ListDonor, ListRcv, DonorType, Coefs)
+                    arr = plan.transferD(fDc)
+                    infos.append([Internal.getValue(s), [','.join(variables), arr, ListRcv.size, 1, 1], ListRcv, loc])
+                    continue
                 varsD = C.getVarNames(zd, 'nodes')
                 if isinstance(variables, list) and len(variables) > 0:
                     names = [v for v in variables if v in varsD and v != cellNVariable]

@@ -5,6 +5,7 @@ can be opened, every compute entry point raises.  numpy host arrays stay owned
 by Python; device mirrors are owned by the handle objects below.
 """
 import ctypes
+import math
 import os
 import weakref
 import numpy as np
@@ -64,6 +65,8 @@ _SIGS = {
     "cx_plan_create": (_i, [_vp, _i, _i, _i, _ll, _i, _vp, _vp, _vp, _vp, _ll, _vp]),
     "cx_transfer": (_i, [_vp, _i, _vp, _vp]),
     "cx_transferD": (_i, [_vp, _i, _vp, _vp]),
+    "cx_transfer_rot": (_i, [_vp, _i, _vp, _vp, _i, _d, _d, _i, _vp]),
+    "cx_rotate_dev": (_i, [_vp, _i, _d, _d, _vp, _vp, _vp]),
     "cx_transfer_celln": (_i, [_vp, _vp, _vp]),
     "cx_transfer_dev": (_i, [_vp, _i, _vp, _vp]),
     "cx_transferD_dev": (_i, [_vp, _i, _vp, _vp, _ll]),
@@ -447,6 +450,19 @@ class Plan:
         fR = self._check_fields(fieldsR, self.nptsR, "receptor")
         assert len(fD) == len(fR)
         check(lib().cx_transfer(self.h, len(fD), ptr_array([ptr(a) for a in fD]), ptr_array([ptr(a) for a in fR])))
+
+    def transfer_rot(self, fieldsD, fieldsR, dirR, theta, triplets):
+        """transfer() followed by the periodicity-by-rotation correction (includeTransfers.h): triplets =
+        list of (ix, iy, iz) positions in the variable list; cos/sin by the host libm like the reference."""
+        fD = self._check_fields(fieldsD, self.nptsD, "donor")
+        fR = self._check_fields(fieldsR, self.nptsR, "receptor")
+        assert len(fD) == len(fR)
+        trip = np.ascontiguousarray(np.asarray(triplets, np.int32).reshape(-1))
+        check(lib().cx_transfer_rot(self.h, len(fD), ptr_array([ptr(a) for a in fD]), ptr_array([ptr(a) for a in fR]),
+                                    int(dirR), math.cos(theta), math.sin(theta), trip.size // 3, ptr(trip)))
+
+    def rotate_dev(self, dirR, theta, dfx, dfy, dfz):
+        check(lib().cx_rotate_dev(self.h, int(dirR), math.cos(theta), math.sin(theta), _vp(dfx), _vp(dfy), _vp(dfz)))
 
     def transferD(self, fieldsD):
         """Dense (nvars, n) host array (connector._setInterpTransfersD)."""

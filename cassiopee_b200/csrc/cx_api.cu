@@ -107,6 +107,8 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
 int cx_plan_launch(cx_plan* P, int nvars, const double* const* dD, double* const* dR, double* dense, long long ld,
                    int mode, cudaStream_t s);
 int cx_plan_launch_celln(cx_plan* P, const double* dCellND, double* dCellNR, cudaStream_t s);
+int cx_plan_rotate_on(cx_plan* P, int dirR, double ct, double st, double* fx, double* fy, double* fz, int dense,
+                      cudaStream_t s);
 
 struct cx_result_full { cx_result R; cx_result_dev D; };
 
@@ -620,8 +622,13 @@ static int pipeline_events(cx_plan_full* F, int nvars)
   return 0;
 }
 
+// Periodicity by rotation (includeTransfers.h): the vector triplets (indices into the variable list) are rotated
+// on the device, in their dense blocks, before they are downloaded.
+struct RotSpec { int dirR; double ct, st; int ntrip; const int* trip; };
+
 // dst[v]: host destination of variable v's dense (n) block
-static int transfer_pipeline(cx_plan_full* F, int nvars, const double* const* fieldD, double* const* dst)
+static int transfer_pipeline(cx_plan_full* F, int nvars, const double* const* fieldD, double* const* dst,
+                             const RotSpec* rot = nullptr)
 {
   cx_plan* P = &F->P; cx_ctx* c = P->ctx;
   CX_CUDA(cudaSetDevice(c->device));
@@ -630,16 +637,41 @@ static int transfer_pipeline(cx_plan_full* F, int nvars, const double* const* fi
   CX_CHECK(ensure(&F->d_dense, &F->dense_cap, sizeof(double) * n * nvars, false));
   CX_CHECK(pipeline_events(F, nvars));
   cudaStream_t sa = c->stream, sb = c->comm_stream;
+  std::vector<char> hold(nvars, 0);        // downloads deferred until the rotation has run
+  if (rot && rot->dirR != 0)
+    for (int t = 0; t < 3 * rot->ntrip; t++)
+    {
+      if (rot->trip[t] < 0 || rot->trip[t] >= nvars) { cx_set_error("cx_transfer_rot: variable index out of range"); return -2; }
+      hold[rot->trip[t]] = 1;
+    }
   for (int v = 0; v < nvars; v++)
   {
     double* dv = F->d_fields + per * v;
     const double* dvp = dv;
     CX_CUDA(cudaMemcpyAsync(dv, fieldD[v], sizeof(double) * per, cudaMemcpyHostToDevice, sa));
     CX_CHECK(cx_plan_launch(P, 1, &dvp, nullptr, F->d_dense + n * v, (long long)n, 1, sa));
+    if (hold[v]) continue;
     CX_CUDA(cudaEventRecord(F->evk[v], sa));
     CX_CUDA(cudaStreamWaitEvent(sb, F->evk[v], 0));
     CX_CUDA(cudaMemcpyAsync(dst[v], F->d_dense + n * v, sizeof(double) * n, cudaMemcpyDeviceToHost, sb));
     CX_CUDA(cudaEventRecord(F->evd[v], sb));
+  }
+  if (rot && rot->dirR != 0)
+  {
+    for (int t = 0; t < rot->ntrip; t++)
+    {
+      const int* tr = rot->trip + 3 * t;
+      CX_CHECK(cx_plan_rotate_on(P, rot->dirR, rot->ct, rot->st, F->d_dense + n * tr[0], F->d_dense + n * tr[1],
+                                 F->d_dense + n * tr[2], 1, sa));
+    }
+    for (int v = 0; v < nvars; v++)
+    {
+      if (!hold[v]) continue;
+      CX_CUDA(cudaEventRecord(F->evk[v], sa));
+      CX_CUDA(cudaStreamWaitEvent(sb, F->evk[v], 0));
+      CX_CUDA(cudaMemcpyAsync(dst[v], F->d_dense + n * v, sizeof(double) * n, cudaMemcpyDeviceToHost, sb));
+      CX_CUDA(cudaEventRecord(F->evd[v], sb));
+    }
   }
   return 0;
 }
@@ -657,7 +689,29 @@ int cx_transferD(cx_plan* P, int nvars, const double* const* fieldD, double* out
   return 0;
 }
 
+static int transfer_host(cx_plan* P, int nvars, const double* const* fieldD, double* const* fieldR, const RotSpec* rot);
+
 int cx_transfer(cx_plan* P, int nvars, const double* const* fieldD, double* const* fieldR)
+{
+  return transfer_host(P, nvars, fieldD, fieldR, nullptr);
+}
+
+int cx_transfer_rot(cx_plan* P, int nvars, const double* const* fieldD, double* const* fieldR, int dirR, double ctheta,
+                    double stheta, int ntrip, const int* trip)
+{
+  if (dirR < 0 || dirR > 3) { cx_set_error("cx_transfer_rot: dirR must be 0..3"); return -2; }
+  RotSpec rot{dirR, ctheta, stheta, ntrip, trip};
+  return transfer_host(P, nvars, fieldD, fieldR, &rot);
+}
+
+int cx_rotate_dev(cx_plan* P, int dirR, double ctheta, double stheta, double* d_fx, double* d_fy, double* d_fz)
+{
+  if (dirR < 1 || dirR > 3) { cx_set_error("cx_rotate_dev: dirR must be 1..3"); return -2; }
+  if (P->n == 0) return 0;
+  return cx_plan_rotate_on(P, dirR, ctheta, stheta, d_fx, d_fy, d_fz, 0, P->ctx->stream);
+}
+
+static int transfer_host(cx_plan* P, int nvars, const double* const* fieldD, double* const* fieldR, const RotSpec* rot)
 {
   cx_plan_full* F = (cx_plan_full*)P; cx_ctx* c = P->ctx;
   if (P->n == 0 || nvars == 0) return 0;
@@ -668,7 +722,7 @@ int cx_transfer(cx_plan* P, int nvars, const double* const* fieldD, double* cons
     // receptor indices are one ascending run (every point of the zone, or one slab): the dense block of a
     // variable IS the receptor field's slice, so it is downloaded in place without a host scatter
     for (int v = 0; v < nvars; v++) dst[v] = fieldR[v] + F->h_rcv[0];
-    CX_CHECK(transfer_pipeline(F, nvars, fieldD, dst.data()));
+    CX_CHECK(transfer_pipeline(F, nvars, fieldD, dst.data(), rot));
     CX_CUDA(cudaStreamSynchronize(c->comm_stream));
     CX_CUDA(cudaStreamSynchronize(c->stream));
     CX_CUDA(cudaGetLastError());
@@ -676,7 +730,7 @@ int cx_transfer(cx_plan* P, int nvars, const double* const* fieldD, double* cons
   }
   CX_CHECK(ensure(&F->h_dense, &F->hdense_cap, sizeof(double) * (size_t)n * nvars, true));
   for (int v = 0; v < nvars; v++) dst[v] = F->h_dense + (size_t)n * v;
-  CX_CHECK(transfer_pipeline(F, nvars, fieldD, dst.data()));
+  CX_CHECK(transfer_pipeline(F, nvars, fieldD, dst.data(), rot));
   // host scatter of variable v while the later variables are still on the bus; receptors of one plan are
   // distinct, so entry ranges can go to different threads
   const int* rcv = F->h_rcv.data();

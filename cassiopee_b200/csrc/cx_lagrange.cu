@@ -183,9 +183,9 @@ __device__ void lag_solve_group(const ZoneView& Z, int ics, int jcs, int kcs, do
   double* py = px + N;
   double* pz = py + N;
   double* sc = pz + N;            // 16: pts(3,4) + transformed receptor
-  volatile double* red_v = sc + 16;          // NT/32 partial maxima
-  volatile int* red_i = (volatile int*)(red_v + 32);  // 2 x NT/32 indices
-  int* ipiv = (int*)(red_v + 32) + 32;       // N flags
+  volatile double* red_v = sc + 16;          // 2 x NT/32 partial maxima (double-buffered, up to 32 warps)
+  volatile int* red_i = (volatile int*)(red_v + 64);  // 2 x NT/32 indices
+  int* ipiv = (int*)(red_v + 64) + 64;       // N flags
   int* ctl = ipiv + N + 3;                   // [0]=irow [1]=icol [2]=singular
 
   const int ni = Z.ni, ninj = Z.ni * Z.nj;
@@ -268,7 +268,7 @@ __device__ void lag_solve_group(const ZoneView& Z, int ics, int jcs, int kcs, do
   // into the elimination of step s: while a thread updates its part of a row it tracks that part's
   // maximum |a| over the still un-pivoted columns (ascending columns, '>=' => last maximum, exactly the
   // scan order of GaussjF.for:34-44), so each search is only a cross-thread arg-max.
-  constexpr int SEG = (NT >= 4 * N) ? 4 : (NT >= 2 * N) ? 2 : 1;
+  constexpr int SEG = (NT >= 8 * N) ? 8 : (NT >= 4 * N) ? 4 : (NT >= 2 * N) ? 2 : 1;
   constexpr int ROWS = NT / SEG;
   const int row = tid % ROWS;
   const int seg = tid / ROWS;
@@ -310,11 +310,11 @@ __device__ void lag_solve_group(const ZoneView& Z, int ics, int jcs, int kcs, do
     {
       // one barrier: every warp publishes its winner, then every warp reduces the NT/32 winners itself
       const int par = step & 1;       // double-buffered so the next step's writes cannot race with late readers
-      if ((tid & 31) == 0) { red_v[par * 16 + (tid >> 5)] = big; red_i[par * 16 + (tid >> 5)] = bidx; }
+      if ((tid & 31) == 0) { red_v[par * 32 + (tid >> 5)] = big; red_i[par * 32 + (tid >> 5)] = bidx; }
       __syncthreads();
       int ln = tid & 31;
-      big = (ln < NT / 32) ? red_v[par * 16 + ln] : -2.;
-      bidx = (ln < NT / 32) ? red_i[par * 16 + ln] : -1;
+      big = (ln < NT / 32) ? red_v[par * 32 + ln] : -2.;
+      bidx = (ln < NT / 32) ? red_i[par * 32 + ln] : -1;
       CX_ARGMAX_STEP(16) CX_ARGMAX_STEP(8) CX_ARGMAX_STEP(4) CX_ARGMAX_STEP(2) CX_ARGMAX_STEP(1)
       bidx = __shfl_sync(0xffffffffu, bidx, 0);
     }
@@ -398,7 +398,7 @@ template <int N1> struct LagCfg {
   static constexpr int N = N1 * N1 * N1;
   static constexpr int LD = (N + 3) | 1;
   // doubles of shared memory per group
-  static constexpr int SMEM_D = N * LD + 3 * N + 16 + 32 + ((32 + N + 3 + 4) * 4 + 7) / 8;
+  static constexpr int SMEM_D = N * LD + 3 * N + 16 + 64 + ((64 + N + 3 + 4) * 4 + 7) / 8;
 };
 
 // order 3: one warp per receptor, 4 receptors per CTA
@@ -445,7 +445,7 @@ k_lag_solve4(LagState S, int nlist, const int* __restrict__ list, const double* 
   }
 }
 
-// order 5: one 512-thread CTA per receptor, matrix (125 x 129 doubles) in shared memory
+// order 5: one 512-thread CTA per receptor, matrix (125 x 129 doubles) in shared memory (CX_LAG5=512)
 __global__ void __launch_bounds__(512)
 k_lag_solve5(LagState S, int nlist, const int* __restrict__ list, const double* __restrict__ xr,
              const double* __restrict__ yr, const double* __restrict__ zr, const ZoneView* __restrict__ zones, int noz)
@@ -459,6 +459,31 @@ k_lag_solve5(LagState S, int nlist, const int* __restrict__ list, const double* 
     stencil_start(5, Z, S.ijk[r], S.ijk[(size_t)S.n + r], S.ijk[2 * (size_t)S.n + r], ics, jcs, kcs);
     double ksi, eta, zeta; int err;
     lag_solve_group<5, 512, false>(Z, ics, jcs, kcs, xr[r], yr[r], zr[r], smem, threadIdx.x, ksi, eta, zeta, err);
+    if (threadIdx.x == 0)
+    {
+      S.ksi[r] = ksi; S.ksi[(size_t)S.n + r] = eta; S.ksi[2 * (size_t)S.n + r] = zeta; S.err[r] = err;
+    }
+    __syncthreads();
+  }
+}
+
+// order 5 with a 1024-thread CTA per receptor (8 column segments of 16 per row, 64 registers): twice the warps
+// per SM for the pivot step's dependent chain; the default (1.90 s vs 1.99 s per 1.06 M receptors; A/B:
+// CX_LAG5=512).  Keeping the matrix in registers instead (three variants, profiles/r01_e_lagrange5.md) did
+// not help: the pivot step is bound by instruction issue and the two barriers, not by shared memory.
+__global__ void __launch_bounds__(1024, 1)
+k_lag_solve5w(LagState S, int nlist, const int* __restrict__ list, const double* __restrict__ xr,
+              const double* __restrict__ yr, const double* __restrict__ zr, const ZoneView* __restrict__ zones, int noz)
+{
+  extern __shared__ double smem[];
+  for (int a = blockIdx.x; a < nlist; a += gridDim.x)
+  {
+    int r = list[a];
+    const ZoneView& Z = zones[noz];
+    int ics, jcs, kcs;
+    stencil_start(5, Z, S.ijk[r], S.ijk[(size_t)S.n + r], S.ijk[2 * (size_t)S.n + r], ics, jcs, kcs);
+    double ksi, eta, zeta; int err;
+    lag_solve_group<5, 1024, false>(Z, ics, jcs, kcs, xr[r], yr[r], zr[r], smem, threadIdx.x, ksi, eta, zeta, err);
     if (threadIdx.x == 0)
     {
       S.ksi[r] = ksi; S.ksi[(size_t)S.n + r] = eta; S.ksi[2 * (size_t)S.n + r] = zeta; S.err[r] = err;
@@ -683,8 +708,13 @@ int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_xr, cons
   const size_t smem3 = sizeof(double) * LagCfg<3>::SMEM_D * 4;
   const size_t smem4 = sizeof(double) * LagCfg<4>::SMEM_D;
   const size_t smem5 = sizeof(double) * LagCfg<5>::SMEM_D;
+  const char* lag5_env = getenv("CX_LAG5");
+  const bool lag5_wide = !(lag5_env && strcmp(lag5_env, "512") == 0);   // A/B: CX_LAG5=512 = one 512-thread CTA
   if (order == 5)
+  {
     CX_CUDA(cudaFuncSetAttribute(k_lag_solve5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+    CX_CUDA(cudaFuncSetAttribute(k_lag_solve5w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+  }
   for (int noz = 0; noz < nz; noz++)
   {
     k_lag_search<<<cx_grid(n, TB), TB, 0, s>>>(S, d_xr, d_yr, d_zr, d_zones, noz, order, d_f, d_stats);
@@ -706,7 +736,8 @@ int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_xr, cons
       else
       {
         int grid = nlist < ctx->sm_count * 4 ? nlist : ctx->sm_count * 4;
-        k_lag_solve5<<<grid, 512, smem5, s>>>(S, nlist, d_list, d_xr, d_yr, d_zr, d_zones, noz);
+        if (lag5_wide) k_lag_solve5w<<<grid, 1024, smem5, s>>>(S, nlist, d_list, d_xr, d_yr, d_zr, d_zones, noz);
+        else k_lag_solve5<<<grid, 512, smem5, s>>>(S, nlist, d_list, d_xr, d_yr, d_zr, d_zones, noz);
       }
     }
     k_lag_finish<<<cx_grid(n, TB), TB, 0, s>>>(S, d_zones, noz, order, nature, penalty);

@@ -26,6 +26,9 @@
 
 #define CX_MAXVARS 16
 #define CX_BIG_PLAN (1 << 20)   // entries; plan sets launch such plans on their own
+#ifndef CX_SET_MINB
+#define CX_SET_MINB 4            // resident CTAs per SM the plan-set kernels are compiled for
+#endif
 
 struct FieldPtrs { const double* d[CX_MAXVARS]; double* r[CX_MAXVARS]; };
 
@@ -187,12 +190,14 @@ template <int MODE, class PD, class PR>
 __device__ __forceinline__ bool transfer_tile2_staged(StageSmem& S, int t0, int m, int nvars, const PD& pd, const PR& pr,
                                                       int imd, int imdjmd, int nptsD, const int* __restrict__ donor,
                                                       const int* __restrict__ idx, const double* __restrict__ cfT,
-                                                      double* __restrict__ dense, long long ld)
+                                                      double* __restrict__ dense, long long ld, int known_lo = -1,
+                                                      int known_hi = -1)
 {
   const int tid = threadIdx.x;
   const int e = t0 + tid;
   const int last = min(t0 + (int)blockDim.x, m) - 1;
-  const int d_lo = donor[t0], d_hi = donor[last];        // sorted ascending inside a group
+  // sorted ascending inside a group; plan sets pass the tile's range from their block table
+  const int d_lo = known_lo >= 0 ? known_lo : donor[t0], d_hi = known_lo >= 0 ? known_hi : donor[last];
   const int off1 = imd, off2 = imdjmd, off3 = imdjmd + imd;
   // 16-byte aligned segment starts (element index even) and lengths (even), per row
   const int s0 = d_lo & 1, s1 = (d_lo + off1) & 1, s2 = (d_lo + off2) & 1, s3 = (d_lo + off3) & 1;
@@ -503,28 +508,34 @@ k_transfer2t(const TileRef* __restrict__ tiles, int m, int nvars, FieldPtrs P, i
 struct SetDesc {
   int m, type, imd, imdjmd, mode, first_block, nptsD;
   int layout, jmd, ntx, nty;                 // layout 2: tiled, blocks = boxes
+  int pad_;
   const TileRef* tiles;
   const int* donor; const int* idx; const double* cfT;
-  const double* const* dptr;   // device table: nvars donor field pointers
-  double* const* rptr;         // device table: nvars receptor field pointers (mode 0)
   double* dense; long long ld; // mode 1
+  const double* dp[CX_MAXVARS];  // donor field pointers (inline: no dependent table fetch)
+  double* rp[CX_MAXVARS];        // receptor field pointers (mode 0)
 };
+static_assert(sizeof(SetDesc) % 8 == 0, "SetDesc is copied to shared memory in 8-byte words");
+// one record per block of a plan-set launch: its descriptor and, for donor-sorted type-2 groups, the donor
+// index range of the block's tile (so the staging can start without reading the donor list first)
+struct BlkRec { int desc, d_lo, d_hi, pad_; };
 
 template <int TYPE, bool TILED>
-__global__ void __launch_bounds__(256, TILED ? 2 : 4)
-k_transfer_set(const SetDesc* __restrict__ descs, const int* __restrict__ blk2desc, int nvars, int staged)
+__global__ void __launch_bounds__(256, TILED ? 2 : CX_SET_MINB)
+k_transfer_set(const SetDesc* __restrict__ descs, const BlkRec* __restrict__ blk, int nvars, int staged)
 {
-  // descriptor and field-pointer tables go through shared memory once per CTA: the per-variable pointer
-  // fetches inside the entry loop are then shared-memory reads instead of dependent global loads
-  __shared__ SetDesc sD;
-  __shared__ const double* s_pd[CX_MAXVARS];
-  __shared__ double* s_pr[CX_MAXVARS];
-  if (threadIdx.x == 0) sD = descs[blk2desc[blockIdx.x]];
-  __syncthreads();
-  if (threadIdx.x < nvars) { s_pd[threadIdx.x] = sD.dptr[threadIdx.x]; s_pr[threadIdx.x] = sD.rptr ? sD.rptr[threadIdx.x] : nullptr; }
+  // the descriptor (with its field-pointer tables) goes through shared memory once per CTA, copied by 8-byte
+  // words in one round trip: the per-variable pointer fetches inside the entry loop are shared-memory reads
+  __shared__ __align__(16) SetDesc sD;
+  const BlkRec br = blk[blockIdx.x];
+  {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(descs + br.desc);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sD);
+    if (threadIdx.x < sizeof(SetDesc) / 8) dst[threadIdx.x] = src[threadIdx.x];
+  }
   __syncthreads();
   const SetDesc& D = sD;
-  PDk pd{s_pd}; PRk pr{s_pr};
+  PDk pd{sD.dp}; PRk pr{sD.rp};
   if (TYPE == 2 && D.type == 1)
   {
     // coincident (type 1) entries ride in the type-2 launch: small plans are launch-latency bound, one launch less
@@ -561,8 +572,8 @@ k_transfer_set(const SetDesc* __restrict__ descs, const int* __restrict__ blk2de
       StageSmem& S = *reinterpret_cast<StageSmem*>(dyn_sm);
       const int t0 = (blockIdx.x - D.first_block) * blockDim.x;
       bool done = (D.mode == 0)
-        ? transfer_tile2_staged<0>(S, t0, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.nptsD, D.donor, D.idx, D.cfT, D.dense, D.ld)
-        : transfer_tile2_staged<1>(S, t0, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.nptsD, D.donor, D.idx, D.cfT, D.dense, D.ld);
+        ? transfer_tile2_staged<0>(S, t0, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.nptsD, D.donor, D.idx, D.cfT, D.dense, D.ld, br.d_lo, br.d_hi)
+        : transfer_tile2_staged<1>(S, t0, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.nptsD, D.donor, D.idx, D.cfT, D.dense, D.ld, br.d_lo, br.d_hi);
       if (done) return;
     }
   }
@@ -584,6 +595,18 @@ k_transfer_set(const SetDesc* __restrict__ descs, const int* __restrict__ blk2de
   if (e >= D.m) return;
   if (D.mode == 0) transfer_entry<TYPE, 0, PDk, PRk, 1>(e, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
   else transfer_entry<TYPE, 1, PDk, PRk, 1>(e, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
+}
+
+// donor index range of every block's tile (donor-sorted type-2 groups of a plan set), once at creation
+__global__ void k_block_ranges(int nblocks, const SetDesc* __restrict__ descs, BlkRec* __restrict__ blk, int tb)
+{
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  const SetDesc& D = descs[blk[b].desc];
+  if (D.type != 2 || D.layout != 1) return;
+  const int t0 = (b - D.first_block) * tb;
+  const int last = min(t0 + tb, D.m) - 1;
+  blk[b].d_lo = D.donor[t0]; blk[b].d_hi = D.donor[last];
 }
 
 // Receptor-side batched scatter of received dense buffers: fieldR[v][rcv[e]] = in[v*ld + e]
@@ -1006,6 +1029,47 @@ int cx_plan_launch_celln(cx_plan* P, const double* dCellND, double* dCellNR, cud
   return 0;
 }
 
+// Periodicity by rotation (Connector/Connector/includeTransfers.h:1-60): after a transfer the vector (fx,fy,fz) of
+// every receptor of the plan is rotated by theta about axis dirR (1: x, 2: y, 3: z); same expressions, no FMA.
+// dense != 0: the three arrays are dense (n) blocks of one transfer (any common entry order); else they are
+// receptor fields addressed through the plan's receptor indices.
+namespace {
+__global__ void k_rotate(int n, const int* __restrict__ rcv, int dirR, double ct, double st, double* __restrict__ fx,
+                         double* __restrict__ fy, double* __restrict__ fz)
+{
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const size_t r = rcv ? (size_t)rcv[e] : (size_t)e;
+  if (dirR == 1)
+  {
+    double v1 = fy[r], v2 = fz[r];
+    fy[r] = ct * v1 - st * v2;
+    fz[r] = st * v1 + ct * v2;
+  }
+  else if (dirR == 2)
+  {
+    double v1 = fx[r], v2 = fz[r];
+    fx[r] = ct * v1 + st * v2;
+    fz[r] = -st * v1 + ct * v2;
+  }
+  else if (dirR == 3)
+  {
+    double v1 = fx[r], v2 = fy[r];
+    fx[r] = ct * v1 - st * v2;
+    fy[r] = st * v1 + ct * v2;
+  }
+}
+}  // namespace
+
+int cx_plan_rotate_on(cx_plan* P, int dirR, double ct, double st, double* fx, double* fy, double* fz, int dense,
+                      cudaStream_t s)
+{
+  if (P->n == 0 || dirR == 0) return 0;
+  k_rotate<<<cx_grid(P->n, 256), 256, 0, s>>>(P->n, dense ? nullptr : P->d_rcv, dirR, ct, st, fx, fy, fz);
+  P->ctx->launches++;
+  CX_CUDA(cudaGetLastError());
+  return 0;
+}
 
 // ---------------------------------------------------------------------------
 // plan set / scatter set
@@ -1018,8 +1082,8 @@ struct cx_planset {
   std::vector<Big> big;
   size_t smem, smem3, smem5;            // dynamic shared memory of the type-2 / 3 / 5 launches
   int nblocks[6];                       // per interpolation type 1,2,3,5,44,22
-  SetDesc* d_descs[6]; int* d_blk2desc[6];
-  void** d_tables; size_t ntables;      // device pointer tables owned by the set
+  SetDesc* d_descs[6]; BlkRec* d_blk2desc[6];
+  void** d_tables; size_t ntables;      // (unused: pointer tables are inline in the descriptors)
 };
 
 struct cx_scatterset {
@@ -1050,7 +1114,7 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
   S->ctx = ctx; S->nvars = nvars; S->d_tables = nullptr; S->ntables = 0; S->ndesc = 0;
   S->staged = cx_transfer_staging(); S->smem = 0; S->smem3 = 0; S->smem5 = 0; S->tiled = 0;
   if (nvars > CX_MAXVARS) { cx_set_error("plan set: at most %d variables per set", CX_MAXVARS); delete S; return -1; }
-  std::vector<SetDesc> descs[6]; std::vector<int> b2d[6]; std::vector<void*> tables;
+  std::vector<SetDesc> descs[6]; std::vector<BlkRec> b2d[6]; std::vector<void*> tables;
   const int TB = 256;
   int nb[6] = {0, 0, 0, 0, 0, 0};
   bool has2 = false;
@@ -1070,9 +1134,6 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
       S->big.push_back(B);
       continue;
     }
-    double** td = nullptr; double** tr = nullptr;
-    CX_CHECK(upload_ptr_table(d_fieldD[p], nvars, &td)); tables.push_back(td);
-    if (modes[p] == 0) { CX_CHECK(upload_ptr_table((const double* const*)d_fieldR[p], nvars, &tr)); tables.push_back(tr); }
     for (auto& G : P->groups)
     {
       int t = G.type == 1 ? (has2 ? 1 : 0) : G.type == 2 ? 1 : G.type == 3 ? 2 : G.type == 5 ? 3 : G.type == 44 ? 4 : 5;
@@ -1086,9 +1147,14 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
       for (int v = 0; v < nvars; v++) if (((uintptr_t)d_fieldD[p][v]) & 15) S->staged = 0;
       D.donor = P->d_donor + G.first;
       D.idx = (modes[p] == 0 ? P->d_rcv : modes[p] == 1 ? P->d_pos : P->d_seq) + G.first; D.cfT = G.d_cf;
-      D.dptr = td; D.rptr = tr; D.dense = modes[p] != 0 ? d_dense[p] : nullptr; D.ld = modes[p] != 0 ? ld[p] : 0;
+      D.pad_ = 0; D.dense = modes[p] != 0 ? d_dense[p] : nullptr; D.ld = modes[p] != 0 ? ld[p] : 0;
+      for (int v = 0; v < CX_MAXVARS; v++)
+      {
+        D.dp[v] = v < nvars ? d_fieldD[p][v] : nullptr;
+        D.rp[v] = (v < nvars && modes[p] == 0) ? d_fieldR[p][v] : nullptr;
+      }
       int blocks = (G.type == 2 && G.layout == 2) ? G.ntiles : cx_grid(G.n, TB);
-      for (int b = 0; b < blocks; b++) b2d[t].push_back((int)descs[t].size());
+      for (int b = 0; b < blocks; b++) b2d[t].push_back(BlkRec{(int)descs[t].size(), -1, -1, 0});
       descs[t].push_back(D);
       nb[t] += blocks;
       S->ndesc++;
@@ -1099,9 +1165,15 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
     S->nblocks[t] = nb[t]; S->d_descs[t] = nullptr; S->d_blk2desc[t] = nullptr;
     if (nb[t] == 0) continue;
     CX_CUDA(cudaMalloc(&S->d_descs[t], sizeof(SetDesc) * descs[t].size()));
-    CX_CUDA(cudaMalloc(&S->d_blk2desc[t], sizeof(int) * b2d[t].size()));
+    CX_CUDA(cudaMalloc(&S->d_blk2desc[t], sizeof(BlkRec) * b2d[t].size()));
     CX_CUDA(cudaMemcpy(S->d_descs[t], descs[t].data(), sizeof(SetDesc) * descs[t].size(), cudaMemcpyHostToDevice));
-    CX_CUDA(cudaMemcpy(S->d_blk2desc[t], b2d[t].data(), sizeof(int) * b2d[t].size(), cudaMemcpyHostToDevice));
+    CX_CUDA(cudaMemcpy(S->d_blk2desc[t], b2d[t].data(), sizeof(BlkRec) * b2d[t].size(), cudaMemcpyHostToDevice));
+    if (t == 1)
+    {
+      k_block_ranges<<<cx_grid(nb[t], 256), 256, 0, ctx->stream>>>(nb[t], S->d_descs[t], S->d_blk2desc[t], TB);
+      CX_CUDA(cudaStreamSynchronize(ctx->stream));
+      CX_CUDA(cudaGetLastError());
+    }
   }
   S->ntables = tables.size();
   S->d_tables = (void**)malloc(sizeof(void*) * (tables.size() + 1));

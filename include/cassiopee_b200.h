@@ -133,6 +133,15 @@ int cx_transfer(cx_plan* plan, int nvars, const double* const* fieldD, double* c
 /* Replaces connector._setInterpTransfersD (setInterpTransfersD.cpp:106-303):
  * dense out[v*n + e]. Host arrays. */
 int cx_transferD(cx_plan* plan, int nvars, const double* const* fieldD, double* out);
+/* cx_transfer followed by the periodicity-by-rotation correction of connector._setInterpTransfers
+ * (setInterpTransfers.cpp:281-285 dirR/theta from AngleX/Y/Z, :468-472, includeTransfers.h:1-60): the ntrip
+ * vector triplets trip[3*t..3*t+2] (indices into the variable list: VelocityX/Y/Z, MomentumX/Y/Z) are rotated
+ * at the plan's receptors by theta about axis dirR (1: x, 2: y, 3: z); ctheta/stheta = cos/sin(theta) computed by
+ * the caller's libm like the reference.  dirR = 0: plain cx_transfer.  Host arrays. */
+int cx_transfer_rot(cx_plan* plan, int nvars, const double* const* fieldD, double* const* fieldR, int dirR,
+                    double ctheta, double stheta, int ntrip, const int* trip);
+/* the rotation alone, in place on device-resident receptor fields, at the plan's receptors */
+int cx_rotate_dev(cx_plan* plan, int dirR, double ctheta, double stheta, double* d_fx, double* d_fy, double* d_fz);
 /* strict cellN rule (commonCellNTransfersStrict.h; setInterpTransfers.cpp:452-467) */
 int cx_transfer_celln(cx_plan* plan, const double* cellND, double* cellNR);
 /* device-resident variants (pointers from cx_dev_alloc); asynchronous on the

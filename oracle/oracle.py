@@ -70,6 +70,8 @@ def lib():
                                     ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.ref_transfer_celln.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.ref_rotate.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p] + [ctypes.c_double] * 3 + \
+            [ctypes.c_int] * 6
         L.ref_cell_volume.restype = ctypes.c_double
         L.ref_cell_volume.argtypes = [ctypes.c_void_p, ctypes.c_int]
         _lib = L
@@ -237,6 +239,13 @@ def transfer_celln(cellND, cellNR, imd, jmd, rcv, dnr, typ, coefs):
     coefs = _f64(coefs)
     lib().ref_transfer_celln(cellND.ctypes.data, cellNR.ctypes.data, int(imd), int(jmd), rcv.size,
                              rcv.ctypes.data, dnr.ctypes.data, typ.ctypes.data, coefs.ctypes.data)
+
+
+def rotate(fieldsR, rcv, angles, posv=(-1, -1, -1), posm=(-1, -1, -1)):
+    """Reference periodicity-by-rotation correction (includeTransfers.h) in place on the receptor fields."""
+    rcv = _i32(rcv)
+    lib().ref_rotate(len(fieldsR), _ptrs(fieldsR), rcv.size, rcv.ctypes.data, float(angles[0]), float(angles[1]),
+                     float(angles[2]), *[int(p) for p in posv], *[int(p) for p in posm])
 
 
 def transfer_numpy(fieldsD, fieldsR, imd, jmd, rcv, dnr, typ, coefs):

@@ -286,6 +286,28 @@ void ref_transfer_celln(double* cellND, double* cellNR, int imd_, int jmd_,
   }
 }
 
+/* Periodicity by rotation after a transfer (setInterpTransfers.cpp:281-285,
+ * :468-472): the reference's own fragment includeTransfers.h on raw pointers.
+ * posv* / posm*: positions of VelocityX/Y/Z and MomentumX/Y/Z (-1: absent). */
+void ref_rotate(int nvars_, double** rcvFields, int nrcv, const int* rcvPts_,
+                double AngleX, double AngleY, double AngleZ, int posvx_, int posvy_,
+                int posvz_, int posmx_, int posmy_, int posmz_)
+{
+  E_Int nvars = nvars_, nbRcvPts = nrcv;
+  E_Int* rcvPts = (E_Int*)rcvPts_;
+  E_Int posvx = posvx_, posvy = posvy_, posvz = posvz_, posmx = posmx_, posmy = posmy_, posmz = posmz_;
+  vector<E_Float*> vectOfRcvFields(nvars);
+  for (E_Int eq = 0; eq < nvars; eq++) vectOfRcvFields[eq] = rcvFields[eq];
+  E_Int dirR = 0; E_Float theta = 0.;
+  if (K_FUNC::E_abs(AngleX) > 0.) {dirR = 1; theta=AngleX;}
+  else if (K_FUNC::E_abs(AngleY) > 0.){dirR=2; theta=AngleY;}
+  else if (K_FUNC::E_abs(AngleZ) > 0.) {dirR=3; theta=AngleZ;}
+  if (dirR != 0)
+  {
+# include "includeTransfers.h"
+  }
+}
+
 /* K_METRIC::compVolOfStructCell3D (selection volume, for unit checks). */
 double ref_cell_volume(void* h, int indnode)
 {

@@ -490,3 +490,114 @@ def test_two_dimensional_pytree_api(ctx):
     t2 = X.setInterpTransfers(t, tc, variables=['F'], storage=1)
     got = C.getFieldArray(Internal.getZones(t2)[1], 'centers:F')
     assert np.abs(got - exact).max() < 1e-12
+
+
+def _rotation_case(rcv_shuffle):
+    """Cart pair with velocity + momentum fields on both sides and interp data in inverse storage."""
+    import cassiopee_b200.Generator as G
+    import cassiopee_b200.Converter as C
+    import cassiopee_b200.Internal as Internal
+    import cassiopee_b200.Connector.PyTree as X
+    h = 1. / 16
+    a = G.cart((0, 0, 0), (h, h, h), (17, 17, 17), name='A')
+    b = G.cart((0.27, 0.22, 0.31), (0.7 * h, 0.7 * h, 0.7 * h), (11, 11, 11), name='B')
+    t = C.newPyTree(['Base', a, b])
+    names = ['Density', 'VelocityX', 'VelocityY', 'VelocityZ', 'Temperature', 'MomentumX', 'MomentumY', 'MomentumZ']
+    for i, v in enumerate(names):
+        C._initVars(t, 'centers:' + v, lambda x, y, z, i=i: 1. + 0.3 * i + np.sin(3 * x + i) + 2. * y * y + 3. * z)
+    C._initVars(t, 'centers:cellN', 1.)
+    zb = Internal.getZones(t)[1]
+    cn = np.ones(C.fieldShape(zb, 'centers'), order='F')
+    if rcv_shuffle:
+        cn[::2, 1::2, :] = 2.          # scattered receptors: host-scatter path of cx_transfer
+    else:
+        cn[...] = 2.                   # every cell: one ascending run, downloaded in place
+    C._initVars(zb, 'centers:cellN', cn)
+    tc = C.node2Center(t)
+    tc = X.setInterpData(t, tc, order=2, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse',
+                         sameName=1, itype='chimera', verbose=0)
+    return t, tc, names
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+@pytest.mark.parametrize("rcv_shuffle", [False, True])
+def test_periodic_rotation_after_transfer(ctx, axis, rcv_shuffle):
+    """RotationAngle child of the ID_* subregion (setInterpTransfers.cpp:281-285, :468-472, includeTransfers.h):
+    velocity and momentum triplets rotated at the receptors; against the reference's own fragment."""
+    import cassiopee_b200.Converter as C
+    import cassiopee_b200.Internal as Internal
+    import cassiopee_b200.Connector.PyTree as X
+    from oracle import oracle as O
+    t, tc, names = _rotation_case(rcv_shuffle)
+    zdA = Internal.getZones(tc)[0]
+    zb = Internal.getZones(t)[1]
+    s = Internal.getNodeFromName1(zdA, 'ID_B')
+    ang = np.zeros(3); ang[axis] = 0.37 * (axis + 1)
+    Internal.createChild(s, 'RotationAngle', 'DataArray_t', ang)
+    rcv = Internal.getNodeFromName1(s, 'PointListDonor')[1]
+    dnr = Internal.getNodeFromName1(s, 'PointList')[1]
+    typ = Internal.getNodeFromName1(s, 'InterpolantsType')[1]
+    cf = Internal.getNodeFromName1(s, 'InterpolantsDonor')[1]
+    assert rcv.size > 100
+    fD = [C.getFieldArray(zdA, v) for v in names]
+    fR = [np.array(C.getFieldArray(zb, 'centers:' + v), order='F', copy=True) for v in names]
+    O.transfer(fD, fR, 16, 16, rcv, dnr, typ, cf)
+    O.rotate(fR, rcv, ang, posv=(1, 2, 3), posm=(5, 6, 7))
+    t2 = X.setInterpTransfers(t, tc, variables=names, storage=1)
+    zb2 = Internal.getZones(t2)[1]
+    for v, r in zip(names, fR):
+        assert np.array_equal(C.getFieldArray(zb2, 'centers:' + v), r), v
+    # device-resident variant: transfer, then the rotation alone at the plan's receptors
+    from cassiopee_b200 import _lib
+    plan = _lib.Plan(ctx, 16, 16, 16, fR[0].size, dnr, rcv, typ, cf)
+    dD = [_lib.DeviceArray.from_host(ctx, np.ascontiguousarray(f.reshape(-1, order='F'))) for f in fD]
+    f0 = [np.ascontiguousarray(C.getFieldArray(zb, 'centers:' + v).reshape(-1, order='F')) for v in names]
+    dR = [_lib.DeviceArray.from_host(ctx, f) for f in f0]
+    plan.transfer_dev([d.ptr for d in dD], [d.ptr for d in dR])
+    plan.rotate_dev(axis + 1, ang[axis], dR[1].ptr, dR[2].ptr, dR[3].ptr)
+    plan.rotate_dev(axis + 1, ang[axis], dR[5].ptr, dR[6].ptr, dR[7].ptr)
+    ctx.sync()
+    for d, r in zip(dR, fR):
+        assert np.array_equal(d.download(), r.reshape(-1, order='F'))
+
+
+def test_compact_fields_transfer(ctx):
+    """_setInterpTransfers(compact=1) (setInterpTransfers.cpp:474-497, getfromzone{D,R}compact.h): 5 fields
+    (varType 1..3) or 6 lying one behind the other behind variables[0]; same arithmetic as the general path."""
+    import cassiopee_b200.Converter as C
+    import cassiopee_b200.Internal as Internal
+    import cassiopee_b200.Connector.PyTree as X
+    from oracle import oracle as O
+    t, tc, _ = _rotation_case(True)
+    zdA = Internal.getZones(tc)[0]
+    zb = Internal.getZones(t)[1]
+    s = Internal.getNodeFromName1(zdA, 'ID_B')
+    rcv = Internal.getNodeFromName1(s, 'PointListDonor')[1]
+    dnr = Internal.getNodeFromName1(s, 'PointList')[1]
+    typ = Internal.getNodeFromName1(s, 'InterpolantsType')[1]
+    cf = Internal.getNodeFromName1(s, 'InterpolantsDonor')[1]
+    for varType, nv in ((2, 5), (21, 6)):
+        names = ['Density', 'VelocityX', 'VelocityY', 'VelocityZ', 'Temperature', 'MomentumX'][:nv]
+        # compact the receptor fields (FlowSolution#Centers of B) and the donor fields (FlowSolution of tc's A)
+        for z, cont, shp in ((zb, Internal.__FlowSolutionCenters__, (10, 10, 10)), (zdA, Internal.__FlowSolutionNodes__, (16, 16, 16))):
+            c = Internal.getNodeFromName1(z, cont)
+            block = np.empty(shp + (nv,), order='F')
+            for i, v in enumerate(names):
+                n = Internal.getNodeFromName1(c, v)
+                block[..., i] = n[1]
+                n[1] = block[..., i]
+        fD = [C.getFieldArray(zdA, v) for v in names]
+        fR = [np.array(C.getFieldArray(zb, 'centers:' + v), order='F', copy=True) for v in names]
+        O.transfer(fD, fR, 16, 16, rcv, dnr, typ, cf)
+        X._setInterpTransfers(t, tc, variables=['Density'], storage=1, compact=1, varType=varType)
+        for v, r in zip(names, fR):
+            assert np.array_equal(C.getFieldArray(zb, 'centers:' + v), r), v
+    # donor-side variant (setInterpTransfersD.cpp:282-296): same 6 compacted fields, dense (nvars, nrcv) array
+    infos = X._setInterpTransfersD(tc, variables=['Density'], compact=1, varType=21)
+    info = [i for i in infos if i[0] == 'B'][0]
+    refD = O.transferD(fD, 16, 16, dnr, typ, cf)
+    assert info[1][0] == 'Density' and np.array_equal(info[1][1], refD) and np.array_equal(info[2], rcv)
+    # non-compacted trees raise instead of reading out of bounds
+    t3, tc3, _ = _rotation_case(True)
+    with pytest.raises(ValueError):
+        X._setInterpTransfers(t3, tc3, variables=['Density'], storage=1, compact=1)

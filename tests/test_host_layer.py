@@ -105,8 +105,6 @@ def test_argument_errors_match_reference():
         X._setInterpDataChimera(t, tc, loc='centers', method='leastsquares', backend=OracleBackend())
     with pytest.raises(TypeError):
         X._setInterpDataChimera(t, tc, loc='centers', hook=[1, 2, 3], backend=OracleBackend())
-    with pytest.raises(NotImplementedError):
-        X._setInterpTransfers(t, tc, variables=['Density'], compact=1)
     # no cellN on the receptor tree -> nothing to do (OversetData.py:1184)
     t2 = C.newPyTree(['Base', G.cart((0, 0, 0), (1, 1, 1), (3, 3, 3))])
     assert X._setInterpDataChimera(t2, t2, loc='nodes', backend=OracleBackend()) is None
@@ -288,3 +286,35 @@ def test_donor_tree_round_trip_on_disk(tmp_path):
                     assert ca[1].dtype == cb[1].dtype and np.array_equal(ca[1], cb[1])
     with pytest.raises(NotImplementedError):
         C.convertPyTree2File(tc, str(tmp_path / "tc.cgns"))
+
+
+def test_rotation_and_compact_helpers():
+    """Host logic of the periodicity-by-rotation correction and of compact=1 (no compute)."""
+    t = _case(); tc = C.node2Center(t)
+    zr = Internal.getZones(t)[1]
+    s = ['ID_B', None, [], 'ZoneSubRegion_t']
+    assert X._rotationOf(s) == (0, 0.)
+    Internal.createChild(s, 'RotationAngle', 'DataArray_t', np.array([0., -0.25, 0.5]))
+    assert X._rotationOf(s) == (2, -0.25)          # first non-zero component (setInterpTransfers.cpp:281-285)
+    for v in ('VelocityX', 'VelocityY', 'VelocityZ'):
+        C._initVars(zr, 'centers:' + v, 1.)
+    names = C.getVarNames(zr, 'centers')
+    trip = X._rotationTriplets(zr, 'centers', len(names))
+    assert trip == [tuple(names.index('Velocity' + a) for a in 'XYZ')]
+    with pytest.raises(ValueError):
+        X._rotationTriplets(zr, 'centers', 2)      # the reference would index vectOfRcvFields out of bounds
+    # compact=1: fields must sit one behind the other in one block
+    block = np.arange(5 * 8, dtype=np.float64)
+    views = X._compactFields(block[:8], 5, 8, 'donor')
+    assert len(views) == 5 and all(v.size == 8 for v in views)
+    assert views[3][0] == 24. and views[3].__array_interface__['data'][0] == block.__array_interface__['data'][0] + 24 * 8
+    blockF = np.zeros((2, 2, 2, 6), order='F')
+    viewsF = X._compactFields(blockF[:, :, :, 0], 6, 8, 'receiver')
+    viewsF[5][:] = 7.
+    assert blockF[0, 0, 0, 5] == 7. and blockF[1, 1, 1, 5] == 7. and blockF[..., :5].max() == 0.
+    with pytest.raises(ValueError):
+        X._compactFields(np.zeros(8), 5, 8, 'donor')     # a stand-alone array is not a compacted block
+    with pytest.raises(ValueError):
+        X._compactFields(block[16:24], 5, 8, 'donor')    # not enough fields behind the first one
+    with pytest.raises(TypeError):
+        X._compactFields(None, 5, 8, 'donor')
