@@ -469,6 +469,188 @@ k_transfer2s(int m, int nvars, FieldPtrs P, int imd, int imdjmd, int nptsD, cons
   transfer_entry<2, MODE>(e, m, nvars, pd, pr, imd, imdjmd, donor, MODE == 0 ? rcv : pos, cfT, dense, ld);
 }
 
+// ---- persistent, software-pipelined type-2 kernel (donor-sorted groups; EXPERIMENTAL, CX_TRANSFER_PIPE=1) ----
+// Measured on C2a (17.0 M receptors, B200): 5 variables 0.62 ms (3 stages, 2-3 consumer groups) against 0.49 ms
+// for k_transfer2s; 7 variables 0.88 ms (only 2 stages fit) against 0.67 ms.  With the producer on a consumer
+// warp (first version) 0.83-0.95 ms: the issue of ~30 bulk copies per tile sat on every iteration's critical
+// path.  One CTA per SM keeps at most 2 tiles (120 KB) in flight, less than the 6 resident CTAs of the
+// per-tile kernel do with plain loads + 2 staged variables, so the per-tile kernel stays the default.
+// k_transfer2s hides the latency of a tile's plan data (indices, 8 coefficient slots) and of its first donor
+// rows only behind OTHER resident CTAs.  Here one CTA per SM walks over its tiles and a single elected thread
+// keeps the NEXT tiles in flight: everything a tile needs -- donor and receptor indices, the 8 coefficient
+// slots, and the four donor row segments of every variable -- arrives in shared memory through cp.async.bulk
+// copies that complete on the stage's mbarrier, one to two tiles ahead of the arithmetic (2-3 stages of
+// 2.1 + 16.5 + 8.3*nvars KB).  No register or scoreboard is tied up while the bytes are in flight, and the
+// consumers only ever wait on shared memory.  Source addresses are rounded down to 16 bytes (the element
+// shift is applied when reading).  Tiles whose donors span more than CX_SPAN nodes stage their plan data
+// only and gather the fields directly.  Arithmetic (operand order, no FMA) is unchanged.
+#define CX_PIPE_MAXV 8
+#define CX_PIPE_IDX 264                       // ints per staged index list (256 + shift + rounding)
+#define CX_PIPE_CF 258                        // doubles per staged coefficient slot
+#define CX_PIPE_ROW (CX_SPAN + 4)             // doubles per staged row segment
+struct PipeRange { int d_lo, d_hi; };         // donor range of a tile; d_lo < 0: rows not stageable
+
+__host__ __device__ inline size_t pipe_stage_bytes(int nvars)
+{
+  return 2 * sizeof(int) * CX_PIPE_IDX + 8 * sizeof(double) * CX_PIPE_CF + (size_t)nvars * 4 * sizeof(double) * CX_PIPE_ROW;
+}
+
+__global__ void k_pipe_ranges(int ntiles, int m, int imd, int imdjmd, int nptsD, const int* __restrict__ donor,
+                              PipeRange* __restrict__ out)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  const int t0 = t * 256, last = min(t0 + 256, m) - 1;
+  int d_lo = donor[t0], d_hi = donor[last];
+  const int span = d_hi - d_lo + 2;
+  // same conditions as transfer_tile2_staged: span fits, rounded segments stay inside the field
+  if (span + 2 > CX_SPAN || d_lo + imdjmd + imd + span + 2 > nptsD) d_lo = -1;
+  out[t].d_lo = d_lo; out[t].d_hi = d_hi;
+}
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+
+// blockDim.x = 256 * NG + 32: NG consumer groups of 256 threads (thread = entry of the tile, the variables are
+// dealt round-robin to the groups) and one producer warp that never computes, so that issuing the next tiles
+// is off the consumers' critical path.  full[st]: bulk copies landed (tx count); empty[st]: every consumer warp
+// is done with the stage.  No CTA-wide barrier inside the loop.
+template <int MODE>
+__global__ void __launch_bounds__(800, 1)
+k_transfer2p(int m, int nvars, FieldPtrs P, int imd, int imdjmd, const int* __restrict__ donor,
+             const int* __restrict__ idx, const double* __restrict__ cfT, const PipeRange* __restrict__ ranges,
+             int ntiles, int nst, double* __restrict__ dense, long long ld)
+{
+  extern __shared__ __align__(128) unsigned char psm[];
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(psm);         // [nst]
+  unsigned long long* empty = full + 4;                                           // [nst]
+  PipeRange* rng = reinterpret_cast<PipeRange*>(psm + 64);                        // [nst] range of the staged tile
+  const size_t stage_bytes = pipe_stage_bytes(nvars);
+  const int tid = threadIdx.x;
+  const int ncons = (int)blockDim.x - 32;            // consumer threads
+  const int off1 = imd, off2 = imdjmd, off3 = imdjmd + imd;
+  if (tid == 0)
+  {
+    for (int q = 0; q < nst; q++) { mbar_init(&full[q], 1); mbar_init(&empty[q], ncons >> 5); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (tid >= ncons)
+  {
+    // ---- producer warp (one lane issues) ----
+    if (tid == ncons)
+    {
+      int it = 0;
+      PipeRange Rn = ranges[blockIdx.x];             // range of the next tile to issue, fetched one tile ahead
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++)
+      {
+        const int st = it % nst;
+        const PipeRange R = Rn;
+        if (tile + (int)gridDim.x < ntiles) Rn = ranges[tile + gridDim.x];
+        if (it >= nst) mbar_wait(&empty[st], (unsigned)(((it / nst) - 1) & 1));
+        unsigned char* sp = psm + 128 + (size_t)st * stage_bytes;
+        int* dS = reinterpret_cast<int*>(sp);
+        int* iS = dS + CX_PIPE_IDX;
+        double* cS = reinterpret_cast<double*>(sp + 2 * sizeof(int) * CX_PIPE_IDX);
+        double* rS = cS + 8 * CX_PIPE_CF;
+        const int t0 = tile * 256, cnt = min(256, m - t0);
+        rng[st] = R;
+        const int sd = (int)((reinterpret_cast<uintptr_t>(donor + t0) >> 2) & 3), nd = (cnt + sd + 3) & ~3;
+        const int si = (int)((reinterpret_cast<uintptr_t>(idx + t0) >> 2) & 3), ni = (cnt + si + 3) & ~3;
+        unsigned bytes = 4u * (unsigned)(nd + ni);
+        for (int k = 0; k < 8; k++) bytes += 8u * (unsigned)((cnt + (int)(((size_t)k * m + t0) & 1) + 1) & ~1);
+        int len[4] = {0, 0, 0, 0}, g[4] = {0, 0, 0, 0};
+        if (R.d_lo >= 0)
+        {
+          const int span = R.d_hi - R.d_lo + 2;
+          g[0] = R.d_lo; g[1] = R.d_lo + off1; g[2] = R.d_lo + off2; g[3] = R.d_lo + off3;
+          for (int r = 0; r < 4; r++) { len[r] = (span + (g[r] & 1) + 1) & ~1; bytes += 8u * (unsigned)len[r] * (unsigned)nvars; }
+        }
+        mbar_expect_tx(&full[st], bytes);
+        bulk_g2s(dS, donor + t0 - sd, 4u * nd, &full[st]);
+        bulk_g2s(iS, idx + t0 - si, 4u * ni, &full[st]);
+        for (int k = 0; k < 8; k++)
+        {
+          const size_t o = (size_t)k * m + t0;
+          const int sk = (int)(o & 1);
+          bulk_g2s(cS + k * CX_PIPE_CF, cfT + (o - sk), 8u * (unsigned)((cnt + sk + 1) & ~1), &full[st]);
+        }
+        if (R.d_lo >= 0)
+          for (int v = 0; v < nvars; v++)
+            for (int r = 0; r < 4; r++)
+              bulk_g2s(rS + (size_t)(v * 4 + r) * CX_PIPE_ROW, P.d[v] + (g[r] & ~1), 8u * (unsigned)len[r], &full[st]);
+      }
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  const int el = tid & 255, vg = tid >> 8, nvg = ncons >> 8;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++)
+  {
+    const int st = it % nst;
+    mbar_wait(&full[st], (unsigned)((it / nst) & 1));
+    const int t0 = tile * 256, cnt = min(256, m - t0);
+    if (el < cnt && vg < nvars)
+    {
+      const unsigned char* sp = psm + 128 + (size_t)st * stage_bytes;
+      const int* dS = reinterpret_cast<const int*>(sp);
+      const int* iS = dS + CX_PIPE_IDX;
+      const double* cS = reinterpret_cast<const double*>(sp + 2 * sizeof(int) * CX_PIPE_IDX);
+      const double* rS = cS + 8 * CX_PIPE_CF;
+      const PipeRange R = rng[st];
+      const int sd = (int)((reinterpret_cast<uintptr_t>(donor + t0) >> 2) & 3);
+      const int si = (int)((reinterpret_cast<uintptr_t>(idx + t0) >> 2) & 3);
+      const int d0 = dS[el + sd];
+      const size_t o = (size_t)iS[el + si];
+      double c[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) c[k] = cS[k * CX_PIPE_CF + el + (int)(((size_t)k * m + t0) & 1)];
+      if (R.d_lo >= 0)
+      {
+        const int l = d0 - R.d_lo;
+        const int l0 = l + (R.d_lo & 1), l1 = l + ((R.d_lo + off1) & 1) + CX_PIPE_ROW;
+        const int l2 = l + ((R.d_lo + off2) & 1) + 2 * CX_PIPE_ROW, l3 = l + ((R.d_lo + off3) & 1) + 3 * CX_PIPE_ROW;
+        for (int v = vg; v < nvars; v += nvg)
+        {
+          const double* b = rS + (size_t)v * 4 * CX_PIPE_ROW;
+          double val = 0.;
+          val += c[0] * b[l0];
+          val += c[1] * b[l0 + 1];
+          val += c[2] * b[l1];
+          val += c[3] * b[l1 + 1];
+          val += c[4] * b[l2];
+          val += c[5] * b[l2 + 1];
+          val += c[6] * b[l3];
+          val += c[7] * b[l3 + 1];
+          if (MODE == 0) P.r[v][o] = val; else dense[(size_t)v * ld + o] = val;
+        }
+      }
+      else
+      {
+        for (int v = vg; v < nvars; v += nvg)
+        {
+          const double* f = P.d[v] + d0;
+          double val = 0.;
+          val += c[0] * __ldg(f);
+          val += c[1] * __ldg(f + 1);
+          val += c[2] * __ldg(f + off1);
+          val += c[3] * __ldg(f + off1 + 1);
+          val += c[4] * __ldg(f + off2);
+          val += c[5] * __ldg(f + off2 + 1);
+          val += c[6] * __ldg(f + off3);
+          val += c[7] * __ldg(f + off3 + 1);
+          if (MODE == 0) P.r[v][o] = val; else dense[(size_t)v * ld + o] = val;
+        }
+      }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty[st]);     // this warp no longer reads the stage
+  }
+}
+
 // types 3 / 5 with shared-memory staging (falls back to the direct gather tile by tile)
 template <int O, int MODE>
 __global__ void __launch_bounds__(256)
@@ -832,6 +1014,15 @@ static int build_sorted_group(cx_ctx* ctx, cx_plan* P, cx_plan::Group& G, int n,
                                                      P->d_rcv + first, P->d_pos + first, G.d_cf);
   ctx->launches += 3;
   cudaFreeAsync(k_in, s); cudaFreeAsync(k_out, s); cudaFreeAsync(v_in, s); cudaFreeAsync(v_out, s); cudaFreeAsync(tmp, s);
+  if (G.type == 2)
+  {
+    // per-tile donor ranges for the pipelined kernel (kept in d_tiles: layout 1 has no box table)
+    G.ntiles = cx_grid(G.n, 256);
+    CX_CUDA(cudaMalloc(&G.d_tiles, sizeof(PipeRange) * (size_t)G.ntiles));
+    k_pipe_ranges<<<cx_grid(G.ntiles, TB), TB, 0, s>>>(G.ntiles, G.n, P->imd, P->imd * P->jmd, P->nptsD, P->d_donor + first,
+                                                       (PipeRange*)G.d_tiles);
+    ctx->launches++;
+  }
   return 0;
 }
 
@@ -875,10 +1066,11 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
   CX_CHECK(cx_upload(ctx, r_ty, type, sizeof(int) * N));
   CX_CHECK(cx_upload(ctx, r_off, off.data(), sizeof(unsigned long long) * N));
   CX_CHECK(cx_upload(ctx, r_cf, coefs, sizeof(double) * (size_t)run));
-  CX_MALLOC(P->d_donor, sizeof(int) * N, s);
-  CX_MALLOC(P->d_rcv, sizeof(int) * N, s);
-  CX_MALLOC(P->d_pos, sizeof(int) * N, s);
-  CX_MALLOC(P->d_seq, sizeof(int) * N, s);
+  // + 64 bytes: the pipelined kernel's bulk copies round a tile's source range outwards to 16 bytes
+  CX_MALLOC(P->d_donor, sizeof(int) * N + 64, s);
+  CX_MALLOC(P->d_rcv, sizeof(int) * N + 64, s);
+  CX_MALLOC(P->d_pos, sizeof(int) * N + 64, s);
+  CX_MALLOC(P->d_seq, sizeof(int) * N + 64, s);
   k_iota<<<cx_grid(n, 256), 256, 0, s>>>(n, P->d_seq);
   const int TB = 256;
   int first = 0;
@@ -888,7 +1080,7 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
     cx_plan::Group G; G.type = types[g]; G.ncf = ncf_host(types[g]); G.sten = sten_host(types[g]);
     G.n = cnt[g]; G.first = first; G.d_cf = nullptr;
     G.layout = sorted ? 1 : 0; G.d_tiles = nullptr; G.ntiles = 0; G.ntx = G.nty = 0;
-    CX_MALLOC(G.d_cf, sizeof(double) * (size_t)G.ncf * G.n, s);
+    CX_MALLOC(G.d_cf, sizeof(double) * (size_t)G.ncf * G.n + 64, s);
     if (G.type == 2 && (mode_env == 2 || mode_env == 3) && kmd >= 2 && G.n >= 4096)
     {
       int rc = build_tiled_group(ctx, P, G, n, kmd, r_ty, r_dn, r_rc, r_off, r_cf, first, mode_env == 3);
@@ -923,6 +1115,27 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
   CX_CUDA(cudaStreamSynchronize(s));
   CX_CUDA(cudaGetLastError());
   cudaFreeAsync(r_dn, s); cudaFreeAsync(r_rc, s); cudaFreeAsync(r_ty, s); cudaFreeAsync(r_off, s); cudaFreeAsync(r_cf, s); cudaFreeAsync(d_cnt, s); cudaFreeAsync(d_scan, s);
+  return 0;
+}
+
+// CX_TRANSFER_PIPE=1 selects the persistent pipelined type-2 kernel (experimental: measured slower than the
+// per-tile kernel on C2a, 0.62 vs 0.49 ms for 5 variables; read at every launch so tests can switch it)
+static int cx_transfer_pipelined()
+{
+  const char* e = getenv("CX_TRANSFER_PIPE");
+  return (e && e[0] == '1') ? 1 : 0;
+}
+
+static int pipe_smem_optin()
+{
+  static int done = 0;
+  if (!done)
+  {
+    const int mx = 224 * 1024;
+    CX_CUDA(cudaFuncSetAttribute(k_transfer2p<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CX_CUDA(cudaFuncSetAttribute(k_transfer2p<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    done = 1;
+  }
   return 0;
 }
 
@@ -983,7 +1196,26 @@ int cx_plan_launch(cx_plan* P, int nvars, const double* const* dD, double* const
           else if (staged && G.layout == 1)
           {
             const int g2 = cx_grid(G.n, tb2s);
-            if (mode == 0) k_transfer2s<0><<<g2, tb2s, sizeof(StageSmem), s>>>(G.n, nv, F, imd, ij, P->nptsD, dn_, rc_, ps_, G.d_cf, dn, ld);
+            int nst = 0;
+            const char* mt = getenv("CX_PIPE_MIN_TILES");          // tests lower the threshold
+            const int min_tiles = mt ? atoi(mt) : 4 * ctx->sm_count;
+            if (cx_transfer_pipelined() && G.d_tiles && nv <= CX_PIPE_MAXV && G.ntiles >= min_tiles)
+            {
+              nst = (128 + 3 * pipe_stage_bytes(nv) <= 200 * 1024) ? 3 : (128 + 2 * pipe_stage_bytes(nv) <= 220 * 1024) ? 2 : 0;
+            }
+            if (nst)
+            {
+              const size_t smb = 128 + (size_t)nst * pipe_stage_bytes(nv);
+              CX_CHECK(pipe_smem_optin());
+              const int gp = std::min(G.ntiles, ctx->sm_count);
+              const PipeRange* rg = (const PipeRange*)G.d_tiles;
+              static int png = 0;    // CX_PIPE_GROUPS: consumer groups of 256 threads per CTA (1..3; + one producer warp)
+              if (!png) { const char* e = getenv("CX_PIPE_GROUPS"); png = e ? atoi(e) : 2; if (png < 1 || png > 3) png = 2; }
+              const int tbp = 256 * std::min(png, nv) + 32;
+              if (mode == 0) k_transfer2p<0><<<gp, tbp, smb, s>>>(G.n, nv, F, imd, ij, dn_, rc_, G.d_cf, rg, G.ntiles, nst, dn, ld);
+              else k_transfer2p<1><<<gp, tbp, smb, s>>>(G.n, nv, F, imd, ij, dn_, ps_, G.d_cf, rg, G.ntiles, nst, dn, ld);
+            }
+            else if (mode == 0) k_transfer2s<0><<<g2, tb2s, sizeof(StageSmem), s>>>(G.n, nv, F, imd, ij, P->nptsD, dn_, rc_, ps_, G.d_cf, dn, ld);
             else k_transfer2s<1><<<g2, tb2s, sizeof(StageSmem), s>>>(G.n, nv, F, imd, ij, P->nptsD, dn_, rc_, ps_, G.d_cf, dn, ld);
           }
           else { CX_LAUNCH(2) }

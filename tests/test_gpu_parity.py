@@ -601,3 +601,45 @@ def test_compact_fields_transfer(ctx):
     t3, tc3, _ = _rotation_case(True)
     with pytest.raises(ValueError):
         X._setInterpTransfers(t3, tc3, variables=['Density'], storage=1, compact=1)
+
+
+@pytest.mark.parametrize("dims,density", [((37, 23, 9), 4.0), ((64, 64, 6), 2.0), ((41, 29, 7), 0.02)])
+def test_transfer_pipelined_kernel(ctx, dims, density, monkeypatch):
+    """Persistent pipelined type-2 kernel (k_transfer2p, experimental) forced on small plans: odd row pitch, a type-1 group in
+    front of the type-2 group (index lists not 16-byte aligned), partial last tile, dense spans (rows staged) and
+    sparse spans (direct gather), 1..8 variables (9 falls back to the per-tile kernel).  Bit-exact vs the
+    reference loops, in place and dense."""
+    from cassiopee_b200 import _lib
+    from oracle import oracle as O
+    monkeypatch.setenv("CX_TRANSFER_PIPE", "1")
+    monkeypatch.setenv("CX_PIPE_MIN_TILES", "1")
+    ni, nj, nk = dims
+    rng = np.random.default_rng(ni * 100 + nk)
+    nD = ni * nj * nk
+    n = int(density * nD) + 3
+    nR = n + 11
+    typ = rng.choice(np.array([1, 2, 2, 2, 2, 2, 2, 2], np.int32), n).astype(np.int32)
+    typ[:5] = 1                                   # type-2 group starts at an odd offset
+    o = np.where(typ == 1, 1, 2)
+    i = (rng.random(n) * (ni - o + 1)).astype(np.int64); j = (rng.random(n) * (nj - o + 1)).astype(np.int64)
+    k = (rng.random(n) * (nk - o + 1)).astype(np.int64)
+    i[5:8] = ni - 2; j[5:8] = nj - 2; k[5:8] = nk - 2      # stencil ends on the last node of the zone
+    dnr = (i + ni * j + ni * nj * k).astype(np.int32)
+    rcv = rng.permutation(nR)[:n].astype(np.int32)
+    ncf = np.where(typ == 1, 1, 8)
+    cf = rng.standard_normal(int(ncf.sum()))
+    plan = _lib.Plan(ctx, ni, nj, nk, nR, dnr, rcv, typ, cf)
+    for nvars in (1, 5, 7, 8, 9):
+        fD = [rng.standard_normal(nD) for _ in range(nvars)]
+        fRo = [np.full(nR, -7.) for _ in range(nvars)]
+        O.transfer(fD, fRo, ni, nj, rcv, dnr, typ, cf)
+        dD = [_lib.DeviceArray.from_host(ctx, f) for f in fD]
+        dR = [_lib.DeviceArray.from_host(ctx, np.full(nR, -7.)) for _ in range(nvars)]
+        plan.transfer_dev([d.ptr for d in dD], [d.ptr for d in dR])
+        ctx.sync()
+        for d, b in zip(dR, fRo):
+            assert np.array_equal(d.download(), b)
+        dense = _lib.DeviceArray(ctx, n * nvars)
+        plan.transferD_dev([d.ptr for d in dD], dense.ptr, n)
+        ctx.sync()
+        assert np.array_equal(dense.download().reshape(nvars, n), O.transferD(fD, ni, nj, dnr, typ, cf))
