@@ -183,9 +183,10 @@ __device__ void lag_solve_group(const ZoneView& Z, int ics, int jcs, int kcs, do
   double* py = px + N;
   double* pz = py + N;
   double* sc = pz + N;            // 16: pts(3,4) + transformed receptor
+  constexpr int RED = WARP ? 0 : 64;         // cross-warp reduction scratch (none for one warp per system)
   volatile double* red_v = sc + 16;          // 2 x NT/32 partial maxima (double-buffered, up to 32 warps)
-  volatile int* red_i = (volatile int*)(red_v + 64);  // 2 x NT/32 indices
-  int* ipiv = (int*)(red_v + 64) + 64;       // N flags
+  volatile int* red_i = (volatile int*)(red_v + RED);  // 2 x NT/32 indices
+  int* ipiv = (int*)(red_v + RED) + RED;     // N flags
   int* ctl = ipiv + N + 3;                   // [0]=irow [1]=icol [2]=singular
 
   const int ni = Z.ni, ninj = Z.ni * Z.nj;
@@ -398,7 +399,8 @@ template <int N1> struct LagCfg {
   static constexpr int N = N1 * N1 * N1;
   static constexpr int LD = (N + 3) | 1;
   // doubles of shared memory per group
-  static constexpr int SMEM_D = N * LD + 3 * N + 16 + 64 + ((64 + N + 3 + 4) * 4 + 7) / 8;
+  static constexpr int RED = (N1 == 3) ? 0 : 64;      // order 3 runs one warp per system
+  static constexpr int SMEM_D = N * LD + 3 * N + 16 + RED + ((RED + N + 3 + 4) * 4 + 7) / 8;
 };
 
 // order 3: one warp per receptor, 4 receptors per CTA

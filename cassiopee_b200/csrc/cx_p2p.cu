@@ -52,6 +52,26 @@ __global__ void k_p2p_wait(int npeers, const int* my_flags, int iter)
   __threadfence_system();
 }
 
+// signal + wait in one launch (one launch less on the exchange's critical path): every peer's flag is raised
+// before any of ours is awaited, so two ranks that run this kernel at the same time cannot wait on each other
+__global__ void k_p2p_signal_wait(int npeers, int* const* __restrict__ peer_flags, const int* my_flags, int iter)
+{
+  int p = threadIdx.x;
+  if (p < npeers)
+  {
+    __threadfence_system();
+    *((volatile int*)peer_flags[p]) = iter;
+    const volatile int* f = my_flags + p;
+    const unsigned long long t0 = global_ns();
+    while (*f < iter)
+    {
+      __nanosleep(100);
+      if (global_ns() - t0 > CX_P2P_TIMEOUT_NS) __trap();
+    }
+  }
+  __threadfence_system();
+}
+
 typedef int (*cuMemGetAddressRange_t)(unsigned long long*, size_t*, unsigned long long);
 cuMemGetAddressRange_t g_range = nullptr;
 int load_range()
@@ -127,6 +147,12 @@ extern "C" int cx_p2p_signal_on(cudaStream_t s, int npeers, int* const* d_peer_f
 {
   if (npeers <= 0) return 0;
   k_p2p_signal<<<1, 32, 0, s>>>(npeers, d_peer_flags, iter);
+  return 0;
+}
+extern "C" int cx_p2p_signal_wait_on(cudaStream_t s, int npeers, int* const* d_peer_flags, const int* d_my_flags, int iter)
+{
+  if (npeers <= 0) return 0;
+  k_p2p_signal_wait<<<1, 32, 0, s>>>(npeers, d_peer_flags, d_my_flags, iter);
   return 0;
 }
 extern "C" int cx_p2p_wait_on(cudaStream_t s, int npeers, const int* d_my_flags, int iter)

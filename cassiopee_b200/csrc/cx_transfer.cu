@@ -179,9 +179,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
                "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+#ifndef CX_NBUF
+#define CX_NBUF 2                 // variables staged per CTA (one being read + CX_NBUF-1 in flight)
+#endif
 struct StageSmem {
-  double buf[2][4][CX_SPAN + 4];
-  unsigned long long bar[2];
+  double buf[CX_NBUF][4][CX_SPAN + 4];
+  unsigned long long bar[CX_NBUF];
 };
 
 // One tile (<= blockDim.x entries starting at t0, all of one plan/type-2 group) of the CTA.
@@ -206,11 +209,11 @@ __device__ __forceinline__ bool transfer_tile2_staged(StageSmem& S, int t0, int 
   if (span + 2 > CX_SPAN || d_lo + off3 - s3 + len3 > nptsD || d_lo + off2 - s2 + len2 > nptsD ||
       d_lo + off1 - s1 + len1 > nptsD || d_lo - s0 + len0 > nptsD)
     return false;
-  if (tid == 0) { mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1); mbar_fence_init(); }
+  if (tid == 0) { for (int q = 0; q < CX_NBUF; q++) mbar_init(&S.bar[q], 1); mbar_fence_init(); }
   __syncthreads();
   const unsigned bytes = 8u * (unsigned)(len0 + len1 + len2 + len3);
   auto issue = [&](int v) {
-    const int st = v & 1;
+    const int st = v % CX_NBUF;
     const double* f = pd[v];
     mbar_expect_tx(&S.bar[st], bytes);
     bulk_g2s(&S.buf[st][0][0], f + (d_lo - s0), 8u * len0, &S.bar[st]);
@@ -218,7 +221,7 @@ __device__ __forceinline__ bool transfer_tile2_staged(StageSmem& S, int t0, int 
     bulk_g2s(&S.buf[st][2][0], f + (d_lo + off2 - s2), 8u * len2, &S.bar[st]);
     bulk_g2s(&S.buf[st][3][0], f + (d_lo + off3 - s3), 8u * len3, &S.bar[st]);
   };
-  if (tid == 0) issue(0);
+  if (tid == 0) for (int q = 0; q < CX_NBUF - 1 && q < nvars; q++) issue(q);
   int l = 0; size_t o = 0;
   double c[8];
   const bool act = e < m;
@@ -230,11 +233,12 @@ __device__ __forceinline__ bool transfer_tile2_staged(StageSmem& S, int t0, int 
   }
   for (int v = 0; v < nvars; v++)
   {
-    if (tid == 0 && v + 1 < nvars) issue(v + 1);         // its buffer was released by the barrier ending iteration v-1
-    mbar_wait(&S.bar[v & 1], (unsigned)((v >> 1) & 1));
+    // variable v+NBUF-1 goes into the buffer released by the barrier that ended iteration v-1
+    if (tid == 0 && v + CX_NBUF - 1 < nvars) issue(v + CX_NBUF - 1);
+    mbar_wait(&S.bar[v % CX_NBUF], (unsigned)((v / CX_NBUF) & 1));
     if (act)
     {
-      const double(*b)[CX_SPAN + 4] = S.buf[v & 1];
+      const double(*b)[CX_SPAN + 4] = S.buf[v % CX_NBUF];
       double val = 0.;
       val += c[0] * b[0][l + s0];
       val += c[1] * b[0][l + s0 + 1];
@@ -1499,6 +1503,7 @@ extern int cx_exchange_on_stream(cx_ctx* ctx, cudaStream_t st, int npeers, const
 
 int cx_p2p_signal_on(cudaStream_t s, int npeers, int* const* d_peer_flags, int iter);
 int cx_p2p_wait_on(cudaStream_t s, int npeers, const int* d_my_flags, int iter);
+int cx_p2p_signal_wait_on(cudaStream_t s, int npeers, int* const* d_peer_flags, const int* d_my_flags, int iter);
 
 struct cx_step {
   cx_ctx* ctx; cx_planset* ps_remote; cx_planset* ps_local; cx_scatterset* ss;
@@ -1559,9 +1564,8 @@ static int step_run_p2p(cx_step* S, int niter, int overlap)
     if (S->ps_remote2[par]) CX_CHECK(planset_run_on(S->ps_remote2[par], comm ? cs : s));
     if (comm)
     {
-      CX_CHECK(cx_p2p_signal_on(cs, S->npeers_p2p, S->d_peer_flags, iter));
-      CX_CHECK(cx_p2p_wait_on(cs, S->npeers_p2p, S->d_my_flags, iter));
-      c->launches += 2;
+      CX_CHECK(cx_p2p_signal_wait_on(cs, S->npeers_p2p, S->d_peer_flags, S->d_my_flags, iter));
+      c->launches += 1;
       if (S->ss2[par]) CX_CHECK(scatterset_run_on(S->ss2[par], cs));
       if (overlap) CX_CUDA(cudaEventRecord(c->ev_join, cs));
     }
