@@ -29,6 +29,9 @@
 #ifndef CX_SET_MINB
 #define CX_SET_MINB 4            // resident CTAs per SM the plan-set kernels are compiled for
 #endif
+#ifndef CX_SET_VU
+#define CX_SET_VU 1              // variables gathered per pass by the plan-set kernels' direct-gather path
+#endif
 
 struct FieldPtrs { const double* d[CX_MAXVARS]; double* r[CX_MAXVARS]; };
 
@@ -152,7 +155,9 @@ __device__ __forceinline__ void transfer_entry(int e, int m, int nvars, const PD
 // span more than CX_SPAN nodes (row wraps at the edge of the overlap region, sparse fringes) take the
 // direct-gather path.  Arithmetic (operand order, no FMA) is the same on both paths.
 // Measured on C2a: tiles of 128 entries 0.576 ms, 256 entries 0.489 ms, 512 entries 0.511 ms; a span buffer of
-// 512 nodes (33 KB per CTA, L1 squeezed to 28 KB) 0.583 ms, 384 or 256 nodes 0.49 ms.
+// 512 nodes (33 KB per CTA, L1 squeezed to 28 KB) 0.583 ms, 384 or 256 nodes 0.49 ms; 3 variables staged per CTA
+// (CX_NBUF=3) 0.493 ms, 4: 0.60 ms; the same segments through 16-byte cp.async + commit groups (LSU path, two
+// barriers per variable) instead of cp.async.bulk: 0.528 ms.
 #define CX_SPAN 256
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -779,8 +784,8 @@ k_transfer_set(const SetDesc* __restrict__ descs, const BlkRec* __restrict__ blk
   }
   int e = (blockIdx.x - D.first_block) * blockDim.x + threadIdx.x;
   if (e >= D.m) return;
-  if (D.mode == 0) transfer_entry<TYPE, 0, PDk, PRk, 1>(e, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
-  else transfer_entry<TYPE, 1, PDk, PRk, 1>(e, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
+  if (D.mode == 0) transfer_entry<TYPE, 0, PDk, PRk, CX_SET_VU>(e, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
+  else transfer_entry<TYPE, 1, PDk, PRk, CX_SET_VU>(e, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
 }
 
 // donor index range of every block's tile (donor-sorted type-2 groups of a plan set), once at creation
