@@ -35,8 +35,8 @@ METRIC = "setInterpTransfers_algorithmic_GBps"
 UNIT = "GB/s"
 NVARS_C2 = 5
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_transfer2s<0> launch on C2a (5 vars), from the
-# `ncu --set full` capture summarised in profiles/r01_c_transfer_staged_summary.md (1.731608 GB + 654.801 MB)
-NCU_TRAFFIC_C2A_5VARS = 1731608000 + 654801152
+# `ncu --set full` capture summarised in profiles/r01_f_summary.md (1.690317 GB + 656.901 MB)
+NCU_TRAFFIC_C2A_5VARS = 1690317000 + 656901376
 
 
 def measured_peaks():
@@ -259,7 +259,7 @@ def run_c2(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": value, "peak": peak, "unit": "GB/s", "frac": value / peak,
                      "traffic": NCU_TRAFFIC_C2A_5VARS if (args.scale == 1.0 and nvars == 5) else None,
-                     "traffic_source": "profiles/r01_c_transfer_staged_summary.md (ncu --set full, one launch)",
+                     "traffic_source": "profiles/r01_f_summary.md (ncu --set full, one launch)",
                      "peak_source": how, "kernel": "k_transfer2s<0>",
                      "frac_of_nominal_8TBps": value / 8000.0},
         "cpu_baseline": cpu,

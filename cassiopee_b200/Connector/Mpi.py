@@ -109,6 +109,45 @@ def _addXZones(aD, meta, donorLists, comm):
     return added
 
 
+def _addXZonesDevice(aD, meta, donorLists, comm, ctx, interpDataType=1):
+    """Device form of _addXZones: the local donor zones go to the GPU once (coordinates + cellN + ADT = the hook),
+    and the zones other ranks need travel GPU to GPU over NCCL together with their ADT replica
+    (cx_zone_exchange), so nothing is staged through host memory and no tree is rebuilt on the receiver.
+    Returns (bare container zones of the replicated donors, {zone name: device hook})"""
+    byname = {m['name']: m for m in meta}
+    need = sorted({n for lst in donorLists.values() for n in lst if byname[n]['rank'] != comm.rank})
+    allneed = comm.allgather_obj(need)
+    localz = {z[0]: z for z in Internal.getZones(aD)}
+    wanted = {n for lst in donorLists.values() for n in lst if n in localz}
+    requested = {n for p, lst in enumerate(allneed) if p != comm.rank for n in lst if n in localz}
+    be = _lib.DeviceBackend(ctx)
+    hooks = {}
+    for n in sorted(wanted | requested):
+        z = localz[n]
+        _, ni, nj, nk, _ = Internal.getZoneDim(z)
+        x, y, zz = [a.reshape(-1, order='F') for a in C.getCoords(z)]
+        c = C.getFieldArray(z, 'cellN')
+        hooks[n] = be.make_zone(ni, nj, nk, x, y, zz, c.reshape(-1, order='F') if c is not None else None,
+                                interpDataType=interpDataType)
+    mine = {}
+    for n in requested:
+        mi, md = hooks[n].meta()
+        mine[n] = (mi.tolist(), md.tolist())
+    zmeta = {}
+    for part in comm.allgather_obj(mine):
+        zmeta.update(part)
+    sends = [(hooks[n], p) for p, lst in enumerate(allneed) if p != comm.rank for n in lst if n in localz]
+    recvs = [(byname[n]['rank'], numpy.asarray(zmeta[n][0], numpy.int32), numpy.asarray(zmeta[n][1], numpy.float64))
+             for n in need]
+    got = _lib.zone_exchange(ctx, sends, recvs)
+    added = []
+    for n, hz in zip(need, got):
+        ni, nj, nk = byname[n]['dims']
+        added.append(Internal.newZone(n, ni, nj, nk))
+        hooks[n] = hz
+    return added, hooks
+
+
 _FIELDS = (('PointList', numpy.int32), ('PointListDonor', numpy.int32), ('InterpolantsType', numpy.int32),
            ('InterpolantsDonor', numpy.float64), ('ExtrapPointList', numpy.int32), ('OrphanPointList', numpy.int32))
 
@@ -134,7 +173,14 @@ def _setInterpData(aR, aD, order=2, penalty=1, nature=0, extrap=1, method='lagra
     meta, donorLists = computeDonorGraph(aR, aD, comm, loc, sameName, zoneOrder)
     byname = {m['name']: m for m in meta}
     t1 = time.perf_counter()
-    added = _addXZones(aD, meta, donorLists, comm)
+    # CX_ZONE_REPL=host: replicate through host memory like the first version (A/B); default: GPU to GPU
+    devrepl = (backend is None and getattr(comm, 'device', False) and not isinstance(interpDataType, list)
+               and os.environ.get("CX_ZONE_REPL", "device") != "host")
+    hooks = None
+    if devrepl:
+        added, hooks = _addXZonesDevice(aD, meta, donorLists, comm, ctx or comm.ctx, interpDataType)
+    else:
+        added = _addXZones(aD, meta, donorLists, comm)
     t2 = time.perf_counter()
     # working donor list: local zones + replicated ones, in the global order
     zonesL = {z[0]: z for z in Internal.getZones(aD)}
@@ -146,10 +192,17 @@ def _setInterpData(aR, aD, order=2, penalty=1, nature=0, extrap=1, method='lagra
         if m['name'] in addedByName: work.append(addedByName[m['name']])
     order_pos = {m['name']: i for i, m in enumerate(meta)}
     work.sort(key=lambda z: order_pos[z[0]])
-    X._setInterpDataChimera(aR, work, order=order, penalty=penalty, nature=nature, extrap=extrap, method=method,
-                            loc=loc, storage='inverse', interpDataType=interpDataType, hook=None, verbose=verbose,
-                            sameName=sameName, dim=dim, itype='chimera', donorLists=donorLists, ctx=ctx,
-                            backend=backend)
+    if devrepl:
+        X._setInterpDataChimera(aR, work, order=order, penalty=penalty, nature=nature, extrap=extrap, method=method,
+                                loc=loc, storage='inverse', interpDataType=interpDataType,
+                                hook=[hooks.get(z[0]) for z in work], verbose=verbose, sameName=sameName, dim=dim,
+                                itype='chimera', donorLists=donorLists, ctx=ctx or comm.ctx, backend=backend,
+                                deviceOnly={z[0] for z in added}, refreshHooks=False)
+    else:
+        X._setInterpDataChimera(aR, work, order=order, penalty=penalty, nature=nature, extrap=extrap, method=method,
+                                loc=loc, storage='inverse', interpDataType=interpDataType, hook=None, verbose=verbose,
+                                sameName=sameName, dim=dim, itype='chimera', donorLists=donorLists, ctx=ctx,
+                                backend=backend)
     t3 = time.perf_counter()
     # route the subregions created under replicated zones to their owners
     outMeta = {}

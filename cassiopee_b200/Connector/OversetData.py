@@ -347,10 +347,15 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
                           method='lagrangian', loc='nodes', storage='direct',
                           interpDataType=1, hook=None, verbose=2,
                           topTreeRcv=None, topTreeDnr=None, sameName=1, dim=3, itype='both', dictOfModels=None,
-                          donorLists=None, ctx=None, backend=None):
+                          donorLists=None, ctx=None, backend=None, deviceOnly=None, refreshHooks=True):
     """donorLists (extension, optional): dict receptorZoneName -> list of donor
     zone names to consider, in that order — what Connector/Mpi.py:950-983 does
-    with bbox-intersecting donors; None = all donors like the sequential API."""
+    with bbox-intersecting donors; None = all donors like the sequential API.
+    deviceOnly (extension, used by Connector.Mpi): names of donor zones that exist only as device hooks
+    (replicated from another rank's GPU): their tree node is a bare container for the ID_* subregions.
+    refreshHooks=False: the hooks were built from the current cellN, no need to upload it again; entries of
+    `hook` may then be None (built here on first use)."""
+    deviceOnly = deviceOnly or ()
     locR = loc
     if loc == 'nodes': cellNPresent = C.isNamePresent(aR, 'cellN')
     elif loc == 'centers': cellNPresent = C.isNamePresent(aR, 'centers:cellN')
@@ -370,8 +375,11 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
 
     dictIsCellNPresent = {}
     for zd in Internal.getZones(aD):
+        if zd[0] in deviceOnly:
+            dictIsCellNPresent[zd[0]] = 1
+            continue
         dictIsCellNPresent[zd[0]] = C.isNamePresent(zd, 'cellN')
-    _addCellN__(aD, loc='nodes')
+        _addCellN__(zd, loc='nodes')
 
     zonesRcv = Internal.getZones(aR)
     zonesDnrL = Internal.getZones(aD)
@@ -386,6 +394,8 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
             raise TypeError("setInterpData: size of list of hooks must be equal to the number of donor zones.")
         allHooksL = hook[:]
         for h, zd in zip(allHooksL, zonesDnrL):   # cellN may have changed since the hook was built
+            if not refreshHooks or h is None or zd[0] in deviceOnly:
+                continue
             c = C.getFieldArray(zd, 'cellN')
             backend.set_celln(h, c.reshape(-1, order='F') if c is not None else None)
     else:

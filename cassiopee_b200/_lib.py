@@ -95,6 +95,8 @@ _SIGS = {
     "cx_comm_barrier": (_i, [_vp]),
     "cx_exchange_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "cx_exchange_bytes_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "cx_zone_meta": (_i, [_vp, _vp, _vp]),
+    "cx_zone_exchange": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
 }
 
 EXPORTED_SYMBOLS = sorted(_SIGS.keys())
@@ -282,6 +284,23 @@ class Zone:
         self.h = h
         self._fin = weakref.finalize(self, lib().cx_zone_destroy, h)
 
+    @classmethod
+    def _from_handle(cls, ctx, h, dims, topo):
+        """Wrap a zone handle created by the library (cx_zone_exchange)."""
+        z = cls.__new__(cls)
+        z.ctx = ctx
+        z.ni, z.nj, z.nk = [int(d) for d in dims]
+        z.interpDataType = 1 if topo == 1 else 0
+        z.h = h
+        z._fin = weakref.finalize(z, lib().cx_zone_destroy, h)
+        return z
+
+    def meta(self):
+        """(ints[6], doubles[9]) a peer needs to adopt this zone's device data (cx_zone_meta)."""
+        mi = np.zeros(6, np.int32); md = np.zeros(9)
+        check(lib().cx_zone_meta(self.h, ptr(mi), ptr(md)))
+        return mi, md
+
     def set_celln(self, cellN):
         c = f64(cellN) if cellN is not None else None
         check(lib().cx_zone_set_celln(self.h, ptr(c)))
@@ -305,6 +324,24 @@ class Zone:
         out = np.zeros(nc, dtype=dt)
         check(lib().cx_zone_export_adt(self.h, ptr(out), out.nbytes))
         return out
+
+
+def zone_exchange(ctx, sends, recvs):
+    """Device-to-device replication of donor zones over NCCL (cx_zone_exchange).
+    sends: list of (Zone, peer); recvs: list of (peer, meta_i, meta_d) with the owner's Zone.meta().
+    Returns the received Zone objects in the order of recvs."""
+    ns, nr = len(sends), len(recvs)
+    sz = (ctypes.c_void_p * max(ns, 1))(*[z.h.value for z, _ in sends])
+    sp = (ctypes.c_int * max(ns, 1))(*[int(p) for _, p in sends])
+    rp = (ctypes.c_int * max(nr, 1))(*[int(p) for p, _, _ in recvs])
+    mi = np.ascontiguousarray(np.concatenate([np.asarray(m, np.int32) for _, m, _ in recvs]) if nr else np.zeros(6, np.int32))
+    md = np.ascontiguousarray(np.concatenate([np.asarray(m, np.float64) for _, _, m in recvs]) if nr else np.zeros(9))
+    out = (ctypes.c_void_p * max(nr, 1))()
+    check(lib().cx_zone_exchange(ctx.h, ns, sz, sp, nr, rp, ptr(mi), ptr(md), out))
+    zones = []
+    for i, (p, m_i, m_d) in enumerate(recvs):
+        zones.append(Zone._from_handle(ctx, _vp(out[i]), m_i[:3], int(m_i[5])))
+    return zones
 
 
 class InterpResult:

@@ -138,4 +138,69 @@ int cx_exchange_bytes_dev(cx_ctx* ctx, int npeers, const int* peers, const void*
   return 0;
 }
 
+// ---- device-to-device replication of donor zones ------------------------------------------------------------
+// The device form of Cmpi._addXZones(aD, graph, variables=['cellN']) (Converter/Converter/Mpi.py, called by
+// Connector/Connector/Mpi.py:941): a rank that needs a remote donor zone receives the owner's resident block
+// (x, y, z, cellN) AND its ADT replica over NCCL/NVLink, so the zone is ready to be queried without a host
+// round trip and without rebuilding the tree.  meta_i[6*i] = ni, nj, nk, depth, levels, topo; meta_d[9*i] =
+// bbox[6], h[3] (from cx_zone_meta on the owner, exchanged by the caller).  Between one pair of ranks the
+// zones must be listed in the same order on both sides.
+int cx_zone_meta(cx_zone* z, int* meta_i, double* meta_d)
+{
+  meta_i[0] = z->ni; meta_i[1] = z->nj; meta_i[2] = z->nk; meta_i[3] = z->depth; meta_i[4] = z->levels; meta_i[5] = z->topo;
+  for (int i = 0; i < 6; i++) meta_d[i] = z->bbox[i];
+  for (int i = 0; i < 3; i++) meta_d[6 + i] = z->h[i];
+  return 0;
+}
+
+int cx_zone_exchange(cx_ctx* ctx, int nsend, cx_zone* const* send_zones, const int* send_peers, int nrecv,
+                     const int* recv_peers, const int* meta_i, const double* meta_d, cx_zone** out)
+{
+  cx_comm* c = (cx_comm*)ctx->nccl;
+  if (!c) { cx_set_error("communicator not initialised"); return -5; }
+  CX_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  for (int i = 0; i < nrecv; i++) out[i] = nullptr;
+  for (int i = 0; i < nrecv; i++)
+  {
+    cx_zone* zn = new cx_zone;
+    memset(zn, 0, sizeof(*zn));
+    const int* mi = meta_i + 6 * i; const double* md = meta_d + 9 * i;
+    zn->ctx = ctx; zn->ni = mi[0]; zn->nj = mi[1]; zn->nk = mi[2]; zn->depth = mi[3]; zn->levels = mi[4]; zn->topo = mi[5];
+    zn->npts = zn->ni * zn->nj * zn->nk;
+    zn->ncells = (zn->ni - 1) * (zn->nj - 1) * (zn->nk > 1 ? zn->nk - 1 : 1);
+    for (int q = 0; q < 6; q++) zn->bbox[q] = md[q];
+    for (int q = 0; q < 3; q++) zn->h[q] = md[6 + q];
+    out[i] = zn;
+    cudaError_t e = cudaMalloc(&zn->d_x, 4 * sizeof(double) * (size_t)zn->npts);
+    if (e == cudaSuccess && zn->topo == 1) e = cudaMalloc(&zn->d_nodes, sizeof(cx::AdtNode) * (size_t)zn->ncells);
+    if (e != cudaSuccess)
+    {
+      cx_set_error("cx_zone_exchange: %s", cudaGetErrorString(e));
+      for (int q = 0; q <= i; q++) { cudaFree(out[q]->d_x); cudaFree(out[q]->d_nodes); delete out[q]; out[q] = nullptr; }
+      return -2;
+    }
+    zn->d_y = zn->d_x + zn->npts; zn->d_z = zn->d_y + zn->npts; zn->d_cellN = zn->d_z + zn->npts;
+  }
+  CX_NCCL(g_nccl.GroupStart());
+  for (int i = 0; i < nsend; i++)
+  {
+    cx_zone* z = send_zones[i];
+    CX_NCCL(g_nccl.Send(z->d_x, 4 * (size_t)z->npts, ncclFloat64, send_peers[i], c->comm, st));
+    if (z->topo == 1)
+      CX_NCCL(g_nccl.Send(z->d_nodes, sizeof(cx::AdtNode) * (size_t)z->ncells, 0 /*ncclInt8*/, send_peers[i], c->comm, st));
+  }
+  for (int i = 0; i < nrecv; i++)
+  {
+    cx_zone* z = out[i];
+    CX_NCCL(g_nccl.Recv(z->d_x, 4 * (size_t)z->npts, ncclFloat64, recv_peers[i], c->comm, st));
+    if (z->topo == 1)
+      CX_NCCL(g_nccl.Recv(z->d_nodes, sizeof(cx::AdtNode) * (size_t)z->ncells, 0 /*ncclInt8*/, recv_peers[i], c->comm, st));
+  }
+  CX_NCCL(g_nccl.GroupEnd());
+  CX_CUDA(cudaStreamSynchronize(st));
+  CX_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // extern "C"

@@ -219,6 +219,15 @@ int cx_exchange_dev(cx_ctx* ctx, int npeers, const int* peers, const double* con
 /* same for raw bytes (one-off shipping of donor coordinates and index lists) */
 int cx_exchange_bytes_dev(cx_ctx* ctx, int npeers, const int* peers, const void* const* d_send,
                           const long long* sendbytes, void* const* d_recv, const long long* recvbytes);
+/* Device-to-device replication of donor zones, the device form of Cmpi._addXZones(aD, graph, variables=['cellN'])
+ * (Converter/Converter/Mpi.py; called by Connector/Connector/Mpi.py:941 before the local setInterpData calls):
+ * the resident (x, y, z, cellN) block and the ADT replica of each listed zone travel over NCCL; the receiver gets
+ * ready-to-query zone handles (no host round trip, no tree rebuild).  cx_zone_meta exports what the receiver
+ * needs beside the bulk data (meta_i[6]: ni, nj, nk, depth, levels, topo; meta_d[9]: bbox[6], h[3]); the caller
+ * exchanges it.  Between one pair of ranks both sides must list the zones in the same order. */
+int cx_zone_meta(cx_zone* zone, int* meta_i, double* meta_d);
+int cx_zone_exchange(cx_ctx* ctx, int nsend, cx_zone* const* send_zones, const int* send_peers, int nrecv,
+                     const int* recv_peers, const int* meta_i, const double* meta_d, cx_zone** out);
 
 #ifdef __cplusplus
 }
