@@ -182,25 +182,31 @@ int cx_zone_exchange(cx_ctx* ctx, int nsend, cx_zone* const* send_zones, const i
     }
     zn->d_y = zn->d_x + zn->npts; zn->d_z = zn->d_y + zn->npts; zn->d_cellN = zn->d_z + zn->npts;
   }
-  CX_NCCL(g_nccl.GroupStart());
-  for (int i = 0; i < nsend; i++)
-  {
-    cx_zone* z = send_zones[i];
-    CX_NCCL(g_nccl.Send(z->d_x, 4 * (size_t)z->npts, ncclFloat64, send_peers[i], c->comm, st));
-    if (z->topo == 1)
-      CX_NCCL(g_nccl.Send(z->d_nodes, sizeof(cx::AdtNode) * (size_t)z->ncells, 0 /*ncclInt8*/, send_peers[i], c->comm, st));
-  }
-  for (int i = 0; i < nrecv; i++)
-  {
-    cx_zone* z = out[i];
-    CX_NCCL(g_nccl.Recv(z->d_x, 4 * (size_t)z->npts, ncclFloat64, recv_peers[i], c->comm, st));
-    if (z->topo == 1)
-      CX_NCCL(g_nccl.Recv(z->d_nodes, sizeof(cx::AdtNode) * (size_t)z->ncells, 0 /*ncclInt8*/, recv_peers[i], c->comm, st));
-  }
-  CX_NCCL(g_nccl.GroupEnd());
-  CX_CUDA(cudaStreamSynchronize(st));
-  CX_CUDA(cudaGetLastError());
-  return 0;
+  auto transfer = [&]() -> int {
+    CX_NCCL(g_nccl.GroupStart());
+    for (int i = 0; i < nsend; i++)
+    {
+      cx_zone* z = send_zones[i];
+      CX_NCCL(g_nccl.Send(z->d_x, 4 * (size_t)z->npts, ncclFloat64, send_peers[i], c->comm, st));
+      if (z->topo == 1)
+        CX_NCCL(g_nccl.Send(z->d_nodes, sizeof(cx::AdtNode) * (size_t)z->ncells, 0 /*ncclInt8*/, send_peers[i], c->comm, st));
+    }
+    for (int i = 0; i < nrecv; i++)
+    {
+      cx_zone* z = out[i];
+      CX_NCCL(g_nccl.Recv(z->d_x, 4 * (size_t)z->npts, ncclFloat64, recv_peers[i], c->comm, st));
+      if (z->topo == 1)
+        CX_NCCL(g_nccl.Recv(z->d_nodes, sizeof(cx::AdtNode) * (size_t)z->ncells, 0 /*ncclInt8*/, recv_peers[i], c->comm, st));
+    }
+    CX_NCCL(g_nccl.GroupEnd());
+    CX_CUDA(cudaStreamSynchronize(st));
+    CX_CUDA(cudaGetLastError());
+    return 0;
+  };
+  const int rc = transfer();
+  if (rc != 0)       // the caller never sees half-filled zones
+    for (int q = 0; q < nrecv; q++) { cudaFree(out[q]->d_x); cudaFree(out[q]->d_nodes); delete out[q]; out[q] = nullptr; }
+  return rc;
 }
 
 }  // extern "C"
