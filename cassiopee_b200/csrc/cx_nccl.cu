@@ -172,8 +172,10 @@ int cx_zone_exchange(cx_ctx* ctx, int nsend, cx_zone* const* send_zones, const i
     for (int q = 0; q < 6; q++) zn->bbox[q] = md[q];
     for (int q = 0; q < 3; q++) zn->h[q] = md[6 + q];
     out[i] = zn;
-    cudaError_t e = cudaMalloc(&zn->d_x, 4 * sizeof(double) * (size_t)zn->npts);
-    if (e == cudaSuccess && zn->topo == 1) e = cudaMalloc(&zn->d_nodes, sizeof(cx::AdtNode) * (size_t)zn->ncells);
+    // stream-ordered pool: the blocks of the previous call's replicas are reused instead of going back to the driver
+    cudaError_t e = cx_malloc_async((void**)&zn->d_x, 4 * sizeof(double) * (size_t)zn->npts, st);
+    if (e == cudaSuccess && zn->topo == 1)
+      e = cx_malloc_async((void**)&zn->d_nodes, sizeof(cx::AdtNode) * (size_t)zn->ncells, st);
     if (e != cudaSuccess)
     {
       cx_set_error("cx_zone_exchange: %s", cudaGetErrorString(e));
