@@ -643,3 +643,59 @@ def test_transfer_pipelined_kernel(ctx, dims, density, monkeypatch):
         plan.transferD_dev([d.ptr for d in dD], dense.ptr, n)
         ctx.sync()
         assert np.array_equal(dense.download().reshape(nvars, n), O.transferD(fD, ni, nj, dnr, typ, cf))
+
+
+@pytest.mark.parametrize("order", [2, 3, 5])
+@pytest.mark.parametrize("loc,storage", [('nodes', 'direct'), ('centers', 'direct'), ('centers', 'inverse'), ('nodes', 'inverse')])
+def test_reference_script_setInterpTransfersPT_t1_t2(ctx, order, loc, storage):
+    """The reference's own known-answer scripts Connector/test/setInterpTransfersPT_t1.py / _t2.py through the
+    PyTree API: an 11^3 Cartesian donor with F = x + 2y + 3z at its nodes, an identical grid as receptor (all of
+    its nodes / centres have cellN = 2), orders 2, 3 and 5, direct and inverse storage; every interpolated value
+    reproduces the linear field, and lists / values equal the oracle's (= the reference's K_INTERP + transfer loop)."""
+    import cassiopee_b200.Generator as G
+    import cassiopee_b200.Converter as C
+    import cassiopee_b200.Internal as Internal
+    import cassiopee_b200.Connector.PyTree as X
+    from oracle import oracle as O
+    ni = nj = nk = 11
+    h = 10. / (ni - 1)
+    F = lambda x, y, z: x + 2. * y + 3. * z
+    m = G.cart((0, 0, 0), (h, h, 1), (ni, nj, nk), name='donor')
+    a = G.cart((0, 0, 0), (h, h, 1), (ni, nj, nk), name='extraction')
+    tD = C.newPyTree(['Dnr', m]); tR = C.newPyTree(['Rcv', a])
+    C._initVars(tD, 'F', F)
+    fld = 'F' if loc == 'nodes' else 'centers:F'
+    C._initVars(tR, 'cellN' if loc == 'nodes' else 'centers:cellN', 2.)
+    res = X.setInterpData(tR, tD, order=order, loc=loc, storage=storage, verbose=0)
+    if storage == 'direct': tR = res
+    else: tD = res
+    C._initVars(tR, fld, 0.)
+    tR2 = X.setInterpTransfers(tR, tD, variables=['F'])
+    zr = Internal.getZones(tR2)[0]; zd = Internal.getZones(tD)[0]
+    got = C.getFieldArray(zr, fld).reshape(-1, order='F')
+    # receptor points as the reference takes them (nodes, or node2Center of the receptor zone)
+    xr, yr, zrr = C.getCoords(Internal.getZones(tR)[0])
+    if loc == 'centers':
+        xr, yr, zrr = [C.node2CenterArray(v) for v in (xr, yr, zrr)]
+    pts = [np.ascontiguousarray(v.reshape(-1, order='F')) for v in (xr, yr, zrr)]
+    xd, yd, zdd = [v.reshape(-1, order='F') for v in C.getCoords(zd)]
+    # the tree layer hands the donor over with cellN = 1 added (OversetData.py:1189-1193)
+    ref = O.set_interp_data(pts[0], pts[1], pts[2], [O.RefZone(ni, nj, nk, xd, yd, zdd, np.ones(xd.size))],
+                            order=order, nature=0, penalty=1, extrap=1)
+    holder = Internal.getZones(tR)[0] if storage == 'direct' else zd
+    s = Internal.getNodeFromName1(holder, 'ID_donor' if storage == 'direct' else 'ID_extraction')
+    assert s is not None
+    pl = Internal.getNodeFromName1(s, 'PointList')[1]; pld = Internal.getNodeFromName1(s, 'PointListDonor')[1]
+    rcv, dnr = (pl, pld) if storage == 'direct' else (pld, pl)
+    assert np.array_equal(rcv, ref[0][0]) and np.array_equal(dnr, ref[1][0])
+    assert np.array_equal(Internal.getNodeFromName1(s, 'InterpolantsType')[1], ref[2][0])
+    assert np.array_equal(Internal.getNodeFromName1(s, 'InterpolantsDonor')[1], ref[3][0])
+    assert rcv.size > 0.9 * got.size
+    fD = [np.ascontiguousarray(C.getFieldArray(zd, 'F').reshape(-1, order='F'))]
+    fR = [np.zeros(got.size)]
+    O.transfer(fD, fR, ni, nj, ref[0][0], ref[1][0], ref[2][0], ref[3][0])
+    assert np.array_equal(got, fR[0])
+    exact = F(*pts)
+    # orders 2 and 3 reproduce the linear field to rounding; the reference's order-5 weights carry its 12-digit
+    # literals (inv24 = 0.041666666667, Interp2.cpp:640-658): its own error on this case is 1.4e-9
+    assert np.abs(got - exact)[rcv].max() < (1e-11 if order < 5 else 1e-8)

@@ -318,3 +318,40 @@ def test_rotation_and_compact_helpers():
         X._compactFields(block[16:24], 5, 8, 'donor')    # not enough fields behind the first one
     with pytest.raises(TypeError):
         X._compactFields(None, 5, 8, 'donor')
+
+
+@pytest.mark.parametrize("loc,storage", [('nodes', 'direct'), ('centers', 'inverse')])
+@pytest.mark.parametrize("order", [2, 3, 5])
+def test_reference_script_storage_layouts(loc, storage, order):
+    """Host half of Connector/test/setInterpTransfersPT_t1.py / _t2.py (identical 11^3 Cartesian grids): where the
+    ID_* subregion lands, its role, and that its lists are the oracle's for the receptor points the tree layer
+    extracts (nodes, or node2Center of the receptor zone)."""
+    from oracle import oracle as O
+    ni = nj = nk = 11
+    m = G.cart((0, 0, 0), (1, 1, 1), (ni, nj, nk), name='donor')
+    a = G.cart((0, 0, 0), (1, 1, 1), (ni, nj, nk), name='extraction')
+    tD = C.newPyTree(['Dnr', m]); tR = C.newPyTree(['Rcv', a])
+    C._initVars(tR, 'cellN' if loc == 'nodes' else 'centers:cellN', 2.)
+    X._setInterpDataChimera(tR, tD, order=order, loc=loc, storage=storage, verbose=0, backend=OracleBackend())
+    zr = Internal.getZones(tR)[0]; zd = Internal.getZones(tD)[0]
+    holder, other, sname, role = (zr, zd, 'ID_donor', 'Receiver') if storage == 'direct' else (zd, zr, 'ID_extraction', 'Donor')
+    s = Internal.getNodeFromName1(holder, sname)
+    assert s is not None and not Internal.getNodesFromType1(other, 'ZoneSubRegion_t')
+    assert Internal.getValue(Internal.getNodeFromName1(s, 'ZoneRole')) == role
+    assert (Internal.getNodeFromName1(s, 'GridLocation') is not None) == (loc == 'centers')
+    xr, yr, zz = C.getCoords(zr)
+    if loc == 'centers':
+        xr, yr, zz = [C.node2CenterArray(v) for v in (xr, yr, zz)]
+    pts = [np.ascontiguousarray(v.reshape(-1, order='F')) for v in (xr, yr, zz)]
+    xd, yd, zdd = [v.reshape(-1, order='F') for v in C.getCoords(zd)]
+    ref = O.set_interp_data(pts[0], pts[1], pts[2], [O.RefZone(ni, nj, nk, xd, yd, zdd, np.ones(xd.size))],
+                            order=order, nature=0, penalty=1, extrap=1)
+    pl = Internal.getNodeFromName1(s, 'PointList')[1]; pld = Internal.getNodeFromName1(s, 'PointListDonor')[1]
+    rcv, dnr = (pl, pld) if storage == 'direct' else (pld, pl)
+    assert np.array_equal(rcv, ref[0][0]) and np.array_equal(dnr, ref[1][0])
+    assert np.array_equal(Internal.getNodeFromName1(s, 'InterpolantsType')[1], ref[2][0])
+    assert np.array_equal(Internal.getNodeFromName1(s, 'InterpolantsDonor')[1], ref[3][0])
+    assert rcv.size == pts[0].size and ref[5].size == 0
+    # coincident nodes collapse to type 1 for every order; cell centres keep the order's own type
+    assert set(np.unique(ref[2][0])) == ({1} if loc == 'nodes' else {order})
+    assert C.isNamePresent(zd, 'cellN') == -1          # the cellN added for the call is removed again
