@@ -141,6 +141,8 @@ def node2CenterArray(a):
     node2Center.cpp:118-146, summation order ind0..ind7."""
     a = numpy.asarray(a)
     ni, nj, nk = a.shape
+    if nj == 1 and nk == 1:
+        return numpy.asfortranarray(0.5 * (a[:-1] + a[1:]))      # curve along i (node2Center.cpp:80-95)
     if nk == 1:
         s = a[:-1, :-1, :] + a[1:, :-1, :]
         s = s + a[:-1, 1:, :]
@@ -169,6 +171,8 @@ def node2CenterSelected(a, sel):
     j = (sel - k * nic * njc) // nic
     i = sel - j * nic - k * nic * njc
     n0 = i + ni * j + ni * nj * k
+    if nj == 1 and nk == 1:
+        return 0.5 * (f[sel] + f[sel + 1])
     if nk == 1:
         s = f[n0] + f[n0 + 1]
         s = s + f[n0 + ni]

@@ -412,7 +412,7 @@ class Receptors:
         self.ctx = ctx
         x, y, z, cellN = f64(x), f64(y), f64(z), f64(cellN)
         nn = int(ni) * int(nj) * int(nk)
-        npts = nn if loc == 'nodes' else (int(ni) - 1) * (int(nj) - 1) * max(int(nk) - 1, 1)
+        npts = nn if loc == 'nodes' else max(int(ni) - 1, 1) * max(int(nj) - 1, 1) * max(int(nk) - 1, 1)
         if x.size != nn or y.size != nn or z.size != nn or cellN.size != npts:
             raise TypeError("getInterpolatedPoints: coordinates / cellN do not match the zone dimensions.")
         h = _vp()

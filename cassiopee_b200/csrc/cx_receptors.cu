@@ -39,11 +39,17 @@ __global__ void k_rcv_gather(int n, int loc, int ni, int nj, int nk, const unsig
   const size_t o = (size_t)pos[c];
   ind[o] = c;
   if (loc == 0) { xo[o] = x[c]; yo[o] = y[c]; zo[o] = z[c]; return; }
+  const double* a[3] = {x, y, z};
+  double* b[3] = {xo, yo, zo};
+  if (nj == 1)
+  {
+    // curve along i (node2Center.cpp:80-95): 0.5*(n0+n1)
+    for (int q = 0; q < 3; q++) b[q][o] = 0.5 * (a[q][c] + a[q][c + 1]);
+    return;
+  }
   const int nic = ni - 1, njc = nj - 1, nij = ni * nj;
   const int k = c / (nic * njc), j = (c - k * nic * njc) / nic, i = c - j * nic - k * nic * njc;
   const int n0 = i + j * ni + k * nij;
-  const double* a[3] = {x, y, z};
-  double* b[3] = {xo, yo, zo};
   if (nk == 1)
   {
     // 2-D zone (node2Center.cpp:98-117): 0.25*(n0+n1+n2+n3)
@@ -78,11 +84,17 @@ int cx_receptors_create(cx_ctx* c, int ni, int nj, int nk, const double* x, cons
                         const double* cellN, int loc, cx_receptors** out)
 {
   if (loc != 0 && loc != 1) { cx_set_error("setInterpData: invalid loc."); return -1; }
-  if (ni < 2 || nj < 2 || nk < 1) { cx_set_error("receptor zones must be 3D, or 2D with nk=1"); return -4; }
+  if (ni < 1 || nj < 1 || nk < 1) { cx_set_error("getInterpolatedPoints: invalid zone dimensions"); return -1; }
+  // loc 'nodes': any structured layout is just a list of points (curves and point clouds like the circle of
+  // Connector/test/setInterpDataPT_t1.py included); loc 'centers': 3-D zones, 2-D zones with nk = 1 and curves
+  // along i (node2Center.cpp:42-72 also knows the j / k curves and the ni = 1 / nj = 1 surfaces)
+  const bool curve = ni >= 2 && nj == 1 && nk == 1;
+  if (loc == 1 && !curve && (ni < 2 || nj < 2))
+  { cx_set_error("receptor zones at centers must be 3D, 2D with nk=1, or curves along i"); return -4; }
   CX_CUDA(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   const size_t nn = (size_t)ni * nj * nk;
-  const size_t np = loc == 0 ? nn : (size_t)(ni - 1) * (nj - 1) * (size_t)(nk > 1 ? nk - 1 : 1);
+  const size_t np = loc == 0 ? nn : curve ? (size_t)(ni - 1) : (size_t)(ni - 1) * (nj - 1) * (size_t)(nk > 1 ? nk - 1 : 1);
   if (nn > 2000000000ull) { cx_set_error("receptor zone too large for int32 indices"); return -1; }
   cx_receptors* R = new cx_receptors;
   R->ctx = c; R->n = 0; R->npts = (int)np; R->d_ind = nullptr; R->d_x = R->d_y = R->d_z = nullptr;

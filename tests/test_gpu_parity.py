@@ -699,3 +699,14 @@ def test_reference_script_setInterpTransfersPT_t1_t2(ctx, order, loc, storage):
     # orders 2 and 3 reproduce the linear field to rounding; the reference's order-5 weights carry its 12-digit
     # literals (inv24 = 0.041666666667, Interp2.cpp:640-658): its own error on this case is 1.4e-9
     assert np.abs(got - exact)[rcv].max() < (1e-11 if order < 5 else 1e-8)
+
+
+@pytest.mark.parametrize("loc", ['nodes', 'centers'])
+@pytest.mark.parametrize("order", [2, 3, 5])
+def test_reference_script_setInterpDataPT_t1_curve_receptors(ctx, loc, order):
+    """Connector/test/setInterpDataPT_t1.py on the device: circle (curve zone) receptors at nodes and at centres,
+    both storages, penalty and nature sweeps, orders 2 / 3 / 5; lists identical to the oracle's."""
+    for storage in ('direct', 'inverse'):
+        for pen in (0, 1):
+            for nat in (0, 1):
+                cases.check_curve_receptors(dict(ctx=ctx), order, loc, storage, pen, nat)

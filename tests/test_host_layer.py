@@ -355,3 +355,15 @@ def test_reference_script_storage_layouts(loc, storage, order):
     # coincident nodes collapse to type 1 for every order; cell centres keep the order's own type
     assert set(np.unique(ref[2][0])) == ({1} if loc == 'nodes' else {order})
     assert C.isNamePresent(zd, 'cellN') == -1          # the cellN added for the call is removed again
+
+
+@pytest.mark.parametrize("loc", ['nodes', 'centers'])
+@pytest.mark.parametrize("order", [2, 3, 5])
+def test_reference_script_setInterpDataPT_t1_curve_receptors(loc, order):
+    """Connector/test/setInterpDataPT_t1.py: a circle (structured curve, 20 points) as receptor zone, nodes and
+    centres (19 segment mid-points, node2Center.cpp:80-95), both storages, penalty and nature sweeps."""
+    from tests import cases
+    for storage in ('direct', 'inverse'):
+        for pen in (0, 1):
+            for nat in (0, 1):
+                cases.check_curve_receptors(dict(backend=OracleBackend()), order, loc, storage, pen, nat)
