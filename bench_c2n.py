@@ -75,7 +75,7 @@ def run_c2n(args):
         strip_interp_data(t)
         barrier()
         t0 = time.perf_counter()
-        Xmpi._setInterpData(t, t, order=2, nature=1, penalty=1, extrap=1, loc='nodes', storage='inverse',
+        Xmpi._setInterpData(t, t, order=2, nature=1, penalty=1, extrap=1, loc='nodes', storage='inverse', sameBase=1,
                             comm=comm, zoneOrder=zoneOrder, ctx=ctx, verbose=0)
         barrier()
         sid_calls.append(time.perf_counter() - t0)

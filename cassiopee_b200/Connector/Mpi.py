@@ -54,17 +54,27 @@ def _makeZone(name, ni, nj, nk, x, y, z, cellN):
     return zn
 
 
-def computeDonorGraph(aR, aD, comm, loc='nodes', sameName=1, zoneOrder=None):
+def _baseNames(t):
+    """zone name -> name of its CGNSBase_t (None for zones outside a base), Connector/Mpi.py:925-928"""
+    out = {}
+    for b in Internal.getBases(t):
+        for z in Internal.getZones(b): out[z[0]] = b[0]
+    return out
+
+
+def computeDonorGraph(aR, aD, comm, loc='nodes', sameName=1, zoneOrder=None, sameBase=1):
     """Global donor metadata and, per local receptor zone, the ordered list of
     bbox-intersecting donor zones (what Connector/Mpi.py:950-983 builds with
     getIntersectingDomains + hooks).  Order = zoneOrder (names) if given, else
-    (rank, position) order, so results do not depend on who computes."""
+    (rank, position) order, so results do not depend on who computes.
+    sameBase=0: only donors of ANOTHER base are kept (Connector/Mpi.py:930-937)."""
     local = []
     boxes = {}          # zone object -> bbox (a tree that is both receptor and donor is reduced once)
+    basesD = _baseNames(aD); basesR = _baseNames(aR)
     for z in Internal.getZones(aD):
         _, ni, nj, nk, _ = Internal.getZoneDim(z)
         boxes[id(z)] = _zoneBBox(z)
-        local.append(dict(name=z[0], dims=(ni, nj, nk), bbox=boxes[id(z)], rank=comm.rank))
+        local.append(dict(name=z[0], dims=(ni, nj, nk), bbox=boxes[id(z)], rank=comm.rank, base=basesD.get(z[0])))
     allmeta = comm.allgather_obj(local)
     meta = [m for part in allmeta for m in part]
     if zoneOrder is not None:
@@ -73,8 +83,10 @@ def computeDonorGraph(aR, aD, comm, loc='nodes', sameName=1, zoneOrder=None):
     donorLists = {}
     for z in Internal.getZones(aR):
         bb = boxes[id(z)] if id(z) in boxes else _receptorBBox(z, loc)
+        baseR = basesR.get(z[0], basesD.get(z[0]))
         donorLists[z[0]] = [m['name'] for m in meta
-                            if not (sameName == 1 and m['name'] == z[0]) and bbox_intersect(bb, m['bbox'])]
+                            if not (sameName == 1 and m['name'] == z[0]) and bbox_intersect(bb, m['bbox'])
+                            and not (sameBase == 0 and m.get('base') == baseR)]
     return meta, donorLists
 
 
@@ -162,24 +174,34 @@ _FIELDS = (('PointList', numpy.int32), ('PointListDonor', numpy.int32), ('Interp
 
 
 def _setInterpData(aR, aD, order=2, penalty=1, nature=0, extrap=1, method='lagrangian', loc='nodes',
-                   storage='inverse', interpDataType=1, hook=None, verbose=0, sameName=1, dim=3, itype='chimera',
+                   storage='inverse', interpDataType=1, hook=None, cartesian=False, sameBase=0,
+                   topTreeRcv=None, topTreeDnr=None, sameName=1, verbose=0, dim=3, itype='chimera',
                    comm=None, zoneOrder=None, backend=None, ctx=None):
     """Distributed setInterpData, storage='inverse': on return every local donor
     zone of aD carries the ID_<receptor> subregions of all receptor zones
-    (local or remote) it feeds.  aR / aD hold the zones owned by this rank."""
+    (local or remote) it feeds.  aR / aD hold the zones owned by this rank.
+    sameBase=0 (the reference's default, Connector/Mpi.py:858-862, :930-937): a zone is only interpolated from
+    zones of OTHER bases; sameBase=1: from every intersecting zone.  cartesian=True (donors of a 'CARTESIAN'
+    base located in closed form) is not distributed here: pass interpDataType=0."""
+    if cartesian:
+        raise NotImplementedError("Mpi._setInterpData: cartesian=True is not distributed; use interpDataType=0.")
     if storage != 'inverse':
         raise NotImplementedError("Mpi._setInterpData: only storage='inverse' is distributed.")
     if comm is None or comm.size == 1:
-        return X._setInterpDataChimera(aR, aD, order=order, penalty=penalty, nature=nature, extrap=extrap,
+        donorLists = computeDonorGraph(aR, aD, _Single(), loc, sameName, zoneOrder, sameBase)[1]
+        # receptor zones without any candidate donor are skipped, like `if dnrZones != []` (Connector/Mpi.py:975)
+        rcvs = [z for z in Internal.getZones(aR) if donorLists.get(z[0])]
+        if not rcvs:
+            return None
+        return X._setInterpDataChimera(rcvs, aD, order=order, penalty=penalty, nature=nature, extrap=extrap,
                                        method=method, loc=loc, storage=storage, interpDataType=interpDataType,
                                        hook=hook, verbose=verbose, sameName=sameName, dim=dim, itype=itype,
-                                       ctx=ctx, backend=backend,
-                                       donorLists=computeDonorGraph(aR, aD, _Single(), loc, sameName, zoneOrder)[1])
+                                       ctx=ctx, backend=backend, donorLists=donorLists)
     prof = os.environ.get("CX_PROFILE") and comm.rank == 0
     t0 = time.perf_counter()
     hadCellN = {z[0]: C.isNamePresent(z, 'cellN') for z in Internal.getZones(aD)}
     X._addCellN__(aD, loc='nodes')
-    meta, donorLists = computeDonorGraph(aR, aD, comm, loc, sameName, zoneOrder)
+    meta, donorLists = computeDonorGraph(aR, aD, comm, loc, sameName, zoneOrder, sameBase)
     byname = {m['name']: m for m in meta}
     t1 = time.perf_counter()
     # CX_ZONE_REPL=host: replicate through host memory like the first version (A/B); default: GPU to GPU
@@ -201,14 +223,17 @@ def _setInterpData(aR, aD, order=2, penalty=1, nature=0, extrap=1, method='lagra
         if m['name'] in addedByName: work.append(addedByName[m['name']])
     order_pos = {m['name']: i for i, m in enumerate(meta)}
     work.sort(key=lambda z: order_pos[z[0]])
-    if devrepl:
-        X._setInterpDataChimera(aR, work, order=order, penalty=penalty, nature=nature, extrap=extrap, method=method,
+    rcvs = [z for z in Internal.getZones(aR) if donorLists.get(z[0])]
+    if not rcvs:
+        pass                       # nothing to interpolate here; the routing collectives below still run
+    elif devrepl:
+        X._setInterpDataChimera(rcvs, work, order=order, penalty=penalty, nature=nature, extrap=extrap, method=method,
                                 loc=loc, storage='inverse', interpDataType=interpDataType,
                                 hook=[hooks.get(z[0]) for z in work], verbose=verbose, sameName=sameName, dim=dim,
                                 itype='chimera', donorLists=donorLists, ctx=ctx or comm.ctx, backend=backend,
                                 deviceOnly={z[0] for z in added}, refreshHooks=False)
     else:
-        X._setInterpDataChimera(aR, work, order=order, penalty=penalty, nature=nature, extrap=extrap, method=method,
+        X._setInterpDataChimera(rcvs, work, order=order, penalty=penalty, nature=nature, extrap=extrap, method=method,
                                 loc=loc, storage='inverse', interpDataType=interpDataType, hook=None, verbose=verbose,
                                 sameName=sameName, dim=dim, itype='chimera', donorLists=donorLists, ctx=ctx,
                                 backend=backend)
@@ -271,16 +296,40 @@ def _rcvFieldName(v, loc):
     return ('centers:' + v) if loc == 'centers' else v
 
 
-def _setInterpTransfers(aR, aD, variables=[], cellNVariable='', storage=1, comm=None, backend=None, ctx=None):
-    """Distributed setInterpTransfers on host trees (reference semantics,
+def setInterpTransfers(aR, aD, variables=[], cellNVariable='',
+                       variablesIBC=['Density', 'MomentumX', 'MomentumY', 'MomentumZ', 'EnergyStagnationDensity'],
+                       bcType=0, varType=1, graph=None, procDict=None, type='ALLD',
+                       Gamma=1.4, Cv=1.7857142857142865, MuS=1.e-08, Cs=0.3831337844872463, Ts=1.0, alpha=1.,
+                       comm=None, backend=None, ctx=None):
+    """Copy variant (Connector/Mpi.py:383-394): the receptor tree is copied by reference, the fields are updated."""
+    tp = Internal.copyRef(aR)
+    _setInterpTransfers(tp, aD, variables=variables, cellNVariable=cellNVariable, variablesIBC=variablesIBC,
+                        bcType=bcType, varType=varType, compact=0, graph=graph, procDict=procDict, type=type,
+                        Gamma=Gamma, Cv=Cv, MuS=MuS, Cs=Cs, Ts=Ts, alpha=alpha, comm=comm, backend=backend, ctx=ctx)
+    return tp
+
+
+def _setInterpTransfers(aR, aD, variables=[], cellNVariable='',
+                        variablesIBC=['Density', 'MomentumX', 'MomentumY', 'MomentumZ', 'EnergyStagnationDensity'],
+                        bcType=0, varType=1, compact=0, graph=None, procDict=None, type='ALLD',
+                        Gamma=1.4, Cv=1.7857142857142865, MuS=1.e-08, Cs=0.3831337844872463, Ts=1.0, alpha=1.,
+                        storage=1, comm=None, backend=None, ctx=None):
+    """Distributed setInterpTransfers on host trees (reference signature and semantics,
     Connector/Mpi.py:396-440): donor-side dense transfer per ID_* subregion,
-    in-place scatter for local receptor zones, send + scatter for remote ones."""
-    infos = X._setInterpTransfersD(aD, variables=variables, cellNVariable=cellNVariable, ctx=ctx, backend=backend)
+    in-place scatter for local receptor zones, send + scatter for remote ones.
+    procDict (zone name -> rank) is used when given, else the owners are gathered; `graph` is not needed (the
+    exchange is sized from the subregions); the IBC arguments only concern IBCD_* subregions, which are not on
+    the device path."""
+    infos = X._setInterpTransfersD(aD, variables=variables, cellNVariable=cellNVariable, varType=varType,
+                                   compact=compact, ctx=ctx, backend=backend)
     zr = {z[0]: z for z in Internal.getZones(aR)}
     owners = {}
     if comm is not None and comm.size > 1:
-        for p, names in enumerate(comm.allgather_obj(sorted(zr.keys()))):
-            for n in names: owners[n] = p
+        if procDict is not None:
+            owners = {n: int(p) for n, p in procDict.items() if n not in zr}
+        else:
+            for p, names in enumerate(comm.allgather_obj(sorted(zr.keys()))):
+                for n in names: owners[n] = p
     outMeta, outData = {}, {}
     for rcvName, arr, ListRcv, loc in infos:
         names = arr[0].split(',') if arr[0] else []

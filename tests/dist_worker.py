@@ -102,7 +102,7 @@ def main():
     zoneOrder = [z[0] for z in Internal.getZones(t)]
     tl = subtree_of(t, rank)
     tcl = tl if case == 'c2n' else C.node2Center(tl)
-    Xmpi._setInterpData(tl, tcl, order=order, nature=1, penalty=1, extrap=1, loc=loc, storage='inverse',
+    Xmpi._setInterpData(tl, tcl, order=order, nature=1, penalty=1, extrap=1, loc=loc, storage='inverse', sameBase=1,
                         comm=comm, zoneOrder=zoneOrder, backend=backend, ctx=ctx)
     if mode == 'nccl':
         sess = Xmpi.TransferSession(tl, tcl, VARS, comm=comm, ctx=ctx)
@@ -121,7 +121,7 @@ def main():
         # single-process run of the same backend on the whole tree
         t1 = make()
         tc1 = t1 if case == 'c2n' else C.node2Center(t1)
-        Xmpi._setInterpData(t1, tc1, order=order, nature=1, penalty=1, extrap=1, loc=loc, storage='inverse',
+        Xmpi._setInterpData(t1, tc1, order=order, nature=1, penalty=1, extrap=1, loc=loc, storage='inverse', sameBase=1,
                             comm=None, zoneOrder=zoneOrder, backend=backend, ctx=ctx)
         if mode == 'nccl':
             s1 = Xmpi.TransferSession(t1, tc1, VARS, comm=None, ctx=ctx)

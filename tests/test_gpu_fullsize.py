@@ -104,7 +104,7 @@ def test_c4_cluster_fullsize_properties(ctx):
     tc = C.node2Center(t)
     for z in Internal.getZones(tc):         # node2Center shares the centre arrays: give the donor tree its own F
         C._initVars(z, 'F', np.array(C.getFieldArray(z, 'F'), order='F', copy=True))
-    Xmpi._setInterpData(t, tc, order=2, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse', comm=None,
+    Xmpi._setInterpData(t, tc, order=2, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse', sameBase=1, comm=None,
                         zoneOrder=[b['name'] for b in blocks], ctx=ctx, verbose=0)
     nrcv = 0
     orphans = {}

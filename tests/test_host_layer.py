@@ -367,3 +367,23 @@ def test_reference_script_setInterpDataPT_t1_curve_receptors(loc, order):
         for pen in (0, 1):
             for nat in (0, 1):
                 cases.check_curve_receptors(dict(backend=OracleBackend()), order, loc, storage, pen, nat)
+
+
+def test_distributed_entry_same_base_semantics():
+    """Connector.Mpi._setInterpData keeps the reference's sameBase rule (Connector/Mpi.py:858-862, :930-937):
+    with the default sameBase=0 a zone is interpolated only from zones of another base."""
+    import cassiopee_b200.Connector.Mpi as Xmpi
+    def trees(two_bases):
+        t = _case()
+        if two_bases:
+            za, zb = Internal.getZones(t)
+            t = C.newPyTree(['BaseA', za, 'BaseB', zb])
+        return t, C.node2Center(t)
+    for two_bases, sameBase, expect in ((False, 0, False), (False, 1, True), (True, 0, True), (True, 1, True)):
+        t, tc = trees(two_bases)
+        Xmpi._setInterpData(t, tc, order=2, nature=1, loc='centers', storage='inverse', sameBase=sameBase,
+                            comm=None, backend=OracleBackend())
+        zdA = [z for z in Internal.getZones(tc) if z[0] == 'A'][0]
+        assert (Internal.getNodeFromName1(zdA, 'ID_B') is not None) == expect, (two_bases, sameBase)
+    with pytest.raises(NotImplementedError):
+        Xmpi._setInterpData(t, tc, loc='centers', storage='inverse', cartesian=True, comm=None, backend=OracleBackend())
