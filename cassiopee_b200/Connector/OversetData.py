@@ -483,6 +483,12 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
             indcells = sel.astype(Internal.E_NpyInt)
             if nborphan > 0:
                 resInterp[5] = indcells[resInterp[5]]
+                if verbose == 3:     # force cellN#Orphan = -1 at the orphan points (OversetData.py:1287-1294)
+                    pre = 'centers:' if locR == 'centers' else ''
+                    if Internal.getNodeFromName2(z, 'cellN#Orphan') is None:
+                        C._initVars(z, pre + 'cellN#Orphan', numpy.array(cellN, dtype=numpy.float64, order='F', copy=True))
+                    co = C.getFieldArray(z, pre + 'cellN#Orphan')
+                    co.reshape(-1, order='F')[resInterp[5]] = -1.
             for noz in range(nzonesDnr):
                 if resInterp[0][noz].size > 0:
                     resInterp[0][noz] = indcells[resInterp[0][noz]]

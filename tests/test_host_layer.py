@@ -93,6 +93,15 @@ def test_direct_storage_and_orphans():
     assert orph.size > 0 and np.array_equal(orph, np.unique(orph))
     rcv = Internal.getNodeFromName1(s, 'PointList')[1]
     assert np.intersect1d(rcv, orph).size == 0 and rcv.size + orph.size == 12 ** 3
+    # verbose=3 also marks the orphans with -1 in a copy of cellN (OversetData.py:1287-1294)
+    tR3 = Internal.copyRef(t); tD3 = Internal.copyRef(tc)
+    C._initVars(tR3, 'centers:cellN', 2.); C._initVars(tD3, 'cellN', 1.)
+    X._setInterpDataChimera(tR3, tD3, order=2, nature=1, extrap=0, loc='centers', storage='direct', verbose=3,
+                            backend=OracleBackend())
+    zA3 = Internal.getZones(tR3)[0]
+    co = C.getFieldArray(zA3, 'centers:cellN#Orphan').reshape(-1, order='F')
+    assert np.array_equal(np.nonzero(co == -1.)[0], orph) and np.all(co[rcv] == 2.)
+    assert np.all(C.getFieldArray(zA3, 'centers:cellN') == 2.)        # cellN itself is untouched
 
 
 def test_argument_errors_match_reference():
