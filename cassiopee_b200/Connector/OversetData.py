@@ -494,6 +494,11 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
                     resInterp[0][noz] = indcells[resInterp[0][noz]]
                 if resInterp[4][noz].size > 0:
                     resInterp[4][noz] = indcells[resInterp[4][noz]]
+                    if verbose == 3:     # force cellN#Orphan = -2 at the extrapolated points (OversetData.py:1313-1319)
+                        pre = 'centers:' if locR == 'centers' else ''
+                        if Internal.getNodeFromName2(z, 'cellN#Orphan') is None:
+                            C._initVars(z, pre + 'cellN#Orphan', numpy.array(cellN, dtype=numpy.float64, order='F', copy=True))
+                        C.getFieldArray(z, pre + 'cellN#Orphan').reshape(-1, order='F')[resInterp[4][noz]] = -2.
 
             # Etape 3: storage in the tree
             for noz in range(nzonesDnr):

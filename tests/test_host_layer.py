@@ -102,6 +102,18 @@ def test_direct_storage_and_orphans():
     co = C.getFieldArray(zA3, 'centers:cellN#Orphan').reshape(-1, order='F')
     assert np.array_equal(np.nonzero(co == -1.)[0], orph) and np.all(co[rcv] == 2.)
     assert np.all(C.getFieldArray(zA3, 'centers:cellN') == 2.)        # cellN itself is untouched
+    # ... and the extrapolated points with -2 (OversetData.py:1313-1319)
+    tR4 = Internal.copyRef(t); tD4 = Internal.copyRef(tc)
+    C._initVars(tR4, 'centers:cellN', 2.); C._initVars(tD4, 'cellN', 1.)
+    X._setInterpDataChimera(tR4, tD4, order=2, nature=1, extrap=1, loc='centers', storage='direct', verbose=3,
+                            backend=OracleBackend())
+    zA4 = Internal.getZones(tR4)[0]
+    s4 = Internal.getNodeFromName1(zA4, 'ID_B')
+    ext = Internal.getNodeFromName1(s4, 'ExtrapPointList')[1]
+    co4 = C.getFieldArray(zA4, 'centers:cellN#Orphan').reshape(-1, order='F')
+    assert ext.size > 0 and np.array_equal(np.nonzero(co4 == -2.)[0], np.sort(ext))
+    o4 = Internal.getNodeFromName1(s4, 'OrphanPointList')
+    if o4 is not None: assert np.array_equal(np.nonzero(co4 == -1.)[0], o4[1])
 
 
 def test_argument_errors_match_reference():
