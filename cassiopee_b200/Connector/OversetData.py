@@ -101,6 +101,8 @@ def _createInterpRegion__(z, zname, pointlist, pointlistdonor, interpCoef, inter
         nameSubRegion = {'chimera': 'ID_', 'abutting': 'ID_', 'ibc': 'IBCD_', 'ibc2': '2_IBCD_'}[itype] + zname
     else:
         nameSubRegion = prefix + zname
+    if RotationAngle is not None: RotationAngle[2] = []     # remove the DimensionalUnits child node
+    extC = None if pointlistdonorExtC is None else ('PointListDonorExtC' if tag == 'Receiver' else 'PointListExtC')
     zsr = Internal.getNodesFromName1(z, nameSubRegion)
     if zsr == []:
         info = Internal.createChild(z, nameSubRegion, 'ZoneSubRegion_t', value=zname)
@@ -109,6 +111,7 @@ def _createInterpRegion__(z, zname, pointlist, pointlistdonor, interpCoef, inter
             Internal._createChild(info, 'GridLocation', 'GridLocation_t', value='CellCenter')
         info[2].append(['PointList', pointlist, [], 'IndexArray_t'])
         info[2].append(['PointListDonor', pointlistdonor, [], 'IndexArray_t'])
+        if extC is not None: info[2].append([extC, pointlistdonorExtC, [], 'IndexArray_t'])
         info[2].append(['InterpolantsDonor', interpCoef, [], 'DataArray_t'])
         if interpVol.size > 0:
             info[2].append(['InterpolantsVol', interpVol, [], 'DataArray_t'])
@@ -127,18 +130,26 @@ def _createInterpRegion__(z, zname, pointlist, pointlistdonor, interpCoef, inter
                 Internal._createChild(s, 'GridLocation', 'GridLocation_t', value='CellCenter')
             s[2].append(['PointList', pointlist, [], 'IndexArray_t'])
             s[2].append(['PointListDonor', pointlistdonor, [], 'IndexArray_t'])
+            if extC is not None: s[2].append([extC, pointlistdonorExtC, [], 'IndexArray_t'])
             s[2].append(['InterpolantsDonor', interpCoef, [], 'DataArray_t'])
             if interpVol.size > 0: s[2].append(['InterpolantsVol', interpVol, [], 'DataArray_t'])
             s[2].append(['InterpolantsType', interpType, [], 'DataArray_t'])
             if indicesOrphan.size > 0:
                 s[2].append(['OrphanPointList', numpy.unique(indicesOrphan), [], 'DataArray_t'])
             if indicesExtrap.size > 0: s[2].append(['ExtrapPointList', indicesExtrap, [], 'DataArray_t'])
+            if RotationAngle is not None: s[2].append(RotationAngle)
+            if RotationCenter is not None: s[2].append(RotationCenter)
         else:
             intd[0][1] = numpy.concatenate((intd[0][1], interpCoef))
+            intv = Internal.getNodesFromName1(s, 'InterpolantsVol')
+            if intv != [] and interpVol.size > 0: intv[0][1] = numpy.concatenate((intv[0][1], interpVol))
             for name, arr in (('InterpolantsType', interpType), ('PointList', pointlist),
                               ('PointListDonor', pointlistdonor)):
                 node = Internal.getNodesFromName1(s, name)
                 if node != []: node[0][1] = numpy.concatenate((node[0][1], arr))
+            for name in ('PointListExtC', 'PointListDonorExtC'):
+                node = Internal.getNodesFromName1(s, name)
+                if node != []: node[0][1] = numpy.concatenate((node[0][1], pointlistdonorExtC))
             node = Internal.getNodesFromName1(s, 'OrphanPointList')
             if node != []: node[0][1] = numpy.unique(indicesOrphan)
             node = Internal.getNodesFromName1(s, 'ExtrapPointList')

@@ -408,3 +408,42 @@ def test_distributed_entry_same_base_semantics():
         assert (Internal.getNodeFromName1(zdA, 'ID_B') is not None) == expect, (two_bases, sameBase)
     with pytest.raises(NotImplementedError):
         Xmpi._setInterpData(t, tc, loc='centers', storage='inverse', cartesian=True, comm=None, backend=OracleBackend())
+
+
+def test_create_interp_region_node_order_and_concatenation():
+    """_createInterpRegion__ (OversetData.py:1752-1884): child names and order, the ExtC / volume / rotation
+    children, and the concatenation rule when the subregion already exists."""
+    z = Internal.newZone('D', 3, 3, 3)
+    i32 = lambda *v: np.array(v, dtype=np.int32)
+    rot = ['RotationAngle', np.array([0., 0., 30.]), [['DimensionalUnits', None, [], 'DimensionalUnits_t']], 'DataArray_t']
+    ctr = ['RotationCenter', np.zeros(3), [], 'DataArray_t']
+    X._createInterpRegion__(z, 'R', i32(5, 6), i32(0, 1), np.arange(16.), i32(2, 2), np.array([.1, .2]), i32(1),
+                            i32(7, 7, 3), pointlistdonorExtC=i32(9, 9), tag='Donor', loc='centers',
+                            RotationAngle=rot, RotationCenter=ctr)
+    s = Internal.getNodeFromName1(z, 'ID_R')
+    assert Internal.getValue(s) == 'R'
+    assert [c[0] for c in s[2]] == ['ZoneRole', 'GridLocation', 'PointList', 'PointListDonor', 'PointListExtC',
+                                    'InterpolantsDonor', 'InterpolantsVol', 'InterpolantsType', 'OrphanPointList',
+                                    'ExtrapPointList', 'RotationAngle', 'RotationCenter']
+    assert Internal.getNodeFromName1(s, 'RotationAngle')[2] == []            # DimensionalUnits child removed
+    assert np.array_equal(Internal.getNodeFromName1(s, 'OrphanPointList')[1], [3, 7])
+    X._createInterpRegion__(z, 'R', i32(8), i32(2), np.arange(8.) + 100, i32(2), np.array([.3]), i32(2), i32(4),
+                            pointlistdonorExtC=i32(10), tag='Donor', loc='centers')
+    assert len(Internal.getNodesFromName1(z, 'ID_R')) == 1
+    assert np.array_equal(Internal.getNodeFromName1(s, 'PointList')[1], [5, 6, 8])
+    assert np.array_equal(Internal.getNodeFromName1(s, 'PointListDonor')[1], [0, 1, 2])
+    assert np.array_equal(Internal.getNodeFromName1(s, 'PointListExtC')[1], [9, 9, 10])
+    assert Internal.getNodeFromName1(s, 'InterpolantsDonor')[1].size == 24
+    assert np.array_equal(Internal.getNodeFromName1(s, 'InterpolantsVol')[1], [.1, .2, .3])
+    assert np.array_equal(Internal.getNodeFromName1(s, 'InterpolantsType')[1], [2, 2, 2])
+    assert np.array_equal(Internal.getNodeFromName1(s, 'OrphanPointList')[1], [4])       # replaced, not appended
+    assert np.array_equal(Internal.getNodeFromName1(s, 'ExtrapPointList')[1], [1, 2])
+    # receiver side names the extra list PointListDonorExtC; prefix overrides the ID_/IBCD_ rule
+    z2 = Internal.newZone('R', 3, 3, 3)
+    X._createInterpRegion__(z2, 'D', i32(1), i32(2), np.ones(8), i32(2), np.array([]), i32(), i32(),
+                            pointlistdonorExtC=i32(3), tag='Receiver', loc='nodes', prefix='XX_')
+    s2 = Internal.getNodeFromName1(z2, 'XX_D')
+    assert [c[0] for c in s2[2]] == ['ZoneRole', 'PointList', 'PointListDonor', 'PointListDonorExtC',
+                                     'InterpolantsDonor', 'InterpolantsType']
+    with pytest.raises(NotImplementedError):
+        X._createInterpRegion__(z2, 'D', i32(1), i32(2), np.ones(8), i32(2), np.array([]), i32(), i32(), loc='faces')
