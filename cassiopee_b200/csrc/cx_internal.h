@@ -76,7 +76,8 @@ struct cx_plan {
   int ngroups;          // type groups
   // entries regrouped by type (stable), SoA coefficients per group
   // layout 0: list order, 1: sorted by donor index, 2: tiled by donor box (type 2 only; d_tiles = ntiles+1 TileRef)
-  struct Group { int type, ncf, sten, n, first; double* d_cf; int layout; void* d_tiles; int ntiles, ntx, nty; };
+  // layout 3: boxes of donor cells sized per plan (type 2 only; d_tiles = ntiles+1 BoxTile, box_vs = doubles of shared memory per variable)
+  struct Group { int type, ncf, sten, n, first; double* d_cf; int layout; void* d_tiles; int ntiles, ntx, nty, box_vs; };
   std::vector<Group> groups;
   int* d_donor; int* d_rcv; int* d_pos;   // regrouped order; pos = original entry position
   int* d_seq;                             // 0..n-1 (dense output in the plan's own order)

@@ -445,6 +445,89 @@ __device__ __forceinline__ void transfer_box2(double* __restrict__ sm, unsigned 
   }
 }
 
+// ---- box layout (layout 3): entries grouped by a 3-D box of donor cells sized for the plan's shape -----
+// Fringe plans (the 2-layer overlap slabs of a multi-block case such as C4) reference a donor region that is
+// only 3-4 nodes thick in one direction.  Sorted by donor index, a CTA's 256 entries then span ~100 short rows
+// and every entry gathers its 8 corners for every variable with dependent 8-byte loads (ncu, round 1: 44.7
+// long-scoreboard stalls per issue, issue slots 12 % busy).  Here the type-2 entries of a plan are grouped by
+// boxes of TI x TJ x TK donor cells chosen from the bounding box of the plan's donor cells (thin directions
+// whole, the rest split so that a box holds ~256 cells and at most CX_BOX_NODES nodes), in ascending receptor
+// order inside a box.  A CTA owns one box: all (TI+1)(TJ+1)(TK+1) nodes of EVERY variable are requested at
+// once with 8-byte cp.async (LDGSTS: no register staging, one memory round trip for the whole box while the
+// threads fetch their entries' indices and coefficients), each node once instead of once per referencing
+// entry, and the stencils are then read from shared memory (row pitch odd: conflict-free for thin rows).
+// cp.async.bulk.tensor is not usable here: a tensor map needs global strides that are multiples of 16 bytes
+// and the donor rows of a centre mesh of a 100^3 block are 99 * 8 = 792 bytes apart; 1-D bulk copies need
+// 16-byte aligned sources, which rows 3-4 nodes long at odd pitch do not have.
+// Arithmetic (operand order, no FMA) is the same as on every other path.
+#define CX_BOX_NODES 768                              // shared-memory doubles per variable and box (pitch included)
+#define CX_BOX_CELLS 256                              // target donor cells per box
+struct BoxTile { int start, base, dims, pad_; };      // first entry; donor node index of the box corner; node counts i | j<<8 | k<<16
+
+__device__ __forceinline__ void cp_async8(double* dst, const double* src)
+{ asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all()
+{ asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int MODE, class PD, class PR>
+__device__ __forceinline__ void transfer_box3(double* __restrict__ sm, int start, int count, int base, int dims, int m,
+                                              int nvars, const PD& pd, const PR& pr, int imd, int imdjmd,
+                                              const int* __restrict__ donor, const int* __restrict__ idx,
+                                              const double* __restrict__ cfT, double* __restrict__ dense, long long ld)
+{
+  const int tid = threadIdx.x;
+  const int ilen = dims & 255, jlen = (dims >> 8) & 255, klen = dims >> 16;
+  const int ip = ilen | 1;                             // odd row pitch
+  const int pk = ip * jlen;                            // plane pitch
+  const int vs = pk * klen;                            // doubles per variable
+  const int ij = ilen * jlen, nn = ij * klen;
+  for (int q = tid; q < nn; q += blockDim.x)
+  {
+    const int lk = q / ij, r = q - lk * ij, lj = r / ilen, li = r - lj * ilen;
+    const size_t g = (size_t)base + li + (size_t)lj * imd + (size_t)lk * imdjmd;
+    double* d = sm + lk * pk + lj * ip + li;
+    for (int v = 0; v < nvars; v++) cp_async8(d + (size_t)v * vs, pd[v] + g);
+  }
+  int c = tid;
+  int d0 = 0; size_t o = 0; double cf[8];
+  if (c < count)
+  {
+    const int e = start + c;
+    d0 = donor[e]; o = (size_t)idx[e];
+#pragma unroll
+    for (int q = 0; q < 8; q++) cf[q] = cfT[(size_t)q * m + e];
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  while (c < count)
+  {
+    const int rel = d0 - base;
+    const int lk = rel / imdjmd, r = rel - lk * imdjmd, lj = r / imd, li = r - lj * imd;
+    const double* b = sm + lk * pk + lj * ip + li;
+    for (int v = 0; v < nvars; v++, b += vs)
+    {
+      double val = 0.;
+      val += cf[0] * b[0];
+      val += cf[1] * b[1];
+      val += cf[2] * b[ip];
+      val += cf[3] * b[ip + 1];
+      val += cf[4] * b[pk];
+      val += cf[5] * b[pk + 1];
+      val += cf[6] * b[pk + ip];
+      val += cf[7] * b[pk + ip + 1];
+      if (MODE == 0) pr[v][o] = val; else dense[(size_t)v * ld + o] = val;
+    }
+    c += blockDim.x;
+    if (c < count)
+    {
+      const int e = start + c;
+      d0 = donor[e]; o = (size_t)idx[e];
+#pragma unroll
+      for (int q = 0; q < 8; q++) cf[q] = cfT[(size_t)q * m + e];
+    }
+  }
+}
+
 struct PDk { const double* const* p; __device__ __forceinline__ const double* operator[](int v) const { return p[v]; } };
 struct PRk { double* const* p; __device__ __forceinline__ double* operator[](int v) const { return p[v]; } };
 
@@ -694,6 +777,21 @@ k_transfer2t(const TileRef* __restrict__ tiles, int m, int nvars, FieldPtrs P, i
                       MODE == 0 ? rcv : pos, cfT, dense, ld);
 }
 
+// type 2, box layout: one CTA per non-empty donor box
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_transfer2b(const BoxTile* __restrict__ tiles, int m, int nvars, FieldPtrs P, int imd, int imdjmd,
+             const int* __restrict__ donor, const int* __restrict__ rcv, const int* __restrict__ pos,
+             const double* __restrict__ cfT, double* __restrict__ dense, long long ld)
+{
+  extern __shared__ __align__(16) double dyn_sm[];
+  PDk pd{P.d}; PRk pr{P.r};
+  const BoxTile t = tiles[blockIdx.x];
+  const int count = tiles[blockIdx.x + 1].start - t.start;
+  transfer_box3<MODE>(dyn_sm, t.start, count, t.base, t.dims, m, nvars, pd, pr, imd, imdjmd, donor, MODE == 0 ? rcv : pos,
+                      cfT, dense, ld);
+}
+
 // Plan set: every (plan, type group) of a rank in ONE launch.  Block b works on
 // descriptor blk2desc[b]; field pointers come from per-zone device tables.
 struct SetDesc {
@@ -709,7 +807,7 @@ struct SetDesc {
 static_assert(sizeof(SetDesc) % 8 == 0, "SetDesc is copied to shared memory in 8-byte words");
 // one record per block of a plan-set launch: its descriptor and, for donor-sorted type-2 groups, the donor
 // index range of the block's tile (so the staging can start without reading the donor list first)
-struct BlkRec { int desc, d_lo, d_hi, pad_; };
+struct BlkRec { int desc, d_lo, d_hi, start, count, base, dims, pad_; };   // start..dims: box layout (layout 3) blocks
 
 template <int TYPE, bool TILED>
 __global__ void __launch_bounds__(256, TILED ? 2 : CX_SET_MINB)
@@ -758,6 +856,12 @@ k_transfer_set(const SetDesc* __restrict__ descs, const BlkRec* __restrict__ blk
         }
       return;
     }
+    if (D.layout == 3)
+    {
+      if (D.mode == 0) transfer_box3<0>(dyn_sm, br.start, br.count, br.base, br.dims, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
+      else transfer_box3<1>(dyn_sm, br.start, br.count, br.base, br.dims, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
+      return;
+    }
     if (staged && D.layout == 1)
     {
       StageSmem& S = *reinterpret_cast<StageSmem*>(dyn_sm);
@@ -794,6 +898,12 @@ __global__ void k_block_ranges(int nblocks, const SetDesc* __restrict__ descs, B
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nblocks) return;
   const SetDesc& D = descs[blk[b].desc];
+  if (D.type == 2 && D.layout == 3)
+  {
+    const BoxTile* T = reinterpret_cast<const BoxTile*>(D.tiles) + (b - D.first_block);
+    blk[b].start = T[0].start; blk[b].count = T[1].start - T[0].start; blk[b].base = T[0].base; blk[b].dims = T[0].dims;
+    return;
+  }
   if (D.type != 2 || D.layout != 1) return;
   const int t0 = (b - D.first_block) * tb;
   const int last = min(t0 + tb, D.m) - 1;
@@ -915,6 +1025,39 @@ __global__ void k_donor_keys(int n, int T, const int* __restrict__ type, const i
   key[e] = (type[e] == T) ? (unsigned)donor[e] : sentinel;
   val[e] = e;
 }
+// box layout: sort key = box of the entry's donor cell, boxes of (ti,tj,tk) cells laid from the corner (i0,j0,k0)
+// of the bounding box of the group's donor cells (entries of other types sort last), value = entry
+struct BoxGrid { int i0, j0, k0, i1, j1, k1, ti, tj, tk, nbx, nby, nbz; };
+__global__ void k_box_keys(int n, int T, const int* __restrict__ type, const int* __restrict__ donor, int imd, int jmd,
+                           BoxGrid B, unsigned nboxes, unsigned* __restrict__ key, int* __restrict__ val)
+{
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  unsigned kk = nboxes;
+  if (type[e] == T)
+  {
+    int d = donor[e];
+    int i = d % imd, j = (d / imd) % jmd, k = d / (imd * jmd);
+    kk = (unsigned)((((k - B.k0) / B.tk) * B.nby + (j - B.j0) / B.tj) * B.nbx + (i - B.i0) / B.ti);
+  }
+  key[e] = kk; val[e] = e;
+}
+__global__ void k_box_table(int m, const unsigned* __restrict__ key, const unsigned long long* __restrict__ scan,
+                            BoxTile* __restrict__ tiles, int ntiles, BoxGrid B, int imd, int imdjmd)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s == 0) { BoxTile t; t.start = m; t.base = 0; t.dims = 0; t.pad_ = 0; tiles[ntiles] = t; }
+  if (s >= m) return;
+  if (s == 0 || key[s] != key[s - 1])
+  {
+    const int b = (int)key[s];
+    const int bx = b % B.nbx, by = (b / B.nbx) % B.nby, bz = b / (B.nbx * B.nby);
+    const int ci = B.i0 + bx * B.ti, cj = B.j0 + by * B.tj, ck = B.k0 + bz * B.tk;     // first donor cell of the box
+    const int ilen = min(B.ti, B.i1 - ci + 1) + 1, jlen = min(B.tj, B.j1 - cj + 1) + 1, klen = min(B.tk, B.k1 - ck + 1) + 1;
+    BoxTile t; t.start = s; t.base = ci + cj * imd + ck * imdjmd; t.dims = ilen | (jlen << 8) | (klen << 16); t.pad_ = 0;
+    tiles[scan[s]] = t;
+  }
+}
 __global__ void k_tile_heads(int m, const unsigned* __restrict__ key, unsigned long long* __restrict__ f)
 {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1002,6 +1145,63 @@ static int build_tiled_group(cx_ctx* ctx, cx_plan* P, cx_plan::Group& G, int n, 
   return ok;
 }
 
+// Box layout for the type-2 group G (see transfer_box3).  bb = i0,i1,j0,j1,k0,k1 of the group's donor cells (lowest
+// corner node of each stencil).  Returns 1 and fills the group when the boxes are filled well enough (or force),
+// 0 if the group is too sparse (caller falls back to the donor-sorted layout), < 0 on error.
+static int build_box_group(cx_ctx* ctx, cx_plan* P, cx_plan::Group& G, int n, const int* bb, const int* r_ty,
+                           const int* r_dn, const int* r_rc, const unsigned long long* r_off, const double* r_cf, int first,
+                           int force)
+{
+  cudaStream_t s = ctx->stream;
+  const int TB = 256;
+  const int ei = bb[1] - bb[0] + 1, ej = bb[3] - bb[2] + 1, ek = bb[5] - bb[4] + 1;     // extents in cells
+  BoxGrid B;
+  B.i0 = bb[0]; B.i1 = bb[1]; B.j0 = bb[2]; B.j1 = bb[3]; B.k0 = bb[4]; B.k1 = bb[5];
+  // rows as long as possible (up to 32 cells), the thinner of the two other directions whole or ~sqrt of the rest
+  B.ti = std::min(ei, 32);
+  int rem = std::max(1, CX_BOX_CELLS / B.ti);
+  int rt = 1; while ((rt + 1) * (rt + 1) <= rem) rt++;
+  if (ek <= ej) { B.tk = std::min(ek, std::max(rt, 1)); B.tj = std::min(ej, std::max(1, rem / B.tk)); }
+  else { B.tj = std::min(ej, std::max(rt, 1)); B.tk = std::min(ek, std::max(1, rem / B.tj)); }
+  auto vs_of = [&]() { return ((B.ti + 1) | 1) * (B.tj + 1) * (B.tk + 1); };
+  while (vs_of() > CX_BOX_NODES) { if (B.tj >= B.tk && B.tj > 1) B.tj--; else if (B.tk > 1) B.tk--; else B.ti--; }
+  if (B.tj > 254 || B.tk > 254) return 0;
+  B.nbx = (ei + B.ti - 1) / B.ti; B.nby = (ej + B.tj - 1) / B.tj; B.nbz = (ek + B.tk - 1) / B.tk;
+  const long long nboxes_ll = (long long)B.nbx * B.nby * B.nbz;
+  if (nboxes_ll >= 0x7fffffffll) return 0;
+  const unsigned nboxes = (unsigned)nboxes_ll;
+  unsigned *k_in, *k_out; int *v_in, *v_out; void* tmp = nullptr; size_t tmp_bytes = 0;
+  CX_MALLOC(k_in, sizeof(unsigned) * (size_t)n, s); CX_MALLOC(k_out, sizeof(unsigned) * (size_t)n, s);
+  CX_MALLOC(v_in, sizeof(int) * (size_t)n, s); CX_MALLOC(v_out, sizeof(int) * (size_t)n, s);
+  k_box_keys<<<cx_grid(n, TB), TB, 0, s>>>(n, G.type, r_ty, r_dn, P->imd, P->jmd, B, nboxes, k_in, v_in);
+  int bits = 1; while ((1ull << bits) <= (unsigned long long)nboxes) bits++;
+  // stable LSD radix sort (CUB): entries keep their list order (ascending receptors) inside a box
+  CX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, n, 0, bits, s));
+  CX_MALLOC(tmp, tmp_bytes, s);
+  CX_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, n, 0, bits, s));
+  const int m = G.n;
+  unsigned long long *f, *sc, total = 0;
+  CX_MALLOC(f, sizeof(unsigned long long) * (size_t)m, s); CX_MALLOC(sc, sizeof(unsigned long long) * (size_t)m, s);
+  k_tile_heads<<<cx_grid(m, TB), TB, 0, s>>>(m, k_out, f);
+  CX_CHECK(cx_exclusive_scan_u64(ctx, f, sc, m, &total));
+  ctx->launches += 3;
+  int ok = 0;
+  // worth it when a box's entries reuse its nodes: at least ~1 entry per 4 staged nodes on average
+  if (force || (long long)m * 4 >= (long long)total * vs_of())
+  {
+    G.ntiles = (int)total; G.layout = 3; G.box_vs = vs_of();
+    CX_CUDA(cudaMalloc(&G.d_tiles, sizeof(BoxTile) * ((size_t)total + 1)));
+    k_box_table<<<cx_grid(m, TB), TB, 0, s>>>(m, k_out, sc, (BoxTile*)G.d_tiles, (int)total, B, P->imd, P->imd * P->jmd);
+    k_plan_place_perm<<<cx_grid(m, TB), TB, 0, s>>>(m, G.ncf, v_out, r_dn, r_rc, r_off, r_cf, P->d_donor + first,
+                                                   P->d_rcv + first, P->d_pos + first, G.d_cf);
+    ctx->launches += 2;
+    ok = 1;
+  }
+  cudaFreeAsync(k_in, s); cudaFreeAsync(k_out, s); cudaFreeAsync(v_in, s); cudaFreeAsync(v_out, s);
+  cudaFreeAsync(tmp, s); cudaFreeAsync(f, s); cudaFreeAsync(sc, s);
+  return ok;
+}
+
 // Donor-sorted layout with a STABLE sort (CUB LSD radix sort on the donor index): entries that share a donor cell
 // keep their list order, i.e. ascending receptor index, so the lanes that handle them store to neighbouring
 // receptor addresses and the warp's store touches fewer 32-byte sectors than with an atomic-cursor placement.
@@ -1046,6 +1246,7 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
   std::vector<unsigned long long> off((size_t)n);
   long long run = 0;
   int cnt[6] = {0, 0, 0, 0, 0, 0};
+  int bb2[6] = {INT_MAX, -1, INT_MAX, -1, INT_MAX, -1};      // donor cells of the type-2 entries: i0,i1,j0,j1,k0,k1
   for (int e = 0; e < n; e++)
   {
     off[e] = (unsigned long long)run;
@@ -1055,6 +1256,12 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
     if (rcv[e] < 0 || (long long)rcv[e] >= nptsR) { cx_set_error("transfer plan: receptor index %d out of range", rcv[e]); return -1; }
     run += nc;
     for (int g = 0; g < 6; g++) if (type[e] == types[g]) cnt[g]++;
+    if (type[e] == 2)
+    {
+      const int d = donor[e], ci = d % imd, cj = (d / imd) % jmd, ck = d / (imd * jmd);
+      bb2[0] = std::min(bb2[0], ci); bb2[1] = std::max(bb2[1], ci); bb2[2] = std::min(bb2[2], cj);
+      bb2[3] = std::max(bb2[3], cj); bb2[4] = std::min(bb2[4], ck); bb2[5] = std::max(bb2[5], ck);
+    }
   }
   if (run != ncoefs) { cx_set_error("transfer plan: coefficient array has %lld entries, types need %lld", ncoefs, run); return -1; }
   P->alg_bytes_fixed = 8 * run + 12ll * n;
@@ -1088,11 +1295,19 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
     if (cnt[g] == 0) continue;
     cx_plan::Group G; G.type = types[g]; G.ncf = ncf_host(types[g]); G.sten = sten_host(types[g]);
     G.n = cnt[g]; G.first = first; G.d_cf = nullptr;
-    G.layout = sorted ? 1 : 0; G.d_tiles = nullptr; G.ntiles = 0; G.ntx = G.nty = 0;
+    G.layout = sorted ? 1 : 0; G.d_tiles = nullptr; G.ntiles = 0; G.ntx = G.nty = 0; G.box_vs = 0;
     CX_MALLOC(G.d_cf, sizeof(double) * (size_t)G.ncf * G.n + 64, s);
     if (G.type == 2 && (mode_env == 2 || mode_env == 3) && kmd >= 2 && G.n >= 4096)
     {
       int rc = build_tiled_group(ctx, P, G, n, kmd, r_ty, r_dn, r_rc, r_off, r_cf, first, mode_env == 3);
+      if (rc < 0) return rc;
+      if (rc == 1) { P->groups.push_back(G); first += G.n; continue; }
+    }
+    // box layout: default for the plans a plan set fuses (below CX_BIG_PLAN entries) when their boxes fill well;
+    // CX_PLAN_SORT=5 forces it for every 3-D type-2 group, =1 keeps the donor-sorted layout
+    if (G.type == 2 && kmd >= 2 && (mode_env == 5 || (mode_env < 0 && G.n >= 1024 && n < CX_BIG_PLAN)))
+    {
+      int rc = build_box_group(ctx, P, G, n, bb2, r_ty, r_dn, r_rc, r_off, r_cf, first, mode_env == 5);
       if (rc < 0) return rc;
       if (rc == 1) { P->groups.push_back(G); first += G.n; continue; }
     }
@@ -1153,7 +1368,10 @@ static int tiled_smem_optin()
   static int done = 0;
   if (!done)
   {
-    const int mx = (int)(sizeof(double) * CX_BOXV * CX_MAXVARS);
+    const int mx = (int)(sizeof(double) * (CX_BOXV > CX_BOX_NODES ? CX_BOXV : CX_BOX_NODES) * CX_MAXVARS);
+    CX_CUDA(cudaFuncSetAttribute(k_transfer2b<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CX_CUDA(cudaFuncSetAttribute(k_transfer2b<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CX_CUDA(cudaFuncSetAttribute(k_transfer_set<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     CX_CUDA(cudaFuncSetAttribute(k_transfer2t<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     CX_CUDA(cudaFuncSetAttribute(k_transfer2t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     CX_CUDA(cudaFuncSetAttribute(k_transfer_set<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
@@ -1201,6 +1419,14 @@ int cx_plan_launch(cx_plan* P, int nvars, const double* const* dD, double* const
             const TileRef* tl = (const TileRef*)G.d_tiles;
             if (mode == 0) k_transfer2t<0><<<G.ntiles, TB, smb, s>>>(tl, G.n, nv, F, imd, P->jmd, P->nptsD, G.ntx, G.nty, dn_, rc_, ps_, G.d_cf, dn, ld);
             else k_transfer2t<1><<<G.ntiles, TB, smb, s>>>(tl, G.n, nv, F, imd, P->jmd, P->nptsD, G.ntx, G.nty, dn_, rc_, ps_, G.d_cf, dn, ld);
+          }
+          else if (G.layout == 3)
+          {
+            const size_t smb = sizeof(double) * (size_t)G.box_vs * (size_t)nv;
+            CX_CHECK(tiled_smem_optin());
+            const BoxTile* tl = (const BoxTile*)G.d_tiles;
+            if (mode == 0) k_transfer2b<0><<<G.ntiles, TB, smb, s>>>(tl, G.n, nv, F, imd, ij, dn_, rc_, ps_, G.d_cf, dn, ld);
+            else k_transfer2b<1><<<G.ntiles, TB, smb, s>>>(tl, G.n, nv, F, imd, ij, dn_, rc_, ps_, G.d_cf, dn, ld);
           }
           else if (staged && G.layout == 1)
           {
@@ -1384,6 +1610,7 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
       D.tiles = (const TileRef*)G.d_tiles;
       if (G.type == 2 && G.layout == 2) { S->smem = std::max(S->smem, sizeof(double) * CX_BOXV * (size_t)nvars); S->tiled = 1; }
       if (G.type == 2 && G.layout == 1) S->smem = std::max(S->smem, sizeof(StageSmem));
+      if (G.type == 2 && G.layout == 3) S->smem = std::max(S->smem, sizeof(double) * (size_t)G.box_vs * (size_t)nvars);
       if (G.type == 3 && G.layout == 1) S->smem3 = sizeof(StageSmemO<3>);
       for (int v = 0; v < nvars; v++) if (((uintptr_t)d_fieldD[p][v]) & 15) S->staged = 0;
       D.donor = P->d_donor + G.first;
@@ -1394,8 +1621,8 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
         D.dp[v] = v < nvars ? d_fieldD[p][v] : nullptr;
         D.rp[v] = (v < nvars && modes[p] == 0) ? d_fieldR[p][v] : nullptr;
       }
-      int blocks = (G.type == 2 && G.layout == 2) ? G.ntiles : cx_grid(G.n, TB);
-      for (int b = 0; b < blocks; b++) b2d[t].push_back(BlkRec{(int)descs[t].size(), -1, -1, 0});
+      int blocks = (G.type == 2 && (G.layout == 2 || G.layout == 3)) ? G.ntiles : cx_grid(G.n, TB);
+      for (int b = 0; b < blocks; b++) b2d[t].push_back(BlkRec{(int)descs[t].size(), -1, -1, 0, 0, 0, 0, 0});
       descs[t].push_back(D);
       nb[t] += blocks;
       S->ndesc++;

@@ -710,3 +710,73 @@ def test_reference_script_setInterpDataPT_t1_curve_receptors(ctx, loc, order):
         for pen in (0, 1):
             for nat in (0, 1):
                 cases.check_curve_receptors(dict(ctx=ctx), order, loc, storage, pen, nat)
+
+
+@pytest.mark.parametrize("shape", ["xslab", "yslab", "zslab", "volume", "sparse"])
+def test_transfer_box_layout(ctx, shape, monkeypatch):
+    """Box layout of the type-2 groups (k_transfer2b / the layout-3 branch of k_transfer_set, forced with
+    CX_PLAN_SORT=5): fringe slabs 3 cells thick normal to each axis (the C4 shape: odd row pitch 99), a dense volume
+    and a sparse cloud, a type-1 group in front, stencils ending on the last node, 1..16 variables; single-plan
+    launches (in place, dense) and the fused plan-set launch in its three output modes.  Bit-exact vs the
+    reference loops."""
+    from cassiopee_b200 import _lib
+    from oracle import oracle as O
+    monkeypatch.setenv("CX_PLAN_SORT", "5")
+    ni, nj, nk = (99, 41, 37) if shape != "volume" else (45, 33, 21)
+    rng = np.random.default_rng(len(shape) * 7 + ni)
+    nD = ni * nj * nk
+    if shape == "xslab":
+        cells = [(i, j, k) for k in range(2, nk - 3) for j in range(1, nj - 1) for i in (91, 92, 93)]
+    elif shape == "yslab":
+        cells = [(i, j, k) for k in range(0, nk - 1) for j in (5, 6, 7) for i in range(0, ni - 1)]
+    elif shape == "zslab":
+        cells = [(i, j, k) for k in (nk - 4, nk - 3, nk - 2) for j in range(0, nj - 1) for i in range(3, ni - 1)]
+    elif shape == "volume":
+        cells = [(i, j, k) for k in range(nk - 1) for j in range(nj - 1) for i in range(ni - 1)]
+    else:
+        cells = [tuple(c) for c in np.stack([rng.integers(0, ni - 1, 3000), rng.integers(0, nj - 1, 3000),
+                                             rng.integers(0, nk - 1, 3000)], axis=1)]
+    cells = np.array(cells, np.int64)
+    rep = 2 if shape != "sparse" else 1
+    cells = np.repeat(cells, rep, axis=0)
+    cells = cells[rng.permutation(cells.shape[0])]
+    n = cells.shape[0]
+    typ = np.full(n, 2, np.int32)
+    typ[rng.random(n) < 0.05] = 1
+    typ[:3] = 1
+    dnr = (cells[:, 0] + ni * cells[:, 1] + ni * nj * cells[:, 2]).astype(np.int32)
+    dnr[3] = (ni - 2) + ni * (nj - 2) + ni * nj * (nk - 2); typ[3] = 2          # stencil ends on the last node
+    nR = n + 17
+    rcv = np.sort(rng.permutation(nR)[:n]).astype(np.int32)
+    ncf = np.where(typ == 1, 1, 8)
+    cf = rng.standard_normal(int(ncf.sum()))
+    plan = _lib.Plan(ctx, ni, nj, nk, nR, dnr, rcv, typ, cf)
+    for nvars in (1, 5, 7, 16):
+        fD = [rng.standard_normal(nD) for _ in range(nvars)]
+        fRo = [np.full(nR, -7.) for _ in range(nvars)]
+        O.transfer(fD, fRo, ni, nj, rcv, dnr, typ, cf)
+        refD = O.transferD(fD, ni, nj, dnr, typ, cf)
+        dD = [_lib.DeviceArray.from_host(ctx, f) for f in fD]
+        dR = [_lib.DeviceArray.from_host(ctx, np.full(nR, -7.)) for _ in range(nvars)]
+        plan.transfer_dev([d.ptr for d in dD], [d.ptr for d in dR])
+        ctx.sync()
+        for d, b in zip(dR, fRo):
+            assert np.array_equal(d.download(), b)
+        dense = _lib.DeviceArray(ctx, n * nvars)
+        plan.transferD_dev([d.ptr for d in dD], dense.ptr, n)
+        ctx.sync()
+        assert np.array_equal(dense.download().reshape(nvars, n), refD)
+        dR2 = [_lib.DeviceArray.from_host(ctx, np.full(nR, -7.)) for _ in range(nvars)]
+        dense1 = _lib.DeviceArray(ctx, n * nvars); dense2 = _lib.DeviceArray(ctx, n * nvars)
+        ps = _lib.PlanSet(ctx, nvars, [(plan, 0, [d.ptr for d in dD], [d.ptr for d in dR2], None, 0),
+                                       (plan, 1, [d.ptr for d in dD], None, dense1.ptr, n),
+                                       (plan, 2, [d.ptr for d in dD], None, dense2.ptr, n)])
+        ps.run(); ctx.sync()
+        for d, b in zip(dR2, fRo):
+            assert np.array_equal(d.download(), b)
+        assert np.array_equal(dense1.download().reshape(nvars, n), refD)
+        srt = plan.sorted_rcv()
+        d2 = dense2.download().reshape(nvars, n)
+        for v in range(nvars):
+            got = np.full(nR, -7.); got[srt] = d2[v]
+            assert np.array_equal(got, fRo[v])
