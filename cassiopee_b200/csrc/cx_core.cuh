@@ -642,19 +642,23 @@ CX_D bool celln_valid_o2(const ZoneView& Z, int ic, int jc, int kc, const double
   if (nature == 0)
   {
     double val = 1.;
-    for (int kk = 0; kk < 2; kk++) for (int jj = 0; jj < 2; jj++) for (int ii = 0; ii < 2; ii++)
+#pragma unroll
+    for (int q = 0; q < 8; q++)
     {
+      const int ii = q & 1, jj = (q >> 1) & 1, kk = q >> 2;
       double c0 = Z.cellN[(ic + ii) + (jc + jj) * ni + (kc + kk) * nij];
-      int d = cf[ii + jj * 2 + kk * 4] > 1.e-12;
+      int d = cf[q] > 1.e-12;
       val *= c0 - d + 1;
     }
     return !eqzero(val, CX_EPS_GEOM);
   }
   double val = 0.;
-  for (int kk = 0; kk < 2; kk++) for (int jj = 0; jj < 2; jj++) for (int ii = 0; ii < 2; ii++)
+#pragma unroll
+  for (int q = 0; q < 8; q++)
   {
+    const int ii = q & 1, jj = (q >> 1) & 1, kk = q >> 2;
     double c0 = Z.cellN[(ic + ii) + (jc + jj) * ni + (kc + kk) * nij];
-    val += fabs(cf[ii + jj * 2 + kk * 4]) * fabs(1. - c0);
+    val += fabs(cf[q]) * fabs(1. - c0);
   }
   return eqzero(val, CX_EPS_GEOM);
 }
@@ -853,6 +857,299 @@ CX_DN int search_extrap_cell(const ZoneView& Z, double x, double y, double z, in
 }
 
 // ---------------------------------------------------------------------------
+// Order-2 search with the dynamically indexed per-thread state OUT of local memory.
+//
+// The functions above keep the DFS stack (int[192]), the query box a[6]/b[6] and the 15 points of the cell
+// under test (Hexa, 45 doubles, indexed by table look-ups) in per-thread arrays, i.e. in local memory: ptxas
+// reported a 1904-byte stack frame for k_interp_o2 and ncu 20.5 GB of DRAM writes for 1.4 GB of results
+// (profiles/r01_f_summary.md).  They remain in use for the rare extrapolation pass only.  Here
+//   * the stack and the 8 vertices of the cell live in a Scratch area addressed with a stride (shared memory on
+//     the device, column = thread, stride = threads per CTA: conflict-free; a plain array with stride 1 on the host);
+//   * the query box is rebuilt per node from registers (a = (zone min, p), b = (p, zone max));
+//   * face centres are recomputed from the scratch vertices when a tetrahedron needs one (same expression and
+//     summation order as coord_hexa, so the same value), the cell centre is kept in three registers;
+//   * the 8 hexa weights are produced with predicated adds instead of table-indexed stores.
+// Every floating-point operation and its operand order is unchanged, so results are bit-identical to the
+// functions above (tests/hostemu runs both against the oracle).
+// ---------------------------------------------------------------------------
+struct Scratch {
+  int* stk;      // DFS stack, entry l at stk[l * ss]
+  double* vtx;   // cell vertices: component c (0 x, 1 y, 2 z) of vertex v at vtx[(c * 8 + v) * ss]
+  int ss;        // stride between consecutive entries
+  int cap;       // stack capacity (>= depth + 2 of every zone searched)
+};
+struct AdtQueryS { double px, py, pz, alphaTol; int sp; int prune; };
+
+CX_D void query_init_s(AdtQueryS& q, const Scratch& S, double x, double y, double z, double alphaTol)
+{
+  q.px = x; q.py = y; q.pz = z; q.alphaTol = alphaTol;
+  S.stk[0] = 0; q.sp = 1;
+  q.prune = (alphaTol == 0.0) ? 1 : 0;
+}
+
+// query_next with the stack in scratch and a[d], b[d] of InterpAdt.cpp:678-682 selected from registers
+CX_D int query_next_s(AdtQueryS& q, const ZoneView& Z, const Scratch& S, int* nodeId, int* nvisit)
+{
+  const AdtNode* __restrict__ nodes = Z.nodes;
+  while (q.sp > 0)
+  {
+    int id = S.stk[(--q.sp) * S.ss];
+    const AdtNode& n = nodes[id];
+    (*nvisit)++;
+    if (q.prune && !subtree_may_hold(n, q.px, q.py, q.pz)) continue;
+    const int d = n.dim;
+    const int dd = d < 3 ? d : d - 3;
+    const double pv = dd == 0 ? q.px : (dd == 1 ? q.py : q.pz);
+    const double av = d < 3 ? Z.bbox[dd] : pv;          // a = (xmin, ymin, zmin, x, y, z)
+    const double bv = d < 3 ? pv : Z.bbox[dd + 3];      // b = (x, y, z, xmax, ymax, zmax)
+    const int nl = n.left, nr = n.right;
+    if (av <= n.mid && nl != CX_NULL && q.sp < S.cap) S.stk[(q.sp++) * S.ss] = nl;
+    if (bv >= n.rlo && nr != CX_NULL && q.sp < S.cap) S.stk[(q.sp++) * S.ss] = nr;
+    if (node_is_candidate(n, q.px, q.py, q.pz, q.alphaTol)) { *nodeId = id; return n.ind; }
+  }
+  return -1;
+}
+
+CX_D bool query_contains_s(const AdtQueryS& q, const ZoneView& Z, int cellId)
+{
+  const AdtNode* __restrict__ nodes = Z.nodes;
+  const AdtNode& t = nodes[cellId];
+  if (!node_is_candidate(t, q.px, q.py, q.pz, q.alphaTol)) return false;
+  int id = 0;
+  while (id != cellId)
+  {
+    const AdtNode& n = nodes[id];
+    const int d = n.dim;
+    const int dd = d < 3 ? d : d - 3;
+    const double pv = dd == 0 ? q.px : (dd == 1 ? q.py : q.pz);
+    if (t.bb[d] <= n.mid)
+    {
+      const double av = d < 3 ? Z.bbox[dd] : pv;
+      if (!(av <= n.mid)) return false;
+      id = n.left;
+    }
+    else
+    {
+      const double bv = d < 3 ? pv : Z.bbox[dd + 3];
+      if (!(bv >= n.rlo)) return false;
+      id = n.right;
+    }
+    if (id == CX_NULL) return false;
+  }
+  return true;
+}
+
+// InterpData::coeffInterpTetra on explicit points P (origin), Q, R, S
+CX_D void tetra_solve_p(double x, double y, double z, double xp, double yp, double zp, double xq, double yq, double zq,
+                        double xr, double yr, double zr, double xs, double ys, double zs,
+                        double& xi, double& yi, double& zi)
+{
+  double a11 = xq - xp, a12 = xr - xp, a13 = xs - xp;
+  double a21 = yq - yp, a22 = yr - yp, a23 = ys - yp;
+  double a31 = zq - zp, a32 = zr - zp, a33 = zs - zp;
+  double c11 = a22 * a33 - a32 * a23;
+  double c12 = -(a21 * a33 - a31 * a23);
+  double c13 = a21 * a32 - a31 * a22;
+  double c21 = -(a12 * a33 - a32 * a13);
+  double c22 = a11 * a33 - a31 * a13;
+  double c23 = -(a11 * a32 - a31 * a12);
+  double c31 = a12 * a23 - a22 * a13;
+  double c32 = -(a11 * a23 - a21 * a13);
+  double c33 = a11 * a22 - a21 * a12;
+  double det = a11 * c11 + a12 * c12 + a13 * c13;
+  if (fabs(det) < CX_EPS_DET) { xi = -10.; yi = -10.; zi = -10.; }
+  else
+  {
+    double xpm = x - xp, ypm = y - yp, zpm = z - zp;
+    det = 1.0 / det;
+    xi = (c11 * xpm + c21 * ypm + c31 * zpm) * det;
+    yi = (c12 * xpm + c22 * ypm + c32 * zpm) * det;
+    zi = (c13 * xpm + c23 * ypm + c33 * zpm) * det;
+  }
+}
+
+// InterpData::coordHexa (InterpData.cpp:56-134) + the centre tetrahedron 14,11,12,10 of getCellJump /
+// coeffInterpHexa (:383-399, :214-222): the 8 vertices go to scratch, the centre point 14 stays in registers.
+CX_D void cell_load_jump(const ZoneView& Z, int ind, const Scratch& S, double x, double y, double z, int& ic, int& jc,
+                         int& kc, double& cx, double& cy, double& cz, double& xi, double& yi, double& zi)
+{
+  const int ni = Z.ni, nij = Z.ni * Z.nj;
+  kc = ind / nij + 1;
+  int kcnij = kc * nij, kcmnij = (kc - 1) * nij;
+  jc = (ind - kcmnij) / ni + 1;
+  int jcni = jc * ni, jcmni = (jc - 1) * ni;
+  ic = ind - jcmni - kcmnij + 1;
+  double vx[8], vy[8], vz[8];
+  {
+    const int i0 = ind, i1 = ic + jcmni + kcmnij, i2 = ic - 1 + jcni + kcmnij, i3 = ic + jcni + kcmnij;
+    vx[0] = Z.x[i0]; vy[0] = Z.y[i0]; vz[0] = Z.z[i0];
+    vx[1] = Z.x[i1]; vy[1] = Z.y[i1]; vz[1] = Z.z[i1];
+    vx[2] = Z.x[i2]; vy[2] = Z.y[i2]; vz[2] = Z.z[i2];
+    vx[3] = Z.x[i3]; vy[3] = Z.y[i3]; vz[3] = Z.z[i3];
+    if (Z.nk > 1)
+    {
+      const int i4 = ic - 1 + jcmni + kcnij, i5 = ic + jcmni + kcnij, i6 = ic - 1 + jcni + kcnij, i7 = ic + jcni + kcnij;
+      vx[4] = Z.x[i4]; vy[4] = Z.y[i4]; vz[4] = Z.z[i4];
+      vx[5] = Z.x[i5]; vy[5] = Z.y[i5]; vz[5] = Z.z[i5];
+      vx[6] = Z.x[i6]; vy[6] = Z.y[i6]; vz[6] = Z.z[i6];
+      vx[7] = Z.x[i7]; vy[7] = Z.y[i7]; vz[7] = Z.z[i7];
+    }
+    else
+    {
+#pragma unroll
+      for (int v = 0; v < 4; v++) { vx[v + 4] = vx[v]; vy[v + 4] = vy[v]; vz[v + 4] = vz[v] + 1.; }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < 8; v++)
+  {
+    S.vtx[v * S.ss] = vx[v]; S.vtx[(8 + v) * S.ss] = vy[v]; S.vtx[(16 + v) * S.ss] = vz[v];
+  }
+#define CX_FCR(a, b, c, d, ox, oy, oz)            \
+  const double ox = 0.25 * (vx[a] + vx[b] + vx[c] + vx[d]); \
+  const double oy = 0.25 * (vy[a] + vy[b] + vy[c] + vy[d]); \
+  const double oz = 0.25 * (vz[a] + vz[b] + vz[c] + vz[d]);
+  CX_FCR(0, 1, 2, 3, x8, y8, z8)
+  CX_FCR(4, 5, 6, 7, x10, y10, z10)
+  CX_FCR(1, 3, 5, 7, x11, y11, z11)
+  CX_FCR(2, 3, 6, 7, x12, y12, z12)
+#undef CX_FCR
+  cx = 0.5 * (x8 + x10); cy = 0.5 * (y8 + y10); cz = 0.5 * (z8 + z10);
+  tetra_solve_p(x, y, z, cx, cy, cz, x11, y11, z11, x12, y12, z12, x10, y10, z10, xi, yi, zi);
+}
+
+// tetrahedron (14, q, r, s): q a face centre (8..13), r and s vertices (0..7), all read from scratch
+CX_D void tetra_solve_s(double x, double y, double z, const Scratch& S, double cx, double cy, double cz, int q, int r,
+                        int s, double& xi, double& yi, double& zi)
+{
+  // vertices of face q in the summation order of coordHexa, 4 bits each: 8:(0,1,2,3) 9:(0,2,4,6) 10:(4,5,6,7)
+  // 11:(1,3,5,7) 12:(2,3,6,7) 13:(0,1,4,5)
+  const unsigned long long lo = 0x7531765464203210ull;
+  const unsigned hi = 0x54107632u;
+  const unsigned f = (q < 12) ? (unsigned)(lo >> (16 * (q - 8))) : (hi >> (16 * (q - 12)));
+  const int a = f & 7, b = (f >> 4) & 7, c = (f >> 8) & 7, d = (f >> 12) & 7;
+  const double* vx = S.vtx; const double* vy = S.vtx + 8 * S.ss; const double* vz = S.vtx + 16 * S.ss;
+  const int ss = S.ss;
+  const double xq = 0.25 * (vx[a * ss] + vx[b * ss] + vx[c * ss] + vx[d * ss]);
+  const double yq = 0.25 * (vy[a * ss] + vy[b * ss] + vy[c * ss] + vy[d * ss]);
+  const double zq = 0.25 * (vz[a * ss] + vz[b * ss] + vz[c * ss] + vz[d * ss]);
+  tetra_solve_p(x, y, z, cx, cy, cz, xq, yq, zq, vx[r * ss], vy[r * ss], vz[r * ss], vx[s * ss], vy[s * ss], vz[s * ss],
+                xi, yi, zi);
+}
+
+// tetra (xi,yi,zi) -> 8 hexa weights with predicated adds in the order of tetra_to_hexa
+CX_D void tetra_to_hexa_s(double xi, double yi, double zi, int indq, int indr, int inds, double* cf)
+{
+  const double cf0 = 0.125 * (1.0 - xi - yi - zi);
+  const double tl = xi * 0.25;
+  // vertices of face indq (T_indfc rows) as bit masks: 8: 0x0f, 9: 0x55, 10: 0xf0, 11: 0xaa, 12: 0xcc, 13: 0x33
+  const unsigned fm = (unsigned)((0x33ccaaf0550full >> (8 * (indq - 8))) & 0xffu);
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+  {
+    double t = cf0;
+    if ((fm >> i) & 1u) t += tl;
+    if (i == indr) t += yi;
+    if (i == inds) t += zi;
+    cf[i] = t;
+  }
+}
+
+CX_D bool hexa_from_corner_s(double x, double y, double z, const Scratch& S, double cx, double cy, double cz, int isomm,
+                             double xi, double yi, double zi, double* cf)
+{
+  if (!(isomm & 1)) xi = -xi;
+  if (!(isomm & 2)) yi = -yi;
+  if (!(isomm & 4)) zi = -zi;
+  int is1 = trunc_int((1.0 + fsign(xi - yi)) * 0.5);
+  int is2 = trunc_int((1.0 + fsign(yi - zi)) * 0.5);
+  int is3 = trunc_int((1.0 + fsign(zi - xi)) * 0.5);
+  int itri = T_indtr[isomm + 8 * is1 + 16 * is2 + 32 * is3];
+  int indr = T_indtd[0 + itri * 4], inds = T_indtd[1 + itri * 4], indq = T_indtd[2 + itri * 4];
+  tetra_solve_s(x, y, z, S, cx, cy, cz, indq, indr, inds, xi, yi, zi);
+  if (tetra_accept(xi, yi, zi)) { tetra_to_hexa_s(xi, yi, zi, indq, indr, inds, cf); return true; }
+  for (int ibsom = 0; ibsom < 4; ibsom++)
+  {
+    int isom = T_indss[ibsom + 4 * isomm];
+    indr = isom;
+    for (int its = 0; its < 3; its++)
+    {
+      inds = T_neighbour[its + isom * 3];
+      for (int itq = 0; itq < 2; itq++)
+      {
+        indq = T_center[itq + its + isom * 4];
+        tetra_solve_s(x, y, z, S, cx, cy, cz, indq, indr, inds, xi, yi, zi);
+        if (tetra_accept(xi, yi, zi)) { tetra_to_hexa_s(xi, yi, zi, indq, indr, inds, cf); return true; }
+      }
+    }
+  }
+  return false;
+}
+
+// InterpAdt::searchInterpolationCellStruct (InterpAdt.cpp:1252-1400), scratch version of search_interp_cell
+CX_D int search_interp_cell_s(const ZoneView& Z, double x, double y, double z, int& ic, int& jc, int& kc, double* cf,
+                              const Scratch& S, SearchStats* st)
+{
+  if (zone_reject(Z, x, y, z, 0.0)) return 0;
+  AdtQueryS q;
+  query_init_s(q, S, x, y, z, 0.0);
+  int nid, nvisit = 0;
+  int first = query_next_s(q, Z, S, &nid, &nvisit);
+  if (st) { st->nvisit += nvisit; }
+  if (first < 0) return 0;
+  const int ni = Z.ni, nj = Z.nj, nk = Z.nk, nij = ni * nj;
+  bool JUMP = false;
+  int ind = first, isomm = 0;
+  double xi = 0, yi = 0, zi = 0, cx = 0, cy = 0, cz = 0;
+  int erased = -1;
+  for (int i = 0; i < 8; i++)
+  {
+    cell_load_jump(Z, ind, S, x, y, z, ic, jc, kc, cx, cy, cz, xi, yi, zi);
+    if (!(fabs(xi) <= 1.0 + CX_EPS_GEOM && fabs(yi) <= 1.0 + CX_EPS_GEOM && fabs(zi) <= 1.0 + CX_EPS_GEOM))
+    {
+      if (i == 7) break;
+      int is = imin(8, trunc_int((xi + fsign(xi)) * 0.5)); is = imax(-8, is);
+      int js = imin(8, trunc_int((yi + fsign(yi)) * 0.5)); js = imax(-8, js);
+      int ks = imin(8, trunc_int((zi + fsign(zi)) * 0.5)); ks = imax(-8, ks);
+      ind = ind + is + js * ni + ks * nij;
+      kc = ind / nij;
+      int kcnij = kc * nij;
+      jc = (ind - kcnij) / ni;
+      int jcni = jc * ni;
+      ic = ind - jcni - kcnij;
+      if (ic < 0 || ic > ni - 2 || jc < 0 || jc > nj - 2 || kc < 0 || kc > nk - 2) break;
+    }
+    else
+    {
+      isomm = (xi >= 0 ? 1 : 0) + (yi >= 0 ? 2 : 0) + (zi >= 0 ? 4 : 0);
+      int cid = (ic - 1) + (ni - 1) * ((jc - 1) + (nj - 1) * (kc - 1));
+      JUMP = (ind == first) ? true : query_contains_s(q, Z, cid);
+      break;
+    }
+  }
+  if (JUMP)
+  {
+    if (hexa_from_corner_s(x, y, z, S, cx, cy, cz, isomm, xi, yi, zi, cf)) return 1;
+    erased = ind;
+  }
+  // ordered fallback over the whole candidate list (InterpAdt.cpp:1378-1397)
+  query_init_s(q, S, x, y, z, 0.0);
+  nvisit = 0;
+  int c;
+  while ((c = query_next_s(q, Z, S, &nid, &nvisit)) >= 0)
+  {
+    if (c == erased) continue;
+    cell_load_jump(Z, c, S, x, y, z, ic, jc, kc, cx, cy, cz, xi, yi, zi);
+    isomm = 0;                                                 // coeffInterpHexa (InterpData.cpp:214-241)
+    if (fabs(xi) <= 1.0 + CX_EPS_GEOM && fabs(yi) <= 1.0 + CX_EPS_GEOM && fabs(zi) <= 1.0 + CX_EPS_GEOM)
+      isomm = (xi >= 0 ? 1 : 0) + (yi >= 0 ? 2 : 0) + (zi >= 0 ? 4 : 0);
+    if (hexa_from_corner_s(x, y, z, S, cx, cy, cz, isomm, xi, yi, zi, cf)) { if (st) st->nvisit += nvisit; return 1; }
+  }
+  if (st) st->nvisit += nvisit;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
 // Per-receptor drivers (bodies of the search kernels)
 // ---------------------------------------------------------------------------
 struct RcvOut { int noblk, type, dind; double cf[8]; };
@@ -873,9 +1170,11 @@ CX_D void collapse_type2(const ZoneView& Z, int& type, int& dind, double* cf)
     if (nb == 1) { type = 1; dind = indNonZero; cf[0] = coefNonZero; }
     return;
   }
-  for (int kk = 0; kk < 2; kk++) for (int jj = 0; jj < 2; jj++) for (int ii = 0; ii < 2; ii++)
+#pragma unroll
+  for (int q = 0; q < 8; q++)
   {
-    double c = cf[ii + jj * 2 + kk * 4];
+    const int ii = q & 1, jj = (q >> 1) & 1, kk = q >> 2;
+    double c = cf[q];
     if (fabs(c) > 1.e-10) { nb++; indNonZero = dind + ii + jj * ni + kk * ninj; coefNonZero = c; }
   }
   if (nb == 1) { type = 1; dind = indNonZero; cf[0] = coefNonZero; }
@@ -928,6 +1227,59 @@ CX_D void interp_o2_receptor(double x, double y, double z, int nz, const ZoneVie
     if (vol < best + CX_EPS_GEOM)
     {
       best = vol; o.type = 2; o.dind = tind; o.noblk = noz + 1;
+      for (int i = 0; i < 8; i++) o.cf[i] = tcf[i];
+    }
+  }
+  if (o.noblk > 0) collapse_type2(zones[o.noblk - 1], o.type, o.dind, o.cf);
+}
+
+// interp_o2_receptor with the search state in scratch (the version the kernels run)
+CX_D void interp_o2_receptor_s(double x, double y, double z, int nz, const ZoneView* zones, int nature, int penalty,
+                               RcvOut& o, const Scratch& S, SearchStats* st)
+{
+  double best = CX_MAXF;
+  o.noblk = 0; o.type = 0; o.dind = -1;
+  double tcf[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { o.cf[i] = 0.; tcf[i] = 0.; }
+  for (int noz = 0; noz < nz; noz++)
+  {
+    const ZoneView& Z = zones[noz];
+    int ic, jc, kc;
+    if (Z.nk == 1)
+    {
+      if (fabs(z - Z.bbox[2]) > CX_EPS_GEOM) continue;
+      int found2 = search_interp_cell_s(Z, x, y, z, ic, jc, kc, tcf, S, st);
+      if (found2 < 1) continue;
+      ic -= 1; jc -= 1;
+      int isBorder2 = (ic == 0 || ic == Z.ni - 2 || jc == 0 || jc == Z.nj - 2);
+      int tind2 = ic + jc * Z.ni;
+#pragma unroll
+      for (int i = 0; i < 4; i++) { tcf[i] += tcf[i + 4]; tcf[i + 4] = 0.; }
+      if (!celln_valid_o2_2d(Z, ic, jc, tcf, nature)) continue;
+      double vol2 = cell_area_2d(Z, tind2);
+      if (penalty == 1 && isBorder2 == 1) vol2 += 1.e3;
+      if (vol2 < best + CX_EPS_GEOM)
+      {
+        best = vol2; o.type = 22; o.dind = tind2; o.noblk = noz + 1;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { o.cf[i] = tcf[i] + tcf[i + 4]; o.cf[i + 4] = 0.; }
+      }
+      continue;
+    }
+    int found = (Z.topo == 0) ? cart_search_o2(Z, x, y, z, ic, jc, kc, tcf)
+                              : search_interp_cell_s(Z, x, y, z, ic, jc, kc, tcf, S, st);
+    if (found < 1) continue;
+    ic -= 1; jc -= 1; kc -= 1;
+    int isBorder = (ic == 0 || ic == Z.ni - 2 || jc == 0 || jc == Z.nj - 2 || kc == 0 || kc == Z.nk - 2);
+    int tind = ic + jc * Z.ni + kc * Z.ni * Z.nj;
+    if (!celln_valid_o2(Z, ic, jc, kc, tcf, nature)) continue;
+    double vol = cell_volume(Z, tind);
+    if (penalty == 1 && isBorder == 1) vol += 1.e3;
+    if (vol < best + CX_EPS_GEOM)
+    {
+      best = vol; o.type = 2; o.dind = tind; o.noblk = noz + 1;
+#pragma unroll
       for (int i = 0; i < 8; i++) o.cf[i] = tcf[i];
     }
   }

@@ -25,6 +25,7 @@
 // (ipiv(k).EQ.0 filter) nor by the RHS update, so the pivot sequence and every
 // value that reaches (ksi,eta,zeta) are bit-identical while the work halves.
 #include "cx_internal.h"
+#include <algorithm>
 
 using namespace cx;
 
@@ -54,9 +55,15 @@ __global__ void k_lag_init(LagState S)
 
 __global__ void __launch_bounds__(128)
 k_lag_search(LagState S, const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr,
-             const ZoneView* __restrict__ zones, int noz, int order, unsigned long long* __restrict__ flags,
+             const ZoneView* __restrict__ zones, int noz, int order, unsigned long long* __restrict__ flags, int cap,
              unsigned long long* gstats)
 {
+  // search scratch in dynamic shared memory (cx_core.cuh: Scratch), column = thread
+  extern __shared__ __align__(16) double lag_sm[];
+  Scratch SC;
+  SC.vtx = lag_sm + threadIdx.x;
+  SC.stk = reinterpret_cast<int*>(lag_sm + 24 * 128) + threadIdx.x;
+  SC.ss = 128; SC.cap = cap;
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= S.n) return;
   const ZoneView& Z = zones[noz];
@@ -91,7 +98,7 @@ k_lag_search(LagState S, const double* __restrict__ xr, const double* __restrict
     }
     else
     {
-      found = search_interp_cell(Z, xr[r], yr[r], zr[r], ic, jc, kc, cf, &st);
+      found = search_interp_cell_s(Z, xr[r], yr[r], zr[r], ic, jc, kc, cf, SC, &st);
       if (found == 1)
         for (int k = 0; k < 8; k++) S.tcf[(size_t)k * S.n + r] = cf[k];
     }
@@ -719,7 +726,11 @@ int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_xr, cons
   }
   for (int noz = 0; noz < nz; noz++)
   {
-    k_lag_search<<<cx_grid(n, TB), TB, 0, s>>>(S, d_xr, d_yr, d_zr, d_zones, noz, order, d_f, d_stats);
+    const int cap = std::max(4, h_zones[noz].depth + 2);
+    const size_t smsearch = (size_t)TB * (24 * sizeof(double) + (size_t)cap * sizeof(int));
+    if (smsearch > 200 * 1024) { cx_set_error("setInterpData: ADT depth %d needs %zu bytes of shared memory per CTA", cap - 2, smsearch); return -1; }
+    CX_CUDA(cudaFuncSetAttribute(k_lag_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smsearch));
+    k_lag_search<<<cx_grid(n, TB), TB, smsearch, s>>>(S, d_xr, d_yr, d_zr, d_zones, noz, order, d_f, cap, d_stats);
     ctx->launches++;
     unsigned long long tot = 0;
     CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, n, &tot));

@@ -11,6 +11,8 @@
 // flag/scan/scatter so every zone's entries come out in ascending receptor
 // order exactly like the reference's static-schedule chunk concatenation.
 #include "cx_internal.h"
+#include <stdlib.h>
+#include <algorithm>
 
 using namespace cx;
 
@@ -34,22 +36,28 @@ __device__ __forceinline__ void warp_add_stats(unsigned long long* g, const Sear
   if ((threadIdx.x & 31) == 0) { atomicAdd(&g[0], a); atomicAdd(&g[1], b); atomicAdd(&g[2], c); }
 }
 
-#ifndef CX_SEARCH_MINB
-#define CX_SEARCH_MINB 8
-#endif
-// Order-2 interpolation, all donor zones fused in one launch.
-__global__ void __launch_bounds__(128, CX_SEARCH_MINB)
+// Order-2 interpolation, all donor zones fused in one launch.  Per-thread scratch in dynamic shared memory
+// (cx_core.cuh: Scratch): 24 doubles of cell vertices + `cap` stack entries per thread, column = thread.
+// blockDim.x = CX_SEARCH_TB (64 or 128); shared memory, not registers, bounds the residency.
+template <int TB>
+__global__ void __launch_bounds__(TB, 512 / TB)
 k_interp_o2(int n, const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr,
-            int nz, const ZoneView* __restrict__ zones, int nature, int penalty, RcvTable T,
+            int nz, const ZoneView* __restrict__ zones, int nature, int penalty, RcvTable T, int cap,
             unsigned long long* gstats)
 {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ __align__(16) double o2_sm[];
+  Scratch S;
+  S.vtx = o2_sm + threadIdx.x;
+  S.stk = reinterpret_cast<int*>(o2_sm + 24 * TB) + threadIdx.x;
+  S.ss = TB; S.cap = cap;
+  int r = blockIdx.x * TB + threadIdx.x;
   SearchStats st; st.nvisit = 0; st.ncand = 0; st.ntet = 0;
   if (r < n)
   {
     RcvOut o;
-    interp_o2_receptor(xr[r], yr[r], zr[r], nz, zones, nature, penalty, o, &st);
+    interp_o2_receptor_s(xr[r], yr[r], zr[r], nz, zones, nature, penalty, o, S, &st);
     T.noblk[r] = o.noblk; T.type[r] = o.type; T.dind[r] = o.dind; T.isext[r] = 0;
+#pragma unroll
     for (int i = 0; i < 8; i++) T.cf[(size_t)i * n + r] = o.cf[i];
   }
   if (gstats) warp_add_stats(gstats, st);
@@ -331,7 +339,22 @@ int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, co
   CX_CUDA(cudaEventRecord(ctx->ev0, s));
   if (order == 2)
   {
-    k_interp_o2<<<cx_grid(n, TB), TB, 0, s>>>(n, d_xr, d_yr, d_zr, nz, d_zones, nature, penalty, T, d_stats);
+    int cap = 4;
+    for (int z = 0; z < nz; z++) if (h_zones[z].topo != 0) cap = std::max(cap, h_zones[z].depth + 2);
+    static int tbs = 0;        // CX_SEARCH_TB: threads per CTA of the search kernel (64 or 128)
+    if (!tbs) { const char* e = getenv("CX_SEARCH_TB"); tbs = e ? atoi(e) : 128; if (tbs != 64 && tbs != 128) tbs = 128; }
+    const size_t smb = (size_t)tbs * (24 * sizeof(double) + (size_t)cap * sizeof(int));
+    if (smb > 200 * 1024) { cx_set_error("setInterpData: ADT depth %d needs %zu bytes of shared memory per CTA", cap - 2, smb); return -1; }
+    if (tbs == 64)
+    {
+      CX_CUDA(cudaFuncSetAttribute(k_interp_o2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+      k_interp_o2<64><<<cx_grid(n, 64), 64, smb, s>>>(n, d_xr, d_yr, d_zr, nz, d_zones, nature, penalty, T, cap, d_stats);
+    }
+    else
+    {
+      CX_CUDA(cudaFuncSetAttribute(k_interp_o2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+      k_interp_o2<128><<<cx_grid(n, 128), 128, smb, s>>>(n, d_xr, d_yr, d_zr, nz, d_zones, nature, penalty, T, cap, d_stats);
+    }
     ctx->launches++;
   }
   else

@@ -121,6 +121,9 @@ int emu_candidates(void* h, double x, double y, double z, double alphaTol, int* 
   return n;
 }
 
+static int use_scratch = 1;
+void emu_use_scratch(int on) { use_scratch = on; }
+
 void emu_set_interp_data(int n, const double* xr, const double* yr, const double* zr, int nz, void** zones,
                          int nature, int penalty, int extrap, int* noblk, int* type, int* dind, int* isext,
                          double* cf, long long* stats)
@@ -131,7 +134,14 @@ void emu_set_interp_data(int n, const double* xr, const double* yr, const double
   for (int r = 0; r < n; r++)
   {
     RcvOut o;
-    interp_o2_receptor(xr[r], yr[r], zr[r], nz, V.data(), nature, penalty, o, &st);
+    if (use_scratch)
+    {
+      // the version the kernels run (search state in a Scratch area; here plain arrays, stride 1)
+      int stk[CX_STACK]; double vtx[24];
+      Scratch S; S.stk = stk; S.vtx = vtx; S.ss = 1; S.cap = CX_STACK;
+      interp_o2_receptor_s(xr[r], yr[r], zr[r], nz, V.data(), nature, penalty, o, S, &st);
+    }
+    else interp_o2_receptor(xr[r], yr[r], zr[r], nz, V.data(), nature, penalty, o, &st);
     isext[r] = 0;
     if (o.noblk == 0 && extrap == 1)
     {
