@@ -718,6 +718,16 @@ def _setInterpTransfers(aR, topTreeD, variables=[], cellNVariable='',
                         bcType=0, varType=2, storage=-1, compact=0, compactD=0,
                         Gamma=1.4, Cv=1.7857142857142865, MuS=1.e-08, Cs=0.3831337844872463, Ts=1.0, ctx=None):
     ctx = ctx or _lib.default_context()
+    # every subregion of a donor zone reads the same donor arrays: one upload per array for the whole call
+    ctx.batch_begin()
+    try:
+        _setInterpTransfersBody(ctx, aR, topTreeD, variables, cellNVariable, varType, storage, compact)
+    finally:
+        ctx.batch_end()
+    return None
+
+
+def _setInterpTransfersBody(ctx, aR, topTreeD, variables, cellNVariable, varType, storage, compact):
     # direct storage: data held by the receptor zones (OversetData.py:1968-2033)
     if storage < 1:
         znd = {z[0]: z for z in Internal.getZones(topTreeD)}
@@ -737,6 +747,7 @@ def _setInterpTransfers(aR, topTreeD, variables=[], cellNVariable='',
     if storage != 0:
         znr = {z[0]: z for z in Internal.getZones(aR)}
         for zd in Internal.getZones(topTreeD):
+            ctx.batch_flush()          # the previous donor zone's fields are not read again
             for s in Internal.getNodesFromType1(zd, 'ZoneSubRegion_t'):
                 sname = s[0][0:2]
                 if sname == 'ID' and variables is not None:
@@ -774,8 +785,18 @@ def _setInterpTransfersD(topTreeD, variables=[], cellNVariable='',
     FlowSolution, or all of them but cellNVariable for an empty list)."""
     if backend is None:
         ctx = ctx or _lib.default_context()
+        ctx.batch_begin()          # a donor zone's fields are uploaded once for all its subregions
+        try:
+            return _setInterpTransfersDBody(topTreeD, variables, cellNVariable, varType, compact, ctx, backend)
+        finally:
+            ctx.batch_end()
+    return _setInterpTransfersDBody(topTreeD, variables, cellNVariable, varType, compact, ctx, backend)
+
+
+def _setInterpTransfersDBody(topTreeD, variables, cellNVariable, varType, compact, ctx, backend):
     infos = []
     for zd in Internal.getZones(topTreeD):
+        if backend is None: ctx.batch_flush()
         for s in Internal.getNodesFromType1(zd, 'ZoneSubRegion_t'):
             if s[0][0:2] == 'ID' and variables is not None:
                 idn = Internal.getNodeFromName1(s, 'InterpolantsDonor')

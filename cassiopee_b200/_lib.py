@@ -66,6 +66,9 @@ _SIGS = {
     "cx_transfer": (_i, [_vp, _i, _vp, _vp]),
     "cx_transferD": (_i, [_vp, _i, _vp, _vp]),
     "cx_transfer_rot": (_i, [_vp, _i, _vp, _vp, _i, _d, _d, _i, _vp]),
+    "cx_batch_begin": (_i, [_vp, _ll]),
+    "cx_batch_flush": (_i, [_vp]),
+    "cx_batch_end": (_i, [_vp, _vp]),
     "cx_rotate_dev": (_i, [_vp, _i, _d, _d, _vp, _vp, _vp]),
     "cx_transfer_celln": (_i, [_vp, _vp, _vp]),
     "cx_transfer_dev": (_i, [_vp, _i, _vp, _vp]),
@@ -187,6 +190,18 @@ class Context:
         ms = ctypes.c_float()
         check(lib().cx_event_elapsed_ms(self.h, ctypes.byref(ms)))
         return float(ms.value)
+
+    def batch_begin(self, budget_bytes=0):
+        """Open a batch of host-pointer transfers: donor fields are uploaded once per host array (cx_batch_begin)."""
+        check(lib().cx_batch_begin(self.h, int(budget_bytes)))
+
+    def batch_flush(self):
+        check(lib().cx_batch_flush(self.h))
+
+    def batch_end(self):
+        n = _ll()
+        check(lib().cx_batch_end(self.h, ctypes.byref(n)))
+        return n.value
 
     def flush_l2(self):
         check(lib().cx_flush_l2(self.h))

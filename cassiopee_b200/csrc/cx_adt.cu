@@ -30,11 +30,12 @@ struct BuildScratch { int* actA; int* actB; };
 
 __global__ void k_cell_keys(int ni, int nj, int nk, const double* __restrict__ x, const double* __restrict__ y,
                             const double* __restrict__ z, double* __restrict__ keys, AdtNode* __restrict__ nodes,
-                            int ncells, double zmin2d, double zmax2d)
+                            int ncells, ZoneBox zb, double zmin2d, double zmax2d)
 {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncells) return;
-  adt_cell_keys(ni, nj, nk, x, y, z, c, ncells, keys, nodes, zmin2d, zmax2d);
+  const double zbbox[6] = {zb.lo[0], zb.lo[1], zb.lo[2], zb.hi[3], zb.hi[4], zb.hi[5]};
+  adt_cell_keys(ni, nj, nk, x, y, z, c, ncells, keys, nodes, zbbox, zmin2d, zmax2d);
 }
 
 __global__ void k_root(AdtNode* nodes, ZoneBox zb)
@@ -160,7 +161,7 @@ int cx_build_adt(cx_zone* z)
   CX_CUDA(cudaEventRecord(ctx->ev0, s));
   const int TB = 256;
   k_cell_keys<<<cx_grid(n, TB), TB, 0, s>>>(z->ni, z->nj, z->nk, z->d_x, z->d_y, z->d_z, B.keys, z->d_nodes, ncells,
-                                            z->bbox[2], z->bbox[5]);
+                                            zb, z->bbox[2], z->bbox[5]);
   k_root<<<1, 1, 0, s>>>(z->d_nodes, zb);
   ctx->launches += 2;
   int nact = ncells - 1;

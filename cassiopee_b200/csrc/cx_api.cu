@@ -1,5 +1,6 @@
 // cx_api.cu — C ABI of libcassiopee_b200.so (see include/cassiopee_b200.h).
 #include "cx_internal.h"
+#include <unordered_map>
 #include "../../include/cassiopee_b200.h"
 #include <stdarg.h>
 #include <stdlib.h>
@@ -166,6 +167,7 @@ int cx_ctx_create(int device, cx_ctx** out)
   return 0;
 }
 
+static void cx_ctx_free_transfer_scratch(cx_ctx* c);
 int cx_ctx_destroy(cx_ctx* c)
 {
   if (!c) return 0;
@@ -173,6 +175,7 @@ int cx_ctx_destroy(cx_ctx* c)
   cudaStreamSynchronize(c->stream);
   if (c->nccl) cx_comm_destroy(c);
   if (c->pinned) cudaFreeHost(c->pinned);
+  cx_ctx_free_transfer_scratch(c);
   for (int i = 0; i < 2; i++) if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
   cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
@@ -401,6 +404,7 @@ static ZoneView make_view(const cx_zone* zn)
     V.h[i] = zn->h[i];
     V.hinv[i] = zn->topo == 0 ? 1.0 / zn->h[i] : 0.;     // InterpCart.cpp:51-56
     V.hs2[i] = 0.5 * zn->h[i];
+    quant_params(zn->bbox, i, V.qorg[i], V.qscl[i]);
   }
   return V;
 }
@@ -571,8 +575,6 @@ int cx_result_destroy(cx_result* R)
 struct cx_plan_full {
   cx_plan P;
   // scratch for the host-pointer entry points
-  double* d_fields; size_t fields_cap;
-  double* d_dense; size_t dense_cap;
   double* h_dense; size_t hdense_cap;   // pinned
   std::vector<int> h_rcv;               // original-order receptor indices (host scatter)
   bool rcv_contiguous;                  // h_rcv[e] == h_rcv[0] + e
@@ -584,7 +586,7 @@ int cx_plan_create(cx_ctx* c, int imd, int jmd, int kmd, long long nptsR, int n,
 {
   CX_CUDA(cudaSetDevice(c->device));
   cx_plan_full* F = new cx_plan_full;
-  F->d_fields = nullptr; F->fields_cap = 0; F->d_dense = nullptr; F->dense_cap = 0; F->h_dense = nullptr; F->hdense_cap = 0;
+  F->h_dense = nullptr; F->hdense_cap = 0;
   int rc = cx_plan_build(c, imd, jmd, (long long)imd * jmd * kmd, nptsR, n, donor, rcv, type, coefs, ncoefs, &F->P);
   if (rc != 0) { cx_plan_destroy(&F->P); return rc; }
   F->h_rcv.assign(rcv, rcv + n);
@@ -610,6 +612,75 @@ static int ensure(double** p, size_t* cap, size_t need, bool pinned)
 // duplex) and the total tends to max(H2D, D2H) instead of their sum.  The per-variable launches re-read the
 // plan's coefficients nvars times from HBM, which costs ~0.25 ms per variable at C2a size against ~2.5 ms of bus
 // time per variable.
+// Donor fields uploaded during a batch of host-pointer transfers (one _setInterpTransfers call over a tree): the k
+// subregions of a donor zone read the same host arrays, which then cross the bus once instead of k times.  A host
+// array a transfer writes into (receptor field) is dropped from the cache, so a later subregion that reads it as a
+// donor field sees the updated values, like the reference's sequential loop over the subregions.
+struct cx_field_cache {
+  struct Buf { double* d; size_t bytes; };
+  std::unordered_map<const void*, Buf> map;
+  size_t bytes = 0, budget = (size_t)8 << 30;
+  long long uploads = 0;
+  bool on = false;
+};
+
+static int field_cache_clear(cx_ctx* c)
+{
+  cx_field_cache* FC = (cx_field_cache*)c->fcache;
+  if (!FC) return 0;
+  for (auto& kv : FC->map) cudaFreeAsync(kv.second.d, c->stream);
+  FC->map.clear(); FC->bytes = 0;
+  return 0;
+}
+
+static void field_cache_written(cx_ctx* c, int nvars, double* const* fieldR)
+{
+  cx_field_cache* FC = (cx_field_cache*)c->fcache;
+  if (!FC || !FC->on || FC->map.empty()) return;
+  for (int v = 0; v < nvars; v++)
+  {
+    auto it = FC->map.find(fieldR[v]);
+    if (it != FC->map.end()) { cudaFreeAsync(it->second.d, c->stream); FC->bytes -= it->second.bytes; FC->map.erase(it); }
+  }
+}
+
+int cx_batch_begin(cx_ctx* c, long long budget_bytes)
+{
+  CX_CUDA(cudaSetDevice(c->device));
+  if (!c->fcache) c->fcache = new cx_field_cache;
+  cx_field_cache* FC = (cx_field_cache*)c->fcache;
+  CX_CHECK(field_cache_clear(c));
+  if (budget_bytes > 0) FC->budget = (size_t)budget_bytes;
+  FC->on = true; FC->uploads = 0;
+  return 0;
+}
+
+// drop the cached fields (called between donor zones: their fields are not read again); the batch stays open
+int cx_batch_flush(cx_ctx* c)
+{
+  CX_CUDA(cudaSetDevice(c->device));
+  return field_cache_clear(c);
+}
+
+int cx_batch_end(cx_ctx* c, long long* uploads)
+{
+  CX_CUDA(cudaSetDevice(c->device));
+  cx_field_cache* FC = (cx_field_cache*)c->fcache;
+  if (uploads) *uploads = FC ? FC->uploads : 0;
+  CX_CHECK(field_cache_clear(c));
+  if (FC) FC->on = false;
+  return 0;
+}
+
+static void cx_ctx_free_transfer_scratch(cx_ctx* c)
+{
+  field_cache_clear(c);
+  delete (cx_field_cache*)c->fcache; c->fcache = nullptr;
+  if (c->d_tfields) cudaFree(c->d_tfields);
+  if (c->d_tdense) cudaFree(c->d_tdense);
+  c->d_tfields = c->d_tdense = nullptr; c->tfields_cap = c->tdense_cap = 0;
+}
+
 static int pipeline_events(cx_plan_full* F, int nvars)
 {
   while ((int)F->evk.size() < nvars)
@@ -633,8 +704,13 @@ static int transfer_pipeline(cx_plan_full* F, int nvars, const double* const* fi
   cx_plan* P = &F->P; cx_ctx* c = P->ctx;
   CX_CUDA(cudaSetDevice(c->device));
   const size_t per = (size_t)P->nptsD, n = (size_t)P->n;
-  CX_CHECK(ensure(&F->d_fields, &F->fields_cap, sizeof(double) * per * nvars, false));
-  CX_CHECK(ensure(&F->d_dense, &F->dense_cap, sizeof(double) * n * nvars, false));
+  // scratch of the context, not of the plan (a tree with k subregions per donor zone would otherwise hold k
+  // copies of the zone's fields); calls are synchronous, so one buffer serves every plan
+  cx_field_cache* FC = (cx_field_cache*)c->fcache;
+  const bool batch = FC && FC->on;
+  if (!batch) CX_CHECK(ensure(&c->d_tfields, &c->tfields_cap, sizeof(double) * per * nvars, false));
+  CX_CHECK(ensure(&c->d_tdense, &c->tdense_cap, sizeof(double) * n * nvars, false));
+  double* const d_dense = c->d_tdense;
   CX_CHECK(pipeline_events(F, nvars));
   cudaStream_t sa = c->stream, sb = c->comm_stream;
   std::vector<char> hold(nvars, 0);        // downloads deferred until the rotation has run
@@ -646,14 +722,34 @@ static int transfer_pipeline(cx_plan_full* F, int nvars, const double* const* fi
     }
   for (int v = 0; v < nvars; v++)
   {
-    double* dv = F->d_fields + per * v;
+    double* dv = nullptr;
+    if (batch)
+    {
+      // donor field already on the device from an earlier subregion of the same batch?
+      auto it = FC->map.find(fieldD[v]);
+      if (it != FC->map.end() && it->second.bytes == sizeof(double) * per) dv = it->second.d;
+      else
+      {
+        if (it != FC->map.end()) { cudaFreeAsync(it->second.d, sa); FC->bytes -= it->second.bytes; FC->map.erase(it); }
+        if (FC->bytes + sizeof(double) * per > FC->budget) CX_CHECK(field_cache_clear(c));
+        CX_MALLOC(dv, sizeof(double) * per, sa);
+        CX_CUDA(cudaMemcpyAsync(dv, fieldD[v], sizeof(double) * per, cudaMemcpyHostToDevice, sa));
+        FC->map[fieldD[v]] = cx_field_cache::Buf{dv, sizeof(double) * per};
+        FC->bytes += sizeof(double) * per;
+        FC->uploads++;
+      }
+    }
+    else
+    {
+      dv = c->d_tfields + per * v;
+      CX_CUDA(cudaMemcpyAsync(dv, fieldD[v], sizeof(double) * per, cudaMemcpyHostToDevice, sa));
+    }
     const double* dvp = dv;
-    CX_CUDA(cudaMemcpyAsync(dv, fieldD[v], sizeof(double) * per, cudaMemcpyHostToDevice, sa));
-    CX_CHECK(cx_plan_launch(P, 1, &dvp, nullptr, F->d_dense + n * v, (long long)n, 1, sa));
+    CX_CHECK(cx_plan_launch(P, 1, &dvp, nullptr, d_dense + n * v, (long long)n, 1, sa));
     if (hold[v]) continue;
     CX_CUDA(cudaEventRecord(F->evk[v], sa));
     CX_CUDA(cudaStreamWaitEvent(sb, F->evk[v], 0));
-    CX_CUDA(cudaMemcpyAsync(dst[v], F->d_dense + n * v, sizeof(double) * n, cudaMemcpyDeviceToHost, sb));
+    CX_CUDA(cudaMemcpyAsync(dst[v], d_dense + n * v, sizeof(double) * n, cudaMemcpyDeviceToHost, sb));
     CX_CUDA(cudaEventRecord(F->evd[v], sb));
   }
   if (rot && rot->dirR != 0)
@@ -661,15 +757,15 @@ static int transfer_pipeline(cx_plan_full* F, int nvars, const double* const* fi
     for (int t = 0; t < rot->ntrip; t++)
     {
       const int* tr = rot->trip + 3 * t;
-      CX_CHECK(cx_plan_rotate_on(P, rot->dirR, rot->ct, rot->st, F->d_dense + n * tr[0], F->d_dense + n * tr[1],
-                                 F->d_dense + n * tr[2], 1, sa));
+      CX_CHECK(cx_plan_rotate_on(P, rot->dirR, rot->ct, rot->st, d_dense + n * tr[0], d_dense + n * tr[1],
+                                 d_dense + n * tr[2], 1, sa));
     }
     for (int v = 0; v < nvars; v++)
     {
       if (!hold[v]) continue;
       CX_CUDA(cudaEventRecord(F->evk[v], sa));
       CX_CUDA(cudaStreamWaitEvent(sb, F->evk[v], 0));
-      CX_CUDA(cudaMemcpyAsync(dst[v], F->d_dense + n * v, sizeof(double) * n, cudaMemcpyDeviceToHost, sb));
+      CX_CUDA(cudaMemcpyAsync(dst[v], d_dense + n * v, sizeof(double) * n, cudaMemcpyDeviceToHost, sb));
       CX_CUDA(cudaEventRecord(F->evd[v], sb));
     }
   }
@@ -726,6 +822,7 @@ static int transfer_host(cx_plan* P, int nvars, const double* const* fieldD, dou
     CX_CUDA(cudaStreamSynchronize(c->comm_stream));
     CX_CUDA(cudaStreamSynchronize(c->stream));
     CX_CUDA(cudaGetLastError());
+    field_cache_written(c, nvars, fieldR);
     return 0;
   }
   CX_CHECK(ensure(&F->h_dense, &F->hdense_cap, sizeof(double) * (size_t)n * nvars, true));
@@ -757,6 +854,7 @@ static int transfer_host(cx_plan* P, int nvars, const double* const* fieldD, dou
   CX_CUDA(cudaStreamSynchronize(c->comm_stream));
   CX_CUDA(cudaStreamSynchronize(c->stream));
   CX_CUDA(cudaGetLastError());
+  field_cache_written(c, nvars, fieldR);
   return 0;
 }
 
@@ -884,8 +982,6 @@ int cx_plan_destroy(cx_plan* P)
   cx_plan_full* F = (cx_plan_full*)P;
   for (auto& G : P->groups) { cudaFree(G.d_cf); if (G.d_tiles) cudaFree(G.d_tiles); }
   cudaFree(P->d_donor); cudaFree(P->d_rcv); cudaFree(P->d_pos); cudaFree(P->d_seq);
-  if (F->d_fields) cudaFree(F->d_fields);
-  if (F->d_dense) cudaFree(F->d_dense);
   if (F->h_dense) cudaFreeHost(F->h_dense);
   for (cudaEvent_t e : F->evk) cudaEventDestroy(e);
   for (cudaEvent_t e : F->evd) cudaEventDestroy(e);

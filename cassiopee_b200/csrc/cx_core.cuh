@@ -13,7 +13,7 @@
 //   extrapolation over all 24 tetrahedra         KCore/KCore/Interp/InterpData.cpp:699-947, InterpAdt.cpp:1069-1182
 //   order-2 zone result + cellN validity         KCore/KCore/Interp/Interp2.cpp:185-342, :84-177
 //   hexa volume for cross-zone selection         KCore/KCore/Metric/compVolOfStructCell.cpp:91-218
-// Design differences (B200-first): the ADT is a flat array of 80-byte nodes
+// Design differences (B200-first): the ADT is a flat array of 128-byte nodes
 // with the split thresholds of each node precomputed at build time, so the
 // query stack holds node ids only (4 B/level instead of the reference's
 // 13-double frames); the candidate std::list is never materialised — the DFS
@@ -47,15 +47,46 @@ namespace cx {
 #define CX_EPS_GEOM 1.e-8
 #define CX_MAXF 1.7976931348623157e308
 
-struct AdtNode {   // 128 B = one cache line
-  double bb[6];    // xmin,ymin,zmin,xmax,ymax,zmax of the cell
-  double sub[6];   // bounding box of all the cells stored in this node's subtree
+struct AdtNode {   // 128 B = one cache line; the first 64 bytes are all a traversal step reads at a non-candidate node
   double mid;      // descend left  iff a[dim] <= mid
   double rlo;      // descend right iff b[dim] >= rlo
   int left, right; // node ids (CX_NULL = none)
   int dim;         // depth % 6
+  // Bounding boxes quantised to 16 bits per coordinate on the zone's bounding box and rounded outwards
+  // (conservative; lo x,y,z then hi x,y,z): qb = this cell (pre-filter of the exact candidate test), ql / qr = the
+  // whole subtree of the left / right child, so that a query decides whether to descend into a child WITHOUT
+  // fetching the child
+  unsigned short qb[6], ql[6], qr[6];
+  // ---- second half: read for candidates only
+  double bb[6];    // xmin,ymin,zmin,xmax,ymax,zmax of the cell
   int ind;         // donor node index i + ni*j + ni*nj*k of the cell corner
+  unsigned short qs[6];   // this node's whole subtree (build only)
 };
+static_assert(sizeof(AdtNode) == 128, "AdtNode must stay one 128-byte line");
+
+// quantisation of coordinate d (0..2) on the zone bounding box: q = (v - org) * scl, the box maps to [250, 65250]
+#ifdef __CUDACC__
+#define CX_HD __host__ __device__ __forceinline__
+#else
+#define CX_HD static inline
+#endif
+CX_HD void quant_params(const double* bbox, int d, double& org, double& scl)
+{
+  double ext = bbox[d + 3] - bbox[d];
+  if (!(ext > 0.)) ext = 1.;
+  scl = 65000.0 / ext;
+  org = bbox[d] - 250.0 / scl;
+}
+CX_D unsigned short quant_lo(double v, double org, double scl)
+{ // two quanta of slack cover the 1e-8 inflation of the candidate test and every rounding of this formula
+  double t = floor((v - org) * scl) - 2.;
+  return (unsigned short)(t < 0. ? 0. : (t > 65535. ? 65535. : t));
+}
+CX_D unsigned short quant_hi(double v, double org, double scl)
+{
+  double t = ceil((v - org) * scl) + 2.;
+  return (unsigned short)(t < 0. ? 0. : (t > 65535. ? 65535. : t));
+}
 
 struct ZoneView {      // device view of one donor zone
   const double* x; const double* y; const double* z; const double* cellN;
@@ -68,6 +99,7 @@ struct ZoneView {      // device view of one donor zone
   // KCore/KCore/Interp/InterpCart.cpp:42-66): h = spacing, hinv = 1/h, hs2 = h/2; origin and end = bbox
   int topo;
   double h[3], hinv[3], hs2[3];
+  double qorg[3], qscl[3];   // quantisation of the subtree boxes (quant_params of bbox)
 };
 
 // double -> int conversion with x86 cvttsd2si semantics (out of range / NaN ->
@@ -92,7 +124,27 @@ struct AdtQuery {
   int stack[CX_STACK];
   int sp;
   int prune;            // 1: skip subtrees whose bounding box cannot hold a candidate (alphaTol == 0 only)
+  int tlo[3], thi[3];   // the point on the quantisation grid, one quantum of slack either side
 };
+
+// No node of a subtree can pass node_is_candidate (alphaTol = 0) when the point is outside the subtree box
+// inflated by 1e-8: fl(xmax_c + 1e-8) is monotone in xmax_c, so x < xmax_c + 1e-8 implies x < sub_xmax + 1e-8.
+// The quantised box contains that inflated box (quant_lo / quant_hi round outwards with slack), so skipping a
+// subtree whose quantised box misses the (equally slackened) quantised point leaves the reference's candidate
+// list and its order unchanged while cutting the visited nodes several-fold.  Codes clamped to 0 / 65535 stand for
+// "unbounded": a point that passed zone_reject lies inside the zone box, i.e. strictly between them.
+CX_D void quant_point(const ZoneView& Z, double x, double y, double z, int* tlo, int* thi)
+{
+  const double t0 = (x - Z.qorg[0]) * Z.qscl[0], t1 = (y - Z.qorg[1]) * Z.qscl[1], t2 = (z - Z.qorg[2]) * Z.qscl[2];
+  tlo[0] = (int)floor(t0) - 1; thi[0] = (int)ceil(t0) + 1;
+  tlo[1] = (int)floor(t1) - 1; thi[1] = (int)ceil(t1) + 1;
+  tlo[2] = (int)floor(t2) - 1; thi[2] = (int)ceil(t2) + 1;
+}
+CX_D bool qbox_may_hold(const unsigned short* q, const int* tlo, const int* thi)
+{
+  return thi[0] >= (int)q[0] && thi[1] >= (int)q[1] && thi[2] >= (int)q[2] &&
+         tlo[0] <= (int)q[3] && tlo[1] <= (int)q[4] && tlo[2] <= (int)q[5];
+}
 
 CX_D bool zone_reject(const ZoneView& Z, double x, double y, double z, double alphaTol)
 { // InterpAdt.cpp:662-672
@@ -117,18 +169,7 @@ CX_D void query_init(AdtQuery& q, const ZoneView& Z, double x, double y, double 
   q.px = x; q.py = y; q.pz = z; q.alphaTol = alphaTol;
   q.stack[0] = 0; q.sp = 1;
   q.prune = (alphaTol == 0.0) ? 1 : 0;
-}
-
-// No node of the subtree can pass node_is_candidate (alphaTol = 0) when the
-// point is outside the subtree box inflated by 1e-8: fl(xmax_c + 1e-8) is
-// monotone in xmax_c, so x < xmax_c + 1e-8 implies x < sub_xmax + 1e-8.
-// Skipping such a subtree therefore leaves the reference's candidate list
-// (and its order) unchanged while cutting the visited nodes several-fold.
-CX_D bool subtree_may_hold(const AdtNode& n, double x, double y, double z)
-{
-  return (x < n.sub[3] + CX_EPS_GEOM && x > n.sub[0] - CX_EPS_GEOM &&
-          y < n.sub[4] + CX_EPS_GEOM && y > n.sub[1] - CX_EPS_GEOM &&
-          z < n.sub[5] + CX_EPS_GEOM && z > n.sub[2] - CX_EPS_GEOM);
+  quant_point(Z, x, y, z, q.tlo, q.thi);
 }
 
 CX_D bool node_is_candidate(const AdtNode& n, double x, double y, double z, double alphaTol)
@@ -150,12 +191,12 @@ CX_D int query_next(AdtQuery& q, const AdtNode* __restrict__ nodes, int* nodeId,
     int id = q.stack[--q.sp];
     const AdtNode& n = nodes[id];
     (*nvisit)++;
-    if (q.prune && !subtree_may_hold(n, q.px, q.py, q.pz)) continue;
     int d = n.dim;
     // left pushed first, right second => right popped first (InterpAdt.cpp:768-925)
-    if (q.a[d] <= n.mid && n.left != CX_NULL) q.stack[q.sp++] = n.left;
-    if (q.b[d] >= n.rlo && n.right != CX_NULL) q.stack[q.sp++] = n.right;
-    if (node_is_candidate(n, q.px, q.py, q.pz, q.alphaTol)) { *nodeId = id; return n.ind; }
+    if (q.a[d] <= n.mid && n.left != CX_NULL && (!q.prune || qbox_may_hold(n.ql, q.tlo, q.thi))) q.stack[q.sp++] = n.left;
+    if (q.b[d] >= n.rlo && n.right != CX_NULL && (!q.prune || qbox_may_hold(n.qr, q.tlo, q.thi))) q.stack[q.sp++] = n.right;
+    if ((!q.prune || qbox_may_hold(n.qb, q.tlo, q.thi)) && node_is_candidate(n, q.px, q.py, q.pz, q.alphaTol))
+    { *nodeId = id; return n.ind; }
   }
   return -1;
 }
@@ -878,13 +919,14 @@ struct Scratch {
   int ss;        // stride between consecutive entries
   int cap;       // stack capacity (>= depth + 2 of every zone searched)
 };
-struct AdtQueryS { double px, py, pz, alphaTol; int sp; int prune; };
+struct AdtQueryS { double px, py, pz, alphaTol; int sp; int prune; int tlo[3], thi[3]; };
 
-CX_D void query_init_s(AdtQueryS& q, const Scratch& S, double x, double y, double z, double alphaTol)
+CX_D void query_init_s(AdtQueryS& q, const ZoneView& Z, const Scratch& S, double x, double y, double z, double alphaTol)
 {
   q.px = x; q.py = y; q.pz = z; q.alphaTol = alphaTol;
   S.stk[0] = 0; q.sp = 1;
   q.prune = (alphaTol == 0.0) ? 1 : 0;
+  quant_point(Z, x, y, z, q.tlo, q.thi);
 }
 
 // query_next with the stack in scratch and a[d], b[d] of InterpAdt.cpp:678-682 selected from registers
@@ -896,16 +938,19 @@ CX_D int query_next_s(AdtQueryS& q, const ZoneView& Z, const Scratch& S, int* no
     int id = S.stk[(--q.sp) * S.ss];
     const AdtNode& n = nodes[id];
     (*nvisit)++;
-    if (q.prune && !subtree_may_hold(n, q.px, q.py, q.pz)) continue;
     const int d = n.dim;
     const int dd = d < 3 ? d : d - 3;
     const double pv = dd == 0 ? q.px : (dd == 1 ? q.py : q.pz);
     const double av = d < 3 ? Z.bbox[dd] : pv;          // a = (xmin, ymin, zmin, x, y, z)
     const double bv = d < 3 ? pv : Z.bbox[dd + 3];      // b = (x, y, z, xmax, ymax, zmax)
     const int nl = n.left, nr = n.right;
-    if (av <= n.mid && nl != CX_NULL && q.sp < S.cap) S.stk[(q.sp++) * S.ss] = nl;
-    if (bv >= n.rlo && nr != CX_NULL && q.sp < S.cap) S.stk[(q.sp++) * S.ss] = nr;
-    if (node_is_candidate(n, q.px, q.py, q.pz, q.alphaTol)) { *nodeId = id; return n.ind; }
+    // a child whose subtree box (kept in this node) cannot hold a candidate is never fetched
+    if (av <= n.mid && nl != CX_NULL && q.sp < S.cap && (!q.prune || qbox_may_hold(n.ql, q.tlo, q.thi)))
+      S.stk[(q.sp++) * S.ss] = nl;
+    if (bv >= n.rlo && nr != CX_NULL && q.sp < S.cap && (!q.prune || qbox_may_hold(n.qr, q.tlo, q.thi)))
+      S.stk[(q.sp++) * S.ss] = nr;
+    if ((!q.prune || qbox_may_hold(n.qb, q.tlo, q.thi)) && node_is_candidate(n, q.px, q.py, q.pz, q.alphaTol))
+    { *nodeId = id; return n.ind; }
   }
   return -1;
 }
@@ -1092,7 +1137,7 @@ CX_D int search_interp_cell_s(const ZoneView& Z, double x, double y, double z, i
 {
   if (zone_reject(Z, x, y, z, 0.0)) return 0;
   AdtQueryS q;
-  query_init_s(q, S, x, y, z, 0.0);
+  query_init_s(q, Z, S, x, y, z, 0.0);
   int nid, nvisit = 0;
   int first = query_next_s(q, Z, S, &nid, &nvisit);
   if (st) { st->nvisit += nvisit; }
@@ -1133,7 +1178,7 @@ CX_D int search_interp_cell_s(const ZoneView& Z, double x, double y, double z, i
     erased = ind;
   }
   // ordered fallback over the whole candidate list (InterpAdt.cpp:1378-1397)
-  query_init_s(q, S, x, y, z, 0.0);
+  query_init_s(q, Z, S, x, y, z, 0.0);
   nvisit = 0;
   int c;
   while ((c = query_next_s(q, Z, S, &nid, &nvisit)) >= 0)
@@ -1407,7 +1452,7 @@ CX_D bool adt_resolve(const BuildView& B, int L, int c)
 // nk == 1 (InterpAdt.cpp:391-431): the 4 nodes of the quad give x,y; the z keys are the zone's plane and plane + 1
 // (zmin2d, zmax2d = _zmin, _zmax of the InterpAdt)
 CX_D void adt_cell_keys(int ni, int nj, int nk, const double* x, const double* y, const double* z, int c,
-                        int ncells, double* keys, AdtNode* nodes, double zmin2d = 0., double zmax2d = 0.)
+                        int ncells, double* keys, AdtNode* nodes, const double* zbbox, double zmin2d = 0., double zmax2d = 0.)
 {
   int nic = ni - 1, njc = nj - 1;
   int k = c / (nic * njc);
@@ -1444,12 +1489,20 @@ CX_D void adt_cell_keys(int ni, int nj, int nk, const double* x, const double* y
   keys[3 * n + c] = xmax; keys[4 * n + c] = ymax; keys[5 * n + c] = zmax;
   AdtNode nd;
   nd.bb[0] = xmin; nd.bb[1] = ymin; nd.bb[2] = zmin; nd.bb[3] = xmax; nd.bb[4] = ymax; nd.bb[5] = zmax;
-  for (int d = 0; d < 6; d++) nd.sub[d] = nd.bb[d];
+  for (int d = 0; d < 3; d++)
+  {
+    double org, scl;
+    quant_params(zbbox, d, org, scl);
+    nd.qs[d] = quant_lo(nd.bb[d] - CX_EPS_GEOM, org, scl); nd.qs[d + 3] = quant_hi(nd.bb[d + 3] + CX_EPS_GEOM, org, scl);
+    nd.qb[d] = nd.qs[d]; nd.qb[d + 3] = nd.qs[d + 3];
+    nd.ql[d] = 65535; nd.ql[d + 3] = 0; nd.qr[d] = 65535; nd.qr[d + 3] = 0;      // no child yet: empty boxes
+  }
   nd.mid = 0.; nd.rlo = 0.; nd.left = CX_NULL; nd.right = CX_NULL; nd.dim = 0; nd.ind = ind;
   nodes[c] = nd;
 }
 
-// bottom-up pass (deepest level first): subtree box = own box U children's boxes
+// bottom-up pass (deepest level first): subtree box = own box U children's boxes; the children's boxes are also
+// copied into the parent (ql, qr)
 CX_D void adt_subtree_box(AdtNode* nodes, int c)
 {
   AdtNode& n = nodes[c];
@@ -1458,10 +1511,12 @@ CX_D void adt_subtree_box(AdtNode* nodes, int c)
     int ch = side ? n.right : n.left;
     if (ch == CX_NULL) continue;
     const AdtNode& m = nodes[ch];
+    unsigned short* dst = side ? n.qr : n.ql;
     for (int d = 0; d < 3; d++)
     {
-      if (m.sub[d] < n.sub[d]) n.sub[d] = m.sub[d];
-      if (m.sub[d + 3] > n.sub[d + 3]) n.sub[d + 3] = m.sub[d + 3];
+      dst[d] = m.qs[d]; dst[d + 3] = m.qs[d + 3];
+      if (m.qs[d] < n.qs[d]) n.qs[d] = m.qs[d];
+      if (m.qs[d + 3] > n.qs[d + 3]) n.qs[d + 3] = m.qs[d + 3];
     }
   }
 }

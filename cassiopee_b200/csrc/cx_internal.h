@@ -40,6 +40,11 @@ struct cx_ctx {
   // last timed kernel durations (ms), written by entry points that time themselves
   float last_kernel_ms;
   void* nccl;   // cx_comm*
+  // host-pointer transfers (cx_api.cu): one grow-only device scratch shared by every plan of the context, and the
+  // donor fields uploaded during a batch of transfers (cx_batch_begin .. cx_batch_end), keyed by host pointer
+  double* d_tfields; size_t tfields_cap;
+  double* d_tdense; size_t tdense_cap;
+  void* fcache;   // cx_field_cache*
 };
 
 struct cx_zone {

@@ -61,7 +61,8 @@ int cx_pinned_free(void* hptr);
  * :284-433 buildStructAdt, :506-646 insert) and the hook of
  * Converter/Converter/hook.cpp:578-632 (C.createHook(z,'adt')).
  * x,y,z,cellN: host arrays of ni*nj*nk doubles, i fastest; cellN may be NULL
- * (all 1, as OversetData.py:1193 _addCellN__ does).  3-D zones only (nk>1). */
+ * (all 1, as OversetData.py:1193 _addCellN__ does).  nk == 1: 2-D zone in a z = constant plane (quads extruded by 1 in z,
+ * InterpAdt.cpp:391-431; results are type 22). */
 int cx_zone_create(cx_ctx* ctx, int ni, int nj, int nk, const double* x, const double* y, const double* z,
                    const double* cellN, cx_zone** out);
 /* Regular Cartesian donor, interpDataType=0: replaces new K_INTERP::InterpCart(ni,nj,nk,hi,hj,hk,x0,y0,z0)
@@ -75,7 +76,7 @@ int cx_zone_info(cx_zone* zone, double bbox[6], int* ncells, int* depth, float* 
 /* test/debug: candidate cells of one point in the reference's list order
  * (InterpAdt::getListOfCandidateCells, InterpAdt.cpp:658-929), device traversal */
 int cx_zone_candidates(cx_zone* zone, double x, double y, double z, double alphaTol, int* out, int cap, int* n);
-/* test/debug: copy the ADT replica to the host, 80-byte nodes (see cx_core.cuh AdtNode) */
+/* test/debug: copy the ADT replica to the host, 128-byte nodes (see cx_core.cuh AdtNode) */
 int cx_zone_export_adt(cx_zone* zone, void* nodes_out, size_t bytes);
 int cx_zone_destroy(cx_zone* zone);
 
@@ -86,7 +87,7 @@ int cx_zone_destroy(cx_zone* zone);
  * InterpAdt.cpp:658-1400, InterpData.cpp:56-947, Metric/compVolOfStructCell.cpp:91-218).
  * xr,yr,zr: receptor coordinates (host, nrcv doubles each), zones: ordered
  * donor list (order matters: commonTypesForExtrapAndInterp.h:16).
- * order 2|3|5, nature 0|1, penalty 0|1, extrap 0|1 as in the reference. */
+ * order 2|3|4|5 (setInterpData.cpp:624-652: types 2, 3, 44, 5), nature 0|1, penalty 0|1, extrap 0|1 as in the reference. */
 int cx_set_interp_data(cx_ctx* ctx, int nrcv, const double* xr, const double* yr, const double* zr, int nz,
                        cx_zone* const* zones, int order, int nature, int penalty, int extrap, cx_result** out);
 /* same with receptor coordinates already on the device */
@@ -140,6 +141,16 @@ int cx_transferD(cx_plan* plan, int nvars, const double* const* fieldD, double* 
  * the caller's libm like the reference.  dirR = 0: plain cx_transfer.  Host arrays. */
 int cx_transfer_rot(cx_plan* plan, int nvars, const double* const* fieldD, double* const* fieldR, int dirR,
                     double ctheta, double stheta, int ntrip, const int* trip);
+/* A batch of host-pointer transfers = one connector loop over the subregions of a tree (the body of
+ * OversetData._setInterpTransfers, Connector/Connector/OversetData.py:1962-2099, which hands the same donor-zone
+ * arrays to connector._setInterpTransfers once per ID_* subregion): between cx_batch_begin and cx_batch_end a donor
+ * field (identified by its host pointer) is uploaded once and reused by the following cx_transfer / cx_transferD /
+ * cx_transfer_rot calls; a host array a transfer writes into is dropped from the cache, so the sequential semantics of
+ * the reference loop are kept.  budget_bytes bounds the device memory held (0: default 8 GiB); cx_batch_flush drops
+ * the cached fields (between donor zones); cx_batch_end closes the batch and reports the uploads done. */
+int cx_batch_begin(cx_ctx* ctx, long long budget_bytes);
+int cx_batch_flush(cx_ctx* ctx);
+int cx_batch_end(cx_ctx* ctx, long long* uploads);
 /* the rotation alone, in place on device-resident receptor fields, at the plan's receptors */
 int cx_rotate_dev(cx_plan* plan, int dirR, double ctheta, double stheta, double* d_fx, double* d_fy, double* d_fz);
 /* strict cellN rule (commonCellNTransfersStrict.h; setInterpTransfers.cpp:452-467) */

@@ -21,7 +21,7 @@ struct EmuZone {
     V.ni = ni; V.nj = nj; V.nk = nk; V.ncells = ncells; V.depth = depth;
     for (int i = 0; i < 6; i++) V.bbox[i] = bbox[i];
     V.topo = topo;
-    for (int i = 0; i < 3; i++) { V.h[i] = h[i]; V.hinv[i] = topo == 0 ? 1.0 / h[i] : 0.; V.hs2[i] = 0.5 * h[i]; }
+    for (int i = 0; i < 3; i++) { V.h[i] = h[i]; V.hinv[i] = topo == 0 ? 1.0 / h[i] : 0.; V.hs2[i] = 0.5 * h[i]; quant_params(bbox, i, V.qorg[i], V.qscl[i]); }
     return V;
   }
 };
@@ -43,7 +43,7 @@ void* emu_zone_create(int ni, int nj, int nk, const double* x, const double* y, 
   BuildView B; B.keys = keys.data(); B.lo = lo.data(); B.hi = hi.data(); B.cur = cur.data(); B.br = br.data(); B.depth = dep.data();
   B.nodes = Z->nodes.data(); B.ncells = n;
   for (int d = 0; d < 6; d++) { B.zb.lo[d] = bbox[d % 3]; B.zb.hi[d] = bbox[3 + d % 3]; }
-  for (int c = 0; c < n; c++) adt_cell_keys(ni, nj, nk, x, y, z, c, n, B.keys, B.nodes, bbox[2], bbox[5]);
+  for (int c = 0; c < n; c++) adt_cell_keys(ni, nj, nk, x, y, z, c, n, B.keys, B.nodes, bbox, bbox[2], bbox[5]);
   freeze_node(B.nodes[0], 0, B.zb.lo[0], B.zb.hi[0]);
   std::vector<int> act, next;
   for (int c = 1; c < n; c++) act.push_back(c);

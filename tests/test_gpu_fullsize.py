@@ -76,10 +76,11 @@ def test_c1_fullsize_bit_exact_vs_reference(ctx, variant):
     t0 = time.perf_counter()
     for order in (2, 3, 5):
         st = 1 if order < 5 else 6          # order 5 costs the oracle 0.1 ms per receptor: every 6th receptor (39.7 k)
-        got = _lib.set_interp_data(ctx, Bc.x[::st], Bc.y[::st], Bc.z[::st], [ga], order, 1, 1, 1).fetch()
-        ref = O.set_interp_data(Bc.x[::st], Bc.y[::st], Bc.z[::st], [oa], order, 1, 1, 1)
+        px, py, pz = [np.ascontiguousarray(a[::st]) for a in (Bc.x, Bc.y, Bc.z)]
+        got = _lib.set_interp_data(ctx, px, py, pz, [ga], order, 1, 1, 1).fetch()
+        ref = O.set_interp_data(px, py, pz, [oa], order, 1, 1, 1)
         _assert_same(got, ref, "C1%s B<-A order %d" % (variant, order))
-        assert got[0][0].size == Bc.x[::st].size
+        assert got[0][0].size == px.size
     got = _lib.set_interp_data(ctx, Ac.x, Ac.y, Ac.z, [gb], 2, 1, 1, 1).fetch()
     ref = O.set_interp_data(Ac.x, Ac.y, Ac.z, [ob], 2, 1, 1, 1)
     _assert_same(got, ref, "C1%s A<-B order 2" % variant)

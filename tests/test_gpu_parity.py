@@ -780,3 +780,58 @@ def test_transfer_box_layout(ctx, shape, monkeypatch):
         for v in range(nvars):
             got = np.full(nR, -7.); got[srt] = d2[v]
             assert np.array_equal(got, fRo[v])
+
+
+def test_set_interp_transfers_batch_keeps_sequential_semantics(ctx):
+    """_setInterpTransfers uploads every donor array once per call (cx_batch_begin/end).  Three node-located zones in
+    ONE tree (donor tree == receptor tree): receptor fields are donor fields of the next subregions, so the loop is
+    sequential like the reference's (a subregion reads what the previous ones wrote).  Checked against the reference
+    loops applied in the same subregion order, and the upload count is the number of (zone, variable) arrays + the
+    re-uploads forced by the writes, not subregions x variables."""
+    import cassiopee_b200.Generator as G
+    import cassiopee_b200.Converter as C
+    import cassiopee_b200.Internal as Internal
+    import cassiopee_b200.Connector.PyTree as X
+    from oracle import oracle as O
+    h = 0.05
+    za = G.cart((0, 0, 0), (h, h, h), (21, 17, 13), name='A')
+    zb = G.cart((0.31, 0.12, 0.07), (0.9 * h, 0.9 * h, 0.9 * h), (19, 15, 11), name='B')
+    zc = G.cart((0.52, 0.22, 0.11), (1.1 * h, 1.1 * h, 1.1 * h), (15, 13, 9), name='C')
+    t = C.newPyTree(['Base', za, zb, zc])
+    names = ['Density', 'MomentumX', 'EnergyStagnationDensity']
+    rng = np.random.default_rng(5)
+    for z in Internal.getZones(t):
+        shp = C.fieldShape(z, 'nodes')
+        for v in names:
+            C._initVars(z, v, np.asfortranarray(rng.standard_normal(shp)))
+        c = np.ones(shp, order='F')
+        c[rng.random(shp) < 0.3] = 2.
+        C._initVars(z, 'cellN', c)
+    t = X.setInterpData(t, t, order=2, nature=0, penalty=0, extrap=1, loc='nodes', storage='inverse', sameName=1,
+                        itype='chimera', verbose=0)
+    before = {(z[0], v): np.array(C.getFieldArray(z, v), order='F', copy=True) for z in Internal.getZones(t) for v in names}
+    nsub = sum(len([s for s in Internal.getNodesFromType1(z, 'ZoneSubRegion_t') if s[0].startswith('ID_')])
+               for z in Internal.getZones(t))
+    assert nsub >= 4
+    l0 = ctx.launches()
+    t2 = X.setInterpTransfers(t, t, variables=names, storage=1)
+    # reference loops, same order: donor zones in tree order, their subregions in node order (OversetData.py:2036-2098)
+    cur = {k: v.copy(order='F') for k, v in before.items()}
+    for zd in Internal.getZones(t):
+        _, imd, jmd, kmd, _ = Internal.getZoneDim(zd)
+        for s in Internal.getNodesFromType1(zd, 'ZoneSubRegion_t'):
+            if not s[0].startswith('ID_'):
+                continue
+            zr = Internal.getValue(s)
+            fD = [cur[(zd[0], v)].reshape(-1, order='F') for v in names]
+            fR = [cur[(zr, v)].reshape(-1, order='F') for v in names]
+            O.transfer(fD, fR, imd, jmd, Internal.getNodeFromName1(s, 'PointListDonor')[1],
+                       Internal.getNodeFromName1(s, 'PointList')[1], Internal.getNodeFromName1(s, 'InterpolantsType')[1],
+                       Internal.getNodeFromName1(s, 'InterpolantsDonor')[1])
+    changed = 0
+    for z in Internal.getZones(t2):
+        for v in names:
+            got = C.getFieldArray(z, v)
+            assert np.array_equal(got, cur[(z[0], v)]), (z[0], v)
+            changed += int(not np.array_equal(got, before[(z[0], v)]))
+    assert changed >= 6 and ctx.launches() > l0
