@@ -292,6 +292,12 @@ class _Single:
         return [o]
 
 
+def _rawF(a):
+    """True when the array's memory IS its Fortran-order flattening (the layout of the device copy), so that it can be
+    copied raw; a C-contiguous 2-D/3-D array is not (it goes through a.reshape(-1, order='F'))."""
+    return a.flags.f_contiguous or a.ndim == 1
+
+
 def _rcvFieldName(v, loc):
     return ('centers:' + v) if loc == 'centers' else v
 
@@ -594,7 +600,7 @@ class TransferSession:
             if zd[0] in self.dD:
                 arrs += [C.getFieldArray(zd, v) for v in self.variables]
         for a in arrs:
-            if id(a) in seen or not (a.flags.c_contiguous or a.flags.f_contiguous):
+            if id(a) in seen or not _rawF(a):
                 continue
             seen.add(id(a))
             try:
@@ -614,10 +620,10 @@ class TransferSession:
             if zd[0] in self.dD:
                 for d, v in zip(self.dD[zd[0]], self.variables):
                     a = C.getFieldArray(zd, v)
-                    if a.flags.c_contiguous or a.flags.f_contiguous:
+                    if _rawF(a):
                         self.ctx.upload_async(d.ptr, a)
                     else:
-                        d.upload(a.reshape(-1, order='F'))
+                        d.upload(numpy.ascontiguousarray(a.reshape(-1, order='F')))
 
     def step(self, niter=1, overlap=True):
         """niter iterations (asynchronous): remote plans -> NCCL exchange + scatter on the
@@ -630,12 +636,12 @@ class TransferSession:
         slow = []
         for name, arrs in self.hR.items():
             for d, a in zip(self.dR[name], arrs):
-                if a.flags.c_contiguous or a.flags.f_contiguous:
+                if _rawF(a):
                     self.ctx.download_async(a, d.ptr)
                 else:
                     slow.append((d, a))
                 nb += a.nbytes
         self.ctx.sync()
         for d, a in slow:
-            a.reshape(-1, order='F')[:] = d.download()
+            a[...] = d.download().reshape(a.shape, order='F')
         return nb

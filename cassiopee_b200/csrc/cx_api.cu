@@ -980,7 +980,7 @@ int cx_plan_destroy(cx_plan* P)
 {
   if (!P) return 0;
   cx_plan_full* F = (cx_plan_full*)P;
-  for (auto& G : P->groups) { cudaFree(G.d_cf); if (G.d_tiles) cudaFree(G.d_tiles); }
+  for (auto& G : P->groups) { cudaFree(G.d_cf); if (G.d_tiles) cudaFree(G.d_tiles); if (G.d_pat) cudaFree(G.d_pat); }
   cudaFree(P->d_donor); cudaFree(P->d_rcv); cudaFree(P->d_pos); cudaFree(P->d_seq);
   if (F->h_dense) cudaFreeHost(F->h_dense);
   for (cudaEvent_t e : F->evk) cudaEventDestroy(e);

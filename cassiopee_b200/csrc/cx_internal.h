@@ -82,7 +82,11 @@ struct cx_plan {
   // entries regrouped by type (stable), SoA coefficients per group
   // layout 0: list order, 1: sorted by donor index, 2: tiled by donor box (type 2 only; d_tiles = ntiles+1 TileRef)
   // layout 3: boxes of donor cells sized per plan (type 2 only; d_tiles = ntiles+1 BoxTile, box_vs = doubles of shared memory per variable)
-  struct Group { int type, ncf, sten, n, first; double* d_cf; int layout; void* d_tiles; int ntiles, ntx, nty, box_vs; };
+  // d_pat != nullptr: packed type-2 group (cx_transfer.cu:load_cf2): d_cf holds the 4 distinct doubles of every entry
+  // slot-major, d_pat the 16-bit selector word (2 bits per vertex); sel = code of the group's entries in the build's
+  // type array (the type, or CX_SEL_PACKED2 for the packable type-2 entries)
+  struct Group { int type, ncf, sten, n, first; double* d_cf; int layout; void* d_tiles; int ntiles, ntx, nty, box_vs;
+                 unsigned short* d_pat; int sel; };
   std::vector<Group> groups;
   int* d_donor; int* d_rcv; int* d_pos;   // regrouped order; pos = original entry position
   int* d_seq;                             // 0..n-1 (dense output in the plan's own order)

@@ -26,6 +26,9 @@
 // value that reaches (ksi,eta,zeta) are bit-identical while the work halves.
 #include "cx_internal.h"
 #include <algorithm>
+#include <string.h>
+#include <stdlib.h>
+#include <cub/device/device_radix_sort.cuh>
 
 using namespace cx;
 
@@ -175,13 +178,17 @@ __device__ __forceinline__ void gsync()
   if (WARP) __syncwarp(); else __syncthreads();
 }
 
-// One thread group (NT threads) solves one receptor's system.
+// One thread group (NT threads) solves the system of one STENCIL and evaluates it for the nr receptors rl[0..nr)
+// that share it.  The frame and the matrix are built from the stencil nodes alone
+// (CompInterpolatedPtInRefElementF.for:92-139, Cp_coord_in_stable_frame_3dF.for), the receptor only enters at the
+// evaluation (:144-186, :242-263), so receptors with the same stencil get bit for bit what one solve each gives them.
 //   N1 = points per direction (3 or 5), N = N1^3 rows, LD = padded row length
 //   (N columns + 3 RHS, odd number of doubles => conflict-free row-strided
 //   access).  Shared layout per group: A[N][LD], px/py/pz[N], small scratch.
 template <int N1, int NT, bool WARP>
-__device__ void lag_solve_group(const ZoneView& Z, int ics, int jcs, int kcs, double x0, double y0, double z0,
-                                double* sm, int tid, double& ksi, double& eta, double& zeta, int& err)
+__device__ void lag_solve_group(const ZoneView& Z, int ics, int jcs, int kcs, const LagState& S, const int* __restrict__ rl,
+                                int nr, const double* __restrict__ xr, const double* __restrict__ yr,
+                                const double* __restrict__ zr, double* sm, int tid)
 {
   constexpr int N = N1 * N1 * N1;
   constexpr int LD = (N + 3) | 1;
@@ -239,8 +246,6 @@ __device__ void lag_solve_group(const ZoneView& Z, int ics, int jcs, int kcs, do
     ctl[2] = 0;
   }
   gsync<WARP>();
-  double xp, yp, zp;
-  ref_frame(sc, x0, y0, z0, xp, yp, zp);      // every thread: identical arithmetic
   for (int p = tid; p < N; p += NT)
   {
     double a, b, c;
@@ -370,35 +375,46 @@ __device__ void lag_solve_group(const ZoneView& Z, int ics, int jcs, int kcs, do
     // a(ll,icol) = 0 for ll != icol happens implicitly: column icol is never read again
   }
   gsync<WARP>();
-  // evaluate the polynomial map at the receptor (CompInterpolatedPtInRefElementF.for:242-263)
-  if (tid < 3)
-  {
-    double acc = 0.;
-    int id = 0;
-    double mk = 1;
-    for (int k = 0; k < N1; k++)
-    {
-      double mj = 1;
-      for (int j = 0; j < N1; j++)
-      {
-        double mi = 1;
-        for (int i = 0; i < N1; i++)
-        {
-          double m = mi * mj * mk;
-          acc = acc + A[id * LD + N + tid] * m;
-          id++;
-          mi = mi * xp;
-        }
-        mj = mj * yp;
-      }
-      mk = mk * zp;
-    }
-    sc[12 + tid] = acc;
-  }
-  gsync<WARP>();
-  ksi = sc[12]; eta = sc[13]; zeta = sc[14];
+  // evaluate the polynomial map at every receptor of the stencil (CompInterpolatedPtInRefElementF.for:242-263):
+  // three lanes per receptor (ksi, eta, zeta), ten receptors per warp and pass
   const double thres = (double)(N1 / 2) + 0.001;
-  err = (fabs(ksi) >= thres || fabs(eta) >= thres || fabs(zeta) >= thres) ? 1 : 0;
+  const int lane = tid & 31, wq = lane / 3, comp = lane - 3 * wq;
+  constexpr int PER_PASS = 10 * (NT / 32);
+  for (int base = 0; base < nr; base += PER_PASS)
+  {
+    const int q = base + (tid >> 5) * 10 + wq;
+    const bool on = lane < 30 && q < nr;
+    double acc = 0.;
+    int r = 0;
+    if (on)
+    {
+      r = rl[q];
+      double xp, yp, zp;
+      ref_frame(sc, xr[r], yr[r], zr[r], xp, yp, zp);
+      int id = 0;
+      double mk = 1;
+      for (int k = 0; k < N1; k++)
+      {
+        double mj = 1;
+        for (int j = 0; j < N1; j++)
+        {
+          double mi = 1;
+          for (int i = 0; i < N1; i++)
+          {
+            double m = mi * mj * mk;
+            acc = acc + A[id * LD + N + comp] * m;
+            id++;
+            mi = mi * xp;
+          }
+          mj = mj * yp;
+        }
+        mk = mk * zp;
+      }
+      S.ksi[(size_t)comp * S.n + r] = acc;
+    }
+    const unsigned bad = __ballot_sync(0xffffffffu, on && fabs(acc) >= thres);
+    if (on && comp == 0) S.err[r] = ((bad >> (3 * wq)) & 7u) ? 1 : 0;
+  }
   gsync<WARP>();
 }
 
@@ -410,93 +426,103 @@ template <int N1> struct LagCfg {
   static constexpr int SMEM_D = N * LD + 3 * N + 16 + RED + ((RED + N + 3 + 4) * 4 + 7) / 8;
 };
 
-// order 3: one warp per receptor, 4 receptors per CTA
+// Distinct stencils of the found receptors: key = linear index of the stencil's first node
+__global__ void k_lag_keys(LagState S, int nlist, const int* __restrict__ list, const ZoneView* __restrict__ zones, int noz,
+                           int order, unsigned* __restrict__ key)
+{
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nlist) return;
+  const int r = list[a];
+  const ZoneView& Z = zones[noz];
+  int ics, jcs, kcs;
+  stencil_start(order, Z, S.ijk[r], S.ijk[(size_t)S.n + r], S.ijk[2 * (size_t)S.n + r], ics, jcs, kcs);
+  key[a] = (unsigned)(ics - 1 + (jcs - 1) * Z.ni + (kcs - 1) * Z.ni * Z.nj);
+}
+__global__ void k_lag_heads(int nlist, const unsigned* __restrict__ key, unsigned long long* __restrict__ f)
+{
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < nlist) f[a] = (a == 0 || key[a] != key[a - 1]) ? 1ull : 0ull;
+}
+__global__ void k_lag_ustart(int nlist, const unsigned long long* __restrict__ f, const unsigned long long* __restrict__ pos,
+                             int* __restrict__ ustart, int nu)
+{
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a == 0) ustart[nu] = nlist;
+  if (a < nlist && f[a]) ustart[(int)pos[a]] = a;
+}
+
+// Stencil u of the sorted list: receptors rl[ustart[u] .. ustart[u+1])
+__device__ __forceinline__ void stencil_of(const LagState& S, const ZoneView& Z, int order, int r0, int& ics, int& jcs, int& kcs)
+{
+  stencil_start(order, Z, S.ijk[r0], S.ijk[(size_t)S.n + r0], S.ijk[2 * (size_t)S.n + r0], ics, jcs, kcs);
+}
+
+// order 3: one warp per stencil, 4 stencils per CTA
 __global__ void __launch_bounds__(128)
-k_lag_solve3(LagState S, int nlist, const int* __restrict__ list, const double* __restrict__ xr,
+k_lag_solve3(LagState S, int nu, const int* __restrict__ ustart, const int* __restrict__ rl, const double* __restrict__ xr,
              const double* __restrict__ yr, const double* __restrict__ zr, const ZoneView* __restrict__ zones, int noz)
 {
   extern __shared__ double smem[];
   int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int a = blockIdx.x * 4 + w;
-  if (a >= nlist) return;
-  int r = list[a];
+  int u = blockIdx.x * 4 + w;
+  if (u >= nu) return;
+  const int a0 = ustart[u], a1 = ustart[u + 1];
   const ZoneView& Z = zones[noz];
   int ics, jcs, kcs;
-  stencil_start(3, Z, S.ijk[r], S.ijk[(size_t)S.n + r], S.ijk[2 * (size_t)S.n + r], ics, jcs, kcs);
-  double ksi, eta, zeta; int err;
-  lag_solve_group<3, 32, true>(Z, ics, jcs, kcs, xr[r], yr[r], zr[r], smem + (size_t)w * LagCfg<3>::SMEM_D, lane, ksi,
-                               eta, zeta, err);
-  if (lane == 0)
-  {
-    S.ksi[r] = ksi; S.ksi[(size_t)S.n + r] = eta; S.ksi[2 * (size_t)S.n + r] = zeta; S.err[r] = err;
-  }
+  stencil_of(S, Z, 3, rl[a0], ics, jcs, kcs);
+  lag_solve_group<3, 32, true>(Z, ics, jcs, kcs, S, rl + a0, a1 - a0, xr, yr, zr, smem + (size_t)w * LagCfg<3>::SMEM_D, lane);
 }
 
-// order 4: one 256-thread CTA per receptor, matrix (64 x 67 doubles) in shared memory
+// order 4: one 256-thread CTA per stencil, matrix (64 x 67 doubles) in shared memory
 __global__ void __launch_bounds__(256)
-k_lag_solve4(LagState S, int nlist, const int* __restrict__ list, const double* __restrict__ xr,
+k_lag_solve4(LagState S, int nu, const int* __restrict__ ustart, const int* __restrict__ rl, const double* __restrict__ xr,
              const double* __restrict__ yr, const double* __restrict__ zr, const ZoneView* __restrict__ zones, int noz)
 {
   extern __shared__ double smem[];
-  for (int a = blockIdx.x; a < nlist; a += gridDim.x)
+  for (int u = blockIdx.x; u < nu; u += gridDim.x)
   {
-    int r = list[a];
+    const int a0 = ustart[u], a1 = ustart[u + 1];
     const ZoneView& Z = zones[noz];
     int ics, jcs, kcs;
-    stencil_start(4, Z, S.ijk[r], S.ijk[(size_t)S.n + r], S.ijk[2 * (size_t)S.n + r], ics, jcs, kcs);
-    double ksi, eta, zeta; int err;
-    lag_solve_group<4, 256, false>(Z, ics, jcs, kcs, xr[r], yr[r], zr[r], smem, threadIdx.x, ksi, eta, zeta, err);
-    if (threadIdx.x == 0)
-    {
-      S.ksi[r] = ksi; S.ksi[(size_t)S.n + r] = eta; S.ksi[2 * (size_t)S.n + r] = zeta; S.err[r] = err;
-    }
+    stencil_of(S, Z, 4, rl[a0], ics, jcs, kcs);
+    lag_solve_group<4, 256, false>(Z, ics, jcs, kcs, S, rl + a0, a1 - a0, xr, yr, zr, smem, threadIdx.x);
     __syncthreads();
   }
 }
 
-// order 5: one 512-thread CTA per receptor, matrix (125 x 129 doubles) in shared memory (CX_LAG5=512)
+// order 5: one 512-thread CTA per stencil, matrix (125 x 129 doubles) in shared memory (CX_LAG5=512)
 __global__ void __launch_bounds__(512)
-k_lag_solve5(LagState S, int nlist, const int* __restrict__ list, const double* __restrict__ xr,
+k_lag_solve5(LagState S, int nu, const int* __restrict__ ustart, const int* __restrict__ rl, const double* __restrict__ xr,
              const double* __restrict__ yr, const double* __restrict__ zr, const ZoneView* __restrict__ zones, int noz)
 {
   extern __shared__ double smem[];
-  for (int a = blockIdx.x; a < nlist; a += gridDim.x)
+  for (int u = blockIdx.x; u < nu; u += gridDim.x)
   {
-    int r = list[a];
+    const int a0 = ustart[u], a1 = ustart[u + 1];
     const ZoneView& Z = zones[noz];
     int ics, jcs, kcs;
-    stencil_start(5, Z, S.ijk[r], S.ijk[(size_t)S.n + r], S.ijk[2 * (size_t)S.n + r], ics, jcs, kcs);
-    double ksi, eta, zeta; int err;
-    lag_solve_group<5, 512, false>(Z, ics, jcs, kcs, xr[r], yr[r], zr[r], smem, threadIdx.x, ksi, eta, zeta, err);
-    if (threadIdx.x == 0)
-    {
-      S.ksi[r] = ksi; S.ksi[(size_t)S.n + r] = eta; S.ksi[2 * (size_t)S.n + r] = zeta; S.err[r] = err;
-    }
+    stencil_of(S, Z, 5, rl[a0], ics, jcs, kcs);
+    lag_solve_group<5, 512, false>(Z, ics, jcs, kcs, S, rl + a0, a1 - a0, xr, yr, zr, smem, threadIdx.x);
     __syncthreads();
   }
 }
 
-// order 5 with a 1024-thread CTA per receptor (8 column segments of 16 per row, 64 registers): twice the warps
+// order 5 with a 1024-thread CTA per stencil (8 column segments of 16 per row, 64 registers): twice the warps
 // per SM for the pivot step's dependent chain; the default (1.90 s vs 1.99 s per 1.06 M receptors; A/B:
 // CX_LAG5=512).  Keeping the matrix in registers instead (three variants, profiles/r01_e_lagrange5.md) did
 // not help: the pivot step is bound by instruction issue and the two barriers, not by shared memory.
 __global__ void __launch_bounds__(1024, 1)
-k_lag_solve5w(LagState S, int nlist, const int* __restrict__ list, const double* __restrict__ xr,
+k_lag_solve5w(LagState S, int nu, const int* __restrict__ ustart, const int* __restrict__ rl, const double* __restrict__ xr,
               const double* __restrict__ yr, const double* __restrict__ zr, const ZoneView* __restrict__ zones, int noz)
 {
   extern __shared__ double smem[];
-  for (int a = blockIdx.x; a < nlist; a += gridDim.x)
+  for (int u = blockIdx.x; u < nu; u += gridDim.x)
   {
-    int r = list[a];
+    const int a0 = ustart[u], a1 = ustart[u + 1];
     const ZoneView& Z = zones[noz];
     int ics, jcs, kcs;
-    stencil_start(5, Z, S.ijk[r], S.ijk[(size_t)S.n + r], S.ijk[2 * (size_t)S.n + r], ics, jcs, kcs);
-    double ksi, eta, zeta; int err;
-    lag_solve_group<5, 1024, false>(Z, ics, jcs, kcs, xr[r], yr[r], zr[r], smem, threadIdx.x, ksi, eta, zeta, err);
-    if (threadIdx.x == 0)
-    {
-      S.ksi[r] = ksi; S.ksi[(size_t)S.n + r] = eta; S.ksi[2 * (size_t)S.n + r] = zeta; S.err[r] = err;
-    }
+    stencil_of(S, Z, 5, rl[a0], ics, jcs, kcs);
+    lag_solve_group<5, 1024, false>(Z, ics, jcs, kcs, S, rl + a0, a1 - a0, xr, yr, zr, smem, threadIdx.x);
     __syncthreads();
   }
 }
@@ -683,6 +709,12 @@ __global__ void k_lag_collapse(LagState S, const ZoneView* __restrict__ zones)
   if (cnt == 1) { S.type[r] = 1; S.dind[r] = indNonZero; S.cf[r] = coefNonZero; }
 }
 
+__global__ void k_iota_lag(int n, int* __restrict__ a)
+{
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) a[e] = e;
+}
+
 __global__ void k_list(int n, const unsigned long long* __restrict__ f, const unsigned long long* __restrict__ pos,
                        int* __restrict__ out)
 {
@@ -707,11 +739,20 @@ int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_xr, cons
   CX_MALLOC(S.ksi, sizeof(double) * 3 * N, s);
   CX_MALLOC(S.err, sizeof(int) * N, s);
   CX_MALLOC(S.best, sizeof(double) * N, s);
-  unsigned long long *d_f, *d_p; int* d_list;
+  unsigned long long *d_f, *d_p; int *d_list, *d_slist, *d_ustart; unsigned *d_key, *d_skey;
   CX_MALLOC(d_f, sizeof(unsigned long long) * N, s);
   CX_MALLOC(d_p, sizeof(unsigned long long) * N, s);
   CX_MALLOC(d_list, sizeof(int) * N, s);
+  CX_MALLOC(d_slist, sizeof(int) * N, s);
+  CX_MALLOC(d_ustart, sizeof(int) * (N + 1), s);
+  CX_MALLOC(d_key, sizeof(unsigned) * N, s);
+  CX_MALLOC(d_skey, sizeof(unsigned) * N, s);
+  void* d_tmp = nullptr; size_t tmp_cap = 0;
+  // CX_LAG_DEDUP=0: one solve per receptor, like the reference (A/B)
+  const char* dd_env = getenv("CX_LAG_DEDUP");
+  const bool dedup = !(dd_env && dd_env[0] == '0');
   const int TB = 128;
+  long long lag_solves = 0, lag_found = 0;
   k_lag_init<<<cx_grid(n, 256), 256, 0, s>>>(S);
   ctx->launches++;
   const size_t smem3 = sizeof(double) * LagCfg<3>::SMEM_D * 4;
@@ -739,19 +780,42 @@ int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_xr, cons
     if (nlist > 0)
     {
       k_list<<<cx_grid(n, 256), 256, 0, s>>>(n, d_f, d_p, d_list);
+      // one system per DISTINCT stencil: receptors sorted by stencil (stable radix sort), run starts = stencils
+      int nu = nlist;
+      const int* rl = d_list;
+      if (dedup)
+      {
+        k_lag_keys<<<cx_grid(nlist, 256), 256, 0, s>>>(S, nlist, d_list, d_zones, noz, order, d_key);
+        const unsigned kmax = (unsigned)h_zones[noz].ni * (unsigned)h_zones[noz].nj * (unsigned)h_zones[noz].nk;
+        int bits = 1; while (bits < 32 && (1ull << bits) <= (unsigned long long)kmax) bits++;
+        size_t need = 0;
+        CX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, d_key, d_skey, d_list, d_slist, nlist, 0, bits, s));
+        if (need > tmp_cap) { if (d_tmp) cudaFreeAsync(d_tmp, s); CX_MALLOC(d_tmp, need, s); tmp_cap = need; }
+        CX_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, need, d_key, d_skey, d_list, d_slist, nlist, 0, bits, s));
+        k_lag_heads<<<cx_grid(nlist, 256), 256, 0, s>>>(nlist, d_skey, d_f);
+        unsigned long long tu = 0;
+        CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, nlist, &tu));
+        nu = (int)tu;
+        k_lag_ustart<<<cx_grid(nlist, 256), 256, 0, s>>>(nlist, d_f, d_p, d_ustart, nu);
+        rl = d_slist;
+        ctx->launches += 4;
+      }
+      else
+        k_iota_lag<<<cx_grid(nlist + 1, 256), 256, 0, s>>>(nlist + 1, d_ustart);
       if (order == 3)
-        k_lag_solve3<<<cx_grid(nlist, 4), 128, smem3, s>>>(S, nlist, d_list, d_xr, d_yr, d_zr, d_zones, noz);
+        k_lag_solve3<<<cx_grid(nu, 4), 128, smem3, s>>>(S, nu, d_ustart, rl, d_xr, d_yr, d_zr, d_zones, noz);
       else if (order == 4)
       {
-        int grid = nlist < ctx->sm_count * 24 ? nlist : ctx->sm_count * 24;
-        k_lag_solve4<<<grid, 256, smem4, s>>>(S, nlist, d_list, d_xr, d_yr, d_zr, d_zones, noz);
+        int grid = nu < ctx->sm_count * 24 ? nu : ctx->sm_count * 24;
+        k_lag_solve4<<<grid, 256, smem4, s>>>(S, nu, d_ustart, rl, d_xr, d_yr, d_zr, d_zones, noz);
       }
       else
       {
-        int grid = nlist < ctx->sm_count * 4 ? nlist : ctx->sm_count * 4;
-        if (lag5_wide) k_lag_solve5w<<<grid, 1024, smem5, s>>>(S, nlist, d_list, d_xr, d_yr, d_zr, d_zones, noz);
-        else k_lag_solve5<<<grid, 512, smem5, s>>>(S, nlist, d_list, d_xr, d_yr, d_zr, d_zones, noz);
+        int grid = nu < ctx->sm_count * 4 ? nu : ctx->sm_count * 4;
+        if (lag5_wide) k_lag_solve5w<<<grid, 1024, smem5, s>>>(S, nu, d_ustart, rl, d_xr, d_yr, d_zr, d_zones, noz);
+        else k_lag_solve5<<<grid, 512, smem5, s>>>(S, nu, d_ustart, rl, d_xr, d_yr, d_zr, d_zones, noz);
       }
+      lag_solves += nu; lag_found += nlist;
     }
     k_lag_finish<<<cx_grid(n, TB), TB, 0, s>>>(S, d_zones, noz, order, nature, penalty);
     ctx->launches += 3;
@@ -762,5 +826,8 @@ int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_xr, cons
   CX_CUDA(cudaGetLastError());
   cudaFreeAsync(S.found, s); cudaFreeAsync(S.ijk, s); cudaFreeAsync(S.tcf, s); cudaFreeAsync(S.ksi, s); cudaFreeAsync(S.err, s); cudaFreeAsync(S.best, s);
   cudaFreeAsync(d_f, s); cudaFreeAsync(d_p, s); cudaFreeAsync(d_list, s);
+  cudaFreeAsync(d_slist, s); cudaFreeAsync(d_ustart, s); cudaFreeAsync(d_key, s); cudaFreeAsync(d_skey, s);
+  if (d_tmp) cudaFreeAsync(d_tmp, s);
+  if (getenv("CX_PROFILE")) fprintf(stderr, "[cx] lagrange order %d: %lld found receptors, %lld systems solved\n", order, lag_found, lag_solves);
   return 0;
 }

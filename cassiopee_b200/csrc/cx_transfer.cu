@@ -30,6 +30,7 @@
 #define CX_SET_MINB 4            // resident CTAs per SM the plan-set kernels are compiled for
 #endif
 #ifndef CX_SET_VU
+#define CX_SEL_PACKED2 102        // build-time code of the packable type-2 entries (cx_plan::Group::sel)
 #define CX_SET_VU 1              // variables gathered per pass by the plan-set kernels' direct-gather path
 #endif
 
@@ -39,13 +40,39 @@ namespace {
 
 template <int O> struct Sten { };
 
+// Type-2 coefficients of entry e.  The 8 weights the reference's tetrahedron formula produces take at most 4
+// distinct values (InterpData.cpp:621-631: cf0 on the four vertices off the tetrahedron's face, cf0+xi/4 on the
+// face, two of those again + yi / + zi), so a plan stores such entries as the 4 distinct doubles (slot-major, like
+// the raw layout) + a 16-bit selector word (2 bits per vertex): 34 bytes instead of 64.  The values are the same
+// doubles bit for bit, so the arithmetic is untouched.  pat == nullptr: raw group, 8 slots.
+__device__ __forceinline__ void load_cf2(double* c, const double* __restrict__ cfT, const unsigned short* __restrict__ pat,
+                                         int m, int e)
+{
+  if (pat == nullptr)
+  {
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = cfT[(size_t)k * m + e];
+  }
+  else
+  {
+    const double v0 = cfT[e], v1 = cfT[(size_t)m + e], v2 = cfT[(size_t)2 * m + e], v3 = cfT[(size_t)3 * m + e];
+    const unsigned p = pat[e];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+    {
+      const unsigned sl = (p >> (2 * k)) & 3u;
+      c[k] = (sl & 2u) ? ((sl & 1u) ? v3 : v2) : ((sl & 1u) ? v1 : v0);
+    }
+  }
+}
+
 // One entry of one plan.  MODE 0: scatter to fieldR[v][rcv[e]];  MODE 1: dense out[v*ld + pos[e]].
 // PD/PR: anything indexable by variable (kernel-parameter struct or device pointer table).
 template <int TYPE, int MODE, class PD, class PR, int VU = 1>
 __device__ __forceinline__ void transfer_entry(int e, int m, int nvars, const PD& pd, const PR& pr, int imd, int imdjmd,
                                                const int* __restrict__ donor, const int* __restrict__ idx,
                                                const double* __restrict__ cfT, double* __restrict__ dense,
-                                               long long ld)
+                                               long long ld, const unsigned short* __restrict__ pat = nullptr)
 {
   const int d0 = donor[e];
   const size_t o = (size_t)idx[e];
@@ -78,8 +105,7 @@ __device__ __forceinline__ void transfer_entry(int e, int m, int nvars, const PD
   else if (TYPE == 2)
   {
     double c[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) c[k] = cfT[(size_t)k * m + e];
+    load_cf2(c, cfT, pat, m, e);
     int v = 0;
     if (VU == 2)
     {
@@ -199,7 +225,7 @@ __device__ __forceinline__ bool transfer_tile2_staged(StageSmem& S, int t0, int 
                                                       int imd, int imdjmd, int nptsD, const int* __restrict__ donor,
                                                       const int* __restrict__ idx, const double* __restrict__ cfT,
                                                       double* __restrict__ dense, long long ld, int known_lo = -1,
-                                                      int known_hi = -1)
+                                                      int known_hi = -1, const unsigned short* __restrict__ pat = nullptr)
 {
   const int tid = threadIdx.x;
   const int e = t0 + tid;
@@ -233,8 +259,7 @@ __device__ __forceinline__ bool transfer_tile2_staged(StageSmem& S, int t0, int 
   if (act)
   {
     l = donor[e] - d_lo; o = (size_t)idx[e];
-#pragma unroll
-    for (int k = 0; k < 8; k++) c[k] = cfT[(size_t)k * m + e];   // (streaming __ldcs loads measured no faster)
+    load_cf2(c, cfT, pat, m, e);
   }
   for (int v = 0; v < nvars; v++)
   {
@@ -473,7 +498,8 @@ template <int MODE, class PD, class PR>
 __device__ __forceinline__ void transfer_box3(double* __restrict__ sm, int start, int count, int base, int dims, int m,
                                               int nvars, const PD& pd, const PR& pr, int imd, int imdjmd,
                                               const int* __restrict__ donor, const int* __restrict__ idx,
-                                              const double* __restrict__ cfT, double* __restrict__ dense, long long ld)
+                                              const double* __restrict__ cfT, double* __restrict__ dense, long long ld,
+                                              const unsigned short* __restrict__ pat = nullptr)
 {
   const int tid = threadIdx.x;
   const int ilen = dims & 255, jlen = (dims >> 8) & 255, klen = dims >> 16;
@@ -494,8 +520,7 @@ __device__ __forceinline__ void transfer_box3(double* __restrict__ sm, int start
   {
     const int e = start + c;
     d0 = donor[e]; o = (size_t)idx[e];
-#pragma unroll
-    for (int q = 0; q < 8; q++) cf[q] = cfT[(size_t)q * m + e];
+    load_cf2(cf, cfT, pat, m, e);
   }
   cp_async_wait_all();
   __syncthreads();
@@ -522,8 +547,7 @@ __device__ __forceinline__ void transfer_box3(double* __restrict__ sm, int start
     {
       const int e = start + c;
       d0 = donor[e]; o = (size_t)idx[e];
-#pragma unroll
-      for (int q = 0; q < 8; q++) cf[q] = cfT[(size_t)q * m + e];
+      load_cf2(cf, cfT, pat, m, e);
     }
   }
 }
@@ -535,12 +559,12 @@ template <int TYPE, int MODE>
 __global__ void __launch_bounds__(256)
 k_transfer(int m, int nvars, FieldPtrs P, int imd, int imdjmd, const int* __restrict__ donor,
            const int* __restrict__ rcv, const int* __restrict__ pos, const double* __restrict__ cfT,
-           double* __restrict__ dense, long long ld)
+           double* __restrict__ dense, long long ld, const unsigned short* __restrict__ pat)
 {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= m) return;
   PDk pd{P.d}; PRk pr{P.r};
-  transfer_entry<TYPE, MODE>(e, m, nvars, pd, pr, imd, imdjmd, donor, MODE == 0 ? rcv : pos, cfT, dense, ld);
+  transfer_entry<TYPE, MODE>(e, m, nvars, pd, pr, imd, imdjmd, donor, MODE == 0 ? rcv : pos, cfT, dense, ld, pat);
 }
 
 // type 2 with shared-memory staging (falls back to the direct gather tile by tile)
@@ -548,18 +572,28 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 k_transfer2s(int m, int nvars, FieldPtrs P, int imd, int imdjmd, int nptsD, const int* __restrict__ donor,
              const int* __restrict__ rcv, const int* __restrict__ pos, const double* __restrict__ cfT,
-             double* __restrict__ dense, long long ld)
+             double* __restrict__ dense, long long ld, const unsigned short* __restrict__ pat)
 {
   extern __shared__ __align__(16) double dyn_sm[];
   StageSmem& S = *reinterpret_cast<StageSmem*>(dyn_sm);
   PDk pd{P.d}; PRk pr{P.r};
   const int t0 = blockIdx.x * blockDim.x;
-  if (transfer_tile2_staged<MODE>(S, t0, m, nvars, pd, pr, imd, imdjmd, nptsD, donor, MODE == 0 ? rcv : pos, cfT, dense, ld))
+  if (transfer_tile2_staged<MODE>(S, t0, m, nvars, pd, pr, imd, imdjmd, nptsD, donor, MODE == 0 ? rcv : pos, cfT, dense, ld,
+                                  -1, -1, pat))
     return;
   int e = t0 + threadIdx.x;
   if (e >= m) return;
-  transfer_entry<2, MODE>(e, m, nvars, pd, pr, imd, imdjmd, donor, MODE == 0 ? rcv : pos, cfT, dense, ld);
+  transfer_entry<2, MODE>(e, m, nvars, pd, pr, imd, imdjmd, donor, MODE == 0 ? rcv : pos, cfT, dense, ld, pat);
 }
+
+// Measured and rejected (round 2, C2a, 17.0 M receptors, 5 variables; gpurun_out/r2_t2v*.out): an all-TMA variant of
+// the kernel above -- the sorted group cut into variable tiles (<= 256 entries AND <= 192 donor nodes, so that every
+// tile stages), indices / selector words / coefficient slots / the four row segments of EVERY variable requested at
+// once with cp.async.bulk (two round trips per CTA instead of 2 + nvars), one mbarrier per variable -- ran 0.549 ms
+// against 0.499 ms (raw 8-slot coefficients: 0.66 ms; tiles of <= 128 nodes: 0.65 ms; the issue spread over the
+// CTA's warps: 0.577 ms).  The time follows the NUMBER of bulk copies (27-31 per tile of ~1-2 KB each, i.e. one copy
+// per 60-80 SM cycles), not the bytes: small non-tensor bulk copies are bound by the TMA unit's per-request cost, so
+// the plan data stays on plain coalesced loads and only the row segments (20 copies per tile) go through TMA.
 
 // ---- persistent, software-pipelined type-2 kernel (donor-sorted groups; EXPERIMENTAL, CX_TRANSFER_PIPE=1) ----
 // Measured on C2a (17.0 M receptors, B200): 5 variables 0.62 ms (3 stages, 2-3 consumer groups) against 0.49 ms
@@ -782,14 +816,15 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 k_transfer2b(const BoxTile* __restrict__ tiles, int m, int nvars, FieldPtrs P, int imd, int imdjmd,
              const int* __restrict__ donor, const int* __restrict__ rcv, const int* __restrict__ pos,
-             const double* __restrict__ cfT, double* __restrict__ dense, long long ld)
+             const double* __restrict__ cfT, double* __restrict__ dense, long long ld,
+             const unsigned short* __restrict__ pat)
 {
   extern __shared__ __align__(16) double dyn_sm[];
   PDk pd{P.d}; PRk pr{P.r};
   const BoxTile t = tiles[blockIdx.x];
   const int count = tiles[blockIdx.x + 1].start - t.start;
   transfer_box3<MODE>(dyn_sm, t.start, count, t.base, t.dims, m, nvars, pd, pr, imd, imdjmd, donor, MODE == 0 ? rcv : pos,
-                      cfT, dense, ld);
+                      cfT, dense, ld, pat);
 }
 
 // Plan set: every (plan, type group) of a rank in ONE launch.  Block b works on
@@ -800,6 +835,7 @@ struct SetDesc {
   int pad_;
   const TileRef* tiles;
   const int* donor; const int* idx; const double* cfT;
+  const unsigned short* pat;   // packed type-2 group: selector words (else nullptr)
   double* dense; long long ld; // mode 1
   const double* dp[CX_MAXVARS];  // donor field pointers (inline: no dependent table fetch)
   double* rp[CX_MAXVARS];        // receptor field pointers (mode 0)
@@ -858,8 +894,8 @@ k_transfer_set(const SetDesc* __restrict__ descs, const BlkRec* __restrict__ blk
     }
     if (D.layout == 3)
     {
-      if (D.mode == 0) transfer_box3<0>(dyn_sm, br.start, br.count, br.base, br.dims, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
-      else transfer_box3<1>(dyn_sm, br.start, br.count, br.base, br.dims, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
+      if (D.mode == 0) transfer_box3<0>(dyn_sm, br.start, br.count, br.base, br.dims, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld, D.pat);
+      else transfer_box3<1>(dyn_sm, br.start, br.count, br.base, br.dims, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld, D.pat);
       return;
     }
     if (staged && D.layout == 1)
@@ -867,8 +903,8 @@ k_transfer_set(const SetDesc* __restrict__ descs, const BlkRec* __restrict__ blk
       StageSmem& S = *reinterpret_cast<StageSmem*>(dyn_sm);
       const int t0 = (blockIdx.x - D.first_block) * blockDim.x;
       bool done = (D.mode == 0)
-        ? transfer_tile2_staged<0>(S, t0, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.nptsD, D.donor, D.idx, D.cfT, D.dense, D.ld, br.d_lo, br.d_hi)
-        : transfer_tile2_staged<1>(S, t0, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.nptsD, D.donor, D.idx, D.cfT, D.dense, D.ld, br.d_lo, br.d_hi);
+        ? transfer_tile2_staged<0>(S, t0, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.nptsD, D.donor, D.idx, D.cfT, D.dense, D.ld, br.d_lo, br.d_hi, D.pat)
+        : transfer_tile2_staged<1>(S, t0, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.nptsD, D.donor, D.idx, D.cfT, D.dense, D.ld, br.d_lo, br.d_hi, D.pat);
       if (done) return;
     }
   }
@@ -888,8 +924,8 @@ k_transfer_set(const SetDesc* __restrict__ descs, const BlkRec* __restrict__ blk
   }
   int e = (blockIdx.x - D.first_block) * blockDim.x + threadIdx.x;
   if (e >= D.m) return;
-  if (D.mode == 0) transfer_entry<TYPE, 0, PDk, PRk, CX_SET_VU>(e, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
-  else transfer_entry<TYPE, 1, PDk, PRk, CX_SET_VU>(e, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld);
+  if (D.mode == 0) transfer_entry<TYPE, 0, PDk, PRk, CX_SET_VU>(e, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld, D.pat);
+  else transfer_entry<TYPE, 1, PDk, PRk, CX_SET_VU>(e, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld, D.pat);
 }
 
 // donor index range of every block's tile (donor-sorted type-2 groups of a plan set), once at creation
@@ -927,7 +963,7 @@ k_scatter_set(const ScatDesc* __restrict__ descs, const int* __restrict__ blk2de
 template <int TYPE>
 __global__ void k_transfer_celln(int m, const double* __restrict__ cellND, double* __restrict__ cellNR, int imd,
                                  int imdjmd, const int* __restrict__ donor, const int* __restrict__ rcv,
-                                 const double* __restrict__ cfT)
+                                 const double* __restrict__ cfT, const unsigned short* __restrict__ pat = nullptr)
 {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= m) return;
@@ -944,9 +980,13 @@ __global__ void k_transfer_celln(int m, const double* __restrict__ cellND, doubl
   }
   else if (TYPE == 2)
   {
-    for (int kk = 0; kk < 2; kk++) for (int jj = 0; jj < 2; jj++) for (int ii = 0; ii < 2; ii++)
+    double c8[8];
+    load_cf2(c8, cfT, pat, m, e);
+#pragma unroll
+    for (int q = 0; q < 8; q++)
     {
-      double cf = cfT[(size_t)(ii + 2 * jj + 4 * kk) * m + e];
+      const int ii = q & 1, jj = (q >> 1) & 1, kk = q >> 2;
+      double cf = c8[q];
       if (fabs(cf) > 1.e-11) { double c = cellND[d0 + ii + jj * imd + kk * imdjmd]; val *= c * (2. - c); }
     }
   }
@@ -1074,14 +1114,41 @@ __global__ void k_tile_table(int m, const unsigned* __restrict__ key, const unsi
 __global__ void k_plan_place_perm(int m, int ncf, const int* __restrict__ perm, const int* __restrict__ donor,
                                   const int* __restrict__ rcv, const unsigned long long* __restrict__ off,
                                   const double* __restrict__ coefs, int* __restrict__ od, int* __restrict__ orc,
-                                  int* __restrict__ op, double* __restrict__ cfT)
+                                  int* __restrict__ op, double* __restrict__ cfT, unsigned short* __restrict__ pat)
 {
   int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= m) return;
   int e = perm[slot];
   od[slot] = donor[e]; orc[slot] = rcv[e]; op[slot] = e;
   const double* c = coefs + off[e];
-  for (int k = 0; k < ncf; k++) cfT[(size_t)k * m + slot] = c[k];
+  if (pat == nullptr)
+  {
+    for (int k = 0; k < ncf; k++) cfT[(size_t)k * m + slot] = c[k];
+    return;
+  }
+  // packed type-2 entry (the host has checked that its 8 weights take at most 4 distinct bit patterns): distinct
+  // values in order of first appearance + 2-bit selector per vertex
+  long long val[4] = {0, 0, 0, 0};
+  int nd = 0; unsigned p = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+  {
+    const long long b = __double_as_longlong(c[k]);
+    int sl = -1;
+#pragma unroll
+    for (int q = 0; q < 4; q++) if (sl < 0 && q < nd && val[q] == b) sl = q;
+    if (sl < 0)
+    {
+      sl = nd < 4 ? nd : 3;
+#pragma unroll
+      for (int q = 0; q < 4; q++) if (q == sl) val[q] = b;
+      nd++;
+    }
+    p |= (unsigned)sl << (2 * k);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; q++) cfT[(size_t)q * m + slot] = __longlong_as_double(val[q]);
+  pat[slot] = (unsigned short)p;
 }
 }  // namespace
 
@@ -1117,7 +1184,7 @@ static int build_tiled_group(cx_ctx* ctx, cx_plan* P, cx_plan::Group& G, int n, 
   unsigned *k_in, *k_out; int *v_in, *v_out; void* tmp = nullptr; size_t tmp_bytes = 0;
   CX_MALLOC(k_in, sizeof(unsigned) * (size_t)n, s); CX_MALLOC(k_out, sizeof(unsigned) * (size_t)n, s);
   CX_MALLOC(v_in, sizeof(int) * (size_t)n, s); CX_MALLOC(v_out, sizeof(int) * (size_t)n, s);
-  k_tile_keys<<<cx_grid(n, TB), TB, 0, s>>>(n, G.type, r_ty, r_dn, P->imd, P->jmd, ntx, nty, nboxes, k_in, v_in);
+  k_tile_keys<<<cx_grid(n, TB), TB, 0, s>>>(n, G.sel, r_ty, r_dn, P->imd, P->jmd, ntx, nty, nboxes, k_in, v_in);
   int bits = 1; while ((1ull << bits) <= (unsigned long long)nboxes) bits++;
   // stable LSD radix sort (CUB): entries keep their list order (ascending receptors) inside a box
   CX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, n, 0, bits, s));
@@ -1136,7 +1203,7 @@ static int build_tiled_group(cx_ctx* ctx, cx_plan* P, cx_plan::Group& G, int n, 
     CX_CUDA(cudaMalloc(&G.d_tiles, sizeof(TileRef) * ((size_t)total + 1)));
     k_tile_table<<<cx_grid(m, TB), TB, 0, s>>>(m, k_out, sc, (TileRef*)G.d_tiles, (int)total);
     k_plan_place_perm<<<cx_grid(m, TB), TB, 0, s>>>(m, G.ncf, v_out, r_dn, r_rc, r_off, r_cf, P->d_donor + first,
-                                                   P->d_rcv + first, P->d_pos + first, G.d_cf);
+                                                   P->d_rcv + first, P->d_pos + first, G.d_cf, G.d_pat);
     ctx->launches += 2;
     ok = 1;
   }
@@ -1173,7 +1240,7 @@ static int build_box_group(cx_ctx* ctx, cx_plan* P, cx_plan::Group& G, int n, co
   unsigned *k_in, *k_out; int *v_in, *v_out; void* tmp = nullptr; size_t tmp_bytes = 0;
   CX_MALLOC(k_in, sizeof(unsigned) * (size_t)n, s); CX_MALLOC(k_out, sizeof(unsigned) * (size_t)n, s);
   CX_MALLOC(v_in, sizeof(int) * (size_t)n, s); CX_MALLOC(v_out, sizeof(int) * (size_t)n, s);
-  k_box_keys<<<cx_grid(n, TB), TB, 0, s>>>(n, G.type, r_ty, r_dn, P->imd, P->jmd, B, nboxes, k_in, v_in);
+  k_box_keys<<<cx_grid(n, TB), TB, 0, s>>>(n, G.sel, r_ty, r_dn, P->imd, P->jmd, B, nboxes, k_in, v_in);
   int bits = 1; while ((1ull << bits) <= (unsigned long long)nboxes) bits++;
   // stable LSD radix sort (CUB): entries keep their list order (ascending receptors) inside a box
   CX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, n, 0, bits, s));
@@ -1193,7 +1260,7 @@ static int build_box_group(cx_ctx* ctx, cx_plan* P, cx_plan::Group& G, int n, co
     CX_CUDA(cudaMalloc(&G.d_tiles, sizeof(BoxTile) * ((size_t)total + 1)));
     k_box_table<<<cx_grid(m, TB), TB, 0, s>>>(m, k_out, sc, (BoxTile*)G.d_tiles, (int)total, B, P->imd, P->imd * P->jmd);
     k_plan_place_perm<<<cx_grid(m, TB), TB, 0, s>>>(m, G.ncf, v_out, r_dn, r_rc, r_off, r_cf, P->d_donor + first,
-                                                   P->d_rcv + first, P->d_pos + first, G.d_cf);
+                                                   P->d_rcv + first, P->d_pos + first, G.d_cf, G.d_pat);
     ctx->launches += 2;
     ok = 1;
   }
@@ -1214,13 +1281,13 @@ static int build_sorted_group(cx_ctx* ctx, cx_plan* P, cx_plan::Group& G, int n,
   CX_MALLOC(k_in, sizeof(unsigned) * (size_t)n, s); CX_MALLOC(k_out, sizeof(unsigned) * (size_t)n, s);
   CX_MALLOC(v_in, sizeof(int) * (size_t)n, s); CX_MALLOC(v_out, sizeof(int) * (size_t)n, s);
   const unsigned sentinel = (unsigned)P->nptsD;
-  k_donor_keys<<<cx_grid(n, TB), TB, 0, s>>>(n, G.type, r_ty, r_dn, sentinel, k_in, v_in);
+  k_donor_keys<<<cx_grid(n, TB), TB, 0, s>>>(n, G.sel, r_ty, r_dn, sentinel, k_in, v_in);
   int bits = 1; while ((1ull << bits) <= (unsigned long long)sentinel) bits++;
   CX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, n, 0, bits, s));
   CX_MALLOC(tmp, tmp_bytes, s);
   CX_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, n, 0, bits, s));
   k_plan_place_perm<<<cx_grid(G.n, TB), TB, 0, s>>>(G.n, G.ncf, v_out, r_dn, r_rc, r_off, r_cf, P->d_donor + first,
-                                                     P->d_rcv + first, P->d_pos + first, G.d_cf);
+                                                     P->d_rcv + first, P->d_pos + first, G.d_cf, G.d_pat);
   ctx->launches += 3;
   cudaFreeAsync(k_in, s); cudaFreeAsync(k_out, s); cudaFreeAsync(v_in, s); cudaFreeAsync(v_out, s); cudaFreeAsync(tmp, s);
   if (G.type == 2)
@@ -1242,10 +1309,20 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
   P->d_donor = P->d_rcv = P->d_pos = P->d_seq = nullptr; P->alg_bytes_fixed = 0; P->distinct_nodes = -1; P->last_ms = 0.f;
   P->groups.clear();
   if (n == 0) { P->ngroups = 0; return 0; }
-  const int types[6] = {1, 2, 3, 5, 44, 22};
+  // group order: type 1, packed type 2, raw type 2, 3, 5, 44, 22
+  const int types[7] = {1, 2, 2, 3, 5, 44, 22};
+  const int sels[7] = {1, CX_SEL_PACKED2, 2, 3, 5, 44, 22};
+  const int mode_env = plan_sort_mode();
+  // packed type-2 groups (load_cf2) for the donor-sorted and box layouts.  Default: the plans a plan set fuses
+  // (< CX_BIG_PLAN entries; C4 step 57.6 -> 56.3 us) -- on the 17 M-entry C2a plan the 22 % fewer bytes do not pay
+  // (0.499 vs 0.490 ms: that launch is bound by latency and LSU wavefronts, not by DRAM).  CX_PLAN_PACK=0 / 1 forces.
+  const char* pk_env = getenv("CX_PLAN_PACK");
+  const bool pack_on = pk_env && pk_env[0] ? pk_env[0] != '0' : n < CX_BIG_PLAN;
+  const bool pack2 = pack_on && (mode_env < 0 || mode_env == 1 || mode_env == 5);
   std::vector<unsigned long long> off((size_t)n);
+  std::vector<int> sel((size_t)n);
   long long run = 0;
-  int cnt[6] = {0, 0, 0, 0, 0, 0};
+  int cnt[7] = {0, 0, 0, 0, 0, 0, 0};
   int bb2[6] = {INT_MAX, -1, INT_MAX, -1, INT_MAX, -1};      // donor cells of the type-2 entries: i0,i1,j0,j1,k0,k1
   for (int e = 0; e < n; e++)
   {
@@ -1254,14 +1331,31 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
     if (nc < 0) { cx_set_error("transfer plan: interpolation type %d is not supported (structured donors: 1,2,22,3,44,5)", type[e]); return -1; }
     if (donor[e] < 0 || (long long)donor[e] >= nptsD) { cx_set_error("transfer plan: donor index %d out of range", donor[e]); return -1; }
     if (rcv[e] < 0 || (long long)rcv[e] >= nptsR) { cx_set_error("transfer plan: receptor index %d out of range", rcv[e]); return -1; }
-    run += nc;
-    for (int g = 0; g < 6; g++) if (type[e] == types[g]) cnt[g]++;
+    if (run + nc > ncoefs) { cx_set_error("transfer plan: coefficient array has %lld entries, types need more", ncoefs); return -1; }
+    int sl = type[e];
     if (type[e] == 2)
     {
       const int d = donor[e], ci = d % imd, cj = (d / imd) % jmd, ck = d / (imd * jmd);
       bb2[0] = std::min(bb2[0], ci); bb2[1] = std::max(bb2[1], ci); bb2[2] = std::min(bb2[2], cj);
       bb2[3] = std::max(bb2[3], cj); bb2[4] = std::min(bb2[4], ck); bb2[5] = std::max(bb2[5], ck);
+      if (pack2)
+      {
+        // packable: the 8 weights take at most 4 distinct bit patterns (always true for the reference's
+        // tetrahedron weights, InterpData.cpp:621-631; extrapolated entries may not be)
+        long long b[8], val[4]; int nd = 0;
+        memcpy(b, coefs + run, sizeof(b));
+        for (int k = 0; k < 8 && nd <= 4; k++)
+        {
+          int q = 0;
+          while (q < nd && q < 4 && val[q] != b[k]) q++;
+          if (q == nd || q == 4) { if (nd < 4) val[nd] = b[k]; nd++; }
+        }
+        if (nd <= 4) sl = CX_SEL_PACKED2;
+      }
     }
+    sel[e] = sl;
+    run += nc;
+    for (int g = 0; g < 7; g++) if (sl == sels[g]) cnt[g]++;
   }
   if (run != ncoefs) { cx_set_error("transfer plan: coefficient array has %lld entries, types need %lld", ncoefs, run); return -1; }
   P->alg_bytes_fixed = 8 * run + 12ll * n;
@@ -1271,7 +1365,6 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
   CX_MALLOC(r_dn, sizeof(int) * N, s); CX_MALLOC(r_rc, sizeof(int) * N, s);
   CX_MALLOC(r_ty, sizeof(int) * N, s); CX_MALLOC(r_off, sizeof(unsigned long long) * N, s);
   CX_MALLOC(r_cf, sizeof(double) * (size_t)std::max(run, 1ll), s);
-  const int mode_env = plan_sort_mode();
   const int sorted = mode_env == 0 ? 0 : 1;
   const int kmd = (int)(nptsD / ((long long)imd * jmd));
   const size_t nscan = sorted ? (size_t)nptsD : N;
@@ -1279,7 +1372,7 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
   CX_MALLOC(d_scan, sizeof(unsigned long long) * nscan, s);
   CX_CHECK(cx_upload(ctx, r_dn, donor, sizeof(int) * N));
   CX_CHECK(cx_upload(ctx, r_rc, rcv, sizeof(int) * N));
-  CX_CHECK(cx_upload(ctx, r_ty, type, sizeof(int) * N));
+  CX_CHECK(cx_upload(ctx, r_ty, sel.data(), sizeof(int) * N));
   CX_CHECK(cx_upload(ctx, r_off, off.data(), sizeof(unsigned long long) * N));
   CX_CHECK(cx_upload(ctx, r_cf, coefs, sizeof(double) * (size_t)run));
   // + 64 bytes: the pipelined kernel's bulk copies round a tile's source range outwards to 16 bytes
@@ -1290,12 +1383,18 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
   k_iota<<<cx_grid(n, 256), 256, 0, s>>>(n, P->d_seq);
   const int TB = 256;
   int first = 0;
-  for (int g = 0; g < 6; g++)
+  for (int g = 0; g < 7; g++)
   {
     if (cnt[g] == 0) continue;
-    cx_plan::Group G; G.type = types[g]; G.ncf = ncf_host(types[g]); G.sten = sten_host(types[g]);
-    G.n = cnt[g]; G.first = first; G.d_cf = nullptr;
+    cx_plan::Group G; G.type = types[g]; G.sel = sels[g]; G.ncf = ncf_host(types[g]); G.sten = sten_host(types[g]);
+    G.n = cnt[g]; G.first = first; G.d_cf = nullptr; G.d_pat = nullptr;
     G.layout = sorted ? 1 : 0; G.d_tiles = nullptr; G.ntiles = 0; G.ntx = G.nty = 0; G.box_vs = 0;
+    if (G.sel == CX_SEL_PACKED2)
+    {
+      CX_MALLOC(G.d_cf, sizeof(double) * 4 * (size_t)G.n + 64, s);
+      CX_MALLOC(G.d_pat, sizeof(unsigned short) * (size_t)G.n + 64, s);
+    }
+    else
     CX_MALLOC(G.d_cf, sizeof(double) * (size_t)G.ncf * G.n + 64, s);
     if (G.type == 2 && (mode_env == 2 || mode_env == 3) && kmd >= 2 && G.n >= 4096)
     {
@@ -1321,15 +1420,15 @@ int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long npts
     if (sorted)       // CX_PLAN_SORT=4: counting sort with an atomic cursor (order inside a donor cell is arbitrary)
     {
       CX_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * nscan, s));
-      k_plan_hist<<<cx_grid(n, TB), TB, 0, s>>>(n, G.type, r_ty, r_dn, d_cnt);
+      k_plan_hist<<<cx_grid(n, TB), TB, 0, s>>>(n, G.sel, r_ty, r_dn, d_cnt);
       CX_CHECK(cx_exclusive_scan_u64(ctx, d_cnt, d_scan, (int)nscan, nullptr));
     }
     else
     {
-      k_plan_flag<<<cx_grid(n, TB), TB, 0, s>>>(n, G.type, r_ty, d_cnt);
+      k_plan_flag<<<cx_grid(n, TB), TB, 0, s>>>(n, G.sel, r_ty, d_cnt);
       CX_CHECK(cx_exclusive_scan_u64(ctx, d_cnt, d_scan, n, nullptr));
     }
-    k_plan_place<<<cx_grid(n, TB), TB, 0, s>>>(n, G.type, G.ncf, G.n, sorted, r_ty, r_dn, r_rc, r_off, r_cf, d_scan,
+    k_plan_place<<<cx_grid(n, TB), TB, 0, s>>>(n, G.sel, G.ncf, G.n, sorted, r_ty, r_dn, r_rc, r_off, r_cf, d_scan,
                                               d_scan, P->d_donor + first, P->d_rcv + first, P->d_pos + first, G.d_cf);
     ctx->launches += 2;
     P->groups.push_back(G);
@@ -1404,8 +1503,8 @@ int cx_plan_launch(cx_plan* P, int nvars, const double* const* dD, double* const
       const int* ps_ = (mode_in == 2 ? P->d_seq : P->d_pos) + G.first;
       int imd = P->imd, ij = P->imd * P->jmd;
 #define CX_LAUNCH(T)                                                                                           \
-      if (mode == 0) k_transfer<T, 0><<<grid, TB, 0, s>>>(G.n, nv, F, imd, ij, dn_, rc_, ps_, G.d_cf, dn, ld); \
-      else k_transfer<T, 1><<<grid, TB, 0, s>>>(G.n, nv, F, imd, ij, dn_, rc_, ps_, G.d_cf, dn, ld);
+      if (mode == 0) k_transfer<T, 0><<<grid, TB, 0, s>>>(G.n, nv, F, imd, ij, dn_, rc_, ps_, G.d_cf, dn, ld, G.d_pat); \
+      else k_transfer<T, 1><<<grid, TB, 0, s>>>(G.n, nv, F, imd, ij, dn_, rc_, ps_, G.d_cf, dn, ld, G.d_pat);
       bool staged = G.layout != 0 && cx_transfer_staging();
       for (int v = 0; v < nv && staged; v++) if (((uintptr_t)F.d[v]) & 15) staged = false;
       switch (G.type)
@@ -1425,8 +1524,8 @@ int cx_plan_launch(cx_plan* P, int nvars, const double* const* dD, double* const
             const size_t smb = sizeof(double) * (size_t)G.box_vs * (size_t)nv;
             CX_CHECK(tiled_smem_optin());
             const BoxTile* tl = (const BoxTile*)G.d_tiles;
-            if (mode == 0) k_transfer2b<0><<<G.ntiles, TB, smb, s>>>(tl, G.n, nv, F, imd, ij, dn_, rc_, ps_, G.d_cf, dn, ld);
-            else k_transfer2b<1><<<G.ntiles, TB, smb, s>>>(tl, G.n, nv, F, imd, ij, dn_, rc_, ps_, G.d_cf, dn, ld);
+            if (mode == 0) k_transfer2b<0><<<G.ntiles, TB, smb, s>>>(tl, G.n, nv, F, imd, ij, dn_, rc_, ps_, G.d_cf, dn, ld, G.d_pat);
+            else k_transfer2b<1><<<G.ntiles, TB, smb, s>>>(tl, G.n, nv, F, imd, ij, dn_, rc_, ps_, G.d_cf, dn, ld, G.d_pat);
           }
           else if (staged && G.layout == 1)
           {
@@ -1434,7 +1533,7 @@ int cx_plan_launch(cx_plan* P, int nvars, const double* const* dD, double* const
             int nst = 0;
             const char* mt = getenv("CX_PIPE_MIN_TILES");          // tests lower the threshold
             const int min_tiles = mt ? atoi(mt) : 4 * ctx->sm_count;
-            if (cx_transfer_pipelined() && G.d_tiles && nv <= CX_PIPE_MAXV && G.ntiles >= min_tiles)
+            if (cx_transfer_pipelined() && !G.d_pat && G.d_tiles && nv <= CX_PIPE_MAXV && G.ntiles >= min_tiles)
             {
               nst = (128 + 3 * pipe_stage_bytes(nv) <= 200 * 1024) ? 3 : (128 + 2 * pipe_stage_bytes(nv) <= 220 * 1024) ? 2 : 0;
             }
@@ -1450,8 +1549,8 @@ int cx_plan_launch(cx_plan* P, int nvars, const double* const* dD, double* const
               if (mode == 0) k_transfer2p<0><<<gp, tbp, smb, s>>>(G.n, nv, F, imd, ij, dn_, rc_, G.d_cf, rg, G.ntiles, nst, dn, ld);
               else k_transfer2p<1><<<gp, tbp, smb, s>>>(G.n, nv, F, imd, ij, dn_, ps_, G.d_cf, rg, G.ntiles, nst, dn, ld);
             }
-            else if (mode == 0) k_transfer2s<0><<<g2, tb2s, sizeof(StageSmem), s>>>(G.n, nv, F, imd, ij, P->nptsD, dn_, rc_, ps_, G.d_cf, dn, ld);
-            else k_transfer2s<1><<<g2, tb2s, sizeof(StageSmem), s>>>(G.n, nv, F, imd, ij, P->nptsD, dn_, rc_, ps_, G.d_cf, dn, ld);
+            else if (mode == 0) k_transfer2s<0><<<g2, tb2s, sizeof(StageSmem), s>>>(G.n, nv, F, imd, ij, P->nptsD, dn_, rc_, ps_, G.d_cf, dn, ld, G.d_pat);
+            else k_transfer2s<1><<<g2, tb2s, sizeof(StageSmem), s>>>(G.n, nv, F, imd, ij, P->nptsD, dn_, rc_, ps_, G.d_cf, dn, ld, G.d_pat);
           }
           else { CX_LAUNCH(2) }
           break;
@@ -1485,7 +1584,7 @@ int cx_plan_launch_celln(cx_plan* P, const double* dCellND, double* dCellNR, cud
     switch (G.type)
     {
       case 1: k_transfer_celln<1><<<grid, TB, 0, s>>>(G.n, dCellND, dCellNR, imd, ij, dn_, rc_, G.d_cf); break;
-      case 2: k_transfer_celln<2><<<grid, TB, 0, s>>>(G.n, dCellND, dCellNR, imd, ij, dn_, rc_, G.d_cf); break;
+      case 2: k_transfer_celln<2><<<grid, TB, 0, s>>>(G.n, dCellND, dCellNR, imd, ij, dn_, rc_, G.d_cf, G.d_pat); break;
       case 3: k_transfer_celln<3><<<grid, TB, 0, s>>>(G.n, dCellND, dCellNR, imd, ij, dn_, rc_, G.d_cf); break;
       case 44: k_transfer_celln<44><<<grid, TB, 0, s>>>(G.n, dCellND, dCellNR, imd, ij, dn_, rc_, G.d_cf); break;
       case 22: k_transfer_celln<22><<<grid, TB, 0, s>>>(G.n, dCellND, dCellNR, imd, ij, dn_, rc_, G.d_cf); break;
@@ -1615,7 +1714,7 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
       for (int v = 0; v < nvars; v++) if (((uintptr_t)d_fieldD[p][v]) & 15) S->staged = 0;
       D.donor = P->d_donor + G.first;
       D.idx = (modes[p] == 0 ? P->d_rcv : modes[p] == 1 ? P->d_pos : P->d_seq) + G.first; D.cfT = G.d_cf;
-      D.pad_ = 0; D.dense = modes[p] != 0 ? d_dense[p] : nullptr; D.ld = modes[p] != 0 ? ld[p] : 0;
+      D.pat = G.d_pat; D.pad_ = 0; D.dense = modes[p] != 0 ? d_dense[p] : nullptr; D.ld = modes[p] != 0 ? ld[p] : 0;
       for (int v = 0; v < CX_MAXVARS; v++)
       {
         D.dp[v] = v < nvars ? d_fieldD[p][v] : nullptr;

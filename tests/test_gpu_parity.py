@@ -712,6 +712,90 @@ def test_reference_script_setInterpDataPT_t1_curve_receptors(ctx, loc, order):
                 cases.check_curve_receptors(dict(ctx=ctx), order, loc, storage, pen, nat)
 
 
+def _tetra_like_coefs(rng, typ):
+    """Coefficient list whose type-2 entries look like the reference's tetrahedron weights (InterpData.cpp:621-631:
+    at most 4 distinct doubles among the 8), with degenerate ones (1, 2, 3 distinct values, +0.0 next to -0.0) and
+    ~20 % of entries with 8 distinct values (what an extrapolated entry may hold) mixed in."""
+    out = []
+    for t in typ:
+        if t == 1:
+            out.append(rng.standard_normal(1)); continue
+        r = rng.random()
+        if r < 0.2:
+            out.append(rng.standard_normal(8)); continue
+        nd = 4 if r < 0.8 else int(rng.integers(1, 4))
+        vals = rng.standard_normal(nd)
+        if r > 0.97:
+            vals[0] = 0.
+            if nd > 1: vals[1] = -0.
+        pick = rng.integers(0, nd, 8)
+        pick[:nd] = rng.permutation(nd)
+        out.append(vals[pick])
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize("layout", ["1", "5"])
+def test_transfer_packed_type2_groups(ctx, layout, monkeypatch):
+    """Packed type-2 groups (4 distinct doubles + 16-bit selector per entry, cx_transfer.cu:load_cf2) next to raw
+    ones in the same plan: every launch flavour (single plan in place / dense, plan set in its three output modes,
+    strict cellN) bit-exact vs the reference loops, and identical to the same plan built with CX_PLAN_PACK=0."""
+    from cassiopee_b200 import _lib
+    from oracle import oracle as O
+    monkeypatch.setenv("CX_PLAN_SORT", layout)
+    ni, nj, nk = 67, 29, 23
+    rng = np.random.default_rng(77 + int(layout))
+    nD = ni * nj * nk
+    cells = np.array([(i, j, k) for k in range(1, nk - 1) for j in range(0, nj - 1) for i in (0, 1, 2, 40, 41, 64, 65)], np.int64)
+    cells = cells[rng.permutation(cells.shape[0])]
+    n = cells.shape[0]
+    typ = np.full(n, 2, np.int32); typ[rng.random(n) < 0.05] = 1
+    dnr = (cells[:, 0] + ni * cells[:, 1] + ni * nj * cells[:, 2]).astype(np.int32)
+    nR = n + 9
+    rcv = np.sort(rng.permutation(nR)[:n]).astype(np.int32)
+    cf = _tetra_like_coefs(rng, typ)
+    monkeypatch.setenv("CX_PLAN_PACK", "1")
+    plan = _lib.Plan(ctx, ni, nj, nk, nR, dnr, rcv, typ, cf)
+    monkeypatch.setenv("CX_PLAN_PACK", "0")
+    plan_raw = _lib.Plan(ctx, ni, nj, nk, nR, dnr, rcv, typ, cf)
+    monkeypatch.delenv("CX_PLAN_PACK")
+    assert plan.info()['ngroups'] == plan_raw.info()['ngroups'] + 1          # one more group: packed + raw type 2
+    for nvars in (1, 5, 7, 16):
+        fD = [rng.standard_normal(nD) for _ in range(nvars)]
+        fRo = [np.full(nR, -7.) for _ in range(nvars)]
+        O.transfer(fD, fRo, ni, nj, rcv, dnr, typ, cf)
+        refD = O.transferD(fD, ni, nj, dnr, typ, cf)
+        dD = [_lib.DeviceArray.from_host(ctx, f) for f in fD]
+        for pl in (plan, plan_raw):
+            dR = [_lib.DeviceArray.from_host(ctx, np.full(nR, -7.)) for _ in range(nvars)]
+            pl.transfer_dev([d.ptr for d in dD], [d.ptr for d in dR])
+            ctx.sync()
+            for d, b in zip(dR, fRo):
+                assert np.array_equal(d.download(), b)
+            dense = _lib.DeviceArray(ctx, n * nvars)
+            pl.transferD_dev([d.ptr for d in dD], dense.ptr, n)
+            ctx.sync()
+            assert np.array_equal(dense.download().reshape(nvars, n), refD)
+            dR2 = [_lib.DeviceArray.from_host(ctx, np.full(nR, -7.)) for _ in range(nvars)]
+            dense1 = _lib.DeviceArray(ctx, n * nvars); dense2 = _lib.DeviceArray(ctx, n * nvars)
+            ps = _lib.PlanSet(ctx, nvars, [(pl, 0, [d.ptr for d in dD], [d.ptr for d in dR2], None, 0),
+                                           (pl, 1, [d.ptr for d in dD], None, dense1.ptr, n),
+                                           (pl, 2, [d.ptr for d in dD], None, dense2.ptr, n)])
+            ps.run(); ctx.sync()
+            for d, b in zip(dR2, fRo):
+                assert np.array_equal(d.download(), b)
+            assert np.array_equal(dense1.download().reshape(nvars, n), refD)
+            srt = pl.sorted_rcv()
+            d2 = dense2.download().reshape(nvars, n)
+            for v in range(nvars):
+                got = np.full(nR, -7.); got[srt] = d2[v]
+                assert np.array_equal(got, fRo[v])
+    cD = np.ones(nD); cD[rng.random(nD) < 0.2] = 0.; cD[rng.random(nD) < 0.2] = 2.
+    cRg = np.full(nR, 2.); cRo = np.full(nR, 2.)
+    plan.transfer_celln(cD, cRg)
+    O.transfer_celln(cD, cRo, ni, nj, rcv, dnr, typ, cf)
+    assert np.array_equal(cRg, cRo)
+
+
 @pytest.mark.parametrize("shape", ["xslab", "yslab", "zslab", "volume", "sparse"])
 def test_transfer_box_layout(ctx, shape, monkeypatch):
     """Box layout of the type-2 groups (k_transfer2b / the layout-3 branch of k_transfer_set, forced with
