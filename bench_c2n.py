@@ -120,11 +120,19 @@ def run_c2n(args):
         d2h = sess.download()
     barrier()
     e2e_s = (time.perf_counter() - t0) / ne2e
+    # phase breakdown of one more step (a sync after every phase; diagnostic, outside the timed region)
+    barrier()
+    tp = [time.perf_counter()]
+    sess.upload_donor_fields(); ctx.sync(); tp.append(time.perf_counter())
+    sess.step(); ctx.sync(); tp.append(time.perf_counter())
+    sess.download(); tp.append(time.perf_counter())
+    e2e_phases = [1e3 * (tp[i + 1] - tp[i]) for i in range(3)]
     sess.unpin_host_fields()
 
     B = sum(gather(sess.alg_bytes()))
     ms_max = max(gather(ms))
     e2e_max = max(gather(e2e_s))
+    e2e_ph = np.max(np.array(gather(e2e_phases)), axis=0)
     sid_max = max(gather(sid_s))
     sid_first = max(gather(sid_calls[0]))
     nrcv = sum(gather(nrcv_local))
@@ -166,6 +174,7 @@ def run_c2n(args):
         "clocks": clocks,
         "e2e": {"value": B / e2e_max / 1e9, "unit": UNIT, "ms_per_step": e2e_max * 1e3,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "phases_ms_max_over_ranks": {"upload": float(e2e_ph[0]), "step": float(e2e_ph[1]), "download": float(e2e_ph[2])},
                 "api": "Connector.Mpi.TransferSession upload_donor_fields/step/download (host tree arrays pinned in "
                        "place, copies inside the timed region)"},
         "gpu_launches": int(launches_all),

@@ -129,6 +129,13 @@ def measure_c4(args, ctx, comm, ngpus, rank, world):
         d2h = sess.download()
     barrier()
     e2e_s = (time.perf_counter() - t0) / ne2e
+    # phase breakdown of one more step (a sync after every phase; diagnostic, outside the timed region)
+    barrier()
+    tp = [time.perf_counter()]
+    sess.upload_donor_fields(); ctx.sync(); tp.append(time.perf_counter())
+    sess.step(); ctx.sync(); tp.append(time.perf_counter())
+    sess.download(); tp.append(time.perf_counter())
+    e2e_phases = [1e3 * (tp[i + 1] - tp[i]) for i in range(3)]
     sess.unpin_host_fields()
 
     def gather(v):
@@ -138,6 +145,7 @@ def measure_c4(args, ctx, comm, ngpus, rank, world):
     ms_max = max(gather(ms))
     ms100_max = max(gather(ms100))
     e2e_max = max(gather(e2e_s))
+    e2e_ph = np.max(np.array(gather(e2e_phases)), axis=0)
     sid_max = max(gather(sid_s))
     sid_first = max(gather(sid_calls[0]))
     nrcv = sum(gather(nrcv_local))
@@ -172,6 +180,7 @@ def measure_c4(args, ctx, comm, ngpus, rank, world):
         "clocks": clocks,
         "e2e": {"value": B / e2e_max / 1e9, "unit": "GB/s", "ms_per_step": e2e_max * 1e3,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "phases_ms_max_over_ranks": {"upload": float(e2e_ph[0]), "step": float(e2e_ph[1]), "download": float(e2e_ph[2])},
                 "api": "TransferSession.upload_donor_fields/step/download (host trees in, host trees out)"},
         "gpu_launches": int(launches_all), "comm_overlap": bool(use_graph),
         "roofline": {"bound": "hbm", "achieved": value / ngpus, "peak": peak, "unit": "GB/s per GPU",

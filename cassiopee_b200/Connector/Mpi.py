@@ -284,6 +284,32 @@ def _setInterpData(aR, aD, order=2, penalty=1, nature=0, extrap=1, method='lagra
     return None
 
 
+def setInterpData2(tR, tD, order=2, loc='centers', cartesian=False, comm=None, ctx=None, backend=None):
+    """Interpolation data between two distributed trees; returns the donor tree (Connector/Connector/Mpi.py:1025-1030)."""
+    aD = Internal.copyRef(tD)
+    aR = Internal.copyRef(tR)
+    _setInterpData2(aR, aD, order=order, loc=loc, cartesian=cartesian, comm=comm, ctx=ctx, backend=backend)
+    return aD
+
+
+def _setInterpData2(tR, tD, order=2, loc='centers', cartesian=False, comm=None, ctx=None, backend=None):
+    """Distributed form of Connector.PyTree._setInterpData2 (Connector/Connector/Mpi.py:1031-1105): tR / tD hold the
+    receptor / donor zones this rank owns.  Previous subregions of tD are dropped, a receptor zone without cellN is
+    interpolated as a whole (cellN = 2 for the call), every bbox-intersecting donor zone of tD is a candidate whatever
+    its base (the two trees are different trees), and the ID_* subregions end up under the donor zones' owners.  Same
+    fixed arguments as the reference: nature=1, penalty=1, extrap=1, storage='inverse', sameName=0, itype='chimera'."""
+    varcelln = 'cellN' if loc == 'nodes' else 'centers:cellN'
+    for z in Internal.getZones(tD):
+        z[2][:] = [c for c in z[2] if c[3] != 'ZoneSubRegion_t' and c[0] != 'GridCoordinates#Init']
+    temporary = [z for z in Internal.getZones(tR) if C.isNamePresent(z, varcelln) == -1]
+    for z in temporary: C._initVars(z, varcelln, 2.)
+    _setInterpData(tR, tD, order=order, penalty=1, nature=1, extrap=1, loc=loc, storage='inverse',
+                   interpDataType=0 if cartesian else 1, sameName=0, sameBase=1, itype='chimera', comm=comm, ctx=ctx,
+                   backend=backend)
+    for z in temporary: C._rmVars(z, [varcelln])
+    return None
+
+
 class _Single:
     rank = 0
     size = 1

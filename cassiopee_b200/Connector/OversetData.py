@@ -56,104 +56,88 @@ def _zoneArray(z, withCellN=True):
     return [names, numpy.ascontiguousarray(numpy.stack(rows)), ni, nj, nk]
 
 
+def _governingModel(node, default='None'):
+    g = Internal.getNodeFromName2(node, 'GoverningEquations')
+    return default if g is None else Internal.getValue(g)
+
+
+# (model that makes a pair mixed, flag node put on the subregion): Connector/Connector/OversetData.py:1741-1748
+_MIXED_MODEL_FLAGS = (('NSTurbulent', 'RANSLES'), ('LBMLaminar', 'NSLBM'))
+
+
 def _adaptForRANSLES__(tR, tD, dictOfModels=None):
-    """Flag RANS/LES and NS/LBM donor-receptor pairs (OversetData.py:1702-1750)."""
-    zrdict = {}
+    """Flag the subregions whose donor and receptor zones solve different equation sets (RANS next to LES, Navier-Stokes
+    next to LBM) with a `RANSLES` / `NSLBM` child, like Connector/Connector/OversetData.py:1702-1750.  A zone's model is
+    its own GoverningEquations node, else its base's, else 'None' (such zones never flag anything)."""
     if dictOfModels is None:
         dictOfModels = {}
-        for tp in [tR, tD]:
-            bases = Internal.getBases(tp)
-            if bases != []:
-                for b in bases:
-                    model_b = Internal.getNodeFromName2(b, 'GoverningEquations')
-                    model_b = Internal.getValue(model_b) if model_b is not None else 'None'
-                    for z in Internal.getZones(b):
-                        model = Internal.getNodeFromName2(z, 'GoverningEquations')
-                        dictOfModels[z[0]] = model_b if model is None else Internal.getValue(model)
-            else:
-                for z in Internal.getZones(tp):
-                    model = Internal.getNodeFromName2(z, 'GoverningEquations')
-                    dictOfModels[z[0]] = 'None' if model is None else Internal.getValue(model)
-    for zr in Internal.getZones(tR):
-        zrdict[zr[0]] = zr
+        for tree in (tR, tD):
+            bases = Internal.getBases(tree)
+            groups = [(b, _governingModel(b)) for b in bases] if bases != [] else [(tree, 'None')]
+            for holder, inherited in groups:
+                dictOfModels.update({z[0]: _governingModel(z, inherited) for z in Internal.getZones(holder)})
+    receptors = {z[0] for z in Internal.getZones(tR)}
+    one = lambda: numpy.ones(1, dtype=Internal.E_NpyInt)
     for zd in Internal.getZones(tD):
-        model_zd = dictOfModels.get(zd[0], 'None')
+        md = dictOfModels.get(zd[0], 'None')
+        if md == 'None': continue
         for s in Internal.getNodesFromType1(zd, 'ZoneSubRegion_t'):
-            zrcvname = Internal.getValue(s)
-            if zrcvname in zrdict:
-                model_zr = dictOfModels.get(zrcvname, 'None')
-                if model_zr != 'None' and model_zd != 'None':
-                    if (model_zr == 'NSTurbulent' or model_zd == 'NSTurbulent') and model_zr != model_zd:
-                        Internal.createUniqueChild(s, 'RANSLES', 'DataArray_t', numpy.ones(1, dtype=Internal.E_NpyInt))
-                    if (model_zr == 'LBMLaminar' or model_zd == 'LBMLaminar') and model_zr != model_zd:
-                        Internal.createUniqueChild(s, 'NSLBM', 'DataArray_t', numpy.ones(1, dtype=Internal.E_NpyInt))
+            zrname = Internal.getValue(s)
+            mr = dictOfModels.get(zrname, 'None') if zrname in receptors else 'None'
+            if mr == 'None' or mr == md: continue
+            for model, flag in _MIXED_MODEL_FLAGS:
+                if model in (mr, md): Internal.createUniqueChild(s, flag, 'DataArray_t', one())
     return None
+
+
+_REGION_PREFIX = {'chimera': 'ID_', 'abutting': 'ID_', 'ibc': 'IBCD_', 'ibc2': '2_IBCD_'}
 
 
 def _createInterpRegion__(z, zname, pointlist, pointlistdonor, interpCoef, interpType, interpVol, indicesExtrap,
                           indicesOrphan, EXDir=[], pointlistdonorExtC=None, tag='Receiver', loc='centers',
                           itype='chimera', prefix=None, RotationAngle=None, RotationCenter=None):
-    """Store one (donor, receptor) interpData block as a ZoneSubRegion_t, same
-    node names / order / concatenation rule as OversetData.py:1752-1884."""
+    """Store one (donor, receptor) interpData block as a ZoneSubRegion_t of zone z.  Node names, their order and the
+    way a second block for the same pair is merged are the storage contract of
+    Connector/Connector/OversetData.py:1752-1884; here they are one table (`payload`) and one merge rule per node."""
     if loc == 'faces':
         raise NotImplementedError("_createInterpRegion__: loc='faces' is not on the device path.")
-    if prefix is None:
-        nameSubRegion = {'chimera': 'ID_', 'abutting': 'ID_', 'ibc': 'IBCD_', 'ibc2': '2_IBCD_'}[itype] + zname
+    name = (_REGION_PREFIX[itype] if prefix is None else prefix) + zname
+    if RotationAngle is not None: RotationAngle[2] = []     # the DimensionalUnits child is not stored
+    extC = None
+    if pointlistdonorExtC is not None: extC = 'PointListDonorExtC' if tag == 'Receiver' else 'PointListExtC'
+    # (node name, value, CGNS type, stored when) in storage order
+    payload = [('PointList', pointlist, 'IndexArray_t', True),
+               ('PointListDonor', pointlistdonor, 'IndexArray_t', True),
+               (extC, pointlistdonorExtC, 'IndexArray_t', extC is not None),
+               ('InterpolantsDonor', interpCoef, 'DataArray_t', True),
+               ('InterpolantsVol', interpVol, 'DataArray_t', interpVol.size > 0),
+               ('InterpolantsType', interpType, 'DataArray_t', True),
+               ('OrphanPointList', indicesOrphan, 'DataArray_t', indicesOrphan.size > 0),
+               ('ExtrapPointList', indicesExtrap, 'DataArray_t', indicesExtrap.size > 0)]
+    found = Internal.getNodesFromName1(z, name)
+    if found == []:
+        region = Internal.createChild(z, name, 'ZoneSubRegion_t', value=zname)
+        Internal._createChild(region, 'ZoneRole', 'DataArray_t', value=tag)
     else:
-        nameSubRegion = prefix + zname
-    if RotationAngle is not None: RotationAngle[2] = []     # remove the DimensionalUnits child node
-    extC = None if pointlistdonorExtC is None else ('PointListDonorExtC' if tag == 'Receiver' else 'PointListExtC')
-    zsr = Internal.getNodesFromName1(z, nameSubRegion)
-    if zsr == []:
-        info = Internal.createChild(z, nameSubRegion, 'ZoneSubRegion_t', value=zname)
-        Internal._createChild(info, 'ZoneRole', 'DataArray_t', value=tag)
+        region = found[0]
+    if Internal.getNodesFromName1(region, 'InterpolantsDonor') == []:
+        # first block of this pair (the region may already exist, e.g. created by a periodicity pass)
         if loc == 'centers':
-            Internal._createChild(info, 'GridLocation', 'GridLocation_t', value='CellCenter')
-        info[2].append(['PointList', pointlist, [], 'IndexArray_t'])
-        info[2].append(['PointListDonor', pointlistdonor, [], 'IndexArray_t'])
-        if extC is not None: info[2].append([extC, pointlistdonorExtC, [], 'IndexArray_t'])
-        info[2].append(['InterpolantsDonor', interpCoef, [], 'DataArray_t'])
-        if interpVol.size > 0:
-            info[2].append(['InterpolantsVol', interpVol, [], 'DataArray_t'])
-        info[2].append(['InterpolantsType', interpType, [], 'DataArray_t'])
-        if indicesOrphan.size > 0:
-            info[2].append(['OrphanPointList', numpy.unique(indicesOrphan), [], 'DataArray_t'])
-        if indicesExtrap.size > 0:
-            info[2].append(['ExtrapPointList', indicesExtrap, [], 'DataArray_t'])
-        if RotationAngle is not None: info[2].append(RotationAngle)
-        if RotationCenter is not None: info[2].append(RotationCenter)
-    else:
-        s = zsr[0]
-        intd = Internal.getNodesFromName1(s, 'InterpolantsDonor')
-        if intd == []:
-            if loc == 'centers':
-                Internal._createChild(s, 'GridLocation', 'GridLocation_t', value='CellCenter')
-            s[2].append(['PointList', pointlist, [], 'IndexArray_t'])
-            s[2].append(['PointListDonor', pointlistdonor, [], 'IndexArray_t'])
-            if extC is not None: s[2].append([extC, pointlistdonorExtC, [], 'IndexArray_t'])
-            s[2].append(['InterpolantsDonor', interpCoef, [], 'DataArray_t'])
-            if interpVol.size > 0: s[2].append(['InterpolantsVol', interpVol, [], 'DataArray_t'])
-            s[2].append(['InterpolantsType', interpType, [], 'DataArray_t'])
-            if indicesOrphan.size > 0:
-                s[2].append(['OrphanPointList', numpy.unique(indicesOrphan), [], 'DataArray_t'])
-            if indicesExtrap.size > 0: s[2].append(['ExtrapPointList', indicesExtrap, [], 'DataArray_t'])
-            if RotationAngle is not None: s[2].append(RotationAngle)
-            if RotationCenter is not None: s[2].append(RotationCenter)
-        else:
-            intd[0][1] = numpy.concatenate((intd[0][1], interpCoef))
-            intv = Internal.getNodesFromName1(s, 'InterpolantsVol')
-            if intv != [] and interpVol.size > 0: intv[0][1] = numpy.concatenate((intv[0][1], interpVol))
-            for name, arr in (('InterpolantsType', interpType), ('PointList', pointlist),
-                              ('PointListDonor', pointlistdonor)):
-                node = Internal.getNodesFromName1(s, name)
-                if node != []: node[0][1] = numpy.concatenate((node[0][1], arr))
-            for name in ('PointListExtC', 'PointListDonorExtC'):
-                node = Internal.getNodesFromName1(s, name)
-                if node != []: node[0][1] = numpy.concatenate((node[0][1], pointlistdonorExtC))
-            node = Internal.getNodesFromName1(s, 'OrphanPointList')
-            if node != []: node[0][1] = numpy.unique(indicesOrphan)
-            node = Internal.getNodesFromName1(s, 'ExtrapPointList')
-            if node != []: node[0][1] = numpy.concatenate((node[0][1], indicesExtrap))
+            Internal._createChild(region, 'GridLocation', 'GridLocation_t', value='CellCenter')
+        for nm, val, typ, keep in payload:
+            if keep: region[2].append([nm, numpy.unique(val) if nm == 'OrphanPointList' else val, [], typ])
+        region[2] += [n for n in (RotationAngle, RotationCenter) if n is not None]
+        return None
+    # further block: lists are appended to the nodes that exist (a node absent from the first block stays absent),
+    # the orphan list is replaced by the new one, both ExtC flavours receive the new ExtC list
+    incoming = {nm: val for nm, val, _, _ in payload if nm is not None}
+    for nm in ('PointListExtC', 'PointListDonorExtC'): incoming[nm] = pointlistdonorExtC
+    for node in region[2]:
+        nm = node[0]
+        if nm not in incoming or incoming[nm] is None: continue
+        if nm == 'OrphanPointList': node[1] = numpy.unique(indicesOrphan)
+        elif nm == 'InterpolantsVol' and interpVol.size == 0: continue
+        else: node[1] = numpy.concatenate((node[1], incoming[nm]))
     return None
 
 
@@ -329,6 +313,28 @@ def setInterpData(tR, tD, order=2, penalty=1, nature=0, extrap=1,
                    dictOfModels=dictOfModels)
     if storage == 'direct': return aR
     else: return aD
+
+
+def setInterpData2(aR, aD, order=2, loc='centers', cartesian=False):
+    """Interpolation data between two different trees, every default the solver set-up uses (nature=1, penalty=1,
+    extrap=1, storage='inverse', sameName=0); returns the donor tree (Connector/Connector/OversetData.py:1083-1087)."""
+    aD = Internal.copyRef(aD)
+    aR = Internal.copyRef(aR)
+    _setInterpData2(aR, aD, order=order, loc=loc, cartesian=cartesian)
+    return aD
+
+
+def _setInterpData2(aR, aD, order=2, loc='centers', cartesian=False):
+    """In-place form (OversetData.py:1089-1101).  A receptor tree without cellN is interpolated as a whole: cellN = 2
+    is put on it for the call and removed afterwards.  cartesian=True: donors located in closed form
+    (interpDataType=0)."""
+    varcelln = 'cellN' if loc == 'nodes' else 'centers:cellN'
+    temporary = C.isNamePresent(aR, varcelln) == -1
+    if temporary: C._initVars(aR, varcelln, 2.)
+    _setInterpData(aR, aD, order=order, penalty=1, nature=1, extrap=1, method='lagrangian', loc=loc,
+                   storage='inverse', interpDataType=0 if cartesian else 1, sameName=0, itype='chimera')
+    if temporary: C._rmVars(aR, [varcelln])
+    return None
 
 
 def _setInterpData(aR, aD, order=2, penalty=1, nature=0, extrap=1,

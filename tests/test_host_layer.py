@@ -447,3 +447,47 @@ def test_create_interp_region_node_order_and_concatenation():
                                      'InterpolantsDonor', 'InterpolantsType']
     with pytest.raises(NotImplementedError):
         X._createInterpRegion__(z2, 'D', i32(1), i32(2), np.ones(8), i32(2), np.array([]), i32(), i32(), loc='faces')
+
+
+def test_set_interp_data2_wrappers(monkeypatch):
+    """setInterpData2 / _setInterpData2 (OversetData.py:1083-1101) and their distributed forms (Connector/Mpi.py:1025-1105):
+    fixed arguments (nature=1, penalty=1, extrap=1, inverse storage, sameName=0), cellN = 2 put on a receptor tree that
+    has none and removed afterwards, previous subregions of the donor tree dropped by the distributed form, the inputs
+    of the copying forms untouched.  Same trees as Connector/test/setInterpData2PT_m1.py (cart 11^3 donors,
+    cart 21^3 receptors of half the spacing)."""
+    import cassiopee_b200.Connector.PyTree as XP
+    import cassiopee_b200.Connector.Mpi as Xmpi
+    from cassiopee_b200 import _lib
+    from oracle import oracle as O
+    monkeypatch.setattr(_lib, 'DeviceBackend', lambda ctx: OracleBackend())
+    monkeypatch.setattr(_lib, 'default_context', lambda *a: None)
+    aD = G.cart((0, 0, 0), (1, 1, 1), (11, 11, 11), name='dnr')
+    aR = G.cart((0, 0, 0), (0.5, 0.5, 0.5), (21, 21, 21), name='rcv')
+    tD = C.newPyTree(['BD', aD]); tR = C.newPyTree(['BR', aR])
+    out = XP.setInterpData2(tR, tD, order=2, loc='centers')
+    assert C.isNamePresent(tR, 'centers:cellN') == -1 and not Internal.getNodesFromType2(tD, 'ZoneSubRegion_t')
+    s = Internal.getNodeFromName1(Internal.getZones(out)[0], 'ID_rcv')
+    assert s is not None and Internal.getValue(Internal.getNodeFromName1(s, 'ZoneRole')) == 'Donor'
+    # oracle on the same points: all 20^3 centres of the receptor zone, donors = the nodes of the donor tree
+    xr, yr, zr = [np.ascontiguousarray(C.node2CenterArray(v).reshape(-1, order='F')) for v in C.getCoords(aR)]
+    xd, yd, zd = [v.reshape(-1, order='F') for v in C.getCoords(aD)]
+    ref = O.set_interp_data(xr, yr, zr, [O.RefZone(11, 11, 11, xd, yd, zd, np.ones(xd.size))], order=2, nature=1,
+                            penalty=1, extrap=1)
+    for name, k in (('PointList', 1), ('PointListDonor', 0), ('InterpolantsType', 2), ('InterpolantsDonor', 3)):
+        assert np.array_equal(Internal.getNodeFromName1(s, name)[1], ref[k][0]), name
+    # in-place distributed form, single rank: stale subregions of the donor tree are dropped first
+    tD2 = Internal.copyRef(out); tR2 = C.newPyTree(['BR', aR])
+    Internal.getZones(tD2)[0][2].append(['ID_old', np.zeros(1), [], 'ZoneSubRegion_t'])
+    Xmpi._setInterpData2(tR2, tD2, loc='centers', cartesian=False, comm=None, backend=OracleBackend())
+    subs = Internal.getNodesFromType1(Internal.getZones(tD2)[0], 'ZoneSubRegion_t')
+    assert [n[0] for n in subs] == ['ID_rcv']
+    assert np.array_equal(Internal.getNodeFromName1(subs[0], 'InterpolantsDonor')[1], ref[3][0])
+    assert C.isNamePresent(tR2, 'centers:cellN') == -1
+    # a receptor tree that carries its own cellN keeps it, and only its cellN == 2 points are interpolated
+    tR3 = C.newPyTree(['BR', G.cart((0, 0, 0), (0.5, 0.5, 0.5), (21, 21, 21), name='rcv')])
+    cn = np.ones((20, 20, 20), order='F'); cn[:2] = 2.
+    C._initVars(tR3, 'centers:cellN', cn)
+    out3 = Xmpi.setInterpData2(tR3, tD, loc='centers', comm=None, backend=OracleBackend())
+    s3 = Internal.getNodeFromName1(Internal.getZones(out3)[0], 'ID_rcv')
+    assert Internal.getNodeFromName1(s3, 'PointListDonor')[1].size == 2 * 20 * 20
+    assert C.isNamePresent(tR3, 'centers:cellN') == 1
