@@ -6,7 +6,9 @@ from .OversetData import (setInterpData, _setInterpData, setInterpData2, _setInt
                           _createInterpRegion__, _addCellN__, applyBCOverlaps, _applyBCOverlaps,
                           getIntersectingDomains, setHoleInterpolatedPoints, _setHoleInterpolatedPoints)
 from .Connector import setInterpData__, getInterpolatedPoints__, createHooks__
+from .compactTransfers import ___setInterpTransfers, miseAPlatDonorTree__
 
 __all__ = ['setInterpData', '_setInterpData', 'setInterpData2', '_setInterpData2', 'setInterpTransfers', '_setInterpTransfers',
            'setInterpTransfersD', '_setInterpTransfersD', 'applyBCOverlaps', '_applyBCOverlaps',
-           'getIntersectingDomains', 'setHoleInterpolatedPoints', '_setHoleInterpolatedPoints']
+           'getIntersectingDomains', 'setHoleInterpolatedPoints', '_setHoleInterpolatedPoints',
+           'miseAPlatDonorTree__', '___setInterpTransfers']

@@ -241,6 +241,31 @@ def transfer_celln(cellND, cellNR, imd, jmd, rcv, dnr, typ, coefs):
                              rcv.ctypes.data, dnr.ctypes.data, typ.ctypes.data, coefs.ctypes.data)
 
 
+def transfer_compact(roR, roD, zparams, dtloc, param_int, param_real, vartype=1, type_transfert=0, no_transfert=1,
+                     nstep=1, threadmax_sdm=1):
+    """The reference's ___setInterpTransfers reader (setInterpTransfers.cpp:761-1410) with its own arithmetic fragments,
+    chimera subset (oracle/ref_driver.cpp:ref_transfer_compact).  roR[nd] / roD[nd]: compact solution blocks (numpy
+    float64, nvars*NDIMDX values) of the receptor / donor zones, updated in place; zparams[nd]: the zones'
+    Parameter_int (int32).  Returns the number of racs transferred."""
+    n = len(roR)
+    assert len(roD) == n and len(zparams) == n
+    zp = [np.ascontiguousarray(z, dtype=np.int32) for z in zparams]
+    R = (ctypes.c_void_p * n)(*[a.ctypes.data for a in roR])
+    D = (ctypes.c_void_p * n)(*[a.ctypes.data for a in roD])
+    Z = (ctypes.c_void_p * n)(*[a.ctypes.data for a in zp])
+    dt = np.ascontiguousarray(dtloc, dtype=np.int32); pi = np.ascontiguousarray(param_int, dtype=np.int32)
+    pr = np.ascontiguousarray(param_real, dtype=np.float64)
+    f = lib().ref_transfer_compact
+    f.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                  ctypes.c_void_p] + [ctypes.c_int] * 5
+    f.restype = ctypes.c_int
+    rc = f(n, R, D, Z, dt.ctypes.data, pi.ctypes.data, pr.ctypes.data, int(vartype), int(type_transfert),
+           int(no_transfert), int(nstep), int(threadmax_sdm))
+    if rc < 0:
+        raise RuntimeError("ref_transfer_compact: rac outside the chimera subset")
+    return rc
+
+
 def rotate(fieldsR, rcv, angles, posv=(-1, -1, -1), posm=(-1, -1, -1)):
     """Reference periodicity-by-rotation correction (includeTransfers.h) in place on the receptor fields."""
     rcv = _i32(rcv)

@@ -308,6 +308,142 @@ void ref_rotate(int nvars_, double** rcvFields, int nrcv, const int* rcvPts_,
   }
 }
 
+/* ___setInterpTransfers (setInterpTransfers.cpp:761-1410), the transfer the Fast solver calls on the flattened
+ * donor tree (param_int / param_real of compactTransfers.py:miseAPlatDonorTree__): the reader loop restated for
+ * chimera (ID) racs of structured, cell-centred zones with 5 or 6 equations, steady racs, implicit / global
+ * explicit time stepping (exploc == 0); the per-type arithmetic is the reference's own fragments
+ * commonInterpTransfers_reorder_5eq.h / _6eq.h, #included.  Sequential (one "thread": pt_deb = ideb, pt_fin = ifin;
+ * the reference only splits each type range over its OpenMP threads).
+ *   roR[nd], roD[nd]  first variable of zone nd's compact solution (receptor tree centres / donor tree nodes)
+ *   zparam[nd]        zone nd's .Solver#ownData/Parameter_int (NIJK, NDIMDX, IFLOW, LEVEL are read)
+ *   threadmax_sdm     __NUMTHREADS__ of the build that wrote dtloc (stride of its task records)
+ * Returns the number of racs transferred, or -1 for a rac outside that scope. */
+#define REF_NIJK 0
+#define REF_IFLOW 27
+#define REF_NDIMDX 41
+#define REF_LEVEL 53
+int ref_transfer_compact(int nidomR, double** roR, double** roD, int** zparam, const int* iptdtloc,
+                         const int* ipt_param_int, const double* ipt_param_real, int vartype, int type_transfert,
+                         int no_transfert, int nstep, int threadmax_sdm)
+{
+  E_Int TypeTransfert = type_transfert;
+  E_Int pass_deb, pass_fin;
+  if     (TypeTransfert==0) { pass_deb =1; pass_fin =2; }//ID
+  else if(TypeTransfert==1) { pass_deb =0; pass_fin =1; }//IBCD
+  else                      { pass_deb =0; pass_fin =2; }//ALL
+  E_Int NoTransfert = no_transfert;
+  E_Int nvars;
+  if (vartype <= 3 && vartype >= 1) nvars = 5; else nvars = 6;
+
+  E_Int nbcomIBC = ipt_param_int[2];
+  E_Int nbcomID  = ipt_param_int[3+nbcomIBC];
+  E_Int shift_graph = nbcomIBC + nbcomID + 3;
+  E_Int ech            = ipt_param_int[ NoTransfert +shift_graph];
+  E_Int nrac           = ipt_param_int[ ech +1 ];
+  E_Int nrac_inst      = ipt_param_int[ ech +2 ];
+  E_Int timelevel      = ipt_param_int[ ech +3 ];
+  E_Int nrac_steady    = nrac - nrac_inst;
+  if (nrac_inst > 0) return -1;
+
+  std::vector<E_Int> impli_local(nidomR, 0);
+  E_Int nssiter  = iptdtloc[0];
+  E_Int shift_omp= iptdtloc[11];
+  const E_Int* ipt_omp = iptdtloc + shift_omp;
+  E_Int nbtask   = ipt_omp[nstep-1];
+  E_Int ptiter   = ipt_omp[nssiter+ nstep-1];
+  for (E_Int ntask = 0; ntask < nbtask; ntask++)
+  {
+    E_Int pttask = ptiter + ntask*(6+threadmax_sdm*7);
+    E_Int nd = ipt_omp[ pttask ];
+    impli_local[nd] = 1;
+  }
+  E_Int maxlevel      =  iptdtloc[ 9];
+  E_Int it_cycl_lbm   =  iptdtloc[10];
+  E_Int max_it        = pow(2, maxlevel-1);
+  E_Int level_next_it =  maxlevel;
+  if (it_cycl_lbm != max_it -1 ) { level_next_it = iptdtloc[13 +it_cycl_lbm +1];}
+  for (E_Int nd = 0; nd < nidomR; nd++)
+  {
+    if (zparam[nd][REF_IFLOW] == 4)
+    {
+      E_Int level = zparam[nd][REF_LEVEL];
+      if (level <=level_next_it +1 ){impli_local[nd]=1;}
+      else                          {impli_local[nd]=0;}
+    }
+  }
+
+  std::vector<E_Float*> RcvFields(nvars), DnrFields(nvars);
+  E_Float** vectOfRcvFields = RcvFields.data();
+  E_Float** vectOfDnrFields = DnrFields.data();
+  E_Int done = 0;
+  E_Int indR, type;
+  E_Int indD0, indD, ncfLoc, indCoef, noi, sizecoefs, imd, jmd, imdjmd;
+  E_Int meshtype = 1; E_Int cnNfldD = 0; E_Int* ptrcnd = NULL;
+  (void)ncfLoc; (void)indD; (void)indD0; (void)cnNfldD; (void)ptrcnd;
+  for (E_Int ipass_typ=pass_deb; ipass_typ < pass_fin; ipass_typ++)
+  {
+    for (E_Int irac=0; irac< nrac_steady; irac++)
+    {
+      E_Int shift_rac =  ech + 4 + timelevel*2 + irac;
+      E_Int NoD0 =  ipt_param_int[ shift_rac + nrac*5 ];
+      if (impli_local[NoD0] != 1) continue;                  // autorisation_transferts (:1033-1038)
+      E_Int ibcType =  ipt_param_int[shift_rac+nrac*3];
+      E_Int ibc = 1;
+      if (ibcType < 0) ibc = 0;
+      if(1-ibc != ipass_typ)  continue;
+      if (ibc == 1) return -1;
+      E_Int NoD      =  ipt_param_int[ shift_rac + nrac*5  ];
+      E_Int loc      =  ipt_param_int[ shift_rac + nrac*9  ];
+      E_Int NoR      =  ipt_param_int[ shift_rac + nrac*11 ];
+      E_Int nvars_loc=  ipt_param_int[ shift_rac + nrac*13 ];
+      E_Int rotation =  ipt_param_int[ shift_rac + nrac*14 ];
+      if (loc == 0 || rotation != 0 || !(nvars_loc == 5 || nvars_loc == 6) || nvars_loc > nvars) return -1;
+      for (E_Int eq = 0; eq < nvars_loc; eq++)
+      {
+        vectOfRcvFields[eq] = roR[ NoR] + eq*zparam[ NoR][ REF_NDIMDX ];
+        vectOfDnrFields[eq] = roD[ NoD] + eq*zparam[ NoD][ REF_NDIMDX ];
+      }
+      imd= zparam[ NoD ][ REF_NIJK ]; jmd= zparam[ NoD ][ REF_NIJK+1];
+      imdjmd = imd*jmd;
+
+      E_Int pos;
+      pos  = ipt_param_int[ shift_rac + nrac*7 ]; const E_Int* ntype    = ipt_param_int  + pos;
+      pos  = pos +1 + ntype[0]                  ; const E_Int* types    = ipt_param_int  + pos;
+      pos  = ipt_param_int[ shift_rac + nrac*6 ]; const E_Int* donorPts = ipt_param_int  + pos;
+      pos  = ipt_param_int[ shift_rac + nrac*12]; const E_Int* rcvPts   = ipt_param_int  + pos;
+      pos  = ipt_param_int[ shift_rac + nrac*8 ]; const E_Float* ptrCoefs = ipt_param_real + pos;
+
+      E_Int ideb      = 0;
+      E_Int ifin      = 0;
+      E_Int shiftCoef = 0;
+      E_Int shiftDonor  = 0;
+      for (E_Int ndtyp = 0; ndtyp < ntype[0]; ndtyp++)
+      {
+        type      = types[ifin];
+        SIZECF(type, meshtype, sizecoefs);
+        ifin =  ifin + ntype[ 1 + ndtyp];
+        E_Int pt_deb = ideb, pt_fin = ifin;
+        noi       = shiftDonor;
+        indCoef   = (pt_deb-ideb)*sizecoefs +  shiftCoef;
+        E_Int shiftv  =0;
+        if (nvars_loc==5)
+        {
+#           include "commonInterpTransfers_reorder_5eq.h"
+        }
+        else
+        {
+#           include "commonInterpTransfers_reorder_6eq.h"
+        }
+        ideb       =  ideb + ntype[ 1 + ndtyp];
+        shiftCoef  = shiftCoef  +  ntype[1+ndtyp]*sizecoefs;
+        shiftDonor = shiftDonor +  ntype[1+ndtyp];
+      }
+      done++;
+    }
+  }
+  return done;
+}
+
 /* K_METRIC::compVolOfStructCell3D (selection volume, for unit checks). */
 double ref_cell_volume(void* h, int indnode)
 {
