@@ -34,9 +34,37 @@ sys.path.insert(0, ROOT)
 METRIC = "setInterpTransfers_algorithmic_GBps"
 UNIT = "GB/s"
 NVARS_C2 = 5
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_transfer2s<0> launch on C2a (5 vars), from the
-# `ncu --set full` capture summarised in profiles/r01_f_summary.md (1.690317 GB + 656.901 MB)
-NCU_TRAFFIC_C2A_5VARS = 1690317000 + 656901376
+
+
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, as extracted from an
+    `ncu --set full` capture of this very command by tools/ncu_traffic.py into profiles/ncu_traffic.json (committed
+    next to the .ncu-rep summary it came from).  None when no capture of that workload is on file: never a constant
+    typed into the source."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        e = json.load(open(p))[key]
+        return int(e["bytes_per_launch"]), "%s (%s, kernel %s)" % (e["source"], e["captured"], e["kernel"])
+    except Exception:
+        return None, None
+
+
+def config_c2(nvars, scale, ngpus=1):
+    """`config` of the C2 lines: static description only, so that both arms (ours, --impl reference) emit the same
+    dict for the same command; measured counts go under "stats"."""
+    if ngpus == 1:
+        wl = ("C2a: cart 256^3 background -> cylinder O-grid (513,129,257) receptors, order 2, nature=1 penalty=1 "
+              "extrap=1, %d vars" % nvars) if scale == 1.0 else "C2a scaled x%g, %d vars" % (scale, nvars)
+        par = "1 GPU"
+    else:
+        wl = ("C2a per GPU (cart 256^3 background -> cylinder O-grid (513,129,257) receptors, order 2, nature=1 "
+              "penalty=1 extrap=1, %d vars), %d bodies in a row, neighbouring backgrounds overlap by 8 cells and "
+              "exchange 2-layer fringes GPU to GPU; C4/C5 cluster under c4_c5" % (nvars, ngpus))
+        if scale != 1.0: wl = "scaled x%g: " % scale + wl
+        par = "one body (2 zones) per GPU by .Solver#Param/proc"
+    return {"workload": wl, "nvars": nvars, "n_gpus": ngpus,
+            "l2": "inputs larger than L2 (about 2.3 GB of plan + field traffic per GPU and step, L2 126 MB); no flush",
+            "parallelism": par}
 
 
 def measured_peaks():
@@ -242,29 +270,37 @@ def run_c2(args):
 
     extra = None if args.quick else extra_legs(ctx, Bg, Oc, zone, dxr, dyr, dzr, pD, nvars)
     peak, how = measured_peaks()
+    traffic, traffic_src = ncu_traffic("c2a_%dvars" % nvars) if args.scale == 1.0 else (None, None)
+    # the multi-GPU config of BASELINE.json (C4/C5) at its N=1 point: 8 zones of 100^3 on this GPU, so that the
+    # per-N lines of a scaling run can be compared like with like
+    c4 = None
+    if not args.quick and args.scale == 1.0:
+        del plan, dD, dR, zone, dxr, dyr, dzr
+        import gc
+        gc.collect()
+        from bench_c4 import measure_c4
+        try:
+            c4 = measure_c4(args, ctx, None, 1, 0, 1)
+        except Exception as e:
+            c4 = {"unavailable": str(e)}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2a: cart 256^3 background -> cylinder O-grid (513,129,257) receptors, order 2, "
-                               "nature=1 penalty=1 extrap=1, %d vars" % nvars if args.scale == 1.0 else
-                               "C2a scaled x%g" % args.scale,
-                   "receptors": int(n), "donor_nodes": int(Bg.npts), "nvars": nvars, "alg_bytes_per_step": int(B),
-                   "distinct_donor_nodes": int(pinfo["distinct"]),
-                   "l2": "inputs larger than L2 (plan+fields %.2f GB per step, L2 126 MB); no flush" %
-                         ((B + 8 * nvars * (Bg.npts - pinfo["distinct"])) / 1e9),
-                   "parallelism": "1 GPU"},
+        "config": config_c2(nvars, args.scale),
+        "stats": {"receptors": int(n), "donor_nodes": int(Bg.npts), "alg_bytes_per_step": int(B),
+                  "distinct_donor_nodes": int(pinfo["distinct"])},
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": value, "peak": peak, "unit": "GB/s", "frac": value / peak,
-                     "traffic": NCU_TRAFFIC_C2A_5VARS if (args.scale == 1.0 and nvars == 5) else None,
-                     "traffic_source": "profiles/r01_f_summary.md (ncu --set full, one launch)",
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": how, "kernel": "k_transfer2s<0>",
                      "frac_of_nominal_8TBps": value / 8000.0},
         "cpu_baseline": cpu,
         "set_interp_data": sid,
         "other_configs": extra,
+        "c4_c5": c4,
     }
     print(json.dumps(line))
 
@@ -352,9 +388,12 @@ def extra_legs(ctx, Bg, Oc, zone, dxr, dyr, dzr, pD, nvars):
         if stride == 1:
             dx, dy, dz, n = dxr, dyr, dzr, nrcv
         else:
-            dx = _lib.DeviceArray.from_host(ctx, np.ascontiguousarray(Oc.x[::stride]))
-            dy = _lib.DeviceArray.from_host(ctx, np.ascontiguousarray(Oc.y[::stride]))
-            dz = _lib.DeviceArray.from_host(ctx, np.ascontiguousarray(Oc.z[::stride]))
+            # 1/16 of the O-grid as one block of consecutive k-planes: neighbouring receptors share Lagrange stencils
+            # exactly like in the full case (a strided sample would hide that and the per-stencil solve)
+            m = nrcv // stride
+            dx = _lib.DeviceArray.from_host(ctx, np.ascontiguousarray(Oc.x[:m]))
+            dy = _lib.DeviceArray.from_host(ctx, np.ascontiguousarray(Oc.y[:m]))
+            dz = _lib.DeviceArray.from_host(ctx, np.ascontiguousarray(Oc.z[:m]))
             n = dx.n
         ctx.sync(); t0 = time.perf_counter()
         r = _lib.set_interp_data_dev(ctx, n, dx.ptr, dy.ptr, dz.ptr, [zone], order, 1, 1, 1)
@@ -376,7 +415,7 @@ def extra_legs(ctx, Bg, Oc, zone, dxr, dyr, dzr, pD, nvars):
         B = plan.alg_bytes(nvars)
         out["lagrange_order%d" % order] = {
             "set_interp_data": {"value": n / dt, "unit": "receptor pts/s", "ms": dt * 1e3, "receptors": int(n),
-                                "sample": "all O-grid nodes" if stride == 1 else "every %dth O-grid node" % stride,
+                                "sample": "all O-grid nodes" if stride == 1 else "the first 1/%d of the O-grid nodes (consecutive k-planes)" % stride,
                                 "gj_gflops_reference_count": gj_flops(order ** 3) * n / dt / 1e9,
                                 "types": {int(k): int(v) for k, v in zip(*np.unique(typ, return_counts=True))}},
             "transfer": {"value": B / (tms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": tms, "alg_bytes_per_step": int(B),
@@ -417,35 +456,30 @@ def run_reference(args):
     if True:
         Bg, Oc = W.c2(args.scale)
         nvars = args.nvars or NVARS_C2
-        # (1) setInterpData on a bounded sample of C2a: donor = background coarsened to 128^3 (the ADT build
-        # is serial on the CPU: the full 256^3 tree alone takes minutes), receptors = every 8th O-grid node.
-        s = 2 if args.scale == 1.0 else 1
-        nb = (Bg.ni + s - 1) // s
-        sub = lambda a: np.ascontiguousarray(a.reshape((Bg.ni, Bg.nj, Bg.nk), order='F')[::s, ::s, ::s].reshape(-1, order='F'))
-        x, y, z = sub(Bg.x), sub(Bg.y), sub(Bg.z)
-        stride = 8 if args.scale == 1.0 else 1
-        xr, yr, zr = Oc.x[::stride].copy(), Oc.y[::stride].copy(), Oc.z[::stride].copy()
+        # (1) setInterpData of the FULL workload with the reference's own code: serial ADT build of the whole background
+        # (InterpAdt.cpp:284-433; a few seconds for 16.6 M cells), then the search of every O-grid receptor on all host
+        # threads.  Its lists ARE the interpData the transfer loop below runs on: same config as the GPU arm.
         t0 = time.perf_counter()
-        zone = O.RefZone(nb, nb, nb, x, y, z)
+        zone = O.RefZone(Bg.ni, Bg.nj, Bg.nk, Bg.x, Bg.y, Bg.z)
         t_adt = time.perf_counter() - t0
         t0 = time.perf_counter()
-        out = O.set_interp_data(xr, yr, zr, [zone], 2, 1, 1, 1)
+        out = O.set_interp_data(Oc.x, Oc.y, Oc.z, [zone], 2, 1, 1, 1)
         t_search = time.perf_counter() - t0
-        sid = {"value": xr.size / (t_adt + t_search), "unit": "receptor pts/s", "receptors": int(xr.size),
-               "adt_build_s": t_adt, "search_s": t_search, "cores": nthreads,
-               "sample": "background coarsened to %d^3, every %dth O-grid receptor" % (nb, stride),
+        rcv, dnr, typ, coefs = out[0][0], out[1][0], out[2][0], out[3][0]
+        sid = {"value": Oc.npts / (t_adt + t_search), "unit": "receptor pts/s", "receptors": int(Oc.npts),
+               "adt_build_s": t_adt, "search_s": t_search, "cores": nthreads, "sample": "full C2a workload",
                "note": "hook=None semantics: serial ADT build inside (InterpAdt.cpp:284-433)"}
         other = {}
         try:
-            for order, st_ in ((3, 8), (5, 64)):
+            for order, st_ in ((3, 64), (5, 512)):
+                m = Oc.npts // st_
                 t0 = time.perf_counter()
-                O.set_interp_data(xr[::st_].copy(), yr[::st_].copy(), zr[::st_].copy(), [zone], order, 1, 1, 1)
+                O.set_interp_data(Oc.x[:m].copy(), Oc.y[:m].copy(), Oc.z[:m].copy(), [zone], order, 1, 1, 1)
                 dtl = time.perf_counter() - t0
-                nl = xr[::st_].size
-                other["lagrange_order%d" % order] = {"value": nl / dtl, "unit": "receptor pts/s", "receptors": int(nl),
+                other["lagrange_order%d" % order] = {"value": m / dtl, "unit": "receptor pts/s", "receptors": int(m),
                                                      "s": dtl, "cores": nthreads,
-                                                     "sample": "every %dth O-grid node, background coarsened to %d^3, "
-                                                               "ADT build not included" % (stride * st_, nb)}
+                                                     "sample": "the first 1/%d of the O-grid nodes, full background ADT, "
+                                                               "ADT build not included" % st_}
             t0 = time.perf_counter()
             zc = O.RefZone(Bg.ni, Bg.nj, Bg.nk, Bg.x, Bg.y, Bg.z, interpDataType=0)
             O.set_interp_data(Oc.x, Oc.y, Oc.z, [zc], 2, 1, 1, 1)
@@ -456,49 +490,31 @@ def run_reference(args):
         except Exception as e:
             other["unavailable"] = str(e)
         del zone, out
-        # (2) the transfer loop on the FULL workload.  Its interpData is laid out like the real one (one type-2
-        # entry per O-grid node, ascending receptor order, 8 coefficients) but the donor cell is located
-        # analytically on the Cartesian background (floor((x-x0)/h)) with trilinear weights, so that the CPU arm
-        # does not need the minutes-long full-size ADT build just to time the transfer loop.
-        n = Oc.npts
-        hx = (Bg.x[1] - Bg.x[0]); hy = (Bg.y[Bg.ni] - Bg.y[0]); hz = (Bg.z[Bg.ni * Bg.nj] - Bg.z[0])
-        fi = (Oc.x - Bg.x[0]) / hx; fj = (Oc.y - Bg.y[0]) / hy; fk = (Oc.z - Bg.z[0]) / hz
-        ii = np.clip(np.floor(fi).astype(np.int64), 0, Bg.ni - 2); jj = np.clip(np.floor(fj).astype(np.int64), 0, Bg.nj - 2)
-        kk = np.clip(np.floor(fk).astype(np.int64), 0, Bg.nk - 2)
-        a = fi - ii; b = fj - jj; c = fk - kk
-        dnr = (ii + Bg.ni * jj + Bg.ni * Bg.nj * kk).astype(np.int32)
-        rcv = np.arange(n, dtype=np.int32); typ = np.full(n, 2, np.int32)
-        coefs = np.empty((n, 8))
-        for q, (wa, wb, wc) in enumerate([(1 - a, 1 - b, 1 - c), (a, 1 - b, 1 - c), (1 - a, b, 1 - c), (a, b, 1 - c),
-                                          (1 - a, 1 - b, c), (a, 1 - b, c), (1 - a, b, c), (a, b, c)]):
-            coefs[:, q] = wa * wb * wc
-        coefs = coefs.reshape(-1)
-        del fi, fj, fk, a, b, c
-        mark = np.zeros(Bg.npts, bool)
-        d64 = dnr.astype(np.int64)
-        for off in (0, 1, Bg.ni, Bg.ni + 1, Bg.ni * Bg.nj, Bg.ni * Bg.nj + 1, Bg.ni * Bg.nj + Bg.ni, Bg.ni * Bg.nj + Bg.ni + 1):
-            mark[d64 + off] = True
-        uniq = int(mark.sum())
-        del mark, d64, ii, jj, kk
+        # (2) the reference's transfer loop on that interpData, full size, the steps and warm-ups asked for
+        n = rcv.size
+        uniq = distinct_nodes(dnr, typ, Bg.ni, Bg.nj, Bg.npts)
         fD = W.conservative_fields(Bg.x, Bg.y, Bg.z, nvars)
-        fR = [np.zeros(n) for _ in range(nvars)]
         B = alg_bytes(n, coefs.size, nvars, uniq)
-        for _ in range(max(1, min(args.warmup, 2))):
+        fR = [np.zeros(Oc.npts) for _ in range(nvars)]
+        warm = max(3, args.warmup)
+        for _ in range(warm):
             O.transfer(fD, fR, Bg.ni, Bg.nj, rcv, dnr, typ, coefs)
-        steps = max(1, min(args.steps, 10))
+        steps = max(1, args.steps)
         t0 = time.perf_counter()
         for _ in range(steps):
             O.transfer(fD, fR, Bg.ni, Bg.nj, rcv, dnr, typ, coefs)
         dt = (time.perf_counter() - t0) / steps
         value = B / dt / 1e9
-        cfg = {"workload": "C2a transfers at full size (%d receptors <- %d^3 background, order 2, %d vars; donor cells "
-                           "located analytically, see bench.py) ; setInterpData on a bounded sample (see set_interp_data)" %
-                           (n, Bg.ni, nvars), "receptors": int(n), "nvars": nvars, "alg_bytes_per_step": int(B),
-               "distinct_donor_nodes": uniq}
+        cfg = config_c2(nvars, args.scale, args.gpus)
+        sample = ("full C2a workload: interpData computed by the reference's own setInterpData (ADT %.1f s + search %.1f s), "
+                  "%d timed passes of its transfer loop after %d warm-ups" % (t_adt, t_search, steps, warm))
+        stats = {"receptors": int(n), "donor_nodes": int(Bg.npts), "alg_bytes_per_step": int(B),
+                 "distinct_donor_nodes": int(uniq)}
         if args.gpus > 1:
             # the N-GPU workload is N such bodies; the host's rate does not depend on how many it is given,
             # so the bounded sample is one body (the fringe exchange has no CPU counterpart in one process)
-            cfg["workload"] = ("bounded sample = 1 of the %d bodies of the N-GPU workload: " % args.gpus) + cfg["workload"]
+            sample = ("bounded sample = 1 of the %d bodies of the N-GPU workload (the host's rate does not depend on how "
+                      "many bodies it is given): " % args.gpus) + sample
             del fD, fR, coefs, dnr, rcv, typ
             try:
                 cv, dt4, st4, cfg4, sid4, nv4 = reference_c4(args, O, W, nthreads)
@@ -507,11 +523,11 @@ def run_reference(args):
             except Exception as e:
                 c4 = {"unavailable": str(e)}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "stats": stats,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(min(nvars, nthreads)), "kind": "reference",
                              "host_cores": os.cpu_count(),
-                             "sample": cfg["workload"] + "; transfer threads = min(nvars, host threads)"},
+                             "sample": sample + "; transfer threads = min(nvars, host threads)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "set_interp_data": sid, "gpu_launches": 0}
     if c4 is not None:
@@ -520,10 +536,22 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def distinct_nodes(dnr, typ, imd, jmd):
-    """U of SURVEY.md 8(d) on the host (numpy.unique of the expanded stencils)."""
-    sel = []
+def distinct_nodes(dnr, typ, imd, jmd, npts=None):
+    """U of SURVEY.md 8(d) on the host: distinct donor nodes of the expanded stencils (a mark array over the donor
+    zone when its size is given, else numpy.unique)."""
     ij = imd * jmd
+    if npts is not None:
+        mark = np.zeros(int(npts), bool)
+        for t, o in ((1, 1), (2, 2), (3, 3), (5, 5)):
+            m = dnr[typ == t].astype(np.int64)
+            if m.size == 0:
+                continue
+            for kk in range(o):
+                for jj in range(o):
+                    for ii in range(o):
+                        mark[m + ii + jj * imd + kk * ij] = True
+        return int(mark.sum())
+    sel = []
     for t, o in ((1, 1), (2, 2), (3, 3), (5, 5)):
         m = dnr[typ == t].astype(np.int64)
         if m.size == 0:

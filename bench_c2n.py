@@ -38,8 +38,8 @@ def build_local(bodies, rank, nvars):
 
 
 def run_c2n(args):
-    from bench import METRIC, UNIT, ClockSampler, measured_peaks, NVARS_C2
-    from bench_c4 import _warm, measure_c4, strip_interp_data
+    from bench import METRIC, UNIT, ClockSampler, measured_peaks, NVARS_C2, config_c2
+    from bench_c4 import _warm, measure_c4, strip_interp_data, linear_field_check
     from cassiopee_b200 import _lib, Mpi as Cmpi, Distributor2 as D2, workloads as W
     import cassiopee_b200.Internal as Internal
     import cassiopee_b200.Converter as C
@@ -129,6 +129,7 @@ def run_c2n(args):
     e2e_phases = [1e3 * (tp[i + 1] - tp[i]) for i in range(3)]
     sess.unpin_host_fields()
 
+    check = linear_field_check(sess, t, t, names[0], 'nodes', ctx, comm)
     B = sum(gather(sess.alg_bytes()))
     ms_max = max(gather(ms))
     e2e_max = max(gather(e2e_s))
@@ -158,19 +159,14 @@ def run_c2n(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ngpus, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2a per GPU (cart %d^3 background -> cylinder O-grid %s receptors, order 2, nature=1 "
-                               "penalty=1 extrap=1, %d vars), %d bodies in a row, neighbouring backgrounds overlap by 8 "
-                               "cells and exchange 2-layer fringes over NCCL; C4/C5 cluster under c4_c5" %
-                               (b0['nb'], str(tuple(b0['nc'])), nvars, len(bodies)),
-                   "zones": 2 * len(bodies), "receptors": int(nrcv), "plans": int(nplans), "nvars": nvars,
-                   "alg_bytes_per_step": int(B), "nccl_bytes_per_step": int(nccl_b), "exchange_bytes_per_step": int(nccl_b),
-                   "transport": {"p2p": "peer memory: remote plans store into the receptor rank's IPC-mapped buffers over "
-                                        "NVLink, flag per rank pair (no NCCL call in the step)",
-                                 "nccl": "grouped ncclSend/ncclRecv of one packed buffer per rank pair",
-                                 "none": "single rank"}[transport], "orphans": int(norphan),
-                   "l2": "inputs larger than L2 (%.2f GB of plan+field traffic per GPU and step, L2 126 MB); no flush" %
-                         (B / max(1, ngpus) / 1e9),
-                   "parallelism": "one body (2 zones) per GPU by .Solver#Param/proc"},
+        "config": config_c2(nvars, args.scale, ngpus),
+        "stats": {"zones": 2 * len(bodies), "receptors": int(nrcv), "plans": int(nplans), "alg_bytes_per_step": int(B),
+                  "exchange_bytes_per_step": int(nccl_b), "orphans": int(norphan),
+                  "transport": {"p2p": "peer memory: remote plans store into the receptor rank's IPC-mapped buffers over "
+                                       "NVLink, flag per rank pair (no NCCL call in the step)",
+                                "nccl": "grouped ncclSend/ncclRecv of one packed buffer per rank pair",
+                                "none": "single rank"}[transport]},
+        "check": check,
         "clocks": clocks,
         "e2e": {"value": B / e2e_max / 1e9, "unit": UNIT, "ms_per_step": e2e_max * 1e3,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -46,6 +46,83 @@ def build_local(blocks, owners, rank, nvars):
     return C.newPyTree(['Base'] + zones)
 
 
+def config_c4(ngpus, nb, nblk, nvars):
+    """Static description of the C4/C5 line (both arms emit the same dict; measured counts go under "stats")."""
+    return {"workload": "C4/C5: %dx%dx%d blocks of %d^3 pts (8-cell overlap, sub-cell shifts), receptors = outer 2 cell "
+                        "layers inside another block, order 2, %d vars, interpData reused" % (nb[0], nb[1], nb[2], nblk, nvars),
+            "zones": nb[0] * nb[1] * nb[2], "zones_per_gpu": nb[0] * nb[1] * nb[2] // max(1, ngpus), "nvars": nvars,
+            "n_gpus": ngpus,
+            "l2": "per-GPU working set about 110 MB of algorithmic traffic; L2 not flushed (steady-state loop of a solver)",
+            "parallelism": "zones over %d GPU(s) by .Solver#Param/proc (rcb)" % ngpus}
+
+
+def linear_field_check(sess, tR, tD, var, loc, ctx, comm):
+    """Correctness of the distributed step at full size, through a size-independent property: with the first variable
+    set to F = 1 + x + 2y + 3z on every zone of every rank (donor side and receptor side), one step must leave F at
+    every INTERPOLATED receptor point (order-2 weights reproduce linear fields exactly).  Extrapolated points (the
+    ExtrapPointList of the ID_* subregions, gathered from the donor owners) are reported apart: their weights, moved
+    onto the valid vertices of the donor cell, are not linear-exact by construction (InterpData.cpp:699-947).  Orphans
+    are never written.  A wrong index list, exchange buffer or scatter shows up as an error of the order of the cell
+    size.  The fields are restored afterwards.  Returns max |error| over all ranks and the number of values compared."""
+    import cassiopee_b200.Internal as Internal
+    import cassiopee_b200.Converter as C
+    F = lambda x, y, z: 1. + x + 2. * y + 3. * z
+    rname = ('centers:' + var) if loc == 'centers' else var
+    g = (lambda v: comm.allgather_obj(v)) if comm is not None else (lambda v: [v])
+    ext = {}
+    for zd in Internal.getZones(tD):
+        for sr in Internal.getNodesFromType1(zd, 'ZoneSubRegion_t'):
+            e = Internal.getNodeFromName1(sr, 'ExtrapPointList')
+            if sr[0].startswith('ID_') and e is not None and e[1].size:
+                ext.setdefault(Internal.getValue(sr), []).append(np.asarray(e[1]))
+    extAll = {}
+    for d in g({k: np.concatenate(v) for k, v in ext.items()}):
+        for k, v in d.items(): extAll.setdefault(k, []).append(v)
+    saved = []
+    for z in Internal.getZones(tD):
+        a = C.getFieldArray(z, var); saved.append((a, a.copy(order='K')))
+        x, y, zz = C.getCoords(z)
+        a[...] = F(x, y, zz)
+    exact = []
+    for z in Internal.getZones(tR):
+        a = C.getFieldArray(z, rname)
+        if not any(a is s[0] for s in saved): saved.append((a, a.copy(order='K')))
+        x, y, zz = C.getCoords(z)
+        if loc == 'centers': x, y, zz = [C.node2CenterArray(v) for v in (x, y, zz)]
+        e = F(x, y, zz)
+        a[...] = e
+        isx = np.zeros(a.size, bool)
+        if z[0] in extAll: isx[np.concatenate(extAll[z[0]])] = True
+        exact.append((a, e, C.getFieldArray(z, ('centers:cellN') if loc == 'centers' else 'cellN') == 2.,
+                      isx.reshape(a.shape, order='F')))
+    sess.upload_donor_fields(); ctx.sync()               # donors hold F everywhere
+    for a, e, m, isx in exact:
+        a[m] = -777.                                     # receptor points start from a wrong value
+    sess.upload_receptor_fields()
+    sess.step(); sess.download()
+    err = 0.; n = 0; nbad = 0; errx = 0.; nx = 0; north = 0
+    for a, e, m, isx in exact:
+        written = m & ~(np.abs(a + 777.) < 1e-9)         # orphans are never written
+        north += int((m & ~written).sum())
+        d = np.abs(a - e)
+        di = d[written & ~isx]; dx = d[written & isx]
+        if di.size:
+            err = max(err, float(di.max())); n += int(di.size); nbad += int((di > 1e-9).sum())
+        if dx.size:
+            errx = max(errx, float(dx.max())); nx += int(dx.size)
+    for a, v in saved:
+        a[...] = v
+    sess.upload_receptor_fields(); sess.upload_donor_fields()
+    ctx.sync()
+    errs = g(err); ns = g(n); bad = g(nbad); errxs = g(errx); nxs = g(nx); norths = g(north)
+    return {"kind": "F = 1+x+2y+3z on all zones of all ranks, one distributed step, |F_interpolated - F| at the "
+                    "interpolated receptor points", "max_abs_err": max(errs), "receptor_values_checked": int(sum(ns)),
+            "values_off_by_more_than_1e-9": int(sum(bad)), "ok": bool(max(errs) < 1e-9),
+            "extrapolated_points": {"n": int(sum(nxs)), "max_abs_err": max(errxs),
+                                    "note": "not linear-exact by construction; reported, not judged"},
+            "orphans_never_written": int(sum(norths))}
+
+
 def measure_c4(args, ctx, comm, ngpus, rank, world):
     """C4/C5 on the ranks of this job; returns the result dict on rank 0 (None elsewhere)."""
     from bench import ClockSampler, measured_peaks
@@ -141,6 +218,7 @@ def measure_c4(args, ctx, comm, ngpus, rank, world):
     def gather(v):
         return comm.allgather_obj(v) if comm is not None else [v]
 
+    check = linear_field_check(sess, tl, tcl, names[0], 'centers', ctx, comm)
     B = sum(gather(sess.alg_bytes()))
     ms_max = max(gather(ms))
     ms100_max = max(gather(ms100))
@@ -162,19 +240,14 @@ def measure_c4(args, ctx, comm, ngpus, rank, world):
     peak, how = measured_peaks()
     return {
         "value": value, "unit": "GB/s", "n_gpus": ngpus, "steps": args.steps, "ms_per_step": ms_step,
-        "config": {"workload": "C4/C5: %dx%dx%d blocks of %d^3 pts (8-cell overlap, sub-cell shifts), receptors = outer "
-                               "2 cell layers inside another block, order 2, %d vars, interpData reused" %
-                               (nb[0], nb[1], nb[2], nblk, nvars),
-                   "zones": len(blocks), "zones_per_gpu": len(blocks) // max(1, ngpus), "receptors": int(nrcv),
-                   "plans": int(nplans), "nvars": nvars, "alg_bytes_per_step": int(B),
-                   "nccl_bytes_per_step": int(nccl_b), "exchange_bytes_per_step": int(nccl_b),
-                   "transport": {"p2p": "peer memory: remote plans store into the receptor rank's IPC-mapped buffers over "
-                                        "NVLink, flag per rank pair (no NCCL call in the step)",
-                                 "nccl": "grouped ncclSend/ncclRecv of one packed buffer per rank pair",
-                                 "none": "single rank"}[transport],
-                   "l2": "per-GPU working set %.0f MB; L2 not flushed (steady-state loop of a solver)" %
-                         ((B / max(1, ngpus)) / 1e6),
-                   "parallelism": "zones over %d GPU(s) by .Solver#Param/proc (rcb)" % ngpus},
+        "config": config_c4(ngpus, nb, nblk, nvars),
+        "stats": {"zones": len(blocks), "receptors": int(nrcv), "plans": int(nplans), "alg_bytes_per_step": int(B),
+                  "exchange_bytes_per_step": int(nccl_b),
+                  "transport": {"p2p": "peer memory: remote plans store into the receptor rank's IPC-mapped buffers over "
+                                       "NVLink, flag per rank pair (no NCCL call in the step)",
+                                "nccl": "grouped ncclSend/ncclRecv of one packed buffer per rank pair",
+                                "none": "single rank"}[transport]},
+        "check": check,
         "c5_100_iterations": {"ms_total": ms100_max, "ms_per_step": ms100_max / 100.,
                               "GBps": B / (ms100_max / 100. * 1e-3) / 1e9},
         "clocks": clocks,
@@ -210,7 +283,7 @@ def run_c4(args):
     line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": ngpus, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
-    for k in ("config", "clocks", "e2e", "gpu_launches", "comm_overlap", "roofline", "set_interp_data",
+    for k in ("config", "stats", "check", "clocks", "e2e", "gpu_launches", "comm_overlap", "roofline", "set_interp_data",
               "c5_100_iterations"):
         line[k] = r[k]
     line["cpu_baseline"] = cpu_baseline_c4(args, layout_for(ngpus, int(os.environ.get("CX_C4_N", "100")))[0],

@@ -427,6 +427,7 @@ class TransferSession:
             owners = {n: 0 for n in self.zr}
         # resident fields
         self.dD, self.dR, self.hR = {}, {}, {}
+        self._rcvIdx = {}      # receptor zone -> index lists written by the plans (local and remote) that feed it
         self.h2d_bytes = 0
         for zd in Internal.getZones(aD):
             arrs = [C.getFieldArray(zd, v) for v in self.variables]
@@ -457,6 +458,7 @@ class TransferSession:
                     zr = self.zr[rname]
                     nptsR = int(numpy.prod(C.fieldShape(zr, loc)))
                     self._residentR(zr, loc)
+                    self._rcvIdx.setdefault(rname, []).append(numpy.asarray(ListRcv))
                     plan = _lib.Plan(ctx, imd, jmd, kmd, nptsR, ListDonor, ListRcv, typ, cf)
                     items.append((plan, 0, [d.ptr for d in self.dD[zd[0]]], [d.ptr for d in self.dR[rname]], None, 0))
                 elif rname in owners:
@@ -502,6 +504,7 @@ class TransferSession:
                     n = r['n']
                     lst = got[q][ob:ob + 4 * n].view(numpy.int32).copy(); ob += 4 * n
                     self._residentR(self.zr[r['rcv']], r['loc'])
+                    self._rcvIdx.setdefault(r['rcv'], []).append(lst)
                     dl = _lib.DeviceArray.from_host(ctx, lst)
                     self._keep.append(dl)
                     rlists.setdefault(q, []).append((n, dl, o, r['rcv']))
@@ -521,7 +524,27 @@ class TransferSession:
             self.planset_remote = None
             self.scatterset = _lib.ScatterSet(ctx, nv, [])
             self._step = _lib.Step(ctx, None, self.planset, self.scatterset, [], [], [], [], [])
+        self._setup_sparse_download(nv)
         ctx.sync()
+
+    def _setup_sparse_download(self, nv):
+        """Receptor zones of which a step writes less than half the points are downloaded sparsely: the written values
+        are packed on the device (cx_gather_dev), copied into a page-locked block and stored into the host arrays by
+        index (cx_host_scatter) -- what Connector/Mpi.py:396-440 does with C._setPartialFields.  CX_SPARSE_D2H=0: always
+        whole fields."""
+        self._sparse = {}
+        if os.environ.get("CX_SPARSE_D2H", "1") == "0":
+            return
+        for name, lists in self._rcvIdx.items():
+            arrs = self.hR.get(name)
+            if not arrs or not all(_rawF(a) for a in arrs):
+                continue
+            idx = numpy.unique(numpy.concatenate(lists)).astype(numpy.int32)
+            if idx.size == 0 or 2 * idx.size >= arrs[0].size:
+                continue
+            self._sparse[name] = dict(idx=idx, didx=_lib.DeviceArray.from_host(self.ctx, idx),
+                                      dbuf=_lib.DeviceArray(self.ctx, nv * idx.size),
+                                      hbuf=_lib.pinned_empty(nv * idx.size))
 
     def _setup_nccl(self, rlayout, rlists, nv):
         """Remote plans -> per-peer send buffers -> grouped ncclSend/ncclRecv -> scatter."""
@@ -651,6 +674,12 @@ class TransferSession:
                     else:
                         d.upload(numpy.ascontiguousarray(a.reshape(-1, order='F')))
 
+    def upload_receptor_fields(self):
+        """Host tree -> device for the receptor fields (the device copies are otherwise only written by step())."""
+        for name, arrs in self.hR.items():
+            for d, a in zip(self.dR[name], arrs):
+                d.upload(numpy.ascontiguousarray(a.reshape(-1, order='F')))
+
     def step(self, niter=1, overlap=True):
         """niter iterations (asynchronous): remote plans -> NCCL exchange + scatter on the
         communication stream, overlapped with the local in-place plans."""
@@ -661,6 +690,13 @@ class TransferSession:
         nb = 0
         slow = []
         for name, arrs in self.hR.items():
+            sp = self._sparse.get(name)
+            if sp is not None:
+                n = sp['idx'].size
+                _lib.gather_dev(self.ctx, sp['dbuf'].ptr, n, n, sp['didx'].ptr, [d.ptr for d in self.dR[name]])
+                self.ctx.download_async(sp['hbuf'], sp['dbuf'].ptr)
+                nb += sp['hbuf'].nbytes
+                continue
             for d, a in zip(self.dR[name], arrs):
                 if _rawF(a):
                     self.ctx.download_async(a, d.ptr)
@@ -668,6 +704,10 @@ class TransferSession:
                     slow.append((d, a))
                 nb += a.nbytes
         self.ctx.sync()
+        for name, sp in self._sparse.items():
+            n = sp['idx'].size
+            for v, a in enumerate(self.hR[name]):
+                _lib.host_scatter(a, sp['idx'], sp['hbuf'][v * n:(v + 1) * n])
         for d, a in slow:
             a[...] = d.download().reshape(a.shape, order='F')
         return nb

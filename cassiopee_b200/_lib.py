@@ -75,6 +75,8 @@ _SIGS = {
     "cx_transferD_dev": (_i, [_vp, _i, _vp, _vp, _ll]),
     "cx_transfer_celln_dev": (_i, [_vp, _vp, _vp]),
     "cx_scatter_dev": (_i, [_vp, _i, _vp, _ll, _i, _vp, _vp]),
+    "cx_gather_dev": (_i, [_vp, _i, _vp, _ll, _i, _vp, _vp]),
+    "cx_host_scatter": (_i, [_vp, _vp, _vp, _ll]),
     "cx_plan_info": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "cx_plan_sorted_rcv": (_i, [_vp, _vp]),
     "cx_ipc_export": (_i, [_vp, _vp]),
@@ -552,6 +554,20 @@ class Plan:
         """B_alg of SURVEY.md 8(d) for one call with nvars variables."""
         i = self.info()
         return i["alg_fixed"] + 8 * nvars * (i["n"] + i["distinct"])
+
+
+def gather_dev(ctx, d_out, ld, n, d_idx, field_ptrs):
+    """out[v*ld + e] = field[v][idx[e]] on the device (asynchronous on the context's stream)."""
+    nv = len(field_ptrs)
+    tab = (ctypes.c_void_p * nv)(*[int(p) for p in field_ptrs])
+    check(lib().cx_gather_dev(ctx.h, nv, _vp(d_out), int(ld), int(n), _vp(d_idx), tab))
+
+
+def host_scatter(dst, idx, src):
+    """dst.flat[idx[e]] = src[e] for an array whose memory is its Fortran-order flattening (threaded on the host)."""
+    assert dst.dtype == np.float64 and src.dtype == np.float64 and idx.dtype == np.int32
+    assert dst.flags.f_contiguous or dst.ndim == 1
+    check(lib().cx_host_scatter(ptr(dst), ptr(idx), ptr(src), int(idx.size)))
 
 
 def host_register(a):

@@ -1659,11 +1659,22 @@ struct cx_scatterset {
   std::vector<void*> owned;
 };
 
-static int upload_ptr_table(const double* const* host, int nvars, double*** out)
+// Descriptor / pointer tables: host -> device ON the context's stream and complete on return.  (A plain cudaMemcpy from
+// pageable memory may return before its DMA has landed, and the non-blocking streams the kernels run on are not
+// ordered behind the legacy stream it uses.)
+static int upload_table(cx_ctx* ctx, void* dptr, const void* host, size_t bytes)
+{
+  if (bytes == 0) return 0;
+  CX_CUDA(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+static int upload_ptr_table(cx_ctx* ctx, const double* const* host, int nvars, double*** out)
 {
   double** d;
   CX_CUDA(cudaMalloc(&d, sizeof(double*) * (size_t)nvars));
-  CX_CUDA(cudaMemcpy(d, host, sizeof(double*) * (size_t)nvars, cudaMemcpyHostToDevice));
+  CX_CHECK(upload_table(ctx, d, host, sizeof(double*) * (size_t)nvars));
   *out = d;
   return 0;
 }
@@ -1733,8 +1744,8 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
     if (nb[t] == 0) continue;
     CX_CUDA(cudaMalloc(&S->d_descs[t], sizeof(SetDesc) * descs[t].size()));
     CX_CUDA(cudaMalloc(&S->d_blk2desc[t], sizeof(BlkRec) * b2d[t].size()));
-    CX_CUDA(cudaMemcpy(S->d_descs[t], descs[t].data(), sizeof(SetDesc) * descs[t].size(), cudaMemcpyHostToDevice));
-    CX_CUDA(cudaMemcpy(S->d_blk2desc[t], b2d[t].data(), sizeof(BlkRec) * b2d[t].size(), cudaMemcpyHostToDevice));
+    CX_CHECK(upload_table(ctx, S->d_descs[t], descs[t].data(), sizeof(SetDesc) * descs[t].size()));
+    CX_CHECK(upload_table(ctx, S->d_blk2desc[t], b2d[t].data(), sizeof(BlkRec) * b2d[t].size()));
     if (t == 1)
     {
       k_block_ranges<<<cx_grid(nb[t], 256), 256, 0, ctx->stream>>>(nb[t], S->d_descs[t], S->d_blk2desc[t], TB);
@@ -1795,7 +1806,7 @@ int cx_scatterset_create(cx_ctx* ctx, int nsets, int nvars, const int* n, const 
   {
     if (n[i] == 0) continue;
     double** tr = nullptr;
-    CX_CHECK(upload_ptr_table((const double* const*)d_fieldR[i], nvars, &tr));
+    CX_CHECK(upload_ptr_table(ctx, (const double* const*)d_fieldR[i], nvars, &tr));
     S->owned.push_back(tr);
     ScatDesc D; D.n = n[i]; D.first_block = nb; D.rcv = d_rcv[i]; D.in = d_in[i]; D.ld = ld[i]; D.rptr = tr;
     int blocks = cx_grid(n[i], 256);
@@ -1808,8 +1819,8 @@ int cx_scatterset_create(cx_ctx* ctx, int nsets, int nvars, const int* n, const 
   {
     CX_CUDA(cudaMalloc(&S->d_descs, sizeof(ScatDesc) * descs.size()));
     CX_CUDA(cudaMalloc(&S->d_blk2desc, sizeof(int) * b2d.size()));
-    CX_CUDA(cudaMemcpy(S->d_descs, descs.data(), sizeof(ScatDesc) * descs.size(), cudaMemcpyHostToDevice));
-    CX_CUDA(cudaMemcpy(S->d_blk2desc, b2d.data(), sizeof(int) * b2d.size(), cudaMemcpyHostToDevice));
+    CX_CHECK(upload_table(ctx, S->d_descs, descs.data(), sizeof(ScatDesc) * descs.size()));
+    CX_CHECK(upload_table(ctx, S->d_blk2desc, b2d.data(), sizeof(int) * b2d.size()));
   }
   *out = S;
   return 0;
@@ -1877,7 +1888,7 @@ int cx_step_create_p2p(cx_ctx* ctx, cx_planset* ps_remote0, cx_planset* ps_remot
   if (npeers > 0)
   {
     CX_CUDA(cudaMalloc(&S->d_peer_flags, sizeof(int*) * (size_t)npeers));
-    CX_CUDA(cudaMemcpy(S->d_peer_flags, peer_flags, sizeof(int*) * (size_t)npeers, cudaMemcpyHostToDevice));
+    CX_CHECK(upload_table(ctx, S->d_peer_flags, peer_flags, sizeof(int*) * (size_t)npeers));
   }
   *out = S;
   return 0;

@@ -164,6 +164,12 @@ int cx_transfer_celln_dev(cx_plan* plan, const double* d_cellND, double* d_cellN
  * (what Connector/Mpi.py:396-440 does with C._setPartialFields on arrival) */
 int cx_scatter_dev(cx_ctx* ctx, int nvars, const double* d_in, long long ld, int n, const int* d_rcv,
                    double* const* d_fieldR);
+/* Sparse download of a receptor zone (the host tree only needs the values a transfer wrote, what
+ * C._setPartialFields(zone, [array], [indices]) stores in Connector/Mpi.py:396-440): device side
+ * out[v*ld+e] = field[v][idx[e]], host side dst[idx[e]] = src[e] (distinct indices). */
+int cx_gather_dev(cx_ctx* ctx, int nvars, double* d_out, long long ld, int n, const int* d_idx,
+                  double* const* d_field);
+int cx_host_scatter(double* dst, const int* idx, const double* src, long long n);
 /* alg_fixed: sum over entries of 8*ncf+12 bytes; distinct: number of distinct
  * donor nodes referenced (U of SURVEY.md 8(d)); B_alg = alg_fixed + 8*N*(n + U) */
 /* receptor indices in the plan's own (regrouped, donor-sorted) entry order = the order of a dense block written

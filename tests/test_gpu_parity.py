@@ -919,3 +919,59 @@ def test_set_interp_transfers_batch_keeps_sequential_semantics(ctx):
             assert np.array_equal(got, cur[(z[0], v)]), (z[0], v)
             changed += int(not np.array_equal(got, before[(z[0], v)]))
     assert changed >= 6 and ctx.launches() > l0
+
+
+@pytest.mark.gpu
+def test_transfer_session_sparse_download_and_c_ordered_fields(ctx, monkeypatch):
+    """TransferSession.upload_donor_fields / step / download on host trees: receptor zones of which the step writes
+    only a fringe are downloaded sparsely (device gather + index store on the host), receptor or donor arrays that are
+    C-contiguous 3-D arrays go through the Fortran-order staging path (raw copies would permute them), and both give
+    what _setInterpTransfers gives on the same trees; the untouched receptor values keep their host content."""
+    import cassiopee_b200.Generator as G
+    import cassiopee_b200.Converter as C
+    import cassiopee_b200.Internal as Internal
+    import cassiopee_b200.Connector.PyTree as X
+    import cassiopee_b200.Connector.Mpi as Xmpi
+    h = 1. / 16
+    def build():
+        a = G.cart((0, 0, 0), (h, h, h), (17, 15, 13), name='A')
+        b = G.cart((0.31, 0.22, 0.18), (0.8 * h, 0.8 * h, 0.8 * h), (15, 13, 11), name='B')
+        t = C.newPyTree(['Base', a, b])
+        names = ['Density', 'MomentumX', 'EnergyStagnationDensity']
+        rng = np.random.default_rng(3)
+        for z in Internal.getZones(t):
+            shp = C.fieldShape(z, 'centers')
+            for v in names:
+                C._initVars(z, 'centers:' + v, np.asfortranarray(rng.standard_normal(shp)))
+        C._initVars(t, 'centers:cellN', 1.)
+        za, zb = Internal.getZones(t)
+        cb = np.ones(C.fieldShape(zb, 'centers'), order='F'); cb[:2] = 2.; cb[:, :, -2:] = 2.     # B: a fringe only
+        C._initVars(zb, 'centers:cellN', cb)
+        ca = np.ones(C.fieldShape(za, 'centers'), order='F'); ca[6:, 5:, 4:] = 2.                  # A: a big block
+        C._initVars(za, 'centers:cellN', ca)
+        tc = C.node2Center(t)
+        tc = X.setInterpData(t, tc, order=2, nature=0, penalty=1, extrap=1, loc='centers', storage='inverse',
+                             sameName=1, itype='chimera', verbose=0)
+        return t, tc, names
+    t, tc, names = build()
+    want = X.setInterpTransfers(t, tc, variables=names, storage=1)
+    for c_order in (False, True):
+        t, tc, names = build()
+        if c_order:
+            for tree, pre in ((t, 'centers:'), (tc, '')):
+                for z in Internal.getZones(tree):
+                    cont = Internal.getNodeFromName1(z, Internal.__FlowSolutionCenters__ if pre else Internal.__FlowSolutionNodes__)
+                    node = Internal.getNodeFromName1(cont, names[1])
+                    node[1] = np.ascontiguousarray(node[1])              # same values, C-ordered memory
+                    assert not node[1].flags.f_contiguous
+        sess = Xmpi.TransferSession(t, tc, names, comm=None, ctx=ctx)
+        assert ('B' in sess._sparse) and ('A' not in sess._sparse or c_order)
+        before = {z[0]: [C.getFieldArray(z, 'centers:' + v).copy() for v in names] for z in Internal.getZones(t)}
+        sess.upload_donor_fields(); sess.step(); nb = sess.download()
+        for z, zw in zip(Internal.getZones(t), Internal.getZones(want)):
+            for v in names:
+                assert np.array_equal(C.getFieldArray(z, 'centers:' + v), C.getFieldArray(zw, 'centers:' + v)), (z[0], v, c_order)
+        if not c_order:
+            full = sum(a.nbytes for z in Internal.getZones(t) for a in before[z[0]])
+            assert nb < full                                             # B's fields were not downloaded whole
+        sess.close()
