@@ -218,7 +218,10 @@ def node2Center(t):
             names = [f[0] for f in newfields]
             for n in fsc[2]:
                 if n[3] == 'DataArray_t' and n[0] not in names:
-                    newfields.append([n[0], n[1], [], 'DataArray_t'])
+                    # a copy, like the reference (getFields(..., api=1) + setFields build new arrays,
+                    # Converter/PyTree.py:6400-6414): tc's fields must not alias t's, or a transfer that writes a
+                    # receptor zone of t would change what the next subregion reads from the same zone of tc
+                    newfields.append([n[0], numpy.array(n[1], order='F', copy=True), [], 'DataArray_t'])
         z[2][:] = [c for c in z[2] if c[0] not in (Internal.__FlowSolutionNodes__, Internal.__FlowSolutionCenters__)]
         if newfields:
             c = Internal.createChild(z, Internal.__FlowSolutionNodes__, 'FlowSolution_t')

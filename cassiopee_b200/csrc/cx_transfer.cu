@@ -928,6 +928,13 @@ k_transfer_set(const SetDesc* __restrict__ descs, const BlkRec* __restrict__ blk
   else transfer_entry<TYPE, 1, PDk, PRk, CX_SET_VU>(e, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld, D.pat);
 }
 
+// Measured and rejected (round 2, C4 step, 8 zones of 100^3, 7 variables; gpurun_out/r2_lean.out): a lean variant of the
+// kernel above for the type-1 / type-2 table -- thread = entry, direct gathers only, no shared memory, the descriptor
+// read straight from global memory, 40 registers = 6 resident CTAs per SM instead of 4 -- ran 56.7 us against 56.0 us
+// (8 CTAs per SM, with spills: 62.6 us).  Half again as many resident warps change nothing: the step is not bound by
+// latency x occupancy but by the sector-granular traffic of the fringe slabs (188 MB of DRAM traffic for 108 MB of
+// algorithmic bytes, 1.45 M partial-sector receptor stores that each cost a fetch-on-write; profiles/r02_*).
+
 // donor index range of every block's tile (donor-sorted type-2 groups of a plan set), once at creation
 __global__ void k_block_ranges(int nblocks, const SetDesc* __restrict__ descs, BlkRec* __restrict__ blk, int tb)
 {
@@ -1642,7 +1649,7 @@ int cx_plan_rotate_on(cx_plan* P, int dirR, double ct, double st, double* fx, do
 // ---------------------------------------------------------------------------
 struct cx_planset {
   cx_ctx* ctx;
-  int nvars, ndesc, staged, tiled;
+  int nvars, ndesc, staged, tiled, boxed;
   // plans too large to gain anything from fusion run as their own launches (leaner kernel, more CTAs per SM)
   struct Big { cx_plan* P; int mode; std::vector<const double*> dD; std::vector<double*> dR; double* dense; long long ld; };
   std::vector<Big> big;
@@ -1689,7 +1696,7 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
   CX_CUDA(cudaSetDevice(ctx->device));
   cx_planset* S = new cx_planset;
   S->ctx = ctx; S->nvars = nvars; S->d_tables = nullptr; S->ntables = 0; S->ndesc = 0;
-  S->staged = cx_transfer_staging(); S->smem = 0; S->smem3 = 0; S->smem5 = 0; S->tiled = 0;
+  S->staged = cx_transfer_staging(); S->smem = 0; S->smem3 = 0; S->smem5 = 0; S->tiled = 0; S->boxed = 0;
   if (nvars > CX_MAXVARS) { cx_set_error("plan set: at most %d variables per set", CX_MAXVARS); delete S; return -1; }
   std::vector<SetDesc> descs[6]; std::vector<BlkRec> b2d[6]; std::vector<void*> tables;
   const int TB = 256;
@@ -1720,7 +1727,7 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
       D.tiles = (const TileRef*)G.d_tiles;
       if (G.type == 2 && G.layout == 2) { S->smem = std::max(S->smem, sizeof(double) * CX_BOXV * (size_t)nvars); S->tiled = 1; }
       if (G.type == 2 && G.layout == 1) S->smem = std::max(S->smem, sizeof(StageSmem));
-      if (G.type == 2 && G.layout == 3) S->smem = std::max(S->smem, sizeof(double) * (size_t)G.box_vs * (size_t)nvars);
+      if (G.type == 2 && G.layout == 3) { S->smem = std::max(S->smem, sizeof(double) * (size_t)G.box_vs * (size_t)nvars); S->boxed = 1; }
       if (G.type == 3 && G.layout == 1) S->smem3 = sizeof(StageSmemO<3>);
       for (int v = 0; v < nvars; v++) if (((uintptr_t)d_fieldD[p][v]) & 15) S->staged = 0;
       D.donor = P->d_donor + G.first;

@@ -1,3 +1,2 @@
-# the whole GPU suite, nothing else
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -6
+timeout 2400 python -m pytest tests -x -q -m gpu 2>&1 | tail -6
