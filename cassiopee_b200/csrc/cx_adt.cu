@@ -21,6 +21,7 @@
 // are evaluated exactly as the reference does, in fp64 without FMA, because
 // the query prunes with the very same numbers (InterpAdt.cpp:768-925).
 #include "cx_internal.h"
+#include <vector>
 
 using namespace cx;
 
@@ -74,22 +75,37 @@ __global__ void k_claim(int L, int nact_known, const int* __restrict__ cnt, cons
   }
 }
 
-__global__ void k_subtree(int ncells, int L, const int* __restrict__ depth, AdtNode* nodes)
+// subtree boxes of the cells placed at one depth: `list` = the cells k_resolve placed at that depth (any order)
+__global__ void k_subtree(int count, const int* __restrict__ list, AdtNode* nodes)
 {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncells || depth[c] != L) return;
-  adt_subtree_box(nodes, c);
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= count) return;
+  adt_subtree_box(nodes, list ? list[a] : 0);
 }
 
+// placed / pcnt: the cells placed at this level are appended to `placed` at n0 - nact + (running count of the level),
+// so that the list ends up grouped by depth (the subtree pass then touches each cell once instead of scanning all
+// cells once per level)
 __global__ void k_resolve(int L, int nact_known, int* __restrict__ cnt, const int* __restrict__ act, BuildView B,
-                          int* __restrict__ next)
+                          int* __restrict__ next, int n0, int* __restrict__ placed, int* __restrict__ pcnt)
 {
   const int nact = nact_known >= 0 ? nact_known : cnt[L];
   int* counter = cnt + L + 1;
   int a = blockIdx.x * blockDim.x + threadIdx.x;
   int c = 0;
-  bool keep = false;
-  if (a < nact) { c = act[a]; keep = !adt_resolve(B, L, c); }
+  bool keep = false, put = false;
+  if (a < nact) { c = act[a]; keep = !adt_resolve(B, L, c); put = !keep; }
+  {
+    const unsigned mp = __ballot_sync(0xffffffffu, put);
+    if (mp)
+    {
+      const int lane = threadIdx.x & 31;
+      int base = 0;
+      if (lane == __ffs(mp) - 1) base = atomicAdd(&pcnt[L], __popc(mp));
+      base = __shfl_sync(0xffffffffu, base, __ffs(mp) - 1);
+      if (put) placed[n0 - nact + base + __popc(mp & ((1u << lane) - 1u))] = c;
+    }
+  }
   // warp-aggregated compaction: one atomicAdd per warp and the lanes keep their relative order, so the active
   // list stays (piecewise) ascending and the next level's accesses to keys/lo/hi[c] stay coalesced
   const unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -154,6 +170,8 @@ int cx_build_adt(cx_zone* z)
   CX_CUDA(cudaMemsetAsync(B.depth, 0, sizeof(int) * n, s));
   CX_MALLOC(S.actA, sizeof(int) * n, s);
   CX_MALLOC(S.actB, sizeof(int) * n, s);
+  int *d_placed, *d_pcnt;
+  CX_MALLOC(d_placed, sizeof(int) * n, s);
   ZoneBox zb;
   for (int d = 0; d < 6; d++) { zb.lo[d] = z->bbox[d % 3]; zb.hi[d] = z->bbox[3 + d % 3]; }
   B.zb = zb;
@@ -176,6 +194,10 @@ int cx_build_adt(cx_zone* z)
   CX_MALLOC(d_cnt, sizeof(int) * (MAXL + BATCH + 2), s);
   CX_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (MAXL + BATCH + 2), s));
   CX_CUDA(cudaMemcpyAsync(d_cnt, &nact, sizeof(int), cudaMemcpyHostToDevice, s));
+  CX_MALLOC(d_pcnt, sizeof(int) * (MAXL + BATCH + 2), s);
+  CX_CUDA(cudaMemsetAsync(d_pcnt, 0, sizeof(int) * (MAXL + BATCH + 2), s));
+  const int n0 = nact;                        // cells to place below the root
+  std::vector<int> cntAll(1, nact);           // cntAll[L] = active cells at the start of level L
   int h_cnt[BATCH + 1];
   while (nact > 0)
   {
@@ -184,7 +206,7 @@ int cx_build_adt(cx_zone* z)
     for (int q = 0; q < nb; q++)
     {
       k_claim<<<grid, TB, 0, s>>>(L + q, q == 0 ? nact : -1, d_cnt, act, B);
-      k_resolve<<<grid, TB, 0, s>>>(L + q, q == 0 ? nact : -1, d_cnt, act, B, next);
+      k_resolve<<<grid, TB, 0, s>>>(L + q, q == 0 ? nact : -1, d_cnt, act, B, next, n0, d_placed, d_pcnt);
       ctx->launches += 2;
       int* t = act; act = next; next = t;
     }
@@ -196,17 +218,22 @@ int cx_build_adt(cx_zone* z)
       if (h_cnt[q + 1] < h_cnt[q]) depth = L + q + 1;   // somebody was placed at depth L+q+1
       if (h_cnt[q + 1] == 0) { used = q + 1; break; }
     }
+    for (int q = 1; q <= used; q++) cntAll.push_back(h_cnt[q]);
     nact = h_cnt[used];
     L += used;
     if (L > MAXL) { cx_set_error("ADT deeper than 4096 levels (degenerate/duplicate cells)"); cudaFreeAsync(d_cnt, s); return -3; }
   }
-  cudaFreeAsync(d_cnt, s);
-  // subtree bounding boxes, deepest level first
-  for (int lv = depth - 1; lv >= 0; lv--)
+  cudaFreeAsync(d_cnt, s); cudaFreeAsync(d_pcnt, s);
+  // subtree bounding boxes, deepest level first: the cells of depth d were placed during level d - 1 and sit at
+  // placed[n0 - cntAll[d-1] .. n0 - cntAll[d]); depth 0 is the root
+  for (int lv = depth - 1; lv >= 1; lv--)
   {
-    k_subtree<<<cx_grid(n, TB), TB, 0, s>>>(ncells, lv, B.depth, z->d_nodes);
+    const int first = n0 - cntAll[lv - 1], count = cntAll[lv - 1] - cntAll[lv];
+    if (count <= 0) continue;
+    k_subtree<<<cx_grid(count, TB), TB, 0, s>>>(count, d_placed + first, z->d_nodes);
     ctx->launches++;
   }
+  if (depth >= 1) { k_subtree<<<1, 32, 0, s>>>(1, nullptr, z->d_nodes); ctx->launches++; }
   CX_CUDA(cudaEventRecord(ctx->ev1, s));
   CX_CUDA(cudaStreamSynchronize(s));
   CX_CUDA(cudaGetLastError());
@@ -214,7 +241,7 @@ int cx_build_adt(cx_zone* z)
   z->depth = depth;
   z->levels = L;
   cudaFreeAsync(B.keys, s); cudaFreeAsync(B.lo, s); cudaFreeAsync(B.hi, s); cudaFreeAsync(B.cur, s); cudaFreeAsync(B.br, s); cudaFreeAsync(B.depth, s);
-  cudaFreeAsync(S.actA, s); cudaFreeAsync(S.actB, s);
+  cudaFreeAsync(S.actA, s); cudaFreeAsync(S.actB, s); cudaFreeAsync(d_placed, s);
   if (depth + 2 > CX_STACK)
   {
     cx_set_error("ADT depth %d exceeds the traversal stack (%d)", depth, CX_STACK);
