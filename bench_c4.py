@@ -125,7 +125,7 @@ def linear_field_check(sess, tR, tD, var, loc, ctx, comm):
 
 def measure_c4(args, ctx, comm, ngpus, rank, world):
     """C4/C5 on the ranks of this job; returns the result dict on rank 0 (None elsewhere)."""
-    from bench import ClockSampler, measured_peaks
+    from bench import ClockSampler, measured_peaks, ncu_traffic
     from cassiopee_b200 import _lib, Distributor2 as D2, workloads as W
     import cassiopee_b200.Internal as Internal
     import cassiopee_b200.Converter as C
@@ -235,6 +235,9 @@ def measure_c4(args, ctx, comm, ngpus, rank, world):
     sess.close()
     if rank != 0:
         return None
+    cpu = None
+    if ngpus == 1 and world == 1 and not args.quick:
+        cpu = cpu_baseline_c4(args, blocks, nvars, tree=tcl)
     ms_step = ms_max / args.steps
     value = B / (ms_step * 1e-3) / 1e9
     peak, how = measured_peaks()
@@ -247,7 +250,7 @@ def measure_c4(args, ctx, comm, ngpus, rank, world):
                                        "NVLink, flag per rank pair (no NCCL call in the step)",
                                 "nccl": "grouped ncclSend/ncclRecv of one packed buffer per rank pair",
                                 "none": "single rank"}[transport]},
-        "check": check,
+        "check": check, "cpu_baseline": cpu,
         "c5_100_iterations": {"ms_total": ms100_max, "ms_per_step": ms100_max / 100.,
                               "GBps": B / (ms100_max / 100. * 1e-3) / 1e9},
         "clocks": clocks,
@@ -257,8 +260,11 @@ def measure_c4(args, ctx, comm, ngpus, rank, world):
                 "api": "TransferSession.upload_donor_fields/step/download (host trees in, host trees out)"},
         "gpu_launches": int(launches_all), "comm_overlap": bool(use_graph),
         "roofline": {"bound": "hbm", "achieved": value / ngpus, "peak": peak, "unit": "GB/s per GPU",
-                     "frac": value / ngpus / peak, "traffic": None, "peak_source": how,
-                     "kernel": "k_transfer_set<2> (+ NCCL send/recv + k_scatter_set inside the step)"},
+                     "frac": value / ngpus / peak,
+                     "traffic": (ncu_traffic("c4_%dvars" % nvars)[0] if (ngpus == 1 and nblk == 100) else None),
+                     "traffic_source": (ncu_traffic("c4_%dvars" % nvars)[1] if (ngpus == 1 and nblk == 100) else None),
+                     "peak_source": how,
+                     "kernel": "k_transfer_set<2> (+ at N>1: remote plans into peer memory, flag exchange, k_scatter_set)"},
         "set_interp_data": {"value": nrcv / sid_max, "unit": "receptor pts/s", "receptors": int(nrcv),
                             "s": sid_max, "s_first_call": sid_first,
                             "note": "second call (device memory pool warm); the first call is reported beside it",
@@ -286,8 +292,7 @@ def run_c4(args):
     for k in ("config", "stats", "check", "clocks", "e2e", "gpu_launches", "comm_overlap", "roofline", "set_interp_data",
               "c5_100_iterations"):
         line[k] = r[k]
-    line["cpu_baseline"] = cpu_baseline_c4(args, layout_for(ngpus, int(os.environ.get("CX_C4_N", "100")))[0],
-                                           int(os.environ.get("CX_C4_NVARS", "7"))) if (ngpus == 1 and not args.quick) else None
+    line["cpu_baseline"] = r.get("cpu_baseline")
     print(json.dumps(line))
 
 
@@ -328,14 +333,17 @@ def _sample_case(blocks, nvars, nrz=2):
     return out, grid
 
 
-def cpu_baseline_c4(args, blocks, nvars, nrz=2):
+def cpu_baseline_c4(args, blocks, nvars, nrz=2, tree=None):
     try:
-        return reference_c4_impl(args, blocks, nvars, nrz)[0]
+        return reference_c4_impl(args, blocks, nvars, nrz, tree)[0]
     except Exception as e:
         return {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
 
 
-def reference_c4_impl(args, blocks, nvars, nrz=2):
+def reference_c4_impl(args, blocks, nvars, nrz=2, tree=None):
+    """The reference's C++ (oracle/_ref) on a bounded sample of C4 on the host cores.  tree: the donor tree the device
+    path filled (N=1): the ID_* subregions of the sampled receptor zones are compared with the reference's lists, list
+    by list, at full size."""
     from oracle import oracle as O
     from cassiopee_b200 import workloads as W
     from bench import alg_bytes, distinct_nodes
@@ -348,7 +356,7 @@ def reference_c4_impl(args, blocks, nvars, nrz=2):
                 d = grid(b)
                 zones[b['name']] = O.RefZone(d.ni, d.nj, d.nk, d.x, d.y, d.z)
     t_adt = time.perf_counter() - t0
-    plans = []
+    plans = []; plans_named = []
     t0 = time.perf_counter()
     nrcv = 0
     for rb, g, sel, donors in sample:
@@ -357,6 +365,7 @@ def reference_c4_impl(args, blocks, nvars, nrz=2):
         for k, b in enumerate(donors):
             if out[0][k].size:
                 plans.append((grid(b), sel[out[0][k]].astype(np.int32), out[1][k], out[2][k], out[3][k], g.npts))
+                plans_named.append(plans[-1] + (rb['name'],))
     t_search = time.perf_counter() - t0
     B = 0
     fields = {}
@@ -381,6 +390,21 @@ def reference_c4_impl(args, blocks, nvars, nrz=2):
             (nrz, nrcv, len(zones), len(plans), nvars))
     cpu = {"value": value, "unit": "GB/s", "cores": int(min(nvars, nth)), "kind": "reference", "host_cores": nth,
            "ms_per_step": dt * 1e3, "sample": desc}
+    if tree is not None:
+        import cassiopee_b200.Internal as Internal
+        zd = {z[0]: z for z in Internal.getZones(tree)}
+        nsub = 0; same = True
+        # plans were appended receptor zone by receptor zone, donors in list order, empty pairs skipped
+        for d, rcv, dnr, typ, cf, nR, rname in plans_named:
+            sr = Internal.getNodeFromName1(zd[d.name], 'ID_' + rname) if d.name in zd else None
+            if sr is None:
+                same = False; continue
+            get = lambda nm: Internal.getNodeFromName1(sr, nm)[1]
+            same = same and np.array_equal(get('PointListDonor'), rcv) and np.array_equal(get('PointList'), dnr) \
+                and np.array_equal(get('InterpolantsType'), typ) and np.array_equal(get('InterpolantsDonor'), cf)
+            nsub += 1
+        cpu["parity_vs_device_at_full_size"] = {"subregions_compared": nsub, "receptors": int(nrcv),
+                                                "lists_identical": bool(same)}
     sid = {"value": nrcv / (t_adt + t_search), "unit": "receptor pts/s", "receptors": int(nrcv), "adt_build_s": t_adt,
            "search_s": t_search, "cores": nth}
     return cpu, sid, dt, steps, desc, B

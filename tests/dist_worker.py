@@ -147,6 +147,30 @@ def main():
         for k, a in ref_fld.items():
             if not np.array_equal(a, got_fld[k]):
                 ok = False; print("FIELD MISMATCH", k, np.abs(a - got_fld[k]).max())
+        if mode == 'nccl':
+            # the distributed DEVICE result against the ORACLE backend (the reference's own C++) driven through the same
+            # tree layer on one process: every ID_* child identical; for the centre-located case (donor fields in a
+            # separate tc: transfers are idempotent and order-free) the transferred fields as well
+            t2 = make()
+            tc2 = t2 if case == 'c2n' else C.node2Center(t2)
+            ob = OracleBackend()
+            Xmpi._setInterpData(t2, tc2, order=order, nature=1, penalty=1, extrap=1, loc=loc, storage='inverse',
+                                sameBase=1, comm=None, zoneOrder=zoneOrder, backend=ob)
+            if case != 'c2n':
+                Xmpi._setInterpTransfers(t2, tc2, variables=VARS, comm=None, backend=ob)
+            ora_sub, ora_fld = collect(tc2, t2)
+            if set(ora_sub) != set(got_sub):
+                ok = False; print("subregion sets differ from the oracle's", sorted(set(got_sub) ^ set(ora_sub))[:5])
+            for k in ora_sub:
+                for name, a in ora_sub[k].items():
+                    b = got_sub.get(k, {}).get(name)
+                    if b is None or not np.array_equal(a, b):
+                        ok = False; print("ORACLE MISMATCH", k, name)
+            if case != 'c2n':
+                for k, a in ora_fld.items():
+                    if not np.array_equal(a, got_fld[k]):
+                        ok = False; print("ORACLE FIELD MISMATCH", k, np.abs(a - got_fld[k]).max())
+            print("dist_worker: distributed device result == oracle backend on one process: %s" % ok)
         nrcv = sum(v['PointListDonor'].size for v in ref_sub.values())
         print("dist_worker %s order=%d world=%d: %d subregions, %d receptors, ok=%s" %
               (mode, order, comm.size, nsub, nrcv, ok))
