@@ -582,15 +582,24 @@ class TransferSession:
             if err and os.environ.get("CX_PROFILE"):
                 print("[TransferSession] peer-memory transport unavailable (%s); using NCCL" % err, file=_sys.stderr, flush=True)
             return False
-        self._ipc_descs = [d for p in self.peers for d in allx[p][rank]]
+        self._ipc_descs = []                    # one entry per successful ipc_open (the mappings are reference counted)
+
+        def _open(d):
+            q = _lib.ipc_open(ctx, d)
+            self._ipc_descs.append(d)
+            return q
         try:
-            rbuf = {p: [_lib.ipc_open(ctx, allx[p][rank][par]) for par in (0, 1)] for p in self.peers}
-            pflags = [_lib.ipc_open(ctx, allx[p][rank][2]) for p in self.peers]
+            rbuf = {p: [_open(allx[p][rank][par]) for par in (0, 1)] for p in self.peers}
+            pflags = [_open(allx[p][rank][2]) for p in self.peers]
         except _lib.CxError as e:
             if os.environ.get("CX_PROFILE"):
                 print("[TransferSession] cudaIpcOpenMemHandle failed (%s); using NCCL" % e, file=_sys.stderr, flush=True)
             rbuf = None
         if not all(comm.allgather_obj(rbuf is not None)):
+            for d in self._ipc_descs:             # NCCL fallback: drop what this rank did map
+                _lib.ipc_close(d)
+            self._ipc_descs = []
+            comm.barrier()
             return False
         ps2, ss2 = [], []
         for par in (0, 1):

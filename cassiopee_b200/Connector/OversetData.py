@@ -144,39 +144,25 @@ def _createInterpRegion__(z, zname, pointlist, pointlistdonor, interpCoef, inter
 # ---------------------------------------------------------------------------
 # 0. callers either side of the path, host side
 # ---------------------------------------------------------------------------
-def _applyBCOverlapsStruct__(cellN, minIndex, maxIndex, depth, loc, val=2):
-    """connector.applyBCOverlapStruct (Connector/Connector/applyBCOverlaps.cpp:27-125) on a
-    Fortran-ordered (im,jm,km) cellN array, in place: the `depth` layers next to the window get
-    `val` unless they are blanked (cellN == 0).  Indices 1-based like the reference."""
-    if loc == 'nodes': shift = 1
-    elif loc == 'centers': shift = 0
-    else: raise ValueError("applyBCOverlapsStruct: invalid location.")
-    im, jm, km = cellN.shape
-    (imin, jmin, kmin), (imax, jmax, kmax) = minIndex, maxIndex
-    lim = (im, jm, km) if loc == 'nodes' else (im + 1, jm + 1, km + 1)
-    if imin < 1 or imax > lim[0] or jmin < 1 or jmax > lim[1] or kmin < 1 or kmax > lim[2]:
-        raise TypeError("applyBCOverlaps: indices of structured window are not valid.")
-
-    def rng(a, b, n):
-        if a == b:
-            if a == 1: return 1, min(depth, n)
-            return max(a - depth + shift, 1), b - 1 + shift
-        return a, b - 1 + shift
-    imin, imax = rng(imin, imax, im); jmin, jmax = rng(jmin, jmax, jm); kmin, kmax = rng(kmin, kmax, km)
-    sub = cellN[imin - 1:imax, jmin - 1:jmax, kmin - 1:kmax]
-    sub[sub != 0.] = float(val)
-    return None
+def _prepBackend(backend, ctx=None):
+    """The compute backend of the cellN preparers: the CUDA library unless a test injects another one."""
+    if backend is None:
+        backend = _lib.DeviceBackend(ctx or _lib.default_context())
+    return backend
 
 
-def _applyBCOverlaps(t, depth=2, loc='centers', val=2, cellNName='cellN'):
+def _applyBCOverlaps(t, depth=2, loc='centers', val=2, cellNName='cellN', ctx=None, backend=None):
     """Connector.PyTree._applyBCOverlaps for structured zones (Connector/PyTree.py:1548-1600, :1674-1720):
     cellN (created =1 if absent) is set to `val` in the `depth` layers next to every non doubly-defined
-    BCOverlap window (GridConnectivity_t of type 'Overset' with a PointRange)."""
+    BCOverlap window (GridConnectivity_t of type 'Overset' with a PointRange).  The windows of a zone are applied
+    by connector.applyBCOverlapStruct = cx_apply_bc_overlap (csrc/cx_prepare.cu), one upload / download per zone."""
+    if loc not in ('nodes', 'centers'):
+        raise ValueError("applyBCOverlapsStruct: invalid location.")
     var = cellNName if loc == 'nodes' else 'centers:' + cellNName
     for z in Internal.getZones(t):
         if C.isNamePresent(z, var) == -1:
             C._initVars(z, var, 1.)
-        cellN = C.getFieldArray(z, var)
+        windows = []
         for o in Internal.getNodesFromType2(z, 'GridConnectivity_t'):
             n = Internal.getNodeFromType1(o, 'GridConnectivityType_t')
             if n is None or Internal.getValue(n) != 'Overset':
@@ -189,81 +175,42 @@ def _applyBCOverlaps(t, depth=2, loc='centers', val=2, cellNName='cellN'):
                 print("Warning: applyBCOverlaps: BCOverlap is ill-defined.")
                 continue
             w = r[1]
-            _applyBCOverlapsStruct__(cellN, (int(w[0, 0]), int(w[1, 0]), int(w[2, 0])),
-                                     (int(w[0, 1]), int(w[1, 1]), int(w[2, 1])), depth, loc, val=val)
+            windows.append(((int(w[0, 0]), int(w[1, 0]), int(w[2, 0])), (int(w[0, 1]), int(w[1, 1]), int(w[2, 1]))))
+        if windows:
+            _prepBackend(backend, ctx).apply_bc_overlaps(C.getFieldArray(z, var), windows, depth, loc, val)
     return None
 
 
-def applyBCOverlaps(t, depth=2, loc='centers', val=2, cellNName='cellN'):
+def applyBCOverlaps(t, depth=2, loc='centers', val=2, cellNName='cellN', ctx=None, backend=None):
     a = Internal.copyRef(t)
     for z in Internal.getZones(a):      # the cellN array is modified in place: give the copy its own
         var = cellNName if loc == 'nodes' else 'centers:' + cellNName
         c = C.getFieldArray(z, var)
         if c is not None:
             C._initVars(z, var, numpy.array(c, order='F', copy=True))
-    _applyBCOverlaps(a, depth=depth, loc=loc, val=val, cellNName=cellNName)
+    _applyBCOverlaps(a, depth=depth, loc=loc, val=val, cellNName=cellNName, ctx=ctx, backend=backend)
     return a
 
 
-def _holeFringeStruct__(cellN, depth, dir):
-    """connector._getOversetHolesInterpNodes on one structured cellN array (i fastest, shape (im,jm,km)):
-    searchMaskInterpolatedCellsStructOpt (Connector/Connector/getInterpolatedPoints.cpp:370-660).  A point with
-    cellN == 1 becomes 2 when a point of its stencil has cellN == 0.  dir=0: cross (+-1..depth along each axis,
-    indices clamped to the zone, :455-484); dir=1: star (the 26 directions, a component that leaves the zone
-    falls back to the point's own index, :582-640).  In place; evaluated on the input values (Jacobi)."""
+def _setHoleInterpolatedPoints(a, depth=2, dir=0, loc='centers', cellNName='cellN', addGC=True, ctx=None, backend=None):
+    """Connector.PyTree._setHoleInterpolatedPoints for structured zones (Connector/PyTree.py:1766-1783,
+    Connector.py:168-192): cellN=2 on the `depth` layers around the blanked (cellN=0) points, by
+    connector._getOversetHolesInterpCellCenters / Nodes = cx_hole_fringe (csrc/cx_prepare.cu; dir 0: cross, dir 1:
+    star); depth<0 grows the fringe inwards (0 and 1 exchanged before and after, Connector.py:179-182).  The
+    reference's second pass on ghost cells (addGC) only propagates through abutting (match) connectivity, which this
+    path does not carry."""
+    if depth == 0: return None
     if dir not in (0, 1):
         raise NotImplementedError("setHoleInterpolatedPoints: dir=%d (diamond / octahedron stencils) is not available." % dir)
-    im, jm, km = cellN.shape
-    blank = (cellN >= -1.e-15) & (cellN <= 1.e-15)                 # K_FUNC::fEqualZero
-    one = numpy.abs(cellN - 1.) <= 1.e-15                           # K_FUNC::fEqual(cellN, 1.)
-    if not blank.any():
-        return None
-    I, J, K = numpy.arange(im), numpy.arange(jm), numpy.arange(km)
-    hit = numpy.zeros(cellN.shape, dtype=bool)
-
-    def idx(base, off, n, clamp):
-        v = base + off
-        if clamp: return numpy.clip(v, 0, n - 1)
-        return numpy.where((v < 0) | (v > n - 1), base, v)
-    if dir == 0:
-        for d in range(1, depth + 1):
-            for sgn in (-1, 1):
-                hit |= blank[idx(I, sgn * d, im, True), :, :]
-                hit |= blank[:, idx(J, sgn * d, jm, True), :]
-                hit |= blank[:, :, idx(K, sgn * d, km, True)]
-    else:
-        for d in range(1, depth + 1):
-            for kd in (-1, 0, 1):
-                for jd in (-1, 0, 1):
-                    for id_ in (-1, 0, 1):
-                        if id_ == 0 and jd == 0 and kd == 0:
-                            continue
-                        hit |= blank[numpy.ix_(idx(I, id_ * d, im, False), idx(J, jd * d, jm, False),
-                                               idx(K, kd * d, km, False))]
-    cellN[one & hit] = 2.
-    return None
-
-
-def _setHoleInterpolatedPoints(a, depth=2, dir=0, loc='centers', cellNName='cellN', addGC=True):
-    """Connector.PyTree._setHoleInterpolatedPoints for structured zones (Connector/PyTree.py:1766-1783,
-    Connector.py:168-192): cellN=2 on the `depth` layers around the blanked (cellN=0) points; depth<0 grows the
-    fringe inwards (0 and 1 exchanged before and after, Connector.py:179-182).  The reference's second pass on
-    ghost cells (addGC) only propagates through abutting (match) connectivity, which this path does not carry."""
-    if depth == 0: return None
     var = cellNName if loc == 'nodes' else 'centers:' + cellNName
     for z in Internal.getZones(a):
         c = C.getFieldArray(z, var)
         if c is None: continue
-        if depth < 0:
-            c[...] = 1. - c + (c > 1.5) * 3.
-            _holeFringeStruct__(c, -depth, dir)
-            c[...] = 1. - c + (c > 1.5) * 3.
-        else:
-            _holeFringeStruct__(c, depth, dir)
+        _prepBackend(backend, ctx).hole_fringe(c, depth, dir)
     return None
 
 
-def setHoleInterpolatedPoints(a, depth=2, dir=0, loc='centers', cellNName='cellN'):
+def setHoleInterpolatedPoints(a, depth=2, dir=0, loc='centers', cellNName='cellN', ctx=None, backend=None):
     """Set cellN=2 around cellN=0 points."""
     b = Internal.copyRef(a)
     var = cellNName if loc == 'nodes' else 'centers:' + cellNName
@@ -271,7 +218,7 @@ def setHoleInterpolatedPoints(a, depth=2, dir=0, loc='centers', cellNName='cellN
         c = C.getFieldArray(z, var)
         if c is not None:
             C._initVars(z, var, numpy.array(c, order='F', copy=True))
-    _setHoleInterpolatedPoints(b, depth=depth, dir=dir, loc=loc, cellNName=cellNName)
+    _setHoleInterpolatedPoints(b, depth=depth, dir=dir, loc=loc, cellNName=cellNName, ctx=ctx, backend=backend)
     return b
 
 

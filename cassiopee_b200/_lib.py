@@ -76,6 +76,10 @@ _SIGS = {
     "cx_transfer_celln_dev": (_i, [_vp, _vp, _vp]),
     "cx_scatter_dev": (_i, [_vp, _i, _vp, _ll, _i, _vp, _vp]),
     "cx_gather_dev": (_i, [_vp, _i, _vp, _ll, _i, _vp, _vp]),
+    "cx_apply_bc_overlaps": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, ctypes.c_double, _vp]),
+    "cx_apply_bc_overlap_dev": (_i, [_vp] + [_i] * 11 + [ctypes.c_double, _vp]),
+    "cx_hole_fringe": (_i, [_vp] + [_i] * 5 + [_vp]),
+    "cx_hole_fringe_dev": (_i, [_vp] + [_i] * 5 + [_vp, _vp]),
     "cx_host_scatter": (_i, [_vp, _vp, _vp, _ll]),
     "cx_plan_info": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "cx_plan_sorted_rcv": (_i, [_vp, _vp]),
@@ -556,6 +560,28 @@ class Plan:
         return i["alg_fixed"] + 8 * nvars * (i["n"] + i["distinct"])
 
 
+def _celln_dims(cellN):
+    if cellN.dtype != np.float64 or not cellN.flags.f_contiguous:
+        raise TypeError("cellN must be a Fortran-ordered float64 array")
+    return (list(cellN.shape) + [1, 1])[:3]
+
+
+def apply_bc_overlaps(ctx, cellN, windows, depth, loc, val):
+    """connector.applyBCOverlapStruct for every (minIndex, maxIndex) window of one zone, on a Fortran-ordered
+    (im,jm,km) float64 array, in place (device: one upload, one launch per window, one download)."""
+    im, jm, km = _celln_dims(cellN)
+    win = np.ascontiguousarray([list(a) + list(b) for a, b in windows], dtype=np.int32)
+    check(lib().cx_apply_bc_overlaps(ctx.h, im, jm, km, len(windows), ptr(win), int(depth), 0 if loc == 'nodes' else 1,
+                                     float(val), ptr(cellN)))
+
+
+def hole_fringe(ctx, cellN, depth, dir):
+    """connector._getOversetHolesInterp* on a Fortran-ordered (im,jm,km) float64 array, in place (device); depth < 0:
+    the fringe grows into the blanked region."""
+    im, jm, km = _celln_dims(cellN)
+    check(lib().cx_hole_fringe(ctx.h, im, jm, km, int(depth), int(dir), ptr(cellN)))
+
+
 def gather_dev(ctx, d_out, ld, n, d_idx, field_ptrs):
     """out[v*ld + e] = field[v][idx[e]] on the device (asynchronous on the context's stream)."""
     nv = len(field_ptrs)
@@ -722,6 +748,12 @@ class DeviceBackend:
 
     def make_plan(self, imd, jmd, kmd, nptsR, donor, rcv, typ, coefs):
         return Plan(self.ctx, imd, jmd, kmd, nptsR, donor, rcv, typ, coefs)
+
+    def apply_bc_overlaps(self, cellN, windows, depth, loc, val):
+        apply_bc_overlaps(self.ctx, cellN, windows, depth, loc, val)
+
+    def hole_fringe(self, cellN, depth, dir):
+        hole_fringe(self.ctx, cellN, depth, dir)
 
 
 def ipc_export(dptr):

@@ -83,7 +83,8 @@ int load_range()
   if (!g_range) { cx_set_error("cuMemGetAddressRange_v2 missing"); return -5; }
   return 0;
 }
-std::map<std::string, void*> g_opened;           // IPC handle bytes -> mapped base (a handle can be opened once per process)
+struct Opened { void* base; int refs; };
+std::map<std::string, Opened> g_opened;          // IPC handle bytes -> mapped base (a handle can be opened once per process) + users
 }  // namespace
 
 extern "C" {
@@ -108,13 +109,13 @@ int cx_ipc_open(cx_ctx* ctx, const void* handle72, void** dptr)
   std::string key((const char*)handle72, 64);
   void* base = nullptr;
   auto it = g_opened.find(key);
-  if (it != g_opened.end()) base = it->second;
+  if (it != g_opened.end()) { base = it->second.base; it->second.refs++; }
   else
   {
     cudaIpcMemHandle_t h;
     memcpy(&h, handle72, 64);
     CX_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
-    g_opened[key] = base;
+    g_opened[key] = Opened{base, 1};
   }
   unsigned long long off;
   memcpy(&off, (const char*)handle72 + 64, 8);
@@ -122,20 +123,22 @@ int cx_ipc_open(cx_ctx* ctx, const void* handle72, void** dptr)
   return 0;
 }
 
-// unmap one imported allocation (all pointers derived from this descriptor become invalid)
+// drop one use of an imported allocation; it is unmapped when its last user closes it (two sessions can hold
+// descriptors that resolve to the same allocation)
 int cx_ipc_close(const void* handle72)
 {
   std::string key((const char*)handle72, 64);
   auto it = g_opened.find(key);
   if (it == g_opened.end()) return 0;
-  cudaIpcCloseMemHandle(it->second);
+  if (--it->second.refs > 0) return 0;
+  cudaIpcCloseMemHandle(it->second.base);
   g_opened.erase(it);
   return 0;
 }
 
 int cx_ipc_close_all(void)
 {
-  for (auto& kv : g_opened) cudaIpcCloseMemHandle(kv.second);
+  for (auto& kv : g_opened) cudaIpcCloseMemHandle(kv.second.base);
   g_opened.clear();
   return 0;
 }

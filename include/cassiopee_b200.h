@@ -80,6 +80,23 @@ int cx_zone_candidates(cx_zone* zone, double x, double y, double z, double alpha
 int cx_zone_export_adt(cx_zone* zone, void* nodes_out, size_t bytes);
 int cx_zone_destroy(cx_zone* zone);
 
+/* ---- cellN preparers either side of the path ------------
+ * cx_apply_bc_overlap: connector.applyBCOverlapStruct(array, imin,jmin,kmin, imax,jmax,kmax, depth, loc, val, cellNName)
+ * (Connector/Connector/applyBCOverlaps.cpp:27-125): the `depth` layers next to the 1-based window get `val` unless
+ * blanked (cellN == 0); loc 0 = nodes, 1 = centres; cellN: (im,jm,km) doubles, i fastest, in place.
+ * cx_hole_fringe: connector._getOversetHolesInterpNodes / _getOversetHolesInterpCellCenters(array, depth, dir, cellNName)
+ * (getInterpolatedPoints.cpp:370-650, searchMaskInterpolatedCellsStructOpt): cellN == 1 -> 2 where a point of the
+ * stencil (dir 0: cross, dir 1: star; dir 2 / 3 return -4) has cellN == 0; depth < 0 grows the fringe into the
+ * blanked region (Connector/Connector/Connector.py:176-182).  cx_apply_bc_overlaps applies all the windows of a zone
+ * ([nwin][6], host pointer) with one upload and one download.  The _dev forms work on device arrays
+ * (cx_dev_alloc), asynchronously on the context's stream; cx_hole_fringe_dev writes d_out (d_in is read only). */
+int cx_apply_bc_overlaps(cx_ctx* ctx, int im, int jm, int km, int nwin, const int* win /* [nwin][6]: imin,jmin,kmin,imax,jmax,kmax */,
+                         int depth, int loc, double val, double* cellN);
+int cx_apply_bc_overlap_dev(cx_ctx* ctx, int im, int jm, int km, int imin, int jmin, int kmin, int imax, int jmax,
+                            int kmax, int depth, int loc, double val, double* d_cellN);
+int cx_hole_fringe(cx_ctx* ctx, int im, int jm, int km, int depth, int dir, double* cellN);
+int cx_hole_fringe_dev(cx_ctx* ctx, int im, int jm, int km, int depth, int dir, const double* d_in, double* d_out);
+
 /* ---- setInterpData ------------------------------------------------------
  * Replaces: connector.setInterpData(interpPts, donorArrays, order, nature,
  * penalty, extrap, interpDataTypeList, hooks) — Connector/Connector/setInterpData.cpp:585-1322

@@ -241,6 +241,31 @@ def transfer_celln(cellND, cellNR, imd, jmd, rcv, dnr, typ, coefs):
                              rcv.ctypes.data, dnr.ctypes.data, typ.ctypes.data, coefs.ctypes.data)
 
 
+def hole_fringe(cellN, depth, dir=0):
+    """The reference's searchMaskInterpolatedCellsStructOpt (getInterpolatedPoints.cpp:370-, compiled unchanged) on a
+    Fortran-ordered (im,jm,km) cellN array, in place."""
+    assert cellN.dtype == np.float64 and cellN.flags.f_contiguous
+    im, jm, km = (list(cellN.shape) + [1, 1])[:3]
+    f = lib().ref_hole_fringe
+    f.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p]
+    f.restype = None
+    f(im, jm, km, int(depth), int(dir), cellN.ctypes.data)
+
+
+def apply_bc_overlap(cellN, minIndex, maxIndex, depth, loc, val=2):
+    """connector.applyBCOverlapStruct (applyBCOverlaps.cpp:27-125, restated in oracle/ref_driver.cpp) on a
+    Fortran-ordered (im,jm,km) cellN array, in place; raises TypeError for the windows the reference refuses."""
+    assert cellN.dtype == np.float64 and cellN.flags.f_contiguous
+    im, jm, km = (list(cellN.shape) + [1, 1])[:3]
+    f = lib().ref_apply_bc_overlap
+    f.argtypes = [ctypes.c_int] * 12 + [ctypes.c_void_p]
+    f.restype = ctypes.c_int
+    rc = f(im, jm, km, int(minIndex[0]), int(minIndex[1]), int(minIndex[2]), int(maxIndex[0]), int(maxIndex[1]),
+           int(maxIndex[2]), int(depth), 0 if loc == 'nodes' else 1, int(val), cellN.ctypes.data)
+    if rc != 0:
+        raise TypeError("applyBCOverlaps: indices of structured window are not valid.")
+
+
 def transfer_compact(roR, roD, zparams, dtloc, param_int, param_real, vartype=1, type_transfert=0, no_transfert=1,
                      nstep=1, threadmax_sdm=1):
     """The reference's ___setInterpTransfers reader (setInterpTransfers.cpp:761-1410) with its own arithmetic fragments,

@@ -37,6 +37,13 @@
 using namespace std;
 using namespace K_FLD;
 
+// Connector/Connector/getInterpolatedPoints.cpp:370 (C++ linkage: declared outside the extern "C" block)
+namespace K_CONNECTOR {
+void searchMaskInterpolatedCellsStructOpt(E_Int imc, E_Int jmc, E_Int kmc, E_Int depth, E_Int dir,
+                                          E_Float* cellN, E_Float* cellN_tmp);
+}
+
+
 /* SIZECF: Connector/Connector/connector.h:27-37 (pulled by macro re-statement
  * because connector.h drags the whole Connector module in). */
 #define SIZECF(type, meshtype, sizecf)                     \
@@ -442,6 +449,66 @@ int ref_transfer_compact(int nidomR, double** roR, double** roD, int** zparam, c
     }
   }
   return done;
+}
+
+/* setHoleInterpolatedPoints on one structured cellN array: the reference's OWN routine
+ * (K_CONNECTOR::searchMaskInterpolatedCellsStructOpt, Connector/Connector/getInterpolatedPoints.cpp:370-, compiled
+ * unchanged), called the way _getOversetHolesInterpNodes / CellCenters call it (:1124-1144): on a copy, then copied
+ * back.  dir 0..3. */
+void ref_hole_fringe(int im, int jm, int km, int depth, int dir, double* cellN)
+{
+  size_t n = (size_t)im * jm * km;
+  std::vector<double> tmp(cellN, cellN + n);
+  K_CONNECTOR::searchMaskInterpolatedCellsStructOpt(im, jm, km, depth, dir, cellN, tmp.data());
+  memcpy(cellN, tmp.data(), sizeof(double) * n);
+}
+
+/* connector.applyBCOverlapStruct (Connector/Connector/applyBCOverlaps.cpp:27-125) without its Python argument
+ * parsing: the window arithmetic (:69-96) and the loop (:98-112) restated statement by statement.  Returns -1 for
+ * the windows the reference refuses (:61-66, :73-78). */
+int ref_apply_bc_overlap(int im, int jm, int km, int imin, int jmin, int kmin, int imax, int jmax, int kmax,
+                         int depth, int loc, int cellNInterpValue, double* cellNt)
+{
+  E_Int shift = 0;
+  if (loc == 0) shift = 1; // loc='nodes'
+  E_Float interpolatedValue = cellNInterpValue;
+  if (loc == 0) // nodes
+  {
+    if (imin < 1 || imax > im || jmin < 1 || jmax > jm || kmin < 1 || kmax > km) return -1;
+  }
+  else // centers
+  {
+    if (imin < 1 || imax > im+1 || jmin < 1 || jmax > jm+1 || kmin < 1 || kmax > km+1) return -1;
+  }
+  if (imin == imax)
+  {
+    if (imin == 1) {imin = 1; imax = K_FUNC::E_min(depth,im);}
+    else { imin =  K_FUNC::E_max(imin-depth+shift,1); imax = imax-1+shift;}
+  }
+  else
+  {imax = imax-1+shift;}
+  if (jmin == jmax )
+  {
+    if (jmin == 1) {jmin = 1; jmax = K_FUNC::E_min(depth, jm);}
+    else {jmin = K_FUNC::E_max(jmin-depth+shift,1); jmax = jmax-1+shift;}
+  }
+  else
+  {jmax = jmax-1+shift;}
+  if (kmin == kmax)
+  {
+    if (kmin == 1) { kmin = 1 ; kmax = K_FUNC::E_min(depth, km);}
+    else {kmin = K_FUNC::E_max(kmin-depth+shift,1); kmax = kmax-1+shift;}
+  }
+  else {kmax = kmax-1+shift;}
+  E_Int imjm = im*jm;
+  for (E_Int k = kmin; k <= kmax; k++)
+    for (E_Int j = jmin; j <= jmax; j++)
+      for (E_Int i = imin; i <= imax; i++)
+      {
+        E_Int ind = (i-1) + (j-1)* im + (k-1)*imjm;
+        if (cellNt[ind] != 0.) cellNt[ind] = interpolatedValue;
+      }
+  return 0;
 }
 
 /* K_METRIC::compVolOfStructCell3D (selection volume, for unit checks). */

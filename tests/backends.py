@@ -45,6 +45,21 @@ class OracleBackend:
     def make_plan(self, *a):
         return OraclePlan(*a)
 
+    def apply_bc_overlaps(self, cellN, windows, depth, loc, val):
+        from oracle import oracle as O
+        for a, b in windows:
+            O.apply_bc_overlap(cellN, a, b, depth, loc, val)
+
+    def hole_fringe(self, cellN, depth, dir):
+        """The reference's own searchMaskInterpolatedCellsStructOpt; depth < 0 as Connector.py:176-182 does it."""
+        from oracle import oracle as O
+        if depth < 0:
+            cellN[...] = 1. - cellN + (cellN > 1.5) * 3.
+            O.hole_fringe(cellN, -depth, dir)
+            cellN[...] = 1. - cellN + (cellN > 1.5) * 3.
+        else:
+            O.hole_fringe(cellN, depth, dir)
+
 
 class OracleReceptors:
     def __init__(self, indcell, pts):

@@ -975,3 +975,84 @@ def test_transfer_session_sparse_download_and_c_ordered_fields(ctx, monkeypatch)
             full = sum(a.nbytes for z in Internal.getZones(t) for a in before[z[0]])
             assert nb < full                                             # B's fields were not downloaded whole
         sess.close()
+
+
+# ---- cellN preparers either side of the path, device vs the reference's routines ----------
+@pytest.mark.parametrize("shape", [(23, 17, 11), (40, 9, 1), (1, 1, 1), (97, 101, 33)])
+def test_hole_fringe_matches_reference(ctx, shape):
+    """cx_hole_fringe against K_CONNECTOR::searchMaskInterpolatedCellsStructOpt (getInterpolatedPoints.cpp:370-,
+    compiled unchanged): cross and star stencils, depths 1-3, 2-D and 3-D, depth < 0 (Connector.py:176-182)."""
+    from cassiopee_b200 import _lib
+    from tests.backends import OracleBackend
+    rng = np.random.default_rng(sum(shape))
+    be = OracleBackend()
+    for dir_ in (0, 1):
+        for depth in (1, 2, 3, -1, -2):
+            c = np.ones(shape, order='F')
+            r = rng.random(shape)
+            c[r < 0.02] = 0.; c[(r > 0.02) & (r < 0.05)] = 2.; c[(r > 0.05) & (r < 0.06)] = 1. + 1e-16
+            got = c.copy(order='F'); ref = c.copy(order='F')
+            _lib.hole_fringe(ctx, got, depth, dir_)
+            be.hole_fringe(ref, depth, dir_)
+            assert np.array_equal(got, ref), (shape, dir_, depth)
+            if depth > 0 and c.size > 1: assert (got != c).any()
+    with pytest.raises(NotImplementedError):
+        _lib.hole_fringe(ctx, np.ones(shape, order='F'), 2, 2)
+
+
+def test_apply_bc_overlaps_matches_reference(ctx):
+    """cx_apply_bc_overlaps against the statements of applyBCOverlaps.cpp:61-112 (oracle/ref_driver.cpp), nodes and
+    centres, every face, depths up to the zone size, blanked cells kept, invalid windows refused."""
+    from cassiopee_b200 import _lib
+    from oracle import oracle as O
+    rng = np.random.default_rng(8)
+    im, jm, km = 14, 9, 6
+    for loc in ('nodes', 'centers'):
+        e = 0 if loc == 'nodes' else 1                      # centres: the window is given on the node grid
+        faces = [((1, 1, 1), (1, jm + e, km + e)), ((im + e, 1, 1), (im + e, jm + e, km + e)),
+                 ((1, 1, 1), (im + e, 1, km + e)), ((1, jm + e, 1), (im + e, jm + e, km + e)),
+                 ((1, 1, 1), (im + e, jm + e, 1)), ((1, 1, km + e), (im + e, jm + e, km + e)),
+                 ((3, jm + e, 2), (8, jm + e, 5)), ((im + e, 2, 2), (im + e, 5, 4))]
+        for depth in (1, 2, 3, 20):
+            for val in (2, 3):
+                c = np.ones((im, jm, km), order='F'); c[rng.random(c.shape) < 0.1] = 0.
+                for w in faces:
+                    got = c.copy(order='F'); ref = c.copy(order='F')
+                    _lib.apply_bc_overlaps(ctx, got, [w], depth, loc, val)
+                    O.apply_bc_overlap(ref, w[0], w[1], depth, loc, val)
+                    assert np.array_equal(got, ref), (loc, depth, w)
+                got = c.copy(order='F'); ref = c.copy(order='F')
+                _lib.apply_bc_overlaps(ctx, got, faces, depth, loc, val)
+                for w in faces: O.apply_bc_overlap(ref, w[0], w[1], depth, loc, val)
+                assert np.array_equal(got, ref)
+        bad = ((0, 1, 1), (1, jm, km))
+        c = np.ones((im, jm, km), order='F')
+        with pytest.raises(TypeError): _lib.apply_bc_overlaps(ctx, c, [bad], 2, loc, 2)
+        with pytest.raises(TypeError): O.apply_bc_overlap(c, bad[0], bad[1], 2, loc, 2)
+        assert (c == 1.).all()
+
+
+def test_preparers_through_the_tree_layer(ctx):
+    """applyBCOverlaps + setHoleInterpolatedPoints (device backend) give the tree the oracle backend gives, and the
+    cellN they leave drives setInterpData."""
+    import cassiopee_b200.Connector.PyTree as XP
+    import cassiopee_b200.Converter as C
+    import cassiopee_b200.Generator as G
+    import cassiopee_b200.Internal as Internal
+    from tests.backends import OracleBackend
+    a = G.cart((0, 0, 0), (0.1, 0.1, 0.1), (21, 21, 21), name='A')
+    b = G.cart((1.45, 0.22, 0.31), (0.1, 0.1, 0.1), (18, 14, 12), name='B')
+    t = C.newPyTree(['Base', a, b])
+    zA, zB = Internal.getZones(t)
+    C._addBC2Zone(zA, 'ov1', 'BCOverlap', [21, 21, 1, 21, 1, 21])
+    C._addBC2Zone(zB, 'ov1', 'BCOverlap', [1, 1, 1, 14, 1, 12])
+    cB = np.ones((17, 13, 11), order='F'); cB[8:11, 5:8, 4:7] = 0.
+    C._initVars(zB, 'centers:cellN', cB)
+    out = []
+    for be in (None, OracleBackend()):
+        t2 = XP.applyBCOverlaps(t, depth=2, loc='centers', backend=be)
+        t2 = XP.setHoleInterpolatedPoints(t2, depth=2, dir=1, loc='centers', backend=be)
+        out.append([C.getFieldArray(z, 'centers:cellN') for z in Internal.getZones(t2)])
+    for g, r in zip(*out):
+        assert np.array_equal(g, r)
+    assert (out[0][1] == 2.).sum() > 2 * 13 * 11 and (out[0][1] == 0.).sum() == 27

@@ -173,13 +173,14 @@ def test_apply_bc_overlaps_and_intersecting_domains():
     C._addBC2Zone(zA, 'ov1', 'BCOverlap', [11, 11, 1, 11, 1, 11])     # imax face of A
     C._addBC2Zone(zB, 'ov1', 'BCOverlap', [1, 1, 1, 7, 1, 6])         # imin face of B
     C._addBC2Zone(zB, 'wall', 'BCWall', [1, 8, 1, 1, 1, 6])
-    t2 = XP.applyBCOverlaps(t, depth=2, loc='centers')
+    be = OracleBackend()
+    t2 = XP.applyBCOverlaps(t, depth=2, loc='centers', backend=be)
     cA = C.getFieldArray(Internal.getZones(t2)[0], 'centers:cellN')
     cB = C.getFieldArray(Internal.getZones(t2)[1], 'centers:cellN')
     assert cA.shape == (10, 10, 10) and (cA[8:, :, :] == 2).all() and (cA[:8, :, :] == 1).all()
     assert (cB[:2, :, :] == 2).all() and (cB[2:, :, :] == 1).all()
     assert C.getFieldArray(zA, 'centers:cellN') is None               # the input tree is untouched
-    t3 = XP.applyBCOverlaps(t, depth=1, loc='nodes')
+    t3 = XP.applyBCOverlaps(t, depth=1, loc='nodes', backend=be)
     nA = C.getFieldArray(Internal.getZones(t3)[0], 'cellN')
     assert (nA[10, :, :] == 2).all() and (nA[:10, :, :] == 1).all()
     d = XP.getIntersectingDomains(t)
@@ -187,7 +188,7 @@ def test_apply_bc_overlaps_and_intersecting_domains():
     # blanked cells stay blanked
     C._initVars(zA, 'centers:cellN', 1.)
     C.getFieldArray(zA, 'centers:cellN')[9, 0, 0] = 0.
-    XP._applyBCOverlaps(zA, depth=2, loc='centers')
+    XP._applyBCOverlaps(zA, depth=2, loc='centers', backend=be)
     assert C.getFieldArray(zA, 'centers:cellN')[9, 0, 0] == 0. and C.getFieldArray(zA, 'centers:cellN')[9, 1, 0] == 2.
 
 
@@ -276,18 +277,18 @@ def test_set_hole_interpolated_points():
                 c[rng.random(shape) < 0.03] = 2.
                 z = G.cart((0, 0, 0), (1, 1, 1), (shape[0] + 1, shape[1] + 1, shape[2] + 1), name='Z')
                 C._initVars(z, 'centers:cellN', c)
-                z2 = XP.setHoleInterpolatedPoints(z, depth=depth, dir=dir_, loc='centers')
+                z2 = XP.setHoleInterpolatedPoints(z, depth=depth, dir=dir_, loc='centers', backend=OracleBackend())
                 got = C.getFieldArray(Internal.getZones(z2)[0], 'centers:cellN')
                 assert np.array_equal(got, _hole_fringe_loops(c, depth, dir_)), (shape, dir_, depth)
                 assert np.array_equal(C.getFieldArray(z, 'centers:cellN'), c)      # input untouched
     # depth < 0: the fringe grows into the blanked region
     c = np.ones((7, 7, 7), order='F'); c[2:5, 2:5, 2:5] = 0.
     z = G.cart((0, 0, 0), (1, 1, 1), (8, 8, 8), name='Z'); C._initVars(z, 'centers:cellN', c)
-    XP._setHoleInterpolatedPoints(z, depth=-1, dir=0, loc='centers')
+    XP._setHoleInterpolatedPoints(z, depth=-1, dir=0, loc='centers', backend=OracleBackend())
     got = C.getFieldArray(z, 'centers:cellN')
     assert got[3, 3, 3] == 0. and got[2, 3, 3] == 2. and got[1, 3, 3] == 1. and got[2, 2, 2] == 2.
     with pytest.raises(NotImplementedError):
-        XP._setHoleInterpolatedPoints(z, depth=2, dir=2, loc='centers')
+        XP._setHoleInterpolatedPoints(z, depth=2, dir=2, loc='centers', backend=OracleBackend())
 
 
 def test_donor_tree_round_trip_on_disk(tmp_path):
