@@ -110,14 +110,18 @@ def run_c2n(args):
     # ---- end to end: host donor fields -> device, step, receptor fields -> host (tree arrays pinned in place) ----
     sess.pin_host_fields()
     ne2e = max(2, min(args.steps, 5))
-    sess.upload_donor_fields(); sess.step(); sess.download()
+    e2e_seq = os.environ.get("CX_E2E", "host") == "seq"      # A/B: the three separate calls instead of transfer_host()
+    sess.transfer_host(); sess.transfer_host()
     barrier()
     t0 = time.perf_counter()
     d2h = 0
     for _ in range(ne2e):
-        sess.upload_donor_fields()
-        sess.step()
-        d2h = sess.download()
+        if e2e_seq:
+            sess.upload_donor_fields()
+            sess.step()
+            h2d_e, d2h = sess.h2d_bytes, sess.download()
+        else:
+            h2d_e, d2h = sess.transfer_host()
     barrier()
     e2e_s = (time.perf_counter() - t0) / ne2e
     # phase breakdown of one more step (a sync after every phase; diagnostic, outside the timed region)
@@ -138,7 +142,7 @@ def run_c2n(args):
     sid_first = max(gather(sid_calls[0]))
     nrcv = sum(gather(nrcv_local))
     nccl_b = sum(gather(sess.nccl_bytes()))
-    h2d = sum(gather(sess.h2d_bytes)); d2h = sum(gather(d2h))
+    h2d = sum(gather(h2d_e)); d2h = sum(gather(d2h))
     nplans = sum(gather(len(sess.plans)))
     transport = sess.transport
     launches_all = sum(gather(launches))
@@ -171,8 +175,10 @@ def run_c2n(args):
         "e2e": {"value": B / e2e_max / 1e9, "unit": UNIT, "ms_per_step": e2e_max * 1e3,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "phases_ms_max_over_ranks": {"upload": float(e2e_ph[0]), "step": float(e2e_ph[1]), "download": float(e2e_ph[2])},
-                "api": "Connector.Mpi.TransferSession upload_donor_fields/step/download (host tree arrays pinned in "
-                       "place, copies inside the timed region)"},
+                "api": "Connector.Mpi.TransferSession.transfer_host(): host trees in, host trees out (tree arrays "
+                       "pinned in place, copies inside the timed region); the donor points the plans read go up, the "
+                       "receptor points they wrote come back, pipelined per variable over three streams (the phases are "
+                       "those of the three separate calls upload_donor_fields / step / download)"},
         "gpu_launches": int(launches_all),
         "roofline": {"bound": "hbm", "achieved": value / ngpus, "peak": peak, "unit": "GB/s per GPU",
                      "frac": value / ngpus / peak, "traffic": None, "peak_source": how,

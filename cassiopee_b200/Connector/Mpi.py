@@ -143,13 +143,16 @@ def _addXZonesDevice(aD, meta, donorLists, comm, ctx, interpDataType=1):
     requested = {n for p, lst in enumerate(allneed) if p != comm.rank for n in lst if n in localz}
     be = _lib.DeviceBackend(ctx)
     hooks = {}
-    for n in sorted(wanted | requested):
+    names = sorted(wanted | requested)
+    specs = []
+    for n in names:
         z = localz[n]
         _, ni, nj, nk, _ = Internal.getZoneDim(z)
         x, y, zz = [a.reshape(-1, order='F') for a in C.getCoords(z)]
         c = C.getFieldArray(z, 'cellN')
-        hooks[n] = be.make_zone(ni, nj, nk, x, y, zz, c.reshape(-1, order='F') if c is not None else None,
-                                interpDataType=interpDataType)
+        specs.append((ni, nj, nk, x, y, zz, c.reshape(-1, order='F') if c is not None else None, interpDataType))
+    for n, h in zip(names, be.make_zones(specs)):      # one batch: the ADT builds run concurrently on the device
+        hooks[n] = h
     mine = {}
     for n in requested:
         mi, md = hooks[n].meta()
@@ -437,6 +440,7 @@ class TransferSession:
             self.h2d_bytes += sum(a.nbytes for a in arrs)
         self._aD = aD
         self.plans = []
+        self._donorPlans = {}  # donor zone -> its plans (local and remote): what the zone has to provide per step
         items = []
         ritems = []
         remote = {}       # peer -> list of (donorName, rcvName, plan)
@@ -468,6 +472,7 @@ class TransferSession:
                 else:
                     continue
                 self.plans.append(plan)
+                self._donorPlans.setdefault(zd[0], []).append(plan)
                 info = plan.info()
                 self.alg_fixed += info['alg_fixed']; self.n_entries += info['n']; self.distinct += info['distinct']
         # one block (nvars, n_pair) per remote plan, in (donor, receptor) name order inside each peer's message.
@@ -622,7 +627,7 @@ class TransferSession:
         if getattr(self, 'transport', 'none') == 'p2p':
             self.ctx.sync()
             self.comm.barrier()                    # nobody is still storing into a peer
-            self._step = None; self._ps2 = None; self.planset_remote = None
+            self._step = None; self._ps2 = None; self.planset_remote = None; self._hostio = None
             for d in getattr(self, '_ipc_descs', []):
                 _lib.ipc_close(d)
             self._ipc_descs = []
@@ -675,7 +680,7 @@ class TransferSession:
     def upload_donor_fields(self):
         """Host tree -> device, asynchronous on the context's stream (the next step() is ordered after it)."""
         for zd in Internal.getZones(self._aD):
-            if zd[0] in self.dD:
+            if zd[0] in self.dD and zd[0] in self._donorPlans:      # a zone nobody interpolates from stays where it is
                 for d, v in zip(self.dD[zd[0]], self.variables):
                     a = C.getFieldArray(zd, v)
                     if _rawF(a):
@@ -693,6 +698,46 @@ class TransferSession:
         """niter iterations (asynchronous): remote plans -> NCCL exchange + scatter on the
         communication stream, overlapped with the local in-place plans."""
         self._step.run(niter, overlap)
+
+    def _setup_hostio(self):
+        """The copies of transfer_host(): per donor zone the points its plans read (whole fields when that is more than
+        half the zone), per receptor zone the points the step writes (the sparse-download lists)."""
+        nv = len(self.variables)
+        io = _lib.HostIO(self.ctx, nv)
+        for zd in Internal.getZones(self._aD):
+            plans = self._donorPlans.get(zd[0])
+            if not plans or zd[0] not in self.dD:
+                continue
+            arrs = [C.getFieldArray(zd, v) for v in self.variables]
+            if not all(_rawF(a) for a in arrs):
+                return None
+            npts = arrs[0].size
+            idx = None
+            if os.environ.get("CX_SPARSE_H2D", "1") != "0":
+                idx = numpy.flatnonzero(_lib.plan_donor_mask(self.ctx, plans, npts)).astype(numpy.int32)
+                if 2 * idx.size >= npts:
+                    idx = None
+            io.add('up', arrs, [d.ptr for d in self.dD[zd[0]]], idx)
+        for name, arrs in self.hR.items():
+            if not all(_rawF(a) for a in arrs):
+                return None
+            sp = self._sparse.get(name)
+            io.add('down', arrs, [d.ptr for d in self.dR[name]], sp['idx'] if sp is not None else None)
+        return io
+
+    def transfer_host(self, pipelined=True):
+        """One iteration, host trees in and host trees out: the donor values the plans read go up, the plans and the
+        exchange run, the receptor values they wrote come back into the tree's arrays (what a call of the reference's
+        Xmpi.__setInterpTransfers + C._setPartialFields does).  Pipelined per variable over three streams (peer-memory
+        transport or a single rank), so uploads, kernels and downloads overlap.  Collective: every rank calls it.
+        Returns (bytes up, bytes down)."""
+        if getattr(self, '_hostio', None) is None:
+            self._hostio = self._setup_hostio() or False
+        if self._hostio is False:           # some field is not a Fortran-flat float64 array: plain sequence
+            self.upload_donor_fields(); self.step(); nb = self.download()
+            return self.h2d_bytes, nb
+        self._step.run_host(self._hostio, pipelined)
+        return self._hostio.bytes()
 
     def download(self):
         """Copy the receptor fields back into the host tree (in place); returns the bytes moved."""

@@ -377,106 +377,132 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
         if ty not in (0, 1):
             raise TypeError("setInterpData: InterpDataType must be 0 for CART or 1 for ADT.")
 
-    def hookOf(i):
-        if allHooksL[i] is None:
-            zd = zonesDnrL[i]
-            _, ni_, nj_, nk_, _ = Internal.getZoneDim(zd)
-            xd, yd, zzd = [a.reshape(-1, order='F') for a in C.getCoords(zd)]
-            cd = C.getFieldArray(zd, 'cellN')
-            cdf = cd.reshape(-1, order='F') if cd is not None else None
-            if typesL[i] == 0:
-                allHooksL[i] = backend.make_zone(ni_, nj_, nk_, xd, yd, zzd, cdf, interpDataType=0)
-            else:
-                allHooksL[i] = backend.make_zone(ni_, nj_, nk_, xd, yd, zzd, cdf)
-        return allHooksL[i]
+    def hookArgs(i):
+        zd = zonesDnrL[i]
+        _, ni_, nj_, nk_, _ = Internal.getZoneDim(zd)
+        xd, yd, zzd = [a.reshape(-1, order='F') for a in C.getCoords(zd)]
+        cd = C.getFieldArray(zd, 'cellN')
+        cdf = cd.reshape(-1, order='F') if cd is not None else None
+        return (ni_, nj_, nk_, xd, yd, zzd, cdf, typesL[i])
+
+    def makeHooks(ids):
+        """The hooks not built yet among `ids`, all at once (the device builds the ADTs of a batch of zones
+        concurrently)."""
+        todo = [i for i in ids if allHooksL[i] is None]
+        if todo:
+            for i, h in zip(todo, backend.make_zones([hookArgs(i) for i in todo])):
+                allHooksL[i] = h
 
     import os as _os, time as _time
     _prof = _os.environ.get("CX_PROFILE")
     _tt = dict(hooks=0., pts=0., search=0., store=0.)
-    try:
-        for z in zonesRcv:
-            _t0 = _time.perf_counter()
-            cellNPresent = C.isNamePresent(z, 'cellN' if loc == 'nodes' else 'centers:cellN')
-            if cellNPresent == -1:
-                continue
-            idx = list(range(len(zonesDnrL)))
-            if sameName == 1:
-                for cL, zo in enumerate(zonesDnrL):
-                    if zo[0] == z[0]:
-                        idx.pop(cL)
-                        break
-            if donorLists is not None and z[0] in donorLists:
-                names = donorLists[z[0]]
-                byname = {zonesDnrL[i][0]: i for i in idx}
-                idx = [byname[n] for n in names if n in byname]
-            zonesDnr = [zonesDnrL[i] for i in idx]
-            nzonesDnr = len(zonesDnr)
 
-            # Etape 1: points to interpolate (cellN == 2): getInterpolatedPoints keeps the points with
-            # |cellN-2| <= 1e-15 in source order and records their index ('indcell'); for loc='centers' the
-            # centre coordinates (node2Center formula) are only evaluated for those cells.  Done by the backend
-            # (on the device: cx_receptors_create), which keeps the coordinates resident for the search.
-            x, y, zc = C.getCoords(z)
-            cellN = C.getFieldArray(z, 'cellN' if locR == 'nodes' else 'centers:cellN')
-            _, ni_r, nj_r, nk_r, _ = Internal.getZoneDim(z)
-            rcvPts = backend.select_receptors(ni_r, nj_r, nk_r, x.reshape(-1, order='F'), y.reshape(-1, order='F'),
-                                              zc.reshape(-1, order='F'), cellN.reshape(-1, order='F'), locR)
-            sel = rcvPts.indcell
-            if nzonesDnr == 0:
-                if sel.size > 0:
-                    raise TypeError("setInterpData: no valid donor zone found.")
-                continue
-
-            # Etape 2: interpolation data on the device
-            if sel.size == 0:
-                continue
-            _t1 = _time.perf_counter()
-            hooks_ = [hookOf(i) for i in idx]
-            _t2 = _time.perf_counter()
-            resInterp = backend.set_interp_data_rcv(rcvPts, hooks_, order, nature, penalty, extrap)
-            _t3 = _time.perf_counter()
-            _tt['pts'] += _t1 - _t0; _tt['hooks'] += _t2 - _t1; _tt['search'] += _t3 - _t2
-            nbinterpolated = sel.size
-            nbextrapolated = sum(r.shape[0] for r in resInterp[4])
-            nborphan = resInterp[5].size
-            nbinterpolated = nbinterpolated - nbextrapolated - nborphan
-            if verbose != 0:
-                print('Zone %s: interpolated=%d ; extrapolated=%d ; orphan=%d' % (z[0], nbinterpolated, nbextrapolated, nborphan))
-                if nborphan > 0: print('Warning: zone %s has %d orphan points !' % (z[0], nborphan))
-            # local position -> index in the receptor zone (indcell), vectorised
-            indcells = sel.astype(Internal.E_NpyInt)
-            if nborphan > 0:
-                resInterp[5] = indcells[resInterp[5]]
-                if verbose == 3:     # force cellN#Orphan = -1 at the orphan points (OversetData.py:1287-1294)
+    def finishZone(z, zonesDnr, sel, cellN, pending):
+        """Etape 2 (end) and 3 for one receptor zone: fetch the lists of its search, index remap, storage."""
+        _t2 = _time.perf_counter()
+        resInterp = pending.fetch()
+        _t3 = _time.perf_counter()
+        _tt['search'] += _t3 - _t2
+        nzonesDnr = len(zonesDnr)
+        nbinterpolated = sel.size
+        nbextrapolated = sum(r.shape[0] for r in resInterp[4])
+        nborphan = resInterp[5].size
+        nbinterpolated = nbinterpolated - nbextrapolated - nborphan
+        if verbose != 0:
+            print('Zone %s: interpolated=%d ; extrapolated=%d ; orphan=%d' % (z[0], nbinterpolated, nbextrapolated, nborphan))
+            if nborphan > 0: print('Warning: zone %s has %d orphan points !' % (z[0], nborphan))
+        # local position -> index in the receptor zone (indcell), vectorised
+        indcells = sel.astype(Internal.E_NpyInt)
+        if nborphan > 0:
+            resInterp[5] = indcells[resInterp[5]]
+            if verbose == 3:     # force cellN#Orphan = -1 at the orphan points (OversetData.py:1287-1294)
+                pre = 'centers:' if locR == 'centers' else ''
+                if Internal.getNodeFromName2(z, 'cellN#Orphan') is None:
+                    C._initVars(z, pre + 'cellN#Orphan', numpy.array(cellN, dtype=numpy.float64, order='F', copy=True))
+                co = C.getFieldArray(z, pre + 'cellN#Orphan')
+                co.reshape(-1, order='F')[resInterp[5]] = -1.
+        for noz in range(nzonesDnr):
+            if resInterp[0][noz].size > 0:
+                resInterp[0][noz] = indcells[resInterp[0][noz]]
+            if resInterp[4][noz].size > 0:
+                resInterp[4][noz] = indcells[resInterp[4][noz]]
+                if verbose == 3:     # force cellN#Orphan = -2 at the extrapolated points (OversetData.py:1313-1319)
                     pre = 'centers:' if locR == 'centers' else ''
                     if Internal.getNodeFromName2(z, 'cellN#Orphan') is None:
                         C._initVars(z, pre + 'cellN#Orphan', numpy.array(cellN, dtype=numpy.float64, order='F', copy=True))
-                    co = C.getFieldArray(z, pre + 'cellN#Orphan')
-                    co.reshape(-1, order='F')[resInterp[5]] = -1.
-            for noz in range(nzonesDnr):
-                if resInterp[0][noz].size > 0:
-                    resInterp[0][noz] = indcells[resInterp[0][noz]]
-                if resInterp[4][noz].size > 0:
-                    resInterp[4][noz] = indcells[resInterp[4][noz]]
-                    if verbose == 3:     # force cellN#Orphan = -2 at the extrapolated points (OversetData.py:1313-1319)
-                        pre = 'centers:' if locR == 'centers' else ''
-                        if Internal.getNodeFromName2(z, 'cellN#Orphan') is None:
-                            C._initVars(z, pre + 'cellN#Orphan', numpy.array(cellN, dtype=numpy.float64, order='F', copy=True))
-                        C.getFieldArray(z, pre + 'cellN#Orphan').reshape(-1, order='F')[resInterp[4][noz]] = -2.
+                    C.getFieldArray(z, pre + 'cellN#Orphan').reshape(-1, order='F')[resInterp[4][noz]] = -2.
 
-            # Etape 3: storage in the tree
-            for noz in range(nzonesDnr):
-                if resInterp[0][noz].size > 0:
-                    extrapPts = resInterp[4][noz] if resInterp[4][noz].size > 0 else numpy.array([], dtype=Internal.E_NpyInt)
-                    if storage == 'direct':
-                        _createInterpRegion__(z, zonesDnr[noz][0], resInterp[0][noz], resInterp[1][noz],
-                                              resInterp[3][noz], resInterp[2][noz], numpy.array([], numpy.float64),
-                                              extrapPts, resInterp[5], tag='Receiver', loc=locR)
-                    else:
-                        _createInterpRegion__(zonesDnr[noz], z[0], resInterp[1][noz], resInterp[0][noz],
-                                              resInterp[3][noz], resInterp[2][noz], numpy.array([], numpy.float64),
-                                              extrapPts, resInterp[5], tag='Donor', loc=locR)
-            _tt['store'] += _time.perf_counter() - _t3
+        # Etape 3: storage in the tree
+        for noz in range(nzonesDnr):
+            if resInterp[0][noz].size > 0:
+                extrapPts = resInterp[4][noz] if resInterp[4][noz].size > 0 else numpy.array([], dtype=Internal.E_NpyInt)
+                if storage == 'direct':
+                    _createInterpRegion__(z, zonesDnr[noz][0], resInterp[0][noz], resInterp[1][noz],
+                                          resInterp[3][noz], resInterp[2][noz], numpy.array([], numpy.float64),
+                                          extrapPts, resInterp[5], tag='Receiver', loc=locR)
+                else:
+                    _createInterpRegion__(zonesDnr[noz], z[0], resInterp[1][noz], resInterp[0][noz],
+                                          resInterp[3][noz], resInterp[2][noz], numpy.array([], numpy.float64),
+                                          extrapPts, resInterp[5], tag='Donor', loc=locR)
+        _tt['store'] += _time.perf_counter() - _t3
+
+    # The receptor zones go through in windows: Etape 1 (receptor points) of every zone of the window, then the hooks
+    # the window needs in one batch, then every search is queued on the device without waiting for the previous one,
+    # then the lists are fetched and stored zone after zone in the reference's order.  A window closes at
+    # _WINDOW_PTS receptor points in flight (the per-receptor tables of a search stay on the device until its fetch).
+    _WINDOW_PTS = 48 * 1000 * 1000
+    try:
+        pos = 0
+        while pos < len(zonesRcv):
+            jobs = []; inflight = 0
+            while pos < len(zonesRcv) and (not jobs or inflight < _WINDOW_PTS):
+                z = zonesRcv[pos]; pos += 1
+                _t0 = _time.perf_counter()
+                cellNPresent = C.isNamePresent(z, 'cellN' if loc == 'nodes' else 'centers:cellN')
+                if cellNPresent == -1:
+                    continue
+                idx = list(range(len(zonesDnrL)))
+                if sameName == 1:
+                    for cL, zo in enumerate(zonesDnrL):
+                        if zo[0] == z[0]:
+                            idx.pop(cL)
+                            break
+                if donorLists is not None and z[0] in donorLists:
+                    names = donorLists[z[0]]
+                    byname = {zonesDnrL[i][0]: i for i in idx}
+                    idx = [byname[n] for n in names if n in byname]
+                zonesDnr = [zonesDnrL[i] for i in idx]
+
+                # Etape 1: points to interpolate (cellN == 2): getInterpolatedPoints keeps the points with
+                # |cellN-2| <= 1e-15 in source order and records their index ('indcell'); for loc='centers' the
+                # centre coordinates (node2Center formula) are only evaluated for those cells.  Done by the backend
+                # (on the device: cx_receptors_create), which keeps the coordinates resident for the search.
+                x, y, zc = C.getCoords(z)
+                cellN = C.getFieldArray(z, 'cellN' if locR == 'nodes' else 'centers:cellN')
+                _, ni_r, nj_r, nk_r, _ = Internal.getZoneDim(z)
+                rcvPts = backend.select_receptors(ni_r, nj_r, nk_r, x.reshape(-1, order='F'), y.reshape(-1, order='F'),
+                                                  zc.reshape(-1, order='F'), cellN.reshape(-1, order='F'), locR)
+                sel = rcvPts.indcell
+                _tt['pts'] += _time.perf_counter() - _t0
+                if len(zonesDnr) == 0:
+                    if sel.size > 0:
+                        raise TypeError("setInterpData: no valid donor zone found.")
+                    continue
+                if sel.size == 0:
+                    continue
+                jobs.append((z, zonesDnr, idx, rcvPts, sel, cellN))
+                inflight += sel.size
+            # Etape 2: interpolation data on the device
+            _t1 = _time.perf_counter()
+            makeHooks(sorted(set(i for job in jobs for i in job[2])))
+            _t2 = _time.perf_counter()
+            _tt['hooks'] += _t2 - _t1
+            pend = [backend.submit_interp_data_rcv(rcvPts, [allHooksL[i] for i in idx], order, nature, penalty, extrap)
+                    for (z, zonesDnr, idx, rcvPts, sel, cellN) in jobs]
+            _tt['search'] += _time.perf_counter() - _t2
+            for (z, zonesDnr, idx, rcvPts, sel, cellN), pending in zip(jobs, pend):
+                finishZone(z, zonesDnr, sel, cellN, pending)
+            del jobs, pend
     finally:
         if _prof:
             print("[_setInterpDataChimera] receptor extraction %.3fs, donor hooks (upload+ADT) %.3fs, search+fetch %.3fs, "

@@ -43,6 +43,8 @@ _SIGS = {
     "cx_pinned_alloc": (_i, [_sz, _vp]),
     "cx_pinned_free": (_i, [_vp]),
     "cx_zone_create": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "cx_zone_create_noadt": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "cx_zones_build_adt": (_i, [_vp, _i, _vp]),
     "cx_zone_create_cart": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "cx_zone_set_celln": (_i, [_vp, _vp]),
     "cx_zone_info": (_i, [_vp, _vp, _vp, _vp, _vp]),
@@ -56,9 +58,11 @@ _SIGS = {
     "cx_receptors_fetch": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "cx_receptors_destroy": (_i, [_vp]),
     "cx_set_interp_data_rcv": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
+    "cx_ctx_search_slot": (_i, [_vp, _i]),
     "cx_result_sizes": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "cx_result_fetch_zone": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "cx_result_fetch_orphans": (_i, [_vp, _vp]),
+    "cx_result_fetch_all": (_i, [_vp] * 7),
     "cx_result_fetch_raw": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "cx_result_stats": (_i, [_vp, _vp]),
     "cx_result_destroy": (_i, [_vp]),
@@ -97,6 +101,15 @@ _SIGS = {
     "cx_step_create": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cx_step_create_p2p": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "cx_step_run": (_i, [_vp, _i, _i]),
+    "cx_step_run_vars": (_i, [_vp, _i, _i, _i, _i]),
+    "cx_step_splittable": (_i, [_vp]),
+    "cx_hostio_create": (_i, [_vp, _i, _vp]),
+    "cx_hostio_add": (_i, [_vp, _i, _ll, _vp, _vp, _vp]),
+    "cx_hostio_bytes": (_i, [_vp, _vp, _vp]),
+    "cx_step_run_host": (_i, [_vp, _vp, _i]),
+    "cx_hostio_destroy": (_i, [_vp]),
+    "cx_plan_mark_donors": (_i, [_vp, _vp]),
+    "cx_host_gather": (_i, [_vp, _vp, _vp, _ll]),
     "cx_step_destroy": (_i, [_vp]),
     "cx_comm_unique_id": (_i, [_vp]),
     "cx_comm_init": (_i, [_vp, _i, _i, _vp]),
@@ -286,9 +299,10 @@ class Zone:
     """Donor zone resident on the device with its ADT replica (cx_zone) — the
     analogue of the reference's ``C.createHook(z, 'adt')``."""
 
-    def __init__(self, ctx, ni, nj, nk, x, y, z, cellN=None, interpDataType=1):
+    def __init__(self, ctx, ni, nj, nk, x, y, z, cellN=None, interpDataType=1, defer_adt=False):
         """interpDataType 1: ADT replica (InterpAdt); 0: regular Cartesian donor located in closed form
-        (InterpCart, setInterpData.cpp:790-804) — no tree is built."""
+        (InterpCart, setInterpData.cpp:790-804) — no tree is built.  defer_adt: the tree is built later, with those of
+        the other zones of a batch (build_adts)."""
         self.ctx = ctx
         self.ni, self.nj, self.nk = int(ni), int(nj), int(nk)
         self.interpDataType = int(interpDataType)
@@ -300,7 +314,8 @@ class Zone:
             raise TypeError("setInterpData: InterpDataType must be 0 for CART or 1 for ADT.")
         c = f64(cellN) if cellN is not None else None
         h = _vp()
-        create = lib().cx_zone_create if self.interpDataType == 1 else lib().cx_zone_create_cart
+        create = lib().cx_zone_create_cart if self.interpDataType == 0 else (
+            lib().cx_zone_create_noadt if defer_adt else lib().cx_zone_create)
         check(create(ctx.h, self.ni, self.nj, self.nk, ptr(x), ptr(y), ptr(z), ptr(c), ctypes.byref(h)))
         self.h = h
         self._fin = weakref.finalize(self, lib().cx_zone_destroy, h)
@@ -347,6 +362,14 @@ class Zone:
         return out
 
 
+def build_adts(ctx, zones):
+    """ADTs of the zones created with defer_adt=True, built concurrently on the device (cx_zones_build_adt)."""
+    if not zones:
+        return
+    hs = (ctypes.c_void_p * len(zones))(*[z.h.value for z in zones])
+    check(lib().cx_zones_build_adt(ctx.h, len(zones), hs))
+
+
 def zone_exchange(ctx, sends, recvs):
     """Device-to-device replication of donor zones over NCCL (cx_zone_exchange).
     sends: list of (Zone, peer); recvs: list of (peer, meta_i, meta_d) with the owner's Zone.meta().
@@ -385,16 +408,21 @@ class InterpResult:
         (Connector/Connector/setInterpData.cpp:1272).  pinned=True returns numpy arrays backed by
         page-locked memory from the reuse pool (fast D2H, no first-touch page faults)."""
         cnt, nco, nex, no = self.sizes()
-        R, D, T, C, E = [], [], [], [], []
         big = 1 << 16
         mk = (lambda n, dt: pinned_empty(n, dt) if (pinned and n >= big) else np.empty(n, dt))
-        for z in range(self.nz):
-            r = mk(cnt[z], np.int32); d = mk(cnt[z], np.int32); t = mk(cnt[z], np.int32)
-            c = mk(nco[z], np.float64); e = np.empty(nex[z], np.int32)
-            check(lib().cx_result_fetch_zone(self.h, z, ptr(r), ptr(d), ptr(t), ptr(c), ptr(e)))
-            R.append(r); D.append(d); T.append(t); C.append(c); E.append(e)
-        orphan = np.empty(no, np.int32)
-        check(lib().cx_result_fetch_orphans(self.h, ptr(orphan)))
+        ne, nc, nx = int(cnt.sum()), int(nco.sum()), int(nex.sum())
+        # one block per kind of list for the whole call (six copies instead of five per donor zone); the per-zone
+        # lists are consecutive slices of them
+        r = mk(ne, np.int32); d = mk(ne, np.int32); t = mk(ne, np.int32); c = mk(nc, np.float64)
+        e = np.empty(nx, np.int32); orphan = np.empty(no, np.int32)
+        check(lib().cx_result_fetch_all(self.h, ptr(r), ptr(d), ptr(t), ptr(c), ptr(e), ptr(orphan)))
+        eo = np.concatenate(([0], np.cumsum(cnt))); co = np.concatenate(([0], np.cumsum(nco)))
+        xo = np.concatenate(([0], np.cumsum(nex)))
+        R = [r[eo[z]:eo[z + 1]] for z in range(self.nz)]
+        D = [d[eo[z]:eo[z + 1]] for z in range(self.nz)]
+        T = [t[eo[z]:eo[z + 1]] for z in range(self.nz)]
+        C = [c[co[z]:co[z + 1]] for z in range(self.nz)]
+        E = [e[xo[z]:xo[z + 1]] for z in range(self.nz)]
         return [R, D, T, C, E, orphan, []]
 
     def raw(self):
@@ -596,6 +624,47 @@ def host_scatter(dst, idx, src):
     check(lib().cx_host_scatter(ptr(dst), ptr(idx), ptr(src), int(idx.size)))
 
 
+class HostIO:
+    """The copies of a host-to-host step (cx_hostio): per zone and direction, whole fields or listed points only."""
+
+    def __init__(self, ctx, nvars):
+        self.ctx = ctx
+        self.nvars = int(nvars)
+        h = _vp()
+        check(lib().cx_hostio_create(ctx.h, self.nvars, ctypes.byref(h)))
+        self.h = h
+        self._keep = []
+        self._fin = weakref.finalize(self, lib().cx_hostio_destroy, h)
+
+    def add(self, direction, host_arrays, dev_ptrs, idx=None):
+        """direction 'up' | 'down'; host_arrays: nvars Fortran-flat float64 arrays (kept alive here); idx: int32 points
+        to move (None: the whole arrays)."""
+        assert len(host_arrays) == self.nvars and len(dev_ptrs) == self.nvars
+        for a in host_arrays:
+            if a.dtype != np.float64 or not (a.flags.f_contiguous or a.ndim == 1):
+                raise TypeError("HostIO: fields must be Fortran-flat float64 arrays")
+        n = int(idx.size) if idx is not None else int(host_arrays[0].size)
+        if idx is not None:
+            idx = np.ascontiguousarray(idx, dtype=np.int32)
+        self._keep.append(list(host_arrays))
+        check(lib().cx_hostio_add(self.h, 0 if direction == 'up' else 1, n, ptr(idx) if idx is not None else None,
+                                  ptr_array([a.ctypes.data for a in host_arrays]), ptr_array(list(dev_ptrs))))
+
+    def bytes(self):
+        a = _ll(); b = _ll()
+        check(lib().cx_hostio_bytes(self.h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+
+def plan_donor_mask(ctx, plans, nptsD):
+    """uint8 mask (host) of the donor points read by `plans` (all of one donor zone of nptsD points)."""
+    d = DeviceArray(ctx, nptsD, np.uint8)
+    ctx.upload(d.ptr, np.zeros(nptsD, np.uint8))
+    for p in plans:
+        check(lib().cx_plan_mark_donors(p.h, _vp(d.ptr)))
+    return d.download()
+
+
 def host_register(a):
     """Page-lock a contiguous numpy array in place (cudaHostRegister); returns True if this call pinned it."""
     rc = lib().cx_host_register(ptr(a), a.nbytes)
@@ -720,6 +789,14 @@ class ScatterSet:
         check(lib().cx_scatterset_run(self.h))
 
 
+class _Pending:
+    def __init__(self, f):
+        self._f = f
+
+    def fetch(self):
+        return self._f()
+
+
 class DeviceBackend:
     """Compute backend of the Python layer = the CUDA library.  (The distributed
     host logic takes a backend object so the CPU tests can inject the oracle;
@@ -730,6 +807,13 @@ class DeviceBackend:
 
     def make_zone(self, ni, nj, nk, x, y, z, cellN=None, interpDataType=1):
         return Zone(self.ctx, ni, nj, nk, x, y, z, cellN, interpDataType)
+
+    def make_zones(self, specs):
+        """Hooks of several donor zones, specs = [(ni, nj, nk, x, y, z, cellN, interpDataType)]: the uploads run zone
+        after zone, the ADT builds of the whole batch run concurrently on the device (cx_zones_build_adt)."""
+        zones = [Zone(self.ctx, *sp[:7], interpDataType=sp[7], defer_adt=True) for sp in specs]
+        build_adts(self.ctx, zones)
+        return zones
 
     def set_celln(self, hook, cellN):
         hook.set_celln(cellN)
@@ -745,6 +829,17 @@ class DeviceBackend:
     def set_interp_data_rcv(self, rcv, hooks, order, nature, penalty, extrap):
         # large lists land in page-locked arrays of the reuse pool (they become the tree's numpy arrays)
         return set_interp_data_rcv(self.ctx, rcv, hooks, order, nature, penalty, extrap).fetch(pinned=True)
+
+    def submit_interp_data_rcv(self, rcv, hooks, order, nature, penalty, extrap):
+        """Queue the search of one receptor zone on the device and return at once; .fetch() of the returned object
+        waits for it and gives the lists."""
+        self._slot = getattr(self, '_slot', 0) % 8 + 1          # round robin over the side streams
+        check(lib().cx_ctx_search_slot(self.ctx.h, self._slot))
+        try:
+            res = set_interp_data_rcv(self.ctx, rcv, hooks, order, nature, penalty, extrap)
+        finally:
+            check(lib().cx_ctx_search_slot(self.ctx.h, 0))
+        return _Pending(lambda: res.fetch(pinned=True))
 
     def make_plan(self, imd, jmd, kmd, nptsR, donor, rcv, typ, coefs):
         return Plan(self.ctx, imd, jmd, kmd, nptsR, donor, rcv, typ, coefs)
@@ -792,6 +887,12 @@ class StepP2P:
     def run(self, niter=1, overlap=True):
         check(lib().cx_step_run(self.h, int(niter), 1 if overlap else 0))
 
+    def run_host(self, io, pipelined=True):
+        check(lib().cx_step_run_host(self.h, io.h, 1 if pipelined else 0))
+
+    def run_host(self, io, pipelined=True):
+        check(lib().cx_step_run_host(self.h, io.h, 1 if pipelined else 0))
+
 
 class Step:
     """One iteration of a rank (cx_step): remote plans -> NCCL exchange + scatter (second
@@ -812,3 +913,6 @@ class Step:
 
     def run(self, niter=1, overlap=True):
         check(lib().cx_step_run(self.h, int(niter), 1 if overlap else 0))
+
+    def run_host(self, io, pipelined=True):
+        check(lib().cx_step_run_host(self.h, io.h, 1 if pipelined else 0))

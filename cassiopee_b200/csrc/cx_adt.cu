@@ -152,57 +152,74 @@ void cx_zone_bbox_host(int ni, int nj, int nk, const double* x, const double* y,
   bb[0] = mn[0]; bb[1] = mn[1]; bb[2] = mn[2]; bb[3] = mx[0]; bb[4] = mx[1]; bb[5] = mx[2];
 }
 
-int cx_build_adt(cx_zone* z)
-{
-  cx_ctx* ctx = z->ctx;
-  cudaStream_t s = ctx->stream;
-  const int ncells = z->ncells;
-  const size_t n = ncells;
+// One zone's build as a small state machine, so that the builds of several zones can be interleaved by the host and
+// overlap on the device (each on its own stream): begin -> { enqueue_batch -> finish_batch } until done -> subtree -> end.
+// A 10^6-cell zone is ~100 dependent launches of ~20 us: alone it leaves the GPU idle most of the time.
+namespace {
+struct AdtBuild {
+  cx_zone* z; cx_ctx* ctx; cudaStream_t s;
   BuildView B; BuildScratch S;
-  CX_MALLOC(z->d_nodes, sizeof(AdtNode) * n, s);
-  B.nodes = z->d_nodes; B.ncells = ncells;
-  CX_MALLOC(B.keys, sizeof(double) * 6 * n, s);
-  CX_MALLOC(B.lo, sizeof(double) * 6 * n, s);
-  CX_MALLOC(B.hi, sizeof(double) * 6 * n, s);
-  CX_MALLOC(B.cur, sizeof(int) * n, s);
-  CX_MALLOC(B.br, n, s);
-  CX_MALLOC(B.depth, sizeof(int) * n, s);
-  CX_CUDA(cudaMemsetAsync(B.depth, 0, sizeof(int) * n, s));
-  CX_MALLOC(S.actA, sizeof(int) * n, s);
-  CX_MALLOC(S.actB, sizeof(int) * n, s);
-  int *d_placed, *d_pcnt;
-  CX_MALLOC(d_placed, sizeof(int) * n, s);
-  ZoneBox zb;
-  for (int d = 0; d < 6; d++) { zb.lo[d] = z->bbox[d % 3]; zb.hi[d] = z->bbox[3 + d % 3]; }
-  B.zb = zb;
+  int *d_placed, *d_pcnt, *d_cnt;
+  int* h_cnt; int h_own;                 // page-locked: the active counts of a batch of levels
+  int *act, *next;
+  int nact, n0, L, depth, nb;
+  std::vector<int> cntAll;               // cntAll[L] = active cells at the start of level L
+  cudaEvent_t ev0, ev1;
+  bool done;
+  static constexpr int BATCH = 8, MAXL = 4096, TB = 256;
 
-  CX_CUDA(cudaEventRecord(ctx->ev0, s));
-  const int TB = 256;
-  k_cell_keys<<<cx_grid(n, TB), TB, 0, s>>>(z->ni, z->nj, z->nk, z->d_x, z->d_y, z->d_z, B.keys, z->d_nodes, ncells,
-                                            zb, z->bbox[2], z->bbox[5]);
-  k_root<<<1, 1, 0, s>>>(z->d_nodes, zb);
-  ctx->launches += 2;
-  int nact = ncells - 1;
-  if (nact > 0) { k_init_active<<<cx_grid(nact, TB), TB, 0, s>>>(S.actA, B.cur, nact); ctx->launches++; }
-  int* act = S.actA; int* next = S.actB;
-  int L = 0, depth = 0;
+  int begin(cx_zone* zone, cudaStream_t stream)
+  {
+    z = zone; ctx = z->ctx; s = stream; done = false; h_cnt = nullptr; ev0 = ev1 = nullptr;
+    const int ncells = z->ncells;
+    const size_t n = ncells;
+    CX_MALLOC(z->d_nodes, sizeof(AdtNode) * n, s);
+    B.nodes = z->d_nodes; B.ncells = ncells;
+    CX_MALLOC(B.keys, sizeof(double) * 6 * n, s);
+    CX_MALLOC(B.lo, sizeof(double) * 6 * n, s);
+    CX_MALLOC(B.hi, sizeof(double) * 6 * n, s);
+    CX_MALLOC(B.cur, sizeof(int) * n, s);
+    CX_MALLOC(B.br, n, s);
+    CX_MALLOC(B.depth, sizeof(int) * n, s);
+    CX_CUDA(cudaMemsetAsync(B.depth, 0, sizeof(int) * n, s));
+    CX_MALLOC(S.actA, sizeof(int) * n, s);
+    CX_MALLOC(S.actB, sizeof(int) * n, s);
+    CX_MALLOC(d_placed, sizeof(int) * n, s);
+    ZoneBox zb;
+    for (int d = 0; d < 6; d++) { zb.lo[d] = z->bbox[d % 3]; zb.hi[d] = z->bbox[3 + d % 3]; }
+    B.zb = zb;
+    CX_CUDA(cudaEventCreate(&ev0)); CX_CUDA(cudaEventCreate(&ev1));
+    CX_CUDA(cudaEventRecord(ev0, s));
+    k_cell_keys<<<cx_grid(n, TB), TB, 0, s>>>(z->ni, z->nj, z->nk, z->d_x, z->d_y, z->d_z, B.keys, z->d_nodes, ncells,
+                                              zb, z->bbox[2], z->bbox[5]);
+    k_root<<<1, 1, 0, s>>>(z->d_nodes, zb);
+    ctx->launches += 2;
+    nact = ncells - 1;
+    if (nact > 0) { k_init_active<<<cx_grid(nact, TB), TB, 0, s>>>(S.actA, B.cur, nact); ctx->launches++; }
+    act = S.actA; next = S.actB;
+    L = 0; depth = 0;
+    CX_MALLOC(d_cnt, sizeof(int) * (MAXL + BATCH + 2), s);
+    CX_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (MAXL + BATCH + 2), s));
+    h_cnt = (int*)cx_pin_take(ctx, sizeof(int) * (BATCH + 2), &h_own);
+    if (!h_cnt) { cx_set_error("ADT build: no page-locked memory"); return -2; }
+    h_cnt[0] = nact;
+    CX_CUDA(cudaMemcpyAsync(d_cnt, h_cnt, sizeof(int), cudaMemcpyHostToDevice, s));
+    CX_MALLOC(d_pcnt, sizeof(int) * (MAXL + BATCH + 2), s);
+    CX_CUDA(cudaMemsetAsync(d_pcnt, 0, sizeof(int) * (MAXL + BATCH + 2), s));
+    n0 = nact;                        // cells to place below the root
+    cntAll.assign(1, nact);
+    if (nact <= 0) done = true;
+    return 0;
+  }
+
   // small zones: levels run in batches of 8 without a host round trip (the per-level synchronisation costs as
   // much as the level's kernels: 941 192 cells 2.2 ms); large zones keep one level per round trip, so that no
   // kernel is launched over a stale, too large active count (16.6 M cells: 39.2 ms, batched 41.9 ms)
-  const int BATCH = 8, MAXL = 4096;
-  int* d_cnt;
-  CX_MALLOC(d_cnt, sizeof(int) * (MAXL + BATCH + 2), s);
-  CX_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (MAXL + BATCH + 2), s));
-  CX_CUDA(cudaMemcpyAsync(d_cnt, &nact, sizeof(int), cudaMemcpyHostToDevice, s));
-  CX_MALLOC(d_pcnt, sizeof(int) * (MAXL + BATCH + 2), s);
-  CX_CUDA(cudaMemsetAsync(d_pcnt, 0, sizeof(int) * (MAXL + BATCH + 2), s));
-  const int n0 = nact;                        // cells to place below the root
-  std::vector<int> cntAll(1, nact);           // cntAll[L] = active cells at the start of level L
-  int h_cnt[BATCH + 1];
-  while (nact > 0)
+  int enqueue_batch()
   {
+    if (done) return 0;
     const int grid = cx_grid(nact, TB);
-    const int nb = nact > (1 << 21) ? 1 : BATCH;
+    nb = nact > (1 << 21) ? 1 : BATCH;
     for (int q = 0; q < nb; q++)
     {
       k_claim<<<grid, TB, 0, s>>>(L + q, q == 0 ? nact : -1, d_cnt, act, B);
@@ -211,6 +228,12 @@ int cx_build_adt(cx_zone* z)
       int* t = act; act = next; next = t;
     }
     CX_CUDA(cudaMemcpyAsync(h_cnt, d_cnt + L, sizeof(int) * (nb + 1), cudaMemcpyDeviceToHost, s));
+    return 0;
+  }
+
+  int finish_batch()
+  {
+    if (done) return 0;
     CX_CUDA(cudaStreamSynchronize(s));
     int used = nb;
     for (int q = 0; q < nb; q++)
@@ -220,32 +243,93 @@ int cx_build_adt(cx_zone* z)
     }
     for (int q = 1; q <= used; q++) cntAll.push_back(h_cnt[q]);
     nact = h_cnt[used];
+    // an odd number of levels used out of the batch: act/next were swapped nb times, the live list is `used` swaps in
+    if ((nb - used) & 1) { int* t = act; act = next; next = t; }
     L += used;
-    if (L > MAXL) { cx_set_error("ADT deeper than 4096 levels (degenerate/duplicate cells)"); cudaFreeAsync(d_cnt, s); return -3; }
+    if (L > MAXL) { cx_set_error("ADT deeper than 4096 levels (degenerate/duplicate cells)"); return -3; }
+    if (nact <= 0) done = true;
+    return 0;
   }
-  cudaFreeAsync(d_cnt, s); cudaFreeAsync(d_pcnt, s);
+
   // subtree bounding boxes, deepest level first: the cells of depth d were placed during level d - 1 and sit at
   // placed[n0 - cntAll[d-1] .. n0 - cntAll[d]); depth 0 is the root
-  for (int lv = depth - 1; lv >= 1; lv--)
+  int subtree()
   {
-    const int first = n0 - cntAll[lv - 1], count = cntAll[lv - 1] - cntAll[lv];
-    if (count <= 0) continue;
-    k_subtree<<<cx_grid(count, TB), TB, 0, s>>>(count, d_placed + first, z->d_nodes);
-    ctx->launches++;
+    cudaFreeAsync(d_cnt, s); cudaFreeAsync(d_pcnt, s);
+    for (int lv = depth - 1; lv >= 1; lv--)
+    {
+      const int first = n0 - cntAll[lv - 1], count = cntAll[lv - 1] - cntAll[lv];
+      if (count <= 0) continue;
+      k_subtree<<<cx_grid(count, TB), TB, 0, s>>>(count, d_placed + first, z->d_nodes);
+      ctx->launches++;
+    }
+    if (depth >= 1) { k_subtree<<<1, 32, 0, s>>>(1, nullptr, z->d_nodes); ctx->launches++; }
+    CX_CUDA(cudaEventRecord(ev1, s));
+    return 0;
   }
-  if (depth >= 1) { k_subtree<<<1, 32, 0, s>>>(1, nullptr, z->d_nodes); ctx->launches++; }
-  CX_CUDA(cudaEventRecord(ctx->ev1, s));
-  CX_CUDA(cudaStreamSynchronize(s));
-  CX_CUDA(cudaGetLastError());
-  cudaEventElapsedTime(&z->build_ms, ctx->ev0, ctx->ev1);
-  z->depth = depth;
-  z->levels = L;
-  cudaFreeAsync(B.keys, s); cudaFreeAsync(B.lo, s); cudaFreeAsync(B.hi, s); cudaFreeAsync(B.cur, s); cudaFreeAsync(B.br, s); cudaFreeAsync(B.depth, s);
-  cudaFreeAsync(S.actA, s); cudaFreeAsync(S.actB, s); cudaFreeAsync(d_placed, s);
-  if (depth + 2 > CX_STACK)
+
+  int end()
   {
-    cx_set_error("ADT depth %d exceeds the traversal stack (%d)", depth, CX_STACK);
-    return -3;
+    CX_CUDA(cudaStreamSynchronize(s));
+    CX_CUDA(cudaGetLastError());
+    cudaEventElapsedTime(&z->build_ms, ev0, ev1);
+    z->depth = depth;
+    z->levels = L;
+    release();
+    if (depth + 2 > CX_STACK)
+    {
+      cx_set_error("ADT depth %d exceeds the traversal stack (%d)", depth, CX_STACK);
+      return -3;
+    }
+    return 0;
   }
-  return 0;
+
+  void release()
+  {
+    if (!z) return;
+    cudaFreeAsync(B.keys, s); cudaFreeAsync(B.lo, s); cudaFreeAsync(B.hi, s); cudaFreeAsync(B.cur, s); cudaFreeAsync(B.br, s); cudaFreeAsync(B.depth, s);
+    cudaFreeAsync(S.actA, s); cudaFreeAsync(S.actB, s); cudaFreeAsync(d_placed, s);
+    if (h_cnt) { cx_pin_give(ctx, h_cnt, h_own); h_cnt = nullptr; }
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    ev0 = ev1 = nullptr;
+    z = nullptr;
+  }
+};
+}  // namespace
+
+int cx_build_adt(cx_zone* z)
+{
+  AdtBuild b;
+  int rc = b.begin(z, z->ctx->stream);
+  while (rc == 0 && !b.done) { rc = b.enqueue_batch(); if (rc == 0) rc = b.finish_batch(); }
+  if (rc == 0) rc = b.subtree();
+  if (rc == 0) return b.end();
+  cudaStreamSynchronize(z->ctx->stream);
+  b.release();
+  return rc;
+}
+
+// The ADTs of several zones at once: zone q is built on stream streams[q % nstreams]; the host walks the zones round
+// after round (a batch of levels each), so the device always has the short kernels of the other zones to run while
+// one zone waits for its counts.
+int cx_build_adt_many(int nz, cx_zone* const* zones, int nstreams, cudaStream_t* streams)
+{
+  std::vector<AdtBuild> b(nz);
+  int rc = 0;
+  for (int q = 0; q < nz && rc == 0; q++) rc = b[q].begin(zones[q], streams[q % nstreams]);
+  bool any = true;
+  while (rc == 0 && any)
+  {
+    any = false;
+    for (int q = 0; q < nz && rc == 0; q++) if (!b[q].done) rc = b[q].enqueue_batch();
+    for (int q = 0; q < nz && rc == 0; q++) if (!b[q].done) { rc = b[q].finish_batch(); any = any || !b[q].done; }
+  }
+  for (int q = 0; q < nz && rc == 0; q++) rc = b[q].subtree();
+  for (int q = 0; q < nz; q++)
+  {
+    if (rc == 0) rc = b[q].end();
+    else if (b[q].z) { cudaStreamSynchronize(b[q].s); b[q].release(); }
+  }
+  return rc;
 }

@@ -69,8 +69,7 @@ int cx_upload(cx_ctx* c, void* dptr, const void* host, size_t bytes)
   if (!nt)
   {
     const char* e = getenv("CX_UPLOAD_THREADS");
-    unsigned hw = std::thread::hardware_concurrency();
-    nt = e ? atoi(e) : (int)std::max(1u, std::min(hw ? hw / 2 : 4u, 8u));
+    nt = e ? atoi(e) : std::min(cx_host_threads(), 8);
     if (nt < 1) nt = 1;
   }
   // about 4 chunks per call (staging of chunk i+1 overlaps the DMA of chunk i), 1..32 MB each, 64-byte multiples
@@ -112,6 +111,7 @@ void cx_zone_bbox_host(int ni, int nj, int nk, const double* x, const double* y,
 int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, const double* d_zr, int nz,
                   const ZoneView* d_zones, const ZoneView* h_zones, int order, int nature, int penalty, int extrap,
                   cx_result* R, cx_result_dev* D);
+int cx_search_finish(cx_result* R, cx_result_dev* D);
 int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long nptsR, int n, const int* donor,
                   const int* rcv, const int* type, const double* coefs, long long ncoefs, cx_plan* P);
 int cx_plan_launch(cx_plan* P, int nvars, const double* const* dD, double* const* dR, double* dense, long long ld,
@@ -121,6 +121,52 @@ int cx_plan_rotate_on(cx_plan* P, int dirR, double ct, double st, double* fx, do
                       cudaStream_t s);
 
 struct cx_result_full { cx_result R; cx_result_dev D; };
+static inline int result_ready(cx_result* R) { return cx_search_finish(R, &((cx_result_full*)R)->D); }
+
+void* cx_pin_take(cx_ctx* c, size_t bytes, int* own)
+{
+  void* p = nullptr;
+  std::vector<void*>* pool = (std::vector<void*>*)c->pin_pool;
+  if (bytes <= CX_PIN_BLOCK && pool)
+  {
+    *own = 0;
+    if (!pool->empty()) { p = pool->back(); pool->pop_back(); return p; }
+    if (cudaHostAlloc(&p, CX_PIN_BLOCK, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+  }
+  *own = 1;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+
+void cx_pin_give(cx_ctx* c, void* p, int own)
+{
+  if (!p) return;
+  if (own || !c->pin_pool) cudaFreeHost(p);
+  else ((std::vector<void*>*)c->pin_pool)->push_back(p);
+}
+
+// threads of the host-side loops (staging copies, index gathers / scatters): CX_HOST_THREADS, else the cores of the
+// box shared between the ranks of the job (LOCAL_WORLD_SIZE), at most 16.  Given to the parallel regions explicitly:
+// torchrun exports OMP_NUM_THREADS=1.
+int cx_host_threads()
+{
+  static int nt = 0;
+  if (!nt)
+  {
+    const char* e = getenv("CX_HOST_THREADS");
+    if (e) nt = atoi(e);
+    else
+    {
+      unsigned hw = std::thread::hardware_concurrency();
+      const char* lw = getenv("LOCAL_WORLD_SIZE");
+      int ranks = lw ? std::max(1, atoi(lw)) : 1;
+      nt = (int)std::min<unsigned>(16u, std::max(1u, (hw ? hw : 4u) / (unsigned)ranks));
+    }
+    if (nt < 1) nt = 1;
+  }
+  return nt;
+}
 
 extern "C" {
 
@@ -172,6 +218,7 @@ int cx_ctx_create(int device, cx_ctx** out)
   CX_CUDA(cudaEventCreate(&c->ev0));
   CX_CUDA(cudaEventCreate(&c->ev1));
   c->pinned = nullptr; c->pinned_bytes = 0; c->launches = 0; c->nccl = nullptr;
+  c->pin_pool = new std::vector<void*>;
   *out = c;
   return 0;
 }
@@ -184,8 +231,14 @@ int cx_ctx_destroy(cx_ctx* c)
   cudaStreamSynchronize(c->stream);
   if (c->nccl) cx_comm_destroy(c);
   if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->pin_pool)
+  {
+    for (void* p : *(std::vector<void*>*)c->pin_pool) cudaFreeHost(p);
+    delete (std::vector<void*>*)c->pin_pool;
+  }
   cx_ctx_free_transfer_scratch(c);
   for (int i = 0; i < 2; i++) if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
+  for (int i = 0; i < c->naux; i++) cudaStreamDestroy(c->aux[i]);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
   cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
   cudaStreamDestroy(c->comm_stream);
@@ -297,8 +350,8 @@ static double wall_ms()
   return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
-int cx_zone_create(cx_ctx* c, int ni, int nj, int nk, const double* x, const double* y, const double* z,
-                   const double* cellN, cx_zone** out)
+static int zone_create_impl(cx_ctx* c, int ni, int nj, int nk, const double* x, const double* y, const double* z,
+                            const double* cellN, bool defer_adt, cx_zone** out)
 {
   if (ni < 2 || nj < 2 || nk < 1) { cx_set_error("setInterpData: structured donor zones must be 3D or 2D with z=constant."); return -1; }
   if ((long long)ni * nj * nk > 2000000000ll) { cx_set_error("donor zone too large for int32 indices"); return -1; }
@@ -336,12 +389,49 @@ int cx_zone_create(cx_ctx* c, int ni, int nj, int nk, const double* x, const dou
   *out = zn;
   int rc = cx_zone_set_celln(zn, cellN);
   double t4 = wall_ms();
-  if (rc == 0) rc = cx_build_adt(zn);
+  if (rc == 0 && !defer_adt) rc = cx_build_adt(zn);
   if (rc != 0) { cx_zone_destroy(zn); *out = nullptr; return rc; }
   if (prof)
     fprintf(stderr, "[cx_zone_create %dx%dx%d] alloc %.2f ms, coord upload %.2f, bbox %.2f, cellN %.2f, ADT %.2f (device %.2f), total %.2f\n",
             ni, nj, nk, t1 - t0, t2 - t1, t3 - t2, t4 - t3, wall_ms() - t4, zn->build_ms, wall_ms() - t0);
   return 0;
+}
+
+int cx_zone_create(cx_ctx* c, int ni, int nj, int nk, const double* x, const double* y, const double* z,
+                   const double* cellN, cx_zone** out)
+{
+  return zone_create_impl(c, ni, nj, nk, x, y, z, cellN, false, out);
+}
+
+// the same without the tree: coordinates and cellN go up, the ADT is built later by cx_zones_build_adt together with
+// those of the other zones of a batch (a search on a zone without its ADT is refused)
+int cx_zone_create_noadt(cx_ctx* c, int ni, int nj, int nk, const double* x, const double* y, const double* z,
+                         const double* cellN, cx_zone** out)
+{
+  return zone_create_impl(c, ni, nj, nk, x, y, z, cellN, true, out);
+}
+
+// ADTs of a batch of zones created with cx_zone_create_noadt, built concurrently (one side stream per zone, up to 8);
+// zones that have their tree already, and Cartesian (InterpCart) zones, are skipped
+int cx_zones_build_adt(cx_ctx* c, int nz, cx_zone* const* zones)
+{
+  CX_CUDA(cudaSetDevice(c->device));
+  std::vector<cx_zone*> todo;
+  for (int i = 0; i < nz; i++)
+  {
+    if (!zones[i] || zones[i]->ctx != c) { cx_set_error("cx_zones_build_adt: zone %d does not belong to this context", i); return -1; }
+    if (zones[i]->topo != 0 && !zones[i]->d_nodes) todo.push_back(zones[i]);
+  }
+  if (todo.empty()) return 0;
+  if (todo.size() == 1) return cx_build_adt(todo[0]);
+  const int want = (int)std::min<size_t>(8, todo.size());
+  while (c->naux < want)
+  {
+    CX_CUDA(cudaStreamCreateWithFlags(&c->aux[c->naux], cudaStreamNonBlocking));
+    c->naux++;
+  }
+  CX_CUDA(cudaStreamSynchronize(c->stream));      // the coordinates are up
+  return cx_build_adt_many((int)todo.size(), todo.data(), want, c->aux);
 }
 
 // Regular Cartesian donor located in closed form (interpDataType=0): the analogue of
@@ -481,13 +571,33 @@ int cx_set_interp_data_dev(cx_ctx* c, int nrcv, const double* d_xr, const double
     if (!zones[i] || (zones[i]->topo != 0 && !zones[i]->d_nodes)) { cx_set_error("setInterpData: donor zone %d has no ADT", i); return -1; }
     hv[i] = make_view(zones[i]);
   }
+  // the zone table goes up from a page-locked block of the context's pool and belongs to the result until the search
+  // is done; the call itself returns as soon as everything is queued (cx_search_finish, reached
+  // through every accessor of the result, waits and reads the counts)
+  // searches of different receptor zones may be spread over the side streams (cx_ctx_search_slot): every helper
+  // below takes the context's stream, so it is swapped for the duration of the call
+  struct StreamSwap {
+    cx_ctx* c; cudaStream_t saved;
+    StreamSwap(cx_ctx* c_, cudaStream_t s) : c(c_), saved(c_->stream) { c->stream = s; }
+    ~StreamSwap() { c->stream = saved; }
+  };
+  cudaStream_t run_on = c->stream;
+  if (c->search_slot > 0)
+  {
+    const int k = (c->search_slot - 1) % 8;
+    while (c->naux <= k) { CX_CUDA(cudaStreamCreateWithFlags(&c->aux[c->naux], cudaStreamNonBlocking)); c->naux++; }
+    run_on = c->aux[k];
+  }
+  StreamSwap swap(c, run_on);
   ZoneView* d_zones;
-  CX_CUDA(cudaMalloc(&d_zones, sizeof(ZoneView) * (size_t)nz));
-  CX_CUDA(cudaMemcpyAsync(d_zones, hv.data(), sizeof(ZoneView) * (size_t)nz, cudaMemcpyHostToDevice, c->stream));
+  CX_MALLOC(d_zones, sizeof(ZoneView) * (size_t)nz, c->stream);
   cx_result_full* F = new cx_result_full;
-  F->R.ctx = c;
+  F->R.ctx = c; F->R.d_zones_owned = d_zones;
+  F->R.h_zones = cx_pin_take(c, sizeof(ZoneView) * (size_t)nz, &F->R.h_zones_own);
+  if (!F->R.h_zones) { cx_set_error("setInterpData: no page-locked memory for the zone table"); delete F; return -2; }
+  memcpy(F->R.h_zones, hv.data(), sizeof(ZoneView) * (size_t)nz);
+  CX_CUDA(cudaMemcpyAsync(d_zones, F->R.h_zones, sizeof(ZoneView) * (size_t)nz, cudaMemcpyHostToDevice, c->stream));
   int rc = cx_search_run(c, nrcv, d_xr, d_yr, d_zr, nz, d_zones, hv.data(), order, nature, penalty, extrap, &F->R, &F->D);
-  cudaFree(d_zones);
   if (rc != 0) { cx_result_destroy(&F->R); return rc; }
   *out = &F->R;
   return 0;
@@ -512,8 +622,20 @@ int cx_set_interp_data(cx_ctx* c, int nrcv, const double* xr, const double* yr, 
   return rc;
 }
 
+// The searches issued next run on side stream `slot` - 1 (slot 1..8) instead of the main stream, so that the searches
+// of several receptor zones overlap on the device (their extrapolation passes are long chains of short work); slot 0
+// goes back to the main stream.  The inputs of such a search (receptor coordinates, donor hooks) must be complete
+// when it is issued (cx_receptors_create and the zone constructors return with their data on the device).
+int cx_ctx_search_slot(cx_ctx* c, int slot)
+{
+  if (slot < 0 || slot > 8) { cx_set_error("cx_ctx_search_slot: slot 0..8"); return -1; }
+  c->search_slot = slot;
+  return 0;
+}
+
 int cx_result_sizes(cx_result* R, int* cnt, int* ncoef, int* nextrap, int* norphan)
 {
+  CX_CHECK(result_ready(R));
   for (int z = 0; z < R->nz; z++)
   {
     if (cnt) cnt[z] = R->cnt[z];
@@ -527,6 +649,7 @@ int cx_result_sizes(cx_result* R, int* cnt, int* ncoef, int* nextrap, int* norph
 int cx_result_fetch_zone(cx_result* R, int z, int* rcv, int* donor, int* type, double* coefs, int* extrap)
 {
   cx_result_dev& D = ((cx_result_full*)R)->D;
+  CX_CHECK(result_ready(R));
   if (z < 0 || z >= R->nz) { cx_set_error("zone %d out of range", z); return -1; }
   size_t n = (size_t)R->cnt[z];
   if (n > 0)
@@ -544,12 +667,34 @@ int cx_result_fetch_zone(cx_result* R, int z, int* rcv, int* donor, int* type, d
 int cx_result_fetch_orphans(cx_result* R, int* orphan)
 {
   cx_result_dev& D = ((cx_result_full*)R)->D;
+  CX_CHECK(result_ready(R));
   if (R->norphan > 0) CX_CUDA(cudaMemcpy(orphan, D.orphan, sizeof(int) * (size_t)R->norphan, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// every list of the call in six copies: rcv / donor / type hold sum(cnt) entries, zones one behind the other in call
+// order, coefs sum(ncoef), extrap sum(nextrap), orphan norphan (cx_result_sizes gives the split); the destinations
+// may be page-locked (then the copies overlap each other)
+int cx_result_fetch_all(cx_result* R, int* rcv, int* donor, int* type, double* coefs, int* extrap, int* orphan)
+{
+  cx_result_dev& D = ((cx_result_full*)R)->D;
+  CX_CHECK(result_ready(R));
+  if (R->nrcv == 0) return 0;
+  cudaStream_t s = R->ctx->stream;
+  const size_t eo = (size_t)D.e_off[R->nz], co = (size_t)D.c_off[R->nz], xo = (size_t)D.x_off[R->nz];
+  if (eo && rcv) CX_CUDA(cudaMemcpyAsync(rcv, D.rcv, sizeof(int) * eo, cudaMemcpyDeviceToHost, s));
+  if (eo && donor) CX_CUDA(cudaMemcpyAsync(donor, D.dnr, sizeof(int) * eo, cudaMemcpyDeviceToHost, s));
+  if (eo && type) CX_CUDA(cudaMemcpyAsync(type, D.typ, sizeof(int) * eo, cudaMemcpyDeviceToHost, s));
+  if (co && coefs) CX_CUDA(cudaMemcpyAsync(coefs, D.coefs, sizeof(double) * co, cudaMemcpyDeviceToHost, s));
+  if (xo && extrap) CX_CUDA(cudaMemcpyAsync(extrap, D.ext, sizeof(int) * xo, cudaMemcpyDeviceToHost, s));
+  if (R->norphan > 0 && orphan) CX_CUDA(cudaMemcpyAsync(orphan, D.orphan, sizeof(int) * (size_t)R->norphan, cudaMemcpyDeviceToHost, s));
+  CX_CUDA(cudaStreamSynchronize(s));
   return 0;
 }
 
 int cx_result_fetch_raw(cx_result* R, int* noblk, int* type, int* dind, int* isext, double* cf)
 {
+  CX_CHECK(result_ready(R));
   size_t n = (size_t)R->nrcv;
   if (n == 0) return 0;
   if (noblk) CX_CUDA(cudaMemcpy(noblk, R->d_noblk, sizeof(int) * n, cudaMemcpyDeviceToHost));
@@ -562,6 +707,7 @@ int cx_result_fetch_raw(cx_result* R, int* noblk, int* type, int* dind, int* ise
 
 int cx_result_stats(cx_result* R, double* out)
 {
+  CX_CHECK(result_ready(R));
   out[0] = R->search_ms; out[1] = R->extrap_ms;
   out[2] = (double)R->stats[0]; out[3] = (double)R->stats[1]; out[4] = (double)R->ncfmax;
   out[5] = (double)R->stats[2]; out[6] = 0; out[7] = 0;
@@ -572,7 +718,11 @@ int cx_result_destroy(cx_result* R)
 {
   if (!R) return 0;
   cx_result_full* F = (cx_result_full*)R;
+  result_ready(R);
   cudaStream_t s = R->ctx->stream;
+  if (R->d_zones_owned) cudaFreeAsync(R->d_zones_owned, s);
+  if (R->h_zones) { cx_pin_give(R->ctx, R->h_zones, R->h_zones_own); R->h_zones = nullptr; }
+  for (int i = 0; i < 5; i++) if (R->ev[i]) cudaEventDestroy(R->ev[i]);
   void* ptrs[] = {R->d_noblk, R->d_type, R->d_dind, R->d_isext, R->d_cf, F->D.rcv, F->D.dnr, F->D.typ, F->D.coefs,
                   F->D.ext, F->D.orphan};
   for (void* p : ptrs) if (p) cudaFreeAsync(p, s);
@@ -974,7 +1124,8 @@ int cx_host_scatter(double* dst, const int* idx, const double* src, long long n)
     for (long long e = 0; e < n; e++) dst[idx[e]] = src[e];
     return 0;
   }
-#pragma omp parallel for schedule(static)
+  const int nt = cx_host_threads();
+#pragma omp parallel for num_threads(nt) schedule(static)
   for (long long e = 0; e < n; e++) dst[idx[e]] = src[e];
   return 0;
 }
@@ -985,6 +1136,182 @@ int cx_plan_sorted_rcv(cx_plan* P, int* out)
 {
   if (P->n == 0) return 0;
   CX_CUDA(cudaMemcpy(out, P->d_rcv, sizeof(int) * (size_t)P->n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// mark[node] = 1 for every donor node the plan reads (the stencil of each entry); mark: nptsD bytes on the device,
+// zeroed by the caller (several plans of one donor zone accumulate into the same mask); asynchronous
+int cx_plan_mark_donors(cx_plan* P, unsigned char* d_mark)
+{
+  cx_ctx* c = P->ctx;
+  for (auto& G : P->groups)
+  {
+    if (G.n == 0) continue;
+    int o = G.type == 1 ? 1 : (G.type == 2 || G.type == 22) ? 2 : G.type == 3 ? 3 : G.type == 44 ? 4 : 5;
+    k_mark<<<cx_grid(G.n, 256), 256, 0, c->stream>>>(G.n, o, G.type == 22 ? 1 : o, P->imd, P->imd * P->jmd, P->d_donor + G.first, d_mark);
+    c->launches++;
+  }
+  return 0;
+}
+
+// host side of a sparse upload: dst[e] = src[idx[e]]
+int cx_host_gather(double* dst, const int* idx, const double* src, long long n)
+{
+  if (n < (1 << 15))
+  {
+    for (long long e = 0; e < n; e++) dst[e] = src[idx[e]];
+    return 0;
+  }
+  const int nt = cx_host_threads();
+#pragma omp parallel for num_threads(nt) schedule(static)
+  for (long long e = 0; e < n; e++) dst[e] = src[idx[e]];
+  return 0;
+}
+
+// ---- host trees in, host trees out: one iteration of a step with its copies --------------------------------
+// What Connector/Mpi.py:396-440 (__setInterpTransfers + C._setPartialFields) does per call with host arrays: the
+// donor values a step reads go up, the receptor values it wrote come back.  An item is one zone's fields in one
+// direction: whole arrays, or (idx != NULL) only the listed points, packed through a page-locked block (host
+// gather / device scatter on the way up, device gather / host scatter on the way down).  The run is pipelined
+// per variable over three streams: upload of variable v+1 | plans + exchange of v | download of v-1, so both
+// directions of the bus are busy at once.
+struct cx_hostio {
+  cx_ctx* ctx; int nvars;
+  cudaStream_t up, dn;
+  std::vector<cudaEvent_t> evU, evS, evD;
+  struct Item {
+    int dir; long long n; bool sparse;
+    std::vector<int> idx; int* d_idx; double* hbuf; double* dbuf;
+    std::vector<double*> h; std::vector<double*> d;
+  };
+  std::vector<Item> items;
+  long long h2d_bytes, d2h_bytes;
+};
+
+int cx_hostio_create(cx_ctx* ctx, int nvars, cx_hostio** out)
+{
+  CX_CUDA(cudaSetDevice(ctx->device));
+  if (nvars < 1 || nvars > 16) { cx_set_error("cx_hostio_create: 1..16 variables"); return -1; }
+  cx_hostio* io = new cx_hostio;
+  io->ctx = ctx; io->nvars = nvars; io->h2d_bytes = io->d2h_bytes = 0;
+  CX_CUDA(cudaStreamCreateWithFlags(&io->up, cudaStreamNonBlocking));
+  CX_CUDA(cudaStreamCreateWithFlags(&io->dn, cudaStreamNonBlocking));
+  io->evU.resize(nvars); io->evS.resize(nvars); io->evD.resize(nvars);
+  for (int v = 0; v < nvars; v++)
+  {
+    CX_CUDA(cudaEventCreateWithFlags(&io->evU[v], cudaEventDisableTiming));
+    CX_CUDA(cudaEventCreateWithFlags(&io->evS[v], cudaEventDisableTiming));
+    CX_CUDA(cudaEventCreateWithFlags(&io->evD[v], cudaEventDisableTiming));
+  }
+  *out = io;
+  return 0;
+}
+
+// dir 0: host -> device before the step; 1: device -> host after it.  n: points moved per variable (the length of
+// h_idx, or of the whole arrays when h_idx == NULL); h_field / d_field: nvars pointers each.
+int cx_hostio_add(cx_hostio* io, int dir, long long n, const int* h_idx, double* const* h_field, double* const* d_field)
+{
+  if (n <= 0) return 0;
+  cx_ctx* c = io->ctx;
+  CX_CUDA(cudaSetDevice(c->device));
+  io->items.emplace_back();
+  cx_hostio::Item& I = io->items.back();
+  I.dir = dir; I.n = n; I.sparse = h_idx != nullptr; I.d_idx = nullptr; I.hbuf = nullptr; I.dbuf = nullptr;
+  I.h.assign(h_field, h_field + io->nvars); I.d.assign(d_field, d_field + io->nvars);
+  if (I.sparse)
+  {
+    I.idx.assign(h_idx, h_idx + n);
+    CX_CUDA(cudaMalloc(&I.d_idx, sizeof(int) * (size_t)n));
+    CX_CHECK(cx_upload(c, I.d_idx, I.idx.data(), sizeof(int) * (size_t)n));
+    CX_CUDA(cudaStreamSynchronize(c->stream));
+    CX_CUDA(cudaMalloc(&I.dbuf, sizeof(double) * (size_t)n * io->nvars));
+    CX_CUDA(cudaHostAlloc(&I.hbuf, sizeof(double) * (size_t)n * io->nvars, cudaHostAllocDefault));
+  }
+  (dir == 0 ? io->h2d_bytes : io->d2h_bytes) += 8ll * n * io->nvars;
+  return 0;
+}
+
+int cx_hostio_bytes(cx_hostio* io, long long* h2d, long long* d2h)
+{
+  if (h2d) *h2d = io->h2d_bytes;
+  if (d2h) *d2h = io->d2h_bytes;
+  return 0;
+}
+
+extern int cx_step_run_vars(cx_step* S, int niter, int overlap, int v0, int nv);
+extern int cx_step_splittable(cx_step* S);
+
+int cx_step_run_host(cx_step* S, cx_hostio* io, int pipelined)
+{
+  cx_ctx* c = io->ctx;
+  CX_CUDA(cudaSetDevice(c->device));
+  const int nv = io->nvars;
+  const int chunk = (pipelined && cx_step_splittable(S)) ? 1 : nv;
+  // the copies of this call must follow whatever is queued on the main stream (e.g. the previous step)
+  CX_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+  CX_CUDA(cudaStreamWaitEvent(io->up, c->ev_fork, 0));
+  for (int v0 = 0; v0 < nv; v0 += chunk)
+  {
+    for (auto& I : io->items)
+    {
+      if (I.dir != 0) continue;
+      if (I.sparse)
+      {
+        for (int v = v0; v < v0 + chunk; v++) cx_host_gather(I.hbuf + (size_t)v * I.n, I.idx.data(), I.h[v], I.n);
+        CX_CUDA(cudaMemcpyAsync(I.dbuf + (size_t)v0 * I.n, I.hbuf + (size_t)v0 * I.n, sizeof(double) * (size_t)I.n * chunk,
+                                cudaMemcpyHostToDevice, io->up));
+        RPtrs R; for (int v = 0; v < chunk; v++) R.r[v] = I.d[v0 + v];
+        k_scatter<<<cx_grid(I.n, 256), 256, 0, io->up>>>((int)I.n, chunk, I.dbuf + (size_t)v0 * I.n, I.n, I.d_idx, R);
+        c->launches++;
+      }
+      else
+        for (int v = v0; v < v0 + chunk; v++)
+          CX_CUDA(cudaMemcpyAsync(I.d[v], I.h[v], sizeof(double) * (size_t)I.n, cudaMemcpyHostToDevice, io->up));
+    }
+    CX_CUDA(cudaEventRecord(io->evU[v0], io->up));
+    CX_CUDA(cudaStreamWaitEvent(c->stream, io->evU[v0], 0));
+    CX_CHECK(cx_step_run_vars(S, 1, 1, v0, chunk));
+    CX_CUDA(cudaEventRecord(io->evS[v0], c->stream));
+    CX_CUDA(cudaStreamWaitEvent(io->dn, io->evS[v0], 0));
+    for (auto& I : io->items)
+    {
+      if (I.dir != 1) continue;
+      if (I.sparse)
+      {
+        RPtrs R; for (int v = 0; v < chunk; v++) R.r[v] = I.d[v0 + v];
+        k_gather<<<cx_grid(I.n, 256), 256, 0, io->dn>>>((int)I.n, chunk, I.dbuf + (size_t)v0 * I.n, I.n, I.d_idx, R);
+        c->launches++;
+        CX_CUDA(cudaMemcpyAsync(I.hbuf + (size_t)v0 * I.n, I.dbuf + (size_t)v0 * I.n, sizeof(double) * (size_t)I.n * chunk,
+                                cudaMemcpyDeviceToHost, io->dn));
+      }
+      else
+        for (int v = v0; v < v0 + chunk; v++)
+          CX_CUDA(cudaMemcpyAsync(I.h[v], I.d[v], sizeof(double) * (size_t)I.n, cudaMemcpyDeviceToHost, io->dn));
+    }
+    CX_CUDA(cudaEventRecord(io->evD[v0], io->dn));
+  }
+  for (int v0 = 0; v0 < nv; v0 += chunk)
+  {
+    CX_CUDA(cudaEventSynchronize(io->evD[v0]));
+    for (auto& I : io->items)
+      if (I.dir == 1 && I.sparse)
+        for (int v = v0; v < v0 + chunk; v++) cx_host_scatter(I.h[v], I.idx.data(), I.hbuf + (size_t)v * I.n, I.n);
+  }
+  CX_CUDA(cudaStreamSynchronize(c->stream));
+  CX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int cx_hostio_destroy(cx_hostio* io)
+{
+  if (!io) return 0;
+  cudaStreamSynchronize(io->up); cudaStreamSynchronize(io->dn);
+  for (auto& I : io->items) { if (I.d_idx) cudaFree(I.d_idx); if (I.dbuf) cudaFree(I.dbuf); if (I.hbuf) cudaFreeHost(I.hbuf); }
+  for (auto e : io->evU) cudaEventDestroy(e);
+  for (auto e : io->evS) cudaEventDestroy(e);
+  for (auto e : io->evD) cudaEventDestroy(e);
+  cudaStreamDestroy(io->up); cudaStreamDestroy(io->dn);
+  delete io;
   return 0;
 }
 
@@ -1003,12 +1330,7 @@ int cx_plan_info(cx_plan* P, int* n, int* ngroups, long long* alg_fixed, long lo
       CX_CUDA(cudaMalloc(&cnt, sizeof(unsigned long long)));
       CX_CUDA(cudaMemsetAsync(mark, 0, (size_t)P->nptsD, c->stream));
       CX_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
-      for (auto& G : P->groups)
-      {
-        int o = G.type == 1 ? 1 : (G.type == 2 || G.type == 22) ? 2 : G.type == 3 ? 3 : G.type == 44 ? 4 : 5;
-        k_mark<<<cx_grid(G.n, 256), 256, 0, c->stream>>>(G.n, o, G.type == 22 ? 1 : o, P->imd, P->imd * P->jmd, P->d_donor + G.first, mark);
-        c->launches++;
-      }
+      CX_CHECK(cx_plan_mark_donors(P, mark));
       k_count<<<cx_grid(P->nptsD, 256), 256, 0, c->stream>>>(P->nptsD, mark, cnt);
       c->launches++;
       unsigned long long h = 0;

@@ -45,7 +45,18 @@ struct cx_ctx {
   double* d_tfields; size_t tfields_cap;
   double* d_tdense; size_t tdense_cap;
   void* fcache;   // cx_field_cache*
+  // free page-locked blocks (CX_PIN_BLOCK bytes each) for the zone tables and the counts of searches in flight
+  void* pin_pool;   // std::vector<void*>*
+  // side streams for work that overlaps across zones (batched ADT builds), created on first use
+  cudaStream_t aux[8]; int naux;
+  int search_slot;   // 0: searches run on the main stream; k > 0: on side stream k-1 (cx_ctx_search_slot)
 };
+#define CX_PIN_BLOCK 16384
+// a page-locked block of at least `bytes` (from the context's pool when it fits a pool block); give it back with the
+// same `own` flag once the device is done with it
+void* cx_pin_take(cx_ctx* c, size_t bytes, int* own);
+void cx_pin_give(cx_ctx* c, void* p, int own);
+int cx_host_threads();
 
 struct cx_zone {
   cx_ctx* ctx;
@@ -72,6 +83,13 @@ struct cx_result {
   // search statistics (sum over receptors): nodes visited, candidates, tetra solves
   unsigned long long stats[4];
   float search_ms, extrap_ms, total_ms;
+  // a launched search whose counts have not been read yet (cx_search_finish): nothing in cx_search_run waits for
+  // the device, so several receptor zones can be in flight
+  int pending;
+  unsigned long long* h_counts; int h_counts_own;   // page-locked: [nz*3+1] counts + 4 statistics
+  void* h_zones; int h_zones_own;                   // page-locked copy of the ZoneView table the upload reads
+  cudaEvent_t ev[5];                                // search begin/end, extrapolation begin/end, all done
+  void* d_zones_owned;                              // the ZoneView table of the call (freed when the search is done)
 };
 
 struct cx_plan {
@@ -104,6 +122,7 @@ int cx_exclusive_scan_u64(cx_ctx* ctx, const unsigned long long* d_in, unsigned 
 
 // ADT build (cx_adt.cu)
 int cx_build_adt(cx_zone* z);
+int cx_build_adt_many(int nz, cx_zone* const* zones, int nstreams, cudaStream_t* streams);
 
 // stream-ordered allocation (pool keeps freed blocks: release threshold = max, set at ctx creation);
 // pointers obtained here may also be released with plain cudaFree

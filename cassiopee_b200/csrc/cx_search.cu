@@ -13,6 +13,7 @@
 #include "cx_internal.h"
 #include <stdlib.h>
 #include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
 
 using namespace cx;
 
@@ -158,15 +159,16 @@ __device__ __forceinline__ int search_extrap_cell_warp(const ZoneView& Z, double
 }
 
 __global__ void __launch_bounds__(128)
-k_extrap(int nlist, const int* __restrict__ list, const double* __restrict__ xr, const double* __restrict__ yr,
+k_extrap(const int* __restrict__ nlist_p, const int* __restrict__ list, const double* __restrict__ xr, const double* __restrict__ yr,
          const double* __restrict__ zr, int nz, const ZoneView* __restrict__ zones, int nature, int penalty,
          RcvTable T, unsigned long long* gstats)
 {
+  // the list length lives on the device (the host never waits for the interpolation pass): the warps stride over it
   __shared__ int s_cand[4][32];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int a = blockIdx.x * 4 + w;
+  const int nlist = *nlist_p;
   SearchStats st; st.nvisit = 0; st.ncand = 0; st.ntet = 0;
-  if (a < nlist)                                   // warp-uniform
+  for (int a = blockIdx.x * 4 + w; a < nlist; a += gridDim.x * 4)      // warp-uniform
   {
     const int r = list[a];
     const double x = xr[r], y = yr[r], z = zr[r];
@@ -234,21 +236,6 @@ __device__ __forceinline__ int ncf_of_type(int t)
   return t == 1 ? 1 : t == 2 ? 8 : t == 3 ? 9 : t == 5 ? 15 : t == 44 ? 12 : t == 22 ? 4 : 0;
 }
 
-// flag pass: which = zone (1-based) to select; mode 0: entries (count<<32|ncoef),
-// mode 1: extrapolated entries of that zone, mode 2: orphans (noblk==0)
-__global__ void k_flags(int n, const int* __restrict__ noblk, const int* __restrict__ type,
-                        const int* __restrict__ isext, int which, int mode, unsigned long long* __restrict__ f)
-{
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
-  unsigned long long v = 0;
-  int b = noblk[r];
-  if (mode == 0) { if (b == which) v = (1ull << 32) | (unsigned long long)ncf_of_type(type[r]); }
-  else if (mode == 1) { if (b == which && isext[r] == 1) v = 1; }
-  else { if (b == 0) v = 1; }
-  f[r] = v;
-}
-
 // per-zone totals in one pass: cnt[z*3+0] entries, +1 coefficients, +2 extrapolated; cnt[nz*3] orphans
 // (lanes of a warp with the same zone are reduced with match/reduce before the atomics)
 __global__ void k_zone_hist(int n, int nz, const int* __restrict__ noblk, const int* __restrict__ type,
@@ -274,28 +261,59 @@ __global__ void k_zone_hist(int n, int nz, const int* __restrict__ noblk, const 
   else atomicAdd(&cnt[nz * 3], (unsigned long long)__popc(grp));
 }
 
-__global__ void k_scatter_entries(int n, RcvTable T, int which, const unsigned long long* __restrict__ f,
-                                  const unsigned long long* __restrict__ pos, int* __restrict__ rcv,
-                                  int* __restrict__ dnr, int* __restrict__ typ, double* __restrict__ coefs)
+// receptors the interpolation pass left without a donor, appended in any order (every one is extrapolated on its own)
+__global__ void k_collect_fail(int n, const int* __restrict__ noblk, int* __restrict__ fail, int* __restrict__ nfail)
 {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
-  if (f[r] == 0) return;
-  unsigned long long p = pos[r];
-  int e = (int)(p >> 32);
-  size_t c = (size_t)(p & 0xffffffffull);
-  int t = T.type[r];
-  rcv[e] = r; dnr[e] = T.dind[r]; typ[e] = t;
-  int ncf = ncf_of_type(t);
-  for (int k = 0; k < ncf; k++) coefs[c + k] = T.cf[(size_t)k * n + r];
+  const bool f = r < n && noblk[r] == 0;
+  const unsigned m = __ballot_sync(0xffffffffu, f);
+  if (m == 0) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == __ffs(m) - 1) base = atomicAdd(nfail, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (f) fail[base + __popc(m & ((1u << lane) - 1u))] = r;
 }
 
-__global__ void k_scatter_index(int n, const unsigned long long* __restrict__ f,
-                                const unsigned long long* __restrict__ pos, int* __restrict__ out)
+// ---- packing: ONE pass for all donor zones ------------------------------------------------------------------
+// A stable sort of the receptors by donor zone number (0 = orphan) gives, zone after zone, the entries in ascending
+// receptor order (setInterpData.cpp:1183-1252: the static-schedule chunks concatenated); one 64-bit scan over that
+// order gives every entry its coefficient offset (low 40 bits) and its rank among the extrapolated entries (high
+// bits), and one scatter writes the ragged lists of all zones.
+__global__ void k_pack_keys(int n, const int* __restrict__ noblk, unsigned* __restrict__ keys, int* __restrict__ vals)
 {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
-  if (f[r]) out[(int)pos[r]] = r;
+  keys[r] = (unsigned)noblk[r]; vals[r] = r;
+}
+
+__global__ void k_pack_flags(int n, const int* __restrict__ order, RcvTable T, unsigned long long* __restrict__ f)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r = order[i];
+  unsigned long long v = 0;
+  if (T.noblk[r] > 0) v = (unsigned long long)ncf_of_type(T.type[r]) | (T.isext[r] == 1 ? (1ull << 40) : 0ull);
+  f[i] = v;
+}
+
+__global__ void k_pack_scatter(int n, int nz, const int* __restrict__ order, RcvTable T,
+                               const unsigned long long* __restrict__ pos, const unsigned long long* __restrict__ cnt,
+                               int* __restrict__ rcv, int* __restrict__ dnr, int* __restrict__ typ,
+                               double* __restrict__ coefs, int* __restrict__ ext, int* __restrict__ orphan)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r = order[i];
+  if (T.noblk[r] == 0) { orphan[i] = r; return; }         // key 0 sorts first: position == rank among the orphans
+  const int e = i - (int)cnt[(size_t)nz * 3];
+  const unsigned long long p = pos[i];
+  const size_t c = (size_t)(p & ((1ull << 40) - 1ull));
+  const int t = T.type[r];
+  rcv[e] = r; dnr[e] = T.dind[r]; typ[e] = t;
+  const int ncf = ncf_of_type(t);
+  for (int k = 0; k < ncf; k++) coefs[c + k] = T.cf[(size_t)k * n + r];
+  if (T.isext[r] == 1) ext[(size_t)(p >> 40)] = r;
 }
 
 }  // namespace
@@ -323,8 +341,11 @@ int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, co
   D->e_off.assign(nz + 1, 0); D->c_off.assign(nz + 1, 0); D->x_off.assign(nz + 1, 0);
   D->rcv = D->dnr = D->typ = D->ext = D->orphan = nullptr; D->coefs = nullptr;
   R->d_noblk = R->d_type = R->d_dind = R->d_isext = nullptr; R->d_cf = nullptr;
-  if (n == 0) return 0;
+  R->pending = 0; R->h_counts = nullptr; R->h_counts_own = 0;
+  for (int i = 0; i < 5; i++) R->ev[i] = nullptr;
+  if (n == 0) return 0;   // (the zone table of the call, if any, is released with the result)
   size_t N = n;
+  for (int i = 0; i < 5; i++) CX_CUDA(cudaEventCreate(&R->ev[i]));
   CX_MALLOC(R->d_noblk, sizeof(int) * N, s);
   CX_MALLOC(R->d_type, sizeof(int) * N, s);
   CX_MALLOC(R->d_dind, sizeof(int) * N, s);
@@ -336,7 +357,7 @@ int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, co
   RcvTable T{R->d_noblk, R->d_type, R->d_dind, R->d_isext, R->d_cf, n, ncfmax};
   const int TB = 128;
 
-  CX_CUDA(cudaEventRecord(ctx->ev0, s));
+  CX_CUDA(cudaEventRecord(R->ev[0], s));
   if (order == 2)
   {
     int cap = 4;
@@ -363,44 +384,75 @@ int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, co
     CX_CHECK(cx_lagrange_pipeline(ctx, order, n, d_xr, d_yr, d_zr, nz, d_zones, h_zones, nature, penalty,
                                   R->d_noblk, R->d_type, R->d_dind, R->d_cf, ncfmax, d_stats));
   }
-  CX_CUDA(cudaEventRecord(ctx->ev1, s));
+  CX_CUDA(cudaEventRecord(R->ev[1], s));
 
+  // ---- extrapolation of the receptors without a donor; nothing here waits for the device ----
+  int* d_fail = nullptr; int* d_nfail = nullptr;
+  CX_CUDA(cudaEventRecord(R->ev[2], s));
+  const int TB2 = 256;
+  if (extrap == 1)
+  {
+    CX_MALLOC(d_fail, sizeof(int) * N, s);
+    CX_MALLOC(d_nfail, sizeof(int), s);
+    CX_CUDA(cudaMemsetAsync(d_nfail, 0, sizeof(int), s));
+    k_collect_fail<<<cx_grid(n, TB2), TB2, 0, s>>>(n, R->d_noblk, d_fail, d_nfail);
+    const int gx = std::max(1, std::min(cx_grid(n, 4), ctx->sm_count * 16));
+    k_extrap<<<gx, 128, 0, s>>>(d_nfail, d_fail, d_xr, d_yr, d_zr, nz, d_zones, nature, penalty, T, d_stats);
+    ctx->launches += 2;
+    cudaFreeAsync(d_fail, s); cudaFreeAsync(d_nfail, s);
+  }
+  CX_CUDA(cudaEventRecord(R->ev[3], s));
+
+  // ---- packing, all donor zones in one pass; outputs sized by their upper bounds (the counts stay on the device
+  // until cx_search_finish reads them) ----
   unsigned long long *d_f, *d_p, *d_cnt;
   CX_MALLOC(d_f, sizeof(unsigned long long) * N, s);
   CX_MALLOC(d_p, sizeof(unsigned long long) * N, s);
   CX_MALLOC(d_cnt, sizeof(unsigned long long) * (size_t)(nz * 3 + 1), s);
-  const int TB2 = 256;
+  CX_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * (size_t)(nz * 3 + 1), s));
+  k_zone_hist<<<cx_grid(n, TB2), TB2, 0, s>>>(n, nz, R->d_noblk, R->d_type, R->d_isext, d_cnt);
+  unsigned *k_in, *k_out; int *v_in, *v_out;
+  CX_MALLOC(k_in, sizeof(unsigned) * N, s); CX_MALLOC(k_out, sizeof(unsigned) * N, s);
+  CX_MALLOC(v_in, sizeof(int) * N, s); CX_MALLOC(v_out, sizeof(int) * N, s);
+  k_pack_keys<<<cx_grid(n, TB2), TB2, 0, s>>>(n, R->d_noblk, k_in, v_in);
+  int bits = 1; while ((1 << bits) <= nz) bits++;
+  size_t tmp_bytes = 0; void* tmp = nullptr;
+  CX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, n, 0, bits, s));
+  CX_MALLOC(tmp, tmp_bytes, s);
+  CX_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, n, 0, bits, s));
+  k_pack_flags<<<cx_grid(n, TB2), TB2, 0, s>>>(n, v_out, T, d_f);
+  CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, n, nullptr));
+  CX_MALLOC(D->rcv, sizeof(int) * N, s);
+  CX_MALLOC(D->dnr, sizeof(int) * N, s);
+  CX_MALLOC(D->typ, sizeof(int) * N, s);
+  CX_MALLOC(D->ext, sizeof(int) * N, s);
+  CX_MALLOC(D->orphan, sizeof(int) * N, s);
+  CX_MALLOC(D->coefs, sizeof(double) * N * ncfmax, s);
+  k_pack_scatter<<<cx_grid(n, TB2), TB2, 0, s>>>(n, nz, v_out, T, d_p, d_cnt, D->rcv, D->dnr, D->typ, D->coefs, D->ext, D->orphan);
+  ctx->launches += 5;
+  cudaFreeAsync(k_in, s); cudaFreeAsync(k_out, s); cudaFreeAsync(v_in, s); cudaFreeAsync(v_out, s); cudaFreeAsync(tmp, s);
+  cudaFreeAsync(d_f, s); cudaFreeAsync(d_p, s);
+  // counts and statistics come back through page-locked memory, so the copy does not stall the host either
+  const size_t ncnt = (size_t)nz * 3 + 1 + 4;
+  R->h_counts = (unsigned long long*)cx_pin_take(ctx, sizeof(unsigned long long) * ncnt, &R->h_counts_own);
+  if (!R->h_counts) { cx_set_error("setInterpData: no page-locked memory for the counts"); return -2; }
+  CX_CUDA(cudaMemcpyAsync(R->h_counts, d_cnt, sizeof(unsigned long long) * (ncnt - 4), cudaMemcpyDeviceToHost, s));
+  CX_CUDA(cudaMemcpyAsync(R->h_counts + (ncnt - 4), d_stats, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));
+  CX_CUDA(cudaEventRecord(R->ev[4], s));
+  cudaFreeAsync(d_stats, s); cudaFreeAsync(d_cnt, s);
+  R->pending = 1;
+  return 0;
+}
 
-  // per-zone totals (one pass); if the interpolation pass left orphans and extrapolation is enabled, run the
-  // warp-per-receptor extrapolation over their compacted list and count again
-  std::vector<unsigned long long> hc((size_t)nz * 3 + 1);
-  auto histogram = [&]() -> int {
-    CX_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * (size_t)(nz * 3 + 1), s));
-    k_zone_hist<<<cx_grid(n, TB2), TB2, 0, s>>>(n, nz, R->d_noblk, R->d_type, R->d_isext, d_cnt);
-    ctx->launches++;
-    CX_CUDA(cudaMemcpyAsync(hc.data(), d_cnt, sizeof(unsigned long long) * hc.size(), cudaMemcpyDeviceToHost, s));
-    CX_CUDA(cudaStreamSynchronize(s));
-    return 0;
-  };
-  CX_CHECK(histogram());
-  cudaEvent_t evx0, evx1;
-  cudaEventCreate(&evx0); cudaEventCreate(&evx1);
-  cudaEventRecord(evx0, s);
-  int nfail = (int)hc[(size_t)nz * 3];
-  if (extrap == 1 && nfail > 0)
-  {
-    int* d_fail;
-    CX_MALLOC(d_fail, sizeof(int) * (size_t)nfail, s);
-    k_flags<<<cx_grid(n, TB2), TB2, 0, s>>>(n, R->d_noblk, R->d_type, R->d_isext, 0, 2, d_f);
-    CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, n, nullptr));
-    k_scatter_index<<<cx_grid(n, TB2), TB2, 0, s>>>(n, d_f, d_p, d_fail);
-    k_extrap<<<cx_grid(nfail, 4), 128, 0, s>>>(nfail, d_fail, d_xr, d_yr, d_zr, nz, d_zones, nature, penalty, T, d_stats);
-    ctx->launches += 3;
-    cudaFreeAsync(d_fail, s);
-    cudaEventRecord(evx1, s);
-    CX_CHECK(histogram());
-  }
-  else cudaEventRecord(evx1, s);
+// wait for a launched search and read its counts (every accessor of a result goes through here)
+int cx_search_finish(cx_result* R, cx_result_dev* D)
+{
+  if (!R->pending) return 0;
+  R->pending = 0;
+  const int nz = R->nz;
+  CX_CUDA(cudaEventSynchronize(R->ev[4]));
+  CX_CUDA(cudaGetLastError());
+  const unsigned long long* hc = R->h_counts;
   long long eo = 0, co = 0, xo = 0;
   for (int z = 0; z < nz; z++)
   {
@@ -410,41 +462,13 @@ int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, co
   }
   D->e_off[nz] = eo; D->c_off[nz] = co; D->x_off[nz] = xo;
   R->norphan = (int)hc[(size_t)nz * 3];
-  CX_MALLOC(D->rcv, sizeof(int) * (size_t)std::max(eo, 1ll), s);
-  CX_MALLOC(D->dnr, sizeof(int) * (size_t)std::max(eo, 1ll), s);
-  CX_MALLOC(D->typ, sizeof(int) * (size_t)std::max(eo, 1ll), s);
-  CX_MALLOC(D->ext, sizeof(int) * (size_t)std::max(xo, 1ll), s);
-  CX_MALLOC(D->orphan, sizeof(int) * (size_t)std::max(R->norphan, 1), s);
-  CX_MALLOC(D->coefs, sizeof(double) * (size_t)std::max(co, 1ll), s);
-  for (int z = 0; z < nz; z++)
-  {
-    if (R->cnt[z] == 0) continue;
-    k_flags<<<cx_grid(n, TB2), TB2, 0, s>>>(n, R->d_noblk, R->d_type, R->d_isext, z + 1, 0, d_f);
-    CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, n, nullptr));
-    k_scatter_entries<<<cx_grid(n, TB2), TB2, 0, s>>>(n, T, z + 1, d_f, d_p, D->rcv + D->e_off[z], D->dnr + D->e_off[z],
-                                                     D->typ + D->e_off[z], D->coefs + D->c_off[z]);
-    ctx->launches += 2;
-    if (R->nextrap[z] > 0)
-    {
-      k_flags<<<cx_grid(n, TB2), TB2, 0, s>>>(n, R->d_noblk, R->d_type, R->d_isext, z + 1, 1, d_f);
-      CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, n, nullptr));
-      k_scatter_index<<<cx_grid(n, TB2), TB2, 0, s>>>(n, d_f, d_p, D->ext + D->x_off[z]);
-      ctx->launches += 2;
-    }
-  }
-  if (R->norphan > 0)
-  {
-    k_flags<<<cx_grid(n, TB2), TB2, 0, s>>>(n, R->d_noblk, R->d_type, R->d_isext, 0, 2, d_f);
-    CX_CHECK(cx_exclusive_scan_u64(ctx, d_f, d_p, n, nullptr));
-    k_scatter_index<<<cx_grid(n, TB2), TB2, 0, s>>>(n, d_f, d_p, D->orphan);
-    ctx->launches += 2;
-  }
-  CX_CUDA(cudaStreamSynchronize(s));
-  CX_CUDA(cudaGetLastError());
-  cudaEventElapsedTime(&R->search_ms, ctx->ev0, ctx->ev1);
-  cudaEventElapsedTime(&R->extrap_ms, evx0, evx1);
-  cudaEventDestroy(evx0); cudaEventDestroy(evx1);
-  CX_CUDA(cudaMemcpy(R->stats, d_stats, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost));
-  cudaFreeAsync(d_stats, s); cudaFreeAsync(d_f, s); cudaFreeAsync(d_p, s); cudaFreeAsync(d_cnt, s);
+  for (int i = 0; i < 4; i++) R->stats[i] = hc[(size_t)nz * 3 + 1 + i];
+  cudaEventElapsedTime(&R->search_ms, R->ev[0], R->ev[1]);
+  cudaEventElapsedTime(&R->extrap_ms, R->ev[2], R->ev[3]);
+  cx_pin_give(R->ctx, R->h_counts, R->h_counts_own);
+  R->h_counts = nullptr;
+  if (R->d_zones_owned) { cudaFreeAsync(R->d_zones_owned, R->ctx->stream); R->d_zones_owned = nullptr; }
+  if (R->h_zones) { cx_pin_give(R->ctx, R->h_zones, R->h_zones_own); R->h_zones = nullptr; }
+  for (int i = 0; i < 5; i++) { cudaEventDestroy(R->ev[i]); R->ev[i] = nullptr; }
   return 0;
 }

@@ -847,7 +847,7 @@ struct BlkRec { int desc, d_lo, d_hi, start, count, base, dims, pad_; };   // st
 
 template <int TYPE, bool TILED>
 __global__ void __launch_bounds__(256, TILED ? 2 : CX_SET_MINB)
-k_transfer_set(const SetDesc* __restrict__ descs, const BlkRec* __restrict__ blk, int nvars, int staged)
+k_transfer_set(const SetDesc* __restrict__ descs, const BlkRec* __restrict__ blk, int nvars, int staged, int v0)
 {
   // the descriptor (with its field-pointer tables) goes through shared memory once per CTA, copied by 8-byte
   // words in one round trip: the per-variable pointer fetches inside the entry loop are shared-memory reads
@@ -859,8 +859,15 @@ k_transfer_set(const SetDesc* __restrict__ descs, const BlkRec* __restrict__ blk
     if (threadIdx.x < sizeof(SetDesc) / 8) dst[threadIdx.x] = src[threadIdx.x];
   }
   __syncthreads();
+  if (v0)
+  {
+    // a sub-range [v0, v0 + nvars) of the set's variables (per-variable pipeline of a host-to-host step): the dense
+    // block of a remote plan is (nvars_of_the_set, ld), variable-major
+    if (threadIdx.x == 0 && sD.dense) sD.dense += (size_t)v0 * sD.ld;
+    __syncthreads();
+  }
   const SetDesc& D = sD;
-  PDk pd{sD.dp}; PRk pr{sD.rp};
+  PDk pd{sD.dp + v0}; PRk pr{sD.rp + v0};
   if (TYPE == 2 && D.type == 1)
   {
     // coincident (type 1) entries ride in the type-2 launch: small plans are launch-latency bound, one launch less
@@ -956,13 +963,13 @@ __global__ void k_block_ranges(int nblocks, const SetDesc* __restrict__ descs, B
 // Receptor-side batched scatter of received dense buffers: fieldR[v][rcv[e]] = in[v*ld + e]
 struct ScatDesc { int n, first_block; const int* rcv; const double* in; long long ld; double* const* rptr; };
 __global__ void __launch_bounds__(256)
-k_scatter_set(const ScatDesc* __restrict__ descs, const int* __restrict__ blk2desc, int nvars)
+k_scatter_set(const ScatDesc* __restrict__ descs, const int* __restrict__ blk2desc, int v0, int nvars)
 {
   const ScatDesc D = descs[blk2desc[blockIdx.x]];
   int e = (blockIdx.x - D.first_block) * blockDim.x + threadIdx.x;
   if (e >= D.n) return;
   int r = D.rcv[e];
-  for (int v = 0; v < nvars; v++) D.rptr[v][r] = D.in[(size_t)v * D.ld + e];
+  for (int v = v0; v < v0 + nvars; v++) D.rptr[v][r] = D.in[(size_t)v * D.ld + e];
 }
 
 // strict cellN rule (commonCellNTransfersStrict.h): product of cellN*(2-cellN)
@@ -1767,22 +1774,24 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
   return 0;
 }
 
-static int planset_run_on(cx_planset* S, cudaStream_t s)
+static int planset_run_on(cx_planset* S, cudaStream_t s, int v0 = 0, int nv = -1)
 {
+  if (nv < 0) nv = S->nvars - v0;
   for (auto& B : S->big)
-    CX_CHECK(cx_plan_launch(B.P, S->nvars, B.dD.data(), B.mode == 0 ? B.dR.data() : nullptr, B.dense, B.ld, B.mode, s));
+    CX_CHECK(cx_plan_launch(B.P, nv, B.dD.data() + v0, B.mode == 0 ? B.dR.data() + v0 : nullptr,
+                            B.dense ? B.dense + (size_t)v0 * B.ld : nullptr, B.ld, B.mode, s));
   if (S->smem > 48 * 1024) CX_CHECK(tiled_smem_optin());
-  if (S->nblocks[0]) { k_transfer_set<1, false><<<S->nblocks[0], 256, 0, s>>>(S->d_descs[0], S->d_blk2desc[0], S->nvars, S->staged); S->ctx->launches++; }
+  if (S->nblocks[0]) { k_transfer_set<1, false><<<S->nblocks[0], 256, 0, s>>>(S->d_descs[0], S->d_blk2desc[0], nv, S->staged, v0); S->ctx->launches++; }
   if (S->nblocks[1])
   {
-    if (S->tiled) k_transfer_set<2, true><<<S->nblocks[1], 256, S->smem, s>>>(S->d_descs[1], S->d_blk2desc[1], S->nvars, S->staged);
-    else k_transfer_set<2, false><<<S->nblocks[1], 256, S->smem, s>>>(S->d_descs[1], S->d_blk2desc[1], S->nvars, S->staged);
+    if (S->tiled) k_transfer_set<2, true><<<S->nblocks[1], 256, S->smem, s>>>(S->d_descs[1], S->d_blk2desc[1], nv, S->staged, v0);
+    else k_transfer_set<2, false><<<S->nblocks[1], 256, S->smem, s>>>(S->d_descs[1], S->d_blk2desc[1], nv, S->staged, v0);
     S->ctx->launches++;
   }
-  if (S->nblocks[2]) { k_transfer_set<3, false><<<S->nblocks[2], 256, S->smem3, s>>>(S->d_descs[2], S->d_blk2desc[2], S->nvars, S->staged); S->ctx->launches++; }
-  if (S->nblocks[3]) { k_transfer_set<5, false><<<S->nblocks[3], 256, S->smem5, s>>>(S->d_descs[3], S->d_blk2desc[3], S->nvars, S->staged); S->ctx->launches++; }
-  if (S->nblocks[4]) { k_transfer_set<44, false><<<S->nblocks[4], 256, 0, s>>>(S->d_descs[4], S->d_blk2desc[4], S->nvars, S->staged); S->ctx->launches++; }
-  if (S->nblocks[5]) { k_transfer_set<22, false><<<S->nblocks[5], 256, 0, s>>>(S->d_descs[5], S->d_blk2desc[5], S->nvars, S->staged); S->ctx->launches++; }
+  if (S->nblocks[2]) { k_transfer_set<3, false><<<S->nblocks[2], 256, S->smem3, s>>>(S->d_descs[2], S->d_blk2desc[2], nv, S->staged, v0); S->ctx->launches++; }
+  if (S->nblocks[3]) { k_transfer_set<5, false><<<S->nblocks[3], 256, S->smem5, s>>>(S->d_descs[3], S->d_blk2desc[3], nv, S->staged, v0); S->ctx->launches++; }
+  if (S->nblocks[4]) { k_transfer_set<44, false><<<S->nblocks[4], 256, 0, s>>>(S->d_descs[4], S->d_blk2desc[4], nv, S->staged, v0); S->ctx->launches++; }
+  if (S->nblocks[5]) { k_transfer_set<22, false><<<S->nblocks[5], 256, 0, s>>>(S->d_descs[5], S->d_blk2desc[5], nv, S->staged, v0); S->ctx->launches++; }
   return 0;
 }
 
@@ -1833,10 +1842,11 @@ int cx_scatterset_create(cx_ctx* ctx, int nsets, int nvars, const int* n, const 
   return 0;
 }
 
-static int scatterset_run_on(cx_scatterset* S, cudaStream_t s)
+static int scatterset_run_on(cx_scatterset* S, cudaStream_t s, int v0 = 0, int nv = -1)
 {
   if (S->nblocks == 0) return 0;
-  k_scatter_set<<<S->nblocks, 256, 0, s>>>(S->d_descs, S->d_blk2desc, S->nvars);
+  if (nv < 0) nv = S->nvars - v0;
+  k_scatter_set<<<S->nblocks, 256, 0, s>>>(S->d_descs, S->d_blk2desc, v0, nv);
   S->ctx->launches++;
   return 0;
 }
@@ -1901,7 +1911,7 @@ int cx_step_create_p2p(cx_ctx* ctx, cx_planset* ps_remote0, cx_planset* ps_remot
   return 0;
 }
 
-static int step_run_p2p(cx_step* S, int niter, int overlap)
+static int step_run_p2p(cx_step* S, int niter, int overlap, int v0, int nv)
 {
   cx_ctx* c = S->ctx;
   cudaStream_t s = c->stream, cs = overlap ? c->comm_stream : c->stream;
@@ -1910,46 +1920,56 @@ static int step_run_p2p(cx_step* S, int niter, int overlap)
   {
     const int iter = ++S->iter, par = iter & 1;
     if (comm && overlap) { CX_CUDA(cudaEventRecord(c->ev_fork, s)); CX_CUDA(cudaStreamWaitEvent(cs, c->ev_fork, 0)); }
-    if (S->ps_remote2[par]) CX_CHECK(planset_run_on(S->ps_remote2[par], comm ? cs : s));
+    if (S->ps_remote2[par]) CX_CHECK(planset_run_on(S->ps_remote2[par], comm ? cs : s, v0, nv));
     if (comm)
     {
       CX_CHECK(cx_p2p_signal_wait_on(cs, S->npeers_p2p, S->d_peer_flags, S->d_my_flags, iter));
       c->launches += 1;
-      if (S->ss2[par]) CX_CHECK(scatterset_run_on(S->ss2[par], cs));
+      if (S->ss2[par]) CX_CHECK(scatterset_run_on(S->ss2[par], cs, v0, nv));
       if (overlap) CX_CUDA(cudaEventRecord(c->ev_join, cs));
     }
-    if (S->ps_local) CX_CHECK(planset_run_on(S->ps_local, s));
+    if (S->ps_local) CX_CHECK(planset_run_on(S->ps_local, s, v0, nv));
     if (comm && overlap) CX_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
   }
   return 0;
 }
 
-int cx_step_run(cx_step* S, int niter, int overlap)
+// One iteration restricted to the variables [v0, v0 + nv) of the step's sets (nv < 0: all from v0).  With the
+// peer-memory transport a sub-range is a complete iteration of the flag protocol (every rank must issue the same
+// sequence of sub-ranges); the NCCL transport ships whole packed buffers, so it only takes the full range.
+int cx_step_run_vars(cx_step* S, int niter, int overlap, int v0, int nv)
 {
-  if (S->p2p) return step_run_p2p(S, niter, overlap);
+  if (S->p2p) return step_run_p2p(S, niter, overlap, v0, nv);
   cx_ctx* c = S->ctx;
   cudaStream_t s = c->stream, cs = overlap ? c->comm_stream : c->stream;
   const bool comm = !S->peers.empty();
+  if (comm && (v0 != 0 || (nv >= 0 && S->ps_local && nv != S->ps_local->nvars)))
+  { cx_set_error("cx_step_run_vars: the NCCL transport exchanges all variables at once"); return -1; }
   for (int it = 0; it < niter; it++)
   {
     // fork at the iteration boundary: everything queued on the main stream so far (the solver's update of the
     // donor fields) precedes the remote plans; the send buffers are free again because the previous
     // iteration's exchange ran on the same communication stream
     if (comm && overlap) { CX_CUDA(cudaEventRecord(c->ev_fork, s)); CX_CUDA(cudaStreamWaitEvent(cs, c->ev_fork, 0)); }
-    if (S->ps_remote) CX_CHECK(planset_run_on(S->ps_remote, comm ? cs : s));
+    if (S->ps_remote) CX_CHECK(planset_run_on(S->ps_remote, comm ? cs : s, v0, nv));
     if (comm)
     {
       CX_CHECK(cx_exchange_on_stream(c, cs, (int)S->peers.size(), S->peers.data(), S->sp.data(), S->sc.data(),
                                      S->rp.data(), S->rc.data()));
-      if (S->ss) CX_CHECK(scatterset_run_on(S->ss, cs));
+      if (S->ss) CX_CHECK(scatterset_run_on(S->ss, cs, v0, nv));
       if (overlap) CX_CUDA(cudaEventRecord(c->ev_join, cs));
     }
-    if (S->ps_local) CX_CHECK(planset_run_on(S->ps_local, s));
+    if (S->ps_local) CX_CHECK(planset_run_on(S->ps_local, s, v0, nv));
     // join: the iteration ends when both the local plans and the scatter of the received values are done
     if (comm && overlap) CX_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
   }
   return 0;
 }
+
+int cx_step_run(cx_step* S, int niter, int overlap) { return cx_step_run_vars(S, niter, overlap, 0, -1); }
+
+// 1 when the step can be split into sub-ranges of variables (single rank, or peer-memory transport)
+int cx_step_splittable(cx_step* S) { return (S->p2p || S->peers.empty()) ? 1 : 0; }
 
 int cx_step_destroy(cx_step* S)
 {

@@ -75,6 +75,12 @@ int cx_zone_set_celln(cx_zone* zone, const double* cellN);
 int cx_zone_info(cx_zone* zone, double bbox[6], int* ncells, int* depth, float* build_ms);
 /* test/debug: candidate cells of one point in the reference's list order
  * (InterpAdt::getListOfCandidateCells, InterpAdt.cpp:658-929), device traversal */
+/* Hooks of a batch of zones: cx_zone_create_noadt uploads coordinates + cellN only, cx_zones_build_adt then builds
+ * the ADTs of all of them concurrently on the device (a 10^6-cell tree is ~100 short dependent launches: alone it
+ * leaves the GPU idle; eight at a time fill it).  The result is the tree cx_zone_create builds. */
+int cx_zone_create_noadt(cx_ctx* ctx, int ni, int nj, int nk, const double* x, const double* y, const double* z,
+                         const double* cellN, cx_zone** out);
+int cx_zones_build_adt(cx_ctx* ctx, int nzones, cx_zone* const* zones);
 int cx_zone_candidates(cx_zone* zone, double x, double y, double z, double alphaTol, int* out, int cap, int* n);
 /* test/debug: copy the ADT replica to the host, 128-byte nodes (see cx_core.cuh AdtNode) */
 int cx_zone_export_adt(cx_zone* zone, void* nodes_out, size_t bytes);
@@ -128,9 +134,16 @@ int cx_set_interp_data_rcv(cx_ctx* ctx, cx_receptors* rcv, int nz, cx_zone* cons
  * returned by the reference at setInterpData.cpp:1272 —
  * rcv[n], donor[n], type[n] (int32), coefs (ragged f64), extrap[ne] per donor
  * zone, ascending receptor position; orphan[no] global. */
+/* cx_set_interp_data_rcv / _dev return as soon as the search is queued; the first accessor of the result waits for it.
+ * cx_ctx_search_slot(ctx, k), k = 1..8: the searches issued next run on side stream k (those of several receptor
+ * zones then overlap on the device); 0: back on the main stream. */
+int cx_ctx_search_slot(cx_ctx* ctx, int slot);
 int cx_result_sizes(cx_result* res, int* cnt, int* ncoef, int* nextrap, int* norphan);
 int cx_result_fetch_zone(cx_result* res, int zone, int* rcv, int* donor, int* type, double* coefs, int* extrap);
 int cx_result_fetch_orphans(cx_result* res, int* orphan);
+/* every list of the call in one go: rcv / donor / type hold sum(cnt) entries (the zones one behind the other, in call
+ * order), coefs sum(ncoef), extrap sum(nextrap), orphan norphan; page-locked destinations make the copies overlap */
+int cx_result_fetch_all(cx_result* res, int* rcv, int* donor, int* type, double* coefs, int* extrap, int* orphan);
 /* per-receptor table (tests): noblk (0 orphan / 1-based zone), type, donor, isext, cf[ncfmax][nrcv] */
 int cx_result_fetch_raw(cx_result* res, int* noblk, int* type, int* dind, int* isext, double* cf);
 /* out[0..7]: search kernel ms, extrapolation ms, nodes visited, candidates tested, ncfmax, ... */
@@ -232,7 +245,29 @@ int cx_step_create_p2p(cx_ctx* ctx, cx_planset* ps_remote0, cx_planset* ps_remot
                        cx_scatterset* ss0, cx_scatterset* ss1, int npeers, int* const* peer_flags, int* d_my_flags,
                        cx_step** out);
 int cx_step_run(cx_step* step, int niter, int overlap);
+/* the same restricted to the variables [v0, v0 + nv) of the step's sets (nv < 0: all from v0).  With the peer-memory
+ * transport (or a single rank) a sub-range is a complete iteration; the NCCL transport only takes the full range
+ * (cx_step_splittable tells). */
+int cx_step_run_vars(cx_step* step, int niter, int overlap, int v0, int nv);
+int cx_step_splittable(cx_step* step);
 int cx_step_destroy(cx_step* step);
+
+/* Host trees in, host trees out: one iteration with its copies, what Connector/Connector/Mpi.py:396-440
+ * (__setInterpTransfers on host arrays, then C._setPartialFields of the received values) does per call.  An item is
+ * the nvars fields of one zone in one direction (dir 0: host -> device before the plans run, 1: device -> host after):
+ * whole arrays of n points (h_idx == NULL) or only the n listed points (packed through a page-locked block; the donor
+ * points a step reads come from cx_plan_mark_donors).  cx_step_run_host pipelines per variable over three streams
+ * (upload of v+1 | plans + exchange of v | download of v-1) and returns when the host arrays hold the result. */
+typedef struct cx_hostio cx_hostio;
+int cx_hostio_create(cx_ctx* ctx, int nvars, cx_hostio** out);
+int cx_hostio_add(cx_hostio* io, int dir, long long n, const int* h_idx, double* const* h_field, double* const* d_field);
+int cx_hostio_bytes(cx_hostio* io, long long* h2d_bytes, long long* d2h_bytes);
+int cx_step_run_host(cx_step* step, cx_hostio* io, int pipelined);
+int cx_hostio_destroy(cx_hostio* io);
+/* mark[node] = 1 for every donor node the plan reads; d_mark: nptsD bytes on the device, zeroed by the caller */
+int cx_plan_mark_donors(cx_plan* plan, unsigned char* d_mark);
+/* dst[e] = src[idx[e]] on the host (OpenMP team): the host side of a sparse upload */
+int cx_host_gather(double* dst, const int* idx, const double* src, long long n);
 
 /* ---- multi-GPU (one process per GPU; NCCL over NVLink) -------------------
  * Replaces the mpi4py pickled isend/recv of Converter/Converter/Mpi4py.py:149-168

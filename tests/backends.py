@@ -20,6 +20,9 @@ class OracleBackend:
         from oracle import oracle as O
         return O.RefZone(ni, nj, nk, x, y, z, cellN, interpDataType=interpDataType)
 
+    def make_zones(self, specs):
+        return [self.make_zone(*sp[:7], interpDataType=sp[7]) for sp in specs]
+
     def set_celln(self, hook, cellN):
         pass
 
@@ -41,6 +44,14 @@ class OracleBackend:
 
     def set_interp_data_rcv(self, rcv, hooks, order, nature, penalty, extrap):
         return self.set_interp_data(rcv.pts[0], rcv.pts[1], rcv.pts[2], hooks, order, nature, penalty, extrap)
+
+    def submit_interp_data_rcv(self, rcv, hooks, order, nature, penalty, extrap):
+        res = self.set_interp_data_rcv(rcv, hooks, order, nature, penalty, extrap)
+
+        class _Done:
+            def fetch(self_):
+                return res
+        return _Done()
 
     def make_plan(self, *a):
         return OraclePlan(*a)

@@ -109,6 +109,14 @@ def main():
         for _ in range(3):          # odd count: both buffer parities of the peer-memory transport are used
             sess.step()
         sess.download()
+        # and one more iteration as a single host-to-host call (sparse uploads, per-variable sub-iterations of the
+        # peer-memory protocol): the trees must not change (the host arrays already hold the transferred values)
+        snap = {z[0]: [C.getFieldArray(z, PREFIX[0] + v).copy() for v in VARS] for z in Internal.getZones(tl)}
+        sess.transfer_host()
+        for z in Internal.getZones(tl):
+            for v, a in zip(VARS, snap[z[0]]):
+                if not np.array_equal(a, C.getFieldArray(z, PREFIX[0] + v)):
+                    print("transfer_host changed", z[0], v); sys.exit(1)
         if rank == 0:
             print("transport=%s" % sess.transport)
         sess.close()

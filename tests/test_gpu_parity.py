@@ -975,6 +975,30 @@ def test_transfer_session_sparse_download_and_c_ordered_fields(ctx, monkeypatch)
             full = sum(a.nbytes for z in Internal.getZones(t) for a in before[z[0]])
             assert nb < full                                             # B's fields were not downloaded whole
         sess.close()
+        # the same iteration as ONE host-to-host call (sparse uploads of the donor points the plans read, per-variable
+        # pipeline over three streams), pipelined or not, on fresh trees
+        for pipelined in (True, False):
+            t, tc, names = build()
+            if c_order:
+                node = Internal.getNodeFromName1(Internal.getNodeFromName1(Internal.getZones(tc)[0], Internal.__FlowSolutionNodes__), names[1])
+                node[1] = np.ascontiguousarray(node[1])
+            sess = Xmpi.TransferSession(t, tc, names, comm=None, ctx=ctx)
+            # poison the device copies of the donor fields: only what transfer_host uploads may be read
+            for lst in sess.dD.values():
+                for d in lst: d.upload(np.full(d.n, np.nan))
+            up, down = sess.transfer_host(pipelined=pipelined)
+            for z, zw in zip(Internal.getZones(t), Internal.getZones(want)):
+                for v in names:
+                    assert np.array_equal(C.getFieldArray(z, 'centers:' + v), C.getFieldArray(zw, 'centers:' + v)), (z[0], v, c_order, pipelined)
+            if not c_order:
+                fullD = sum(C.getFieldArray(z, v).nbytes for z in Internal.getZones(tc) for v in names)
+                assert 0 < up < fullD and 0 < down < full      # B reads a part of A only; B is written on a fringe only
+            up2, down2 = sess.transfer_host(pipelined=pipelined)         # idempotent (donor fields live in tc)
+            assert (up2, down2) == (up, down)
+            for z, zw in zip(Internal.getZones(t), Internal.getZones(want)):
+                for v in names:
+                    assert np.array_equal(C.getFieldArray(z, 'centers:' + v), C.getFieldArray(zw, 'centers:' + v))
+            sess.close()
 
 
 # ---- cellN preparers either side of the path, device vs the reference's routines ----------
