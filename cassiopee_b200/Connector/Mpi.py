@@ -715,7 +715,7 @@ class TransferSession:
             idx = None
             if os.environ.get("CX_SPARSE_H2D", "1") != "0":
                 idx = numpy.flatnonzero(_lib.plan_donor_mask(self.ctx, plans, npts)).astype(numpy.int32)
-                if 2 * idx.size >= npts:
+                if 4 * idx.size >= npts:      # a host gather over most of the array is slower than the plain copy
                     idx = None
             io.add('up', arrs, [d.ptr for d in self.dD[zd[0]]], idx)
         for name, arrs in self.hR.items():

@@ -86,6 +86,7 @@ _SIGS = {
     "cx_hole_fringe_dev": (_i, [_vp] + [_i] * 5 + [_vp, _vp]),
     "cx_host_scatter": (_i, [_vp, _vp, _vp, _ll]),
     "cx_plan_info": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "cx_plan_upload_points": (_i, [_vp, _vp]),
     "cx_plan_sorted_rcv": (_i, [_vp, _vp]),
     "cx_ipc_export": (_i, [_vp, _vp]),
     "cx_ipc_open": (_i, [_vp, _vp, _vp]),
@@ -581,6 +582,12 @@ class Plan:
         n = _i(); ng = _i(); af = _ll(); di = _ll()
         check(lib().cx_plan_info(self.h, ctypes.byref(n), ctypes.byref(ng), ctypes.byref(af), ctypes.byref(di)))
         return dict(n=n.value, ngroups=ng.value, alg_fixed=af.value, distinct=di.value)
+
+    def upload_points(self):
+        """Donor points per variable a host-pointer transfer of this plan moves to the device."""
+        n = _ll()
+        check(lib().cx_plan_upload_points(self.h, ctypes.byref(n)))
+        return n.value
 
     def alg_bytes(self, nvars):
         """B_alg of SURVEY.md 8(d) for one call with nvars variables."""

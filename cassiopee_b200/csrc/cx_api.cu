@@ -738,6 +738,10 @@ struct cx_plan_full {
   std::vector<int> h_rcv;               // original-order receptor indices (host scatter)
   bool rcv_contiguous;                  // h_rcv[e] == h_rcv[0] + e
   std::vector<cudaEvent_t> evk, evd;    // per-variable kernel-done / download-done events (host-pointer pipeline)
+  // sparse upload of the donor fields (host-pointer pipeline, large zones): the donor points the plan reads
+  int didx_state = 0;                   // 0: not looked at yet, 1: sparse (h_didx / d_didx), 2: whole fields
+  std::vector<int> h_didx; int* d_didx = nullptr;
+  double* h_stage = nullptr; size_t hstage_cap = 0;   // pinned, nvars x h_didx.size()
 };
 
 int cx_plan_create(cx_ctx* c, int imd, int jmd, int kmd, long long nptsR, int n, const int* donor, const int* rcv,
@@ -837,7 +841,8 @@ static void cx_ctx_free_transfer_scratch(cx_ctx* c)
   delete (cx_field_cache*)c->fcache; c->fcache = nullptr;
   if (c->d_tfields) cudaFree(c->d_tfields);
   if (c->d_tdense) cudaFree(c->d_tdense);
-  c->d_tfields = c->d_tdense = nullptr; c->tfields_cap = c->tdense_cap = 0;
+  if (c->d_tstage) cudaFree(c->d_tstage);
+  c->d_tfields = c->d_tdense = c->d_tstage = nullptr; c->tfields_cap = c->tdense_cap = c->tstage_cap = 0;
 }
 
 static int pipeline_events(cx_plan_full* F, int nvars)
@@ -856,6 +861,47 @@ static int pipeline_events(cx_plan_full* F, int nvars)
 // on the device, in their dense blocks, before they are downloaded.
 struct RotSpec { int dirR; double ct, st; int ntrip; const int* trip; };
 
+namespace {
+__global__ void k_unpack1(int n, const double* __restrict__ in, const int* __restrict__ idx, double* __restrict__ out)
+{
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) out[idx[e]] = in[e];
+}
+}
+
+// Which donor points does the plan read?  For a large donor zone of which the plan reads less than 1/4 (fringe
+// plans), only those cross the bus: gathered on the host by an OpenMP team into a page-locked block, copied, and
+// stored by index into the device copy of the field (the rest of that copy is never read).  Decided once per plan
+// (mark kernel + one mask download + a host compaction).  CX_SPARSE_H2D=0: never.  Measured on C2a, where the plan
+// reads 53 % of the background: 19.7 ms per call against 17.5 ms with whole fields (gpurun_out/r3_e2e_*.json) -- the
+// host gather walks the whole array at less than the DMA engine's rate -- hence the 1/4.
+static int plan_donor_list(cx_plan_full* F)
+{
+  cx_plan* P = &F->P; cx_ctx* c = P->ctx;
+  F->didx_state = 2;
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("CX_SPARSE_H2D"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
+  if (!enabled || P->nptsD < (1 << 20)) return 0;
+  unsigned char* d_mark;
+  CX_MALLOC(d_mark, (size_t)P->nptsD, c->stream);
+  CX_CUDA(cudaMemsetAsync(d_mark, 0, (size_t)P->nptsD, c->stream));
+  CX_CHECK(cx_plan_mark_donors(P, d_mark));
+  std::vector<unsigned char> mark((size_t)P->nptsD);
+  CX_CUDA(cudaMemcpyAsync(mark.data(), d_mark, (size_t)P->nptsD, cudaMemcpyDeviceToHost, c->stream));
+  CX_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFreeAsync(d_mark, c->stream);
+  size_t nd = 0;
+  for (size_t i = 0; i < mark.size(); i++) nd += mark[i];
+  if (nd == 0 || 4 * nd >= (size_t)P->nptsD) return 0;
+  F->h_didx.resize(nd);
+  size_t k = 0;
+  for (size_t i = 0; i < mark.size(); i++) if (mark[i]) F->h_didx[k++] = (int)i;
+  CX_CUDA(cudaMalloc(&F->d_didx, sizeof(int) * nd));
+  CX_CHECK(cx_upload(c, F->d_didx, F->h_didx.data(), sizeof(int) * nd));
+  F->didx_state = 1;
+  return 0;
+}
+
 // dst[v]: host destination of variable v's dense (n) block
 static int transfer_pipeline(cx_plan_full* F, int nvars, const double* const* fieldD, double* const* dst,
                              const RotSpec* rot = nullptr)
@@ -868,6 +914,14 @@ static int transfer_pipeline(cx_plan_full* F, int nvars, const double* const* fi
   cx_field_cache* FC = (cx_field_cache*)c->fcache;
   const bool batch = FC && FC->on;
   if (!batch) CX_CHECK(ensure(&c->d_tfields, &c->tfields_cap, sizeof(double) * per * nvars, false));
+  if (!batch && F->didx_state == 0) CX_CHECK(plan_donor_list(F));
+  const bool sparse = !batch && F->didx_state == 1;
+  const size_t nd = F->h_didx.size();
+  if (sparse)
+  {
+    CX_CHECK(ensure(&F->h_stage, &F->hstage_cap, sizeof(double) * nd * nvars, true));
+    CX_CHECK(ensure(&c->d_tstage, &c->tstage_cap, sizeof(double) * nd * nvars, false));
+  }
   CX_CHECK(ensure(&c->d_tdense, &c->tdense_cap, sizeof(double) * n * nvars, false));
   double* const d_dense = c->d_tdense;
   CX_CHECK(pipeline_events(F, nvars));
@@ -897,6 +951,16 @@ static int transfer_pipeline(cx_plan_full* F, int nvars, const double* const* fi
         FC->bytes += sizeof(double) * per;
         FC->uploads++;
       }
+    }
+    else if (sparse)
+    {
+      // the team gathers variable v while the copies of the variables before it are on the bus
+      dv = c->d_tfields + per * v;
+      double* hs = F->h_stage + nd * v; double* ds = c->d_tstage + nd * v;
+      cx_host_gather(hs, F->h_didx.data(), fieldD[v], (long long)nd);
+      CX_CUDA(cudaMemcpyAsync(ds, hs, sizeof(double) * nd, cudaMemcpyHostToDevice, sa));
+      k_unpack1<<<cx_grid((long long)nd, 256), 256, 0, sa>>>((int)nd, ds, F->d_didx, dv);
+      c->launches++;
     }
     else
     {
@@ -1344,6 +1408,16 @@ int cx_plan_info(cx_plan* P, int* n, int* ngroups, long long* alg_fixed, long lo
   return 0;
 }
 
+// donor points per variable the host-pointer transfers of this plan move to the device: the whole zone, or the
+// points the plan reads when the sparse upload applies (decided here if no transfer has run yet)
+int cx_plan_upload_points(cx_plan* P, long long* npts)
+{
+  cx_plan_full* F = (cx_plan_full*)P;
+  if (F->didx_state == 0 && P->n > 0) CX_CHECK(plan_donor_list(F));
+  *npts = F->didx_state == 1 ? (long long)F->h_didx.size() : (long long)P->nptsD;
+  return 0;
+}
+
 int cx_plan_destroy(cx_plan* P)
 {
   if (!P) return 0;
@@ -1351,6 +1425,8 @@ int cx_plan_destroy(cx_plan* P)
   for (auto& G : P->groups) { cudaFree(G.d_cf); if (G.d_tiles) cudaFree(G.d_tiles); if (G.d_pat) cudaFree(G.d_pat); }
   cudaFree(P->d_donor); cudaFree(P->d_rcv); cudaFree(P->d_pos); cudaFree(P->d_seq);
   if (F->h_dense) cudaFreeHost(F->h_dense);
+  if (F->h_stage) cudaFreeHost(F->h_stage);
+  if (F->d_didx) cudaFree(F->d_didx);
   for (cudaEvent_t e : F->evk) cudaEventDestroy(e);
   for (cudaEvent_t e : F->evd) cudaEventDestroy(e);
   delete F;

@@ -44,6 +44,7 @@ struct cx_ctx {
   // donor fields uploaded during a batch of transfers (cx_batch_begin .. cx_batch_end), keyed by host pointer
   double* d_tfields; size_t tfields_cap;
   double* d_tdense; size_t tdense_cap;
+  double* d_tstage; size_t tstage_cap;   // packed donor values of a sparse upload
   void* fcache;   // cx_field_cache*
   // free page-locked blocks (CX_PIN_BLOCK bytes each) for the zone tables and the counts of searches in flight
   void* pin_pool;   // std::vector<void*>*

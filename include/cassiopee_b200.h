@@ -206,6 +206,10 @@ int cx_host_scatter(double* dst, const int* idx, const double* src, long long n)
  * by a plan set with mode 2 */
 int cx_plan_sorted_rcv(cx_plan* plan, int* out);
 int cx_plan_info(cx_plan* plan, int* n, int* ngroups, long long* alg_fixed, long long* distinct);
+/* donor points per variable a host-pointer transfer (cx_transfer / cx_transferD) of this plan uploads: for a donor zone
+ * of at least 2^20 points of which the plan reads less than 1/4, only the points it reads (gathered on the host into a
+ * page-locked block, stored by index on the device); else the whole zone.  CX_SPARSE_H2D=0 disables it. */
+int cx_plan_upload_points(cx_plan* plan, long long* npts);
 int cx_plan_destroy(cx_plan* plan);
 
 /* ---- batched transfers: every plan of a rank in one launch ------------------

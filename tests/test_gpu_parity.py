@@ -278,6 +278,56 @@ def test_transfer_synthetic_plans_staged_and_gather(ctx, dims, density):
             assert np.array_equal(dense.download().reshape(nvars, n), O.transferD(fD, ni, nj, dnr, typ, cf))
 
 
+def test_host_pointer_transfer_sparse_upload(ctx, monkeypatch):
+    """cx_transfer on a donor zone of more than 2^20 points of which the plan reads a part: only the donor points of
+    the stencils cross the bus (host gather, packed copy, device store by index); same fields bit for bit as the
+    reference loops and as the whole-field upload, for type 1/2/3/5 entries and stencils on the zone's last nodes."""
+    from cassiopee_b200 import _lib
+    from oracle import oracle as O
+    ni, nj, nk = 129, 97, 88
+    nD = ni * nj * nk
+    assert nD >= 1 << 20
+    rng = np.random.default_rng(12)
+    n = 90000
+    nR = 2 * n + 11
+    typ = rng.choice(np.array([1, 2, 2, 2, 3, 5], np.int32), n).astype(np.int32)
+    o = np.where(typ == 1, 1, typ)
+    # receptors fed from a slab of the donor zone (k < 16) plus a few stencils that end on the very last node
+    i = (rng.random(n) * (ni - o + 1)).astype(np.int64); j = (rng.random(n) * (nj - o + 1)).astype(np.int64)
+    k = (rng.random(n) * (16 - o + 1)).astype(np.int64)
+    i[:4] = ni - o[:4]; j[:4] = nj - o[:4]; k[:4] = nk - o[:4]
+    dnr = (i + ni * j + ni * nj * k).astype(np.int32)
+    rcv = np.sort(rng.choice(nR, n, replace=False)).astype(np.int32)
+    ncf = np.where(typ == 1, 1, np.where(typ == 2, 8, np.where(typ == 3, 9, 15)))
+    cf = rng.standard_normal(int(ncf.sum()))
+    fD = [rng.standard_normal(nD) for _ in range(3)]
+    want = [np.full(nR, -7.) for _ in range(3)]
+    O.transfer(fD, want, ni, nj, rcv, dnr, typ, cf)
+    plan = _lib.Plan(ctx, ni, nj, nk, nR, dnr, rcv, typ, cf)
+    up = plan.upload_points()
+    assert 0 < up < 0.25 * nD                                  # the slab only
+    for rep in range(2):                                       # second call: the lists and staging blocks are reused
+        got = [np.full(nR, -7.) for _ in range(3)]
+        plan.transfer(fD, got)
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b)
+    assert np.array_equal(plan.transferD(fD), O.transferD(fD, ni, nj, dnr, typ, cf))
+    monkeypatch.setenv("CX_SPARSE_H2D", "0")                   # read once per process: only new plans could differ
+    # a plan that reads most of the zone keeps the whole-field upload
+    k2 = (rng.random(n) * (nk - o + 1)).astype(np.int64)
+    i2 = (np.arange(n) * 7 % (ni - 5)).astype(np.int64); j2 = (np.arange(n) * 13 % (nj - 5)).astype(np.int64)
+    typ2 = np.full(n, 5, np.int32)
+    k2 = (np.arange(n) * 3 % (nk - 5)).astype(np.int64)
+    dnr2 = (i2 + ni * j2 + ni * nj * k2).astype(np.int32)
+    cf2 = rng.standard_normal(15 * n)
+    plan2 = _lib.Plan(ctx, ni, nj, nk, nR, dnr2, rcv, typ2, cf2)
+    got = [np.full(nR, -7.) for _ in range(3)]; want2 = [np.full(nR, -7.) for _ in range(3)]
+    plan2.transfer(fD, got)
+    O.transfer(fD, want2, ni, nj, rcv, dnr2, typ2, cf2)
+    for a, b in zip(got, want2):
+        assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("order", [2, 3, 4])
 def test_interpcart_donors(ctx, order):
     """interpDataType=0 (regular Cartesian donors located in closed form, K_INTERP::InterpCart): single donor,
