@@ -231,6 +231,214 @@ k_extrap(const int* __restrict__ nlist_p, const int* __restrict__ list, const do
   if (gstats) warp_add_stats(gstats, st);
 }
 
+// ---- extrapolation, second form: the walks of 16 receptors run side by side -------------------------------------
+// In k_extrap lane 0 walks the tree while 31 lanes wait: 63 % of the issued instructions ran on one lane (ncu,
+// profiles/r03_*: 12 active threads per instruction, fp64 pipe 11 % busy, 8 resident warps per SM at 228 registers).
+// Here a warp takes a group of CX_XG receptors and ONE donor zone: lanes 0..CX_XG-1 walk their own receptor's tree
+// and buffer up to CX_XB candidates each in shared memory (in the reference's list order), then the whole warp
+// evaluates the buffered candidates of one receptor after the other, 32 at a time, and replays the reference's
+// sequential fold (InterpAdt.cpp:1113-1147) in candidate order; rounds repeat until every walk is exhausted.  The
+// per-(receptor, zone) winner goes to a table; k_extrap_combine then runs the cross-zone choice of
+// getExtrapolationCell (Interp.cpp:282-360) zone after zone, exactly as k_extrap does.
+#define CX_XG 16
+#define CX_XB 64
+struct ExtrapZoneRes { int found, ic, jc, kc; double cf[8]; };   // per (zone, failing receptor of the chunk)
+
+__global__ void __launch_bounds__(128)
+k_extrap_zone(const int* __restrict__ nlist_p, const int* __restrict__ list, int chunk0, int chunkN,
+              const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, int nz,
+              const ZoneView* __restrict__ zones, int nature, ExtrapZoneRes* __restrict__ out, unsigned long long* gstats)
+{
+  __shared__ int s_buf[4][CX_XG][CX_XB];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nlist = min(*nlist_p, chunk0 + chunkN);
+  const int ngroups = (max(nlist - chunk0, 0) + CX_XG - 1) / CX_XG;
+  const long long nitems = (long long)ngroups * nz;
+  SearchStats st; st.nvisit = 0; st.ncand = 0; st.ntet = 0;
+  const double constraint = 40.;
+  const double alphaTol = fmax((2 * constraint - 5.) * 0.1, 0.);
+  for (long long item = (long long)blockIdx.x * 4 + w; item < nitems; item += (long long)gridDim.x * 4)   // warp-uniform
+  {
+    const int g = (int)(item / nz), noz = (int)(item - (long long)g * nz);
+    const ZoneView& Z = zones[noz];
+    const bool cart = Z.topo == 0;
+    const int a = chunk0 + g * CX_XG + lane;
+    const bool mine = lane < CX_XG && a < nlist;
+    double x = 0., y = 0., z = 0.;
+    if (mine) { const int r = list[a]; x = xr[r]; y = yr[r]; z = zr[r]; }
+    // walk state of this lane's receptor
+    AdtQuery q;
+    int clo[3] = {0, 0, 0}, chi[3] = {0, 0, 0}, ctotal = 0, cbase = 0;
+    bool walking = mine;
+    if (mine)
+    {
+      if (cart) { ctotal = cart_candidate_box(Z, x, y, z, alphaTol, clo, chi); if (ctotal == 0) walking = false; }
+      else if (zone_reject(Z, x, y, z, alphaTol)) walking = false;
+      else query_init(q, Z, x, y, z, alphaTol);
+    }
+    // fold state of this lane's receptor (InterpAdt.cpp:1113-1147)
+    double saved_sum = CX_MAXF, saved_diff = CX_MAXF;
+    int found = 0, icsav = 0, jcsav = 0, kcsav = 0, ncand = 0;
+    double cfs[8];
+    for (int i = 0; i < 8; i++) cfs[i] = 0.;
+    const int ni = Z.ni, nij = Z.ni * Z.nj;
+    while (true)
+    {
+      // every walking lane buffers its next candidates, in list order
+      int cnt = 0;
+      if (walking)
+      {
+        if (cart)
+        {
+          // InterpCart::searchExtrapolationCellCart: the cells of a small box around the point, k-outer / i-inner
+          const int bi = chi[0] - clo[0] + 1, bj = chi[1] - clo[1] + 1;
+          while (cnt < CX_XB && cbase < ctotal)
+          {
+            const int c = cbase++;
+            const int k = c / (bi * bj), j = (c - k * bi * bj) / bi, i = c - j * bi - k * bi * bj;
+            s_buf[w][lane][cnt++] = (i + clo[0] - 1) + (j + clo[1] - 1) * ni + (k + clo[2] - 1) * nij;
+          }
+          if (cbase >= ctotal) walking = false;
+        }
+        else
+        {
+          int c, nid, nvisit = 0;
+          while (cnt < CX_XB && (c = query_next(q, Z.nodes, &nid, &nvisit)) >= 0) s_buf[w][lane][cnt++] = c;
+          st.nvisit += nvisit;
+          if (cnt < CX_XB) walking = false;          // traversal exhausted
+        }
+      }
+      __syncwarp();
+      unsigned have = __ballot_sync(0xffffffffu, cnt > 0);
+      if (have == 0) { if (__ballot_sync(0xffffffffu, walking) == 0) break; else continue; }
+      // the warp evaluates the buffered candidates of one receptor after the other
+      while (have)
+      {
+        const int rl = __ffs(have) - 1; have &= have - 1;
+        const int n_rl = __shfl_sync(0xffffffffu, cnt, rl);
+        const double px = __shfl_sync(0xffffffffu, x, rl), py = __shfl_sync(0xffffffffu, y, rl), pz = __shfl_sync(0xffffffffu, z, rl);
+        double f_sum = __shfl_sync(0xffffffffu, saved_sum, rl), f_diff = __shfl_sync(0xffffffffu, saved_diff, rl);
+        int f_new = 0, f_i = 0, f_j = 0, f_k = 0;
+        double f_cf[8];
+        for (int m = 0; m < 8; m++) f_cf[m] = 0.;
+        for (int b0 = 0; b0 < n_rl; b0 += 32)
+        {
+          const int nb = min(32, n_rl - b0);
+          int ret = 0, i = 0, j = 0, k = 0;
+          double sum = 0., diff = CX_MAXF, cft[8];
+          if (lane < nb)
+          {
+            const int c = s_buf[w][rl][b0 + lane];
+            k = c / nij; j = (c - k * nij) / ni; i = c - j * ni - k * nij;
+            k++; j++; i++;
+            ret = extrap_coeff_for_cell(Z, px, py, pz, i, j, k, cft, nature, constraint, diff);
+            sum = fabs(cft[0]) + fabs(cft[1]) + fabs(cft[2]) + fabs(cft[3]) + fabs(cft[4]) + fabs(cft[5]) + fabs(cft[6]) +
+                  fabs(cft[7]);
+          }
+          __syncwarp();
+          for (int l = 0; l < nb; l++)
+          {
+            const int rl_ = __shfl_sync(0xffffffffu, ret, l);
+            const double sl = __shfl_sync(0xffffffffu, sum, l);
+            const double dl = __shfl_sync(0xffffffffu, diff, l);
+            if (rl_ == 1 && sl < f_sum + 1.e-6 && dl < f_diff)      // uniform across the warp
+            {
+              f_diff = dl; f_sum = sl; f_new = 1;
+              f_i = __shfl_sync(0xffffffffu, i, l); f_j = __shfl_sync(0xffffffffu, j, l); f_k = __shfl_sync(0xffffffffu, k, l);
+              for (int m = 0; m < 8; m++) f_cf[m] = __shfl_sync(0xffffffffu, cft[m], l);
+            }
+          }
+        }
+        if (lane == rl)
+        {
+          ncand += n_rl;
+          if (f_new)
+          {
+            saved_sum = f_sum; saved_diff = f_diff; found = 1; icsav = f_i; jcsav = f_j; kcsav = f_k;
+            for (int m = 0; m < 8; m++) cfs[m] = f_cf[m];
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (mine)
+    {
+      st.ncand += ncand;
+      ExtrapZoneRes& o = out[(size_t)noz * chunkN + (size_t)(a - chunk0)];
+      o.found = (ncand > 0) ? found : 0; o.ic = icsav; o.jc = jcsav; o.kc = kcsav;
+      for (int m = 0; m < 8; m++) o.cf[m] = cfs[m];
+    }
+  }
+  if (gstats) warp_add_stats(gstats, st);
+}
+
+// K_INTERP::getExtrapolationCell (Interp.cpp:282-360: constraint=40, extrapOrder=1, order forced to O2CF): the
+// choice between the donor zones, zone after zone, from the per-zone winners of k_extrap_zone
+__global__ void k_extrap_combine(const int* __restrict__ nlist_p, const int* __restrict__ list, int chunk0, int chunkN,
+                                 int nz, const ZoneView* __restrict__ zones, int penalty,
+                                 const ExtrapZoneRes* __restrict__ res, RcvTable T)
+{
+  const int nlist = min(*nlist_p, chunk0 + chunkN);
+  for (int a = chunk0 + blockIdx.x * blockDim.x + threadIdx.x; a < nlist; a += gridDim.x * blockDim.x)
+  {
+    const int r = list[a];
+    double best = CX_MAXF, sumCoefMin = CX_MAXF;
+    int noblk = 0, type = 0, dind = -1;
+    double cf[8], tcf[8];
+    for (int i = 0; i < 8; i++) { cf[i] = 0.; tcf[i] = 0.; }
+    for (int noz = 0; noz < nz; noz++)
+    {
+      const ExtrapZoneRes& o = res[(size_t)noz * chunkN + (size_t)(a - chunk0)];
+      if (o.found < 1) continue;
+      const ZoneView& Z = zones[noz];
+      for (int i = 0; i < 8; i++) tcf[i] = o.cf[i];
+      const int ic = o.ic - 1, jc = o.jc - 1, kc = o.kc - 1;
+      if (Z.nk == 1)
+      {
+        // 2-D donor: type 22, coefficients folded onto the plane (Interp2.cpp:125-136, commonTypesForExtrapAndInterp.h:72-105)
+        int isBorder2 = (ic == 0 || ic == Z.ni - 2 || jc == 0 || jc == Z.nj - 2);
+        int tind2 = ic + jc * Z.ni;
+        for (int i = 0; i < 4; i++) { tcf[i] += tcf[i + 4]; tcf[i + 4] = 0.; }
+        double vol2 = cell_area_2d(Z, tind2);
+        if (penalty == 1 && isBorder2 == 1) vol2 += 1.e3;
+        if (vol2 < best + CX_EPS_GEOM)
+        {
+          double sumCf = 0.;
+          for (int i = 0; i < 4; i++) sumCf += fabs(tcf[i]);
+          if (sumCf < sumCoefMin)
+          {
+            sumCoefMin = sumCf;
+            best = vol2; type = 22; dind = tind2; noblk = noz + 1;
+            for (int i = 0; i < 4; i++) { cf[i] = tcf[i] + tcf[i + 4]; cf[i + 4] = 0.; }
+          }
+        }
+        continue;
+      }
+      int isBorder = (ic == 0 || ic == Z.ni - 2 || jc == 0 || jc == Z.nj - 2 || kc == 0 || kc == Z.nk - 2);
+      int tind = ic + jc * Z.ni + kc * Z.ni * Z.nj;
+      double vol = cell_volume(Z, tind);
+      if (penalty == 1 && isBorder == 1) vol += 1.e3;
+      if (vol < best + CX_EPS_GEOM)
+      {
+        double sumCf = 0.;
+        for (int i = 0; i < 8; i++) sumCf += fabs(tcf[i]);
+        if (sumCf < sumCoefMin)
+        {
+          sumCoefMin = sumCf;
+          best = vol; type = 2; dind = tind; noblk = noz + 1;
+          for (int i = 0; i < 8; i++) cf[i] = tcf[i];
+        }
+      }
+    }
+    if (noblk > 0)
+    {
+      collapse_type2(zones[noblk - 1], type, dind, cf);
+      T.noblk[r] = noblk; T.type[r] = type; T.dind[r] = dind; T.isext[r] = 1;
+      for (int i = 0; i < 8; i++) T.cf[(size_t)i * T.n + r] = cf[i];
+    }
+  }
+}
+
 __device__ __forceinline__ int ncf_of_type(int t)
 { // SIZECF, Connector/Connector/connector.h:27-37 (structured donors)
   return t == 1 ? 1 : t == 2 ? 8 : t == 3 ? 9 : t == 5 ? 15 : t == 44 ? 12 : t == 22 ? 4 : 0;
@@ -396,9 +604,33 @@ int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, co
     CX_MALLOC(d_nfail, sizeof(int), s);
     CX_CUDA(cudaMemsetAsync(d_nfail, 0, sizeof(int), s));
     k_collect_fail<<<cx_grid(n, TB2), TB2, 0, s>>>(n, R->d_noblk, d_fail, d_nfail);
-    const int gx = std::max(1, std::min(cx_grid(n, 4), ctx->sm_count * 16));
-    k_extrap<<<gx, 128, 0, s>>>(d_nfail, d_fail, d_xr, d_yr, d_zr, nz, d_zones, nature, penalty, T, d_stats);
-    ctx->launches += 2;
+    static int xmode = -1;       // CX_EXTRAP=warp: the first form (one warp per receptor, lane 0 walks); default: grouped
+    if (xmode < 0) { const char* e = getenv("CX_EXTRAP"); xmode = (e && e[0] == 'w') ? 1 : 0; }
+    if (xmode == 1)
+    {
+      const int gx = std::max(1, std::min(cx_grid(n, 4), ctx->sm_count * 16));
+      k_extrap<<<gx, 128, 0, s>>>(d_nfail, d_fail, d_xr, d_yr, d_zr, nz, d_zones, nature, penalty, T, d_stats);
+      ctx->launches += 2;
+    }
+    else
+    {
+      // the failing receptors go through in chunks of at most CHUNK (the per-(zone, receptor) table is sized by the
+      // chunk, not by the unknown number of failures: the count stays on the device, chunks beyond it do nothing)
+      const int CHUNK = (int)std::min<long long>(n, std::max<long long>(1 << 16, (512ll << 20) / ((long long)sizeof(ExtrapZoneRes) * nz)));
+      ExtrapZoneRes* d_res;
+      CX_MALLOC(d_res, sizeof(ExtrapZoneRes) * (size_t)CHUNK * nz, s);
+      const long long items = (long long)((CHUNK + CX_XG - 1) / CX_XG) * nz;
+      const int gz = (int)std::max(1ll, std::min((items + 3) / 4, (long long)ctx->sm_count * 32));
+      const int gc = std::max(1, std::min(cx_grid(CHUNK, 128), ctx->sm_count * 8));
+      for (int c0 = 0; c0 < n; c0 += CHUNK)
+      {
+        k_extrap_zone<<<gz, 128, 0, s>>>(d_nfail, d_fail, c0, CHUNK, d_xr, d_yr, d_zr, nz, d_zones, nature, d_res, d_stats);
+        k_extrap_combine<<<gc, 128, 0, s>>>(d_nfail, d_fail, c0, CHUNK, nz, d_zones, penalty, d_res, T);
+        ctx->launches += 2;
+      }
+      ctx->launches += 1;
+      cudaFreeAsync(d_res, s);
+    }
     cudaFreeAsync(d_fail, s); cudaFreeAsync(d_nfail, s);
   }
   CX_CUDA(cudaEventRecord(R->ev[3], s));
