@@ -734,7 +734,14 @@ class TransferSession:
         if getattr(self, '_hostio', None) is None:
             self._hostio = self._setup_hostio() or False
         if self._hostio is False:           # some field is not a Fortran-flat float64 array: plain sequence
-            self.upload_donor_fields(); self.step(); nb = self.download()
+            self.upload_donor_fields()
+            if pipelined and self._step.splittable():
+                # the same sequence of sub-iterations as the ranks that pipeline (the flag protocol counts them)
+                for v in range(len(self.variables)):
+                    self._step.run_vars(v, 1)
+            else:
+                self.step()
+            nb = self.download()
             return self.h2d_bytes, nb
         self._step.run_host(self._hostio, pipelined)
         return self._hostio.bytes()

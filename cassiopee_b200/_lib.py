@@ -876,7 +876,24 @@ def ipc_close(desc):
     lib().cx_ipc_close(ctypes.c_char_p(desc))
 
 
-class StepP2P:
+class _StepRun:
+    """What both kinds of step (cx_step) can run."""
+
+    def run(self, niter=1, overlap=True):
+        check(lib().cx_step_run(self.h, int(niter), 1 if overlap else 0))
+
+    def run_host(self, io, pipelined=True):
+        check(lib().cx_step_run_host(self.h, io.h, 1 if pipelined else 0))
+
+    def run_vars(self, v0, nv, overlap=True):
+        """One iteration restricted to the variables [v0, v0 + nv) (cx_step_run_vars)."""
+        check(lib().cx_step_run_vars(self.h, 1, 1 if overlap else 0, int(v0), int(nv)))
+
+    def splittable(self):
+        return bool(lib().cx_step_splittable(self.h))
+
+
+class StepP2P(_StepRun):
     """One solver iteration of a rank with the peer-memory transport (cx_step_create_p2p): remote plans store into
     the peers' IPC-mapped receive buffers, flags instead of messages, scatter, overlapped with the local plans."""
 
@@ -891,17 +908,9 @@ class StepP2P:
         self.h = h
         self._fin = weakref.finalize(self, lib().cx_step_destroy, h)
 
-    def run(self, niter=1, overlap=True):
-        check(lib().cx_step_run(self.h, int(niter), 1 if overlap else 0))
-
-    def run_host(self, io, pipelined=True):
-        check(lib().cx_step_run_host(self.h, io.h, 1 if pipelined else 0))
-
-    def run_host(self, io, pipelined=True):
-        check(lib().cx_step_run_host(self.h, io.h, 1 if pipelined else 0))
 
 
-class Step:
+class Step(_StepRun):
     """One iteration of a rank (cx_step): remote plans -> NCCL exchange + scatter (second
     stream) overlapped with the local plans."""
 
@@ -918,8 +927,3 @@ class Step:
         self.h = h
         self._fin = weakref.finalize(self, lib().cx_step_destroy, h)
 
-    def run(self, niter=1, overlap=True):
-        check(lib().cx_step_run(self.h, int(niter), 1 if overlap else 0))
-
-    def run_host(self, io, pipelined=True):
-        check(lib().cx_step_run_host(self.h, io.h, 1 if pipelined else 0))

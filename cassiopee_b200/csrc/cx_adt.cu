@@ -70,9 +70,14 @@ __global__ void k_claim(int L, int nact_known, const int* __restrict__ cnt, cons
   int leader = __ffs(grp) - 1;
   if ((threadIdx.x & 31) == leader)
   {
-    int* slot = right ? &B.nodes[p].right : &B.nodes[p].left;
-    atomicMin(slot, mn);
+    atomicMin(&B.child[2 * (size_t)p + (right ? 1 : 0)], mn);
   }
+}
+
+__global__ void k_set_children(int ncells, BuildView B)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ncells) adt_set_children(B, c);
 }
 
 // subtree boxes of the cells placed at one depth: `list` = the cells k_resolve placed at that depth (any order)
@@ -182,6 +187,8 @@ struct AdtBuild {
     CX_MALLOC(B.br, n, s);
     CX_MALLOC(B.depth, sizeof(int) * n, s);
     CX_CUDA(cudaMemsetAsync(B.depth, 0, sizeof(int) * n, s));
+    CX_MALLOC(B.child, sizeof(int) * 2 * n, s);
+    CX_CUDA(cudaMemsetAsync(B.child, 0x7f, sizeof(int) * 2 * n, s));      // 0x7f7f7f7f: larger than any cell id
     CX_MALLOC(S.actA, sizeof(int) * n, s);
     CX_MALLOC(S.actB, sizeof(int) * n, s);
     CX_MALLOC(d_placed, sizeof(int) * n, s);
@@ -256,6 +263,8 @@ struct AdtBuild {
   int subtree()
   {
     cudaFreeAsync(d_cnt, s); cudaFreeAsync(d_pcnt, s);
+    k_set_children<<<cx_grid(z->ncells, TB), TB, 0, s>>>(z->ncells, B);
+    ctx->launches++;
     for (int lv = depth - 1; lv >= 1; lv--)
     {
       const int first = n0 - cntAll[lv - 1], count = cntAll[lv - 1] - cntAll[lv];
@@ -287,7 +296,7 @@ struct AdtBuild {
   void release()
   {
     if (!z) return;
-    cudaFreeAsync(B.keys, s); cudaFreeAsync(B.lo, s); cudaFreeAsync(B.hi, s); cudaFreeAsync(B.cur, s); cudaFreeAsync(B.br, s); cudaFreeAsync(B.depth, s);
+    cudaFreeAsync(B.keys, s); cudaFreeAsync(B.lo, s); cudaFreeAsync(B.hi, s); cudaFreeAsync(B.cur, s); cudaFreeAsync(B.br, s); cudaFreeAsync(B.depth, s); cudaFreeAsync(B.child, s);
     cudaFreeAsync(S.actA, s); cudaFreeAsync(S.actB, s); cudaFreeAsync(d_placed, s);
     if (h_cnt) { cx_pin_give(ctx, h_cnt, h_own); h_cnt = nullptr; }
     if (ev0) cudaEventDestroy(ev0);

@@ -42,6 +42,7 @@ void* emu_zone_create(int ni, int nj, int nk, const double* x, const double* y, 
   std::vector<int> cur(n, 0), dep(n, 0); std::vector<unsigned char> br(n, 0);
   BuildView B; B.keys = keys.data(); B.lo = lo.data(); B.hi = hi.data(); B.cur = cur.data(); B.br = br.data(); B.depth = dep.data();
   B.nodes = Z->nodes.data(); B.ncells = n;
+  std::vector<int> child(2 * (size_t)n, CX_NULL); B.child = child.data();
   for (int d = 0; d < 6; d++) { B.zb.lo[d] = bbox[d % 3]; B.zb.hi[d] = bbox[3 + d % 3]; }
   for (int c = 0; c < n; c++) adt_cell_keys(ni, nj, nk, x, y, z, c, n, B.keys, B.nodes, bbox, bbox[2], bbox[5]);
   freeze_node(B.nodes[0], 0, B.zb.lo[0], B.zb.hi[0]);
@@ -55,7 +56,7 @@ void* emu_zone_create(int ni, int nj, int nk, const double* x, const double* y, 
     for (int c : act)
     {
       int p, right; adt_claim(B, L, c, p, right);
-      int* slot = right ? &B.nodes[p].right : &B.nodes[p].left;
+      int* slot = &B.child[2 * (size_t)p + (right ? 1 : 0)];
       if (c < *slot) *slot = c;   // atomicMin
     }
     next.clear();
@@ -64,6 +65,7 @@ void* emu_zone_create(int ni, int nj, int nk, const double* x, const double* y, 
     L++;
   }
   Z->depth = depth;
+  for (int c = 0; c < n; c++) adt_set_children(B, c);
   for (int lv = depth - 1; lv >= 0; lv--)
     for (int c = 0; c < n; c++) if (dep[c] == lv) adt_subtree_box(B.nodes, c);
   return Z;
