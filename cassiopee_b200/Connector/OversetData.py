@@ -307,6 +307,11 @@ def _setInterpData(aR, aD, order=2, penalty=1, nature=0, extrap=1,
     return None
 
 
+# receptor points in flight per window of _setInterpDataChimera (the per-receptor tables of a queued search stay on the
+# device until its lists are fetched)
+_WINDOW_PTS = 48 * 1000 * 1000
+
+
 def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
                           method='lagrangian', loc='nodes', storage='direct',
                           interpDataType=1, hook=None, verbose=2,
@@ -450,7 +455,6 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
     # the window needs in one batch, then every search is queued on the device without waiting for the previous one,
     # then the lists are fetched and stored zone after zone in the reference's order.  A window closes at
     # _WINDOW_PTS receptor points in flight (the per-receptor tables of a search stay on the device until its fetch).
-    _WINDOW_PTS = 48 * 1000 * 1000
     try:
         pos = 0
         while pos < len(zonesRcv):

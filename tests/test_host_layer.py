@@ -495,3 +495,48 @@ def test_set_interp_data2_wrappers(monkeypatch):
     s3 = Internal.getNodeFromName1(Internal.getZones(out3)[0], 'ID_rcv')
     assert Internal.getNodeFromName1(s3, 'PointListDonor')[1].size == 2 * 20 * 20
     assert C.isNamePresent(tR3, 'centers:cellN') == 1
+
+
+def test_receptor_zones_in_windows(monkeypatch):
+    """_setInterpDataChimera queues the searches of a window of receptor zones before fetching any: with a window of
+    one zone, or of all zones, the tree is the same (three mutually overlapping zones, every zone receptor and donor;
+    hooks built in batches, some given by the caller)."""
+    h = 1. / 10
+    def build():
+        zs = [G.cart((0, 0, 0), (h, h, h), (11, 11, 11), name='A'),
+              G.cart((0.45, 0.12, 0.08), (0.9 * h, 0.9 * h, 0.9 * h), (10, 10, 10), name='B'),
+              G.cart((0.21, 0.47, 0.33), (0.8 * h, 0.8 * h, 0.8 * h), (9, 9, 9), name='C')]
+        t = C.newPyTree(['Base'] + zs)
+        C._initVars(t, 'centers:cellN', 1.)
+        for z in Internal.getZones(t):
+            c = C.getFieldArray(z, 'centers:cellN'); c[:2] = 2.; c[:, -2:] = 2.
+        return t, C.node2Center(t)
+    be = OracleBackend()
+    trees = []
+    for window, hooks in ((1, False), (10 ** 9, False), (5, True)):
+        monkeypatch.setattr(X, '_WINDOW_PTS', window)
+        t, tc = build()
+        hook = None
+        if hooks:      # the caller gives one hook, the others are built in the window's batch
+            zd = Internal.getZones(tc)[1]
+            _, ni, nj, nk, _ = Internal.getZoneDim(zd)
+            xd, yd, zzd = [a.reshape(-1, order='F') for a in C.getCoords(zd)]
+            hook = [None, be.make_zone(ni, nj, nk, xd, yd, zzd, C.getFieldArray(zd, 'cellN').reshape(-1, order='F')), None]
+        X._setInterpDataChimera(t, tc, order=2, nature=1, loc='centers', storage='inverse', verbose=0, backend=be,
+                                hook=hook, refreshHooks=False)
+        trees.append(tc)
+    names = ('PointList', 'PointListDonor', 'InterpolantsDonor', 'InterpolantsType', 'ExtrapPointList', 'OrphanPointList')
+    ref = trees[0]
+    nsub = 0
+    for other in trees[1:]:
+        for za, zb in zip(Internal.getZones(ref), Internal.getZones(other)):
+            sa = [s for s in Internal.getNodesFromType1(za, 'ZoneSubRegion_t') if s[0].startswith('ID_')]
+            sb = [s for s in Internal.getNodesFromType1(zb, 'ZoneSubRegion_t') if s[0].startswith('ID_')]
+            assert [s[0] for s in sa] == [s[0] for s in sb]
+            for a, b in zip(sa, sb):
+                for n in names:
+                    na, nb = Internal.getNodeFromName1(a, n), Internal.getNodeFromName1(b, n)
+                    assert (na is None) == (nb is None)
+                    if na is not None: assert np.array_equal(na[1], nb[1]), (za[0], a[0], n)
+                nsub += 1
+    assert nsub >= 8
