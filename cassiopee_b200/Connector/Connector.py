@@ -64,6 +64,51 @@ def createHooks__(zonesD, ctx=None, interpDataType=1):
     return hooks
 
 
+def _dwDonorSlots(donor, typ):
+    """The donor list as connector.setInterpDataDW stores it (setInterpData.cpp:1655-1659): a coincident (type 1) entry
+    writes its donor index to the NEXT slot of an array initialised to -1, every other entry to its own slot, in entry
+    order; the array is then cut to the number of entries.  Slot p therefore holds donor[p] unless entry p is of type 1,
+    in which case it holds donor[p-1] if entry p-1 is of type 1 too, else -1."""
+    m = donor.size
+    out = numpy.full(m, -1, dtype=donor.dtype)
+    t1 = typ == 1
+    out[~t1] = donor[~t1]
+    if m > 1:
+        both = t1[1:] & t1[:-1]
+        out[1:][both] = donor[:-1][both]
+    return out
+
+
+def _setInterpDataDW(interpPts, zonesD, order, nature, penalty, hook, ctx=None):
+    if len(interpPts) != len(zonesD):
+        raise TypeError("setInterpDataDW: 1st and 2nd arguments must be lists of the same size.")
+    if order not in (2, 3, 5):
+        print("Warning: setInterpDataDW: unknown interpolation order. Set to 2nd order.")
+        order = 2
+    if order != 2:
+        raise NotImplementedError("setInterpDataDW: only order 2 has a device path.")
+    ctx = ctx or _lib.default_context()
+    pts = []
+    for a in interpPts:
+        px, py, pz = _posxyz(a[0])
+        if px == -1 or py == -1 or pz == -1:
+            raise TypeError("setInterpDataDW: 1st arg must contain coordinates.")
+        if _pos(a[0], ['EXdir']) != -1:
+            raise NotImplementedError("setInterpDataDW: EX points have no device path.")
+        f = a[1]
+        pts.append((numpy.ascontiguousarray(f[px]), numpy.ascontiguousarray(f[py]), numpy.ascontiguousarray(f[pz])))
+    if hook is None:
+        zones = createHooks__(zonesD, ctx, 1)
+    else:
+        if not isinstance(hook, list) or len(hook) != len(zonesD):
+            raise TypeError("setInterpDataDW: hook must be a list of one hook per donor zone.")
+        zones = hook
+    res = _lib.set_interp_data_dw(ctx, pts, zones, order=order, nature=nature, penalty=penalty)
+    out = res.fetch()
+    out[1] = [_dwDonorSlots(d, t) for d, t in zip(out[1], out[2])]
+    return out
+
+
 def setInterpData__(interpPts, zonesD, order=2, penalty=1, extrap=1, nature=0, method='lagrangian',
                     interpDataType=1, hook=None, dim=3, ctx=None):
     """connector.setInterpData on the device.  Returns the reference's list
@@ -76,7 +121,11 @@ def setInterpData__(interpPts, zonesD, order=2, penalty=1, extrap=1, nature=0, m
             raise NotImplementedError("setInterpData: method='leastsquares' has no device path.")
         raise ValueError("setInterpData__: %s: not a valid interpolation method." % method)
     if isinstance(interpPts[0], list):
-        raise NotImplementedError("setInterpData: double-wall receptor lists have no device path.")
+        # list of arrays = double wall (Connector.py:427-429): array noz holds the receptor points as donor zone noz
+        # must see them; connector.setInterpDataDW(interpPts, zonesD, order, nature, penalty, hook)
+        if interpPts[0][1].shape[1] == 0:
+            return None
+        return _setInterpDataDW(interpPts, zonesD, order, nature, penalty, hook, ctx)
     if interpPts[1].shape[1] == 0:
         return None
     types = interpDataType if isinstance(interpDataType, list) else [interpDataType] * len(zonesD)

@@ -59,6 +59,7 @@ _SIGS = {
     "cx_receptors_destroy": (_i, [_vp]),
     "cx_set_interp_data_rcv": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "cx_ctx_search_slot": (_i, [_vp, _i]),
+    "cx_set_interp_data_dw": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp]),
     "cx_result_sizes": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "cx_result_fetch_zone": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "cx_result_fetch_orphans": (_i, [_vp, _vp]),
@@ -450,6 +451,25 @@ def set_interp_data(ctx, xr, yr, zr, zones, order=2, nature=0, penalty=1, extrap
     check(lib().cx_set_interp_data(ctx.h, n, ptr(xr), ptr(yr), ptr(zr), len(zones), hs, int(order), int(nature),
                                    int(penalty), int(extrap), ctypes.byref(h)))
     return InterpResult(h, len(zones), n)
+
+
+def set_interp_data_dw(ctx, pts, zones, order=2, nature=0, penalty=1):
+    """connector.setInterpDataDW: pts[noz] = (x, y, z) host arrays of the receptors as donor zone noz sees them."""
+    if len(pts) != len(zones):
+        raise TypeError("setInterpDataDW: one receptor array per donor zone is expected.")
+    arrs = [[f64(a).reshape(-1) for a in p] for p in pts]
+    n = arrs[0][0].size
+    for p in arrs:
+        if any(a.size != n for a in p):
+            raise TypeError("setInterpDataDW: receptor arrays must have the same number of points.")
+    hs = (ctypes.c_void_p * len(zones))(*[z.h.value for z in zones])
+    h = _vp()
+    check(lib().cx_set_interp_data_dw(ctx.h, n, ptr_array([ptr(p[0]) for p in arrs]), ptr_array([ptr(p[1]) for p in arrs]),
+                                      ptr_array([ptr(p[2]) for p in arrs]), len(zones), hs, int(order), int(nature),
+                                      int(penalty), ctypes.byref(h)))
+    res = InterpResult(h, len(zones), n)
+    res._keep = arrs
+    return res
 
 
 class Receptors:

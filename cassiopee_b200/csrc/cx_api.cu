@@ -110,7 +110,7 @@ struct cx_result_dev {
 void cx_zone_bbox_host(int ni, int nj, int nk, const double* x, const double* y, const double* z, double* bb);
 int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, const double* d_zr, int nz,
                   const ZoneView* d_zones, const ZoneView* h_zones, int order, int nature, int penalty, int extrap,
-                  cx_result* R, cx_result_dev* D);
+                  cx_result* R, cx_result_dev* D, const RcvPerZone* d_pz);
 int cx_search_finish(cx_result* R, cx_result_dev* D);
 int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long nptsR, int n, const int* donor,
                   const int* rcv, const int* type, const double* coefs, long long ncoefs, cx_plan* P);
@@ -558,8 +558,49 @@ int cx_zone_destroy(cx_zone* zn)
 }
 
 /* ---- setInterpData --------------------------------------------------------- */
+static int set_interp_data_impl(cx_ctx* c, int nrcv, const double* d_xr, const double* d_yr, const double* d_zr,
+                                const RcvPerZone* d_pz, void* dw_block, int nz, cx_zone* const* zones, int order,
+                                int nature, int penalty, int extrap, cx_result** out);
+
 int cx_set_interp_data_dev(cx_ctx* c, int nrcv, const double* d_xr, const double* d_yr, const double* d_zr, int nz,
                            cx_zone* const* zones, int order, int nature, int penalty, int extrap, cx_result** out)
+{
+  return set_interp_data_impl(c, nrcv, d_xr, d_yr, d_zr, nullptr, nullptr, nz, zones, order, nature, penalty, extrap, out);
+}
+
+// Double wall: connector.setInterpDataDW(receiverArrays, donorArrays, order, nature, penalty, hook)
+// (Connector/Connector/setInterpData.cpp:1346-1890): receiver array noz holds the receptor points as donor zone noz
+// must see them (projected onto its walls by changeWall); extrapolation is always on, donors are ADT zones.
+int cx_set_interp_data_dw(cx_ctx* c, int nrcv, const double* const* xr, const double* const* yr, const double* const* zr,
+                          int nz, cx_zone* const* zones, int order, int nature, int penalty, cx_result** out)
+{
+  if (order != 2) { cx_set_error("setInterpDataDW: only order 2 has a device path"); return -4; }
+  if (nz <= 0) { cx_set_error("setInterpDataDW: no valid donor zone found."); return -1; }
+  CX_CUDA(cudaSetDevice(c->device));
+  const size_t n = (size_t)std::max(nrcv, 1);
+  double* blk = nullptr;
+  CX_CUDA(cudaMalloc(&blk, sizeof(double) * 3 * n * nz + sizeof(RcvPerZone) * (size_t)nz));
+  std::vector<RcvPerZone> pz(nz);
+  for (int i = 0; i < nz; i++)
+  {
+    pz[i].x = blk + (3 * (size_t)i) * n; pz[i].y = blk + (3 * (size_t)i + 1) * n; pz[i].z = blk + (3 * (size_t)i + 2) * n;
+    if (nrcv > 0)
+    {
+      CX_CHECK(cx_upload(c, (void*)pz[i].x, xr[i], sizeof(double) * (size_t)nrcv));
+      CX_CHECK(cx_upload(c, (void*)pz[i].y, yr[i], sizeof(double) * (size_t)nrcv));
+      CX_CHECK(cx_upload(c, (void*)pz[i].z, zr[i], sizeof(double) * (size_t)nrcv));
+    }
+  }
+  RcvPerZone* d_pz = (RcvPerZone*)(blk + 3 * n * nz);
+  CX_CHECK(cx_upload(c, d_pz, pz.data(), sizeof(RcvPerZone) * (size_t)nz));
+  int rc = set_interp_data_impl(c, nrcv, pz[0].x, pz[0].y, pz[0].z, d_pz, blk, nz, zones, order, nature, penalty, 1, out);
+  if (rc != 0) cudaFree(blk);
+  return rc;
+}
+
+static int set_interp_data_impl(cx_ctx* c, int nrcv, const double* d_xr, const double* d_yr, const double* d_zr,
+                                const RcvPerZone* d_pz, void* dw_block, int nz, cx_zone* const* zones, int order,
+                                int nature, int penalty, int extrap, cx_result** out)
 {
   if (order != 2 && order != 3 && order != 4 && order != 5)
   { cx_set_error("setInterpData: order %d not supported on the device (2, 3, 4 or 5)", order); return -4; }
@@ -592,13 +633,14 @@ int cx_set_interp_data_dev(cx_ctx* c, int nrcv, const double* d_xr, const double
   ZoneView* d_zones;
   CX_MALLOC(d_zones, sizeof(ZoneView) * (size_t)nz, c->stream);
   cx_result_full* F = new cx_result_full;
-  F->R.ctx = c; F->R.d_zones_owned = d_zones;
+  F->R.ctx = c; F->R.d_zones_owned = d_zones; F->R.d_dw_owned = nullptr;
   F->R.h_zones = cx_pin_take(c, sizeof(ZoneView) * (size_t)nz, &F->R.h_zones_own);
   if (!F->R.h_zones) { cx_set_error("setInterpData: no page-locked memory for the zone table"); delete F; return -2; }
   memcpy(F->R.h_zones, hv.data(), sizeof(ZoneView) * (size_t)nz);
   CX_CUDA(cudaMemcpyAsync(d_zones, F->R.h_zones, sizeof(ZoneView) * (size_t)nz, cudaMemcpyHostToDevice, c->stream));
-  int rc = cx_search_run(c, nrcv, d_xr, d_yr, d_zr, nz, d_zones, hv.data(), order, nature, penalty, extrap, &F->R, &F->D);
+  int rc = cx_search_run(c, nrcv, d_xr, d_yr, d_zr, nz, d_zones, hv.data(), order, nature, penalty, extrap, &F->R, &F->D, d_pz);
   if (rc != 0) { cx_result_destroy(&F->R); return rc; }
+  F->R.d_dw_owned = dw_block;       // the per-zone receptor coordinates live as long as the result
   *out = &F->R;
   return 0;
 }
@@ -722,6 +764,7 @@ int cx_result_destroy(cx_result* R)
   cudaStream_t s = R->ctx->stream;
   if (R->d_zones_owned) cudaFreeAsync(R->d_zones_owned, s);
   if (R->h_zones) { cx_pin_give(R->ctx, R->h_zones, R->h_zones_own); R->h_zones = nullptr; }
+  if (R->d_dw_owned) cudaFree(R->d_dw_owned);
   for (int i = 0; i < 5; i++) if (R->ev[i]) cudaEventDestroy(R->ev[i]);
   void* ptrs[] = {R->d_noblk, R->d_type, R->d_dind, R->d_isext, R->d_cf, F->D.rcv, F->D.dnr, F->D.typ, F->D.coefs,
                   F->D.ext, F->D.orphan};

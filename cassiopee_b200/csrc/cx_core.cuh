@@ -1278,9 +1278,14 @@ CX_D void interp_o2_receptor(double x, double y, double z, int nz, const ZoneVie
   if (o.noblk > 0) collapse_type2(zones[o.noblk - 1], o.type, o.dind, o.cf);
 }
 
+// Double wall (K_INTERP::getInterpolationCellDW / getExtrapolationCellDW, Interp.cpp:176-255, :362-): the receptor
+// seen from donor zone noz is (x[r], y[r], z[r]) of entry noz of this table -- the point projected onto that zone's
+// walls by the caller; everything else is the ordinary search.  nullptr: one point for every zone.
+struct RcvPerZone { const double* x; const double* y; const double* z; };
+
 // interp_o2_receptor with the search state in scratch (the version the kernels run)
 CX_D void interp_o2_receptor_s(double x, double y, double z, int nz, const ZoneView* zones, int nature, int penalty,
-                               RcvOut& o, const Scratch& S, SearchStats* st)
+                               RcvOut& o, const Scratch& S, SearchStats* st, const RcvPerZone* pz = nullptr, int r = 0)
 {
   double best = CX_MAXF;
   o.noblk = 0; o.type = 0; o.dind = -1;
@@ -1290,6 +1295,7 @@ CX_D void interp_o2_receptor_s(double x, double y, double z, int nz, const ZoneV
   for (int noz = 0; noz < nz; noz++)
   {
     const ZoneView& Z = zones[noz];
+    if (pz) { x = pz[noz].x[r]; y = pz[noz].y[r]; z = pz[noz].z[r]; }
     int ic, jc, kc;
     if (Z.nk == 1)
     {

@@ -91,6 +91,7 @@ struct cx_result {
   void* h_zones; int h_zones_own;                   // page-locked copy of the ZoneView table the upload reads
   cudaEvent_t ev[5];                                // search begin/end, extrapolation begin/end, all done
   void* d_zones_owned;                              // the ZoneView table of the call (freed when the search is done)
+  void* d_dw_owned;                                 // double wall: per-zone receptor coordinates + their table
 };
 
 struct cx_plan {

@@ -44,7 +44,7 @@ template <int TB>
 __global__ void __launch_bounds__(TB, 512 / TB)
 k_interp_o2(int n, const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr,
             int nz, const ZoneView* __restrict__ zones, int nature, int penalty, RcvTable T, int cap,
-            unsigned long long* gstats)
+            unsigned long long* gstats, const RcvPerZone* __restrict__ pz)
 {
   extern __shared__ __align__(16) double o2_sm[];
   Scratch S;
@@ -56,7 +56,7 @@ k_interp_o2(int n, const double* __restrict__ xr, const double* __restrict__ yr,
   if (r < n)
   {
     RcvOut o;
-    interp_o2_receptor_s(xr[r], yr[r], zr[r], nz, zones, nature, penalty, o, S, &st);
+    interp_o2_receptor_s(xr[r], yr[r], zr[r], nz, zones, nature, penalty, o, S, &st, pz, r);
     T.noblk[r] = o.noblk; T.type[r] = o.type; T.dind[r] = o.dind; T.isext[r] = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) T.cf[(size_t)i * n + r] = o.cf[i];
@@ -161,7 +161,7 @@ __device__ __forceinline__ int search_extrap_cell_warp(const ZoneView& Z, double
 __global__ void __launch_bounds__(128)
 k_extrap(const int* __restrict__ nlist_p, const int* __restrict__ list, const double* __restrict__ xr, const double* __restrict__ yr,
          const double* __restrict__ zr, int nz, const ZoneView* __restrict__ zones, int nature, int penalty,
-         RcvTable T, unsigned long long* gstats)
+         RcvTable T, unsigned long long* gstats, const RcvPerZone* __restrict__ pz)
 {
   // the list length lives on the device (the host never waits for the interpolation pass): the warps stride over it
   __shared__ int s_cand[4][32];
@@ -171,7 +171,7 @@ k_extrap(const int* __restrict__ nlist_p, const int* __restrict__ list, const do
   for (int a = blockIdx.x * 4 + w; a < nlist; a += gridDim.x * 4)      // warp-uniform
   {
     const int r = list[a];
-    const double x = xr[r], y = yr[r], z = zr[r];
+    double x = xr[r], y = yr[r], z = zr[r];
     // K_INTERP::getExtrapolationCell (Interp.cpp:282-360): constraint=40, extrapOrder=1, order forced to O2CF
     double best = CX_MAXF, sumCoefMin = CX_MAXF;
     int noblk = 0, type = 0, dind = -1;
@@ -180,6 +180,7 @@ k_extrap(const int* __restrict__ nlist_p, const int* __restrict__ list, const do
     for (int noz = 0; noz < nz; noz++)
     {
       const ZoneView& Z = zones[noz];
+      if (pz) { x = pz[noz].x[r]; y = pz[noz].y[r]; z = pz[noz].z[r]; }
       int ic, jc, kc;
       int found = search_extrap_cell_warp(Z, x, y, z, ic, jc, kc, tcf, nature, 40., s_cand[w], lane, &st);
       if (found < 1) continue;
@@ -247,7 +248,8 @@ struct ExtrapZoneRes { int found, ic, jc, kc; double cf[8]; };   // per (zone, f
 __global__ void __launch_bounds__(128)
 k_extrap_zone(const int* __restrict__ nlist_p, const int* __restrict__ list, int chunk0, int chunkN,
               const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, int nz,
-              const ZoneView* __restrict__ zones, int nature, ExtrapZoneRes* __restrict__ out, unsigned long long* gstats)
+              const ZoneView* __restrict__ zones, int nature, ExtrapZoneRes* __restrict__ out, unsigned long long* gstats,
+              const RcvPerZone* __restrict__ pz)
 {
   __shared__ int s_buf[4][CX_XG][CX_XB];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -265,7 +267,12 @@ k_extrap_zone(const int* __restrict__ nlist_p, const int* __restrict__ list, int
     const int a = chunk0 + g * CX_XG + lane;
     const bool mine = lane < CX_XG && a < nlist;
     double x = 0., y = 0., z = 0.;
-    if (mine) { const int r = list[a]; x = xr[r]; y = yr[r]; z = zr[r]; }
+    if (mine)
+    {
+      const int r = list[a];
+      if (pz) { x = pz[noz].x[r]; y = pz[noz].y[r]; z = pz[noz].z[r]; }
+      else { x = xr[r]; y = yr[r]; z = zr[r]; }
+    }
     // walk state of this lane's receptor
     AdtQuery q;
     int clo[3] = {0, 0, 0}, chi[3] = {0, 0, 0}, ctotal = 0, cbase = 0;
@@ -539,9 +546,10 @@ extern int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_x
 
 int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, const double* d_zr, int nz,
                   const ZoneView* d_zones, const ZoneView* h_zones, int order, int nature, int penalty, int extrap,
-                  cx_result* R, cx_result_dev* D)
+                  cx_result* R, cx_result_dev* D, const RcvPerZone* d_pz)
 {
   cudaStream_t s = ctx->stream;
+  if (d_pz && order != 2) { cx_set_error("setInterpDataDW: only order 2 has a device path"); return -4; }
   const int ncfmax = (order == 3) ? 9 : (order == 4) ? 12 : (order == 5) ? 15 : 8;   // setInterpData.cpp:624-652
   R->nrcv = n; R->nz = nz; R->ncfmax = ncfmax;
   R->cnt.assign(nz, 0); R->ncoef.assign(nz, 0); R->nextrap.assign(nz, 0); R->norphan = 0;
@@ -577,12 +585,12 @@ int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, co
     if (tbs == 64)
     {
       CX_CUDA(cudaFuncSetAttribute(k_interp_o2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
-      k_interp_o2<64><<<cx_grid(n, 64), 64, smb, s>>>(n, d_xr, d_yr, d_zr, nz, d_zones, nature, penalty, T, cap, d_stats);
+      k_interp_o2<64><<<cx_grid(n, 64), 64, smb, s>>>(n, d_xr, d_yr, d_zr, nz, d_zones, nature, penalty, T, cap, d_stats, d_pz);
     }
     else
     {
       CX_CUDA(cudaFuncSetAttribute(k_interp_o2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
-      k_interp_o2<128><<<cx_grid(n, 128), 128, smb, s>>>(n, d_xr, d_yr, d_zr, nz, d_zones, nature, penalty, T, cap, d_stats);
+      k_interp_o2<128><<<cx_grid(n, 128), 128, smb, s>>>(n, d_xr, d_yr, d_zr, nz, d_zones, nature, penalty, T, cap, d_stats, d_pz);
     }
     ctx->launches++;
   }
@@ -609,7 +617,7 @@ int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, co
     if (xmode == 1)
     {
       const int gx = std::max(1, std::min(cx_grid(n, 4), ctx->sm_count * 16));
-      k_extrap<<<gx, 128, 0, s>>>(d_nfail, d_fail, d_xr, d_yr, d_zr, nz, d_zones, nature, penalty, T, d_stats);
+      k_extrap<<<gx, 128, 0, s>>>(d_nfail, d_fail, d_xr, d_yr, d_zr, nz, d_zones, nature, penalty, T, d_stats, d_pz);
       ctx->launches += 2;
     }
     else
@@ -624,7 +632,7 @@ int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, co
       const int gc = std::max(1, std::min(cx_grid(CHUNK, 128), ctx->sm_count * 8));
       for (int c0 = 0; c0 < n; c0 += CHUNK)
       {
-        k_extrap_zone<<<gz, 128, 0, s>>>(d_nfail, d_fail, c0, CHUNK, d_xr, d_yr, d_zr, nz, d_zones, nature, d_res, d_stats);
+        k_extrap_zone<<<gz, 128, 0, s>>>(d_nfail, d_fail, c0, CHUNK, d_xr, d_yr, d_zr, nz, d_zones, nature, d_res, d_stats, d_pz);
         k_extrap_combine<<<gc, 128, 0, s>>>(d_nfail, d_fail, c0, CHUNK, nz, d_zones, penalty, d_res, T);
         ctx->launches += 2;
       }

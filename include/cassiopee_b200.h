@@ -134,6 +134,13 @@ int cx_set_interp_data_rcv(cx_ctx* ctx, cx_receptors* rcv, int nz, cx_zone* cons
  * returned by the reference at setInterpData.cpp:1272 —
  * rcv[n], donor[n], type[n] (int32), coefs (ragged f64), extrap[ne] per donor
  * zone, ascending receptor position; orphan[no] global. */
+/* Double wall: connector.setInterpDataDW(receiverArrays, donorArrays, order, nature, penalty, hook)
+ * (Connector/Connector/setInterpData.cpp:1346-1890, K_INTERP::getInterpolationCellDW Interp.cpp:176-255): xr[noz], yr[noz],
+ * zr[noz] (host, nrcv values each) are the receptor points as donor zone noz must see them (projected onto its walls by
+ * the caller); extrapolation is always on; order 2 (others return -4).  The result is read like cx_set_interp_data's. */
+int cx_set_interp_data_dw(cx_ctx* ctx, int nrcv, const double* const* xr, const double* const* yr,
+                          const double* const* zr, int nzones, cx_zone* const* zones, int order, int nature, int penalty,
+                          cx_result** out);
 /* cx_set_interp_data_rcv / _dev return as soon as the search is queued; the first accessor of the result waits for it.
  * cx_ctx_search_slot(ctx, k), k = 1..8: the searches issued next run on side stream k (those of several receptor
  * zones then overlap on the device); 0: back on the main stream. */

@@ -187,6 +187,47 @@ def set_interp_data(xr, yr, zr, zones, order=2, nature=0, penalty=1, extrap=1):
     return pack_per_zone(raw, len(zones))
 
 
+def set_interp_data_dw(pts, zones, order=2, nature=0, penalty=1):
+    """connector.setInterpDataDW (setInterpData.cpp:1346-1890): pts[noz] = (x, y, z) of the receptors as donor zone noz
+    sees them.  The reference's own getInterpolationCellDW / getExtrapolationCellDW per receptor (ref_set_interp_data_dw),
+    then the reference's storage statement by statement (:1627-1737), including its slot rule for type 1: the donor
+    index of a coincident entry goes to slot size+1 of an array initialised to -1 (:1655-1659), so it is overwritten by
+    the next entry of the zone unless that one is coincident too."""
+    nz = len(zones)
+    assert len(pts) == nz
+    arrs = [[_f64(a) for a in p] for p in pts]
+    n = arrs[0][0].size
+    hs = (ctypes.c_void_p * nz)(*[z.h for z in zones])
+    noblk = np.zeros(n, np.int32); typ = np.zeros(n, np.int32); dind = np.zeros(n, np.int32)
+    isext = np.zeros(n, np.int32); cf = np.zeros((n, 16))
+    f = lib().ref_set_interp_data_dw
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 5
+    rc = f(n, _ptrs([a[0] for a in arrs]), _ptrs([a[1] for a in arrs]), _ptrs([a[2] for a in arrs]), nz, hs, order, nature,
+           penalty, noblk.ctypes.data, typ.ctypes.data, dind.ctypes.data, isext.ctypes.data, cf.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("ref_set_interp_data_dw failed rc=%d" % rc)
+    rcvL = [[] for _ in range(nz)]; typL = [[] for _ in range(nz)]; cfL = [[] for _ in range(nz)]
+    extL = [[] for _ in range(nz)]; orphan = []
+    dnrA = [np.full(2 * n + 2, -1, np.int32) for _ in range(nz)]
+    size = [0] * nz
+    for ind in range(n):
+        b = int(noblk[ind])
+        if b == 0:
+            orphan.append(ind); continue
+        z = b - 1
+        t = int(typ[ind])
+        typL[z].append(t); rcvL[z].append(ind)
+        cfL[z].extend(cf[ind, :_NCF[t]])
+        if t == 1: dnrA[z][size[z] + 1] = dind[ind]
+        else: dnrA[z][size[z]] = dind[ind]
+        size[z] += 1
+        if isext[ind] == 1: extL[z].append(ind)
+    return [[np.array(r, np.int32) for r in rcvL], [dnrA[z][:size[z]].copy() for z in range(nz)],
+            [np.array(t, np.int32) for t in typL], [np.array(c, np.float64) for c in cfL],
+            [np.array(e, np.int32) for e in extL], np.array(orphan, np.int32), []]
+
+
 def get_interpolated_points(cellN):
     """getInterpolatedPoints.cpp:1717-1724: positions with |cellN-2| <= 1e-15,
     source order."""

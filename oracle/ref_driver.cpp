@@ -220,6 +220,70 @@ int ref_set_interp_data(int nrcv, const double* xr, const double* yr,
   return 0;
 }
 
+/* Double wall: the receptor loop of K_CONNECTOR::setInterpDataDW (Connector/Connector/setInterpData.cpp:1606-1625) on raw
+ * pointers: receptor ind seen from donor zone noz is (xt[noz][ind], yt[noz][ind], zt[noz][ind]); the reference's own
+ * K_INTERP::getInterpolationCellDW / getExtrapolationCellDW (Interp.cpp:176-255, :371-) do the work; extrapolation is
+ * always tried.  Same per-receptor tables as ref_set_interp_data (the packing, with its type-1 slot rule, is
+ * oracle.py:set_interp_data_dw). */
+int ref_set_interp_data_dw(int nrcv, const double* const* xt_, const double* const* yt_, const double* const* zt_,
+                           int nz, void** zones, int order, int nature, int penalty, int* noblk_o, int* type_o,
+                           int* dind_o, int* isext_o, double* cf_o)
+{
+  K_INTERP::InterpData::InterpolationType interpType;
+  E_Int nindi = 1, ncfmax;
+  switch (order)  // setInterpData.cpp:1366-1391
+  {
+    case 2: interpType = K_INTERP::InterpData::O2CF; ncfmax = 8; break;
+    case 3: interpType = K_INTERP::InterpData::O3ABC; ncfmax = 9; break;
+    case 5: interpType = K_INTERP::InterpData::O5ABC; ncfmax = 15; break;
+    default: interpType = K_INTERP::InterpData::O2CF; ncfmax = 8; break;
+  }
+  vector<K_INTERP::InterpData*> interpDatas;
+  vector<FldArrayF*> fields;
+  vector<void*> a2, a3, a4, a5;
+  vector<E_Int> posxs, posys, poszs, poscs;
+  for (int i = 0; i < nz; i++)
+  {
+    RefZone* zn = (RefZone*)zones[i];
+    if (!zn->data()) return -1;
+    interpDatas.push_back(zn->data());
+    fields.push_back(zn->f);
+    a2.push_back(&zn->ni); a3.push_back(&zn->nj); a4.push_back(&zn->nk);
+    a5.push_back(NULL);
+    posxs.push_back(1); posys.push_back(2); poszs.push_back(3); poscs.push_back(4);
+  }
+  FldArrayI indi(nindi); FldArrayF cf(ncfmax);
+  vector<E_Float> xt(nz), yt(nz), zt(nz);
+  E_Float vol; E_Int type, noblk = 0;
+  for (E_Int ind = 0; ind < nrcv; ind++)
+  {
+    for (E_Int noz = 0; noz < nz; noz++) { xt[noz] = xt_[noz][ind]; yt[noz] = yt_[noz][ind]; zt[noz] = zt_[noz][ind]; }
+    type = 0;
+    short ok = K_INTERP::getInterpolationCellDW(&xt[0], &yt[0], &zt[0], interpDatas, fields, a2, a3, a4, a5, posxs,
+                                                posys, poszs, poscs, vol, indi, cf, type, noblk, interpType, nature,
+                                                penalty);
+    E_Int isExtrapolated = 0;
+    if (ok != 1)
+    {
+      ok = K_INTERP::getExtrapolationCellDW(&xt[0], &yt[0], &zt[0], interpDatas, fields, a2, a3, a4, a5, posxs, posys,
+                                            poszs, poscs, vol, indi, cf, type, noblk, interpType, nature, penalty);
+      if (noblk > 0) isExtrapolated = 1;
+    }
+    noblk_o[ind] = noblk;
+    isext_o[ind] = isExtrapolated;
+    for (int k = 0; k < 16; k++) cf_o[(size_t)ind * 16 + k] = 0.;
+    if (noblk > 0)
+    {
+      type_o[ind] = type;
+      dind_o[ind] = indi[0];
+      E_Int ncf = cf.getSize() < ncfmax ? cf.getSize() : ncfmax;
+      for (E_Int k = 0; k < ncf; k++) cf_o[(size_t)ind * 16 + k] = cf[k];
+    }
+    else { type_o[ind] = 0; dind_o[ind] = -1; }
+  }
+  return 0;
+}
+
 /* _setInterpTransfers general path (setInterpTransfers.cpp:436-449) on raw
  * pointers: fieldR[v][rcvPts[n]] = sum cf*fieldD[v][stencil]. */
 void ref_transfer(int nvars_, double** dnrFields, double** rcvFields, int imd_,
