@@ -235,26 +235,26 @@ k_extrap(const int* __restrict__ nlist_p, const int* __restrict__ list, const do
 // ---- extrapolation, second form: the walks of 16 receptors run side by side -------------------------------------
 // In k_extrap lane 0 walks the tree while 31 lanes wait: 63 % of the issued instructions ran on one lane (ncu,
 // profiles/r03_*: 12 active threads per instruction, fp64 pipe 11 % busy, 8 resident warps per SM at 228 registers).
-// Here a warp takes a group of CX_XG receptors and ONE donor zone: lanes 0..CX_XG-1 walk their own receptor's tree
+// Here a warp takes a group of XG receptors and ONE donor zone: lanes 0..XG-1 walk their own receptor's tree
 // and buffer up to CX_XB candidates each in shared memory (in the reference's list order), then the whole warp
 // evaluates the buffered candidates of one receptor after the other, 32 at a time, and replays the reference's
 // sequential fold (InterpAdt.cpp:1113-1147) in candidate order; rounds repeat until every walk is exhausted.  The
 // per-(receptor, zone) winner goes to a table; k_extrap_combine then runs the cross-zone choice of
 // getExtrapolationCell (Interp.cpp:282-360) zone after zone, exactly as k_extrap does.
-#define CX_XG 16
 #define CX_XB 64
 struct ExtrapZoneRes { int found, ic, jc, kc; double cf[8]; };   // per (zone, failing receptor of the chunk)
 
-__global__ void __launch_bounds__(128)
+template <int MINB, int XG>
+__global__ void __launch_bounds__(128, MINB)
 k_extrap_zone(const int* __restrict__ nlist_p, const int* __restrict__ list, int chunk0, int chunkN,
               const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, int nz,
               const ZoneView* __restrict__ zones, int nature, ExtrapZoneRes* __restrict__ out, unsigned long long* gstats,
               const RcvPerZone* __restrict__ pz)
 {
-  __shared__ int s_buf[4][CX_XG][CX_XB];
+  __shared__ int s_buf[4][XG][CX_XB];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nlist = min(*nlist_p, chunk0 + chunkN);
-  const int ngroups = (max(nlist - chunk0, 0) + CX_XG - 1) / CX_XG;
+  const int ngroups = (max(nlist - chunk0, 0) + XG - 1) / XG;
   const long long nitems = (long long)ngroups * nz;
   SearchStats st; st.nvisit = 0; st.ncand = 0; st.ntet = 0;
   const double constraint = 40.;
@@ -264,8 +264,8 @@ k_extrap_zone(const int* __restrict__ nlist_p, const int* __restrict__ list, int
     const int g = (int)(item / nz), noz = (int)(item - (long long)g * nz);
     const ZoneView& Z = zones[noz];
     const bool cart = Z.topo == 0;
-    const int a = chunk0 + g * CX_XG + lane;
-    const bool mine = lane < CX_XG && a < nlist;
+    const int a = chunk0 + g * XG + lane;
+    const bool mine = lane < XG && a < nlist;
     double x = 0., y = 0., z = 0.;
     if (mine)
     {
@@ -627,12 +627,25 @@ int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, co
       const int CHUNK = (int)std::min<long long>(n, std::max<long long>(1 << 16, (512ll << 20) / ((long long)sizeof(ExtrapZoneRes) * nz)));
       ExtrapZoneRes* d_res;
       CX_MALLOC(d_res, sizeof(ExtrapZoneRes) * (size_t)CHUNK * nz, s);
-      const long long items = (long long)((CHUNK + CX_XG - 1) / CX_XG) * nz;
+      // CX_XMINB = resident CTAs per SM (2 | 4 | 6: 246 / 128 / 80 registers, the last two with ~0.5 KB of spills),
+      // CX_XG = receptors per warp (16 | 8 | 4).  The kernel is bound by the latency of each warp's dependent chain:
+      // more resident warps and shorter chains win over fewer spills and wider walks (measured: gpurun_out/r3_xg_*).
+      static int minb = 0, xg = 0;
+      if (!minb)
+      {
+        const char* e = getenv("CX_XMINB"); minb = e ? atoi(e) : 4; if (minb != 2 && minb != 4 && minb != 6) minb = 4;
+        const char* g = getenv("CX_XG"); xg = g ? atoi(g) : 16; if (xg != 16 && xg != 8 && xg != 4) xg = 16;
+      }
+      const long long items = (long long)((CHUNK + xg - 1) / xg) * nz;
       const int gz = (int)std::max(1ll, std::min((items + 3) / 4, (long long)ctx->sm_count * 32));
       const int gc = std::max(1, std::min(cx_grid(CHUNK, 128), ctx->sm_count * 8));
       for (int c0 = 0; c0 < n; c0 += CHUNK)
       {
-        k_extrap_zone<<<gz, 128, 0, s>>>(d_nfail, d_fail, c0, CHUNK, d_xr, d_yr, d_zr, nz, d_zones, nature, d_res, d_stats, d_pz);
+#define CX_XZ(MB, G) k_extrap_zone<MB, G><<<gz, 128, 0, s>>>(d_nfail, d_fail, c0, CHUNK, d_xr, d_yr, d_zr, nz, d_zones, nature, d_res, d_stats, d_pz)
+        if (xg == 16) { if (minb == 2) CX_XZ(2, 16); else if (minb == 4) CX_XZ(4, 16); else CX_XZ(6, 16); }
+        else if (xg == 8) { if (minb == 2) CX_XZ(2, 8); else if (minb == 4) CX_XZ(4, 8); else CX_XZ(6, 8); }
+        else { if (minb == 2) CX_XZ(2, 4); else if (minb == 4) CX_XZ(4, 4); else CX_XZ(6, 4); }
+#undef CX_XZ
         k_extrap_combine<<<gc, 128, 0, s>>>(d_nfail, d_fail, c0, CHUNK, nz, d_zones, penalty, d_res, T);
         ctx->launches += 2;
       }
