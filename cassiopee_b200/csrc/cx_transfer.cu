@@ -45,44 +45,18 @@ template <int O> struct Sten { };
 // face, two of those again + yi / + zi), so a plan stores such entries as the 4 distinct doubles (slot-major, like
 // the raw layout) + a 16-bit selector word (2 bits per vertex): 34 bytes instead of 64.  The values are the same
 // doubles bit for bit, so the arithmetic is untouched.  pat == nullptr: raw group, 8 slots.
-// Plan data of a plan SET is read again by every iteration of a solver loop while the fields stream through: loaded
-// with an L2 evict_last policy (createpolicy + ld.global.nc.L2::cache_hint) it stays resident between iterations as
-// long as the set's plans fit in L2 (keep = 0: plain loads).
-__device__ __forceinline__ unsigned long long plan_policy()
-{
-  unsigned long long pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ int ld_plan(const int* p, unsigned long long keep)
-{
-  if (!keep) return *p;
-  int v; asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(keep)); return v;
-}
-__device__ __forceinline__ double ld_plan(const double* p, unsigned long long keep)
-{
-  if (!keep) return *p;
-  double v; asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(keep)); return v;
-}
-__device__ __forceinline__ unsigned ld_plan(const unsigned short* p, unsigned long long keep)
-{
-  if (!keep) return *p;
-  unsigned short v; asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(keep)); return v;
-}
-
 __device__ __forceinline__ void load_cf2(double* c, const double* __restrict__ cfT, const unsigned short* __restrict__ pat,
-                                         int m, int e, unsigned long long keep = 0ull)
+                                         int m, int e)
 {
   if (pat == nullptr)
   {
 #pragma unroll
-    for (int k = 0; k < 8; k++) c[k] = ld_plan(cfT + (size_t)k * m + e, keep);
+    for (int k = 0; k < 8; k++) c[k] = cfT[(size_t)k * m + e];
   }
   else
   {
-    const double v0 = ld_plan(cfT + e, keep), v1 = ld_plan(cfT + (size_t)m + e, keep), v2 = ld_plan(cfT + (size_t)2 * m + e, keep),
-                 v3 = ld_plan(cfT + (size_t)3 * m + e, keep);
-    const unsigned p = ld_plan(pat + e, keep);
+    const double v0 = cfT[e], v1 = cfT[(size_t)m + e], v2 = cfT[(size_t)2 * m + e], v3 = cfT[(size_t)3 * m + e];
+    const unsigned p = pat[e];
 #pragma unroll
     for (int k = 0; k < 8; k++)
     {
@@ -251,10 +225,8 @@ __device__ __forceinline__ bool transfer_tile2_staged(StageSmem& S, int t0, int 
                                                       int imd, int imdjmd, int nptsD, const int* __restrict__ donor,
                                                       const int* __restrict__ idx, const double* __restrict__ cfT,
                                                       double* __restrict__ dense, long long ld, int known_lo = -1,
-                                                      int known_hi = -1, const unsigned short* __restrict__ pat = nullptr,
-                                                      bool keep_plan = false)
+                                                      int known_hi = -1, const unsigned short* __restrict__ pat = nullptr)
 {
-  const unsigned long long keep = keep_plan ? plan_policy() : 0ull;     // 0 is never a valid evict_last policy word
   const int tid = threadIdx.x;
   const int e = t0 + tid;
   const int last = min(t0 + (int)blockDim.x, m) - 1;
@@ -286,8 +258,8 @@ __device__ __forceinline__ bool transfer_tile2_staged(StageSmem& S, int t0, int 
   const bool act = e < m;
   if (act)
   {
-    l = ld_plan(donor + e, keep) - d_lo; o = (size_t)ld_plan(idx + e, keep);
-    load_cf2(c, cfT, pat, m, e, keep);
+    l = donor[e] - d_lo; o = (size_t)idx[e];
+    load_cf2(c, cfT, pat, m, e);
   }
   for (int v = 0; v < nvars; v++)
   {
@@ -914,7 +886,7 @@ k_transfer_set(const SetDesc* __restrict__ descs, const BlkRec* __restrict__ blk
       const int b = blockIdx.x - D.first_block;
       const TileRef t = D.tiles[b];
       const int count = D.tiles[b + 1].start - t.start;
-      if (staged & 1)
+      if (staged)
       {
         if (D.mode == 0) transfer_box2<0>(dyn_sm, &bar, t.tile, t.start, count, D.m, nvars, pd, pr, D.imd, D.jmd, D.imdjmd, D.nptsD, D.ntx, D.nty, D.donor, D.idx, D.cfT, D.dense, D.ld);
         else transfer_box2<1>(dyn_sm, &bar, t.tile, t.start, count, D.m, nvars, pd, pr, D.imd, D.jmd, D.imdjmd, D.nptsD, D.ntx, D.nty, D.donor, D.idx, D.cfT, D.dense, D.ld);
@@ -933,13 +905,13 @@ k_transfer_set(const SetDesc* __restrict__ descs, const BlkRec* __restrict__ blk
       else transfer_box3<1>(dyn_sm, br.start, br.count, br.base, br.dims, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.donor, D.idx, D.cfT, D.dense, D.ld, D.pat);
       return;
     }
-    if ((staged & 1) && D.layout == 1)
+    if (staged && D.layout == 1)
     {
       StageSmem& S = *reinterpret_cast<StageSmem*>(dyn_sm);
       const int t0 = (blockIdx.x - D.first_block) * blockDim.x;
       bool done = (D.mode == 0)
-        ? transfer_tile2_staged<0>(S, t0, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.nptsD, D.donor, D.idx, D.cfT, D.dense, D.ld, br.d_lo, br.d_hi, D.pat, (staged & 2) != 0)
-        : transfer_tile2_staged<1>(S, t0, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.nptsD, D.donor, D.idx, D.cfT, D.dense, D.ld, br.d_lo, br.d_hi, D.pat, (staged & 2) != 0);
+        ? transfer_tile2_staged<0>(S, t0, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.nptsD, D.donor, D.idx, D.cfT, D.dense, D.ld, br.d_lo, br.d_hi, D.pat)
+        : transfer_tile2_staged<1>(S, t0, D.m, nvars, pd, pr, D.imd, D.imdjmd, D.nptsD, D.donor, D.idx, D.cfT, D.dense, D.ld, br.d_lo, br.d_hi, D.pat);
       if (done) return;
     }
   }
@@ -947,7 +919,7 @@ k_transfer_set(const SetDesc* __restrict__ descs, const BlkRec* __restrict__ blk
   {
     constexpr int O = 3;
     extern __shared__ __align__(16) double dyn_sm[];
-    if ((staged & 1) && D.layout == 1)
+    if (staged && D.layout == 1)
     {
       StageSmemO<O>& S = *reinterpret_cast<StageSmemO<O>*>(dyn_sm);
       const int t0 = (blockIdx.x - D.first_block) * blockDim.x;
@@ -1685,8 +1657,6 @@ int cx_plan_rotate_on(cx_plan* P, int dirR, double ct, double st, double* fx, do
 struct cx_planset {
   cx_ctx* ctx;
   int nvars, ndesc, staged, tiled, boxed;
-  int keep;                             // plan data loaded with the L2 evict_last priority (the set fits in half of L2)
-  size_t plan_bytes;
   // plans too large to gain anything from fusion run as their own launches (leaner kernel, more CTAs per SM)
   struct Big { cx_plan* P; int mode; std::vector<const double*> dD; std::vector<double*> dR; double* dense; long long ld; };
   std::vector<Big> big;
@@ -1733,7 +1703,6 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
   CX_CUDA(cudaSetDevice(ctx->device));
   cx_planset* S = new cx_planset;
   S->ctx = ctx; S->nvars = nvars; S->d_tables = nullptr; S->ntables = 0; S->ndesc = 0;
-  S->keep = 0; S->plan_bytes = 0;
   S->staged = cx_transfer_staging(); S->smem = 0; S->smem3 = 0; S->smem5 = 0; S->tiled = 0; S->boxed = 0;
   if (nvars > CX_MAXVARS) { cx_set_error("plan set: at most %d variables per set", CX_MAXVARS); delete S; return -1; }
   std::vector<SetDesc> descs[6]; std::vector<BlkRec> b2d[6]; std::vector<void*> tables;
@@ -1781,18 +1750,12 @@ int cx_planset_create(cx_ctx* ctx, int nplans, cx_plan* const* plans, int nvars,
       descs[t].push_back(D);
       nb[t] += blocks;
       S->ndesc++;
-      S->plan_bytes += (size_t)G.n * (8 + (G.d_pat ? 34 : 8 * (size_t)G.ncf));
     }
   }
-  {
-    // CX_PLAN_KEEP=<MB>: the plans of a set of at most that size are loaded with the L2 evict_last policy, to stay
-    // resident between the iterations of a loop.  Off by default: measured on the C4 step (38 MB of plans, 7
-    // variables) it changes nothing, 59.6 us either way (gpurun_out/r3_keep_*.json) -- the step is bound by the
-    // sector-granular field traffic, not by re-reading the plans.
-    const char* e = getenv("CX_PLAN_KEEP");
-    const size_t cap = e ? (size_t)atoi(e) * (1u << 20) : 0;
-    S->keep = (S->plan_bytes > 0 && S->plan_bytes <= cap) ? 1 : 0;
-  }
+  // Measured and rejected (round 2, third session): loading the plan data of a set with an L2 evict_last policy
+  // (createpolicy.fractional.L2::evict_last + ld.global.nc.L2::cache_hint), so that the 38 MB of plans of the C4 step
+  // stay resident between the iterations of a loop while the fields stream through: 59.6 us per step either way
+  // (gpurun_out/r3_keep_*.json) -- the step waits for the sector-granular field traffic, not for the plans.
   for (int t = 0; t < 6; t++)
   {
     S->nblocks[t] = nb[t]; S->d_descs[t] = nullptr; S->d_blk2desc[t] = nullptr;
@@ -1825,8 +1788,8 @@ static int planset_run_on(cx_planset* S, cudaStream_t s, int v0 = 0, int nv = -1
   if (S->nblocks[0]) { k_transfer_set<1, false><<<S->nblocks[0], 256, 0, s>>>(S->d_descs[0], S->d_blk2desc[0], nv, S->staged, v0); S->ctx->launches++; }
   if (S->nblocks[1])
   {
-    if (S->tiled) k_transfer_set<2, true><<<S->nblocks[1], 256, S->smem, s>>>(S->d_descs[1], S->d_blk2desc[1], nv, S->staged | (S->keep << 1), v0);
-    else k_transfer_set<2, false><<<S->nblocks[1], 256, S->smem, s>>>(S->d_descs[1], S->d_blk2desc[1], nv, S->staged | (S->keep << 1), v0);
+    if (S->tiled) k_transfer_set<2, true><<<S->nblocks[1], 256, S->smem, s>>>(S->d_descs[1], S->d_blk2desc[1], nv, S->staged, v0);
+    else k_transfer_set<2, false><<<S->nblocks[1], 256, S->smem, s>>>(S->d_descs[1], S->d_blk2desc[1], nv, S->staged, v0);
     S->ctx->launches++;
   }
   if (S->nblocks[2]) { k_transfer_set<3, false><<<S->nblocks[2], 256, S->smem3, s>>>(S->d_descs[2], S->d_blk2desc[2], nv, S->staged, v0); S->ctx->launches++; }
