@@ -45,6 +45,7 @@ _SIGS = {
     "cx_zone_create": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "cx_zone_create_noadt": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "cx_zones_build_adt": (_i, [_vp, _i, _vp]),
+    "cx_zone_adt_begin": (_i, [_vp]),
     "cx_zone_create_cart": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "cx_zone_set_celln": (_i, [_vp, _vp]),
     "cx_zone_info": (_i, [_vp, _vp, _vp, _vp, _vp]),
@@ -838,7 +839,11 @@ class DeviceBackend:
     def make_zones(self, specs):
         """Hooks of several donor zones, specs = [(ni, nj, nk, x, y, z, cellN, interpDataType)]: the uploads run zone
         after zone, the ADT builds of the whole batch run concurrently on the device (cx_zones_build_adt)."""
-        zones = [Zone(self.ctx, *sp[:7], interpDataType=sp[7], defer_adt=True) for sp in specs]
+        zones = []
+        for sp in specs:
+            z = Zone(self.ctx, *sp[:7], interpDataType=sp[7], defer_adt=True)
+            check(lib().cx_zone_adt_begin(z.h))      # builds while the next zone's coordinates go up
+            zones.append(z)
         build_adts(self.ctx, zones)
         return zones
 

@@ -171,7 +171,8 @@ struct AdtBuild {
   std::vector<int> cntAll;               // cntAll[L] = active cells at the start of level L
   cudaEvent_t ev0, ev1;
   bool done;
-  static constexpr int BATCH = 8, MAXL = 4096, TB = 256;
+  static constexpr int BATCH = 8, BATCH_MAX = 64, MAXL = 4096, TB = 256;
+  int batch = BATCH;                     // levels queued per host round trip (small zones)
 
   int begin(cx_zone* zone, cudaStream_t stream)
   {
@@ -205,14 +206,14 @@ struct AdtBuild {
     if (nact > 0) { k_init_active<<<cx_grid(nact, TB), TB, 0, s>>>(S.actA, B.cur, nact); ctx->launches++; }
     act = S.actA; next = S.actB;
     L = 0; depth = 0;
-    CX_MALLOC(d_cnt, sizeof(int) * (MAXL + BATCH + 2), s);
-    CX_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (MAXL + BATCH + 2), s));
-    h_cnt = (int*)cx_pin_take(ctx, sizeof(int) * (BATCH + 2), &h_own);
+    CX_MALLOC(d_cnt, sizeof(int) * (MAXL + BATCH_MAX + 2), s);
+    CX_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (MAXL + BATCH_MAX + 2), s));
+    h_cnt = (int*)cx_pin_take(ctx, sizeof(int) * (BATCH_MAX + 2), &h_own);
     if (!h_cnt) { cx_set_error("ADT build: no page-locked memory"); return -2; }
     h_cnt[0] = nact;
     CX_CUDA(cudaMemcpyAsync(d_cnt, h_cnt, sizeof(int), cudaMemcpyHostToDevice, s));
-    CX_MALLOC(d_pcnt, sizeof(int) * (MAXL + BATCH + 2), s);
-    CX_CUDA(cudaMemsetAsync(d_pcnt, 0, sizeof(int) * (MAXL + BATCH + 2), s));
+    CX_MALLOC(d_pcnt, sizeof(int) * (MAXL + BATCH_MAX + 2), s);
+    CX_CUDA(cudaMemsetAsync(d_pcnt, 0, sizeof(int) * (MAXL + BATCH_MAX + 2), s));
     n0 = nact;                        // cells to place below the root
     cntAll.assign(1, nact);
     if (nact <= 0) done = true;
@@ -226,7 +227,7 @@ struct AdtBuild {
   {
     if (done) return 0;
     const int grid = cx_grid(nact, TB);
-    nb = nact > (1 << 21) ? 1 : BATCH;
+    nb = nact > (1 << 21) ? 1 : batch;
     for (int q = 0; q < nb; q++)
     {
       k_claim<<<grid, TB, 0, s>>>(L + q, q == 0 ? nact : -1, d_cnt, act, B);
@@ -316,6 +317,35 @@ int cx_build_adt(cx_zone* z)
   if (rc == 0) return b.end();
   cudaStreamSynchronize(z->ctx->stream);
   b.release();
+  return rc;
+}
+
+// A build that overlaps what the host does next (the upload of the following zones of a batch of hooks): the first 48
+// levels of a small zone are queued in one go on a side stream (grids sized by the zone, the active counts stay on
+// the device: a 100^3 zone has 35 levels), cx_adt_finish picks the build up again, queues what is left and ends it.
+int cx_adt_begin(cx_zone* z, cudaStream_t s)
+{
+  if (z->adt_pending || z->d_nodes) { cx_set_error("ADT build: the zone already has a tree or a build in flight"); return -1; }
+  AdtBuild* b = new AdtBuild;
+  int rc = b->begin(z, s);
+  if (rc == 0) { b->batch = 48; rc = b->enqueue_batch(); b->batch = AdtBuild::BATCH; }
+  if (rc != 0) { cudaStreamSynchronize(s); b->release(); delete b; return rc; }
+  z->adt_pending = b;
+  return 0;
+}
+
+int cx_adt_finish(cx_zone* z)
+{
+  AdtBuild* b = (AdtBuild*)z->adt_pending;
+  if (!b) return 0;
+  z->adt_pending = nullptr;
+  int rc = 0;
+  if (!b->done) rc = b->finish_batch();
+  while (rc == 0 && !b->done) { rc = b->enqueue_batch(); if (rc == 0) rc = b->finish_batch(); }
+  if (rc == 0) rc = b->subtree();
+  if (rc == 0) rc = b->end();
+  else { cudaStreamSynchronize(b->s); b->release(); }
+  delete b;
   return rc;
 }
 

@@ -411,17 +411,33 @@ int cx_zone_create_noadt(cx_ctx* c, int ni, int nj, int nk, const double* x, con
   return zone_create_impl(c, ni, nj, nk, x, y, z, cellN, true, out);
 }
 
+// Start the ADT build of a zone created with cx_zone_create_noadt on a side stream and return at once: the build
+// then overlaps the upload of the next zones of a batch of hooks.  cx_zones_build_adt finishes it.
+int cx_zone_adt_begin(cx_zone* zn)
+{
+  cx_ctx* c = zn->ctx;
+  if (zn->topo == 0) return 0;
+  CX_CUDA(cudaSetDevice(c->device));
+  const int k = (int)(c->aux_next++ % 8);
+  while (c->naux <= k) { CX_CUDA(cudaStreamCreateWithFlags(&c->aux[c->naux], cudaStreamNonBlocking)); c->naux++; }
+  return cx_adt_begin(zn, c->aux[k]);
+}
+
 // ADTs of a batch of zones created with cx_zone_create_noadt, built concurrently (one side stream per zone, up to 8);
-// zones that have their tree already, and Cartesian (InterpCart) zones, are skipped
+// builds started with cx_zone_adt_begin are finished; zones that have their tree already, and Cartesian (InterpCart)
+// zones, are skipped
 int cx_zones_build_adt(cx_ctx* c, int nz, cx_zone* const* zones)
 {
   CX_CUDA(cudaSetDevice(c->device));
   std::vector<cx_zone*> todo;
+  int rcp = 0;
   for (int i = 0; i < nz; i++)
   {
     if (!zones[i] || zones[i]->ctx != c) { cx_set_error("cx_zones_build_adt: zone %d does not belong to this context", i); return -1; }
-    if (zones[i]->topo != 0 && !zones[i]->d_nodes) todo.push_back(zones[i]);
+    if (zones[i]->adt_pending) { int rc = cx_adt_finish(zones[i]); if (rc != 0 && rcp == 0) rcp = rc; }
+    else if (zones[i]->topo != 0 && !zones[i]->d_nodes) todo.push_back(zones[i]);
   }
+  if (rcp != 0) return rcp;
   if (todo.empty()) return 0;
   if (todo.size() == 1) return cx_build_adt(todo[0]);
   const int want = (int)std::min<size_t>(8, todo.size());
@@ -552,6 +568,7 @@ int cx_zone_export_adt(cx_zone* zn, void* nodes_out, size_t bytes)
 int cx_zone_destroy(cx_zone* zn)
 {
   if (!zn) return 0;
+  if (zn->adt_pending) cx_adt_finish(zn);
   cudaFree(zn->d_x); cudaFree(zn->d_nodes);   // d_y, d_z, d_cellN live in d_x's block
   delete zn;
   return 0;
@@ -609,7 +626,7 @@ static int set_interp_data_impl(cx_ctx* c, int nrcv, const double* d_xr, const d
   std::vector<ZoneView> hv(nz);
   for (int i = 0; i < nz; i++)
   {
-    if (!zones[i] || (zones[i]->topo != 0 && !zones[i]->d_nodes)) { cx_set_error("setInterpData: donor zone %d has no ADT", i); return -1; }
+    if (!zones[i] || (zones[i]->topo != 0 && (!zones[i]->d_nodes || zones[i]->adt_pending))) { cx_set_error("setInterpData: donor zone %d has no ADT", i); return -1; }
     hv[i] = make_view(zones[i]);
   }
   // the zone table goes up from a page-locked block of the context's pool and belongs to the result until the search

@@ -49,7 +49,7 @@ struct cx_ctx {
   // free page-locked blocks (CX_PIN_BLOCK bytes each) for the zone tables and the counts of searches in flight
   void* pin_pool;   // std::vector<void*>*
   // side streams for work that overlaps across zones (batched ADT builds), created on first use
-  cudaStream_t aux[8]; int naux;
+  cudaStream_t aux[8]; int naux; unsigned aux_next;
   int search_slot;   // 0: searches run on the main stream; k > 0: on side stream k-1 (cx_ctx_search_slot)
 };
 #define CX_PIN_BLOCK 16384
@@ -70,6 +70,7 @@ struct cx_zone {
   float build_ms;
   int topo;           // 1: ADT donor, 0: regular Cartesian donor (InterpCart), no tree
   double h[3];        // topo 0: spacings
+  void* adt_pending;  // a build started by cx_adt_begin and not yet finished (AdtBuild*)
 };
 
 struct cx_result {
@@ -125,6 +126,9 @@ int cx_exclusive_scan_u64(cx_ctx* ctx, const unsigned long long* d_in, unsigned 
 // ADT build (cx_adt.cu)
 int cx_build_adt(cx_zone* z);
 int cx_build_adt_many(int nz, cx_zone* const* zones, int nstreams, cudaStream_t* streams);
+// start the build of one zone on stream s without waiting for it (the first levels are queued in one go), finish it later
+int cx_adt_begin(cx_zone* z, cudaStream_t s);
+int cx_adt_finish(cx_zone* z);
 
 // stream-ordered allocation (pool keeps freed blocks: release threshold = max, set at ctx creation);
 // pointers obtained here may also be released with plain cudaFree

@@ -80,6 +80,9 @@ int cx_zone_info(cx_zone* zone, double bbox[6], int* ncells, int* depth, float* 
  * leaves the GPU idle; eight at a time fill it).  The result is the tree cx_zone_create builds. */
 int cx_zone_create_noadt(cx_ctx* ctx, int ni, int nj, int nk, const double* x, const double* y, const double* z,
                          const double* cellN, cx_zone** out);
+/* cx_zone_adt_begin starts the build of one such zone on a side stream and returns at once (it then overlaps the upload
+ * of the next zones); cx_zones_build_adt finishes the builds in flight and builds the rest. */
+int cx_zone_adt_begin(cx_zone* zone);
 int cx_zones_build_adt(cx_ctx* ctx, int nzones, cx_zone* const* zones);
 int cx_zone_candidates(cx_zone* zone, double x, double y, double z, double alphaTol, int* out, int cap, int* n);
 /* test/debug: copy the ADT replica to the host, 128-byte nodes (see cx_core.cuh AdtNode) */
