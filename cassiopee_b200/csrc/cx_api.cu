@@ -365,8 +365,10 @@ static int zone_create_impl(cx_ctx* c, int ni, int nj, int nk, const double* x, 
   zn->ncells = (ni - 1) * (nj - 1) * std::max(nk - 1, 1);
   zn->topo = 1;
   size_t nb = sizeof(double) * (size_t)zn->npts;
-  // x, y, z, cellN in one block (one allocation instead of four)
-  CX_CUDA(cudaMalloc(&zn->d_x, 4 * nb));
+  // x, y, z, cellN in one block (one allocation instead of four), from the stream-ordered pool: the blocks of the
+  // previous call's hooks are reused instead of going back to the driver (cudaFree of a 30-150 MB block synchronises
+  // the device and unmaps; when Python collected the old hooks in the middle of a call that showed as 30-40 ms outliers)
+  CX_MALLOC(zn->d_x, 4 * nb, c->stream);
   zn->d_y = zn->d_x + zn->npts; zn->d_z = zn->d_y + zn->npts; zn->d_cellN = zn->d_z + zn->npts;
   double t1 = wall_ms();
   CX_CHECK(cx_upload(c, zn->d_x, x, nb));
@@ -472,7 +474,7 @@ int cx_zone_create_cart(cx_ctx* c, int ni, int nj, int nk, const double* x, cons
   zn->bbox[4] = zn->bbox[1] + (nj - 1) * zn->h[1];
   zn->bbox[5] = zn->bbox[2] + (nk - 1) * zn->h[2];
   size_t nb = sizeof(double) * (size_t)zn->npts;
-  CX_CUDA(cudaMalloc(&zn->d_x, 4 * nb));
+  CX_MALLOC(zn->d_x, 4 * nb, c->stream);
   zn->d_y = zn->d_x + zn->npts; zn->d_z = zn->d_y + zn->npts; zn->d_cellN = zn->d_z + zn->npts;
   CX_CHECK(cx_upload(c, zn->d_x, x, nb));
   CX_CHECK(cx_upload(c, zn->d_y, y, nb));
@@ -569,7 +571,11 @@ int cx_zone_destroy(cx_zone* zn)
 {
   if (!zn) return 0;
   if (zn->adt_pending) cx_adt_finish(zn);
-  cudaFree(zn->d_x); cudaFree(zn->d_nodes);   // d_y, d_z, d_cellN live in d_x's block
+  // d_y, d_z, d_cellN live in d_x's block; pool blocks go back to the pool in stream order, the few allocations too
+  // large for it (cx_malloc_async) to the driver
+  const size_t bx = 4 * sizeof(double) * (size_t)zn->npts, bn = sizeof(AdtNode) * (size_t)zn->ncells;
+  if (zn->d_x) { if (bx > cx_async_max_bytes()) cudaFree(zn->d_x); else cudaFreeAsync(zn->d_x, zn->ctx->stream); }
+  if (zn->d_nodes) { if (bn > cx_async_max_bytes()) cudaFree(zn->d_nodes); else cudaFreeAsync(zn->d_nodes, zn->ctx->stream); }
   delete zn;
   return 0;
 }
