@@ -23,6 +23,7 @@ class Comm:
         self.ctx = ctx
         self.device = (ctx is not None) if device is None else device
         self._dist = None
+        self._nccl_ready = False
         if self.size > 1:
             import torch.distributed as dist
             if not dist.is_initialized():
@@ -40,14 +41,30 @@ class Comm:
             w = np.zeros(8, np.uint8)
             self.exchange_host({p: w for p in range(self.size) if p != self.rank},
                                {p: 8 for p in range(self.size) if p != self.rank})
+            self._nccl_ready = os.environ.get("CX_ALLGATHER", "gloo") == "nccl"
 
     # -- small objects ------------------------------------------------------
     def allgather_obj(self, obj):
         if self.size == 1:
             return [obj]
+        if self._nccl_ready:
+            return self._allgather_obj_nccl(obj)
         out = [None] * self.size
         self._dist.all_gather_object(out, obj)
         return out
+
+    def _allgather_obj_nccl(self, obj):
+        """The pickled object of every rank through the library's NCCL communicator (two grouped exchanges: sizes,
+        then the blobs): the tree layer gathers small metadata four or five times per distributed setInterpData,
+        and a gloo all_gather_object costs several milliseconds each at 8 ranks (CX_ALLGATHER=gloo keeps it)."""
+        import pickle
+        blob = np.frombuffer(pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL), dtype=np.uint8)
+        peers = [p for p in range(self.size) if p != self.rank]
+        mysize = np.array([blob.size], np.int64).view(np.uint8)
+        sizes = self._exchange_via_nccl({p: mysize for p in peers}, {p: 8 for p in peers}, np.uint8)
+        nbytes = {p: int(sizes[p].view(np.int64)[0]) for p in peers}
+        got = self._exchange_via_nccl({p: blob for p in peers}, nbytes, np.uint8)
+        return [obj if p == self.rank else pickle.loads(got[p].tobytes()) for p in range(self.size)]
 
     def barrier(self):
         if self.size == 1:
