@@ -41,7 +41,7 @@ class Comm:
             w = np.zeros(8, np.uint8)
             self.exchange_host({p: w for p in range(self.size) if p != self.rank},
                                {p: 8 for p in range(self.size) if p != self.rank})
-            self._nccl_ready = os.environ.get("CX_ALLGATHER", "gloo") == "nccl"
+            self._nccl_ready = os.environ.get("CX_ALLGATHER", "nccl") != "gloo"
 
     # -- small objects ------------------------------------------------------
     def allgather_obj(self, obj):
