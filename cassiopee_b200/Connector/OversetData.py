@@ -416,10 +416,12 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
         if verbose != 0:
             print('Zone %s: interpolated=%d ; extrapolated=%d ; orphan=%d' % (z[0], nbinterpolated, nbextrapolated, nborphan))
             if nborphan > 0: print('Warning: zone %s has %d orphan points !' % (z[0], nborphan))
-        # local position -> index in the receptor zone (indcell), vectorised
+        # local position -> index in the receptor zone (indcell), vectorised; when every point of the zone is a receptor
+        # the map is the identity and the lists are kept as they are
         indcells = sel.astype(Internal.E_NpyInt)
+        identity = sel.size == cellN.size
         if nborphan > 0:
-            resInterp[5] = indcells[resInterp[5]]
+            if not identity: resInterp[5] = indcells[resInterp[5]]
             if verbose == 3:     # force cellN#Orphan = -1 at the orphan points (OversetData.py:1287-1294)
                 pre = 'centers:' if locR == 'centers' else ''
                 if Internal.getNodeFromName2(z, 'cellN#Orphan') is None:
@@ -427,10 +429,10 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
                 co = C.getFieldArray(z, pre + 'cellN#Orphan')
                 co.reshape(-1, order='F')[resInterp[5]] = -1.
         for noz in range(nzonesDnr):
-            if resInterp[0][noz].size > 0:
+            if resInterp[0][noz].size > 0 and not identity:
                 resInterp[0][noz] = indcells[resInterp[0][noz]]
             if resInterp[4][noz].size > 0:
-                resInterp[4][noz] = indcells[resInterp[4][noz]]
+                if not identity: resInterp[4][noz] = indcells[resInterp[4][noz]]
                 if verbose == 3:     # force cellN#Orphan = -2 at the extrapolated points (OversetData.py:1313-1319)
                     pre = 'centers:' if locR == 'centers' else ''
                     if Internal.getNodeFromName2(z, 'cellN#Orphan') is None:
@@ -484,8 +486,19 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
                 x, y, zc = C.getCoords(z)
                 cellN = C.getFieldArray(z, 'cellN' if locR == 'nodes' else 'centers:cellN')
                 _, ni_r, nj_r, nk_r, _ = Internal.getZoneDim(z)
-                rcvPts = backend.select_receptors(ni_r, nj_r, nk_r, x.reshape(-1, order='F'), y.reshape(-1, order='F'),
-                                                  zc.reshape(-1, order='F'), cellN.reshape(-1, order='F'), locR)
+                # a tree interpolated from itself at the nodes: the zone is resident as a donor hook already (same node
+                # coordinates, same node cellN), its receptor points are taken from there and nothing is uploaded
+                own = None
+                if locR == 'nodes' and hasattr(backend, 'select_receptors_from_hook'):
+                    for i, zo in enumerate(zonesDnrL):
+                        if zo is z and allHooksL[i] is not None and zo[0] not in deviceOnly:
+                            own = allHooksL[i]
+                            break
+                if own is not None:
+                    rcvPts = backend.select_receptors_from_hook(own)
+                else:
+                    rcvPts = backend.select_receptors(ni_r, nj_r, nk_r, x.reshape(-1, order='F'), y.reshape(-1, order='F'),
+                                                      zc.reshape(-1, order='F'), cellN.reshape(-1, order='F'), locR)
                 sel = rcvPts.indcell
                 _tt['pts'] += _time.perf_counter() - _t0
                 if len(zonesDnr) == 0:

@@ -55,6 +55,7 @@ _SIGS = {
     "cx_set_interp_data": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "cx_set_interp_data_dev": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "cx_receptors_create": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    "cx_receptors_from_zone": (_i, [_vp, _vp, _vp]),
     "cx_receptors_count": (_i, [_vp, _vp]),
     "cx_receptors_fetch": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "cx_receptors_destroy": (_i, [_vp]),
@@ -496,6 +497,21 @@ class Receptors:
         self.n = n.value
         self._ind = None
 
+    @classmethod
+    def from_zone(cls, ctx, zone):
+        """Receptor points (node cellN == 2) of a zone that is resident as a donor hook: nothing is uploaded."""
+        r = cls.__new__(cls)
+        r.ctx = ctx
+        h = _vp()
+        check(lib().cx_receptors_from_zone(ctx.h, zone.h, ctypes.byref(h)))
+        r.h = h
+        r._fin = weakref.finalize(r, lib().cx_receptors_destroy, h)
+        n = _i()
+        check(lib().cx_receptors_count(h, ctypes.byref(n)))
+        r.n = n.value
+        r._ind = None
+        return r
+
     @property
     def indcell(self):
         if self._ind is None:
@@ -857,6 +873,10 @@ class DeviceBackend:
     def select_receptors(self, ni, nj, nk, x, y, z, cellN, loc):
         """Receptor points (cellN == 2 at loc) of one zone, extracted and kept on the device."""
         return Receptors(self.ctx, ni, nj, nk, x, y, z, cellN, loc)
+
+    def select_receptors_from_hook(self, hook):
+        """The receptor points of a zone whose donor hook `hook` holds the same node coordinates and node cellN."""
+        return Receptors.from_zone(self.ctx, hook)
 
     def set_interp_data_rcv(self, rcv, hooks, order, nature, penalty, extrap):
         # large lists land in page-locked arrays of the reuse pool (they become the tree's numpy arrays)

@@ -173,6 +173,7 @@ struct AdtBuild {
   bool done;
   static constexpr int BATCH = 8, BATCH_MAX = 64, MAXL = 4096, TB = 256;
   int batch = BATCH;                     // levels queued per host round trip (small zones)
+  bool force_batch = false;              // queue `batch` levels whatever the size (cx_adt_begin: the build overlaps an upload)
 
   int begin(cx_zone* zone, cudaStream_t stream)
   {
@@ -227,7 +228,7 @@ struct AdtBuild {
   {
     if (done) return 0;
     const int grid = cx_grid(nact, TB);
-    nb = nact > (1 << 21) ? 1 : batch;
+    nb = (nact > (1 << 21) && !force_batch) ? 1 : batch;
     for (int q = 0; q < nb; q++)
     {
       k_claim<<<grid, TB, 0, s>>>(L + q, q == 0 ? nact : -1, d_cnt, act, B);
@@ -328,7 +329,9 @@ int cx_adt_begin(cx_zone* z, cudaStream_t s)
   if (z->adt_pending || z->d_nodes) { cx_set_error("ADT build: the zone already has a tree or a build in flight"); return -1; }
   AdtBuild* b = new AdtBuild;
   int rc = b->begin(z, s);
-  if (rc == 0) { b->batch = 48; rc = b->enqueue_batch(); b->batch = AdtBuild::BATCH; }
+  // (a large zone pays ~7 % for launches over a stale active count -- 39.2 vs 41.9 ms at 16.6 M cells -- and gains the
+  // whole upload of the next zone)
+  if (rc == 0) { b->batch = 48; b->force_batch = true; rc = b->enqueue_batch(); b->batch = AdtBuild::BATCH; b->force_batch = false; }
   if (rc != 0) { cudaStreamSynchronize(s); b->release(); delete b; return rc; }
   z->adt_pending = b;
   return 0;

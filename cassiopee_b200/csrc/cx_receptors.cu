@@ -134,6 +134,46 @@ int cx_receptors_create(cx_ctx* c, int ni, int nj, int nk, const double* x, cons
   return 0;
 }
 
+// The receptor points of a zone that is ALSO resident as a donor hook (a tree interpolated from itself, loc='nodes':
+// the node coordinates and the node cellN of the hook are the receptor zone's own): nothing is uploaded.
+int cx_receptors_from_zone(cx_ctx* c, cx_zone* zn, cx_receptors** out)
+{
+  if (zn->ctx != c) { cx_set_error("getInterpolatedPoints: zone and context differ"); return -1; }
+  CX_CUDA(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  const size_t np = (size_t)zn->npts;
+  cx_receptors* R = new cx_receptors;
+  R->ctx = c; R->n = 0; R->npts = (int)np; R->d_ind = nullptr; R->d_x = R->d_y = R->d_z = nullptr;
+  unsigned long long *f, *p;
+  CX_MALLOC(f, sizeof(unsigned long long) * np, s); CX_MALLOC(p, sizeof(unsigned long long) * np, s);
+  k_rcv_flag<<<cx_grid((long long)np, 256), 256, 0, s>>>((int)np, zn->d_cellN, f);
+  c->launches++;
+  unsigned long long tot = 0;
+  int rc = cx_exclusive_scan_u64(c, f, p, (int)np, &tot);
+  if (rc == 0)
+  {
+    R->n = (int)tot;
+    const size_t m = tot ? (size_t)tot : 1;
+    cudaError_t e = cx_malloc_async((void**)&R->d_ind, sizeof(int) * m, s);
+    if (e == cudaSuccess) e = cx_malloc_async((void**)&R->d_x, sizeof(double) * m, s);
+    if (e == cudaSuccess) e = cx_malloc_async((void**)&R->d_y, sizeof(double) * m, s);
+    if (e == cudaSuccess) e = cx_malloc_async((void**)&R->d_z, sizeof(double) * m, s);
+    if (e != cudaSuccess) { cx_set_error("receptor extraction: %s", cudaGetErrorString(e)); rc = -2; }
+  }
+  if (rc == 0 && tot > 0)
+  {
+    k_rcv_gather<<<cx_grid((long long)np, 256), 256, 0, s>>>((int)np, 0, zn->ni, zn->nj, zn->nk, f, p, zn->d_x, zn->d_y, zn->d_z,
+                                                             R->d_ind, R->d_x, R->d_y, R->d_z);
+    c->launches++;
+  }
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (rc == 0 && e != cudaSuccess) { cx_set_error("receptor extraction: %s", cudaGetErrorString(e)); rc = -2; }
+  cudaFreeAsync(f, s); cudaFreeAsync(p, s);
+  if (rc != 0) { cx_receptors_destroy(R); return rc; }
+  *out = R;
+  return 0;
+}
+
 int cx_receptors_count(cx_receptors* R, int* n) { *n = R->n; return 0; }
 
 int cx_receptors_fetch(cx_receptors* R, int* indcell, double* x, double* y, double* z)

@@ -126,6 +126,9 @@ int cx_set_interp_data_dev(cx_ctx* ctx, int nrcv, const double* d_xr, const doub
  * cellN: host, at nodes (loc 0) or at centres (loc 1: (ni-1)*(nj-1)*(nk-1) values). */
 int cx_receptors_create(cx_ctx* ctx, int ni, int nj, int nk, const double* x, const double* y, const double* z,
                         const double* cellN, int loc, cx_receptors** out);
+/* the same for a zone that is also resident as a donor hook (a tree interpolated from itself, loc = nodes): the hook's
+ * node coordinates and node cellN are the receptor zone's own, nothing is uploaded */
+int cx_receptors_from_zone(cx_ctx* ctx, cx_zone* zone, cx_receptors** out);
 int cx_receptors_count(cx_receptors* rcv, int* n);
 /* copies to the host: indcell[n] (index in the zone at loc, ascending) and/or the coordinates; any may be NULL */
 int cx_receptors_fetch(cx_receptors* rcv, int* indcell, double* x, double* y, double* z);

@@ -1130,3 +1130,37 @@ def test_preparers_through_the_tree_layer(ctx):
     for g, r in zip(*out):
         assert np.array_equal(g, r)
     assert (out[0][1] == 2.).sum() > 2 * 13 * 11 and (out[0][1] == 0.).sum() == 27
+
+
+def test_batched_hooks_build_the_same_trees(ctx):
+    """DeviceBackend.make_zones (uploads zone after zone, every ADT build started on a side stream while the next zone
+    goes up, a long first batch of levels whatever the zone size) gives node for node the tree Zone() builds alone:
+    a zone above the 2^21-cell threshold of the one-level-per-round-trip regime, small zones, a 2-D zone, a Cartesian
+    (InterpCart) zone in the middle of the batch."""
+    from cassiopee_b200 import _lib
+    rng = np.random.default_rng(21)
+
+    def grid(ni, nj, nk, h, o, wobble):
+        i, j, k = np.meshgrid(np.arange(ni), np.arange(nj), np.arange(nk), indexing='ij')
+        x = o[0] + h * i + wobble * np.sin(0.7 * j + 0.3 * k); y = o[1] + h * j + wobble * np.sin(0.5 * k + 0.2 * i)
+        z = o[2] + h * k + (wobble * np.sin(0.9 * i + 0.4 * j) if nk > 1 else 0.)
+        return [a.reshape(-1, order='F') for a in (x, y, z)]
+    specs = []
+    for (ni, nj, nk, ty) in ((131, 131, 131, 1), (23, 19, 17, 1), (40, 33, 1, 1), (21, 21, 21, 0), (64, 48, 40, 1)):
+        x, y, z = grid(ni, nj, nk, 0.1, rng.random(3), 0.02 if ty == 1 else 0.)
+        c = np.ones(ni * nj * nk); c[rng.random(c.size) < 0.05] = 0.
+        specs.append((ni, nj, nk, x, y, z, c, ty))
+    assert (131 - 1) ** 3 > 1 << 21
+    batch = _lib.DeviceBackend(ctx).make_zones(specs)
+    for sp, zb in zip(specs, batch):
+        alone = _lib.Zone(ctx, *sp[:7], interpDataType=sp[7])
+        ia, ib = alone.info(), zb.info()
+        assert ia["depth"] == ib["depth"] and np.array_equal(ia["bbox"], ib["bbox"])
+        if sp[7] == 1:
+            assert np.array_equal(alone.export_adt().view(np.uint8), zb.export_adt().view(np.uint8))
+    # and they answer a search like the ones built alone
+    pts = [rng.random(5000) * 2. for _ in range(3)]
+    ra = _lib.set_interp_data(ctx, *pts, [batch[1], batch[4]], 2, 1, 1, 1).fetch()
+    rb = _lib.set_interp_data(ctx, *pts, [_lib.Zone(ctx, *specs[1][:7]), _lib.Zone(ctx, *specs[4][:7])], 2, 1, 1, 1).fetch()
+    for k in range(5):
+        for a, b in zip(ra[k], rb[k]): assert np.array_equal(a, b)
