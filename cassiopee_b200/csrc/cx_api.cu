@@ -609,13 +609,14 @@ int cx_set_interp_data_dw(cx_ctx* c, int nrcv, const double* const* xr, const do
     pz[i].x = blk + (3 * (size_t)i) * n; pz[i].y = blk + (3 * (size_t)i + 1) * n; pz[i].z = blk + (3 * (size_t)i + 2) * n;
     if (nrcv > 0)
     {
-      CX_CHECK(cx_upload(c, (void*)pz[i].x, xr[i], sizeof(double) * (size_t)nrcv));
-      CX_CHECK(cx_upload(c, (void*)pz[i].y, yr[i], sizeof(double) * (size_t)nrcv));
-      CX_CHECK(cx_upload(c, (void*)pz[i].z, zr[i], sizeof(double) * (size_t)nrcv));
+      int rcu = cx_upload(c, (void*)pz[i].x, xr[i], sizeof(double) * (size_t)nrcv);
+      if (rcu == 0) rcu = cx_upload(c, (void*)pz[i].y, yr[i], sizeof(double) * (size_t)nrcv);
+      if (rcu == 0) rcu = cx_upload(c, (void*)pz[i].z, zr[i], sizeof(double) * (size_t)nrcv);
+      if (rcu != 0) { cudaFree(blk); return rcu; }
     }
   }
   RcvPerZone* d_pz = (RcvPerZone*)(blk + 3 * n * nz);
-  CX_CHECK(cx_upload(c, d_pz, pz.data(), sizeof(RcvPerZone) * (size_t)nz));
+  { int rcu = cx_upload(c, d_pz, pz.data(), sizeof(RcvPerZone) * (size_t)nz); if (rcu != 0) { cudaFree(blk); return rcu; } }
   int rc = set_interp_data_impl(c, nrcv, pz[0].x, pz[0].y, pz[0].z, d_pz, blk, nz, zones, order, nature, penalty, 1, out);
   if (rc != 0) cudaFree(blk);
   return rc;
