@@ -85,8 +85,6 @@ def _setInterpDataDW(interpPts, zonesD, order, nature, penalty, hook, ctx=None):
     if order not in (2, 3, 5):
         print("Warning: setInterpDataDW: unknown interpolation order. Set to 2nd order.")
         order = 2
-    if order != 2:
-        raise NotImplementedError("setInterpDataDW: only order 2 has a device path.")
     ctx = ctx or _lib.default_context()
     pts = []
     for a in interpPts:

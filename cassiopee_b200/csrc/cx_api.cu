@@ -110,7 +110,7 @@ struct cx_result_dev {
 void cx_zone_bbox_host(int ni, int nj, int nk, const double* x, const double* y, const double* z, double* bb);
 int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, const double* d_zr, int nz,
                   const ZoneView* d_zones, const ZoneView* h_zones, int order, int nature, int penalty, int extrap,
-                  cx_result* R, cx_result_dev* D, const RcvPerZone* d_pz);
+                  cx_result* R, cx_result_dev* D, const RcvPerZone* d_pz, const RcvPerZone* h_pz);
 int cx_search_finish(cx_result* R, cx_result_dev* D);
 int cx_plan_build(cx_ctx* ctx, int imd, int jmd, long long nptsD, long long nptsR, int n, const int* donor,
                   const int* rcv, const int* type, const double* coefs, long long ncoefs, cx_plan* P);
@@ -582,13 +582,13 @@ int cx_zone_destroy(cx_zone* zn)
 
 /* ---- setInterpData --------------------------------------------------------- */
 static int set_interp_data_impl(cx_ctx* c, int nrcv, const double* d_xr, const double* d_yr, const double* d_zr,
-                                const RcvPerZone* d_pz, void* dw_block, int nz, cx_zone* const* zones, int order,
-                                int nature, int penalty, int extrap, cx_result** out);
+                                const RcvPerZone* d_pz, const RcvPerZone* h_pz, void* dw_block, int nz,
+                                cx_zone* const* zones, int order, int nature, int penalty, int extrap, cx_result** out);
 
 int cx_set_interp_data_dev(cx_ctx* c, int nrcv, const double* d_xr, const double* d_yr, const double* d_zr, int nz,
                            cx_zone* const* zones, int order, int nature, int penalty, int extrap, cx_result** out)
 {
-  return set_interp_data_impl(c, nrcv, d_xr, d_yr, d_zr, nullptr, nullptr, nz, zones, order, nature, penalty, extrap, out);
+  return set_interp_data_impl(c, nrcv, d_xr, d_yr, d_zr, nullptr, nullptr, nullptr, nz, zones, order, nature, penalty, extrap, out);
 }
 
 // Double wall: connector.setInterpDataDW(receiverArrays, donorArrays, order, nature, penalty, hook)
@@ -597,7 +597,7 @@ int cx_set_interp_data_dev(cx_ctx* c, int nrcv, const double* d_xr, const double
 int cx_set_interp_data_dw(cx_ctx* c, int nrcv, const double* const* xr, const double* const* yr, const double* const* zr,
                           int nz, cx_zone* const* zones, int order, int nature, int penalty, cx_result** out)
 {
-  if (order != 2) { cx_set_error("setInterpDataDW: only order 2 has a device path"); return -4; }
+  if (order != 2 && order != 3 && order != 5) { cx_set_error("setInterpDataDW: order %d (2, 3 or 5)", order); return -4; }
   if (nz <= 0) { cx_set_error("setInterpDataDW: no valid donor zone found."); return -1; }
   CX_CUDA(cudaSetDevice(c->device));
   const size_t n = (size_t)std::max(nrcv, 1);
@@ -617,14 +617,14 @@ int cx_set_interp_data_dw(cx_ctx* c, int nrcv, const double* const* xr, const do
   }
   RcvPerZone* d_pz = (RcvPerZone*)(blk + 3 * n * nz);
   { int rcu = cx_upload(c, d_pz, pz.data(), sizeof(RcvPerZone) * (size_t)nz); if (rcu != 0) { cudaFree(blk); return rcu; } }
-  int rc = set_interp_data_impl(c, nrcv, pz[0].x, pz[0].y, pz[0].z, d_pz, blk, nz, zones, order, nature, penalty, 1, out);
+  int rc = set_interp_data_impl(c, nrcv, pz[0].x, pz[0].y, pz[0].z, d_pz, pz.data(), blk, nz, zones, order, nature, penalty, 1, out);
   if (rc != 0) cudaFree(blk);
   return rc;
 }
 
 static int set_interp_data_impl(cx_ctx* c, int nrcv, const double* d_xr, const double* d_yr, const double* d_zr,
-                                const RcvPerZone* d_pz, void* dw_block, int nz, cx_zone* const* zones, int order,
-                                int nature, int penalty, int extrap, cx_result** out)
+                                const RcvPerZone* d_pz, const RcvPerZone* h_pz, void* dw_block, int nz,
+                                cx_zone* const* zones, int order, int nature, int penalty, int extrap, cx_result** out)
 {
   if (order != 2 && order != 3 && order != 4 && order != 5)
   { cx_set_error("setInterpData: order %d not supported on the device (2, 3, 4 or 5)", order); return -4; }
@@ -662,7 +662,7 @@ static int set_interp_data_impl(cx_ctx* c, int nrcv, const double* d_xr, const d
   if (!F->R.h_zones) { cx_set_error("setInterpData: no page-locked memory for the zone table"); delete F; return -2; }
   memcpy(F->R.h_zones, hv.data(), sizeof(ZoneView) * (size_t)nz);
   CX_CUDA(cudaMemcpyAsync(d_zones, F->R.h_zones, sizeof(ZoneView) * (size_t)nz, cudaMemcpyHostToDevice, c->stream));
-  int rc = cx_search_run(c, nrcv, d_xr, d_yr, d_zr, nz, d_zones, hv.data(), order, nature, penalty, extrap, &F->R, &F->D, d_pz);
+  int rc = cx_search_run(c, nrcv, d_xr, d_yr, d_zr, nz, d_zones, hv.data(), order, nature, penalty, extrap, &F->R, &F->D, d_pz, h_pz);
   if (rc != 0) { cx_result_destroy(&F->R); return rc; }
   F->R.d_dw_owned = dw_block;       // the per-zone receptor coordinates live as long as the result
   *out = &F->R;

@@ -725,10 +725,12 @@ __global__ void k_list(int n, const unsigned long long* __restrict__ f, const un
 
 }  // namespace
 
-int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_xr, const double* d_yr, const double* d_zr,
+int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_xr0, const double* d_yr0, const double* d_zr0,
                          int nz, const ZoneView* d_zones, const ZoneView* h_zones, int nature, int penalty, int* noblk,
-                         int* type, int* dind, double* cf, int ncfmax, unsigned long long* d_stats)
+                         int* type, int* dind, double* cf, int ncfmax, unsigned long long* d_stats, const RcvPerZone* h_pz)
 {
+  // h_pz (host copy of the double-wall table, or nullptr): donor zone noz sees the receptors at h_pz[noz]; the zones go
+  // through one after the other, so each zone's launches simply get that zone's coordinate arrays
   cudaStream_t s = ctx->stream;
   LagState S;
   size_t N = n;
@@ -767,6 +769,8 @@ int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_xr, cons
   }
   for (int noz = 0; noz < nz; noz++)
   {
+    const double* d_xr = h_pz ? h_pz[noz].x : d_xr0; const double* d_yr = h_pz ? h_pz[noz].y : d_yr0;
+    const double* d_zr = h_pz ? h_pz[noz].z : d_zr0;
     const int cap = std::max(4, h_zones[noz].depth + 2);
     const size_t smsearch = (size_t)TB * (24 * sizeof(double) + (size_t)cap * sizeof(int));
     if (smsearch > 200 * 1024) { cx_set_error("setInterpData: ADT depth %d needs %zu bytes of shared memory per CTA", cap - 2, smsearch); return -1; }

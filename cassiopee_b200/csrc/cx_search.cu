@@ -542,14 +542,14 @@ struct cx_result_dev {
 extern int cx_lagrange_pipeline(cx_ctx* ctx, int order, int n, const double* d_xr, const double* d_yr,
                                 const double* d_zr, int nz, const ZoneView* d_zones, const ZoneView* h_zones,
                                 int nature, int penalty, int* noblk, int* type, int* dind, double* cf, int ncfmax,
-                                unsigned long long* d_stats);
+                                unsigned long long* d_stats, const RcvPerZone* h_pz);
 
 int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, const double* d_zr, int nz,
                   const ZoneView* d_zones, const ZoneView* h_zones, int order, int nature, int penalty, int extrap,
-                  cx_result* R, cx_result_dev* D, const RcvPerZone* d_pz)
+                  cx_result* R, cx_result_dev* D, const RcvPerZone* d_pz, const RcvPerZone* h_pz)
 {
   cudaStream_t s = ctx->stream;
-  if (d_pz && order != 2) { cx_set_error("setInterpDataDW: only order 2 has a device path"); return -4; }
+  if (d_pz && order == 4) { cx_set_error("setInterpDataDW: orders 2, 3 and 5 (the reference knows no order 4 here)"); return -4; }
   const int ncfmax = (order == 3) ? 9 : (order == 4) ? 12 : (order == 5) ? 15 : 8;   // setInterpData.cpp:624-652
   R->nrcv = n; R->nz = nz; R->ncfmax = ncfmax;
   R->cnt.assign(nz, 0); R->ncoef.assign(nz, 0); R->nextrap.assign(nz, 0); R->norphan = 0;
@@ -598,7 +598,7 @@ int cx_search_run(cx_ctx* ctx, int n, const double* d_xr, const double* d_yr, co
   {
     CX_CUDA(cudaMemsetAsync(R->d_isext, 0, sizeof(int) * N, s));
     CX_CHECK(cx_lagrange_pipeline(ctx, order, n, d_xr, d_yr, d_zr, nz, d_zones, h_zones, nature, penalty,
-                                  R->d_noblk, R->d_type, R->d_dind, R->d_cf, ncfmax, d_stats));
+                                  R->d_noblk, R->d_type, R->d_dind, R->d_cf, ncfmax, d_stats, h_pz));
   }
   CX_CUDA(cudaEventRecord(R->ev[1], s));
 

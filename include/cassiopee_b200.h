@@ -143,7 +143,8 @@ int cx_set_interp_data_rcv(cx_ctx* ctx, cx_receptors* rcv, int nz, cx_zone* cons
 /* Double wall: connector.setInterpDataDW(receiverArrays, donorArrays, order, nature, penalty, hook)
  * (Connector/Connector/setInterpData.cpp:1346-1890, K_INTERP::getInterpolationCellDW Interp.cpp:176-255): xr[noz], yr[noz],
  * zr[noz] (host, nrcv values each) are the receptor points as donor zone noz must see them (projected onto its walls by
- * the caller); extrapolation is always on; order 2 (others return -4).  The result is read like cx_set_interp_data's. */
+ * the caller); extrapolation is always on; orders 2, 3 and 5 like the reference (4 returns -4).  The result is read like
+ * cx_set_interp_data's. */
 int cx_set_interp_data_dw(cx_ctx* ctx, int nrcv, const double* const* xr, const double* const* yr,
                           const double* const* zr, int nzones, cx_zone* const* zones, int order, int nature, int penalty,
                           cx_result** out);

@@ -83,8 +83,20 @@ def test_double_wall_matches_reference(ctx):
     # the displaced zone really changes the outcome
     same = _lib.set_interp_data_dw(ctx, [pa, pa], gz, 2, 1, 1).fetch()
     assert not np.array_equal(same[0][1], got[0][1])
+    # Lagrange orders through the same per-zone coordinates (order 5 on fewer points: one 125 x 125 solve per stencil)
+    for order, m in ((3, 4000), (5, 600)):
+        qa = tuple(a[:m] for a in pa); qb = tuple(a[:m] for a in pb)
+        got = _lib.set_interp_data_dw(ctx, [qa, qb], gz, order, 1, 1).fetch()
+        ref = O.set_interp_data_dw([qa, qb], oz, order, 1, 1)
+        for z in range(2):
+            assert np.array_equal(got[0][z], ref[0][z]), (order, "receptors", z)
+            assert np.array_equal(_dwDonorSlots(got[1][z], got[2][z]), ref[1][z]), (order, "donors", z)
+            assert np.array_equal(got[2][z], ref[2][z]) and np.array_equal(got[3][z], ref[3][z]), (order, z)
+            assert np.array_equal(got[4][z], ref[4][z])
+        assert np.array_equal(got[5], ref[5])
+        assert sum(int((t == order).sum()) for t in got[2]) > 50
     with pytest.raises(NotImplementedError):
-        _lib.set_interp_data_dw(ctx, [pa, pb], gz, 3, 1, 1)
+        _lib.set_interp_data_dw(ctx, [pa, pb], gz, 4, 1, 1)
 
 
 @pytest.mark.gpu
