@@ -390,13 +390,20 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
         cdf = cd.reshape(-1, order='F') if cd is not None else None
         return (ni_, nj_, nk_, xd, yd, zzd, cdf, typesL[i])
 
-    def makeHooks(ids):
-        """The hooks not built yet among `ids`, all at once (the device builds the ADTs of a batch of zones
-        concurrently)."""
+    def beginHooks(ids):
+        """Start the hooks not built yet among `ids`: coordinates and cellN go up zone after zone, every ADT build starts
+        on a side stream as soon as its zone is up (backend.make_zones_begin); finishHooks waits for the builds."""
         todo = [i for i in ids if allHooksL[i] is None]
-        if todo:
-            for i, h in zip(todo, backend.make_zones([hookArgs(i) for i in todo])):
-                allHooksL[i] = h
+        if not todo:
+            return []
+        started = backend.make_zones_begin([hookArgs(i) for i in todo])
+        for i, h in zip(todo, started):
+            allHooksL[i] = h
+        return started
+
+    def finishHooks(started):
+        if started:
+            backend.make_zones_finish(started)
 
     import os as _os, time as _time
     _prof = _os.environ.get("CX_PROFILE")
@@ -453,30 +460,40 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
                                           extrapPts, resInterp[5], tag='Donor', loc=locR)
         _tt['store'] += _time.perf_counter() - _t3
 
-    # The receptor zones go through in windows: Etape 1 (receptor points) of every zone of the window, then the hooks
-    # the window needs in one batch, then every search is queued on the device without waiting for the previous one,
-    # then the lists are fetched and stored zone after zone in the reference's order.  A window closes at
-    # _WINDOW_PTS receptor points in flight (the per-receptor tables of a search stay on the device until its fetch).
+    # The receptor zones go through in windows: the hooks the window needs are started first (coordinates up, ADT builds
+    # in flight on side streams), the receptor points of every zone of the window are extracted meanwhile (Etape 1), the
+    # builds are finished, every search is queued on the device without waiting for the previous one, and the lists are
+    # fetched and stored zone after zone in the reference's order.  A window closes at _WINDOW_PTS points (the
+    # per-receptor tables of a search stay on the device until its fetch; a zone counts with all its points).
+    def donorsOf(z):
+        idx = list(range(len(zonesDnrL)))
+        if sameName == 1:
+            for cL, zo in enumerate(zonesDnrL):
+                if zo[0] == z[0]:
+                    idx.pop(cL)
+                    break
+        if donorLists is not None and z[0] in donorLists:
+            names = donorLists[z[0]]
+            byname = {zonesDnrL[i][0]: i for i in idx}
+            idx = [byname[n] for n in names if n in byname]
+        return idx
+
     try:
         pos = 0
         while pos < len(zonesRcv):
-            jobs = []; inflight = 0
-            while pos < len(zonesRcv) and (not jobs or inflight < _WINDOW_PTS):
+            cand = []; inflight = 0
+            while pos < len(zonesRcv) and (not cand or inflight < _WINDOW_PTS):
                 z = zonesRcv[pos]; pos += 1
-                _t0 = _time.perf_counter()
-                cellNPresent = C.isNamePresent(z, 'cellN' if loc == 'nodes' else 'centers:cellN')
-                if cellNPresent == -1:
+                if C.isNamePresent(z, 'cellN' if loc == 'nodes' else 'centers:cellN') == -1:
                     continue
-                idx = list(range(len(zonesDnrL)))
-                if sameName == 1:
-                    for cL, zo in enumerate(zonesDnrL):
-                        if zo[0] == z[0]:
-                            idx.pop(cL)
-                            break
-                if donorLists is not None and z[0] in donorLists:
-                    names = donorLists[z[0]]
-                    byname = {zonesDnrL[i][0]: i for i in idx}
-                    idx = [byname[n] for n in names if n in byname]
+                cand.append((z, donorsOf(z)))
+                inflight += int(numpy.prod(C.fieldShape(z, locR)))
+            _t1 = _time.perf_counter()
+            started = beginHooks(sorted(set(i for _, idx in cand for i in idx)))
+            _tt['hooks'] += _time.perf_counter() - _t1
+            jobs = []
+            for z, idx in cand:
+                _t0 = _time.perf_counter()
                 zonesDnr = [zonesDnrL[i] for i in idx]
 
                 # Etape 1: points to interpolate (cellN == 2): getInterpolatedPoints keeps the points with
@@ -508,10 +525,9 @@ def _setInterpDataChimera(aR, aD, order=2, penalty=1, nature=0, extrap=1,
                 if sel.size == 0:
                     continue
                 jobs.append((z, zonesDnr, idx, rcvPts, sel, cellN))
-                inflight += sel.size
             # Etape 2: interpolation data on the device
             _t1 = _time.perf_counter()
-            makeHooks(sorted(set(i for job in jobs for i in job[2])))
+            finishHooks(started)
             _t2 = _time.perf_counter()
             _tt['hooks'] += _t2 - _t1
             pend = [backend.submit_interp_data_rcv(rcvPts, [allHooksL[i] for i in idx], order, nature, penalty, extrap)

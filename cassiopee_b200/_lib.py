@@ -855,13 +855,22 @@ class DeviceBackend:
     def make_zones(self, specs):
         """Hooks of several donor zones, specs = [(ni, nj, nk, x, y, z, cellN, interpDataType)]: the uploads run zone
         after zone, the ADT builds of the whole batch run concurrently on the device (cx_zones_build_adt)."""
+        zones = self.make_zones_begin(specs)
+        self.make_zones_finish(zones)
+        return zones
+
+    def make_zones_begin(self, specs):
+        """Uploads zone after zone, every ADT build started on a side stream as soon as its zone is up; the zones can
+        serve as receptor sources (coordinates, cellN) at once, as donors after make_zones_finish."""
         zones = []
         for sp in specs:
             z = Zone(self.ctx, *sp[:7], interpDataType=sp[7], defer_adt=True)
             check(lib().cx_zone_adt_begin(z.h))      # builds while the next zone's coordinates go up
             zones.append(z)
-        build_adts(self.ctx, zones)
         return zones
+
+    def make_zones_finish(self, zones):
+        build_adts(self.ctx, zones)
 
     def set_celln(self, hook, cellN):
         hook.set_celln(cellN)

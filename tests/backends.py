@@ -23,6 +23,12 @@ class OracleBackend:
     def make_zones(self, specs):
         return [self.make_zone(*sp[:7], interpDataType=sp[7]) for sp in specs]
 
+    def make_zones_begin(self, specs):
+        return self.make_zones(specs)
+
+    def make_zones_finish(self, zones):
+        pass
+
     def set_celln(self, hook, cellN):
         pass
 
