@@ -806,7 +806,8 @@ struct cx_plan_full {
   bool rcv_contiguous;                  // h_rcv[e] == h_rcv[0] + e
   std::vector<cudaEvent_t> evk, evd;    // per-variable kernel-done / download-done events (host-pointer pipeline)
   // sparse upload of the donor fields (host-pointer pipeline, large zones): the donor points the plan reads
-  int didx_state = 0;                   // 0: not looked at yet, 1: sparse (h_didx / d_didx), 2: whole fields
+  int didx_state = 0;                   // 0: not looked at yet, 1: sparse (h_didx / d_didx), 2: whole fields, 3: box
+  int box[6] = {0, 0, 0, 0, 0, 0};      // state 3: i0, i1, j0, j1, k0, k1 (inclusive) of the donor points read
   std::vector<int> h_didx; int* d_didx = nullptr;
   double* h_stage = nullptr; size_t hstage_cap = 0;   // pinned, nvars x h_didx.size()
 };
@@ -959,7 +960,29 @@ static int plan_donor_list(cx_plan_full* F)
   cudaFreeAsync(d_mark, c->stream);
   size_t nd = 0;
   for (size_t i = 0; i < mark.size(); i++) nd += mark[i];
-  if (nd == 0 || 4 * nd >= (size_t)P->nptsD) return 0;
+  if (nd == 0) return 0;
+  if (4 * nd >= (size_t)P->nptsD)
+  {
+    // too dense for the index list: the bounding box of the points read (a near-body grid inside a background reads a
+    // block of it) goes up as ONE strided copy per variable when it holds less than 85 % of the zone
+    const int imd = P->imd, jmd = P->jmd, kmd = (int)(P->nptsD / ((long long)imd * jmd));
+    int b[6] = {imd, -1, jmd, -1, kmd, -1};
+    for (int k = 0; k < kmd; k++)
+      for (int j = 0; j < jmd; j++)
+      {
+        const unsigned char* row = mark.data() + ((size_t)k * jmd + j) * imd;
+        int lo = -1, hi = -1;
+        for (int i = 0; i < imd; i++) if (row[i]) { if (lo < 0) lo = i; hi = i; }
+        if (lo < 0) continue;
+        b[0] = std::min(b[0], lo); b[1] = std::max(b[1], hi);
+        b[2] = std::min(b[2], j); b[3] = std::max(b[3], j); b[4] = std::min(b[4], k); b[5] = std::max(b[5], k);
+      }
+    const double vol = (double)(b[1] - b[0] + 1) * (b[3] - b[2] + 1) * (b[5] - b[4] + 1);
+    static int box_on = -1;
+    if (box_on < 0) { const char* e = getenv("CX_BOX_H2D"); box_on = (e && atoi(e) == 0) ? 0 : 1; }
+    if (box_on && vol <= 0.85 * (double)P->nptsD) { for (int q = 0; q < 6; q++) F->box[q] = b[q]; F->didx_state = 3; }
+    return 0;
+  }
   F->h_didx.resize(nd);
   size_t k = 0;
   for (size_t i = 0; i < mark.size(); i++) if (mark[i]) F->h_didx[k++] = (int)i;
@@ -1028,6 +1051,21 @@ static int transfer_pipeline(cx_plan_full* F, int nvars, const double* const* fi
       CX_CUDA(cudaMemcpyAsync(ds, hs, sizeof(double) * nd, cudaMemcpyHostToDevice, sa));
       k_unpack1<<<cx_grid((long long)nd, 256), 256, 0, sa>>>((int)nd, ds, F->d_didx, dv);
       c->launches++;
+    }
+    else if (!batch && F->didx_state == 3)
+    {
+      // the box of the donor points read, as one strided copy (rows of the box, plane after plane)
+      dv = c->d_tfields + per * v;
+      const int* b = F->box;
+      cudaMemcpy3DParms p;
+      memset(&p, 0, sizeof(p));
+      p.srcPtr = make_cudaPitchedPtr((void*)fieldD[v], sizeof(double) * (size_t)P->imd, sizeof(double) * (size_t)P->imd, (size_t)P->jmd);
+      p.dstPtr = make_cudaPitchedPtr((void*)dv, sizeof(double) * (size_t)P->imd, sizeof(double) * (size_t)P->imd, (size_t)P->jmd);
+      p.srcPos = make_cudaPos(sizeof(double) * (size_t)b[0], (size_t)b[2], (size_t)b[4]);
+      p.dstPos = p.srcPos;
+      p.extent = make_cudaExtent(sizeof(double) * (size_t)(b[1] - b[0] + 1), (size_t)(b[3] - b[2] + 1), (size_t)(b[5] - b[4] + 1));
+      p.kind = cudaMemcpyHostToDevice;
+      CX_CUDA(cudaMemcpy3DAsync(&p, sa));
     }
     else
     {
@@ -1481,7 +1519,9 @@ int cx_plan_upload_points(cx_plan* P, long long* npts)
 {
   cx_plan_full* F = (cx_plan_full*)P;
   if (F->didx_state == 0 && P->n > 0) CX_CHECK(plan_donor_list(F));
-  *npts = F->didx_state == 1 ? (long long)F->h_didx.size() : (long long)P->nptsD;
+  *npts = F->didx_state == 1 ? (long long)F->h_didx.size()
+        : F->didx_state == 3 ? (long long)(F->box[1] - F->box[0] + 1) * (F->box[3] - F->box[2] + 1) * (F->box[5] - F->box[4] + 1)
+        : (long long)P->nptsD;
   return 0;
 }
 

@@ -312,6 +312,24 @@ def test_host_pointer_transfer_sparse_upload(ctx, monkeypatch):
         for a, b in zip(got, want):
             assert np.array_equal(a, b)
     assert np.array_equal(plan.transferD(fD), O.transferD(fD, ni, nj, dnr, typ, cf))
+    # a plan that reads a block of the zone (more than a quarter of it, its bounding box under 85 %): the box goes up as
+    # one strided copy per variable
+    typ3 = rng.choice(np.array([1, 2, 3], np.int32), n).astype(np.int32)
+    o3 = np.where(typ3 == 1, 1, typ3)
+    i3 = 20 + (rng.random(n) * (70 - o3 + 1)).astype(np.int64); j3 = 5 + (rng.random(n) * (80 - o3 + 1)).astype(np.int64)
+    k3 = (rng.random(n) * (nk - o3 + 1)).astype(np.int64)
+    i3[:2] = 20; j3[:2] = 5; k3[:2] = 0; i3[2:4] = 20 + 70 - o3[2:4]; j3[2:4] = 5 + 80 - o3[2:4]; k3[2:4] = nk - o3[2:4]
+    dnr3 = (i3 + ni * j3 + ni * nj * k3).astype(np.int32)
+    cf3 = rng.standard_normal(int(np.where(typ3 == 1, 1, np.where(typ3 == 2, 8, 9)).sum()))
+    plan3 = _lib.Plan(ctx, ni, nj, nk, nR, dnr3, rcv, typ3, cf3)
+    assert plan3.upload_points() == 70 * 80 * nk and 0.25 * nD < plan3.upload_points() < 0.85 * nD
+    want3 = [np.full(nR, -7.) for _ in range(3)]
+    O.transfer(fD, want3, ni, nj, rcv, dnr3, typ3, cf3)
+    for rep in range(2):
+        got = [np.full(nR, -7.) for _ in range(3)]
+        plan3.transfer(fD, got)
+        for a, b in zip(got, want3):
+            assert np.array_equal(a, b)
     monkeypatch.setenv("CX_SPARSE_H2D", "0")                   # read once per process: only new plans could differ
     # a plan that reads most of the zone keeps the whole-field upload
     k2 = (rng.random(n) * (nk - o + 1)).astype(np.int64)
