@@ -266,8 +266,8 @@ def run_c2(args):
                "h2d_bytes_per_step": int(8 * nvars * plan.upload_points()), "d2h_bytes_per_step": int(8 * nvars * n),
                "donor_points_uploaded": int(plan.upload_points()), "donor_points": int(Bg.npts),
                "api": "cx_transfer (connector._setInterpTransfers boundary), pinned host fields in and out; only the "
-                      "donor points the plan reads cross the bus (host gather + packed copy) when that is < 1/4 of "
-                      "the zone (not the case here)"}
+                      "donor points the plan reads cross the bus: their index list when that is < 1/4 of the zone, else "
+                      "their bounding box as one strided copy per variable when it holds < 85 % of the zone"}
         # ---- CPU baseline: the reference's own transfer loops on the host cores ----
         cpu = cpu_baseline_transfer(fD, nrcv, Bg, rcv, dnr, typ, coefs, B, nvars)
 
