@@ -712,12 +712,24 @@ class TransferSession:
             if not all(_rawF(a) for a in arrs):
                 return None
             npts = arrs[0].size
-            idx = None
+            idx = None; box = None
             if os.environ.get("CX_SPARSE_H2D", "1") != "0":
-                idx = numpy.flatnonzero(_lib.plan_donor_mask(self.ctx, plans, npts)).astype(numpy.int32)
-                if 4 * idx.size >= npts:      # a host gather over most of the array is slower than the plain copy
+                mask = _lib.plan_donor_mask(self.ctx, plans, npts)
+                idx = numpy.flatnonzero(mask).astype(numpy.int32)
+                if 4 * idx.size >= npts:      # a host gather over most of the array is slower than the plain copy:
+                    # the bounding box of the points read goes up as one strided copy per variable instead
+                    if idx.size and arrs[0].ndim == 3 and all(a.flags.f_contiguous for a in arrs):
+                        m3 = mask.reshape(arrs[0].shape, order='F').astype(bool)
+                        ii = numpy.flatnonzero(m3.any(axis=(1, 2))); jj = numpy.flatnonzero(m3.any(axis=(0, 2)))
+                        kk = numpy.flatnonzero(m3.any(axis=(0, 1)))
+                        b = (int(ii[0]), int(ii[-1]), int(jj[0]), int(jj[-1]), int(kk[0]), int(kk[-1]))
+                        if (b[1] - b[0] + 1) * (b[3] - b[2] + 1) * (b[5] - b[4] + 1) <= 0.85 * npts:
+                            box = b
                     idx = None
-            io.add('up', arrs, [d.ptr for d in self.dD[zd[0]]], idx)
+            if box is not None:
+                io.add_box('up', arrs, [d.ptr for d in self.dD[zd[0]]], box)
+            else:
+                io.add('up', arrs, [d.ptr for d in self.dD[zd[0]]], idx)
         for name, arrs in self.hR.items():
             if not all(_rawF(a) for a in arrs):
                 return None

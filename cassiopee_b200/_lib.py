@@ -109,6 +109,7 @@ _SIGS = {
     "cx_step_splittable": (_i, [_vp]),
     "cx_hostio_create": (_i, [_vp, _i, _vp]),
     "cx_hostio_add": (_i, [_vp, _i, _ll, _vp, _vp, _vp]),
+    "cx_hostio_add_box": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "cx_hostio_bytes": (_i, [_vp, _vp, _vp]),
     "cx_step_run_host": (_i, [_vp, _vp, _i]),
     "cx_hostio_destroy": (_i, [_vp]),
@@ -693,6 +694,19 @@ class HostIO:
         self._keep.append(list(host_arrays))
         check(lib().cx_hostio_add(self.h, 0 if direction == 'up' else 1, n, ptr(idx) if idx is not None else None,
                                   ptr_array([a.ctypes.data for a in host_arrays]), ptr_array(list(dev_ptrs))))
+
+    def add_box(self, direction, host_arrays, dev_ptrs, box):
+        """The same for the index box (i0, i1, j0, j1, k0, k1), inclusive, of 3-D Fortran-ordered arrays: one strided
+        copy per variable."""
+        assert len(host_arrays) == self.nvars and len(dev_ptrs) == self.nvars
+        for a in host_arrays:
+            if a.dtype != np.float64 or a.ndim != 3 or not a.flags.f_contiguous:
+                raise TypeError("HostIO.add_box: fields must be 3-D Fortran-ordered float64 arrays")
+        im, jm, km = host_arrays[0].shape
+        b = np.ascontiguousarray(box, dtype=np.int32)
+        self._keep.append(list(host_arrays))
+        check(lib().cx_hostio_add_box(self.h, 0 if direction == 'up' else 1, im, jm, km, ptr(b),
+                                      ptr_array([a.ctypes.data for a in host_arrays]), ptr_array(list(dev_ptrs))))
 
     def bytes(self):
         a = _ll(); b = _ll()

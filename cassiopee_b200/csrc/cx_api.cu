@@ -1350,6 +1350,7 @@ struct cx_hostio {
   std::vector<cudaEvent_t> evU, evS, evD;
   struct Item {
     int dir; long long n; bool sparse;
+    bool boxed = false; int dims[2] = {0, 0}; int box[6] = {0, 0, 0, 0, 0, 0};   // whole-array item cut to a box
     std::vector<int> idx; int* d_idx; double* hbuf; double* dbuf;
     std::vector<double*> h; std::vector<double*> d;
   };
@@ -1400,6 +1401,40 @@ int cx_hostio_add(cx_hostio* io, int dir, long long n, const int* h_idx, double*
   return 0;
 }
 
+// the same for the box [i0,i1] x [j0,j1] x [k0,k1] (inclusive) of (imd, jmd, kmd) arrays: one strided copy per variable
+int cx_hostio_add_box(cx_hostio* io, int dir, int imd, int jmd, int kmd, const int* box, double* const* h_field,
+                      double* const* d_field)
+{
+  if (box[0] < 0 || box[1] >= imd || box[2] < 0 || box[3] >= jmd || box[4] < 0 || box[5] >= kmd || box[0] > box[1] ||
+      box[2] > box[3] || box[4] > box[5]) { cx_set_error("cx_hostio_add_box: box outside the array"); return -1; }
+  io->items.emplace_back();
+  cx_hostio::Item& I = io->items.back();
+  I.dir = dir; I.sparse = false; I.boxed = true; I.d_idx = nullptr; I.hbuf = nullptr; I.dbuf = nullptr;
+  I.dims[0] = imd; I.dims[1] = jmd;
+  for (int q = 0; q < 6; q++) I.box[q] = box[q];
+  I.n = (long long)(box[1] - box[0] + 1) * (box[3] - box[2] + 1) * (box[5] - box[4] + 1);
+  I.h.assign(h_field, h_field + io->nvars); I.d.assign(d_field, d_field + io->nvars);
+  (dir == 0 ? io->h2d_bytes : io->d2h_bytes) += 8ll * I.n * io->nvars;
+  return 0;
+}
+
+static int hostio_box_copy(const cx_hostio::Item& I, int v, cudaStream_t s)
+{
+  cudaMemcpy3DParms p;
+  memset(&p, 0, sizeof(p));
+  const size_t pitch = sizeof(double) * (size_t)I.dims[0];
+  cudaPitchedPtr hp = make_cudaPitchedPtr((void*)I.h[v], pitch, pitch, (size_t)I.dims[1]);
+  cudaPitchedPtr dp = make_cudaPitchedPtr((void*)I.d[v], pitch, pitch, (size_t)I.dims[1]);
+  p.srcPtr = I.dir == 0 ? hp : dp; p.dstPtr = I.dir == 0 ? dp : hp;
+  p.srcPos = make_cudaPos(sizeof(double) * (size_t)I.box[0], (size_t)I.box[2], (size_t)I.box[4]);
+  p.dstPos = p.srcPos;
+  p.extent = make_cudaExtent(sizeof(double) * (size_t)(I.box[1] - I.box[0] + 1), (size_t)(I.box[3] - I.box[2] + 1),
+                             (size_t)(I.box[5] - I.box[4] + 1));
+  p.kind = I.dir == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+  CX_CUDA(cudaMemcpy3DAsync(&p, s));
+  return 0;
+}
+
 int cx_hostio_bytes(cx_hostio* io, long long* h2d, long long* d2h)
 {
   if (h2d) *h2d = io->h2d_bytes;
@@ -1433,6 +1468,8 @@ int cx_step_run_host(cx_step* S, cx_hostio* io, int pipelined)
         k_scatter<<<cx_grid(I.n, 256), 256, 0, io->up>>>((int)I.n, chunk, I.dbuf + (size_t)v0 * I.n, I.n, I.d_idx, R);
         c->launches++;
       }
+      else if (I.boxed)
+        for (int v = v0; v < v0 + chunk; v++) CX_CHECK(hostio_box_copy(I, v, io->up));
       else
         for (int v = v0; v < v0 + chunk; v++)
           CX_CUDA(cudaMemcpyAsync(I.d[v], I.h[v], sizeof(double) * (size_t)I.n, cudaMemcpyHostToDevice, io->up));
@@ -1453,6 +1490,8 @@ int cx_step_run_host(cx_step* S, cx_hostio* io, int pipelined)
         CX_CUDA(cudaMemcpyAsync(I.hbuf + (size_t)v0 * I.n, I.dbuf + (size_t)v0 * I.n, sizeof(double) * (size_t)I.n * chunk,
                                 cudaMemcpyDeviceToHost, io->dn));
       }
+      else if (I.boxed)
+        for (int v = v0; v < v0 + chunk; v++) CX_CHECK(hostio_box_copy(I, v, io->dn));
       else
         for (int v = v0; v < v0 + chunk; v++)
           CX_CUDA(cudaMemcpyAsync(I.h[v], I.d[v], sizeof(double) * (size_t)I.n, cudaMemcpyDeviceToHost, io->dn));

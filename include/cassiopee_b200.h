@@ -279,6 +279,9 @@ int cx_step_destroy(cx_step* step);
 typedef struct cx_hostio cx_hostio;
 int cx_hostio_create(cx_ctx* ctx, int nvars, cx_hostio** out);
 int cx_hostio_add(cx_hostio* io, int dir, long long n, const int* h_idx, double* const* h_field, double* const* d_field);
+/* a whole-array item cut to the box [i0,i1] x [j0,j1] x [k0,k1] (inclusive) of (imd, jmd, kmd) arrays: one strided copy per variable */
+int cx_hostio_add_box(cx_hostio* io, int dir, int imd, int jmd, int kmd, const int* box6, double* const* h_field,
+                      double* const* d_field);
 int cx_hostio_bytes(cx_hostio* io, long long* h2d_bytes, long long* d2h_bytes);
 int cx_step_run_host(cx_step* step, cx_hostio* io, int pipelined);
 int cx_hostio_destroy(cx_hostio* io);

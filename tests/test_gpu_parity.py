@@ -1182,3 +1182,40 @@ def test_batched_hooks_build_the_same_trees(ctx):
     rb = _lib.set_interp_data(ctx, *pts, [_lib.Zone(ctx, *specs[1][:7]), _lib.Zone(ctx, *specs[4][:7])], 2, 1, 1, 1).fetch()
     for k in range(5):
         for a, b in zip(ra[k], rb[k]): assert np.array_equal(a, b)
+
+
+def test_transfer_session_box_upload(ctx):
+    """transfer_host() when the plans of a donor zone read more than a quarter of it: the bounding box of the donor
+    points goes up as one strided copy per variable (HostIO.add_box).  The device copies of the donor fields are
+    poisoned first, so the result can only be right if that box holds everything the plans read."""
+    import cassiopee_b200.Generator as G
+    import cassiopee_b200.Converter as C
+    import cassiopee_b200.Internal as Internal
+    import cassiopee_b200.Connector.PyTree as X
+    import cassiopee_b200.Connector.Mpi as Xmpi
+    h = 1. / 20
+    a = G.cart((0, 0, 0), (h, h, h), (31, 21, 17), name='A')
+    b = G.cart((0.52, 0.11, 0.09), (0.7 * h, 0.7 * h, 0.7 * h), (25, 21, 17), name='B')     # B inside the right part of A
+    t = C.newPyTree(['Base', a, b])
+    names = ['Density', 'MomentumX']
+    rng = np.random.default_rng(31)
+    for z in Internal.getZones(t):
+        for v in names:
+            C._initVars(z, 'centers:' + v, np.asfortranarray(rng.standard_normal(C.fieldShape(z, 'centers'))))
+    C._initVars(t, 'centers:cellN', 1.)
+    C._initVars(Internal.getZones(t)[1], 'centers:cellN', 2.)
+    tc = C.node2Center(t)
+    tc = X.setInterpData(t, tc, order=2, nature=0, penalty=1, extrap=1, loc='centers', storage='inverse', sameName=1,
+                         itype='chimera', verbose=0)
+    want = X.setInterpTransfers(t, tc, variables=names, storage=1)
+    sess = Xmpi.TransferSession(t, tc, names, comm=None, ctx=ctx)
+    for lst in sess.dD.values():
+        for d in lst: d.upload(np.full(d.n, np.nan))
+    up, down = sess.transfer_host()
+    zA = Internal.getZones(tc)[0]
+    full = sum(C.getFieldArray(zA, v).nbytes for v in names)
+    assert 0.25 * full < up < 0.86 * full, (up, full)            # a box of A, not its index list, not the whole zone
+    for z, zw in zip(Internal.getZones(t), Internal.getZones(want)):
+        for v in names:
+            assert np.array_equal(C.getFieldArray(z, 'centers:' + v), C.getFieldArray(zw, 'centers:' + v)), (z[0], v)
+    sess.close()
