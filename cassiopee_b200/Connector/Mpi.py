@@ -130,7 +130,7 @@ def _addXZones(aD, meta, donorLists, comm):
     return added
 
 
-def _addXZonesDevice(aD, meta, donorLists, comm, ctx, interpDataType=1):
+def _addXZonesDevice(aD, meta, donorLists, comm, ctx, interpDataType=1, typeOf=None):
     """Device form of _addXZones: the local donor zones go to the GPU once (coordinates + cellN + ADT = the hook),
     and the zones other ranks need travel GPU to GPU over NCCL together with their ADT replica
     (cx_zone_exchange), so nothing is staged through host memory and no tree is rebuilt on the receiver.
@@ -150,7 +150,8 @@ def _addXZonesDevice(aD, meta, donorLists, comm, ctx, interpDataType=1):
         _, ni, nj, nk, _ = Internal.getZoneDim(z)
         x, y, zz = [a.reshape(-1, order='F') for a in C.getCoords(z)]
         c = C.getFieldArray(z, 'cellN')
-        specs.append((ni, nj, nk, x, y, zz, c.reshape(-1, order='F') if c is not None else None, interpDataType))
+        specs.append((ni, nj, nk, x, y, zz, c.reshape(-1, order='F') if c is not None else None,
+                      typeOf[n] if typeOf is not None else interpDataType))
     for n, h in zip(names, be.make_zones(specs)):      # one batch: the ADT builds run concurrently on the device
         hooks[n] = h
     mine = {}
@@ -184,13 +185,16 @@ def _setInterpData(aR, aD, order=2, penalty=1, nature=0, extrap=1, method='lagra
     zone of aD carries the ID_<receptor> subregions of all receptor zones
     (local or remote) it feeds.  aR / aD hold the zones owned by this rank.
     sameBase=0 (the reference's default, Connector/Mpi.py:858-862, :930-937): a zone is only interpolated from
-    zones of OTHER bases; sameBase=1: from every intersecting zone.  cartesian=True (donors of a 'CARTESIAN'
-    base located in closed form) is not distributed here: pass interpDataType=0."""
-    if cartesian:
-        raise NotImplementedError("Mpi._setInterpData: cartesian=True is not distributed; use interpDataType=0.")
+    zones of OTHER bases; sameBase=1: from every intersecting zone.  Like the reference (Connector/Mpi.py:950-983: the
+    hook of a zone of a base named 'CARTESIAN' is None, i.e. interpDataType 0) the donor zones of a 'CARTESIAN' base are
+    located in closed form (InterpCart) whatever `interpDataType` says; `cartesian` itself only selects a compressed
+    transport of such zones in the reference's Cmpi._addXZones and changes nothing here (zones travel GPU to GPU)."""
     if storage != 'inverse':
         raise NotImplementedError("Mpi._setInterpData: only storage='inverse' is distributed.")
+    cartBase = {z[0] for b in Internal.getBases(aD) if b[0] == 'CARTESIAN' for z in Internal.getZones(b)}
     if comm is None or comm.size == 1:
+        if cartBase and not isinstance(interpDataType, list):
+            interpDataType = [0 if z[0] in cartBase else interpDataType for z in Internal.getZones(aD)]
         donorLists = computeDonorGraph(aR, aD, _Single(), loc, sameName, zoneOrder, sameBase)[1]
         # receptor zones without any candidate donor are skipped, like `if dnrZones != []` (Connector/Mpi.py:975)
         rcvs = [z for z in Internal.getZones(aR) if donorLists.get(z[0])]
@@ -210,9 +214,13 @@ def _setInterpData(aR, aD, order=2, penalty=1, nature=0, extrap=1, method='lagra
     # CX_ZONE_REPL=host: replicate through host memory like the first version (A/B); default: GPU to GPU
     devrepl = (backend is None and getattr(comm, 'device', False) and not isinstance(interpDataType, list)
                and os.environ.get("CX_ZONE_REPL", "device") != "host")
+    # zones of a base named 'CARTESIAN' (on any rank: the base travels in the metadata) are InterpCart donors
+    typeOf = None
+    if any(m.get('base') == 'CARTESIAN' for m in meta) and not isinstance(interpDataType, list):
+        typeOf = {m['name']: (0 if m.get('base') == 'CARTESIAN' else interpDataType) for m in meta}
     hooks = None
     if devrepl:
-        added, hooks = _addXZonesDevice(aD, meta, donorLists, comm, ctx or comm.ctx, interpDataType)
+        added, hooks = _addXZonesDevice(aD, meta, donorLists, comm, ctx or comm.ctx, interpDataType, typeOf)
     else:
         added = _addXZones(aD, meta, donorLists, comm)
     t2 = time.perf_counter()
@@ -227,6 +235,8 @@ def _setInterpData(aR, aD, order=2, penalty=1, nature=0, extrap=1, method='lagra
     order_pos = {m['name']: i for i, m in enumerate(meta)}
     work.sort(key=lambda z: order_pos[z[0]])
     rcvs = [z for z in Internal.getZones(aR) if donorLists.get(z[0])]
+    if typeOf is not None:
+        interpDataType = [typeOf[z[0]] for z in work]
     if not rcvs:
         pass                       # nothing to interpolate here; the routing collectives below still run
     elif devrepl:

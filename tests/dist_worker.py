@@ -43,6 +43,15 @@ def build_case(nb=(2, 2, 1), n=13):
     return t
 
 
+def build_case_cartbase(nb=(2, 2, 1), n=13):
+    """The C4 blocks in two bases: the donors of the base named 'CARTESIAN' are located in closed form (InterpCart), the
+    others through their ADT (Connector/Mpi.py:950-983: the hook of a 'CARTESIAN' zone is None)."""
+    t = build_case(nb, n)
+    zs = Internal.getZones(t)
+    half = len(zs) // 2
+    return C.newPyTree(['CARTESIAN'] + zs[:half] + ['Base'] + zs[half:])
+
+
 def build_case_c2n(nbodies):
     """Tiny version of the multi-body C2 weak-scaling workload of bench_c2n.py (node-located receptors,
     donor tree == receptor tree, one body = two zones per rank)."""
@@ -57,8 +66,11 @@ def build_case_c2n(nbodies):
 
 
 def subtree_of(t, rank):
-    zs = [z for z in Internal.getZones(t) if D2.getProc(z) == rank]
-    return C.newPyTree(['Base'] + zs)
+    """The zones placed on `rank`, in their bases."""
+    args = []
+    for b in Internal.getBases(t):
+        args += [b[0]] + [z for z in Internal.getZones(b) if D2.getProc(z) == rank]
+    return C.newPyTree(args)
 
 
 def collect(tc, t):
@@ -97,7 +109,7 @@ def main():
     loc = 'centers'
     if case == 'c2n':
         loc = 'nodes'; PREFIX[0] = ''
-    make = (lambda: build_case_c2n(comm.size)) if case == 'c2n' else build_case
+    make = (lambda: build_case_c2n(comm.size)) if case == 'c2n' else build_case_cartbase if case == 'cartbase' else build_case
     t = make()
     zoneOrder = [z[0] for z in Internal.getZones(t)]
     tl = subtree_of(t, rank)

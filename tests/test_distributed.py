@@ -35,6 +35,22 @@ def test_world2_gloo_oracle_backend_multibody_nodes():
     _run(2, "gloo-oracle", 2, 29614, case='c2n')
 
 
+def test_world2_gloo_oracle_backend_cartesian_base():
+    """Zones of a base named 'CARTESIAN' are InterpCart donors on every rank, also when replicated."""
+    _run(2, "gloo-oracle", 2, 29621, case='cartbase')
+
+
+@pytest.mark.gpu
+def test_world2_nccl_device_backend_cartesian_base():
+    import ctypes
+    from cassiopee_b200 import _lib
+    n = ctypes.c_int(0)
+    _lib.lib().cx_device_count(ctypes.byref(n))
+    if n.value < 2:
+        pytest.skip("needs 2 GPUs")
+    _run(2, "nccl", 2, 29622, case='cartbase', transport="p2p")
+
+
 @pytest.mark.gpu
 def test_world2_nccl_device_backend_multibody_nodes():
     import ctypes

@@ -540,3 +540,45 @@ def test_receptor_zones_in_windows(monkeypatch):
                     if na is not None: assert np.array_equal(na[1], nb[1]), (za[0], a[0], n)
                 nsub += 1
     assert nsub >= 8
+
+
+def test_cartesian_base_zones_are_interpcart_donors():
+    """Xmpi._setInterpData (single process): the donor zones of a base named 'CARTESIAN' are located in closed form
+    (interpDataType 0), the others through their ADT, like the reference's hooks[z] = None rule (Connector/Mpi.py:950-983);
+    cartesian=True only names a transport of the reference and is accepted."""
+    import cassiopee_b200.Connector.Mpi as Xmpi
+    h = 1. / 10
+    def build():
+        a = G.cart((0, 0, 0), (h, h, h), (11, 11, 11), name='A')
+        b = G.cart((0.45, 0.12, 0.08), (0.9 * h, 0.9 * h, 0.9 * h), (10, 10, 10), name='B')
+        c = G.cart((0.21, 0.47, 0.33), (0.8 * h, 0.8 * h, 0.8 * h), (9, 9, 9), name='C')
+        t = C.newPyTree(['CARTESIAN', a, 'Body', b, c])
+        C._initVars(t, 'centers:cellN', 1.)
+        for z in Internal.getZones(t):
+            cn = C.getFieldArray(z, 'centers:cellN'); cn[:2] = 2.; cn[:, -2:] = 2.
+        return t, C.node2Center(t)
+
+    class Recording(OracleBackend):
+        def __init__(self): self.types = {}
+        def make_zone(self, ni, nj, nk, x, y, z, cellN=None, interpDataType=1):
+            self.types[(ni, nj, nk)] = interpDataType
+            return OracleBackend.make_zone(self, ni, nj, nk, x, y, z, cellN, interpDataType=interpDataType)
+
+    be = Recording()
+    t, tc = build()
+    Xmpi._setInterpData(t, tc, order=2, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse', sameBase=1,
+                        cartesian=True, comm=None, backend=be)
+    assert be.types == {(10, 10, 10): 0, (9, 9, 9): 1, (8, 8, 8): 1}
+    t2, tc2 = build()
+    X._setInterpDataChimera(t2, tc2, order=2, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse', verbose=0,
+                            interpDataType=[0, 1, 1], backend=OracleBackend())
+    n = 0
+    for za, zb in zip(Internal.getZones(tc), Internal.getZones(tc2)):
+        sa = [s for s in Internal.getNodesFromType1(za, 'ZoneSubRegion_t') if s[0].startswith('ID_')]
+        sb = [s for s in Internal.getNodesFromType1(zb, 'ZoneSubRegion_t') if s[0].startswith('ID_')]
+        assert [s[0] for s in sa] == [s[0] for s in sb]
+        for a, b in zip(sa, sb):
+            for nm in ('PointList', 'PointListDonor', 'InterpolantsDonor', 'InterpolantsType'):
+                assert np.array_equal(Internal.getNodeFromName1(a, nm)[1], Internal.getNodeFromName1(b, nm)[1])
+            n += 1
+    assert n >= 4
