@@ -151,16 +151,37 @@ def _prepBackend(backend, ctx=None):
     return backend
 
 
-def _applyBCOverlaps(t, depth=2, loc='centers', val=2, cellNName='cellN', ctx=None, backend=None):
-    """Connector.PyTree._applyBCOverlaps for structured zones (Connector/PyTree.py:1548-1600, :1674-1720):
-    cellN (created =1 if absent) is set to `val` in the `depth` layers next to every non doubly-defined
-    BCOverlap window (GridConnectivity_t of type 'Overset' with a PointRange).  The windows of a zone are applied
-    by connector.applyBCOverlapStruct = cx_apply_bc_overlap (csrc/cx_prepare.cu), one upload / download per zone."""
+def _applyBCOverlaps(a, depth=2, loc='centers', val=2, cellNName='cellN', checkCellN=True, ctx=None, backend=None):
+    """Connector.PyTree._applyBCOverlaps for structured zones (Connector/PyTree.py:1600-1645, :1699-1717):
+    cellN (created =1 if absent, unless checkCellN=False: a zone without it is then left alone) is set to `val` in the
+    `depth` layers next to every overset window of the zone: the non doubly-defined BCOverlap windows
+    (GridConnectivity_t of type 'Overset' with a PointRange) and the BC_t windows whose family carries a
+    `.Solver#Overlap` node.  The windows of a zone are applied by connector.applyBCOverlapStruct =
+    cx_apply_bc_overlaps (csrc/cx_prepare.cu), one upload / download per zone."""
     if loc not in ('nodes', 'centers'):
         raise ValueError("applyBCOverlapsStruct: invalid location.")
     var = cellNName if loc == 'nodes' else 'centers:' + cellNName
-    for z in Internal.getZones(t):
+
+    def families(node, out):            # Family_t nodes at any depth (they sit under the bases)
+        for c in node[2]:
+            if c[3] == 'Family_t':
+                if Internal.getNodeFromName1(c, '.Solver#Overlap') is not None: out.append(c[0])
+            elif c[3] in ('CGNSBase_t', 'CGNSTree_t'):
+                families(c, out)
+        return out
+    oversetFamNames = families(a, []) if isinstance(a, list) and len(a) == 4 and isinstance(a[2], list) else []
+
+    def window(node):
+        r = Internal.getNodeFromType1(node, 'IndexRange_t')
+        if r is None:
+            print("Warning: applyBCOverlaps: BCOverlap is ill-defined.")
+            return None
+        w = r[1]
+        return ((int(w[0, 0]), int(w[1, 0]), int(w[2, 0])), (int(w[0, 1]), int(w[1, 1]), int(w[2, 1])))
+
+    for z in Internal.getZones(a):
         if C.isNamePresent(z, var) == -1:
+            if not checkCellN: continue
             C._initVars(z, var, 1.)
         windows = []
         for o in Internal.getNodesFromType2(z, 'GridConnectivity_t'):
@@ -170,12 +191,14 @@ def _applyBCOverlaps(t, depth=2, loc='centers', val=2, cellNName='cellN', ctx=No
             ud = Internal.getNodeFromName1(o, 'UserDefinedData')
             if ud is not None and Internal.getNodeFromName1(ud, 'doubly_defined') is not None:
                 continue
-            r = Internal.getNodeFromType1(o, 'IndexRange_t')
-            if r is None:
-                print("Warning: applyBCOverlaps: BCOverlap is ill-defined.")
-                continue
-            w = r[1]
-            windows.append(((int(w[0, 0]), int(w[1, 0]), int(w[2, 0])), (int(w[0, 1]), int(w[1, 1]), int(w[2, 1]))))
+            w = window(o)
+            if w is not None: windows.append(w)
+        if oversetFamNames:
+            for bc in Internal.getNodesFromType2(z, 'BC_t'):
+                fam = Internal.getNodeFromType1(bc, 'FamilyName_t')
+                if fam is not None and Internal.getValue(fam) in oversetFamNames:
+                    w = window(bc)
+                    if w is not None: windows.append(w)
         if windows:
             _prepBackend(backend, ctx).apply_bc_overlaps(C.getFieldArray(z, var), windows, depth, loc, val)
     return None

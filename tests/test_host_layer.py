@@ -582,3 +582,31 @@ def test_cartesian_base_zones_are_interpcart_donors():
                 assert np.array_equal(Internal.getNodeFromName1(a, nm)[1], Internal.getNodeFromName1(b, nm)[1])
             n += 1
     assert n >= 4
+
+
+def test_apply_bc_overlaps_overset_families_and_checkcelln():
+    """BC_t windows whose family carries .Solver#Overlap count like BCOverlap windows (Connector/PyTree.py:1634-1650);
+    checkCellN=False leaves a zone without cellN alone."""
+    import cassiopee_b200.Connector.PyTree as XP
+    a = G.cart((0, 0, 0), (0.1, 0.1, 0.1), (11, 9, 7), name='A')
+    b = G.cart((2, 0, 0), (0.1, 0.1, 0.1), (6, 6, 6), name='B')
+    t = C.newPyTree(['Base', a, b])
+    base = Internal.getBases(t)[0]
+    fam = Internal.createChild(base, 'OVS', 'Family_t')
+    Internal.createChild(fam, '.Solver#Overlap', 'UserDefinedData_t')
+    Internal.createChild(base, 'WALLS', 'Family_t')
+    zA = Internal.getZones(t)[0]
+    C._addBC2Zone(zA, 'ovfam', 'FamilySpecified', [1, 11, 1, 1, 1, 7])       # jmin face, overset by family
+    bc = Internal.getNodesFromType2(zA, 'BC_t')[0]
+    Internal.createChild(bc, 'FamilyName', 'FamilyName_t', value='OVS')
+    C._addBC2Zone(zA, 'wall', 'FamilySpecified', [11, 11, 1, 9, 1, 7])       # imax face, an ordinary family
+    Internal.createChild(Internal.getNodesFromType2(zA, 'BC_t')[1], 'FamilyName', 'FamilyName_t', value='WALLS')
+    be = OracleBackend()
+    XP._applyBCOverlaps(t, depth=2, loc='centers', backend=be)
+    cA = C.getFieldArray(zA, 'centers:cellN')
+    assert (cA[:, :2, :] == 2).all() and (cA[:, 2:, :] == 1).all()
+    cB = C.getFieldArray(Internal.getZones(t)[1], 'centers:cellN')
+    assert cB is not None and (cB == 1).all()                                # created, no window
+    t2 = C.newPyTree(['Base', G.cart((0, 0, 0), (1, 1, 1), (4, 4, 4), name='Z')])
+    XP._applyBCOverlaps(t2, depth=1, loc='centers', checkCellN=False, backend=be)
+    assert C.getFieldArray(Internal.getZones(t2)[0], 'centers:cellN') is None
