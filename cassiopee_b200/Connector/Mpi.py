@@ -178,10 +178,11 @@ _FIELDS = (('PointList', numpy.int32), ('PointListDonor', numpy.int32), ('Interp
 
 
 def _setInterpData(aR, aD, order=2, penalty=1, nature=0, extrap=1, method='lagrangian', loc='nodes',
-                   storage='inverse', interpDataType=1, hook=None, cartesian=False, sameBase=0,
-                   topTreeRcv=None, topTreeDnr=None, sameName=1, verbose=0, dim=3, itype='chimera',
+                   storage='direct', interpDataType=1, hook=None, cartesian=False, sameBase=0,
+                   topTreeRcv=None, topTreeDnr=None, sameName=1, verbose=2, dim=3, itype='abutting',
                    comm=None, zoneOrder=None, backend=None, ctx=None):
-    """Distributed setInterpData, storage='inverse': on return every local donor
+    """Distributed setInterpData (signature and defaults of Connector/Mpi.py:858-862).  itype='chimera' with
+    storage='inverse' is the path built here: on return every local donor
     zone of aD carries the ID_<receptor> subregions of all receptor zones
     (local or remote) it feeds.  aR / aD hold the zones owned by this rank.
     sameBase=0 (the reference's default, Connector/Mpi.py:858-862, :930-937): a zone is only interpolated from
@@ -189,6 +190,16 @@ def _setInterpData(aR, aD, order=2, penalty=1, nature=0, extrap=1, method='lagra
     hook of a zone of a base named 'CARTESIAN' is None, i.e. interpDataType 0) the donor zones of a 'CARTESIAN' base are
     located in closed form (InterpCart) whatever `interpDataType` says; `cartesian` itself only selects a compressed
     transport of such zones in the reference's Cmpi._addXZones and changes nothing here (zones travel GPU to GPU)."""
+    if itype == 'abutting':
+        # the reference's default: match (ghost-cell) connectivity only, which has no device path; like
+        # OversetData._setInterpData it is an error only when the zones actually carry such connectivity
+        for z in Internal.getZones(aR):
+            if Internal.getNodesFromType2(z, 'GridConnectivity1to1_t') or Internal.getNodesFromType2(z, 'GridConnectivity_t'):
+                raise NotImplementedError("Mpi._setInterpData: abutting (ghost-cell) interpolation data has no device "
+                                          "path; call with itype='chimera'.")
+        return None
+    if itype != 'chimera':
+        raise NotImplementedError("Mpi._setInterpData: itype=%r has no device path (itype='chimera')." % (itype,))
     if storage != 'inverse':
         raise NotImplementedError("Mpi._setInterpData: only storage='inverse' is distributed.")
     cartBase = {z[0] for b in Internal.getBases(aD) if b[0] == 'CARTESIAN' for z in Internal.getZones(b)}
@@ -317,7 +328,7 @@ def _setInterpData2(tR, tD, order=2, loc='centers', cartesian=False, comm=None, 
     temporary = [z for z in Internal.getZones(tR) if C.isNamePresent(z, varcelln) == -1]
     for z in temporary: C._initVars(z, varcelln, 2.)
     _setInterpData(tR, tD, order=order, penalty=1, nature=1, extrap=1, loc=loc, storage='inverse',
-                   interpDataType=0 if cartesian else 1, sameName=0, sameBase=1, itype='chimera', comm=comm, ctx=ctx,
+                   interpDataType=0 if cartesian else 1, sameName=0, sameBase=1, itype='chimera', verbose=0, comm=comm, ctx=ctx,
                    backend=backend)
     for z in temporary: C._rmVars(z, [varcelln])
     return None

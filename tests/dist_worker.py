@@ -114,7 +114,7 @@ def main():
     zoneOrder = [z[0] for z in Internal.getZones(t)]
     tl = subtree_of(t, rank)
     tcl = tl if case == 'c2n' else C.node2Center(tl)
-    Xmpi._setInterpData(tl, tcl, order=order, nature=1, penalty=1, extrap=1, loc=loc, storage='inverse', sameBase=1,
+    Xmpi._setInterpData(tl, tcl, order=order, nature=1, penalty=1, extrap=1, loc=loc, storage='inverse', sameBase=1, itype='chimera', verbose=0,
                         comm=comm, zoneOrder=zoneOrder, backend=backend, ctx=ctx)
     if mode == 'nccl':
         sess = Xmpi.TransferSession(tl, tcl, VARS, comm=comm, ctx=ctx)
@@ -141,7 +141,7 @@ def main():
         # single-process run of the same backend on the whole tree
         t1 = make()
         tc1 = t1 if case == 'c2n' else C.node2Center(t1)
-        Xmpi._setInterpData(t1, tc1, order=order, nature=1, penalty=1, extrap=1, loc=loc, storage='inverse', sameBase=1,
+        Xmpi._setInterpData(t1, tc1, order=order, nature=1, penalty=1, extrap=1, loc=loc, storage='inverse', sameBase=1, itype='chimera', verbose=0,
                             comm=None, zoneOrder=zoneOrder, backend=backend, ctx=ctx)
         if mode == 'nccl':
             s1 = Xmpi.TransferSession(t1, tc1, VARS, comm=None, ctx=ctx)
@@ -174,7 +174,7 @@ def main():
             t2 = make()
             tc2 = t2 if case == 'c2n' else C.node2Center(t2)
             ob = OracleBackend()
-            Xmpi._setInterpData(t2, tc2, order=order, nature=1, penalty=1, extrap=1, loc=loc, storage='inverse',
+            Xmpi._setInterpData(t2, tc2, order=order, nature=1, penalty=1, extrap=1, loc=loc, storage='inverse', itype='chimera', verbose=0,
                                 sameBase=1, comm=None, zoneOrder=zoneOrder, backend=ob)
             if case != 'c2n':
                 Xmpi._setInterpTransfers(t2, tc2, variables=VARS, comm=None, backend=ob)

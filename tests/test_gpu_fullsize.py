@@ -216,7 +216,8 @@ def test_c4_share_tree_level_bit_exact_vs_reference(ctx):
     import time
     import cassiopee_b200.Connector.Mpi as Xmpi
     from tests.backends import OracleBackend
-    kw = dict(order=2, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse', sameBase=1, comm=None, verbose=0)
+    kw = dict(order=2, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse', sameBase=1, comm=None, verbose=0,
+              itype='chimera')
     t, tc, names = _c4_share()
     t0 = time.perf_counter()
     Xmpi._setInterpData(t, tc, zoneOrder=names, ctx=ctx, **kw)
@@ -327,6 +328,7 @@ def test_c4_cluster_fullsize_properties(ctx):
     for z in Internal.getZones(tc):         # node2Center shares the centre arrays: give the donor tree its own F
         C._initVars(z, 'F', np.array(C.getFieldArray(z, 'F'), order='F', copy=True))
     Xmpi._setInterpData(t, tc, order=2, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse', sameBase=1, comm=None,
+                        itype='chimera',
                         zoneOrder=[b['name'] for b in blocks], ctx=ctx, verbose=0)
     nrcv = 0
     orphans = {}

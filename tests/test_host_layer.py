@@ -406,12 +406,24 @@ def test_distributed_entry_same_base_semantics():
         return t, C.node2Center(t)
     for two_bases, sameBase, expect in ((False, 0, False), (False, 1, True), (True, 0, True), (True, 1, True)):
         t, tc = trees(two_bases)
-        Xmpi._setInterpData(t, tc, order=2, nature=1, loc='centers', storage='inverse', sameBase=sameBase,
+        Xmpi._setInterpData(t, tc, order=2, nature=1, loc='centers', storage='inverse', sameBase=sameBase, itype='chimera', verbose=0,
                             comm=None, backend=OracleBackend())
         zdA = [z for z in Internal.getZones(tc) if z[0] == 'A'][0]
         assert (Internal.getNodeFromName1(zdA, 'ID_B') is not None) == expect, (two_bases, sameBase)
+    # cartesian=True only names a transport of the reference's Cmpi._addXZones: accepted, same result
+    t, tc = trees(True)
+    Xmpi._setInterpData(t, tc, order=2, nature=1, loc='centers', storage='inverse', sameBase=1, cartesian=True, itype='chimera',
+                        verbose=0, comm=None, backend=OracleBackend())
+    assert Internal.getNodeFromName1([z for z in Internal.getZones(tc) if z[0] == 'A'][0], 'ID_B') is not None
+    # the reference's defaults (storage='direct', itype='abutting'): nothing to do without match connectivity, and the
+    # combinations without a device path say so
+    t, tc = trees(True)
+    assert Xmpi._setInterpData(t, tc, comm=None, backend=OracleBackend()) is None
+    assert Internal.getNodeFromName1([z for z in Internal.getZones(tc) if z[0] == 'A'][0], 'ID_B') is None
     with pytest.raises(NotImplementedError):
-        Xmpi._setInterpData(t, tc, loc='centers', storage='inverse', cartesian=True, comm=None, backend=OracleBackend())
+        Xmpi._setInterpData(t, tc, loc='centers', itype='chimera', comm=None, backend=OracleBackend())      # storage='direct'
+    with pytest.raises(NotImplementedError):
+        Xmpi._setInterpData(t, tc, loc='centers', storage='inverse', itype='chimeraOld', comm=None, backend=OracleBackend())
 
 
 def test_create_interp_region_node_order_and_concatenation():
@@ -567,7 +579,7 @@ def test_cartesian_base_zones_are_interpcart_donors():
     be = Recording()
     t, tc = build()
     Xmpi._setInterpData(t, tc, order=2, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse', sameBase=1,
-                        cartesian=True, comm=None, backend=be)
+                        cartesian=True, itype='chimera', verbose=0, comm=None, backend=be)
     assert be.types == {(10, 10, 10): 0, (9, 9, 9): 1, (8, 8, 8): 1}
     t2, tc2 = build()
     X._setInterpDataChimera(t2, tc2, order=2, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse', verbose=0,
