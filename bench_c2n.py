@@ -76,7 +76,7 @@ def run_c2n(args):
         barrier()
         t0 = time.perf_counter()
         Xmpi._setInterpData(t, t, order=2, nature=1, penalty=1, extrap=1, loc='nodes', storage='inverse', sameBase=1,
-                            itype='chimera', verbose=0,
+                            itype='chimera',
                             comm=comm, zoneOrder=zoneOrder, ctx=ctx, verbose=0)
         barrier()
         sid_calls.append(time.perf_counter() - t0)

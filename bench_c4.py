@@ -158,7 +158,7 @@ def measure_c4(args, ctx, comm, ngpus, rank, world):
         barrier()
         t0 = time.perf_counter()
         Xmpi._setInterpData(tl, tcl, order=2, nature=1, penalty=1, extrap=1, loc='centers', storage='inverse', sameBase=1,
-                            itype='chimera', verbose=0,
+                            itype='chimera',
                             comm=comm, zoneOrder=zoneOrder, ctx=ctx, verbose=0)
         barrier()
         sid_calls.append(time.perf_counter() - t0)
