@@ -40,3 +40,17 @@ def test_no_device_fails_loudly():
         pytest.skip("a CUDA device is present")
     with pytest.raises(Exception):
         _lib.Context(0)
+
+
+def test_entry_scripts_compile():
+    """bench.py and its legs, __graft_entry__.py, the workers and the tools byte-compile (a repeated keyword argument is
+    a SyntaxError at compile time that neither an import of the package nor the CPU tests would show)."""
+    import glob
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, "bench*.py")) + [os.path.join(root, "__graft_entry__.py")] + \
+        glob.glob(os.path.join(root, "tests", "*.py")) + glob.glob(os.path.join(root, "tools", "*.py")) + \
+        glob.glob(os.path.join(root, "cassiopee_b200", "**", "*.py"), recursive=True)
+    assert len(files) > 20
+    for f in files:
+        py_compile.compile(f, doraise=True)
